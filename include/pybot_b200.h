@@ -1,0 +1,214 @@
+/*
+ * pybot_b200.h - C-ABI of libpybot_b200.so: the B200 (sm_100a) implementation of
+ * the data-parallel geometry-and-matching hot path of spillai/pybot.
+ *
+ * The reference has no FFI for this path: its "operator API" is the Python
+ * method surface, which bottoms out in numpy BLAS and three OpenCV entry
+ * points.  Each entry point below names the reference site (file:line under
+ * /root/reference) whose arithmetic it replaces; pybot_b200/_ffi.py is the
+ * ctypes binding and INTEGRATION.md shows the stub a pybot maintainer adds.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer documented "device" must be
+ *    a CUDA device pointer valid in the calling thread's current context;
+ *    "host" pointers are read before the call returns.
+ *  - all launches are asynchronous on `stream` (a cudaStream_t / CUstream
+ *    handle cast to void*; NULL = legacy default stream).
+ *  - the library never allocates or frees device memory and keeps no pointers
+ *    after a call returns; all outputs and scratch are caller-allocated.
+ *  - every function returns PBK_OK (0) or a negative pbk_status; the message
+ *    of the last failure on the calling thread is pbk_last_error_string().
+ *  - device pointers must be 16-byte aligned (PBK_EALIGN otherwise).
+ *  - there is no CPU fallback: without a CUDA device every compute entry point
+ *    returns PBK_ECUDA.
+ */
+#ifndef PYBOT_B200_H_
+#define PYBOT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBK_VERSION 100
+
+#if defined(__GNUC__)
+#define PBK_API __attribute__((visibility("default")))
+#else
+#define PBK_API
+#endif
+
+typedef enum pbk_status {
+  PBK_OK = 0,
+  PBK_EINVAL = -1,       /* bad argument (size, null pointer, enum)         */
+  PBK_ECUDA = -2,        /* CUDA runtime error; see pbk_last_error_string   */
+  PBK_EALIGN = -3,       /* device pointer not 16-byte aligned              */
+  PBK_EUNSUPPORTED = -4  /* valid in the reference but not implemented here */
+} pbk_status;
+
+typedef enum pbk_dtype {
+  PBK_U8 = 0, PBK_S16 = 1, PBK_S32 = 2, PBK_F32 = 3, PBK_F64 = 4
+} pbk_dtype;
+
+typedef void* pbk_stream_t;
+
+/* ---------------------------------------------------------------- runtime */
+PBK_API int pbk_version(void);
+PBK_API const char* pbk_last_error_string(void);
+/* props[0]=SM count, [1]=cc major, [2]=cc minor, [3]=max smem/block optin,
+ * [4]=L2 bytes, [5]=SM clock kHz, [6]=memory clock kHz, [7]=bus width bits */
+PBK_API int pbk_device_props(int device, int64_t props[8]);
+
+/* ------------------------------------------------- disparity -> XYZ (a6,a7)
+ * Replaces cv2.reprojectImageTo3D(disp, self.Q) in StereoCamera.reconstruct,
+ * pybot/vision/camera_utils.py:964-969, and reconstruct_with_texture :982-990
+ * (including its two np.copy(...[::s, ::s]).reshape(-1,3) passes :988-989).
+ *
+ * disp   device, (batch, H, W) contiguous, dtype in {U8,S16,S32,F32}
+ *        (float64 is rejected like OpenCV rejects it: PBK_EUNSUPPORTED)
+ * Q      host, 16 floats row-major (StereoCamera.Q is float32, :893)
+ * xyz    device, (batch, Hs, Ws, 3) float32, Hs=ceil(H/sample), Ws=ceil(W/sample)
+ * bgr    device or NULL, (batch, H, W, 3) uint8; bgr_out (batch, Hs, Ws, 3)
+ * Per pixel, bit-exact with OpenCV 4.13: h = Q*[x,y,d,1] in fp64 without FMA,
+ * out = float( double(float(h_i)) * (1.0/h_3) ).
+ */
+PBK_API int pbk_reproject_disp(const void* disp, int disp_dtype, int batch, int H, int W,
+                       const float* Q, int sample, float* xyz,
+                       const uint8_t* bgr, uint8_t* bgr_out,
+                       pbk_stream_t stream);
+
+/* StereoCamera.reconstruct_sparse, camera_utils.py:971-980: float64
+ * (Q * [x,y,d,1])[:3] / W per row of xyd (N,3) float64 -> out (N,3) float64. */
+PBK_API int pbk_reproject_sparse(const double* xyd, int64_t n, const float* Q,
+                         double* out, pbk_stream_t stream);
+
+/* ---------------------------------------- SE(3)/Sim(3) point transform (a1,a3,a5)
+ * Replaces np.hstack + np.dot(self.matrix, X) in RigidTransform.__mul__,
+ * pybot/geometry/rigid_transform.py:139-141 (and CameraExtrinsic.c2w/w2c,
+ * camera_utils.py:585-595).  Y = s*R*X + t (s = 1 for SE(3); Sim(3) semantics
+ * per SURVEY.md A.6).
+ *
+ * X      device, (n,3) AoS, in_dtype in {F32,F64}
+ * Rt     host, 12 doubles: R row-major (9) then t (3); scale host double
+ * Y      device, (n,3) AoS, out_dtype in {F32,F64} (reference returns F64)
+ */
+PBK_API int pbk_transform_points(const void* X, int in_dtype, int64_t n,
+                         const double* Rt, double scale,
+                         void* Y, int out_dtype, pbk_stream_t stream);
+
+/* ------------------------------------------------------ Camera.project (a4,a5)
+ * Replaces cv2.projectPoints + depth_from_projection + the depth / bounds
+ * masks + the x[valid] compaction of Camera.project,
+ * pybot/vision/camera_utils.py:687-734, in one pass.
+ */
+typedef struct pbk_project_params {
+  double R[9];        /* rotation used for the pixel (cv2.Rodrigues round trip) */
+  double t[3];
+  double Rz[3];       /* third row of the rotation used for the depth          */
+  double tz;          /*   (extrinsics round trip, camera_utils.py:683-685)     */
+  double fx, fy, cx, cy;
+  double k[8];        /* k1 k2 p1 p2 k3 k4 k5 k6 ; all zero -> pinhole only     */
+  double min_depth;
+  int32_t width, height;
+  int32_t check_depth;   /* valid &= depth >= min_depth        (:708-710)      */
+  int32_t check_bounds;  /* valid &= 0<=u<W && 0<=v<H          (:714-725)      */
+  int32_t has_distortion;
+  int32_t compact;       /* 1: uv/depth outputs are x[valid] order-preserving  */
+} pbk_project_params;
+
+/* X        device (n,3) AoS, in_dtype in {F32,F64}
+ * uv       device (n,2) same dtype as X (cv2 semantics), compacted if compact
+ * depth    device (n,) float64 or NULL
+ * valid    device (n,) uint8 or NULL (never compacted)
+ * count    device int64[1] or NULL: number of valid points (needed if compact)
+ * scratch  device, >= pbk_project_scratch_bytes(n) bytes, only if compact
+ */
+PBK_API size_t pbk_project_scratch_bytes(int64_t n);
+PBK_API int pbk_project_points(const void* X, int in_dtype, int64_t n,
+                       const pbk_project_params* params,
+                       void* uv, double* depth, uint8_t* valid,
+                       int64_t* count, void* scratch, pbk_stream_t stream);
+
+/* ------------------------------------------------------- Hamming kNN (a9)
+ * Replaces cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, k=2) over a collection
+ * (no call site in the reference: SURVEY.md 0.3; semantics pinned against
+ * OpenCV 4.13).  256-bit descriptors, 32 bytes per row.
+ *
+ * Result keys are (distance << 32) | global_train_row, so an unsigned 64-bit
+ * min reproduces BFMatcher's lowest-train-index tie-break across tiles,
+ * splits and GPUs.  PBK_KEY_NONE marks "fewer than k neighbours".
+ */
+#define PBK_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+
+/* number of train splits the kernel will use for (nq, nt) on this device, and
+ * the scratch it needs: partial keys (nq, splits, 2) uint64                    */
+PBK_API int pbk_hamming_plan(int64_t nq, int64_t nt, int* splits, size_t* scratch_bytes);
+
+/* q (nq,32) u8 device; t (nt,32) u8 device; train_base = global row index of
+ * t[0] (database shard offset); keys (nq,2) uint64 device out;
+ * scratch from pbk_hamming_plan.                                              */
+PBK_API int pbk_hamming_knn2(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt,
+                     uint64_t train_base, uint64_t* keys, void* scratch,
+                     pbk_stream_t stream);
+
+/* merge `parts` partial results laid out (parts, nq, 2) -> keys (nq,2): the
+ * step after an all-gather of per-shard keys.                                 */
+PBK_API int pbk_hamming_merge_top2(const uint64_t* partial, int parts, int64_t nq,
+                           uint64_t* keys, pbk_stream_t stream);
+
+/* rows[i] = t[(keys[i,0] & 0xffffffff) - train_base] if that row lies in
+ * [train_base, train_base+nt), else 32 zero bytes; rows (nq,32) u8.           */
+PBK_API int pbk_hamming_gather_best(const uint8_t* t, int64_t nt, uint64_t train_base,
+                            const uint64_t* keys, int64_t nq, uint8_t* rows,
+                            pbk_stream_t stream);
+
+/* Lowe ratio + mutual check.  rev_keys (nq,2): result of pbk_hamming_knn2 with
+ * the gathered best rows as queries and q as train (only [:,0] is used).
+ * ratio_ok[i]  = has 2 neighbours && (double)d1 < ratio*(double)d2
+ * mutual_ok[i] = has 1 neighbour  && (rev_keys[i,0] & 0xffffffff) == i
+ * valid = ratio_ok & mutual_ok ; idx (nq,2) int64 (-1 = none), dist (nq,2) int32 */
+PBK_API int pbk_hamming_ratio_mutual(const uint64_t* keys, const uint64_t* rev_keys,
+                             int64_t nq, double ratio, int64_t* idx,
+                             int32_t* dist, uint8_t* ratio_ok,
+                             uint8_t* mutual_ok, uint8_t* valid,
+                             pbk_stream_t stream);
+
+/* popc-pipe peak probe (measurement only): ctas x 256 threads run `iters`
+ * rounds of mode 0: independent POPC chains; 1: POPC + one LOP3 each;
+ * 2 / 3: the matcher's inner instruction mix (8 / 4 POPC per pair) on
+ * registers.  *popc_per_launch receives the number of 32-bit POPC executed
+ * (modes 2/3: 16*iters pairs per thread).  sink: device uint32[8 + ctas*256],
+ * first 8 words are read as inputs.                                           */
+PBK_API int pbk_popc_peak_probe(int mode, int ctas, int iters, uint32_t* sink,
+                        double* popc_per_launch, pbk_stream_t stream);
+
+/* ------------------------------------- BA residual + Jacobians (a10)
+ * Replaces cv2.projectPoints(X, rvec, tvec, K, D=0) -> (x, J) minus the
+ * observation: the Jacobian Camera.project computes and discards at
+ * pybot/vision/camera_utils.py:697 (columns 0:6), plus J_pt = J_t * R.
+ *
+ * ba_camera_precompute: rvec (C,3) f32, tvec (C,3) f32 device ->
+ *   cam_blocks (C, PBK_BA_CAM_DOUBLES) f64 device: R(9) t(3) dR/dr(27).
+ * ba_residual_jacobian: obs (O,4) {int32 cam, int32 pt, f32 u, f32 v} device,
+ *   points (P,3) f32 device -> r (O,2) f32, J_cam (O,2,6) f32, J_pt (O,2,3)
+ *   f32 (any may be NULL), cost_partials (pbk_ba_cost_slots(O),) f64 device,
+ *   cost (1,) f64 device = sum ||r||^2 (deterministic two-stage sum).
+ */
+#define PBK_BA_CAM_DOUBLES 40
+PBK_API int pbk_ba_camera_precompute(const float* rvec, const float* tvec, int n_cams,
+                             double* cam_blocks, pbk_stream_t stream);
+PBK_API int pbk_ba_cost_slots(int64_t n_obs);
+PBK_API int pbk_ba_residual_jacobian(const void* obs, int64_t n_obs,
+                             const float* points, int64_t n_points,
+                             const double* cam_blocks, int n_cams,
+                             double fx, double fy, double cx, double cy,
+                             float* r, float* J_cam, float* J_pt,
+                             double* cost_partials, double* cost,
+                             pbk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYBOT_B200_H_ */

@@ -1,0 +1,30 @@
+"""ctypes wrapper of oracle/c/hamming_knn.c.  TEST INFRASTRUCTURE ONLY."""
+import ctypes
+
+import numpy as np
+
+from . import build as _build
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(_build.build())
+        _lib.pbo_hamming_knn2.restype = None
+        _lib.pbo_hamming_knn2.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                          ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    return _lib
+
+
+def hamming_knn2(q, t):
+    """(idx (nq,2) int64, dist (nq,2) int32) with BFMatcher tie semantics."""
+    q = np.ascontiguousarray(q, np.uint8)
+    t = np.ascontiguousarray(t, np.uint8)
+    assert q.ndim == 2 and q.shape[1] == 32 and t.ndim == 2 and t.shape[1] == 32
+    idx = np.empty((len(q), 2), np.int64)
+    dist = np.empty((len(q), 2), np.int32)
+    _load().pbo_hamming_knn2(q.ctypes.data, len(q), t.ctypes.data, len(t), idx.ctypes.data,
+                             dist.ctypes.data)
+    return idx, dist

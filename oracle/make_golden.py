@@ -1,0 +1,216 @@
+"""Regenerates tests/golden/*.npz by running the REAL reference (and the cv2
+calls a pybot user makes for matching / BA) on small seeded inputs.
+
+TEST INFRASTRUCTURE.  Needs /root/reference (authoring container only):
+
+    python -m oracle.make_golden
+
+The fixtures pin (a) the oracle port/model against the reference
+(tests/test_oracle_pinning.py, CPU) and (b) the CUDA path against the
+reference (tests/test_gpu_*.py) on the GPU box, where /root/reference does
+not exist.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "tests", "golden")
+
+from oracle import ref_loader  # noqa: E402
+from pybot_b200 import synthetic as syn  # noqa: E402
+
+
+def g1_reconstruct(ns):
+    """G1: KITTI-calibrated frame with specials, all accepted dtypes, texture."""
+    cam = ns.StereoCamera.from_calib_params(syn.KITTI_FX, syn.KITTI_FX, syn.KITTI_CX, syn.KITTI_CY,
+                                            baseline_px=syn.KITTI_BASELINE_PX, shape=(96, 317))
+    rng = np.random.default_rng(101)
+    disp = syn.disparity_image(rng, (96, 317), syn.KITTI_FX, syn.KITTI_BASELINE)
+    im = rng.integers(0, 256, (96, 317, 3), dtype=np.uint8)
+    out = dict(Q=cam.Q, baseline=cam.baseline, disp_f32=disp, im=im,
+               xyz_f32=cam.reconstruct(disp))
+    for name, dt in (("u8", np.uint8), ("s16", np.int16), ("s32", np.int32)):
+        d = np.clip(np.nan_to_num(disp, nan=0, posinf=0), -1, 250).astype(dt)
+        out["disp_" + name] = d
+        out["xyz_" + name] = cam.reconstruct(d)
+    for s in (1, 2, 3):
+        c, x = cam.reconstruct_with_texture(disp, im, sample=s)
+        out["tex%d_im" % s], out["tex%d_xyz" % s] = c, x
+    xyd = np.stack([rng.uniform(0, 317, 64), rng.uniform(0, 96, 64), rng.uniform(1, 90, 64)], 1)
+    out["sparse_xyd"] = xyd
+    out["sparse_xyz"] = cam.reconstruct_sparse(xyd)
+    np.savez_compressed(os.path.join(OUT, "g1_reconstruct.npz"), **out)
+
+
+def g1b_divcases():
+    """Pixels where float(n / W) != float(n * (1/W)): cv2 multiplies by the
+    reciprocal.  Found by random search; checked here."""
+    import cv2
+    q43 = np.float32(-1.0 / 0.5371657)
+    cases = [(2610, 15.590840339660645), (3549, 224.04904174804688),
+             (3470, 172.59080505371094), (3201, 189.9710235595703)]
+    Q = np.float32([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, q43, 0]])
+    disp = np.ones((2, 4096), np.float32)
+    for x, d in cases:
+        disp[0, x] = np.float32(d)
+    xyz = cv2.reprojectImageTo3D(disp, Q)
+    for x, d in cases:
+        W = float(q43) * float(np.float32(d))
+        assert np.float32(x / W) != np.float32(x * (1.0 / W))
+        assert xyz[0, x, 0] == np.float32(x * (1.0 / W))
+    np.savez_compressed(os.path.join(OUT, "reproject_divcases.npz"), Q=Q, disp=disp, xyz=xyz)
+
+
+def g2_transform_project(ns):
+    """G2: transform + project with z in {<0, 0, tiny}, border pixels, min_depth edge."""
+    rng = np.random.default_rng(102)
+    n = 4000
+    X = np.stack([rng.uniform(-40, 40, n), rng.uniform(-3, 3, n), rng.uniform(-5, 80, n)], 1)
+    X = X.astype(np.float32)
+    K = syn.kitti_K()
+    out = dict(K=K, X=X)
+    poses = {"c2": syn.C2_RPYXYZ, "ident": (0, 0, 0, 0, 0, 0), "big": (2.5, -1.2, 0.7, -3.0, 4.0, 9.0)}
+    for name, rp in poses.items():
+        p = ns.RigidTransform.from_rpyxyz(*rp)
+        out["pose_%s_xyzw" % name] = p.quat.q.copy()
+        out["pose_%s_tvec" % name] = p.tvec.copy()
+        out["mul_%s" % name] = p * X
+        out["mul64_%s" % name] = p * X.astype(np.float64)
+        inv = p.inverse()
+        out["inv_%s_xyzw" % name], out["inv_%s_tvec" % name] = inv.quat.q.copy(), inv.tvec.copy()
+        cam = ns.Camera.from_intrinsics_extrinsics(
+            ns.CameraIntrinsic(K, shape=syn.KITTI_SHAPE), ns.CameraExtrinsic.from_rigid_transform(p))
+        out["cam_%s_xyzw" % name], out["cam_%s_tvec" % name] = cam.quat.q.copy(), cam.tvec.copy()
+        out["proj_%s" % name] = cam.project(X)
+        x, d, v = cam.project(X, check_bounds=True, check_depth=True, return_depth=True,
+                              return_valid=True)
+        out["projv_%s_x" % name], out["projv_%s_d" % name], out["projv_%s_v" % name] = x, d, v
+        x, v = cam.project(X, check_depth=True, return_valid=True, min_depth=2.0)
+        out["projd_%s_x" % name], out["projd_%s_v" % name] = x, v
+        out["proj64_%s" % name] = cam.project(X.astype(np.float64))
+    # identity camera, planted edge cases
+    cam = ns.Camera.from_intrinsics(ns.CameraIntrinsic(K, shape=syn.KITTI_SHAPE))
+    W, H = 1241.0, 376.0
+    fx, cx, cy = syn.KITTI_FX, syn.KITTI_CX, syn.KITTI_CY
+    edge = np.float32([
+        [1, 1, 0], [0, 0, 0], [1, 2, 1e-12], [1, 1, -4], [0, 0, 0.1], [0, 0, 0.099999994],
+        [(W - cx) / fx * 10, 0, 10], [(W - 1e-3 - cx) / fx * 10, 0, 10], [(0 - cx) / fx * 10, 0, 10],
+        [0, (H - cy) / fx * 10, 10], [0, (0 - cy) / fx * 10, 10], [np.nan, 0, 5], [np.inf, 1, 5],
+        [3e38, 3e38, 1e-30]])
+    out["edge_X"] = edge
+    with np.errstate(all="ignore"):
+        out["edge_proj"] = cam.project(edge)
+        x, d, v = cam.project(edge, check_bounds=True, check_depth=True, return_depth=True,
+                              return_valid=True)
+    out["edge_x"], out["edge_d"], out["edge_v"] = x, d, v
+    # distortion
+    Dcam = ns.Camera.from_intrinsics_extrinsics(
+        ns.CameraIntrinsic.from_calib_params(fx, fx, cx, cy, k1=-0.3, k2=0.1, k3=0.05, p1=0.001,
+                                             p2=-0.002, shape=syn.KITTI_SHAPE),
+        ns.CameraExtrinsic.from_rigid_transform(ns.RigidTransform.from_rpyxyz(*syn.C2_RPYXYZ)))
+    out["dist_D"] = Dcam.D
+    out["dist_proj"] = Dcam.project(X)
+    np.savez_compressed(os.path.join(OUT, "g2_transform_project.npz"), **out)
+
+
+def g3_matching():
+    """G3/G4: tie-heavy descriptors, duplicates, Nt<k, multi-keyframe collection."""
+    import cv2
+    out = {}
+    q, t = syn.low_entropy_pair(seed=7, nq=300, nt=450)
+    t[17] = t[3]
+    t[200] = q[5]
+    t[9] = q[5]
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+    res = bf.knnMatch(q, t, k=2)
+    out["le_q"], out["le_t"] = q, t
+    out["le_idx"] = np.array([[m.trainIdx for m in r] for r in res], np.int32)
+    out["le_dist"] = np.array([[int(m.distance) for m in r] for r in res], np.int32)
+    cc = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(q, t)
+    out["le_cross"] = np.array([[m.queryIdx, m.trainIdx] for m in cc], np.int32)
+    # Nt = 1 (< k)
+    r1 = bf.knnMatch(q[:4], t[:1], k=2)
+    out["nt1_len"] = np.array([len(r) for r in r1], np.int32)
+    # collection with a duplicate across keyframes
+    q2, t2 = syn.orb_pair(seed=33, nq=200, nt=600)
+    kfs = [t2[:150].copy(), t2[150:400].copy(), t2[400:].copy()]
+    kfs[1][0] = kfs[0][5]
+    kfs[0][5] = q2[10]
+    kfs[1][0] = q2[10]
+    bf2 = cv2.BFMatcher(cv2.NORM_HAMMING)
+    bf2.add(kfs)
+    res = bf2.knnMatch(q2, k=2)
+    out["kf_q"] = q2
+    out["kf_0"], out["kf_1"], out["kf_2"] = kfs
+    out["kf_img"] = np.array([[m.imgIdx for m in r] for r in res], np.int32)
+    out["kf_idx"] = np.array([[m.trainIdx for m in r] for r in res], np.int32)
+    out["kf_dist"] = np.array([[int(m.distance) for m in r] for r in res], np.int32)
+    np.savez_compressed(os.path.join(OUT, "g3_matching.npz"), **out)
+
+
+def g5_ba():
+    """G5: cv2.projectPoints Jacobians at |rvec| in {~1, 1e-9, 0, pi-1e-3}."""
+    import cv2
+    rng = np.random.default_rng(105)
+    K = syn.kitti_K()
+    n = 300
+    X = np.stack([rng.uniform(-10, 10, n), rng.uniform(-3, 3, n), rng.uniform(4, 60, n)], 1)
+    X = X.astype(np.float32)
+    ax = np.array([0.3, -0.5, 0.8])
+    ax /= np.linalg.norm(ax)
+    rvecs = np.float32([[0.3, -0.2, 0.5], [1e-9, 2e-9, -1e-9], [0, 0, 0], ax * (np.pi - 1e-3),
+                        [0.01, -1.2, 0.02]])
+    tvecs = np.float32([[0.5, -0.1, 1.2], [0, 0, 0], [1, 2, 3], [0.2, 0.1, 70.0], [-3, 0.2, 5]])
+    xs, Js = [], []
+    for rv, tv in zip(rvecs, tvecs):
+        x, J = cv2.projectPoints(X.astype(np.float64), rv.astype(np.float64), tv.astype(np.float64),
+                                 K, np.zeros(5))
+        xs.append(x.reshape(-1, 2))
+        Js.append(J.reshape(n, 2, 15)[:, :, :6])
+    np.savez_compressed(os.path.join(OUT, "g5_ba.npz"), K=K, X=X, rvecs=rvecs, tvecs=tvecs,
+                        x=np.stack(xs), Jcam=np.stack(Js))
+
+
+def g0_host_algebra(ns):
+    """Pose algebra known answers from the reference itself (host-side glue)."""
+    rng = np.random.default_rng(100)
+    rp = rng.uniform(-3, 3, (12, 6))
+    mats, invs, comps, vecs, rts = [], [], [], [], []
+    prev = ns.RigidTransform.identity()
+    for a in rp:
+        p = ns.RigidTransform.from_rpyxyz(*a)
+        mats.append(p.matrix)
+        invs.append(p.inverse().matrix)
+        comps.append((prev * p).matrix)
+        vecs.append(p.to_vector())
+        rts.append(ns.RigidTransform.from_Rt(*p.to_Rt()).matrix)
+        prev = p
+    s = ns.Sim3(xyzw=ns.RigidTransform.from_rpyxyz(*rp[0]).xyzw, tvec=rp[0, 3:], scale=2.5)
+    np.savez_compressed(
+        os.path.join(OUT, "g0_host_algebra.npz"), rpyxyz=rp, matrix=np.stack(mats),
+        inverse=np.stack(invs), compose=np.stack(comps), vector=np.stack(vecs),
+        from_Rt=np.stack(rts), sim3_matrix=s.to_matrix(),
+        sim3_oplus=s.oplus(ns.RigidTransform.from_rpyxyz(*rp[1])).matrix,
+        axes_q=np.stack([ns.tf.quaternion_from_euler(0.3, -0.7, 1.1, axes=a)
+                         for a in sorted(ns.tf._AXES2TUPLE)]),
+        axes_names=np.array(sorted(ns.tf._AXES2TUPLE)))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_loader.load()
+    g0_host_algebra(ns)
+    g1_reconstruct(ns)
+    g1b_divcases()
+    g2_transform_project(ns)
+    g3_matching()
+    g5_ba()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,488 @@
+// Brute-force Hamming kNN (k=2) over 256-bit ORB descriptors with
+// cv2.BFMatcher semantics.
+//
+// Replaces cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, k=2) + Lowe ratio +
+// mutual check.  The reference has no call site for it; the
+// semantics are pinned against OpenCV 4.13: per query the two smallest
+// distances, ties broken by the LOWEST train index (imgIdx, trainIdx order
+// for collections == global row order).
+//
+// Design (integer pipe; tensor cores are not used - there is no b1 tcgen05
+// kind):
+//  * grid = (query tiles of 512) x (train splits).  A CTA of 128 threads keeps
+//    4 queries per thread in registers (8 x u32 each).
+//  * the CTA's train split streams through a 4-stage shared-memory ring of
+//    256-row (8 KB) tiles filled by TMA bulk copies (cp.async.bulk ->
+//    UBLKCP) that complete on mbarriers; the query tile is staged the same way.
+//  * every lane reads the same train row (broadcast LDS.128 x2) and scores
+//    it against its 4 queries: XOR (LOP3) + POPC + integer adds.
+//    VARIANT 1 compresses the eight 32-bit words with carry-save adders
+//    (LOP3 full adders) so only 4 POPC per pair are issued instead of 8 -
+//    the popc pipe is the narrow one (16 lanes/clk/SM vs 64 for LOP3).
+//  * top-2 selection is a 3-instruction min/max network on a packed 32-bit key
+//    (distance << 23 | local row): rows are scanned in ascending order and the
+//    key order is lexicographic, so ties resolve to the lowest train index.
+//  * each CTA emits (distance << 32 | global row) u64 keys per query; a merge
+//    kernel reduces the splits (and, multi-GPU, the all-gathered shards) with
+//    the same unsigned min - bit-identical to a single ascending scan.
+#include "pbk_common.cuh"
+
+namespace pbk {
+
+constexpr int kHThreads = 128;
+constexpr int kRQ = 4;                          // queries per thread
+constexpr int kQTile = kHThreads * kRQ;         // 512 queries per CTA
+constexpr int kTR = 256;                        // train rows per stage
+constexpr int kStages = 4;
+constexpr int kStageBytes = kTR * 32;
+constexpr int kKeyShift = 23;                   // local row index < 2^23
+constexpr uint32_t kLocalNone = 0xFFFFFFFFu;
+constexpr long long kMaxSplitRows = 1ll << kKeyShift;
+
+struct HammingParams {
+  const uint8_t* q;
+  const uint8_t* t;
+  unsigned long long* partial;   // (splits, nq, 2)
+  long long nq, nt;
+  long long rows_per_split;      // multiple of kTR
+  unsigned long long train_base;
+  int splits;
+};
+
+// ------------------------------------------------------------ TMA / mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completing `bytes` on `bar`.
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ------------------------------------------------------------------ scoring
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
+// Hamming distance of two 256-bit rows held as 8 words each.
+template <int VARIANT>
+__device__ __forceinline__ uint32_t hamming256(const uint32_t* q, const uint4& a, const uint4& b) {
+  const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
+  const uint32_t x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
+  if (VARIANT == 0) {
+    return __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3) + __popc(x4) + __popc(x5) + __popc(x6) +
+           __popc(x7);
+  } else {
+    // carry-save reduction: ones = sc, x7 ; twos = sd ; fours = cd
+    const uint32_t sa = xor3(x0, x1, x2), ca = maj3(x0, x1, x2);
+    const uint32_t sb = xor3(x3, x4, x5), cb = maj3(x3, x4, x5);
+    const uint32_t sc = xor3(sa, sb, x6), cc = maj3(sa, sb, x6);
+    const uint32_t sd = xor3(ca, cb, cc), cd = maj3(ca, cb, cc);
+    return (__popc(sc) + __popc(x7)) + 2u * __popc(sd) + 4u * __popc(cd);
+  }
+}
+
+__device__ __forceinline__ void top2_insert(uint32_t& k1, uint32_t& k2, uint32_t key) {
+  const uint32_t mx = max(k1, key);
+  k1 = min(k1, key);
+  k2 = min(k2, mx);
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kHThreads, 4)
+hamming_knn2_kernel(const __grid_constant__ HammingParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* ring = smem;                                   // kStages * kStageBytes
+  uint8_t* qstage = smem + kStages * kStageBytes;         // kQTile * 32
+  uint64_t* full = reinterpret_cast<uint64_t*>(qstage + kQTile * 32);   // kStages + 1 barriers
+
+  const int tid = threadIdx.x;
+  const long long q0 = (long long)blockIdx.x * kQTile;
+  const int split = blockIdx.y;
+  const long long row0 = (long long)split * P.rows_per_split;
+  long long rows = P.nt - row0;
+  if (rows > P.rows_per_split) rows = P.rows_per_split;
+  if (rows < 0) rows = 0;
+  const int nstage_total = (int)((rows + kTR - 1) / kTR);
+  const int nq_tile = (int)((P.nq - q0) < kQTile ? (P.nq - q0) : kQTile);
+
+  if (tid == 0) {
+    for (int s = 0; s <= kStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const uint8_t* tsplit = P.t + row0 * 32;
+  auto issue = [&](int it) {
+    const int s = it % kStages;
+    const long long r = (long long)it * kTR;
+    const uint32_t bytes = (uint32_t)(((rows - r) < kTR ? (rows - r) : kTR) * 32);
+    mbar_expect_tx(&full[s], bytes);
+    tma_load_1d(ring + s * kStageBytes, tsplit + r * 32, bytes, &full[s]);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(&full[kStages], (uint32_t)nq_tile * 32u);
+    tma_load_1d(qstage, P.q + q0 * 32, (uint32_t)nq_tile * 32u, &full[kStages]);
+    for (int it = 0; it < kStages - 1 && it < nstage_total; ++it) issue(it);
+  }
+
+  // this thread's queries: q0 + r*128 + tid
+  uint32_t qr[kRQ][8];
+  mbar_wait(&full[kStages], 0);
+#pragma unroll
+  for (int r = 0; r < kRQ; ++r) {
+    const uint4* src = reinterpret_cast<const uint4*>(qstage + (r * kHThreads + tid) * 32);
+    const uint4 a = src[0], b = src[1];
+    qr[r][0] = a.x; qr[r][1] = a.y; qr[r][2] = a.z; qr[r][3] = a.w;
+    qr[r][4] = b.x; qr[r][5] = b.y; qr[r][6] = b.z; qr[r][7] = b.w;
+  }
+  uint32_t k1[kRQ], k2[kRQ];
+#pragma unroll
+  for (int r = 0; r < kRQ; ++r) k1[r] = k2[r] = kLocalNone;
+
+  for (int it = 0; it < nstage_total; ++it) {
+    const int s = it % kStages;
+    // refill the slot freed in the previous iteration (all threads passed the
+    // __syncthreads at its end)
+    if (tid == 0 && it + kStages - 1 < nstage_total) issue(it + kStages - 1);
+    mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
+    const long long r_base = (long long)it * kTR;
+    const int nrows = (int)((rows - r_base) < kTR ? (rows - r_base) : kTR);
+    const uint4* tile = reinterpret_cast<const uint4*>(ring + s * kStageBytes);
+    uint32_t rowkey = (uint32_t)r_base;
+    if (nrows == kTR) {
+#pragma unroll 4
+      for (int j = 0; j < kTR; ++j) {
+        const uint4 a = tile[2 * j], b = tile[2 * j + 1];
+#pragma unroll
+        for (int r = 0; r < kRQ; ++r) {
+          const uint32_t d = hamming256<VARIANT>(qr[r], a, b);
+          top2_insert(k1[r], k2[r], d * (1u << kKeyShift) + rowkey);
+        }
+        ++rowkey;
+      }
+    } else {
+      for (int j = 0; j < nrows; ++j) {
+        const uint4 a = tile[2 * j], b = tile[2 * j + 1];
+#pragma unroll
+        for (int r = 0; r < kRQ; ++r) {
+          const uint32_t d = hamming256<VARIANT>(qr[r], a, b);
+          top2_insert(k1[r], k2[r], d * (1u << kKeyShift) + rowkey);
+        }
+        ++rowkey;
+      }
+    }
+    __syncthreads();   // everyone is done with slot s before it is refilled
+  }
+
+  // emit (distance << 32 | global row) keys
+  const unsigned long long gbase = P.train_base + (unsigned long long)row0;
+#pragma unroll
+  for (int r = 0; r < kRQ; ++r) {
+    const long long qi = q0 + r * kHThreads + tid;
+    if (qi < P.nq) {
+      unsigned long long o[2];
+      const uint32_t kk[2] = {k1[r], k2[r]};
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        o[c] = (kk[c] == kLocalNone)
+                   ? PBK_KEY_NONE
+                   : (((unsigned long long)(kk[c] >> kKeyShift) << 32) |
+                      (gbase + (kk[c] & ((1u << kKeyShift) - 1u))));
+      }
+      ulonglong2* dst = reinterpret_cast<ulonglong2*>(P.partial + ((long long)split * P.nq + qi) * 2);
+      *dst = make_ulonglong2(o[0], o[1]);
+    }
+  }
+}
+
+// partial (parts, nq, 2) -> keys (nq, 2): global top-2 by unsigned min.
+__global__ void __launch_bounds__(256)
+hamming_merge_kernel(const unsigned long long* __restrict__ partial, int parts, long long nq,
+                     unsigned long long* __restrict__ keys) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  unsigned long long b1 = PBK_KEY_NONE, b2 = PBK_KEY_NONE;
+  for (int p = 0; p < parts; ++p) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(partial + ((long long)p * nq + i) * 2);
+    unsigned long long mx = max(b1, v.x);
+    b1 = min(b1, v.x);
+    b2 = min(b2, mx);
+    mx = max(b1, v.y);
+    b1 = min(b1, v.y);
+    b2 = min(b2, mx);
+  }
+  *reinterpret_cast<ulonglong2*>(keys + i * 2) = make_ulonglong2(b1, b2);
+}
+
+__global__ void __launch_bounds__(256)
+hamming_gather_kernel(const uint8_t* __restrict__ t, long long nt, unsigned long long train_base,
+                      const unsigned long long* __restrict__ keys, long long nq,
+                      uint8_t* __restrict__ rows) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const unsigned long long k = keys[2 * i];
+  uint4 a = make_uint4(0, 0, 0, 0), b = a;
+  if (k != PBK_KEY_NONE) {
+    const unsigned long long g = k & 0xffffffffull;
+    if (g >= train_base && g - train_base < (unsigned long long)nt) {
+      const uint4* src = reinterpret_cast<const uint4*>(t + (g - train_base) * 32);
+      a = src[0];
+      b = src[1];
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(rows + i * 32);
+  dst[0] = a;
+  dst[1] = b;
+}
+
+__global__ void __launch_bounds__(256)
+hamming_ratio_mutual_kernel(const unsigned long long* __restrict__ keys,
+                            const unsigned long long* __restrict__ rev, long long nq, double ratio,
+                            long long* __restrict__ idx, int* __restrict__ dist,
+                            uint8_t* __restrict__ ratio_ok, uint8_t* __restrict__ mutual_ok,
+                            uint8_t* __restrict__ valid) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const unsigned long long a = keys[2 * i], b = keys[2 * i + 1];
+  const bool h1 = a != PBK_KEY_NONE, h2 = b != PBK_KEY_NONE;
+  const int d1 = h1 ? (int)(a >> 32) : -1, d2 = h2 ? (int)(b >> 32) : -1;
+  if (idx != nullptr) {
+    idx[2 * i] = h1 ? (long long)(a & 0xffffffffull) : -1;
+    idx[2 * i + 1] = h2 ? (long long)(b & 0xffffffffull) : -1;
+  }
+  if (dist != nullptr) {
+    dist[2 * i] = d1;
+    dist[2 * i + 1] = d2;
+  }
+  // Python: m.distance < ratio * n.distance on doubles holding exact integers
+  const bool r_ok = h2 && ((double)d1 < __dmul_rn(ratio, (double)d2));
+  bool m_ok = false;
+  if (h1 && rev != nullptr) {
+    const unsigned long long rk = rev[2 * i];
+    m_ok = rk != PBK_KEY_NONE && (long long)(rk & 0xffffffffull) == i;
+  }
+  if (ratio_ok != nullptr) ratio_ok[i] = r_ok;
+  if (mutual_ok != nullptr) mutual_ok[i] = m_ok;
+  if (valid != nullptr) valid[i] = r_ok && m_ok;
+}
+
+// ------------------------------------------------------- popc pipe probe
+// mode 0: pure POPC chains (8 independent per thread)
+// mode 1: POPC + one dependent LOP3 per POPC (checks POPC/ALU overlap)
+// mode 2: the matcher's VARIANT 0 inner mix (8 LOP3 + 8 POPC + adds) on registers
+// mode 3: the matcher's VARIANT 1 inner mix (16 LOP3 + 4 POPC + adds)
+template <int MODE>
+__global__ void __launch_bounds__(256) popc_probe_kernel(int iters, uint32_t* sink) {
+  uint32_t v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x;
+  if (MODE == 0) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __popc(v[i]);
+      }
+    }
+  } else if (MODE == 1) {
+    const uint32_t c = sink[0];
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __popc(v[i] ^ c);
+      }
+    }
+  } else {
+    uint32_t k1 = kLocalNone, k2 = kLocalNone;
+    uint4 a = make_uint4(sink[0], sink[1], sink[2], sink[3]);
+    uint4 b = make_uint4(sink[4], sink[5], sink[6], sink[7]);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const uint32_t d = hamming256<MODE == 2 ? 0 : 1>(v, a, b);
+        top2_insert(k1, k2, d * (1u << kKeyShift) + (uint32_t)(it * 16 + u));
+        a.x += 0x9e3779b9u;          // a new "train row" every round
+        b.w += 0x7f4a7c15u;
+      }
+    }
+    v[0] = k1 ^ k2 ^ a.x ^ b.w;
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc ^= v[i];
+  sink[8 + blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+static int g_variant = -1;
+static int hamming_variant() {
+  if (g_variant < 0) {
+    const char* e = getenv("PBK_HAMMING_VARIANT");
+    g_variant = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_variant;
+}
+
+static int plan(const DeviceInfo* di, long long nq, long long nt, int* splits, long long* rows_per_split) {
+  const long long qtiles = (nq + kQTile - 1) / kQTile;
+  const long long target = (long long)di->sm_count * 4;            // 4 CTAs (16 warps) per SM
+  long long s = qtiles > 0 ? (target + qtiles - 1) / qtiles : 1;
+  const long long max_by_rows = (nt + kTR - 1) / kTR;              // >= one stage per split
+  if (s > max_by_rows) s = max_by_rows;
+  if (s < 1) s = 1;
+  long long rps = (nt + s - 1) / s;
+  rps = ((rps + kTR - 1) / kTR) * kTR;
+  if (rps > kMaxSplitRows) rps = kMaxSplitRows;
+  if (rps < kTR) rps = kTR;
+  s = (nt + rps - 1) / rps;
+  if (s < 1) s = 1;
+  PBK_REQUIRE(s <= 65535, PBK_EINVAL, "train set too large for one call (%lld splits)", s);
+  *splits = (int)s;
+  *rows_per_split = rps;
+  return PBK_OK;
+}
+
+}  // namespace pbk
+
+extern "C" {
+
+int pbk_hamming_plan(int64_t nq, int64_t nt, int* splits, size_t* scratch_bytes) {
+  using namespace pbk;
+  PBK_REQUIRE(nq >= 0 && nt >= 0 && splits && scratch_bytes, PBK_EINVAL, "bad arguments");
+  const DeviceInfo* di;
+  int rc = current_device_info(&di);
+  if (rc) return rc;
+  long long rps;
+  rc = plan(di, nq, nt, splits, &rps);
+  if (rc) return rc;
+  *scratch_bytes = (size_t)(*splits) * (size_t)(nq > 0 ? nq : 1) * 16;
+  return PBK_OK;
+}
+
+int pbk_hamming_knn2(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, uint64_t train_base,
+                     uint64_t* keys, void* scratch, pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(nq >= 0 && nt >= 0, PBK_EINVAL, "negative size");
+  if (nq == 0) return PBK_OK;
+  PBK_REQUIRE(q != nullptr && keys != nullptr && scratch != nullptr, PBK_EINVAL, "NULL device pointer");
+  PBK_REQUIRE(nt == 0 || t != nullptr, PBK_EINVAL, "NULL train pointer");
+  PBK_REQUIRE(aligned16(q) && aligned16(t) && aligned16(keys) && aligned16(scratch), PBK_EALIGN,
+              "device pointers must be 16-byte aligned");
+  PBK_REQUIRE(train_base + (uint64_t)nt <= (1ull << 32), PBK_EINVAL,
+              "global train row index must fit 32 bits");
+  const DeviceInfo* di;
+  int rc = current_device_info(&di);
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  int splits;
+  long long rps;
+  rc = plan(di, nq, nt, &splits, &rps);
+  if (rc) return rc;
+  HammingParams P;
+  P.q = q; P.t = t; P.partial = static_cast<unsigned long long*>(scratch);
+  P.nq = nq; P.nt = nt; P.rows_per_split = rps; P.train_base = train_base; P.splits = splits;
+  const int smem = kStages * kStageBytes + kQTile * 32 + (kStages + 1) * 8;
+  const dim3 grid((unsigned)((nq + kQTile - 1) / kQTile), (unsigned)splits);
+  if (hamming_variant() == 0) {
+    PBK_CUDA(cudaFuncSetAttribute(hamming_knn2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    hamming_knn2_kernel<0><<<grid, kHThreads, smem, s>>>(P);
+  } else {
+    PBK_CUDA(cudaFuncSetAttribute(hamming_knn2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    hamming_knn2_kernel<1><<<grid, kHThreads, smem, s>>>(P);
+  }
+  PBK_CHECK_LAUNCH("hamming_knn2_kernel");
+  hamming_merge_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(P.partial, splits, nq,
+                                                                    reinterpret_cast<unsigned long long*>(keys));
+  PBK_CHECK_LAUNCH("hamming_merge_kernel");
+  return PBK_OK;
+}
+
+int pbk_hamming_merge_top2(const uint64_t* partial, int parts, int64_t nq, uint64_t* keys,
+                           pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(parts >= 1 && nq >= 0, PBK_EINVAL, "bad arguments");
+  if (nq == 0) return PBK_OK;
+  PBK_REQUIRE(partial != nullptr && keys != nullptr, PBK_EINVAL, "NULL device pointer");
+  PBK_REQUIRE(aligned16(partial) && aligned16(keys), PBK_EALIGN, "device pointers must be 16-byte aligned");
+  hamming_merge_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(partial), parts, nq,
+      reinterpret_cast<unsigned long long*>(keys));
+  PBK_CHECK_LAUNCH("hamming_merge_kernel");
+  return PBK_OK;
+}
+
+int pbk_hamming_gather_best(const uint8_t* t, int64_t nt, uint64_t train_base, const uint64_t* keys,
+                            int64_t nq, uint8_t* rows, pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(nt >= 0 && nq >= 0, PBK_EINVAL, "negative size");
+  if (nq == 0) return PBK_OK;
+  PBK_REQUIRE(keys != nullptr && rows != nullptr && (nt == 0 || t != nullptr), PBK_EINVAL, "NULL device pointer");
+  PBK_REQUIRE(aligned16(t) && aligned16(keys) && aligned16(rows), PBK_EALIGN,
+              "device pointers must be 16-byte aligned");
+  hamming_gather_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, as_stream(stream)>>>(
+      t, nt, train_base, reinterpret_cast<const unsigned long long*>(keys), nq, rows);
+  PBK_CHECK_LAUNCH("hamming_gather_kernel");
+  return PBK_OK;
+}
+
+int pbk_hamming_ratio_mutual(const uint64_t* keys, const uint64_t* rev_keys, int64_t nq, double ratio,
+                             int64_t* idx, int32_t* dist, uint8_t* ratio_ok, uint8_t* mutual_ok,
+                             uint8_t* valid, pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(nq >= 0, PBK_EINVAL, "negative size");
+  if (nq == 0) return PBK_OK;
+  PBK_REQUIRE(keys != nullptr, PBK_EINVAL, "NULL device pointer");
+  hamming_ratio_mutual_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const unsigned long long*>(keys), reinterpret_cast<const unsigned long long*>(rev_keys),
+      nq, ratio, reinterpret_cast<long long*>(idx), dist, ratio_ok, mutual_ok, valid);
+  PBK_CHECK_LAUNCH("hamming_ratio_mutual_kernel");
+  return PBK_OK;
+}
+
+int pbk_popc_peak_probe(int mode, int ctas, int iters, uint32_t* sink, double* popc_per_launch,
+                        pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(ctas > 0 && iters > 0 && sink != nullptr, PBK_EINVAL, "bad arguments");
+  cudaStream_t s = as_stream(stream);
+  double per_round;
+  switch (mode) {
+    case 0: popc_probe_kernel<0><<<ctas, 256, 0, s>>>(iters, sink); per_round = 16.0 * 8; break;
+    case 1: popc_probe_kernel<1><<<ctas, 256, 0, s>>>(iters, sink); per_round = 16.0 * 8; break;
+    case 2: popc_probe_kernel<2><<<ctas, 256, 0, s>>>(iters, sink); per_round = 16.0 * 8; break;
+    case 3: popc_probe_kernel<3><<<ctas, 256, 0, s>>>(iters, sink); per_round = 16.0 * 4; break;
+    default: PBK_REQUIRE(false, PBK_EINVAL, "bad probe mode %d", mode);
+  }
+  PBK_CHECK_LAUNCH("popc_probe_kernel");
+  if (popc_per_launch) *popc_per_launch = per_round * (double)iters * 256.0 * (double)ctas;
+  return PBK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// Shared helpers for the libpybot_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pybot_b200.h"
+
+namespace pbk {
+
+// ----------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);   // sets message, returns PBK_ECUDA
+
+#define PBK_REQUIRE(cond, code, ...)            \
+  do {                                          \
+    if (!(cond)) {                              \
+      ::pbk::set_error(__VA_ARGS__);            \
+      return (code);                            \
+    }                                           \
+  } while (0)
+
+#define PBK_CUDA(expr)                                        \
+  do {                                                        \
+    cudaError_t _e = (expr);                                  \
+    if (_e != cudaSuccess) return ::pbk::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define PBK_CHECK_LAUNCH(name)                                      \
+  do {                                                              \
+    cudaError_t _e = cudaGetLastError();                            \
+    if (_e != cudaSuccess) return ::pbk::cuda_fail(_e, name);       \
+  } while (0)
+
+static inline bool aligned16(const void* p) {
+  return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
+// Cached per-device facts (SM count etc.); returns 0 or a pbk_status.
+struct DeviceInfo {
+  int device;
+  int sm_count;
+  int cc_major, cc_minor;
+  int max_smem_optin;
+  int l2_bytes;
+};
+int current_device_info(const DeviceInfo** out);
+
+static inline cudaStream_t as_stream(pbk_stream_t s) {
+  return reinterpret_cast<cudaStream_t>(s);
+}
+
+// ------------------------------------------------ streaming loads / stores
+// Inputs on this path are read exactly once: bypass L1 allocation.  Outputs
+// are written exactly once: streaming (evict-first) stores.
+__device__ __forceinline__ float4 ld_stream_f4(const void* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint2 ld_stream_u2(const void* p) {
+  uint2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
+               : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u1(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream_f4(void* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream_u4(void* p, uint4 v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream_f2(void* p, float2 v) {
+  asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};"
+               :: "l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_stream_d1(void* p, double v) {
+  asm volatile("st.global.cs.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
+}
+
+// Grid for a streaming kernel: enough resident CTAs to cover every SM
+// `ctas_per_sm` times, never more than the work needs.
+static inline int stream_grid(const DeviceInfo* di, long long work_items,
+                              int ctas_per_sm) {
+  long long g = (long long)di->sm_count * ctas_per_sm;
+  if (g > work_items) g = work_items;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace pbk

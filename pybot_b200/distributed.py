@@ -1,0 +1,122 @@
+"""Multi-GPU sharding for the two paths that partition.
+
+One process per GPU, ``torch.distributed`` (NCCL over NVLink on the B200 box,
+gloo in the CPU tests) for the plumbing.
+
+* Loop-closure matching: the keyframe database is split into contiguous
+  keyframe ranges, one per rank; queries are replicated.  Every rank computes
+  its top-2 packed keys ``(distance << 32 | global_row)``, the 32 KB results are
+  all-gathered and merged with the same unsigned min the kernel uses, so the
+  result is bit-identical to the single-GPU scan.  For the mutual check the
+  owner of each matched train row contributes it to a (nq,32) uint8 buffer that
+  is sum-all-reduced (every other rank contributes zeros), then every rank runs
+  the tiny reverse pass locally.
+* BA residual/Jacobian: observations are split into contiguous chunks; cameras
+  and points are replicated; the only exchange is an all-reduce of the fp64
+  cost.
+
+Per-frame reprojection / projection do not shard (replicas only).
+
+The compute steps are injected through ``kernels`` so the CPU tests can drive
+the sharding and collective logic with the oracle; the default is the CUDA
+library and it raises without a GPU.
+"""
+import numpy as np
+
+from . import _ffi
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous, balanced [lo, hi) of n_items for `rank` of `world`."""
+    base, extra = divmod(int(n_items), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class _CudaMatchKernels(object):
+    """Default compute backend: libpybot_b200.so."""
+
+    def knn2(self, q, t, train_base):
+        from . import ops
+        return ops.hamming_knn2_keys(q, t, train_base)
+
+    def merge(self, partial):
+        from . import ops
+        return ops.hamming_merge(partial)
+
+    def gather_best(self, t, keys, train_base):
+        from . import ops
+        return ops.hamming_gather_best(t, keys, train_base)
+
+    def ratio_mutual(self, keys, rev, ratio):
+        from . import ops
+        return ops.hamming_ratio_mutual(keys, rev, ratio)
+
+
+class ShardedKeyframeMatcher(object):
+    """Holds this rank's shard of the keyframe database and matches replicated
+    queries against the whole database."""
+
+    def __init__(self, shard, shard_base, group=None, kernels=None):
+        """shard: (n_local, 32) uint8 tensor on this rank's device;
+        shard_base: global row index of shard[0]."""
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.shard = shard
+        self.shard_base = int(shard_base)
+        self.kernels = kernels if kernels is not None else _CudaMatchKernels()
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def local_keys(self, q):
+        return self.kernels.knn2(q, self.shard, self.shard_base)
+
+    def global_keys(self, q):
+        """(nq,2) global top-2 keys, identical on every rank."""
+        T = _ffi.torch()
+        local = self.local_keys(q)
+        if self.world == 1:
+            return local
+        gathered = T.empty((self.world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+        self.dist.all_gather_into_tensor(gathered, local.contiguous(), group=self.group)
+        return self.kernels.merge(gathered)
+
+    def match(self, q, ratio=0.75, mutual=True):
+        """idx (nq,2) global rows, dist (nq,2), ratio_ok, mutual_ok, valid."""
+        keys = self.global_keys(q)
+        rev = None
+        if mutual:
+            rows = self.kernels.gather_best(self.shard, keys, self.shard_base)
+            if self.world > 1:
+                self.dist.all_reduce(rows, op=self.dist.ReduceOp.SUM, group=self.group)
+            rev = self.kernels.knn2(rows, q, 0)
+        return self.kernels.ratio_mutual(keys, rev, ratio)
+
+
+class ShardedBA(object):
+    """This rank's contiguous chunk of the observations of a BA problem."""
+
+    def __init__(self, rvecs, tvecs, K, points, obs_cam, obs_pt, obs_uv, group=None,
+                 problem_factory=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        lo, hi = shard_range(len(obs_cam), self.rank, self.world)
+        self.range = (lo, hi)
+        if problem_factory is None:
+            from .ops import BAProblemDevice as problem_factory
+        self.problem = problem_factory(rvecs, tvecs, K, points, obs_cam[lo:hi], obs_pt[lo:hi],
+                                       obs_uv[lo:hi])
+
+    def evaluate(self):
+        """Evaluates the local residuals/Jacobians (they stay on the owning
+        rank) and returns the global cost tensor (1,) float64, all-reduced."""
+        self.problem.evaluate()
+        cost = self.problem.cost
+        if self.world > 1:
+            cost = cost.clone()
+            self.dist.all_reduce(cost, op=self.dist.ReduceOp.SUM, group=self.group)
+        return cost

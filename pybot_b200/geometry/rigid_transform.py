@@ -1,0 +1,234 @@
+"""SE(3) / Sim(3) poses with GPU point application.
+
+Same class and method names as /root/reference/pybot/geometry/rigid_transform.py
+(:99-368), so ``from pybot_b200.geometry.rigid_transform import RigidTransform``
+is a one-line swap.  Pose algebra (compounding, inversion, conversions) is
+7-scalar host work in float64 numpy; applying a pose to an (N,3) array - the
+hot path, ``np.hstack`` + ``np.dot`` at rigid_transform.py:139-141 - runs on the
+B200 through ``pbk_transform_points``.
+
+Kept reference semantics: the translation is stored as
+float32, the quaternion as float64, ``pose * X`` returns float64 (N,3).
+"""
+import random as rnd
+
+import numpy as np
+
+from .quaternion import Quaternion
+from .. import ops
+
+
+def rpyxyz(roll, pitch, yaw, x, y, z, axes="rxyz"):
+    return RigidTransform.from_rpyxyz(roll, pitch, yaw, x, y, z, axes=axes)
+
+
+def pose(pid, rt):
+    assert isinstance(rt, RigidTransform)
+    return Pose.from_rigid_transform(pid, rt)
+
+
+def _is_points(other):
+    if isinstance(other, np.ndarray):
+        return True
+    return hasattr(other, "shape") and hasattr(other, "dtype")      # torch tensor
+
+
+class RigidTransform(object):
+    """quat: rotation (xyzw); tvec: translation (xyz)."""
+
+    def __init__(self, xyzw=(0., 0., 0., 1.), tvec=(0., 0., 0.)):
+        self.quat = Quaternion(xyzw)
+        self.tvec = np.float32(tvec)
+
+    def __repr__(self):
+        return "rpy (rxyz): %s tvec: %s" % (
+            np.array_str(self.quat.to_rpy(axes="rxyz"), precision=2, suppress_small=True),
+            np.array_str(self.tvec, precision=2, suppress_small=True))
+
+    # ------------------------------------------------------------- hot path
+    def __mul__(self, other):
+        """pose * pose -> oplus; pose * (N,3) array -> transformed points on
+        the GPU (float64, like the reference)."""
+        if isinstance(other, RigidTransform):
+            return self.oplus(other)
+        if isinstance(other, (list, tuple)):
+            other = np.asarray(other)
+        if not _is_points(other):
+            raise TypeError("cannot apply a RigidTransform to %s" % type(other))
+        return self.transform_points(other)
+
+    def transform_points(self, X, out_dtype=np.float64):
+        T = self.to_matrix()
+        return ops.transform_points(X, T[:3, :3], T[:3, 3], 1.0, out_dtype)
+
+    def __rmul__(self, other):
+        raise NotImplementedError("Right multiply not implemented yet!")
+
+    # ------------------------------------------------------------ pose algebra
+    def copy(self):
+        return RigidTransform(self.quat.copy(), self.tvec.copy())
+
+    def inverse(self):
+        qinv = self.quat.inverse()
+        return RigidTransform(qinv, qinv.rotate(-self.tvec))
+
+    def oplus(self, other):
+        if isinstance(other, RigidTransform):
+            t = self.quat.rotate(other.tvec) + self.tvec
+            return RigidTransform(self.quat * other.quat, t)
+        if isinstance(other, list):
+            return [self.oplus(o) for o in other]
+        raise TypeError("Type inconsistent", type(other), other.__class__)
+
+    def ominus(self, other):
+        raise NotImplementedError()
+
+    def wrt(self, p_tr):
+        return self * p_tr
+
+    def rotate_vec(self, v):
+        v = np.asarray(v)
+        if v.ndim == 2:
+            return np.vstack([self.quat.rotate(row) for row in v])
+        assert v.ndim == 1
+        return self.quat.rotate(v)
+
+    def interpolate(self, other, w):
+        assert 0 <= w <= 1.0
+        return self.from_Rt(self.rotation.interpolate(other.rotation, w).R,
+                            self.t + w * (other.t - self.t))
+
+    # ------------------------------------------------------------ conversions
+    def to_matrix(self):
+        """4x4 [R t; 0 1] float64 (translation already rounded to float32)."""
+        M = self.quat.to_matrix()
+        M[:3, 3] = self.tvec
+        return M
+
+    def to_vector(self):
+        return np.hstack([self.tvec, self.xyzw])
+
+    def to_Rt(self):
+        M = self.to_matrix()
+        return M[:3, :3].copy(), M[:3, 3].copy()
+
+    def to_rpyxyz(self, axes="rxyz"):
+        r, p, y = self.quat.to_rpy(axes=axes)
+        return np.array((r, p, y, self.tvec[0], self.tvec[1], self.tvec[2]))
+
+    @classmethod
+    def from_rpyxyz(cls, roll, pitch, yaw, x, y, z, axes="rxyz"):
+        return cls(Quaternion.from_rpy(roll, pitch, yaw, axes=axes), (x, y, z))
+
+    @classmethod
+    def from_Rt(cls, R, t):
+        M = np.eye(4)
+        M[:3, :3] = np.asarray(R, np.float64)
+        return cls(Quaternion.from_matrix(M), t)
+
+    @classmethod
+    def from_matrix(cls, T):
+        T = np.asarray(T, np.float64)
+        return cls(Quaternion.from_matrix(T), T[:3, 3])
+
+    @classmethod
+    def from_vector(cls, v):
+        return cls(xyzw=v[3:], tvec=v[:3])
+
+    @classmethod
+    def from_triad(cls, pos, v1, v2):
+        # right-handed frame from two direction hints, origin at pos
+        x = np.asarray(v1, np.float64)
+        x = x / np.linalg.norm(x)
+        y = np.asarray(v2, np.float64)
+        y = y - x * np.dot(x, y)
+        y = y / np.linalg.norm(y)
+        M = np.eye(4)
+        M[:3, 0], M[:3, 1], M[:3, 2] = x, y, np.cross(x, y)
+        M[:3, 3] = pos
+        return cls.from_matrix(M)
+
+    @classmethod
+    def from_angle_axis(cls, angle, axis, tvec):
+        return cls(Quaternion.from_angle_axis(angle, axis), tvec)
+
+    @classmethod
+    def identity(cls):
+        return cls()
+
+    @classmethod
+    def random(cls, t=1):
+        w = np.array([rnd.random() for _ in range(4)])
+        w /= np.sqrt(np.sum(w * w))
+        return cls(Quaternion.from_wxyz(w), [rnd.uniform(-t, t) for _ in range(3)])
+
+    def scaled(self, scale):
+        return Sim3(xyzw=self.xyzw, tvec=self.tvec, scale=scale)
+
+    # -------------------------------------------------------------- properties
+    wxyz = property(lambda self: self.quat.wxyz)
+    xyzw = property(lambda self: self.quat.xyzw)
+    R = property(lambda self: self.quat.R)
+    t = property(lambda self: self.tvec)
+    orientation = property(lambda self: self.quat)
+    rotation = property(lambda self: self.quat)
+    rpyxyz = property(lambda self: self.to_rpyxyz())
+    translation = property(lambda self: self.tvec)
+    matrix = property(lambda self: self.to_matrix())
+    vector = property(lambda self: self.to_vector())
+
+
+class Sim3(RigidTransform):
+    """Similarity transform (reference :307-352).
+
+    ``to_matrix`` keeps the reference's [R/s t; 0 1/s] form and ``oplus`` its
+    t = s*R*t_o + t rule.  Applying a Sim3 to points raises
+    NotImplementedError in the reference (:339-342); here it evaluates
+    Y = s*R*X + t on the GPU, the semantics consistent with ``oplus``
+    (parity unpinned).
+    """
+
+    def __init__(self, xyzw=(0., 0., 0., 1.), tvec=(0., 0., 0.), scale=1.0):
+        RigidTransform.__init__(self, xyzw=xyzw, tvec=tvec)
+        self.scale = scale
+
+    @classmethod
+    def from_matrix(cls, T):
+        T = np.asarray(T, np.float64)
+        M = np.eye(4)
+        M[:3, :3] = T[:3, :3] / T[3, 3]
+        return cls(Quaternion.from_matrix(M), T[:3, 3], scale=1.0 / T[3, 3])
+
+    def to_matrix(self):
+        M = self.quat.to_matrix()
+        M[:3, 3] = self.tvec
+        M[3, 3] = 1.0 / self.scale
+        M[:3, :3] /= self.scale
+        return M
+
+    def transform_points(self, X, out_dtype=np.float64):
+        M = RigidTransform.to_matrix(self)
+        return ops.transform_points(X, M[:3, :3], M[:3, 3], float(self.scale), out_dtype)
+
+    def oplus(self, other):
+        if isinstance(other, RigidTransform):
+            t = self.scale * self.quat.rotate(other.tvec) + self.tvec
+            return RigidTransform(self.quat * other.quat, t)
+        if isinstance(other, list):
+            return [self.oplus(o) for o in other]
+        raise TypeError("Type inconsistent", type(other), other.__class__)
+
+
+class Pose(RigidTransform):
+    def __init__(self, pid, xyzw=(0., 0., 0., 1.), tvec=(0., 0., 0.)):
+        RigidTransform.__init__(self, xyzw=xyzw, tvec=tvec)
+        self.id = pid
+
+    @classmethod
+    def from_rigid_transform(cls, pid, pose):
+        return cls(pid, pose.quat, pose.tvec)
+
+    def __repr__(self):
+        return "Pose ID: %i, rpy (rxyz): %s tvec: %s" % (
+            self.id, np.array_str(self.quat.to_rpy(axes="rxyz"), precision=2),
+            np.array_str(self.tvec, precision=2))

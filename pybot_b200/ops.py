@@ -1,0 +1,343 @@
+"""Array-level wrappers over the C-ABI (one function per kernel family).
+
+Inputs may be numpy arrays (copied host->device, results copied back through
+pinned memory) or torch CUDA tensors (zero-copy; results stay on the device).
+torch is only the carrier: every arithmetic result comes from
+libpybot_b200.so.  Nothing here falls back to the CPU.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _ffi
+
+_NP = {"float32": np.float32, "float64": np.float64}
+
+
+def _tdtype(t, npdt):
+    return getattr(t, np.dtype(npdt).name)
+
+
+def _points_in(X):
+    """(n,3) float32/float64 device tensor from any float array-like."""
+    t = _ffi.require_cuda()
+    if isinstance(X, t.Tensor):
+        if X.dtype not in (t.float32, t.float64):
+            X = X.to(t.float64)
+    else:
+        X = np.asarray(X)
+        if X.dtype not in (np.float32, np.float64):
+            X = X.astype(np.float64)         # like np.hstack with float64 ones
+    if X.ndim != 2 or X.shape[1] != 3:
+        raise ValueError("expected an (N, 3) point array, got %s" % (tuple(X.shape),))
+    return _ffi.to_device(X)
+
+
+def _finish(tensor, on_device):
+    return tensor if on_device else _ffi.to_host(tensor)
+
+
+# ---------------------------------------------------------------- transform
+def transform_points(X, R, t, scale=1.0, out_dtype=np.float64):
+    """Y = scale * R @ X + t for (N,3) points.  Reference:
+    RigidTransform.__mul__ (rigid_transform.py:139-141) returns float64."""
+    T = _ffi.require_cuda()
+    Xd, on_dev = _points_in(X)
+    n = Xd.shape[0]
+    Y = T.empty((n, 3), dtype=_tdtype(T, out_dtype), device=Xd.device)
+    Rt = np.concatenate([np.asarray(R, np.float64).reshape(9), np.asarray(t, np.float64).reshape(3)])
+    Rt, Rt_p = _ffi.host_f64(Rt, 12)
+    _ffi.check(_ffi.lib().pbk_transform_points(
+        _ffi.ptr(Xd), _ffi.pbk_dtype(_NP[str(Xd.dtype).split(".")[-1]]), n, Rt_p,
+        float(scale), _ffi.ptr(Y), _ffi.pbk_dtype(out_dtype), _ffi.stream_ptr()))
+    return _finish(Y, on_dev)
+
+
+# ------------------------------------------------------------------ project
+def project_points(X, R, t, K, D=None, Rz=None, tz=None, shape=None, check_bounds=False,
+                   check_depth=False, return_depth=False, return_valid=False, min_depth=0.1,
+                   compact=True):
+    """Fused cv2.projectPoints + depth + masks + x[valid] compaction.
+
+    R, t      rotation/translation used for the pixel coordinates
+    Rz, tz    third row / z-translation used for the depth (defaults to R[2], t[2])
+    Returns (uv, depth or None, valid or None, count).  With compact=True uv
+    and depth hold only the valid points, in input order (camera_utils.py:727-732).
+    """
+    T = _ffi.require_cuda()
+    Xd, on_dev = _points_in(X)
+    n = Xd.shape[0]
+    P = _ffi.ProjectParams()
+    R = np.asarray(R, np.float64).reshape(9)
+    t = np.asarray(t, np.float64).reshape(3)
+    P.R[:] = R.tolist()
+    P.t[:] = t.tolist()
+    rz = R[6:9] if Rz is None else np.asarray(Rz, np.float64).reshape(3)
+    P.Rz[:] = rz.tolist()
+    P.tz = float(t[2] if tz is None else tz)
+    K = np.asarray(K, np.float64)
+    P.fx, P.fy, P.cx, P.cy = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+    k = np.zeros(8)
+    if D is not None:
+        Dv = np.asarray(D, np.float64).ravel()
+        if Dv.size > 8:
+            raise NotImplementedError("thin-prism / tilt distortion (>8 coefficients) is not supported")
+        if Dv.size not in (0, 4, 5, 8):
+            raise ValueError("distortion must have 4, 5 or 8 coefficients")
+        k[:Dv.size] = Dv
+    P.k[:] = k.tolist()
+    P.has_distortion = int(np.any(k != 0))
+    P.min_depth = float(min_depth)
+    if check_bounds and shape is None:
+        raise ValueError("check_bounds cannot proceed. Camera.shape is not set")
+    P.height, P.width = (int(shape[0]), int(shape[1])) if shape is not None else (0, 0)
+    P.check_depth = int(bool(check_depth))
+    P.check_bounds = int(bool(check_bounds))
+    do_compact = bool(compact and (check_depth or check_bounds))
+    P.compact = int(do_compact)
+    uv = T.empty((n, 2), dtype=Xd.dtype, device=Xd.device)
+    depth = T.empty((n,), dtype=T.float64, device=Xd.device) if return_depth else None
+    valid = T.empty((n,), dtype=T.uint8, device=Xd.device) if return_valid else None
+    count = T.empty((1,), dtype=T.int64, device=Xd.device)
+    scratch = None
+    if do_compact:
+        nbytes = _ffi.lib().pbk_project_scratch_bytes(n)
+        scratch = T.empty((max(nbytes, 16),), dtype=T.uint8, device=Xd.device)
+    in_dt = _ffi.PBK_F32 if Xd.dtype == T.float32 else _ffi.PBK_F64
+    _ffi.check(_ffi.lib().pbk_project_points(
+        _ffi.ptr(Xd), in_dt, n, ctypes.byref(P), _ffi.ptr(uv), _ffi.ptr(depth), _ffi.ptr(valid),
+        _ffi.ptr(count), _ffi.ptr(scratch), _ffi.stream_ptr()))
+    m = n
+    if do_compact:
+        m = int(count.item())            # one 8-byte D2H; also orders the stream
+        uv = uv[:m]
+        if depth is not None:
+            depth = depth[:m]
+    if valid is not None:
+        valid = valid.bool() if on_dev else valid
+    outs = [_finish(uv, on_dev),
+            _finish(depth, on_dev) if depth is not None else None,
+            (_finish(valid, on_dev) if valid is not None else None)]
+    if not on_dev and outs[2] is not None:
+        outs[2] = outs[2].view(np.bool_)
+    return outs[0], outs[1], outs[2], m
+
+
+# ---------------------------------------------------------------- reproject
+_DISP_DTYPES = (np.uint8, np.int16, np.int32, np.float32)
+
+
+def reproject_disparity(disp, Q, sample=1, bgr=None):
+    """cv2.reprojectImageTo3D(disp, Q) for (H,W) or (B,H,W) disparity; with
+    `bgr` also returns the sub-sampled colour like reconstruct_with_texture.
+    Returns xyz (..., Hs, Ws, 3) float32 [, bgr_out (..., Hs, Ws, 3) uint8]."""
+    T = _ffi.require_cuda()
+    is_t = isinstance(disp, T.Tensor)
+    dt = np.dtype(str(disp.dtype).split(".")[-1]) if is_t else np.asarray(disp).dtype
+    if dt == np.float64:
+        raise NotImplementedError(
+            "float64 disparity is not supported (cv2.reprojectImageTo3D rejects it as well)")
+    if dt.type not in _DISP_DTYPES:
+        raise TypeError("disparity dtype must be uint8, int16, int32 or float32; got %s" % dt)
+    d, on_dev = _ffi.to_device(disp)
+    if d.ndim not in (2, 3):
+        raise ValueError("disparity must be (H,W) or (B,H,W)")
+    batched = d.ndim == 3
+    B = d.shape[0] if batched else 1
+    H, W = int(d.shape[-2]), int(d.shape[-1])
+    s = int(sample)
+    if s < 1:
+        raise ValueError("sample must be >= 1")
+    Hs, Ws = -(-H // s), -(-W // s)
+    Qh, Qp = _ffi.host_f32(Q, 16)
+    xyz = T.empty((B, Hs, Ws, 3), dtype=T.float32, device=d.device)
+    c = c_out = None
+    if bgr is not None:
+        c, _ = _ffi.to_device(bgr)
+        if c.dtype != T.uint8 or tuple(c.shape[-3:]) != (H, W, 3):
+            raise ValueError("colour image must be uint8 (H, W, 3) matching the disparity")
+        c_out = T.empty((B, Hs, Ws, 3), dtype=T.uint8, device=d.device)
+    _ffi.check(_ffi.lib().pbk_reproject_disp(
+        _ffi.ptr(d), _ffi.pbk_dtype(dt), B, H, W, Qp, s, _ffi.ptr(xyz), _ffi.ptr(c), _ffi.ptr(c_out),
+        _ffi.stream_ptr()))
+    if not batched:
+        xyz = xyz[0]
+        c_out = c_out[0] if c_out is not None else None
+    if c_out is None:
+        return _finish(xyz, on_dev)
+    return _finish(xyz, on_dev), _finish(c_out, on_dev)
+
+
+def reproject_sparse(xyd, Q):
+    """StereoCamera.reconstruct_sparse (camera_utils.py:971-980): float64."""
+    T = _ffi.require_cuda()
+    x, on_dev = _ffi.to_device(xyd, np.float64)
+    if x.ndim != 2 or x.shape[1] != 3:
+        raise ValueError("expected (N,3) [x, y, d] rows")
+    Qh, Qp = _ffi.host_f32(Q, 16)
+    out = T.empty_like(x)
+    _ffi.check(_ffi.lib().pbk_reproject_sparse(_ffi.ptr(x), x.shape[0], Qp, _ffi.ptr(out),
+                                               _ffi.stream_ptr()))
+    return _finish(out, on_dev)
+
+
+# ------------------------------------------------------------------ hamming
+def _desc_in(a):
+    T = _ffi.require_cuda()
+    if isinstance(a, T.Tensor):
+        if a.dtype != T.uint8:
+            raise TypeError("descriptors must be uint8")
+    else:
+        a = np.asarray(a)
+        if a.dtype != np.uint8:
+            raise TypeError("descriptors must be uint8")
+    if a.ndim != 2 or a.shape[1] != 32:
+        raise ValueError("descriptors must be (N, 32) uint8 (256-bit ORB)")
+    return _ffi.to_device(a)[0]
+
+
+def hamming_knn2_keys(q_dev, t_dev, train_base=0):
+    """Top-2 packed keys (nq,2) uint64-as-int64 device tensor for device inputs."""
+    T = _ffi.torch()
+    nq, nt = q_dev.shape[0], t_dev.shape[0]
+    splits = ctypes.c_int(0)
+    nbytes = ctypes.c_size_t(0)
+    L = _ffi.lib()
+    _ffi.check(L.pbk_hamming_plan(nq, nt, ctypes.byref(splits), ctypes.byref(nbytes)))
+    scratch = T.empty((max(int(nbytes.value), 16),), dtype=T.uint8, device=q_dev.device)
+    keys = T.empty((max(nq, 1), 2), dtype=T.int64, device=q_dev.device)[:nq]
+    _ffi.check(L.pbk_hamming_knn2(_ffi.ptr(q_dev), nq, _ffi.ptr(t_dev) if nt else None, nt,
+                                  int(train_base), _ffi.ptr(keys), _ffi.ptr(scratch),
+                                  _ffi.stream_ptr()))
+    return keys
+
+
+def hamming_merge(partial_dev):
+    """(parts, nq, 2) keys -> (nq, 2) global top-2."""
+    T = _ffi.torch()
+    parts, nq = int(partial_dev.shape[0]), int(partial_dev.shape[1])
+    keys = T.empty((max(nq, 1), 2), dtype=T.int64, device=partial_dev.device)[:nq]
+    _ffi.check(_ffi.lib().pbk_hamming_merge_top2(_ffi.ptr(partial_dev.contiguous()), parts, nq,
+                                                 _ffi.ptr(keys), _ffi.stream_ptr()))
+    return keys
+
+
+def hamming_gather_best(t_dev, keys, train_base=0):
+    T = _ffi.torch()
+    nq = int(keys.shape[0])
+    rows = T.empty((max(nq, 1), 32), dtype=T.uint8, device=keys.device)[:nq]
+    nt = int(t_dev.shape[0])
+    _ffi.check(_ffi.lib().pbk_hamming_gather_best(_ffi.ptr(t_dev) if nt else None, nt, int(train_base),
+                                                  _ffi.ptr(keys), nq, _ffi.ptr(rows), _ffi.stream_ptr()))
+    return rows
+
+
+def hamming_ratio_mutual(keys, rev_keys, ratio):
+    T = _ffi.torch()
+    nq = int(keys.shape[0])
+    dev = keys.device
+    m = max(nq, 1)
+    idx = T.empty((m, 2), dtype=T.int64, device=dev)[:nq]
+    dist = T.empty((m, 2), dtype=T.int32, device=dev)[:nq]
+    flags = T.empty((3, m), dtype=T.uint8, device=dev)
+    _ffi.check(_ffi.lib().pbk_hamming_ratio_mutual(
+        _ffi.ptr(keys), _ffi.ptr(rev_keys), nq, float(ratio), _ffi.ptr(idx), _ffi.ptr(dist),
+        _ffi.ptr(flags[0]), _ffi.ptr(flags[1]), _ffi.ptr(flags[2]), _ffi.stream_ptr()))
+    return idx, dist, flags[0, :nq].bool(), flags[1, :nq].bool(), flags[2, :nq].bool()
+
+
+def knn_ratio_mutual(q, t, ratio=0.75, train_base=0, mutual=True):
+    """Forward k=2 + Lowe ratio + mutual check on one GPU.
+    Returns numpy (idx (nq,2) int64, dist (nq,2) int32, ratio_ok, mutual_ok, valid)
+    or device tensors if q is a CUDA tensor."""
+    T = _ffi.require_cuda()
+    on_dev = isinstance(q, T.Tensor) and q.is_cuda
+    qd, td = _desc_in(q), _desc_in(t)
+    keys = hamming_knn2_keys(qd, td, train_base)
+    rev = None
+    if mutual:
+        rows = hamming_gather_best(td, keys, train_base)
+        rev = hamming_knn2_keys(rows, qd, 0)
+    out = hamming_ratio_mutual(keys, rev, ratio)
+    if on_dev:
+        return out
+    return tuple(_ffi.to_host(o) for o in out)
+
+
+def popc_probe(mode=0, ctas=None, iters=2000):
+    """Launches the popc-pipe probe; returns the POPC count of the launch."""
+    T = _ffi.require_cuda()
+    if ctas is None:
+        ctas = T.cuda.get_device_properties(0).multi_processor_count * 8
+    sink = T.zeros((8 + ctas * 256,), dtype=T.int32, device="cuda")
+    n = ctypes.c_double(0)
+    _ffi.check(_ffi.lib().pbk_popc_peak_probe(int(mode), int(ctas), int(iters), _ffi.ptr(sink),
+                                              ctypes.byref(n), _ffi.stream_ptr()))
+    return n.value
+
+
+# ----------------------------------------------------------------------- BA
+class BAProblemDevice(object):
+    """Device-resident BA inputs + outputs (allocated once, reused per eval)."""
+
+    def __init__(self, rvecs, tvecs, K, points, obs_cam, obs_pt, obs_uv, want=("r", "Jc", "Jp")):
+        T = _ffi.require_cuda()
+        self.T = T
+        self.rvec, _ = _ffi.to_device(rvecs, np.float32)
+        self.tvec, _ = _ffi.to_device(tvecs, np.float32)
+        self.points, _ = _ffi.to_device(points, np.float32)
+        self.n_cams, self.n_points = int(self.rvec.shape[0]), int(self.points.shape[0])
+        K = np.asarray(K, np.float64)
+        self.fx, self.fy, self.cx, self.cy = (float(K[0, 0]), float(K[1, 1]), float(K[0, 2]),
+                                              float(K[1, 2]))
+        if isinstance(obs_cam, T.Tensor):
+            oc, op, ouv = obs_cam.cuda().int(), obs_pt.cuda().int(), obs_uv.cuda().float()
+            if oc.numel() and (int(oc.min()) < 0 or int(oc.max()) >= self.n_cams
+                               or int(op.min()) < 0 or int(op.max()) >= self.n_points):
+                raise ValueError("observation index out of range")
+            obs = T.empty((oc.shape[0], 4), dtype=T.int32, device="cuda")
+            obs[:, 0], obs[:, 1] = oc, op
+            obs[:, 2:] = ouv.contiguous().view(T.int32)
+            self.obs = obs
+        else:
+            oc = np.asarray(obs_cam, np.int32)
+            op = np.asarray(obs_pt, np.int32)
+            if oc.size and (oc.min() < 0 or oc.max() >= self.n_cams or op.min() < 0
+                            or op.max() >= self.n_points):
+                raise ValueError("observation index out of range")
+            packed = np.empty((len(oc), 4), np.int32)
+            packed[:, 0], packed[:, 1] = oc, op
+            packed[:, 2:] = np.ascontiguousarray(obs_uv, np.float32).view(np.int32)
+            self.obs, _ = _ffi.to_device(packed)
+        self.n_obs = int(self.obs.shape[0])
+        O = max(self.n_obs, 1)
+        dev = "cuda"
+        self.cam_blocks = T.empty((max(self.n_cams, 1), _ffi.PBK_BA_CAM_DOUBLES), dtype=T.float64, device=dev)
+        self.r = T.empty((O, 2), dtype=T.float32, device=dev)[:self.n_obs] if "r" in want else None
+        self.Jc = T.empty((O, 2, 6), dtype=T.float32, device=dev)[:self.n_obs] if "Jc" in want else None
+        self.Jp = T.empty((O, 2, 3), dtype=T.float32, device=dev)[:self.n_obs] if "Jp" in want else None
+        slots = _ffi.lib().pbk_ba_cost_slots(self.n_obs)
+        if slots < 0:
+            _ffi.check(_ffi.PBK_ECUDA)
+        self.partials = T.zeros((max(slots, 1),), dtype=T.float64, device=dev)
+        self.cost = T.zeros((1,), dtype=T.float64, device=dev)
+
+    def evaluate(self):
+        """One residual + Jacobian evaluation (asynchronous on the current stream)."""
+        L = _ffi.lib()
+        s = _ffi.stream_ptr()
+        _ffi.check(L.pbk_ba_camera_precompute(_ffi.ptr(self.rvec), _ffi.ptr(self.tvec), self.n_cams,
+                                              _ffi.ptr(self.cam_blocks), s))
+        _ffi.check(L.pbk_ba_residual_jacobian(
+            _ffi.ptr(self.obs), self.n_obs, _ffi.ptr(self.points), self.n_points,
+            _ffi.ptr(self.cam_blocks), self.n_cams, self.fx, self.fy, self.cx, self.cy,
+            _ffi.ptr(self.r), _ffi.ptr(self.Jc), _ffi.ptr(self.Jp), _ffi.ptr(self.partials),
+            _ffi.ptr(self.cost), s))
+        return self
+
+
+def ba_residual_jacobian(rvecs, tvecs, K, points, obs_cam, obs_pt, obs_uv):
+    """r (O,2), J_cam (O,2,6), J_pt (O,2,3) float32 and cost = sum ||r||^2 (float)."""
+    p = BAProblemDevice(rvecs, tvecs, K, points, obs_cam, obs_pt, obs_uv).evaluate()
+    cost = float(p.cost.item())
+    return _ffi.to_host(p.r), _ffi.to_host(p.Jc), _ffi.to_host(p.Jp), cost

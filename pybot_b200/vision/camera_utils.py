@@ -1,0 +1,332 @@
+"""Pinhole / stereo camera models with GPU projection and reconstruction.
+
+Same class, method and argument names as the hot-path part of
+/root/reference/pybot/vision/camera_utils.py (:93-133, :400-1007), so
+``from pybot_b200.vision.camera_utils import Camera, StereoCamera`` is a
+one-line swap.  Intrinsics / extrinsics bookkeeping is host-side scalar work;
+the array work runs on the B200:
+
+    Camera.project                      -> pbk_project_points   (was cv2.projectPoints
+                                           + np.dot + masks + fancy indexing, :687-734)
+    Camera.depth_from_projection,
+    CameraExtrinsic.c2w / w2c           -> pbk_transform_points (was np.dot, :585-595,:736-743)
+    StereoCamera.reconstruct*           -> pbk_reproject_disp   (was cv2.reprojectImageTo3D
+                                           + np.copy passes, :964-990)
+
+Unlike the reference, failures raise (the reference prints and continues at
+:696-701).  Everything needs a CUDA device; there is no CPU fallback.
+"""
+import numpy as np
+
+from ..geometry.rigid_transform import RigidTransform
+from ..geometry.rodrigues import rodrigues_round_trip
+from .. import ops
+
+
+def get_baseline(fx, baseline=None, baseline_px=None):
+    """baseline [m] <-> baseline [px] through the focal length (reference :93-105)."""
+    assert baseline is not None or baseline_px is not None
+    if baseline is not None:
+        baseline_px = baseline * fx
+    else:
+        baseline = baseline_px / fx
+    return baseline, baseline_px
+
+
+def construct_K(fx=500.0, fy=500.0, cx=319.5, cy=239.5):
+    K = np.eye(3)
+    K[0, 0], K[1, 1] = fx, fy
+    K[0, 2], K[1, 2] = cx, cy
+    return K
+
+
+def construct_D(k1=0, k2=0, k3=0, p1=0, p2=0):
+    """OpenCV order [k1, k2, p1, p2, k3] (reference :129-133)."""
+    return np.float64([k1, k2, p1, p2, k3])
+
+
+def check_visibility(camera, pts_w, zmin=0, zmax=100):
+    """Field-of-view test of reference :245-266; the transform runs on the GPU."""
+    pts_c = np.asarray(camera.c2w(np.asarray(pts_w).reshape(-1, 3)))
+    z = pts_c[:, 2]
+    v = pts_c / np.linalg.norm(pts_c, axis=1).reshape(-1, 1)
+    hangle, vangle = np.arctan2(v[:, 0], v[:, 2]), np.arctan2(-v[:, 1], v[:, 2])
+    return np.bitwise_and.reduce([np.fabs(hangle) < camera.fov[0] * 0.5,
+                                  np.fabs(vangle) < camera.fov[1] * 0.5, z >= zmin, z <= zmax])
+
+
+def get_median_depth(camera, pts, subsample=10):
+    return np.median(np.asarray(camera * pts[::subsample])[:, 2])
+
+
+def get_bounded_projection(camera, pts, subsample=10, return_depth=False):
+    """Reference :279-288, with the bounds test and compaction fused into the
+    projection kernel instead of a second numpy pass."""
+    return camera.project(np.asarray(pts[::subsample], np.float32), check_bounds=True,
+                          return_valid=True)
+
+
+class CameraIntrinsic(object):
+    def __init__(self, K, D=np.zeros(5, dtype=np.float64), shape=None):
+        """K: 3x3 calibration; D: distortion; shape: (H, W[, C])."""
+        self.K = K
+        self.D = D
+        self.shape = np.int32(shape) if shape is not None else None
+
+    def __repr__(self):
+        return ("CameraIntrinsic: fx {:3.2f} fy {:3.2f} cx {:3.2f} cy {:3.2f} shape {} D {}"
+                .format(self.fx, self.fy, self.cx, self.cy, self.shape,
+                        np.array_str(np.asarray(self.D), precision=2, suppress_small=True)))
+
+    @classmethod
+    def simulate(cls):
+        return cls.from_calib_params(500., 500., 320., 240., shape=(480, 640))
+
+    @classmethod
+    def from_calib_params(cls, fx, fy, cx, cy, k1=0, k2=0, k3=0, p1=0, p2=0, shape=None):
+        return cls(construct_K(fx, fy, cx, cy), D=construct_D(k1, k2, k3, p1, p2), shape=shape)
+
+    @classmethod
+    def from_calib_params_fov(cls, fov, cx, cy, D=np.zeros(5, dtype=np.float64), shape=None):
+        return cls(construct_K(cx / np.tan(fov), cy / np.tan(fov), cx, cy), D=D, shape=shape)
+
+    fx = property(lambda self: self.K[0, 0])
+    fy = property(lambda self: self.K[1, 1])
+    cx = property(lambda self: self.K[0, 2])
+    cy = property(lambda self: self.K[1, 2])
+    skew = property(lambda self: self.K[0, 1])
+    k1 = property(lambda self: self.D[0])
+    k2 = property(lambda self: self.D[1])
+    p1 = property(lambda self: self.D[2])
+    p2 = property(lambda self: self.D[3])
+    k3 = property(lambda self: self.D[4])
+
+    @property
+    def fov(self):
+        return np.float32([np.arctan(self.shape[1] * 0.5 / self.fx),
+                           np.arctan(self.shape[0] * 0.5 / self.fy)]) * 2.0
+
+    def scaled(self, scale):
+        shape = np.int32(self.shape * scale) if self.shape is not None else None
+        return CameraIntrinsic.from_calib_params(
+            self.fx * scale, self.fy * scale, self.cx * scale, self.cy * scale,
+            k1=self.k1, k2=self.k2, k3=self.k3, p1=self.p1, p2=self.p2, shape=shape)
+
+    def in_view(self, x):
+        x = np.asarray(x)
+        return np.where((x[:, 0] >= 0) & (x[:, 0] < self.shape[1])
+                        & (x[:, 1] >= 0) & (x[:, 1] < self.shape[0]))[0]
+
+
+class CameraExtrinsic(RigidTransform):
+    def __init__(self, R=np.eye(3), t=np.zeros(3)):
+        """Pose p_cw (world with respect to the camera)."""
+        p = RigidTransform.from_Rt(R, t)
+        RigidTransform.__init__(self, xyzw=p.quat.to_xyzw(), tvec=p.tvec)
+        self.__cached_inverse = None
+
+    def inverse(self):
+        if self.__cached_inverse is None:
+            self.__cached_inverse = super(CameraExtrinsic, self).inverse()
+        return self.__cached_inverse
+
+    def __repr__(self):
+        return "CameraExtrinsic: pose = {:}".format(RigidTransform.__repr__(self))
+
+    def c2w(self, X):
+        return self * X
+
+    def w2c(self, X):
+        return self.inverse() * X
+
+    @classmethod
+    def from_rigid_transform(cls, p):
+        R, t = p.to_Rt()
+        return cls(R, t)
+
+    R = property(lambda self: self.quat.R)
+    Rt = property(lambda self: self.matrix[:3])
+    t = property(lambda self: self.tvec)
+    o2w = property(lambda self: self)
+    w2o = property(lambda self: self.inverse())
+
+    @classmethod
+    def identity(cls):
+        return cls()
+
+    @classmethod
+    def simulate(cls):
+        return cls.identity()
+
+
+class Camera(CameraIntrinsic, CameraExtrinsic):
+    def __init__(self, K, R, t, D=np.zeros(5, dtype=np.float64), shape=None):
+        CameraIntrinsic.__init__(self, K, D, shape=shape)
+        CameraExtrinsic.__init__(self, R, t)
+
+    def __repr__(self):
+        return "{:}\n{:}".format(CameraIntrinsic.__repr__(self), CameraExtrinsic.__repr__(self))
+
+    @property
+    def P(self):
+        return self.K.dot(self.Rt)
+
+    @classmethod
+    def simulate(cls):
+        return cls.from_intrinsics_extrinsics(CameraIntrinsic.simulate(), CameraExtrinsic.simulate())
+
+    @classmethod
+    def from_intrinsics_extrinsics(cls, intrinsic, extrinsic):
+        return cls(intrinsic.K, extrinsic.R, extrinsic.t, D=intrinsic.D, shape=intrinsic.shape)
+
+    @classmethod
+    def from_intrinsics(cls, intrinsic):
+        return cls.from_intrinsics_extrinsics(intrinsic, CameraExtrinsic.identity())
+
+    @classmethod
+    def from_KD(cls, K, D, shape=None):
+        return cls.from_intrinsics(CameraIntrinsic(K, D=D, shape=shape))
+
+    @property
+    def intrinsics(self):
+        return CameraIntrinsic(self.K, self.D, shape=self.shape)
+
+    @property
+    def extrinsics(self):
+        return CameraExtrinsic(self.R, self.t)
+
+    # ---------------------------------------------------------------- hot path
+    def _projection_params(self):
+        """Rotation for the pixels (Rodrigues round trip, reference :693-697)
+        and depth row (extrinsics round trip, :683-685, :743)."""
+        R, t = self.to_Rt()
+        Rp = rodrigues_round_trip(R)
+        Tz = self.extrinsics.to_matrix()
+        return Rp, t, Tz[2, :3].copy(), float(Tz[2, 3])
+
+    def project(self, X, check_bounds=False, check_depth=False, return_depth=False,
+                return_valid=False, min_depth=0.1):
+        """Project (N,3) points to (M,2) pixels; M <= N when a check is on.
+        Output list/array structure and dtypes follow the reference (:727-734):
+        x has X's float dtype, depths float64, valid bool."""
+        if check_bounds and self.shape is None:
+            raise ValueError("check_bounds cannot proceed. Camera.shape is not set")
+        Rp, t, Rz, tz = self._projection_params()
+        x, depths, valid, _ = ops.project_points(
+            X, Rp, t, self.K, self.D, Rz=Rz, tz=tz,
+            shape=None if self.shape is None else (int(self.shape[0]), int(self.shape[1])),
+            check_bounds=check_bounds, check_depth=check_depth, return_depth=return_depth,
+            return_valid=return_valid, min_depth=min_depth, compact=True)
+        output = [x]
+        if return_depth:
+            output.append(depths)
+        if return_valid:
+            output.append(valid)
+        return output if len(output) > 1 else output[0]
+
+    def depth_from_projection(self, X):
+        """z of p_cw * X (reference :736-743)."""
+        return (self.extrinsics * X)[:, 2]
+
+    def center(self):
+        if self.cx is None:
+            raise AssertionError("cx, cy is not set")
+        return np.matrix([self.cx, self.cy])
+
+    def set_pose(self, pose):
+        self.quat = pose.quat
+        self.tvec = pose.tvec
+
+    def scaled(self, scale):
+        return Camera.from_intrinsics_extrinsics(self.intrinsics.scaled(scale), self.extrinsics)
+
+    def check_visibility(self, pts, zmin=0, zmax=100):
+        return check_visibility(self, pts, zmin=zmin, zmax=zmax)
+
+
+class StereoCamera(Camera):
+    def __init__(self, lcamera, rcamera, baseline):
+        if not isinstance(lcamera, Camera) or not isinstance(rcamera, Camera):
+            raise TypeError("lcamera, rcamera are not Camera type")
+        Camera.__init__(self, lcamera.K, lcamera.R, lcamera.t, D=lcamera.D, shape=lcamera.shape)
+        if np.linalg.norm(lcamera.t - rcamera.t) < 1e-2:
+            raise ValueError("Right camera does not have an offset from the left camera")
+        self.right = rcamera
+        self.baseline = baseline
+
+    @classmethod
+    def simulate(cls):
+        return cls.from_left_with_baseline(Camera.simulate(), baseline=0.1)
+
+    @property
+    def left(self):
+        return Camera.from_intrinsics_extrinsics(self.intrinsics, self.extrinsics)
+
+    def __repr__(self):
+        return "StereoCamera: baseline {:} m\nLEFT {:}\nRIGHT {:}".format(
+            self.baseline, Camera.__repr__(self), self.right)
+
+    @property
+    def baseline_px(self):
+        return self.baseline * self.left.fx
+
+    @property
+    def Q(self):
+        """float32 reprojection matrix of the reference (:884-896):
+        X = (x-cx)*b/d, Y = (y-cy)*b/d, Z = fx*b/d."""
+        q43 = -1.0 / self.baseline
+        return np.float32([[-1, 0, 0, self.left.cx], [0, -1, 0, self.left.cy],
+                           [0, 0, 0, -self.left.fx], [0, 0, q43, 0]])
+
+    @classmethod
+    def from_calib_params(cls, fx, fy, cx, cy, k1=0, k2=0, k3=0, p1=0, p2=0, baseline=None,
+                          baseline_px=None, shape=None):
+        baseline, baseline_px = get_baseline(fx, baseline=baseline, baseline_px=baseline_px)
+        lcamera = Camera.from_intrinsics(CameraIntrinsic.from_calib_params(
+            fx, fy, cx, cy, k1=k1, k2=k2, k3=k3, p1=p1, p2=p2, shape=shape))
+        return cls.from_left_with_baseline(lcamera, baseline=baseline)
+
+    @classmethod
+    def from_left_with_baseline(cls, lcamera, baseline):
+        """Left extrinsics is assumed to be identity."""
+        rcamera = Camera.from_intrinsics_extrinsics(
+            lcamera.intrinsics, CameraExtrinsic.from_rigid_transform(
+                lcamera.oplus(RigidTransform.from_rpyxyz(0, 0, 0, baseline, 0, 0))))
+        return cls(lcamera, rcamera, baseline=baseline)
+
+    def scaled(self, scale):
+        left = super(StereoCamera, self).scaled(scale)
+        return StereoCamera(left, self.right.scaled(scale), baseline=self.baseline)
+
+    def disparity_from_plane(self, rows, height):
+        Z = height * self.left.fy / (np.arange(rows) - self.left.cy + 1e-9)
+        return self.left.fx * self.baseline / Z
+
+    def depth_from_disparity(self, disp):
+        return self.left.fx * self.baseline / disp
+
+    def disparity_from_depth(self, depth):
+        return self.left.fx * self.baseline / depth
+
+    # ---------------------------------------------------------------- hot path
+    def reconstruct(self, disp):
+        """(H,W) disparity -> (H,W,3) float32 XYZ.  Also accepts a (B,H,W)
+        batch of frames from the same camera (one launch)."""
+        return ops.reproject_disparity(disp, self.Q)
+
+    def reconstruct_sparse(self, xyd):
+        """(N,3) [x, y, d] rows -> (N,3) float64 XYZ."""
+        return ops.reproject_sparse(xyd, self.Q)
+
+    def reconstruct_with_texture(self, disp, im, sample=1):
+        """Returns (im_pub (N,3) uint8, X_pub (N,3) float32), N = ceil(H/s)*ceil(W/s);
+        batched inputs give (B,N,3)."""
+        if im.ndim != disp.ndim + 1:
+            raise AssertionError("image must be (H, W, 3)")
+        xyz, col = ops.reproject_disparity(disp, self.Q, sample=sample, bgr=im)
+        lead = tuple(xyz.shape[:-3])
+        return col.reshape(lead + (-1, 3)), xyz.reshape(lead + (-1, 3))
+
+    def set_pose(self, left_pose):
+        super(StereoCamera, self).set_pose(left_pose)
+        self.right.set_pose(self.left.oplus(RigidTransform.from_rpyxyz(0, 0, 0, self.baseline, 0, 0)))

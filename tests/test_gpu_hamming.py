@@ -1,0 +1,148 @@
+"""GPU parity: Hamming kNN k=2 + ratio + mutual with BFMatcher semantics (a9)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import model, port
+from pybot_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def g3(golden_dir):
+    return np.load(golden_dir + "/g3_matching.npz")
+
+
+def _check_against_model(q, t, ratio=0.75):
+    from pybot_b200.vision.matcher import knn_ratio_mutual
+    idx, dist, r_ok, m_ok, valid = knn_ratio_mutual(q, t, ratio)
+    ridx, rdist, rr, rm, rv = model.ratio_mutual(q, t, ratio)
+    assert np.array_equal(idx, ridx.astype(np.int64))
+    assert np.array_equal(dist, rdist)
+    assert np.array_equal(r_ok, rr) and np.array_equal(m_ok, rm) and np.array_equal(valid, rv)
+    return idx, dist, valid
+
+
+def test_low_entropy_ties_golden(g3):
+    """46%-tied descriptors: lowest-train-index tie-break, exact duplicates."""
+    from pybot_b200.vision.matcher import BFMatcher
+    q, t = g3["le_q"], g3["le_t"]
+    idx, dist, valid = _check_against_model(q, t)
+    assert np.array_equal(idx, g3["le_idx"]) and np.array_equal(dist, g3["le_dist"])
+    assert (dist[:, 0] == dist[:, 1]).mean() > 0.3
+    res = BFMatcher().knnMatch(q, t, k=2)
+    assert [[m.trainIdx for m in r] for r in res] == g3["le_idx"].tolist()
+    assert [[int(m.distance) for m in r] for r in res] == g3["le_dist"].tolist()
+    assert all(m.imgIdx == 0 and m.queryIdx == i for i, r in enumerate(res) for m in r)
+    cross = BFMatcher(crossCheck=True).match(q, t)
+    assert [[m.queryIdx, m.trainIdx] for m in cross] == g3["le_cross"].tolist()
+
+
+def test_train_smaller_than_k(g3):
+    from pybot_b200.vision.matcher import BFMatcher
+    res = BFMatcher().knnMatch(g3["le_q"][:4], g3["le_t"][:1], k=2)
+    assert [len(r) for r in res] == g3["nt1_len"].tolist()
+    _check_against_model(g3["le_q"][:4], g3["le_t"][:1])
+    empty = BFMatcher().knnMatch(g3["le_q"][:4], np.zeros((0, 32), np.uint8), k=2)
+    assert empty == [[], [], [], []]
+
+
+def test_keyframe_collection_golden(g3):
+    """BFMatcher.add([kf0, kf1, kf2]) ordering incl. a duplicate across keyframes."""
+    from pybot_b200.vision.matcher import BFMatcher
+    bf = BFMatcher()
+    bf.add([g3["kf_0"], g3["kf_1"], g3["kf_2"]])
+    res = bf.knnMatch(g3["kf_q"], k=2)
+    assert [[m.imgIdx for m in r] for r in res] == g3["kf_img"].tolist()
+    assert [[m.trainIdx for m in r] for r in res] == g3["kf_idx"].tolist()
+    assert [[int(m.distance) for m in r] for r in res] == g3["kf_dist"].tolist()
+    assert len(bf.getTrainDescriptors()) == 3
+    bf.clear()
+    assert bf.empty()
+
+
+def test_c1_orb_2000x2000():
+    q, t = syn.orb_pair()
+    idx, dist, valid = _check_against_model(q, t)
+    assert 0.3 < valid.mean() < 0.7          # planted matches survive ratio + mutual
+    pidx, pdist, pr, pm, pv = port.knn_ratio_mutual(q, [t])       # cv2 engine when importable
+    assert np.array_equal(idx, pidx) and np.array_equal(dist, pdist) and np.array_equal(valid, pv)
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 1), (1, 2), (5, 255), (511, 256), (513, 257), (1000, 1025),
+                                   (37, 70001)])
+def test_ragged_sizes(nq, nt):
+    rng = np.random.default_rng(nq * 7919 + nt)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    t[rng.integers(0, nt)] = q[0]
+    _check_against_model(q, t)
+
+
+@pytest.mark.parametrize("variant", ["0", "1"])
+def test_both_popc_variants_agree(variant):
+    """PBK_HAMMING_VARIANT selects 8-POPC vs carry-save 4-POPC scoring: same keys."""
+    import subprocess, sys
+    code = (
+        "import numpy as np, sys; sys.path.insert(0, %r);"
+        "from pybot_b200 import synthetic as syn; from pybot_b200.vision.matcher import knn_ratio_mutual;"
+        "from oracle import model;"
+        "q,t = syn.low_entropy_pair(seed=3, nq=700, nt=3000);"
+        "a = knn_ratio_mutual(q,t); b = model.ratio_mutual(q,t);"
+        "assert all(np.array_equal(np.asarray(x).astype(np.int64), np.asarray(y).astype(np.int64)) for x,y in zip(a,b));"
+        "print('ok')") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PBK_HAMMING_VARIANT=variant)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_database_sized_vs_c_oracle():
+    """2000 queries x 400k rows (200 keyframes): GPU vs the C restatement of
+    BFMatcher (oracle/c), global indices, with planted revisits."""
+    from oracle import c_oracle
+    from pybot_b200.vision.matcher import knn_ratio_mutual
+    q, db = syn.c3_database(nq=2000, n_keyframes=200, per_kf=2000, n_revisit=3)
+    idx, dist, r_ok, m_ok, valid = knn_ratio_mutual(q, db, 0.75)
+    ridx, rdist = c_oracle.hamming_knn2(q, db)
+    assert np.array_equal(idx, ridx) and np.array_equal(dist, rdist)
+    assert valid.sum() > 1000
+
+
+def test_sharded_merge_equals_single_scan():
+    """Split the DB in 3 uneven shards, merge the partial keys: identical to one scan
+    (the multi-GPU path run on one device)."""
+    import torch
+    from pybot_b200 import ops
+    q, db = syn.c3_database(nq=600, n_keyframes=30, per_kf=1000, n_revisit=2)
+    db[12345] = db[777]                           # cross-shard duplicate -> tie on global index
+    qd, dbd = torch.from_numpy(q).cuda(), torch.from_numpy(db).cuda()
+    whole = ops.hamming_knn2_keys(qd, dbd, 0)
+    cuts = [0, 7000, 19000, 30000]
+    parts = torch.stack([ops.hamming_knn2_keys(qd, dbd[a:b], a) for a, b in zip(cuts[:-1], cuts[1:])])
+    merged = ops.hamming_merge(parts)
+    assert torch.equal(whole, merged)
+
+
+def test_full_size_properties_c3_shard():
+    """One 8-GPU shard of C3 (2.5M rows): self-match property - planting each
+    query in the shard must return distance 0 at the planted (lowest) row."""
+    import torch
+    from pybot_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1003)
+    nt, nq = 2_500_000, 2000
+    db = torch.randint(0, 256, (nt, 32), device="cuda", dtype=torch.uint8, generator=g)
+    q = torch.randint(0, 256, (nq, 32), device="cuda", dtype=torch.uint8, generator=g)
+    rows = torch.randperm(nt, device="cuda", generator=g)[:nq]
+    db[rows] = q
+    keys = ops.hamming_knn2_keys(q, db, 5_000_000)
+    assert torch.equal(keys[:, 0] >> 32, torch.zeros(nq, dtype=torch.int64, device="cuda"))
+    assert torch.equal(keys[:, 0] & 0xffffffff, rows + 5_000_000)
+    d2 = keys[:, 1] >> 32
+    assert int(d2.min()) > 60 and int(d2.max()) < 110          # random 256-bit: ~ 85-95
+
+
+def test_popc_probe_runs():
+    from pybot_b200 import ops
+    assert ops.popc_probe(mode=0, ctas=148, iters=10) == 16 * 8 * 10 * 256 * 148

@@ -1,0 +1,179 @@
+"""GPU parity: RigidTransform.__mul__, Sim3, Camera.project."""
+import numpy as np
+import pytest
+
+from oracle import model, port
+from pybot_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+POSES = ("c2", "ident", "big")
+
+
+def _bits_equal(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype, (a.shape, b.shape, a.dtype, b.dtype)
+    na, nb = np.isnan(a), np.isnan(b)
+    assert np.array_equal(na, nb)
+    return np.array_equal(a[~na], b[~nb])
+
+
+@pytest.fixture(scope="module")
+def g2(golden_dir):
+    return np.load(golden_dir + "/g2_transform_project.npz")
+
+
+def _camera(g2, name, D=None):
+    from pybot_b200.vision.camera_utils import Camera, CameraIntrinsic, CameraExtrinsic
+    from pybot_b200.geometry import RigidTransform
+    p = RigidTransform(g2["pose_%s_xyzw" % name], g2["pose_%s_tvec" % name])
+    intr = CameraIntrinsic(g2["K"], shape=syn.KITTI_SHAPE) if D is None else CameraIntrinsic(
+        g2["K"], D=D, shape=syn.KITTI_SHAPE)
+    cam = Camera.from_intrinsics_extrinsics(intr, CameraExtrinsic.from_rigid_transform(p))
+    assert np.array_equal(cam.quat.q, g2["cam_%s_xyzw" % name])
+    assert np.array_equal(cam.tvec, g2["cam_%s_tvec" % name])
+    return cam
+
+
+@pytest.mark.parametrize("name", POSES)
+def test_rigid_transform_mul_matches_reference(g2, name):
+    from pybot_b200.geometry import RigidTransform
+    p = RigidTransform(g2["pose_%s_xyzw" % name], g2["pose_%s_tvec" % name])
+    Y = p * g2["X"]
+    ref = g2["mul_%s" % name]
+    assert Y.dtype == np.float64 and Y.shape == ref.shape
+    # tolerance of the north star: 1e-5 relative (+ abs for cancellation); the
+    # FMA chain mirrors OpenBLAS so it is normally bit-exact
+    np.testing.assert_allclose(Y, ref, rtol=1e-12, atol=1e-12)
+    Y64 = p * g2["X"].astype(np.float64)
+    np.testing.assert_allclose(Y64, g2["mul64_%s" % name], rtol=1e-12, atol=1e-12)
+    Yf = p.transform_points(g2["X"], out_dtype=np.float32)
+    assert Yf.dtype == np.float32
+    np.testing.assert_allclose(Yf, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_transform_ragged_sizes_and_int_input():
+    from pybot_b200.geometry import RigidTransform
+    p = RigidTransform.from_rpyxyz(*syn.C2_RPYXYZ)
+    T = port.rt_matrix(p.quat.q, p.tvec)
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 3, 127, 128, 129, 1023, 1025, 5000):
+        X = rng.normal(size=(n, 3)).astype(np.float32) * 20
+        Y = p * X
+        assert Y.shape == (n, 3)
+        if n:
+            np.testing.assert_allclose(Y, port.rt_mul_points(T, X), rtol=1e-12, atol=1e-12)
+    Xi = rng.integers(-50, 50, (77, 3))
+    np.testing.assert_allclose(p * Xi, port.rt_mul_points(T, Xi), rtol=1e-12, atol=1e-12)
+
+
+def test_sim3_points():
+    from pybot_b200.geometry import Sim3, RigidTransform
+    base = RigidTransform.from_rpyxyz(0.3, -0.4, 1.0, 1.0, -2.0, 0.5)
+    s = Sim3(xyzw=base.xyzw, tvec=base.tvec, scale=2.5)
+    rng = np.random.default_rng(1)
+    X = rng.normal(size=(999, 3)).astype(np.float32)
+    np.testing.assert_allclose(s * X, port.sim3_mul_points(base.xyzw, base.tvec, 2.5, X),
+                               rtol=1e-12, atol=1e-12)
+    # consistent with oplus applied to a translation
+    o = s.oplus(RigidTransform(tvec=X[0]))
+    np.testing.assert_allclose((s * X[:1])[0], o.tvec, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", POSES)
+def test_project_plain_matches_reference(g2, name):
+    cam = _camera(g2, name)
+    x = cam.project(g2["X"])
+    ref = g2["proj_%s" % name]
+    assert x.dtype == np.float32
+    np.testing.assert_allclose(x, ref, rtol=1e-5, atol=1e-4)          # north-star bar
+    assert _bits_equal(x, ref), "expected bit-exact float32 pixels"
+    x64 = cam.project(g2["X"].astype(np.float64))
+    assert x64.dtype == np.float64
+    np.testing.assert_allclose(x64, g2["proj64_%s" % name], rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", POSES)
+def test_project_masks_and_compaction(g2, name):
+    cam = _camera(g2, name)
+    x, d, v = cam.project(g2["X"], check_bounds=True, check_depth=True, return_depth=True,
+                          return_valid=True)
+    assert v.dtype == np.bool_ and d.dtype == np.float64
+    assert np.array_equal(v, g2["projv_%s_v" % name])                 # masks bit-exact
+    assert _bits_equal(x, g2["projv_%s_x" % name])                    # order-preserving compaction
+    np.testing.assert_allclose(d, g2["projv_%s_d" % name], rtol=1e-12, atol=1e-12)
+    x2, v2 = cam.project(g2["X"], check_depth=True, return_valid=True, min_depth=2.0)
+    assert np.array_equal(v2, g2["projd_%s_v" % name])
+    assert _bits_equal(x2, g2["projd_%s_x" % name])
+
+
+def test_project_edge_cases(g2):
+    from pybot_b200.vision.camera_utils import Camera, CameraIntrinsic
+    cam = Camera.from_intrinsics(CameraIntrinsic(g2["K"], shape=syn.KITTI_SHAPE))
+    x = cam.project(g2["edge_X"])
+    assert _bits_equal(x, g2["edge_proj"])
+    x, d, v = cam.project(g2["edge_X"], check_bounds=True, check_depth=True, return_depth=True,
+                          return_valid=True)
+    assert np.array_equal(v, g2["edge_v"])
+    assert _bits_equal(x, g2["edge_x"])
+    np.testing.assert_allclose(d, g2["edge_d"], rtol=1e-12)
+
+
+def test_project_distortion(g2):
+    cam = _camera(g2, "c2", D=g2["dist_D"])
+    x = cam.project(g2["X"])
+    assert _bits_equal(x, g2["dist_proj"])
+
+
+def test_check_bounds_without_shape_raises(g2):
+    from pybot_b200.vision.camera_utils import Camera, CameraIntrinsic
+    cam = Camera.from_intrinsics(CameraIntrinsic(g2["K"]))
+    with pytest.raises(ValueError):
+        cam.project(g2["X"], check_bounds=True)
+
+
+def test_project_vs_oracle_seeded_200k():
+    """C2 distribution at 200k points against the oracle port (cv2 when importable)."""
+    from pybot_b200.vision.camera_utils import Camera, CameraIntrinsic, CameraExtrinsic
+    from pybot_b200.geometry import RigidTransform
+    X = syn.c2_points(n=200_000)
+    p = RigidTransform.from_rpyxyz(*syn.C2_RPYXYZ)
+    K = syn.kitti_K()
+    cam = Camera.from_intrinsics_extrinsics(CameraIntrinsic(K, shape=syn.KITTI_SHAPE),
+                                            CameraExtrinsic.from_rigid_transform(p))
+    got = cam.project(X, check_bounds=True, check_depth=True, return_depth=True, return_valid=True)
+    ref = port.camera_project(K, np.zeros(5), cam.quat.q, cam.tvec, syn.KITTI_SHAPE, X, True, True,
+                              True, True)
+    assert np.array_equal(got[2], ref[2])
+    assert _bits_equal(got[0], ref[0])
+    np.testing.assert_allclose(got[1], ref[1], rtol=1e-12, atol=1e-12)
+    assert 0.70 < got[2].mean() < 0.78                      # 73.7 % in view
+    ref2 = port.camera_project(K, np.zeros(5), cam.quat.q, cam.tvec, syn.KITTI_SHAPE, X, True, True,
+                               True, True, use_cv2=False)    # pure-numpy model of OpenCV
+    assert np.array_equal(got[2], ref2[2]) and _bits_equal(got[0], ref2[0])
+
+
+def test_compaction_full_size_properties():
+    """C2 full size (10M): compaction is order-preserving and complete; checked
+    against the uncompacted output of the same kernel family."""
+    import torch
+    from pybot_b200 import ops
+    from pybot_b200.geometry import RigidTransform
+    g = torch.Generator(device="cuda").manual_seed(1002)
+    n = 10_000_000
+    X = torch.rand((n, 3), device="cuda", generator=g)
+    X[:, 0] = X[:, 0] * 80 - 40
+    X[:, 1] = X[:, 1] * 6 - 3
+    X[:, 2] = X[:, 2] * 78 + 2
+    T = RigidTransform.from_rpyxyz(*syn.C2_RPYXYZ).to_matrix()
+    K = syn.kitti_K()
+    kw = dict(shape=syn.KITTI_SHAPE, check_bounds=True, check_depth=True, return_depth=True,
+              return_valid=True)
+    uv_c, d_c, valid, m = ops.project_points(X, T[:3, :3], T[:3, 3], K, compact=True, **kw)
+    uv_f, d_f, valid2, m2 = ops.project_points(X, T[:3, :3], T[:3, 3], K, compact=False, **kw)
+    assert torch.equal(valid, valid2)
+    assert m == int(valid.sum()) == m2
+    assert uv_c.shape[0] == m
+    assert torch.equal(uv_c, uv_f[valid]) and torch.equal(d_c, d_f[valid])
+    inb = (uv_c[:, 0] >= 0) & (uv_c[:, 0] < 1241) & (uv_c[:, 1] >= 0) & (uv_c[:, 1] < 376)
+    assert bool(inb.all()) and bool((d_c >= 0.1).all())
