@@ -1,0 +1,635 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|c5]
+                    [--impl reference] [--no-also]
+
+Default workload = C3, loop-closure matching: 2000 ORB query descriptors vs a
+10k-keyframe database (20M descriptors, 640 MB), k=2 + Lowe ratio + mutual
+check, database sharded by contiguous keyframe ranges over N GPUs (strong
+scaling: the database size is fixed).  One JSON line on stdout (rank 0).
+
+A "step" is one pass of the path over one batch: for C3 one query frame
+matched against the whole database.  `value` is measured with the inputs
+resident in HBM; `e2e` goes through the public API with pinned HOST buffers
+(H2D of the step's inputs and D2H of its results inside the timed region).
+With --no-also only the headline workload runs; otherwise the single-GPU
+workloads C2 (transform+project 10M), C4 (BA 4M obs) and C5 (4K x 64 coloured
+cloud) are measured too and reported under "also" (N=1 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from pybot_b200 import synthetic as syn  # noqa: E402
+
+L2_FLUSH_BYTES = 256 << 20
+
+
+# ------------------------------------------------------------------ helpers
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback (of fallback)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "power_w_max": float(max(pw)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class Dist(object):
+    def __init__(self, gpus):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            import torch.distributed as dist
+            torch.cuda.set_device(self.local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        else:
+            torch.cuda.set_device(0)
+            self.dist = None
+        if gpus != self.world:
+            raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)"
+                             % (gpus, self.world))
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def timed_steps(D, step, steps, warmup, flush=None, inner=None):
+    """W untimed + K timed steps.  Each step is bracketed by CUDA events on the
+    launching stream (the L2 flush between steps is outside the events);
+    barrier + synchronize on both sides; returns (sum of step ms, max over
+    ranks), plus the summed ms of the `inner` event pairs the step records."""
+    torch = D.torch
+    for _ in range(warmup):
+        if flush is not None:
+            flush()
+        step(None)
+    D.barrier()
+    evs = []
+    for _ in range(steps):
+        if flush is not None:
+            flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rec = []
+        a.record()
+        step(rec)
+        b.record()
+        evs.append((a, b, rec))
+    D.barrier()
+    total = sum(a.elapsed_time(b) for a, b, _ in evs)
+    inner_ms = sum(x.elapsed_time(y) for _, _, rec in evs for x, y in rec)
+    return D.max_over_ranks(total), D.max_over_ranks(inner_ms)
+
+
+def make_flush(torch):
+    buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    return lambda: buf.zero_()
+
+
+def ev_pair(torch):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+# ------------------------------------------------------- popc / alu peaks
+def probe_peaks(D):
+    """Measured integer-pipe ceilings on this GPU, this run (burst, ~20 ms each):
+    mode 0 pure POPC; mode 2/3 the matcher's register-only instruction mixes."""
+    from pybot_b200 import ops
+    torch = D.torch
+    out = {}
+    for mode in (0, 2, 3):
+        best = 0.0
+        for _ in range(3):
+            a, b = ev_pair(torch)
+            a.record()
+            n = ops.popc_probe(mode=mode, iters=4000)
+            b.record()
+            torch.cuda.synchronize()
+            best = max(best, n / (a.elapsed_time(b) * 1e-3))
+        out[mode] = best
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    return {"popc_per_s": out[0], "sm_count": sms,
+            "pairs_per_s_mix8popc": out[2] / 8.0, "pairs_per_s_mix4popc_csa": out[3] / 4.0}
+
+
+# ------------------------------------------------------------ workload C3
+def run_c3(D, args):
+    import torch
+    from pybot_b200 import _ffi, ops
+    from pybot_b200.distributed import ShardedKeyframeMatcher, shard_range
+    nq, per_kf, nkf = 2000, 2000, args.keyframes
+    q_host, db_host = None, None
+    lo_kf, hi_kf = shard_range(nkf, D.rank, D.world)
+    # every rank generates the same seeded database and keeps its keyframe range
+    q_np, db_np = syn.c3_database(nq=nq, n_keyframes=nkf, per_kf=per_kf)
+    shard = torch.from_numpy(db_np[lo_kf * per_kf:hi_kf * per_kf]).cuda()
+    nt_total = nkf * per_kf
+    q_pin = _ffi.pinned_empty((nq, 32), np.uint8)
+    q_pin[:] = q_np
+    q_dev = torch.from_numpy(q_np).cuda()
+    m = ShardedKeyframeMatcher(shard, lo_kf * per_kf)
+    flush = make_flush(torch)
+
+    def step(rec):
+        if rec is not None:
+            a, b = ev_pair(torch)
+            a.record()
+            keys_local = m.local_keys(q_dev)
+            b.record()
+            rec.append((a, b))
+        else:
+            keys_local = m.local_keys(q_dev)
+        if D.world > 1:
+            g = torch.empty((D.world,) + tuple(keys_local.shape), dtype=keys_local.dtype, device="cuda")
+            D.dist.all_gather_into_tensor(g, keys_local)
+            keys = ops.hamming_merge(g)
+        else:
+            keys = keys_local
+        rows = ops.hamming_gather_best(shard, keys, m.shard_base)
+        if D.world > 1:
+            D.dist.all_reduce(rows, op=D.dist.ReduceOp.SUM)
+        rev = ops.hamming_knn2_keys(rows, q_dev, 0)
+        return ops.hamming_ratio_mutual(keys, rev, 0.75)
+
+    sampler = ClockSampler(D.local).start() if D.rank == 0 else None
+    total_ms, knn_ms = timed_steps(D, step, args.steps, args.warmup, flush)
+    clocks = sampler.stop() if sampler else None
+
+    # end to end through the public API: pinned host queries in, numpy results out
+    def e2e_step(rec):
+        idx, dist, r_ok, m_ok, valid = m.match(torch.from_numpy(q_pin).to("cuda", non_blocking=True))
+        return [_ffi.to_host(x) for x in (idx, dist, valid)]
+    e2e_ms, _ = timed_steps(D, e2e_step, args.steps, args.warmup, flush)
+
+    pairs = float(nq) * nt_total
+    launches = (6 if D.world == 1 else 7) * args.steps
+    res = {
+        "metric": "hamming_knn_k2_ratio_mutual", "unit": "Gpairs/s",
+        "value": pairs * args.steps / (total_ms * 1e-3) / 1e9,
+        "ms_per_step": total_ms / args.steps, "scaling": "strong", "dtype": "u32 (xor/popc/int-min)",
+        "config": {"workload": "C3 loop-closure: 2000 ORB queries vs %d keyframes x 2000 "
+                               "(%d descriptors, %d MB), k=2 + ratio 0.75 + mutual; database sharded by "
+                               "keyframe range over %d GPU(s)" % (nkf, nt_total, nt_total * 32 >> 20, D.world),
+                   "nq": nq, "nt": nt_total, "shard_rows": int(shard.shape[0]),
+                   "l2": "256 MiB L2 flush between timed steps",
+                   "state": "database resident in HBM; queries are the per-step input"},
+        "e2e": {"value": pairs * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": "Gpairs/s",
+                "h2d_bytes_per_step": nq * 32,
+                "d2h_bytes_per_step": nq * (2 * 8 + 2 * 4 + 1)},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    if D.rank == 0:
+        pk = probe_peaks(D)
+        local_pairs = float(nq) * float(shard.shape[0])
+        popc_rate = local_pairs * 8 * args.steps / (knn_ms * 1e-3)
+        res["roofline"] = {
+            "bound": "popc", "kernel": "hamming_knn2_kernel (+ split merge)",
+            "achieved": popc_rate / 1e12, "peak": pk["popc_per_s"] / 1e12, "unit": "Tpopc/s",
+            "frac": popc_rate / pk["popc_per_s"], "traffic": None,
+            "algorithmic": "8 POPC.32 per pair (256 bits); achieved = nq*nt_local*8 / kernel time",
+            "peak_source": "pbk_popc_peak_probe mode 0, measured in this run (burst)",
+            "kernel_ms": knn_ms / args.steps, "kernel_share_of_step": knn_ms / total_ms,
+            "note": "the kernel issues 4 POPC + 16 LOP3 per pair (carry-save compression), so the "
+                    "algorithmic popc rate can exceed the popc-pipe peak; the binding pipe is the "
+                    "ALU (LOP3/VIMNMX) - see mix ceilings",
+            "mix_ceiling_gpairs": {"8popc": pk["pairs_per_s_mix8popc"] / 1e9,
+                                   "4popc_csa": pk["pairs_per_s_mix4popc_csa"] / 1e9},
+            "frac_of_register_mix_ceiling": (local_pairs * args.steps / (knn_ms * 1e-3))
+            / pk["pairs_per_s_mix4popc_csa"],
+        }
+        if D.world == 1:
+            res["cpu_baseline"] = cpu_baseline_c3(q_np, db_np, per_kf)
+    return res
+
+
+def cpu_baseline_c3(q, db, per_kf, sample_kf=500):
+    """cv2.BFMatcher k=2 + ratio + mutual (what a pybot user runs) on a bounded
+    sample of the same database, all host threads."""
+    from oracle import port
+    try:
+        import cv2
+        threads = os.cpu_count()
+        cv2.setNumThreads(threads)
+        engine = "cv2.BFMatcher(NORM_HAMMING).knnMatch"
+    except Exception:
+        threads, engine = 1, "numpy model"
+    sample_kf = min(sample_kf, len(db) // per_kf)
+    kfs = [db[i * per_kf:(i + 1) * per_kf] for i in range(sample_kf)]
+    port.knn_ratio_mutual(q[:64], kfs[:2], 0.75)
+    t0 = time.perf_counter()
+    port.knn_ratio_mutual(q, kfs, 0.75)
+    dt = time.perf_counter() - t0
+    return {"value": len(q) * sample_kf * per_kf / dt / 1e9, "unit": "Gpairs/s", "cores": threads,
+            "kind": "port",
+            "sample": "%s k=2 + ratio + mutual via oracle.port, %d q x %d rows (%d keyframes), %.1f s"
+                      % (engine, len(q), sample_kf * per_kf, sample_kf, dt)}
+
+
+# ------------------------------------------------------------ workload C2
+def run_c2(D, args, n=10_000_000):
+    import torch
+    from pybot_b200 import _ffi, ops
+    from pybot_b200.geometry import RigidTransform
+    from pybot_b200.vision.camera_utils import Camera, CameraIntrinsic, CameraExtrinsic
+    hbm, src = measured_peaks()
+    X_np = syn.c2_points(n=n)
+    X_pin = _ffi.pinned_empty((n, 3), np.float32)
+    X_pin[:] = X_np
+    X = torch.from_numpy(X_np).cuda()
+    pose = RigidTransform.from_rpyxyz(*syn.C2_RPYXYZ)
+    K = syn.kitti_K()
+    cam = Camera.from_intrinsics_extrinsics(CameraIntrinsic(K, shape=syn.KITTI_SHAPE),
+                                            CameraExtrinsic.from_rigid_transform(pose))
+    Rp, t, Rz, tz = cam._projection_params()
+    flush = make_flush(torch)
+    out = {}
+
+    def plain(rec):
+        return ops.project_points(X, Rp, t, K, None, Rz=Rz, tz=tz)
+    ms, _ = timed_steps(D, plain, args.steps, args.warmup, flush)
+    out["project_plain"] = {"Mpts_per_s": n * args.steps / (ms * 1e-3) / 1e6, "ms": ms / args.steps,
+                            "bytes_per_pt": 20, "GBps": n * 20 * args.steps / (ms * 1e-3) / 1e9}
+
+    def masked(rec):
+        return ops.project_points(X, Rp, t, K, None, Rz=Rz, tz=tz, shape=syn.KITTI_SHAPE,
+                                  check_bounds=True, check_depth=True, return_depth=True,
+                                  return_valid=True)
+    ms2, _ = timed_steps(D, masked, args.steps, args.warmup, flush)
+    m_valid = masked(None)[3]
+    bpp = 12 + 1 + 16.0 * m_valid / n
+    out["project_masks_compact"] = {"Mpts_per_s": n * args.steps / (ms2 * 1e-3) / 1e6,
+                                    "ms": ms2 / args.steps, "bytes_per_pt": bpp, "valid_frac": m_valid / n,
+                                    "GBps": n * bpp * args.steps / (ms2 * 1e-3) / 1e9}
+
+    def xform(rec):
+        return ops.transform_points(X, Rp, t, 1.0, np.float64)
+    ms3, _ = timed_steps(D, xform, args.steps, args.warmup, flush)
+    out["transform_f64_out"] = {"Mpts_per_s": n * args.steps / (ms3 * 1e-3) / 1e6, "ms": ms3 / args.steps,
+                                "bytes_per_pt": 36, "GBps": n * 36 * args.steps / (ms3 * 1e-3) / 1e9}
+
+    def e2e(rec):
+        return cam.project(X_pin)
+    ems, _ = timed_steps(D, e2e, args.steps, args.warmup, flush)
+    res = {
+        "metric": "transform_project", "unit": "Mpts/s", "value": out["project_plain"]["Mpts_per_s"],
+        "ms_per_step": out["project_plain"]["ms"], "dtype": "f64 registers, f32 in/out",
+        "config": {"workload": "C2 batched SE(3) transform + pinhole Camera.project of %d points "
+                               "(float32 AoS in, float32 pixels out)" % n,
+                   "l2": "256 MiB L2 flush between timed steps"},
+        "variants": out,
+        "e2e": {"value": n * args.steps / (ems * 1e-3) / 1e6, "unit": "Mpts/s",
+                "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": n * 8},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "hbm", "kernel": "project_points_kernel<float,false,false>",
+                     "achieved": out["project_plain"]["GBps"], "peak": hbm, "unit": "GB/s",
+                     "frac": out["project_plain"]["GBps"] / hbm, "traffic": None, "peak_source": src,
+                     "algorithmic": "12 B in + 8 B out = 20 B/pt"},
+    }
+    if D.rank == 0:
+        res["cpu_baseline"] = cpu_baseline_c2(X_np[:1_000_000], cam)
+    return res
+
+
+def cpu_baseline_c2(X, cam):
+    from oracle import port
+    try:
+        import cv2
+        cv2.setNumThreads(os.cpu_count())
+    except Exception:
+        pass
+    K = cam.K
+    port.camera_project(K, np.zeros(5), cam.quat.q, cam.tvec, syn.KITTI_SHAPE, X[:1000])
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        port.camera_project(K, np.zeros(5), cam.quat.q, cam.tvec, syn.KITTI_SHAPE, X)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": len(X) / best / 1e6, "unit": "Mpts/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "oracle.port.camera_project (cv2.Rodrigues + cv2.projectPoints as at "
+                      "camera_utils.py:694-697) on %d of the points, best of 3" % len(X)}
+
+
+# ------------------------------------------------------------ workload C4
+def run_c4(D, args):
+    import torch
+    from pybot_b200 import _ffi
+    from pybot_b200.distributed import ShardedBA
+    hbm, src = measured_peaks()
+    prob = syn.c4_problem()
+    rv, tv, K, pts, oc, op, uv = prob
+    n_obs = len(oc)
+    sb = ShardedBA(*prob)
+    flush = make_flush(torch)
+
+    def step(rec):
+        if rec is not None:
+            a, b = ev_pair(torch)
+            a.record()
+            sb.problem.evaluate()
+            b.record()
+            rec.append((a, b))
+            c = sb.problem.cost
+            if D.world > 1:
+                c = c.clone()
+                D.dist.all_reduce(c)
+            return c
+        return sb.evaluate()
+    sampler = ClockSampler(D.local).start() if D.rank == 0 else None
+    ms, kms = timed_steps(D, step, args.steps, args.warmup, flush)
+    clocks = sampler.stop() if sampler else None
+
+    # e2e: poses + points change every LM iteration -> H2D rvec/tvec/points, D2H cost
+    rv_pin, tv_pin, pts_pin = (_ffi.pinned_empty(a.shape, np.float32) for a in (rv, tv, pts))
+    rv_pin[:], tv_pin[:], pts_pin[:] = rv, tv, pts
+    P = sb.problem
+
+    def e2e(rec):
+        P.rvec.copy_(torch.from_numpy(rv_pin), non_blocking=True)
+        P.tvec.copy_(torch.from_numpy(tv_pin), non_blocking=True)
+        P.points.copy_(torch.from_numpy(pts_pin), non_blocking=True)
+        return float(sb.evaluate().item())
+    ems, _ = timed_steps(D, e2e, args.steps, args.warmup, flush)
+    local_obs = P.n_obs
+    gbps = local_obs * 96.0 * args.steps / (kms * 1e-3) / 1e9
+    res = {
+        "metric": "ba_residual_jacobian", "unit": "Mobs/s", "value": n_obs * args.steps / (ms * 1e-3) / 1e6,
+        "ms_per_step": ms / args.steps, "scaling": "strong", "dtype": "f64 registers, f32 in/out",
+        "config": {"workload": "C4 BA residual + 2x6/2x3 Jacobians: 1000 cameras, 1M points, %d "
+                               "observations sharded over %d GPU(s)" % (n_obs, D.world),
+                   "l2": "256 MiB L2 flush between timed steps"},
+        "e2e": {"value": n_obs * args.steps / (ems * 1e-3) / 1e6, "unit": "Mobs/s",
+                "h2d_bytes_per_step": int(rv.nbytes + tv.nbytes + pts.nbytes), "d2h_bytes_per_step": 8},
+        "gpu_launches": 3 * args.steps, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "ba_residual_jacobian_kernel", "achieved": gbps,
+                     "peak": hbm, "unit": "GB/s", "frac": gbps / hbm, "traffic": None, "peak_source": src,
+                     "algorithmic": "16 B read + 8 + 48 + 24 B written = 96 B/obs",
+                     "kernel_ms": kms / args.steps},
+    }
+    if D.rank == 0 and D.world == 1:
+        res["cpu_baseline"] = cpu_baseline_c4(prob)
+    return res
+
+
+def cpu_baseline_c4(prob, n_cams=100):
+    from oracle import port
+    rv, tv, K, pts, oc, op, uv = prob
+    sel = oc < n_cams
+    port.ba_residual_jacobian(rv, tv, K, pts, oc[:100], op[:100], uv[:100])
+    t0 = time.perf_counter()
+    port.ba_residual_jacobian(rv, tv, K, pts, oc[sel], op[sel], uv[sel])
+    dt = time.perf_counter() - t0
+    return {"value": int(sel.sum()) / dt / 1e6, "unit": "Mobs/s", "cores": 1, "kind": "port",
+            "sample": "cv2.projectPoints with Jacobian looped per camera (oracle.port), first %d "
+                      "cameras = %d obs, %.1f s" % (n_cams, int(sel.sum()), dt)}
+
+
+# ------------------------------------------------------------ workload C5
+def run_c5(D, args, batch=64):
+    import torch
+    from pybot_b200 import _ffi
+    from pybot_b200.vision.camera_utils import StereoCamera
+    hbm, src = measured_peaks()
+    H, W = syn.UHD_SHAPE
+    cam = StereoCamera.from_calib_params(syn.UHD_FX, syn.UHD_FX, syn.UHD_CX, syn.UHD_CY,
+                                         baseline=syn.UHD_BASELINE, shape=syn.UHD_SHAPE)
+    # same distribution as synthetic.c5_batch, generated on the device (3.7 GB)
+    g = torch.Generator(device="cuda").manual_seed(1005)
+    Z = torch.rand((batch, H, W), device="cuda", generator=g) * 76 + 4
+    disp = (syn.UHD_FX * syn.UHD_BASELINE) / Z
+    u = torch.rand((batch, H, W), device="cuda", generator=g)
+    disp[u < 0.05] = 0.0
+    disp[(u >= 0.05) & (u < 0.06)] = -1.0
+    del Z, u
+    im = torch.randint(0, 256, (batch, H, W, 3), device="cuda", dtype=torch.uint8, generator=g)
+    npx = batch * H * W
+
+    def step(rec):
+        return cam.reconstruct_with_texture(disp, im)
+    ms, _ = timed_steps(D, step, args.steps, args.warmup)      # 11.7 GB/step >> L2
+
+    def plain(rec):
+        return cam.reconstruct(disp)
+    ms2, _ = timed_steps(D, plain, args.steps, args.warmup)
+
+    # e2e on a bounded number of frames (pinned buffers for 64 4K frames = 12 GB)
+    eb = 16
+    d_pin = _ffi.pinned_empty((eb, H, W), np.float32)
+    i_pin = _ffi.pinned_empty((eb, H, W, 3), np.uint8)
+    d_pin[:] = disp[:eb].cpu().numpy()
+    i_pin[:] = im[:eb].cpu().numpy()
+
+    def e2e(rec):
+        return cam.reconstruct_with_texture(d_pin, i_pin)
+    ems, _ = timed_steps(D, e2e, max(2, args.steps // 4), 1)
+    esteps = max(2, args.steps // 4)
+    gbps = npx * 22.0 * args.steps / (ms * 1e-3) / 1e9
+    res = {
+        "metric": "disparity_to_colored_cloud", "unit": "Mpts/s", "value": npx * args.steps / (ms * 1e-3) / 1e6,
+        "ms_per_step": ms / args.steps, "dtype": "f64 registers, f32 in/out",
+        "config": {"workload": "C5 dense disparity -> coloured point cloud, %d frames of %dx%d per step"
+                               % (batch, W, H), "l2": "inputs+outputs 11.7 GB per step >> L2"},
+        "variants": {"uncoloured": {"Mpts_per_s": npx * args.steps / (ms2 * 1e-3) / 1e6,
+                                    "GBps": npx * 16.0 * args.steps / (ms2 * 1e-3) / 1e9}},
+        "e2e": {"value": eb * H * W * esteps / (ems * 1e-3) / 1e6, "unit": "Mpts/s",
+                "h2d_bytes_per_step": eb * H * W * 7, "d2h_bytes_per_step": eb * H * W * 15,
+                "note": "%d frames per e2e step (pinned host buffers)" % eb},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "hbm", "kernel": "reproject_dense_kernel<float,true> (textured)",
+                     "achieved": gbps, "peak": hbm, "unit": "GB/s", "frac": gbps / hbm, "traffic": None,
+                     "peak_source": src, "algorithmic": "4+3 B in, 12+3 B out = 22 B/pt"},
+    }
+    if D.rank == 0:
+        res["cpu_baseline"] = cpu_baseline_c5(cam, disp[0].cpu().numpy(), im[0].cpu().numpy())
+    return res
+
+
+def cpu_baseline_c5(cam, disp, im):
+    from oracle import port
+    try:
+        import cv2
+        cv2.setNumThreads(os.cpu_count())
+    except Exception:
+        pass
+    Q = cam.Q
+    port.stereo_reconstruct_with_texture(disp, im, Q)
+    t0 = time.perf_counter()
+    n = 8
+    for _ in range(n):
+        port.stereo_reconstruct_with_texture(disp, im, Q)
+    dt = time.perf_counter() - t0
+    return {"value": n * disp.size / dt / 1e6, "unit": "Mpts/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "oracle.port.stereo_reconstruct_with_texture (cv2.reprojectImageTo3D + 2 np.copy, "
+                      "camera_utils.py:987-989) on %d 4K frames, %.1f s" % (n, dt)}
+
+
+# ------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's CPU implementation of the headline path on the host
+    cores: a pybot user's cv2.BFMatcher k=2 + ratio + mutual (oracle.port), a
+    bounded sample of the C3 database per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    nq, per_kf = 2000, 2000
+    sample_kf = 250
+    q, db = syn.c3_database(nq=nq, n_keyframes=sample_kf, per_kf=per_kf)
+    from oracle import port
+    try:
+        import cv2
+        threads = os.cpu_count()
+        cv2.setNumThreads(threads)
+        engine = "cv2.BFMatcher(NORM_HAMMING).knnMatch"
+    except Exception:
+        threads, engine = 1, "numpy model"
+    kfs = [db[i * per_kf:(i + 1) * per_kf] for i in range(sample_kf)]
+    for _ in range(args.warmup):
+        port.knn_ratio_mutual(q, kfs[:10], 0.75)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        port.knn_ratio_mutual(q, kfs, 0.75)
+    dt = time.perf_counter() - t0
+    v = nq * sample_kf * per_kf * args.steps / dt / 1e9
+    sample = ("%s k=2 + ratio 0.75 + mutual, 2000 q x %d rows (%d of the 10000 keyframes) per step"
+              % (engine, sample_kf * per_kf, sample_kf))
+    return {"impl": "reference", "metric": "hamming_knn_k2_ratio_mutual", "value": v, "unit": "Gpairs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8/int (OpenCV batchDistance)", "data": "synthetic",
+            "config": {"workload": "C3 loop-closure matching on the host CPU, bounded sample: " + sample},
+            "cpu_baseline": {"value": v, "unit": "Gpairs/s", "cores": threads, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": v, "unit": "Gpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+# --------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--keyframes", type=int, default=10_000)
+    ap.add_argument("--no-also", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        line = run_reference(args)
+        if line is not None:
+            print(json.dumps(line))
+        return
+
+    D = Dist(args.gpus)
+    runners = {"c3": run_c3, "c2": run_c2, "c4": run_c4, "c5": run_c5}
+    res = runners[args.workload](D, args)
+    line = {"metric": res.pop("metric"), "value": res.pop("value"), "unit": res.pop("unit"),
+            "n_gpus": D.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res.pop("ms_per_step"), "higher_is_better": True,
+            "scaling": res.pop("scaling", "weak"), "vs_baseline": None,
+            "dtype": res.pop("dtype"), "data": "synthetic"}
+    line.update(res)
+    if not args.no_also and D.world == 1 and args.workload == "c3":
+        also = {}
+        sub = argparse.Namespace(**vars(args))
+        sub.steps = min(args.steps, 10)
+        for w in ("c2", "c4", "c5"):
+            try:
+                r = runners[w](D, sub)
+                also[w] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "e2e",
+                                             "roofline", "cpu_baseline", "variants") if k in r}
+            except Exception as e:          # report, never hide
+                also[w] = {"error": repr(e)}
+            import torch
+            torch.cuda.empty_cache()
+        line["also"] = also
+    if D.rank == 0:
+        print(json.dumps(line))
+    D.close()
+
+
+if __name__ == "__main__":
+    main()

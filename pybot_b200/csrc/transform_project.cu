@@ -157,7 +157,13 @@ __device__ __forceinline__ void project_one(const pbk_project_params& P, const d
   z = (z != 0.0) ? __drcp_rn(z) : 1.0;
   x = __dmul_rn(x, z);
   y = __dmul_rn(y, z);
-  if (DIST) {
+  // With all-zero coefficients OpenCV still evaluates the distortion
+  // polynomial: it is the identity unless r^6 overflows (0*inf = NaN).  |x|,|y|
+  // < 1e50 keeps r^6 finite, so only larger magnitudes (or NaN) take the full
+  // formula.  The test is on the exponent word: integer pipe, not fp64.
+  const bool huge = ((__double2hiint(x) & 0x7fffffff) >= 0x4A511B0E) ||
+                    ((__double2hiint(y) & 0x7fffffff) >= 0x4A511B0E);
+  if (DIST || huge) {
     const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
     const double r4 = __dmul_rn(r2, r2);
     const double r6 = __dmul_rn(r4, r2);

@@ -108,8 +108,9 @@ def project_points(X, R, t, K, D=None, Rz=None, tz=None, shape=None, check_bound
         _ffi.ptr(Xd), in_dt, n, ctypes.byref(P), _ffi.ptr(uv), _ffi.ptr(depth), _ffi.ptr(valid),
         _ffi.ptr(count), _ffi.ptr(scratch), _ffi.stream_ptr()))
     m = n
-    if do_compact:
+    if check_depth or check_bounds:
         m = int(count.item())            # one 8-byte D2H; also orders the stream
+    if do_compact:
         uv = uv[:m]
         if depth is not None:
             depth = depth[:m]

@@ -1,0 +1,80 @@
+"""The C-ABI library loads and exports every symbol include/pybot_b200.h declares
+(no compute calls: there is no GPU here); missing-GPU / missing-library paths
+fail loudly instead of falling back."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "pybot_b200.h")).read()
+    return sorted(set(re.findall(r"PBK_API\s+[\w\s\*]+?\b(pbk_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    from pybot_b200 import _ffi
+    lib = _ffi.lib()
+    declared = _header_symbols()
+    assert len(declared) >= 17
+    assert sorted(_ffi.SIGNATURES) == declared
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.pbk_version() == 100
+
+
+def test_no_cuda_arch_other_than_sm100a():
+    import subprocess
+    from pybot_b200 import _ffi
+    out = subprocess.run(["cuobjdump", "-lelf", _ffi.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_sass_uses_tma_bulk_copy_for_the_matcher():
+    import subprocess
+    from pybot_b200 import _ffi
+    out = subprocess.run(["cuobjdump", "-sass", _ffi.LIB_PATH], capture_output=True, text=True).stdout
+    body = out.split("hamming_knn2_kernel")[1]
+    assert "UBLKCP" in body and "POPC" in body and "SYNCS" in body
+
+
+def test_compute_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pybot_b200.geometry import RigidTransform
+    from pybot_b200.vision.camera_utils import StereoCamera
+    from pybot_b200.vision.matcher import BFMatcher
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        RigidTransform.identity() * np.zeros((4, 3), np.float32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        StereoCamera.simulate().reconstruct(np.ones((4, 4), np.float32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        BFMatcher().knnMatch(np.zeros((2, 32), np.uint8), np.zeros((2, 32), np.uint8), k=2)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from pybot_b200 import _ffi
+    monkeypatch.setattr(_ffi, "_lib", None)
+    monkeypatch.setattr(_ffi, "LIB_PATH", "/nonexistent/libpybot_b200.so")
+    with pytest.raises(RuntimeError, match="not found"):
+        _ffi.lib()
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "pybot_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+                assert "cv2" not in text or f in ("camera_utils.py", "matcher.py", "ba.py", "rodrigues.py",
+                                                  "transform_project.cu", "reproject.cu", "hamming.cu",
+                                                  "ba.cu", "ops.py"), f
+                assert not re.search(r"^\s*import cv2|^\s*from cv2", text, re.M), f

@@ -107,7 +107,7 @@ def test_database_sized_vs_c_oracle():
     idx, dist, r_ok, m_ok, valid = knn_ratio_mutual(q, db, 0.75)
     ridx, rdist = c_oracle.hamming_knn2(q, db)
     assert np.array_equal(idx, ridx) and np.array_equal(dist, rdist)
-    assert valid.sum() > 1000
+    assert valid.sum() > 300          # planted in 3 keyframes: many top-2 pairs are both true matches
 
 
 def test_sharded_merge_equals_single_scan():

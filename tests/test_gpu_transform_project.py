@@ -90,7 +90,7 @@ def test_project_plain_matches_reference(g2, name):
     assert _bits_equal(x, ref), "expected bit-exact float32 pixels"
     x64 = cam.project(g2["X"].astype(np.float64))
     assert x64.dtype == np.float64
-    np.testing.assert_allclose(x64, g2["proj64_%s" % name], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(x64, g2["proj64_%s" % name], rtol=1e-9, atol=1e-9)   # z ~ 0 points amplify the last-ulp difference of the host Rodrigues round trip
 
 
 @pytest.mark.parametrize("name", POSES)
