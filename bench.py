@@ -174,22 +174,25 @@ def ev_pair(torch):
 
 # ------------------------------------------------------- popc / alu peaks
 def probe_peaks(D):
-    """Measured integer-pipe ceilings on this GPU, this run (burst, ~20 ms each):
-    mode 0 pure POPC; mode 2/3 the matcher's register-only instruction mixes."""
+    """Measured integer-pipe ceilings on this GPU, in this run (burst, ~20 ms
+    each): mode 0 = pure POPC chains -> popc-pipe peak; modes 2 / 3 = the
+    matcher's own inner loop (8-POPC / carry-save 4-POPC) over a resident
+    shared-memory tile with 4 CTAs per SM and no global traffic -> the
+    instruction-mix ceiling of the kernel."""
     from pybot_b200 import ops
     torch = D.torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
     out = {}
-    for mode in (0, 2, 3):
+    for mode, ctas, iters in ((0, sms * 8, 4000), (2, sms * 4, 100), (3, sms * 4, 200)):
         best = 0.0
         for _ in range(3):
             a, b = ev_pair(torch)
             a.record()
-            n = ops.popc_probe(mode=mode, iters=4000)
+            n = ops.popc_probe(mode=mode, ctas=ctas, iters=iters)
             b.record()
             torch.cuda.synchronize()
             best = max(best, n / (a.elapsed_time(b) * 1e-3))
         out[mode] = best
-    sms = torch.cuda.get_device_properties(0).multi_processor_count
     return {"popc_per_s": out[0], "sm_count": sms,
             "pairs_per_s_mix8popc": out[2] / 8.0, "pairs_per_s_mix4popc_csa": out[3] / 4.0}
 
@@ -272,9 +275,10 @@ def run_c3(D, args):
             "algorithmic": "8 POPC.32 per pair (256 bits); achieved = nq*nt_local*8 / kernel time",
             "peak_source": "pbk_popc_peak_probe mode 0, measured in this run (burst)",
             "kernel_ms": knn_ms / args.steps, "kernel_share_of_step": knn_ms / total_ms,
-            "note": "the kernel issues 4 POPC + 16 LOP3 per pair (carry-save compression), so the "
-                    "algorithmic popc rate can exceed the popc-pipe peak; the binding pipe is the "
-                    "ALU (LOP3/VIMNMX) - see mix ceilings",
+            "note": "the kernel issues 4 POPC + 13 LOP3 + 3 VIMNMX per pair (carry-save compression of "
+                    "the 8 words), so the algorithmic popc rate can exceed the popc-pipe peak; ALU and "
+                    "POPC pipes are both ~0.25 clk/pair/SM - see mix ceilings (same inner loop on a "
+                    "resident smem tile)",
             "mix_ceiling_gpairs": {"8popc": pk["pairs_per_s_mix8popc"] / 1e9,
                                    "4popc_csa": pk["pairs_per_s_mix4popc_csa"] / 1e9},
             "frac_of_register_mix_ceiling": (local_pairs * args.steps / (knn_ms * 1e-3))
@@ -327,25 +331,30 @@ def run_c2(D, args, n=10_000_000):
     flush = make_flush(torch)
     out = {}
 
+    pr_plain = ops.Projector(Rp, t, K, None, Rz=Rz, tz=tz)
+
     def plain(rec):
-        return ops.project_points(X, Rp, t, K, None, Rz=Rz, tz=tz)
+        return pr_plain.run(X)
     ms, _ = timed_steps(D, plain, args.steps, args.warmup, flush)
     out["project_plain"] = {"Mpts_per_s": n * args.steps / (ms * 1e-3) / 1e6, "ms": ms / args.steps,
                             "bytes_per_pt": 20, "GBps": n * 20 * args.steps / (ms * 1e-3) / 1e9}
 
+    pr_mask = ops.Projector(Rp, t, K, None, Rz=Rz, tz=tz, shape=syn.KITTI_SHAPE, check_bounds=True,
+                            check_depth=True, return_depth=True, return_valid=True)
+
     def masked(rec):
-        return ops.project_points(X, Rp, t, K, None, Rz=Rz, tz=tz, shape=syn.KITTI_SHAPE,
-                                  check_bounds=True, check_depth=True, return_depth=True,
-                                  return_valid=True)
+        return pr_mask.run(X)
     ms2, _ = timed_steps(D, masked, args.steps, args.warmup, flush)
-    m_valid = masked(None)[3]
+    m_valid = int(masked(None)[3].item())
     bpp = 12 + 1 + 16.0 * m_valid / n
     out["project_masks_compact"] = {"Mpts_per_s": n * args.steps / (ms2 * 1e-3) / 1e6,
                                     "ms": ms2 / args.steps, "bytes_per_pt": bpp, "valid_frac": m_valid / n,
                                     "GBps": n * bpp * args.steps / (ms2 * 1e-3) / 1e9}
 
+    Y64 = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+
     def xform(rec):
-        return ops.transform_points(X, Rp, t, 1.0, np.float64)
+        return ops.transform_points(X, Rp, t, 1.0, np.float64, out=Y64)
     ms3, _ = timed_steps(D, xform, args.steps, args.warmup, flush)
     out["transform_f64_out"] = {"Mpts_per_s": n * args.steps / (ms3 * 1e-3) / 1e6, "ms": ms3 / args.steps,
                                 "bytes_per_pt": 36, "GBps": n * 36 * args.steps / (ms3 * 1e-3) / 1e9}

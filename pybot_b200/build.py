@@ -22,6 +22,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "--expt-relaxed-constexpr",
+    "-diag-suppress", "128",
     "-cudart", "static",
 ]
 

@@ -10,9 +10,10 @@
 // Two kernels.  ba_camera_precompute turns each rvec into R (9) and dR/dr (27)
 // by OpenCV's Rodrigues closed form (one thread per camera, fp64).  The
 // streaming kernel is HBM-write-bound: 16 B read + 80 B written per
-// observation; cameras (320 B each) and points (12 B each) are gathered through
-// L1/L2.  One warp owns 32 observations: the 16 B observation records load
-// coalesced, fp64 math in registers, J_cam / J_pt rows are transposed through a
+// observation; points (12 B each) are gathered through L2 one tile ahead and the
+// warp's camera block (320 B) is cached in shared memory.  One warp owns 32
+// observations: the 16 B observation records load coalesced (prefetched two
+// tiles ahead), fp64 math in registers, J_cam / J_pt rows are transposed through a
 // warp-private shared-memory stage so global stores are coalesced 16 B, and
 // sum ||r||^2 is reduced warp -> CTA -> one fp64 partial per CTA, summed in
 // fixed order by a second tiny kernel (deterministic, no atomics).
@@ -82,76 +83,110 @@ struct BaParams {
   double fx, fy, cx, cy;
 };
 
-__global__ void __launch_bounds__(kBaWarps * 32)
+__device__ __forceinline__ uint4 ba_load_obs(const BaParams& P, long long i) {
+  return i < P.n_obs ? ld_stream_u4(P.obs + i) : make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ int ba_clamp_pt(const BaParams& P, uint32_t raw) {
+  const int pt = (int)raw;      // out-of-range indices are clamped (the wrapper validates them)
+  return pt < 0 ? 0 : ((long long)pt >= P.n_points ? (int)(P.n_points - 1) : pt);
+}
+
+__global__ void __launch_bounds__(kBaWarps * 32, 3)
 ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
   __shared__ __align__(16) float stage[kBaWarps][32 * 18];   // 12 (Jc) + 6 (Jp) floats per obs
+  __shared__ __align__(16) double cam_cache[kBaWarps][kCam]; // the warp's current camera block
   __shared__ double warp_cost[kBaWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* st = stage[warp];
+  const double* C = cam_cache[warp];
   const long long ntiles = (P.n_obs + 31) / 32;
   const long long stride = (long long)gridDim.x * kBaWarps;
   double cost = 0.0;
+  int cached_cam = -1;
 
-  for (long long tile = (long long)blockIdx.x * kBaWarps + warp; tile < ntiles; tile += stride) {
+  // software pipeline: the observation record is fetched two tiles ahead and
+  // the point one tile ahead, so the DRAM latency of the 16 B record and the
+  // L2 latency of the dependent gather overlap with the fp64 math.
+  long long tile = (long long)blockIdx.x * kBaWarps + warp;
+  uint4 ob = ba_load_obs(P, tile * 32 + lane);
+  uint4 ob_n = ba_load_obs(P, (tile + stride) * 32 + lane);
+  float px, py, pz;
+  {
+    const float* pp = P.points + 3ll * ba_clamp_pt(P, ob.y);
+    px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2);
+  }
+
+  for (; tile < ntiles; tile += stride) {
     const long long i = tile * 32 + lane;
     const bool live = i < P.n_obs;
-    float jc[12], jp[6];
+    const uint4 ob_nn = ba_load_obs(P, (tile + 2 * stride) * 32 + lane);
+    float pxn, pyn, pzn;
+    {
+      const float* pp = P.points + 3ll * ba_clamp_pt(P, ob_n.y);
+      pxn = __ldg(pp); pyn = __ldg(pp + 1); pzn = __ldg(pp + 2);
+    }
+    int cam = (int)ob.x;
+    cam = cam < 0 ? 0 : (cam >= P.n_cams ? P.n_cams - 1 : cam);
+    const double uo = (double)__uint_as_float(ob.z), vo = (double)__uint_as_float(ob.w);
+    const double X = (double)px, Y = (double)py, Z = (double)pz;
     float2 res = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < 12; ++k) jc[k] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) jp[k] = 0.f;
-    if (live) {
-      const uint4 ob = ld_stream_u4(P.obs + i);
-      int cam = (int)ob.x, pt = (int)ob.y;
-      // out-of-range indices are clamped (the wrapper validates them)
-      cam = cam < 0 ? 0 : (cam >= P.n_cams ? P.n_cams - 1 : cam);
-      pt = pt < 0 ? 0 : ((long long)pt >= P.n_points ? (int)(P.n_points - 1) : pt);
-      const double uo = (double)__uint_as_float(ob.z), vo = (double)__uint_as_float(ob.w);
-      const float* pp = P.points + 3ll * pt;
-      const double X = (double)__ldg(pp), Y = (double)__ldg(pp + 1), Z = (double)__ldg(pp + 2);
-      const double* cb = P.cams + (long long)cam * kCam;
-      double R[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) R[k] = __ldg(cb + k);
-      const double xc = fma(R[0], X, fma(R[1], Y, fma(R[2], Z, __ldg(cb + 9))));
-      const double yc = fma(R[3], X, fma(R[4], Y, fma(R[5], Z, __ldg(cb + 10))));
-      const double zc = fma(R[6], X, fma(R[7], Y, fma(R[8], Z, __ldg(cb + 11))));
-      const double iz = (zc != 0.0) ? 1.0 / zc : 1.0;
-      const double x = xc * iz, y = yc * iz;
-      const double ru = fma(P.fx, x, P.cx) - uo;
-      const double rv = fma(P.fy, y, P.cy) - vo;
-      res = make_float2((float)ru, (float)rv);
-      cost = fma(ru, ru, fma(rv, rv, cost));
-      // J_t = [[a, 0, b], [0, c, d]]
-      const double a = P.fx * iz, b = -P.fx * x * iz;
-      const double c = P.fy * iz, d = -P.fy * y * iz;
-      jc[3] = (float)a;  jc[4] = 0.f;       jc[5] = (float)b;
-      jc[9] = 0.f;       jc[10] = (float)c; jc[11] = (float)d;
-#pragma unroll
-      for (int m = 0; m < 3; ++m) {
-        // d(R X)/d r_m : rows 0..2 of (dR/dr_m) X
-        const double* Jm = cb + 12 + 9 * m;
-        const double g0 = fma(__ldg(Jm + 0), X, fma(__ldg(Jm + 1), Y, __ldg(Jm + 2) * Z));
-        const double g1 = fma(__ldg(Jm + 3), X, fma(__ldg(Jm + 4), Y, __ldg(Jm + 5) * Z));
-        const double g2 = fma(__ldg(Jm + 6), X, fma(__ldg(Jm + 7), Y, __ldg(Jm + 8) * Z));
-        jc[m] = (float)fma(a, g0, b * g2);
-        jc[6 + m] = (float)fma(c, g1, d * g2);
-        jp[m] = (float)fma(a, R[m], b * R[6 + m]);
-        jp[3 + m] = (float)fma(c, R[3 + m], d * R[6 + m]);
+    float4* s4 = reinterpret_cast<float4*>(st);
+    float2* s2 = reinterpret_cast<float2*>(st + 384);
+
+    // Observations are sorted by camera in practice, so a warp's 32 records
+    // normally share one camera: its 320 B block is staged in shared memory
+    // once and read by broadcast LDS at the point of use (no registers pinned,
+    // no per-record global gathers).  A tile that straddles cameras takes one
+    // pass per distinct camera.
+    unsigned todo = 0xffffffffu;
+    while (todo) {
+      const int c = __shfl_sync(0xffffffffu, cam, __ffs(todo) - 1);
+      const bool mine = (cam == c) && ((todo >> lane) & 1u);
+      if (c != cached_cam) {
+        __syncwarp();
+        if (lane < kCam / 2)
+          reinterpret_cast<double2*>(cam_cache[warp])[lane] =
+              __ldg(reinterpret_cast<const double2*>(P.cams + (long long)c * kCam) + lane);
+        cached_cam = c;
+        __syncwarp();
       }
+      if (mine) {
+        const double xc = fma(C[0], X, fma(C[1], Y, fma(C[2], Z, C[9])));
+        const double yc = fma(C[3], X, fma(C[4], Y, fma(C[5], Z, C[10])));
+        const double zc = fma(C[6], X, fma(C[7], Y, fma(C[8], Z, C[11])));
+        const double iz = (zc != 0.0) ? 1.0 / zc : 1.0;
+        const double x = xc * iz, y = yc * iz;
+        const double ru = fma(P.fx, x, P.cx) - uo;
+        const double rv = fma(P.fy, y, P.cy) - vo;
+        if (live) {
+          res = make_float2((float)ru, (float)rv);
+          cost = fma(ru, ru, fma(rv, rv, cost));
+        }
+        // J_t = [[a, 0, b], [0, c, d]]
+        const double a = P.fx * iz, b = -P.fx * x * iz;
+        const double cc = P.fy * iz, d = -P.fy * y * iz;
+        float jr[6];                                     // d/drvec: [row u | row v]
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          // d(R X)/d r_m = (dR/dr_m) X
+          const double* Jm = C + 12 + 9 * m;
+          const double g0 = fma(Jm[0], X, fma(Jm[1], Y, Jm[2] * Z));
+          const double g1 = fma(Jm[3], X, fma(Jm[4], Y, Jm[5] * Z));
+          const double g2 = fma(Jm[6], X, fma(Jm[7], Y, Jm[8] * Z));
+          jr[m] = (float)fma(a, g0, b * g2);
+          jr[3 + m] = (float)fma(cc, g1, d * g2);
+        }
+        // stage: Jc rows at [lane*12, +12), Jp rows at [384 + lane*6, +6)
+        s4[lane * 3 + 0] = make_float4(jr[0], jr[1], jr[2], (float)a);
+        s4[lane * 3 + 1] = make_float4(0.f, (float)b, jr[3], jr[4]);
+        s4[lane * 3 + 2] = make_float4(jr[5], 0.f, (float)cc, (float)d);
+        s2[lane * 3 + 0] = make_float2((float)fma(a, C[0], b * C[6]), (float)fma(a, C[1], b * C[7]));
+        s2[lane * 3 + 1] = make_float2((float)fma(a, C[2], b * C[8]), (float)fma(cc, C[3], d * C[6]));
+        s2[lane * 3 + 2] = make_float2((float)fma(cc, C[4], d * C[7]), (float)fma(cc, C[5], d * C[8]));
+      }
+      todo &= ~__ballot_sync(0xffffffffu, mine);
     }
     if (P.r != nullptr && live) st_stream_f2(P.r + 2 * i, res);
-
-    // stage: Jc rows at [lane*12, +12), Jp rows at [384 + lane*6, +6)
-    float4* s4 = reinterpret_cast<float4*>(st);
-    s4[lane * 3 + 0] = make_float4(jc[0], jc[1], jc[2], jc[3]);
-    s4[lane * 3 + 1] = make_float4(jc[4], jc[5], jc[6], jc[7]);
-    s4[lane * 3 + 2] = make_float4(jc[8], jc[9], jc[10], jc[11]);
-    float2* s2 = reinterpret_cast<float2*>(st + 384);
-    s2[lane * 3 + 0] = make_float2(jp[0], jp[1]);
-    s2[lane * 3 + 1] = make_float2(jp[2], jp[3]);
-    s2[lane * 3 + 2] = make_float2(jp[4], jp[5]);
     __syncwarp();
     const long long o0 = tile * 32;
     const int nlive = (int)((P.n_obs - o0) < 32 ? (P.n_obs - o0) : 32);
@@ -178,6 +213,8 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
       }
     }
     __syncwarp();
+    ob = ob_n; ob_n = ob_nn;
+    px = pxn; py = pyn; pz = pzn;
   }
 
   // cost: warp -> CTA -> partial
@@ -204,7 +241,7 @@ __global__ void ba_cost_sum_kernel(const double* __restrict__ partials, int n, d
 
 static int ba_grid(const DeviceInfo* di, long long n_obs) {
   const long long ntiles = (n_obs + 31) / 32;
-  return stream_grid(di, (ntiles + kBaWarps - 1) / kBaWarps, 4);
+  return resident_grid(di, ba_residual_jacobian_kernel, kBaWarps * 32, 0, (ntiles + kBaWarps - 1) / kBaWarps);
 }
 
 }  // namespace pbk

@@ -16,11 +16,16 @@
 //    UBLKCP) that complete on mbarriers; the query tile is staged the same way.
 //  * every lane reads the same train row (broadcast LDS.128 x2) and scores
 //    it against its 4 queries: XOR (LOP3) + POPC + integer adds.
-//    VARIANT 1 compresses the eight 32-bit words with carry-save adders
-//    (LOP3 full adders) so only 4 POPC per pair are issued instead of 8 -
-//    the popc pipe is the narrow one (16 lanes/clk/SM vs 64 for LOP3).
+//    VARIANT 0 is the textbook 8 XOR + 8 POPC.  VARIANT 1 (default) compresses
+//    the eight words with carry-save adders (LOP3 full adders) so only 4 POPC
+//    per pair are issued - the popc pipe is the narrow one (16 lanes/clk/SM vs
+//    64 for LOP3).  To keep the LOP3 count at 13 per pair, each staged train
+//    row is rewritten in shared memory (once per CTA, amortised over 512
+//    queries) to [t0 t1 t3 t4 t7 | t0^t1^t2 | t3^t4^t5 | t0^..^t6] and every
+//    query is held in the same derived form: a full adder's sum bit is then one
+//    XOR of precomputed words and its carry is maj(x, y, x^y^sum) - one LOP3.
 //  * top-2 selection is a 3-instruction min/max network on a packed 32-bit key
-//    (distance << 23 | local row): rows are scanned in ascending order and the
+//    (distance * (2^23+1) + local row): rows are scanned in ascending order and the
 //    key order is lexicographic, so ties resolve to the lowest train index.
 //  * each CTA emits (distance << 32 | global row) u64 keys per query; a merge
 //    kernel reduces the splits (and, multi-GPU, the all-gathered shards) with
@@ -36,6 +41,10 @@ constexpr int kTR = 256;                        // train rows per stage
 constexpr int kStages = 4;
 constexpr int kStageBytes = kTR * 32;
 constexpr int kKeyShift = 23;                   // local row index < 2^23
+// packed key = distance * kKeyMul + local_row.  An odd multiplier (not a power of
+// two) keeps the key build on the FMA pipe as IMAD; a shift would be an ALU LEA
+// and the ALU pipe is the binding one.
+constexpr uint32_t kKeyMul = (1u << kKeyShift) + 1u;
 constexpr uint32_t kLocalNone = 0xFFFFFFFFu;
 constexpr long long kMaxSplitRows = 1ll << kKeyShift;
 
@@ -49,36 +58,6 @@ struct HammingParams {
   int splits;
 };
 
-// ------------------------------------------------------------ TMA / mbarrier
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completing `bytes` on `bar`.
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-
 // ------------------------------------------------------------------ scoring
 __device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t r;
@@ -91,21 +70,47 @@ __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
   return r;
 }
 
-// Hamming distance of two 256-bit rows held as 8 words each.
+// carry of a full adder given two inputs and the SUM bit: maj(a, b, a^b^s)
+__device__ __forceinline__ uint32_t carry_from_sum(uint32_t a, uint32_t b, uint32_t s) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xD4;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
+  return r;
+}
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;       // keeps the weighted popc sum on the FMA pipe (IMAD), off the ALU pipe
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
+// derived 8-word form of a descriptor (VARIANT 1): [w0 w1 w3 w4 | w7 Sa Sb Sabc]
+__device__ __forceinline__ void derive_row(uint4& a, uint4& b) {
+  const uint32_t sa = xor3(a.x, a.y, a.z), sb = xor3(a.w, b.x, b.y);
+  const uint32_t sabc = xor3(sa, sb, b.z);
+  a = make_uint4(a.x, a.y, a.w, b.x);
+  b = make_uint4(b.w, sa, sb, sabc);
+}
+
+// packed key (distance << 23) + rowkey of one query against one train row
 template <int VARIANT>
-__device__ __forceinline__ uint32_t hamming256(const uint32_t* q, const uint4& a, const uint4& b) {
-  const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
-  const uint32_t x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
+__device__ __forceinline__ uint32_t pair_key(const uint32_t* q, const uint4& a, const uint4& b,
+                                             uint32_t rowkey) {
   if (VARIANT == 0) {
-    return __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3) + __popc(x4) + __popc(x5) + __popc(x6) +
-           __popc(x7);
+    const uint32_t d = __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
+                       __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
+    return mad_u32(d, kKeyMul, rowkey);
   } else {
-    // carry-save reduction: ones = sc, x7 ; twos = sd ; fours = cd
-    const uint32_t sa = xor3(x0, x1, x2), ca = maj3(x0, x1, x2);
-    const uint32_t sb = xor3(x3, x4, x5), cb = maj3(x3, x4, x5);
-    const uint32_t sc = xor3(sa, sb, x6), cc = maj3(sa, sb, x6);
+    // q and (a,b) in derived form.  ones: sc, x7 ; twos: sd ; fours: cd
+    const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x3 = q[2] ^ a.z, x4 = q[3] ^ a.w;
+    const uint32_t x7 = q[4] ^ b.x;
+    const uint32_t sa = q[5] ^ b.y, sb = q[6] ^ b.z, sc = q[7] ^ b.w;
+    const uint32_t ca = carry_from_sum(x0, x1, sa);       // maj(x0, x1, x2)
+    const uint32_t cb = carry_from_sum(x3, x4, sb);       // maj(x3, x4, x5)
+    const uint32_t cc = carry_from_sum(sa, sb, sc);       // maj(sa, sb, x6)
     const uint32_t sd = xor3(ca, cb, cc), cd = maj3(ca, cb, cc);
-    return (__popc(sc) + __popc(x7)) + 2u * __popc(sd) + 4u * __popc(cd);
+    uint32_t key = mad_u32(__popc(x7), kKeyMul, rowkey);
+    key = mad_u32(__popc(sc), kKeyMul, key);
+    key = mad_u32(__popc(sd), 2u * kKeyMul, key);
+    return mad_u32(__popc(cd), 4u * kKeyMul, key);
   }
 }
 
@@ -113,6 +118,21 @@ __device__ __forceinline__ void top2_insert(uint32_t& k1, uint32_t& k2, uint32_t
   const uint32_t mx = max(k1, key);
   k1 = min(k1, key);
   k2 = min(k2, mx);
+}
+
+// Scores `nrows` staged rows (FULL: exactly kTR) against the thread's 4 queries.
+template <int VARIANT, bool FULL>
+__device__ __forceinline__ void score_tile(const uint4* __restrict__ tile, int nrows, uint32_t rowkey,
+                                           const uint32_t (&qr)[kRQ][8], uint32_t (&k1)[kRQ],
+                                           uint32_t (&k2)[kRQ]) {
+  const int n = FULL ? kTR : nrows;
+#pragma unroll 4
+  for (int j = 0; j < n; ++j) {
+    const uint4 a = tile[2 * j], b = tile[2 * j + 1];
+#pragma unroll
+    for (int r = 0; r < kRQ; ++r) top2_insert(k1[r], k2[r], pair_key<VARIANT>(qr[r], a, b, rowkey));
+    ++rowkey;
+  }
 }
 
 template <int VARIANT>
@@ -160,8 +180,10 @@ hamming_knn2_kernel(const __grid_constant__ HammingParams P) {
   for (int r = 0; r < kRQ; ++r) {
     const uint4* src = reinterpret_cast<const uint4*>(qstage + (r * kHThreads + tid) * 32);
     const uint4 a = src[0], b = src[1];
-    qr[r][0] = a.x; qr[r][1] = a.y; qr[r][2] = a.z; qr[r][3] = a.w;
-    qr[r][4] = b.x; qr[r][5] = b.y; qr[r][6] = b.z; qr[r][7] = b.w;
+    uint4 da = a, db = b;
+    if (VARIANT == 1) derive_row(da, db);
+    qr[r][0] = da.x; qr[r][1] = da.y; qr[r][2] = da.z; qr[r][3] = da.w;
+    qr[r][4] = db.x; qr[r][5] = db.y; qr[r][6] = db.z; qr[r][7] = db.w;
   }
   uint32_t k1[kRQ], k2[kRQ];
 #pragma unroll
@@ -175,30 +197,23 @@ hamming_knn2_kernel(const __grid_constant__ HammingParams P) {
     mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
     const long long r_base = (long long)it * kTR;
     const int nrows = (int)((rows - r_base) < kTR ? (rows - r_base) : kTR);
-    const uint4* tile = reinterpret_cast<const uint4*>(ring + s * kStageBytes);
-    uint32_t rowkey = (uint32_t)r_base;
-    if (nrows == kTR) {
-#pragma unroll 4
-      for (int j = 0; j < kTR; ++j) {
-        const uint4 a = tile[2 * j], b = tile[2 * j + 1];
+    uint4* tile = reinterpret_cast<uint4*>(ring + s * kStageBytes);
+    if (VARIANT == 1) {
+      // rewrite the staged rows to derived form, two rows per thread, in place
 #pragma unroll
-        for (int r = 0; r < kRQ; ++r) {
-          const uint32_t d = hamming256<VARIANT>(qr[r], a, b);
-          top2_insert(k1[r], k2[r], d * (1u << kKeyShift) + rowkey);
+      for (int h = 0; h < kTR / kHThreads; ++h) {
+        const int row = h * kHThreads + tid;
+        if (row < nrows) {
+          uint4 a = tile[2 * row], b = tile[2 * row + 1];
+          derive_row(a, b);
+          tile[2 * row] = a;
+          tile[2 * row + 1] = b;
         }
-        ++rowkey;
       }
-    } else {
-      for (int j = 0; j < nrows; ++j) {
-        const uint4 a = tile[2 * j], b = tile[2 * j + 1];
-#pragma unroll
-        for (int r = 0; r < kRQ; ++r) {
-          const uint32_t d = hamming256<VARIANT>(qr[r], a, b);
-          top2_insert(k1[r], k2[r], d * (1u << kKeyShift) + rowkey);
-        }
-        ++rowkey;
-      }
+      __syncthreads();
     }
+    if (nrows == kTR) score_tile<VARIANT, true>(tile, kTR, (uint32_t)r_base, qr, k1, k2);
+    else score_tile<VARIANT, false>(tile, nrows, (uint32_t)r_base, qr, k1, k2);
     __syncthreads();   // everyone is done with slot s before it is refilled
   }
 
@@ -214,8 +229,7 @@ hamming_knn2_kernel(const __grid_constant__ HammingParams P) {
       for (int c = 0; c < 2; ++c) {
         o[c] = (kk[c] == kLocalNone)
                    ? PBK_KEY_NONE
-                   : (((unsigned long long)(kk[c] >> kKeyShift) << 32) |
-                      (gbase + (kk[c] & ((1u << kKeyShift) - 1u))));
+                   : (((unsigned long long)(kk[c] / kKeyMul) << 32) | (gbase + (kk[c] % kKeyMul)));
       }
       ulonglong2* dst = reinterpret_cast<ulonglong2*>(P.partial + ((long long)split * P.nq + qi) * 2);
       *dst = make_ulonglong2(o[0], o[1]);
@@ -295,12 +309,35 @@ hamming_ratio_mutual_kernel(const unsigned long long* __restrict__ keys,
 }
 
 // ------------------------------------------------------- popc pipe probe
-// mode 0: pure POPC chains (8 independent per thread)
-// mode 1: POPC + one dependent LOP3 per POPC (checks POPC/ALU overlap)
-// mode 2: the matcher's VARIANT 0 inner mix (8 LOP3 + 8 POPC + adds) on registers
-// mode 3: the matcher's VARIANT 1 inner mix (16 LOP3 + 4 POPC + adds)
+// mode 0: pure POPC chains (8 independent per thread) -> popc-pipe peak
+// mode 1: POPC + one LOP3 per POPC (checks POPC/ALU overlap)
+// mode 2 / 3: the matcher's own inner loop (VARIANT 0 / 1) over one resident
+//             shared-memory tile, no global traffic, no barriers: the
+//             instruction-mix ceiling of the kernel on this chip.
 template <int MODE>
-__global__ void __launch_bounds__(256) popc_probe_kernel(int iters, uint32_t* sink) {
+__global__ void __launch_bounds__(MODE >= 2 ? kHThreads : 256) popc_probe_kernel(int iters, uint32_t* sink) {
+  if (MODE >= 2) {
+    __shared__ __align__(16) uint4 tile[kTR * 2];
+    for (int i = threadIdx.x; i < kTR * 2; i += blockDim.x) {
+      const uint32_t h = (i + 1) * 2654435761u;
+      tile[i] = make_uint4(h, h * 40503u, h ^ (h >> 7), h * 0x9e3779b9u);
+    }
+    __syncthreads();
+    uint32_t qr[kRQ][8], k1[kRQ], k2[kRQ];
+#pragma unroll
+    for (int r = 0; r < kRQ; ++r) {
+      k1[r] = k2[r] = kLocalNone;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) qr[r][w] = (threadIdx.x * 8 + w + r * 977) * 2246822519u + sink[w];
+    }
+    for (int it = 0; it < iters; ++it)
+      score_tile<MODE == 2 ? 0 : 1, true>(tile, kTR, (uint32_t)it * kTR, qr, k1, k2);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int r = 0; r < kRQ; ++r) acc ^= k1[r] ^ k2[r];
+    sink[8 + blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    return;
+  }
   uint32_t v[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x;
@@ -312,7 +349,7 @@ __global__ void __launch_bounds__(256) popc_probe_kernel(int iters, uint32_t* si
         for (int i = 0; i < 8; ++i) v[i] = __popc(v[i]);
       }
     }
-  } else if (MODE == 1) {
+  } else {
     const uint32_t c = sink[0];
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -321,20 +358,6 @@ __global__ void __launch_bounds__(256) popc_probe_kernel(int iters, uint32_t* si
         for (int i = 0; i < 8; ++i) v[i] = __popc(v[i] ^ c);
       }
     }
-  } else {
-    uint32_t k1 = kLocalNone, k2 = kLocalNone;
-    uint4 a = make_uint4(sink[0], sink[1], sink[2], sink[3]);
-    uint4 b = make_uint4(sink[4], sink[5], sink[6], sink[7]);
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const uint32_t d = hamming256<MODE == 2 ? 0 : 1>(v, a, b);
-        top2_insert(k1, k2, d * (1u << kKeyShift) + (uint32_t)(it * 16 + u));
-        a.x += 0x9e3779b9u;          // a new "train row" every round
-        b.w += 0x7f4a7c15u;
-      }
-    }
-    v[0] = k1 ^ k2 ^ a.x ^ b.w;
   }
   uint32_t acc = 0;
 #pragma unroll
@@ -472,16 +495,17 @@ int pbk_popc_peak_probe(int mode, int ctas, int iters, uint32_t* sink, double* p
   using namespace pbk;
   PBK_REQUIRE(ctas > 0 && iters > 0 && sink != nullptr, PBK_EINVAL, "bad arguments");
   cudaStream_t s = as_stream(stream);
-  double per_round;
+  double per_thread;   // POPC per thread per iteration (modes 2/3: 4 queries x 256 rows x POPC/pair)
+  int threads = 256;
   switch (mode) {
-    case 0: popc_probe_kernel<0><<<ctas, 256, 0, s>>>(iters, sink); per_round = 16.0 * 8; break;
-    case 1: popc_probe_kernel<1><<<ctas, 256, 0, s>>>(iters, sink); per_round = 16.0 * 8; break;
-    case 2: popc_probe_kernel<2><<<ctas, 256, 0, s>>>(iters, sink); per_round = 16.0 * 8; break;
-    case 3: popc_probe_kernel<3><<<ctas, 256, 0, s>>>(iters, sink); per_round = 16.0 * 4; break;
+    case 0: popc_probe_kernel<0><<<ctas, 256, 0, s>>>(iters, sink); per_thread = 16.0 * 8; break;
+    case 1: popc_probe_kernel<1><<<ctas, 256, 0, s>>>(iters, sink); per_thread = 16.0 * 8; break;
+    case 2: popc_probe_kernel<2><<<ctas, kHThreads, 0, s>>>(iters, sink); per_thread = kRQ * kTR * 8.0; threads = kHThreads; break;
+    case 3: popc_probe_kernel<3><<<ctas, kHThreads, 0, s>>>(iters, sink); per_thread = kRQ * kTR * 4.0; threads = kHThreads; break;
     default: PBK_REQUIRE(false, PBK_EINVAL, "bad probe mode %d", mode);
   }
   PBK_CHECK_LAUNCH("popc_probe_kernel");
-  if (popc_per_launch) *popc_per_launch = per_round * (double)iters * 256.0 * (double)ctas;
+  if (popc_per_launch) *popc_per_launch = per_thread * (double)iters * (double)threads * (double)ctas;
   return PBK_OK;
 }
 

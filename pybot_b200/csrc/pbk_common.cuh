@@ -103,4 +103,50 @@ static inline int stream_grid(const DeviceInfo* di, long long work_items,
   return (int)g;
 }
 
+// ------------------------------------------------------------ TMA / mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completing `bytes` on `bar`.
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+
+// Persistent grid = what is actually resident: SMs x occupancy of `kernel`
+// (a grid larger than that runs a ragged second wave), capped by the work.
+template <typename K>
+static inline int resident_grid(const DeviceInfo* di, K kernel, int threads, size_t dyn_smem,
+                                long long work_items) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess ||
+      per_sm < 1)
+    per_sm = 1;
+  long long g = (long long)di->sm_count * per_sm;
+  if (g > work_items) g = work_items;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
 }  // namespace pbk

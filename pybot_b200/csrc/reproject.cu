@@ -253,15 +253,13 @@ static int launch_reproject(const void* disp_v, int batch, int H, int W, const R
     const long long ntiles = total / kTilePx;
     if (ntiles > 0) {
       const long long ctas_needed = (ntiles + kWarpsPerCta - 1) / kWarpsPerCta;
-      const int grid = stream_grid(di, ctas_needed, 8);
+      const bool fast = q_is_stereo_sparse(P.q);
+      auto kern = fast ? reproject_dense_kernel<T, true> : reproject_dense_kernel<T, false>;
+      const int grid = resident_grid(di, kern, kWarpsPerCta * 32, 0, ctas_needed);
       const long long stride_px = (long long)grid * kWarpsPerCta * kTilePx;
       P.dx = (int)(stride_px % W);
       P.dy = (int)((stride_px / W) % H);
-      const bool fast = q_is_stereo_sparse(P.q);
-      if (fast)
-        reproject_dense_kernel<T, true><<<grid, kWarpsPerCta * 32, 0, stream>>>(disp, xyz, bgr, bgr_out, P);
-      else
-        reproject_dense_kernel<T, false><<<grid, kWarpsPerCta * 32, 0, stream>>>(disp, xyz, bgr, bgr_out, P);
+      kern<<<grid, kWarpsPerCta * 32, 0, stream>>>(disp, xyz, bgr, bgr_out, P);
       PBK_CHECK_LAUNCH("reproject_dense_kernel");
     }
     const long long done = ntiles * kTilePx;

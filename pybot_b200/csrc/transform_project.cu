@@ -40,23 +40,40 @@ struct XformParams {
   int has_scale;
 };
 
-// ---- warp-private stage: coalesced tile load ---------------------------------
-// Copies `bytes` (multiple of 16, <= 3072) from g to s with 16 B per lane per
-// step; rows past `valid_bytes` (tail tile) are zero-filled.
-__device__ __forceinline__ void warp_load_tile(const char* __restrict__ g, char* s, int lane,
-                                               int bytes, int valid_bytes) {
-  for (int off = lane * 16; off < bytes; off += 32 * 16) {
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (off + 16 <= valid_bytes) {
-      v = ld_stream_u4(g + off);
-    } else if (off < valid_bytes) {       // ragged end: 4 B granularity
-      uint32_t w[4] = {0, 0, 0, 0};
-      for (int b = 0; b < 4; ++b)
-        if (off + 4 * b < valid_bytes) w[b] = ld_stream_u1(g + off + 4 * b);
-      v = make_uint4(w[0], w[1], w[2], w[3]);
+// ---- warp-private TMA ring ----------------------------------------------------
+// Every warp owns NST shared-memory slots of one 128-point tile each and NST
+// mbarriers.  Lane 0 issues a 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) for
+// tile k+NST-1 while the warp computes tile k, so each warp keeps NST-1 tiles
+// of HBM reads in flight without holding them in registers.  Only the single
+// ragged tile at the end of the array (whose byte count is not a multiple of
+// 16) is loaded with plain loads.
+template <int TILE_BYTES, int NST>
+struct WarpRing {
+  char* slots;
+  uint64_t* bars;
+  __device__ __forceinline__ void init(char* warp_smem, uint64_t* warp_bars, int lane) {
+    slots = warp_smem;
+    bars = warp_bars;
+    if (lane == 0) {
+      for (int s = 0; s < NST; ++s) mbar_init(&bars[s], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    *reinterpret_cast<uint4*>(s + off) = v;
+    __syncwarp();
   }
+  __device__ __forceinline__ char* slot(int k) const { return slots + (k % NST) * TILE_BYTES; }
+  // lane 0 only; `src` 16 B aligned, full tile
+  __device__ __forceinline__ void issue(int k, const char* src) const {
+    mbar_expect_tx(&bars[k % NST], TILE_BYTES);
+    tma_load_1d(slot(k), src, TILE_BYTES, &bars[k % NST]);
+  }
+  __device__ __forceinline__ void wait(int k) const { mbar_wait(&bars[k % NST], (uint32_t)((k / NST) & 1)); }
+};
+
+// ragged tile: plain loads of `valid_bytes` (multiple of 4), zero fill to `bytes`
+__device__ __forceinline__ void warp_load_ragged(const char* __restrict__ g, char* s, int lane,
+                                                 int bytes, int valid_bytes) {
+  for (int off = lane * 4; off < bytes; off += 128)
+    *reinterpret_cast<uint32_t*>(s + off) = off < valid_bytes ? ld_stream_u1(g + off) : 0u;
 }
 
 template <typename T>
@@ -65,31 +82,48 @@ __device__ __forceinline__ void stage_read_point(const char* s, int p, double X[
   X[0] = (double)r[0]; X[1] = (double)r[1]; X[2] = (double)r[2];
 }
 
+template <typename T> struct RingCfg { static constexpr int kStages = 4; };
+template <> struct RingCfg<double> { static constexpr int kStages = 3; };
+
 // =============================================================== transform
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(kWarps * 32)
 transform_points_kernel(const TI* __restrict__ X, long long n, TO* __restrict__ Y,
                         const __grid_constant__ XformParams P) {
-  constexpr int kStageBytes = kTilePts * 3 * (sizeof(TI) > sizeof(TO) ? sizeof(TI) : sizeof(TO));
-  __shared__ __align__(16) char stage[kWarps][kStageBytes];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  char* st = stage[warp];
-  const long long ntiles = (n + kTilePts - 1) / kTilePts;
-  const long long stride = (long long)gridDim.x * kWarps;
+  constexpr int NST = RingCfg<TI>::kStages;
   constexpr int kInBytes = kTilePts * 3 * sizeof(TI);
   constexpr int kOutBytes = kTilePts * 3 * sizeof(TO);
+  extern __shared__ __align__(128) char dyn_smem[];
+  // layout: [warp][NST][kInBytes] | [warp][kOutBytes] | barriers
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  char* out_stage = dyn_smem + kWarps * NST * kInBytes + warp * kOutBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dyn_smem + kWarps * (NST * kInBytes + kOutBytes)) + warp * NST;
+  WarpRing<kInBytes, NST> ring;
+  ring.init(dyn_smem + warp * NST * kInBytes, bars, lane);
 
-  for (long long tile = (long long)blockIdx.x * kWarps + warp; tile < ntiles; tile += stride) {
+  const long long ntiles = (n + kTilePts - 1) / kTilePts;
+  const long long nfull = n / kTilePts;
+  const long long stride = (long long)gridDim.x * kWarps;
+  const long long t0 = (long long)blockIdx.x * kWarps + warp;
+  const char* Xb = reinterpret_cast<const char*>(X);
+  if (lane == 0)
+    for (int k = 0; k < NST - 1; ++k)
+      if (t0 + k * stride < nfull) ring.issue(k, Xb + (t0 + k * stride) * kInBytes);
+
+  int k = 0;
+  for (long long tile = t0; tile < ntiles; tile += stride, ++k) {
+    const long long nxt = tile + (NST - 1) * stride;
+    if (lane == 0 && nxt < nfull) ring.issue(k + NST - 1, Xb + nxt * kInBytes);
     const long long first = tile * kTilePts;
     const int npts = (int)((n - first) < kTilePts ? (n - first) : kTilePts);
-    warp_load_tile(reinterpret_cast<const char*>(X + first * 3), st, lane, kInBytes,
-                   npts * 3 * (int)sizeof(TI));
-    __syncwarp();
+    char* st = ring.slot(k);
+    if (tile < nfull) ring.wait(k);
+    else { warp_load_ragged(Xb + first * 3 * sizeof(TI), st, lane, kInBytes, npts * 3 * (int)sizeof(TI)); __syncwarp(); }
     double Xp[4][3];
 #pragma unroll
     for (int j = 0; j < 4; ++j) stage_read_point<TI>(st, j * 32 + lane, Xp[j]);
-    __syncwarp();
-    TO* so = reinterpret_cast<TO*>(st);
+    __syncwarp();                       // slot may be refilled from here on
+    TO* so = reinterpret_cast<TO*>(out_stage);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -105,14 +139,13 @@ transform_points_kernel(const TI* __restrict__ X, long long n, TO* __restrict__ 
     __syncwarp();
     char* dst = reinterpret_cast<char*>(Y + first * 3);
     const int valid = npts * 3 * (int)sizeof(TO);
-    for (int off = lane * 16; off < kOutBytes; off += 32 * 16) {
-      if (off + 16 <= valid) {
-        st_stream_u4(dst + off, *reinterpret_cast<const uint4*>(st + off));
-      } else if (off < valid) {
-        for (int b = 0; b < 16; b += 4)
-          if (off + b < valid)
-            *reinterpret_cast<uint32_t*>(dst + off + b) = *reinterpret_cast<const uint32_t*>(st + off + b);
-      }
+    if (valid == kOutBytes) {
+#pragma unroll
+      for (int off = 0; off < kOutBytes; off += 512)
+        st_stream_u4(dst + off + lane * 16, *reinterpret_cast<const uint4*>(out_stage + off + lane * 16));
+    } else {
+      for (int off = lane * 4; off < valid; off += 128)
+        *reinterpret_cast<uint32_t*>(dst + off) = *reinterpret_cast<const uint32_t*>(out_stage + off);
     }
     __syncwarp();
   }
@@ -199,72 +232,136 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// scratch layout: [0] ticket counter (u64), [1 .. ntiles] tile status words.
-template <typename T, bool DIST, bool COMPACT>
+// MODE 0: plain projection (no depth, masks, count).
+// MODE 1: depth / masks / valid flags per runtime switches, outputs uncompacted.
+// MODE 2: as 1 + order-preserving compaction of uv / depth (decoupled look-back
+//         over CTA tiles of 1024 points handed out by an atomic ticket).
+// scratch layout (MODE 2): [0] ticket counter (u64), [1 .. ntiles] tile status words.
+template <typename T, bool DIST, int MODE>
 __global__ void __launch_bounds__(kWarps * 32)
 project_points_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
                       double* __restrict__ depth, uint8_t* __restrict__ valid_out,
                       long long* __restrict__ count, unsigned long long* __restrict__ scratch,
                       const __grid_constant__ pbk_project_params P) {
+  constexpr int NST = RingCfg<T>::kStages;
   constexpr int kInBytes = kTilePts * 3 * sizeof(T);
-  __shared__ __align__(16) char stage[kWarps][kInBytes];
+  extern __shared__ __align__(128) char dyn_smem[];
   __shared__ int warp_count[kWarps];
-  __shared__ long long s_tile;
-  __shared__ long long s_excl;
+  __shared__ long long s_ticket[2];
+  __shared__ long long s_part[kWarps];
+  __shared__ int s_has[kWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  char* st = stage[warp];
-  const long long ntiles = (n + kCtaPts - 1) / kCtaPts;
-  const bool need_depth = (depth != nullptr) || P.check_depth;
-  long long tile = blockIdx.x;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dyn_smem + kWarps * NST * kInBytes) + warp * NST;
+  WarpRing<kInBytes, NST> ring;
+  ring.init(dyn_smem + warp * NST * kInBytes, bars, lane);
 
-  while (true) {
-    if (COMPACT) {
-      __syncthreads();                      // s_tile / s_excl reuse
-      if (threadIdx.x == 0) s_tile = (long long)atomicAdd(scratch, 1ull);
-      __syncthreads();
-      tile = s_tile;
+  const long long nfull = n / kTilePts;                    // full 128-point tiles
+  const long long nwt = (n + kTilePts - 1) / kTilePts;     // warp tiles
+  const long long ncta = (n + kCtaPts - 1) / kCtaPts;      // CTA tiles (MODE 2)
+  const char* Xb = reinterpret_cast<const char*>(X);
+  const bool need_depth = MODE != 0 && ((depth != nullptr) || P.check_depth);
+
+  // warp tile index of step k.  MODE 2: CTA tiles are handed out by an atomic
+  // ticket, exactly ONE tile ahead of the one being computed (s_ticket[k & 1]):
+  // taking several tickets at once would make a CTA sit on consecutive tiles and
+  // serialise the look-back chain of every CTA behind it.
+  const long long stride = (long long)gridDim.x * kWarps;
+  const long long t0 = (long long)blockIdx.x * kWarps + warp;
+  auto wtile = [&](int k) -> long long {
+    if (MODE == 2) {
+      const long long c = s_ticket[k & 1];
+      return c >= ncta ? nwt : c * kWarps + warp;
     }
-    if (tile >= ntiles) break;
+    return t0 + (long long)k * stride;
+  };
+  if (MODE == 2) {
+    if (threadIdx.x == 0) s_ticket[0] = (long long)atomicAdd(scratch, 1ull);
+    __syncthreads();
+    if (lane == 0) {
+      const long long t = wtile(0);
+      if (t < nfull) ring.issue(0, Xb + t * kInBytes);
+    }
+  } else if (lane == 0) {
+    for (int k = 0; k < NST - 1; ++k) {
+      const long long t = wtile(k);
+      if (t < nfull) ring.issue(k, Xb + t * kInBytes);
+    }
+  }
 
-    const long long first = tile * kCtaPts + (long long)warp * kTilePts;
-    long long rem = n - first;
+  long long local_count = 0;
+  for (int k = 0;; ++k) {
+    long long cta_tile = 0;
+    if (MODE == 2) {
+      cta_tile = s_ticket[k & 1];
+      if (cta_tile >= ncta) break;
+      if (threadIdx.x == 0) s_ticket[(k + 1) & 1] = (long long)atomicAdd(scratch, 1ull);
+      __syncthreads();                  // (A0) next ticket visible
+      if (lane == 0) {
+        const long long t = wtile(k + 1);
+        if (t < nfull) ring.issue(k + 1, Xb + t * kInBytes);
+      }
+    }
+    const long long tile = wtile(k);
+    if (MODE != 2) {
+      if (tile >= nwt) break;
+      const long long nxt = tile + (NST - 1) * stride;
+      if (lane == 0 && nxt < nfull) ring.issue(k + NST - 1, Xb + nxt * kInBytes);
+    }
+    const long long first = tile * kTilePts;
+    const long long rem = n - first;
     const int npts = rem <= 0 ? 0 : (rem < kTilePts ? (int)rem : kTilePts);
-    if (npts > 0)
-      warp_load_tile(reinterpret_cast<const char*>(X + first * 3), st, lane, kInBytes,
-                     npts * 3 * (int)sizeof(T));
-    __syncwarp();
+    char* st = ring.slot(k);
+    if (npts == kTilePts) ring.wait(k);
+    else {
+      if (npts > 0) warp_load_ragged(Xb + first * 3 * sizeof(T), st, lane, kInBytes, npts * 3 * (int)sizeof(T));
+      else warp_load_ragged(Xb, st, lane, kInBytes, 0);
+      __syncwarp();
+    }
+    double Xp[4][3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) stage_read_point<T>(st, j * 32 + lane, Xp[j]);
+    __syncwarp();                       // slot may be refilled from here on
 
     T uo[4], vo[4];
     double dep[4];
     bool ok[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int p = j * 32 + lane;
-      double Xp[3];
-      stage_read_point<T>(st, p, Xp);
       double u, v;
-      project_one<DIST>(P, Xp, u, v);
+      project_one<DIST>(P, Xp[j], u, v);
       uo[j] = (T)u;
       vo[j] = (T)v;
-      bool good = p < npts;
-      if (need_depth) {
-        double acc = __dmul_rn(P.Rz[0], Xp[0]);
-        acc = __fma_rn(P.Rz[1], Xp[1], acc);
-        acc = __fma_rn(P.Rz[2], Xp[2], acc);
-        acc = __fma_rn(P.tz, 1.0, acc);
-        dep[j] = acc;
-        if (P.check_depth) good = good && (acc >= P.min_depth);
+      if (MODE != 0) {
+        bool good = (j * 32 + lane) < npts;
+        if (need_depth) {
+          double acc = __dmul_rn(P.Rz[0], Xp[j][0]);
+          acc = __fma_rn(P.Rz[1], Xp[j][1], acc);
+          acc = __fma_rn(P.Rz[2], Xp[j][2], acc);
+          acc = __fma_rn(P.tz, 1.0, acc);
+          dep[j] = acc;
+          if (P.check_depth) good = good && (acc >= P.min_depth);
+        }
+        if (P.check_bounds) good = good && OutPix<T>::in_bounds(uo[j], vo[j], P.width, P.height);
+        ok[j] = good;
       }
-      if (P.check_bounds) good = good && OutPix<T>::in_bounds(uo[j], vo[j], P.width, P.height);
-      ok[j] = good;
     }
-    __syncwarp();
+
+    if (MODE == 0) {
+      if (npts == kTilePts) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) OutPix<T>::store(uv, first + j * 32 + lane, uo[j], vo[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j * 32 + lane < npts) OutPix<T>::store(uv, first + j * 32 + lane, uo[j], vo[j]);
+      }
+      continue;
+    }
 
     unsigned m[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) m[j] = __ballot_sync(0xffffffffu, ok[j]);
     const int wc = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
-
     if (valid_out != nullptr) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -273,7 +370,7 @@ project_points_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
       }
     }
 
-    if (!COMPACT) {
+    if (MODE == 1) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int p = j * 32 + lane;
@@ -282,54 +379,57 @@ project_points_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
           if (depth != nullptr) st_stream_d1(depth + first + p, dep[j]);
         }
       }
-      if (count != nullptr && lane == 0 && wc)
-        atomicAdd(reinterpret_cast<unsigned long long*>(count), (unsigned long long)wc);
-      tile += gridDim.x;
+      local_count += wc;
       continue;
     }
 
-    // ---- compaction: CTA aggregate, decoupled look-back, ordered scatter
+    // ---- MODE 2: CTA aggregate, decoupled look-back, ordered scatter.
+    // The look-back inspects 256 predecessor tiles per round (one per thread):
+    // tiles complete at ~250 per microsecond across the chip, so a 32-wide
+    // window could not keep up and every CTA ended up waiting at the barrier.
     if (lane == 0) warp_count[warp] = wc;
-    __syncthreads();
-    if (warp == 0) {
-      int c = lane < kWarps ? warp_count[lane] : 0;
-      int agg = c;
+    __syncthreads();                    // (A)
+    int agg = 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) agg += __shfl_xor_sync(0xffffffffu, agg, o);
-      unsigned long long* status = scratch + 1;
-      long long excl = 0;
-      if (tile == 0) {
-        if (lane == 0) st_status(status, kStatePrefix | (unsigned long long)agg);
-      } else {
-        if (lane == 0) st_status(status + tile, kStateAgg | (unsigned long long)agg);
-        long long look = tile - 1;
-        while (true) {
-          const long long idx = look - lane;
-          unsigned long long s = kStatePrefix;          // virtual prefix 0 before tile 0
-          if (idx >= 0) {
-            do { s = ld_status(status + idx); } while ((s >> 62) == 0);
-          }
-          const unsigned is_prefix = __ballot_sync(0xffffffffu, (s >> 62) == 2);
-          long long val = (long long)(s & kValueMask);
-          if (is_prefix) {
-            const int firstp = __ffs(is_prefix) - 1;     // nearest tile holding a prefix
-            if (lane > firstp) val = 0;
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-          excl += val;
-          if (is_prefix) break;
-          look -= 32;
+    for (int w = 0; w < kWarps; ++w) agg += warp_count[w];
+    unsigned long long* status = scratch + 1;
+    if (threadIdx.x == 0)
+      st_status(status + cta_tile, (cta_tile == 0 ? kStatePrefix : kStateAgg) | (unsigned long long)agg);
+    long long excl = 0;
+    if (cta_tile > 0) {
+      long long look = cta_tile - 1;
+      while (true) {
+        const long long idx = look - (long long)threadIdx.x;      // thread 0 = nearest predecessor
+        unsigned long long sw = kStatePrefix;                     // virtual prefix 0 before tile 0
+        if (idx >= 0) {
+          do { sw = ld_status(status + idx); } while ((sw >> 62) == 0);
         }
-        if (lane == 0) st_status(status + tile, kStatePrefix | (unsigned long long)(excl + agg));
+        const unsigned is_prefix = __ballot_sync(0xffffffffu, (sw >> 62) == 2);
+        long long val = (long long)(sw & kValueMask);
+        if (is_prefix && lane > __ffs(is_prefix) - 1) val = 0;   // stop at the nearest prefix
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        if (lane == 0) {
+          s_part[warp] = val;
+          s_has[warp] = is_prefix != 0;
+        }
+        __syncthreads();                // (B1)
+        bool found = false;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          if (!found) {
+            excl += s_part[w];
+            found = s_has[w] != 0;
+          }
+        }
+        if (found) break;
+        look -= kWarps * 32;
+        __syncthreads();                // (B2) s_part reuse
       }
-      if (lane == 0) {
-        s_excl = excl;
-        if (tile == ntiles - 1 && count != nullptr) *count = excl + agg;
-      }
+      if (threadIdx.x == 0) st_status(status + cta_tile, kStatePrefix | (unsigned long long)(excl + agg));
     }
-    __syncthreads();
-    long long base = s_excl;
+    if (threadIdx.x == 0 && cta_tile == ncta - 1 && count != nullptr) *count = excl + agg;
+    long long base = excl;
     for (int w = 0; w < warp; ++w) base += warp_count[w];
     const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
@@ -341,29 +441,49 @@ project_points_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
       }
       base += __popc(m[j]);
     }
+    __syncthreads();                    // (C) warp_count / s_part reuse
   }
+  if (MODE == 1 && count != nullptr) {
+    if (lane == 0 && local_count)
+      atomicAdd(reinterpret_cast<unsigned long long*>(count), (unsigned long long)local_count);
+  }
+}
+
+template <typename K>
+static int opt_in_smem(K kernel, int bytes) {
+  if (bytes > 48 * 1024) PBK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return PBK_OK;
 }
 
 template <typename TI, typename TO>
 static int launch_transform(const void* X, int64_t n, const XformParams& P, void* Y,
                             cudaStream_t s, const DeviceInfo* di) {
+  constexpr int NST = RingCfg<TI>::kStages;
+  const int smem = kWarps * (NST * kTilePts * 3 * (int)sizeof(TI) + kTilePts * 3 * (int)sizeof(TO)) + kWarps * NST * 8;
+  auto kern = transform_points_kernel<TI, TO>;
+  int rc = opt_in_smem(kern, smem);
+  if (rc) return rc;
   const long long ntiles = (n + kTilePts - 1) / kTilePts;
-  const int grid = stream_grid(di, (ntiles + kWarps - 1) / kWarps, 4);
-  transform_points_kernel<TI, TO><<<grid, kWarps * 32, 0, s>>>(static_cast<const TI*>(X), n,
-                                                              static_cast<TO*>(Y), P);
+  const int grid = resident_grid(di, kern, kWarps * 32, smem, (ntiles + kWarps - 1) / kWarps);
+  kern<<<grid, kWarps * 32, smem, s>>>(static_cast<const TI*>(X), n, static_cast<TO*>(Y), P);
   PBK_CHECK_LAUNCH("transform_points_kernel");
   return PBK_OK;
 }
 
-template <typename T, bool DIST, bool COMPACT>
+template <typename T, bool DIST, int MODE>
 static int launch_project(const void* X, int64_t n, const pbk_project_params& P, void* uv,
                           double* depth, uint8_t* valid, int64_t* count, void* scratch,
                           cudaStream_t s, const DeviceInfo* di) {
-  const long long ntiles = (n + kCtaPts - 1) / kCtaPts;
-  const int grid = stream_grid(di, ntiles, 4);
-  project_points_kernel<T, DIST, COMPACT><<<grid, kWarps * 32, 0, s>>>(
-      static_cast<const T*>(X), n, static_cast<T*>(uv), depth, valid,
-      reinterpret_cast<long long*>(count), static_cast<unsigned long long*>(scratch), P);
+  constexpr int NST = RingCfg<T>::kStages;
+  const int smem = kWarps * NST * kTilePts * 3 * (int)sizeof(T) + kWarps * NST * 8;
+  auto kern = project_points_kernel<T, DIST, MODE>;
+  int rc = opt_in_smem(kern, smem);
+  if (rc) return rc;
+  const long long ncta = (n + kCtaPts - 1) / kCtaPts;
+  const int grid = resident_grid(di, kern, kWarps * 32, smem, ncta);
+  kern<<<grid, kWarps * 32, smem, s>>>(static_cast<const T*>(X), n, static_cast<T*>(uv), depth, valid,
+                                       reinterpret_cast<long long*>(count),
+                                       static_cast<unsigned long long*>(scratch), P);
   PBK_CHECK_LAUNCH("project_points_kernel");
   return PBK_OK;
 }
@@ -424,14 +544,27 @@ int pbk_project_points(const void* X, int in_dtype, int64_t n, const pbk_project
   const DeviceInfo* di;
   int rc = current_device_info(&di);
   if (rc) return rc;
+  const bool plain = !P.compact && !P.check_depth && !P.check_bounds && depth == nullptr && valid == nullptr;
   if (P.compact) PBK_CUDA(cudaMemsetAsync(scratch, 0, pbk_project_scratch_bytes(n), s));
-  else if (count != nullptr) PBK_CUDA(cudaMemsetAsync(count, 0, 8, s));
+  else if (count != nullptr) {
+    if (plain) {
+      const int64_t all = n;            // pageable source: staged before the call returns
+      PBK_CUDA(cudaMemcpyAsync(count, &all, 8, cudaMemcpyHostToDevice, s));
+    } else {
+      PBK_CUDA(cudaMemsetAsync(count, 0, 8, s));
+    }
+  }
   const bool dist = P.has_distortion != 0;
-#define PBK_DISPATCH(T)                                                                        \
-  if (dist && P.compact) return launch_project<T, true, true>(X, n, P, uv, depth, valid, count, scratch, s, di);   \
-  if (dist) return launch_project<T, true, false>(X, n, P, uv, depth, valid, count, scratch, s, di);               \
-  if (P.compact) return launch_project<T, false, true>(X, n, P, uv, depth, valid, count, scratch, s, di);          \
-  return launch_project<T, false, false>(X, n, P, uv, depth, valid, count, scratch, s, di);
+  const int mode = plain ? 0 : (P.compact ? 2 : 1);
+#define PBK_DISPATCH(T)                                                                              \
+  switch (mode * 2 + (dist ? 1 : 0)) {                                                               \
+    case 0: return launch_project<T, false, 0>(X, n, P, uv, depth, valid, count, scratch, s, di);    \
+    case 1: return launch_project<T, true, 0>(X, n, P, uv, depth, valid, count, scratch, s, di);     \
+    case 2: return launch_project<T, false, 1>(X, n, P, uv, depth, valid, count, scratch, s, di);    \
+    case 3: return launch_project<T, true, 1>(X, n, P, uv, depth, valid, count, scratch, s, di);     \
+    case 4: return launch_project<T, false, 2>(X, n, P, uv, depth, valid, count, scratch, s, di);    \
+    default: return launch_project<T, true, 2>(X, n, P, uv, depth, valid, count, scratch, s, di);    \
+  }
   if (in_dtype == PBK_F32) { PBK_DISPATCH(float) }
   PBK_DISPATCH(double)
 #undef PBK_DISPATCH

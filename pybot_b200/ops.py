@@ -38,13 +38,14 @@ def _finish(tensor, on_device):
 
 
 # ---------------------------------------------------------------- transform
-def transform_points(X, R, t, scale=1.0, out_dtype=np.float64):
+def transform_points(X, R, t, scale=1.0, out_dtype=np.float64, out=None):
     """Y = scale * R @ X + t for (N,3) points.  Reference:
-    RigidTransform.__mul__ (rigid_transform.py:139-141) returns float64."""
+    RigidTransform.__mul__ (rigid_transform.py:139-141) returns float64.
+    `out`: optional preallocated (N,3) CUDA tensor of out_dtype."""
     T = _ffi.require_cuda()
     Xd, on_dev = _points_in(X)
     n = Xd.shape[0]
-    Y = T.empty((n, 3), dtype=_tdtype(T, out_dtype), device=Xd.device)
+    Y = out if out is not None else T.empty((n, 3), dtype=_tdtype(T, out_dtype), device=Xd.device)
     Rt = np.concatenate([np.asarray(R, np.float64).reshape(9), np.asarray(t, np.float64).reshape(3)])
     Rt, Rt_p = _ffi.host_f64(Rt, 12)
     _ffi.check(_ffi.lib().pbk_transform_points(
@@ -54,6 +55,78 @@ def transform_points(X, R, t, scale=1.0, out_dtype=np.float64):
 
 
 # ------------------------------------------------------------------ project
+class Projector(object):
+    """Prepared Camera.project launch: the parameter block is built once and
+    output buffers are reused, so a call costs one ctypes call (a few us of
+    host time) - per-frame callers and the benchmark use this directly."""
+
+    def __init__(self, R, t, K, D=None, Rz=None, tz=None, shape=None, check_bounds=False,
+                 check_depth=False, return_depth=False, return_valid=False, min_depth=0.1,
+                 compact=True):
+        P = _ffi.ProjectParams()
+        R = np.asarray(R, np.float64).reshape(9)
+        t = np.asarray(t, np.float64).reshape(3)
+        P.R[:] = R.tolist()
+        P.t[:] = t.tolist()
+        rz = R[6:9] if Rz is None else np.asarray(Rz, np.float64).reshape(3)
+        P.Rz[:] = rz.tolist()
+        P.tz = float(t[2] if tz is None else tz)
+        K = np.asarray(K, np.float64)
+        P.fx, P.fy, P.cx, P.cy = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+        k = np.zeros(8)
+        if D is not None:
+            Dv = np.asarray(D, np.float64).ravel()
+            if Dv.size > 8:
+                raise NotImplementedError("thin-prism / tilt distortion (>8 coefficients) is not supported")
+            if Dv.size not in (0, 4, 5, 8):
+                raise ValueError("distortion must have 4, 5 or 8 coefficients")
+            k[:Dv.size] = Dv
+        P.k[:] = k.tolist()
+        P.has_distortion = int(np.any(k != 0))
+        P.min_depth = float(min_depth)
+        if check_bounds and shape is None:
+            raise ValueError("check_bounds cannot proceed. Camera.shape is not set")
+        P.height, P.width = (int(shape[0]), int(shape[1])) if shape is not None else (0, 0)
+        P.check_depth = int(bool(check_depth))
+        P.check_bounds = int(bool(check_bounds))
+        self.masked = bool(check_depth or check_bounds)
+        self.compact = bool(compact and self.masked)
+        P.compact = int(self.compact)
+        self.params = P
+        self.return_depth, self.return_valid = bool(return_depth), bool(return_valid)
+        self._bufs = None
+
+    def _buffers(self, Xd):
+        T = _ffi.torch()
+        n = Xd.shape[0]
+        key = (n, Xd.dtype, Xd.device)
+        if self._bufs is None or self._bufs[0] != key:
+            uv = T.empty((n, 2), dtype=Xd.dtype, device=Xd.device)
+            depth = T.empty((n,), dtype=T.float64, device=Xd.device) if self.return_depth else None
+            valid = T.empty((n,), dtype=T.uint8, device=Xd.device) if self.return_valid else None
+            count = T.empty((1,), dtype=T.int64, device=Xd.device)
+            scratch = None
+            if self.compact:
+                nbytes = _ffi.lib().pbk_project_scratch_bytes(n)
+                scratch = T.empty((max(nbytes, 16),), dtype=T.uint8, device=Xd.device)
+            self._bufs = (key, uv, depth, valid, count, scratch)
+        return self._bufs[1:]
+
+    def run(self, Xd, fresh=False):
+        """Xd: (n,3) float32/float64 CUDA tensor.  Returns device tensors
+        (uv, depth, valid_u8, count); asynchronous.  Buffers are reused across
+        calls unless fresh=True."""
+        T = _ffi.torch()
+        if fresh:
+            self._bufs = None
+        uv, depth, valid, count, scratch = self._buffers(Xd)
+        in_dt = _ffi.PBK_F32 if Xd.dtype == T.float32 else _ffi.PBK_F64
+        _ffi.check(_ffi.lib().pbk_project_points(
+            _ffi.ptr(Xd), in_dt, Xd.shape[0], ctypes.byref(self.params), _ffi.ptr(uv), _ffi.ptr(depth),
+            _ffi.ptr(valid), _ffi.ptr(count), _ffi.ptr(scratch), _ffi.stream_ptr()))
+        return uv, depth, valid, count
+
+
 def project_points(X, R, t, K, D=None, Rz=None, tz=None, shape=None, check_bounds=False,
                    check_depth=False, return_depth=False, return_valid=False, min_depth=0.1,
                    compact=True):
@@ -64,53 +137,15 @@ def project_points(X, R, t, K, D=None, Rz=None, tz=None, shape=None, check_bound
     Returns (uv, depth or None, valid or None, count).  With compact=True uv
     and depth hold only the valid points, in input order (camera_utils.py:727-732).
     """
-    T = _ffi.require_cuda()
     Xd, on_dev = _points_in(X)
     n = Xd.shape[0]
-    P = _ffi.ProjectParams()
-    R = np.asarray(R, np.float64).reshape(9)
-    t = np.asarray(t, np.float64).reshape(3)
-    P.R[:] = R.tolist()
-    P.t[:] = t.tolist()
-    rz = R[6:9] if Rz is None else np.asarray(Rz, np.float64).reshape(3)
-    P.Rz[:] = rz.tolist()
-    P.tz = float(t[2] if tz is None else tz)
-    K = np.asarray(K, np.float64)
-    P.fx, P.fy, P.cx, P.cy = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
-    k = np.zeros(8)
-    if D is not None:
-        Dv = np.asarray(D, np.float64).ravel()
-        if Dv.size > 8:
-            raise NotImplementedError("thin-prism / tilt distortion (>8 coefficients) is not supported")
-        if Dv.size not in (0, 4, 5, 8):
-            raise ValueError("distortion must have 4, 5 or 8 coefficients")
-        k[:Dv.size] = Dv
-    P.k[:] = k.tolist()
-    P.has_distortion = int(np.any(k != 0))
-    P.min_depth = float(min_depth)
-    if check_bounds and shape is None:
-        raise ValueError("check_bounds cannot proceed. Camera.shape is not set")
-    P.height, P.width = (int(shape[0]), int(shape[1])) if shape is not None else (0, 0)
-    P.check_depth = int(bool(check_depth))
-    P.check_bounds = int(bool(check_bounds))
-    do_compact = bool(compact and (check_depth or check_bounds))
-    P.compact = int(do_compact)
-    uv = T.empty((n, 2), dtype=Xd.dtype, device=Xd.device)
-    depth = T.empty((n,), dtype=T.float64, device=Xd.device) if return_depth else None
-    valid = T.empty((n,), dtype=T.uint8, device=Xd.device) if return_valid else None
-    count = T.empty((1,), dtype=T.int64, device=Xd.device)
-    scratch = None
-    if do_compact:
-        nbytes = _ffi.lib().pbk_project_scratch_bytes(n)
-        scratch = T.empty((max(nbytes, 16),), dtype=T.uint8, device=Xd.device)
-    in_dt = _ffi.PBK_F32 if Xd.dtype == T.float32 else _ffi.PBK_F64
-    _ffi.check(_ffi.lib().pbk_project_points(
-        _ffi.ptr(Xd), in_dt, n, ctypes.byref(P), _ffi.ptr(uv), _ffi.ptr(depth), _ffi.ptr(valid),
-        _ffi.ptr(count), _ffi.ptr(scratch), _ffi.stream_ptr()))
+    pr = Projector(R, t, K, D, Rz, tz, shape, check_bounds, check_depth, return_depth, return_valid,
+                   min_depth, compact)
+    uv, depth, valid, count = pr.run(Xd)
     m = n
-    if check_depth or check_bounds:
+    if pr.masked:
         m = int(count.item())            # one 8-byte D2H; also orders the stream
-    if do_compact:
+    if pr.compact:
         uv = uv[:m]
         if depth is not None:
             depth = depth[:m]
