@@ -225,9 +225,9 @@ def run_c3(D, args):
         else:
             keys_local = m.local_keys(q_dev)
         if D.world > 1:
-            g = torch.empty((D.world,) + tuple(keys_local.shape), dtype=keys_local.dtype, device="cuda")
+            g = torch.empty((D.world * keys_local.shape[0], 2), dtype=keys_local.dtype, device="cuda")
             D.dist.all_gather_into_tensor(g, keys_local)
-            keys = ops.hamming_merge(g)
+            keys = ops.hamming_merge(g.view(D.world, -1, 2))
         else:
             keys = keys_local
         rows = ops.hamming_gather_best(shard, keys, m.shard_base)

@@ -78,9 +78,11 @@ class ShardedKeyframeMatcher(object):
         local = self.local_keys(q)
         if self.world == 1:
             return local
-        gathered = T.empty((self.world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+        # flat (world*nq, 2) output: the layout both NCCL and gloo accept
+        gathered = T.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                           device=local.device)
         self.dist.all_gather_into_tensor(gathered, local.contiguous(), group=self.group)
-        return self.kernels.merge(gathered)
+        return self.kernels.merge(gathered.view((self.world,) + tuple(local.shape)))
 
     def match(self, q, ratio=0.75, mutual=True):
         """idx (nq,2) global rows, dist (nq,2), ratio_ok, mutual_ok, valid."""
