@@ -61,6 +61,12 @@ PBK_API const char* pbk_last_error_string(void);
  * [4]=L2 bytes, [5]=SM clock kHz, [6]=memory clock kHz, [7]=bus width bits */
 PBK_API int pbk_device_props(int device, int64_t props[8]);
 
+/* HBM bandwidth probe (measurement only).  mode 0: read `bytes` from src;
+ * 1: write `bytes` to dst; 2: copy src -> dst.  16 B vector accesses, grid =
+ * 8 CTAs per SM.  sink: device uint32[1].                                      */
+PBK_API int pbk_hbm_probe(int mode, const void* src, void* dst, int64_t bytes,
+                          uint32_t* sink, pbk_stream_t stream);
+
 /* ------------------------------------------------- disparity -> XYZ (a6,a7)
  * Replaces cv2.reprojectImageTo3D(disp, self.Q) in StereoCamera.reconstruct,
  * pybot/vision/camera_utils.py:964-969, and reconstruct_with_texture :982-990

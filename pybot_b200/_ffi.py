@@ -45,6 +45,7 @@ SIGNATURES = {
     "pbk_version": (_i, []),
     "pbk_last_error_string": (ctypes.c_char_p, []),
     "pbk_device_props": (_i, [_i, ctypes.POINTER(_i64)]),
+    "pbk_hbm_probe": (_i, [_i, _vp, _vp, _i64, _vp, _vp]),
     "pbk_reproject_disp": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "pbk_reproject_sparse": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "pbk_transform_points": (_i, [_vp, _i, _i64, _vp, _d, _vp, _i, _vp]),

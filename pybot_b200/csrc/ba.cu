@@ -11,12 +11,18 @@
 // by OpenCV's Rodrigues closed form (one thread per camera, fp64).  The
 // streaming kernel is HBM-write-bound: 16 B read + 80 B written per
 // observation; points (12 B each) are gathered through L2 one tile ahead and the
-// warp's camera block (320 B) is cached in shared memory.  One warp owns 32
-// observations: the 16 B observation records load coalesced (prefetched two
-// tiles ahead), fp64 math in registers, J_cam / J_pt rows are transposed through a
-// warp-private shared-memory stage so global stores are coalesced 16 B, and
-// sum ||r||^2 is reduced warp -> CTA -> one fp64 partial per CTA, summed in
-// fixed order by a second tiny kernel (deterministic, no atomics).
+// warp's camera block (320 B) is cached in shared memory.  One warp owns 64
+// observations (2 per lane): the 16 B observation records load coalesced
+// (prefetched two tiles ahead), fp64 math in registers with every camera
+// coefficient read once for both observations, r / J_cam / J_pt rows are written
+// to a warp-private shared-memory stage and leave as TMA bulk stores
+// (cp.async.bulk shared -> global), which keeps the output bytes off the LSU
+// data path - the first version of this kernel was L1-wavefront-bound (ncu
+// l1tex 83 %), not HBM-bound.  sum ||r||^2 is reduced warp -> CTA -> one fp64
+// partial per CTA, summed in fixed order by a second tiny kernel
+// (deterministic, no atomics).
+#include <stdlib.h>
+
 #include "pbk_common.cuh"
 
 namespace pbk {
@@ -83,139 +89,285 @@ struct BaParams {
   double fx, fy, cx, cy;
 };
 
+// Compile-time shape of the streaming kernel: OPL observations per lane.
+template <int OPL>
+struct BaCfg {
+  static constexpr int kTile = 32 * OPL;              // observations per warp tile
+  static constexpr int kStJc = 0;                     // stage layout (bytes): J_cam rows
+  static constexpr int kStJp = kTile * 48;            //                       J_pt rows
+  static constexpr int kStR = kStJp + kTile * 24;     //                       residuals
+  static constexpr int kStage = kStR + kTile * 8;     // 80 B per observation
+  static constexpr int kRingStages = 3;
+  static constexpr int kObsBytes = kTile * 16;        // one tile of observation records
+  // dynamic shared memory layout
+  static constexpr int kSmemRing = kBaWarps * kStage;
+  static constexpr int kSmemCam = kSmemRing + kBaWarps * kRingStages * kObsBytes;
+  static constexpr int kSmemBars = kSmemCam + kBaWarps * kCam * 8;
+  static constexpr int kSmemCost = kSmemBars + kBaWarps * kRingStages * 8;
+  static constexpr int kSmemBytes = kSmemCost + kBaWarps * 8;
+};
+
 __device__ __forceinline__ uint4 ba_load_obs(const BaParams& P, long long i) {
   return i < P.n_obs ? ld_stream_u4(P.obs + i) : make_uint4(0, 0, 0, 0);
 }
-__device__ __forceinline__ int ba_clamp_pt(const BaParams& P, uint32_t raw) {
-  const int pt = (int)raw;      // out-of-range indices are clamped (the wrapper validates them)
-  return pt < 0 ? 0 : ((long long)pt >= P.n_points ? (int)(P.n_points - 1) : pt);
+__device__ __forceinline__ void ba_load_point(const BaParams& P, uint32_t raw, float (&p)[3]) {
+  int pt = (int)raw;            // out-of-range indices are clamped (the wrapper validates them)
+  pt = pt < 0 ? 0 : ((long long)pt >= P.n_points ? (int)(P.n_points - 1) : pt);
+  const float* pp = P.points + 3ll * pt;
+  p[0] = __ldg(pp); p[1] = __ldg(pp + 1); p[2] = __ldg(pp + 2);
 }
 
-__global__ void __launch_bounds__(kBaWarps * 32, 3)
+// Residual + Jacobian blocks of N observations that share the camera block C
+// (shared memory, 40 doubles).  The block is pulled into registers in three
+// groups of 16 B broadcast loads (R|t, dR/dr0|dR/dr1, dR/dr2) and every
+// coefficient is used for all N observations, so the shared-memory traffic per
+// observation falls with N.  Results go straight to the warp's stage:
+//   J_cam row [lane-slot*12, +12), J_pt row [slot*6, +6), r [slot*2, +2).
+template <int N, int TILE>
+__device__ __forceinline__ void ba_eval(const double* C, const BaParams& P, const float (&pt)[N][3],
+                                        const uint4 (&ob)[N], const int (&slot)[N], const bool (&act)[N],
+                                        const bool (&live)[N], char* st, double& cost) {
+  const double2* C2 = reinterpret_cast<const double2*>(C);
+  float4* sJc = reinterpret_cast<float4*>(st);
+  float2* sJp = reinterpret_cast<float2*>(st + TILE * 48);
+  float2* sR = reinterpret_cast<float2*>(st + TILE * 72);
+  double X[N][3], a[N], b[N], cc[N], d[N];
+  {
+    const double2 c0 = C2[0], c1 = C2[1], c2 = C2[2], c3 = C2[3], c4 = C2[4], c5 = C2[5];
+    const double R0 = c0.x, R1 = c0.y, R2 = c1.x, R3 = c1.y, R4 = c2.x, R5 = c2.y, R6 = c3.x, R7 = c3.y,
+                 R8 = c4.x, t0 = c4.y, t1 = c5.x, t2 = c5.y;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      X[j][0] = (double)pt[j][0]; X[j][1] = (double)pt[j][1]; X[j][2] = (double)pt[j][2];
+      const double uo = (double)__uint_as_float(ob[j].z), vo = (double)__uint_as_float(ob[j].w);
+      const double xc = fma(R0, X[j][0], fma(R1, X[j][1], fma(R2, X[j][2], t0)));
+      const double yc = fma(R3, X[j][0], fma(R4, X[j][1], fma(R5, X[j][2], t1)));
+      const double zc = fma(R6, X[j][0], fma(R7, X[j][1], fma(R8, X[j][2], t2)));
+      const double iz = (zc != 0.0) ? 1.0 / zc : 1.0;
+      const double x = xc * iz, y = yc * iz;
+      const double ru = fma(P.fx, x, P.cx) - uo;
+      const double rv = fma(P.fy, y, P.cy) - vo;
+      // J_t = [[a, 0, b], [0, cc, d]]
+      a[j] = P.fx * iz; b[j] = -P.fx * x * iz;
+      cc[j] = P.fy * iz; d[j] = -P.fy * y * iz;
+      if (act[j]) {
+        if (live[j]) cost = fma(ru, ru, fma(rv, rv, cost));
+        sR[slot[j]] = make_float2((float)ru, (float)rv);
+        // J_pt = J_t * R
+        sJp[slot[j] * 3 + 0] = make_float2((float)fma(a[j], R0, b[j] * R6), (float)fma(a[j], R1, b[j] * R7));
+        sJp[slot[j] * 3 + 1] = make_float2((float)fma(a[j], R2, b[j] * R8), (float)fma(cc[j], R3, d[j] * R6));
+        sJp[slot[j] * 3 + 2] = make_float2((float)fma(cc[j], R4, d[j] * R7), (float)fma(cc[j], R5, d[j] * R8));
+      }
+    }
+  }
+  float jr[N][6];                                  // d/drvec: [row u | row v]
+  {
+    // dR/dr_0 = C[12..20], dR/dr_1 = C[21..29]  (18 doubles, 16 B aligned)
+    double J[18];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const double2 v = C2[6 + k];
+      J[2 * k] = v.x; J[2 * k + 1] = v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const double* Jm = J + 9 * m;                // d(R X)/d r_m = (dR/dr_m) X
+        const double g0 = fma(Jm[0], X[j][0], fma(Jm[1], X[j][1], Jm[2] * X[j][2]));
+        const double g1 = fma(Jm[3], X[j][0], fma(Jm[4], X[j][1], Jm[5] * X[j][2]));
+        const double g2 = fma(Jm[6], X[j][0], fma(Jm[7], X[j][1], Jm[8] * X[j][2]));
+        jr[j][m] = (float)fma(a[j], g0, b[j] * g2);
+        jr[j][3 + m] = (float)fma(cc[j], g1, d[j] * g2);
+      }
+    }
+  }
+  {
+    // dR/dr_2 = C[30..38] (+ pad)
+    double J[10];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const double2 v = C2[15 + k];
+      J[2 * k] = v.x; J[2 * k + 1] = v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const double g0 = fma(J[0], X[j][0], fma(J[1], X[j][1], J[2] * X[j][2]));
+      const double g1 = fma(J[3], X[j][0], fma(J[4], X[j][1], J[5] * X[j][2]));
+      const double g2 = fma(J[6], X[j][0], fma(J[7], X[j][1], J[8] * X[j][2]));
+      jr[j][2] = (float)fma(a[j], g0, b[j] * g2);
+      jr[j][5] = (float)fma(cc[j], g1, d[j] * g2);
+      if (act[j]) {
+        sJc[slot[j] * 3 + 0] = make_float4(jr[j][0], jr[j][1], jr[j][2], (float)a[j]);
+        sJc[slot[j] * 3 + 1] = make_float4(0.f, (float)b[j], jr[j][3], jr[j][4]);
+        sJc[slot[j] * 3 + 2] = make_float4(jr[j][5], 0.f, (float)cc[j], (float)d[j]);
+      }
+    }
+  }
+}
+
+// plain copy of the first `bytes` (multiple of 8) of a stage region to global
+__device__ __forceinline__ void ba_copy_out(float* gdst, const char* ssrc, int bytes, int lane) {
+  for (int off = lane * 8; off < bytes; off += 256)
+    st_stream_f2(reinterpret_cast<char*>(gdst) + off, *reinterpret_cast<const float2*>(ssrc + off));
+}
+
+template <int OPL, int MINB>
+__global__ void __launch_bounds__(kBaWarps * 32, MINB)
 ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
-  __shared__ __align__(16) float stage[kBaWarps][32 * 18];   // 12 (Jc) + 6 (Jp) floats per obs
-  __shared__ __align__(16) double cam_cache[kBaWarps][kCam]; // the warp's current camera block
-  __shared__ double warp_cost[kBaWarps];
+  using Cfg = BaCfg<OPL>;
+  constexpr int kBaOpl = OPL, kBaTile = Cfg::kTile, kBaStage = Cfg::kStage, kBaRingStages = Cfg::kRingStages,
+                kBaObsBytes = Cfg::kObsBytes, kBaStJc = Cfg::kStJc, kBaStJp = Cfg::kStJp, kBaStR = Cfg::kStR,
+                kBaSmemRing = Cfg::kSmemRing, kBaSmemCam = Cfg::kSmemCam, kBaSmemBars = Cfg::kSmemBars,
+                kBaSmemCost = Cfg::kSmemCost;
+  extern __shared__ __align__(128) char ba_smem[];
+  char (*stage)[kBaStage] = reinterpret_cast<char (*)[kBaStage]>(ba_smem);
+  char (*obs_ring)[kBaRingStages * kBaObsBytes] =
+      reinterpret_cast<char (*)[kBaRingStages * kBaObsBytes]>(ba_smem + kBaSmemRing);
+  double (*cam_cache)[kCam] = reinterpret_cast<double (*)[kCam]>(ba_smem + kBaSmemCam);
+  uint64_t (*ring_bars)[kBaRingStages] = reinterpret_cast<uint64_t (*)[kBaRingStages]>(ba_smem + kBaSmemBars);
+  double* warp_cost = reinterpret_cast<double*>(ba_smem + kBaSmemCost);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* st = stage[warp];
+  char* st = stage[warp];
   const double* C = cam_cache[warp];
-  const long long ntiles = (P.n_obs + 31) / 32;
-  const long long stride = (long long)gridDim.x * kBaWarps;
   double cost = 0.0;
   int cached_cam = -1;
 
-  // software pipeline: the observation record is fetched two tiles ahead and
-  // the point one tile ahead, so the DRAM latency of the 16 B record and the
-  // L2 latency of the dependent gather overlap with the fp64 math.
-  long long tile = (long long)blockIdx.x * kBaWarps + warp;
-  uint4 ob = ba_load_obs(P, tile * 32 + lane);
-  uint4 ob_n = ba_load_obs(P, (tile + stride) * 32 + lane);
-  float px, py, pz;
-  {
-    const float* pp = P.points + 3ll * ba_clamp_pt(P, ob.y);
-    px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2);
-  }
+  // Every warp owns a CONTIGUOUS range of 64-observation tiles (observations
+  // are sorted by camera, so consecutive tiles share the camera block and the
+  // 320 B cache is refilled once per ~60 tiles, not once per tile).
+  const long long ntiles = (P.n_obs + kBaTile - 1) / kBaTile;
+  const long long nwarps = (long long)gridDim.x * kBaWarps;
+  const long long gw = (long long)blockIdx.x * kBaWarps + warp;
+  const long long t_begin = gw * ntiles / nwarps, t_end = (gw + 1) * ntiles / nwarps;
+  const int my_tiles = (int)(t_end - t_begin);
 
-  for (; tile < ntiles; tile += stride) {
-    const long long i = tile * 32 + lane;
-    const bool live = i < P.n_obs;
-    const uint4 ob_nn = ba_load_obs(P, (tile + 2 * stride) * 32 + lane);
-    float pxn, pyn, pzn;
-    {
-      const float* pp = P.points + 3ll * ba_clamp_pt(P, ob_n.y);
-      pxn = __ldg(pp); pyn = __ldg(pp + 1); pzn = __ldg(pp + 2);
-    }
-    int cam = (int)ob.x;
-    cam = cam < 0 ? 0 : (cam >= P.n_cams ? P.n_cams - 1 : cam);
-    const double uo = (double)__uint_as_float(ob.z), vo = (double)__uint_as_float(ob.w);
-    const double X = (double)px, Y = (double)py, Z = (double)pz;
-    float2 res = make_float2(0.f, 0.f);
-    float4* s4 = reinterpret_cast<float4*>(st);
-    float2* s2 = reinterpret_cast<float2*>(st + 384);
+  // Observation records stream through a warp-private 4-stage TMA ring (1 KB per
+  // tile, three tiles in flight, no registers held); the dependent point gathers
+  // (L2-resident) are issued one tile ahead into ping-pong registers.
+  WarpRing<kBaObsBytes, kBaRingStages> ring;
+  ring.init(obs_ring[warp], ring_bars[warp], lane);
+  const char* obs_b = reinterpret_cast<const char*>(P.obs);
+  auto issue = [&](int k) {        // lane 0
+    const long long o0 = (t_begin + k) * kBaTile;
+    const long long rem = P.n_obs - o0;
+    if (rem >= kBaTile) ring.issue(k, obs_b + o0 * 16);
+    else ring.issue_bytes(k, obs_b + o0 * 16, (uint32_t)rem * 16u);
+  };
+  if (lane == 0)
+    for (int k = 0; k < kBaRingStages - 1 && k < my_tiles; ++k) issue(k);
 
-    // Observations are sorted by camera in practice, so a warp's 32 records
-    // normally share one camera: its 320 B block is staged in shared memory
-    // once and read by broadcast LDS at the point of use (no registers pinned,
-    // no per-record global gathers).  A tile that straddles cameras takes one
-    // pass per distinct camera.
-    unsigned todo = 0xffffffffu;
-    while (todo) {
-      const int c = __shfl_sync(0xffffffffu, cam, __ffs(todo) - 1);
-      const bool mine = (cam == c) && ((todo >> lane) & 1u);
-      if (c != cached_cam) {
-        __syncwarp();
-        if (lane < kCam / 2)
-          reinterpret_cast<double2*>(cam_cache[warp])[lane] =
-              __ldg(reinterpret_cast<const double2*>(P.cams + (long long)c * kCam) + lane);
-        cached_cam = c;
-        __syncwarp();
-      }
-      if (mine) {
-        const double xc = fma(C[0], X, fma(C[1], Y, fma(C[2], Z, C[9])));
-        const double yc = fma(C[3], X, fma(C[4], Y, fma(C[5], Z, C[10])));
-        const double zc = fma(C[6], X, fma(C[7], Y, fma(C[8], Z, C[11])));
-        const double iz = (zc != 0.0) ? 1.0 / zc : 1.0;
-        const double x = xc * iz, y = yc * iz;
-        const double ru = fma(P.fx, x, P.cx) - uo;
-        const double rv = fma(P.fy, y, P.cy) - vo;
-        if (live) {
-          res = make_float2((float)ru, (float)rv);
-          cost = fma(ru, ru, fma(rv, rv, cost));
-        }
-        // J_t = [[a, 0, b], [0, c, d]]
-        const double a = P.fx * iz, b = -P.fx * x * iz;
-        const double cc = P.fy * iz, d = -P.fy * y * iz;
-        float jr[6];                                     // d/drvec: [row u | row v]
+  // record of observation slot j*32+lane of tile k (zero beyond n_obs)
+  auto read_obs = [&](int k, int j) -> uint4 {
+    const long long i = (t_begin + k) * kBaTile + j * 32 + lane;
+    uint4 v = *reinterpret_cast<const uint4*>(ring.slot(k) + (j * 32 + lane) * 16);
+    if (i >= P.n_obs) v = make_uint4(0, 0, 0, 0);
+    return v;
+  };
+  auto gather = [&](int k, float (&pt)[kBaOpl][3]) {
 #pragma unroll
-        for (int m = 0; m < 3; ++m) {
-          // d(R X)/d r_m = (dR/dr_m) X
-          const double* Jm = C + 12 + 9 * m;
-          const double g0 = fma(Jm[0], X, fma(Jm[1], Y, Jm[2] * Z));
-          const double g1 = fma(Jm[3], X, fma(Jm[4], Y, Jm[5] * Z));
-          const double g2 = fma(Jm[6], X, fma(Jm[7], Y, Jm[8] * Z));
-          jr[m] = (float)fma(a, g0, b * g2);
-          jr[3 + m] = (float)fma(cc, g1, d * g2);
-        }
-        // stage: Jc rows at [lane*12, +12), Jp rows at [384 + lane*6, +6)
-        s4[lane * 3 + 0] = make_float4(jr[0], jr[1], jr[2], (float)a);
-        s4[lane * 3 + 1] = make_float4(0.f, (float)b, jr[3], jr[4]);
-        s4[lane * 3 + 2] = make_float4(jr[5], 0.f, (float)cc, (float)d);
-        s2[lane * 3 + 0] = make_float2((float)fma(a, C[0], b * C[6]), (float)fma(a, C[1], b * C[7]));
-        s2[lane * 3 + 1] = make_float2((float)fma(a, C[2], b * C[8]), (float)fma(cc, C[3], d * C[6]));
-        s2[lane * 3 + 2] = make_float2((float)fma(cc, C[4], d * C[7]), (float)fma(cc, C[5], d * C[8]));
-      }
-      todo &= ~__ballot_sync(0xffffffffu, mine);
+    for (int j = 0; j < kBaOpl; ++j) ba_load_point(P, read_obs(k, j).y, pt[j]);
+  };
+  auto load_cam = [&](int c) {
+    if (c != cached_cam) {
+      __syncwarp();
+      if (lane < kCam / 2)
+        reinterpret_cast<double2*>(cam_cache[warp])[lane] =
+            __ldg(reinterpret_cast<const double2*>(P.cams + (long long)c * kCam) + lane);
+      cached_cam = c;
+      __syncwarp();
     }
-    if (P.r != nullptr && live) st_stream_f2(P.r + 2 * i, res);
+  };
+
+  // one tile: `pt` holds its points, `ptn` receives the next tile's
+  auto process = [&](int k, const float (&pt)[kBaOpl][3], float (&ptn)[kBaOpl][3]) {
+    const long long o0 = (t_begin + k) * kBaTile;
+    if (lane == 0 && k + kBaRingStages - 1 < my_tiles) issue(k + kBaRingStages - 1);
+    if (k + 1 < my_tiles) {
+      ring.wait(k + 1);
+      gather(k + 1, ptn);
+    }
+    uint4 ob[kBaOpl];
+    int cam[kBaOpl], slot[kBaOpl];
+    bool live[kBaOpl];
+    bool same = true;
+#pragma unroll
+    for (int j = 0; j < kBaOpl; ++j) ob[j] = read_obs(k, j);
+    const int c0 = __shfl_sync(0xffffffffu, (int)ob[0].x, 0);
+#pragma unroll
+    for (int j = 0; j < kBaOpl; ++j) {
+      slot[j] = j * 32 + lane;
+      live[j] = o0 + slot[j] < P.n_obs;
+      cam[j] = live[j] ? (int)ob[j].x : c0;
+      same = same && (cam[j] == c0);
+      cam[j] = cam[j] < 0 ? 0 : (cam[j] >= P.n_cams ? P.n_cams - 1 : cam[j]);
+    }
+    const bool uniform = __all_sync(0xffffffffu, same) && c0 >= 0 && c0 < P.n_cams;
+
+    // the previous tile's bulk stores must have drained the stage before it is rewritten
+    if (lane == 0) tma_store_wait_read();
     __syncwarp();
-    const long long o0 = tile * 32;
-    const int nlive = (int)((P.n_obs - o0) < 32 ? (P.n_obs - o0) : 32);
-    if (P.Jc != nullptr) {
-      float* dst = P.Jc + o0 * 12;
+
+    if (uniform) {
+      // the 64 records share one camera: every coefficient of its block is
+      // read from shared memory once for both observations of the lane
+      load_cam(c0);
+      bool act[kBaOpl];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int v4 = j * 32 + lane;               // float4 index within the tile
-        if (v4 * 4 < nlive * 12) st_stream_f4(dst + v4 * 4, s4[v4]);
-      }
-    }
-    if (P.Jp != nullptr) {
-      float* dst = P.Jp + o0 * 6;                   // 24 B per obs: tile base is 16 B aligned
-      const float4* sp = reinterpret_cast<const float4*>(st + 384);
+      for (int j = 0; j < kBaOpl; ++j) act[j] = true;
+      ba_eval<kBaOpl, kBaTile>(C, P, pt, ob, slot, act, live, st, cost);
+    } else {
+      // a tile that straddles cameras takes one pass per distinct camera of each 32-record row
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int v4 = j * 32 + lane;
-        if (v4 < 48) {
-          if (v4 * 4 + 4 <= nlive * 6) st_stream_f4(dst + v4 * 4, sp[v4]);
-          else if (v4 * 4 < nlive * 6) {            // ragged last tile: 8 B granularity
-            st_stream_f2(dst + v4 * 4, make_float2(sp[v4].x, sp[v4].y));
-          }
+      for (int j = 0; j < kBaOpl; ++j) {
+        unsigned todo = 0xffffffffu;
+        while (todo) {
+          const int c = __shfl_sync(0xffffffffu, cam[j], __ffs(todo) - 1);
+          load_cam(c);
+          const float p1[1][3] = {{pt[j][0], pt[j][1], pt[j][2]}};
+          const uint4 o1[1] = {ob[j]};
+          const int s1[1] = {slot[j]};
+          const bool a1[1] = {(cam[j] == c) && ((todo >> lane) & 1u)};
+          const bool l1[1] = {live[j]};
+          ba_eval<1, kBaTile>(C, P, p1, o1, s1, a1, l1, st, cost);
+          todo &= ~__ballot_sync(0xffffffffu, a1[0]);
         }
       }
     }
-    __syncwarp();
-    ob = ob_n; ob_n = ob_nn;
-    px = pxn; py = pyn; pz = pzn;
+
+    // ---- stage -> global.  Full tiles leave as three TMA bulk stores issued by
+    // lane 0 (the LSU never touches the outputs again); the ragged last tile is
+    // copied with plain stores.
+    const long long rem = P.n_obs - o0;
+    if (rem >= kBaTile) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (P.Jc != nullptr) tma_store_1d(P.Jc + o0 * 12, st + kBaStJc, kBaTile * 48);
+        if (P.Jp != nullptr) tma_store_1d(P.Jp + o0 * 6, st + kBaStJp, kBaTile * 24);
+        if (P.r != nullptr) tma_store_1d(P.r + o0 * 2, st + kBaStR, kBaTile * 8);
+        tma_store_commit();
+      }
+    } else {
+      __syncwarp();
+      const int nlive = (int)rem;
+      if (P.Jc != nullptr) ba_copy_out(P.Jc + o0 * 12, st + kBaStJc, nlive * 48, lane);
+      if (P.Jp != nullptr) ba_copy_out(P.Jp + o0 * 6, st + kBaStJp, nlive * 24, lane);
+      if (P.r != nullptr) ba_copy_out(P.r + o0 * 2, st + kBaStR, nlive * 8, lane);
+      __syncwarp();
+    }
+  };
+
+  float ptA[kBaOpl][3], ptB[kBaOpl][3];
+  if (my_tiles > 0) {
+    ring.wait(0);
+    gather(0, ptA);
   }
+  for (int k = 0; k < my_tiles; k += 2) {       // ping-pong: no register rotation between tiles
+    process(k, ptA, ptB);
+    if (k + 1 < my_tiles) process(k + 1, ptB, ptA);
+  }
+  if (lane == 0) tma_store_wait_all();
 
   // cost: warp -> CTA -> partial
 #pragma unroll
@@ -239,9 +391,32 @@ __global__ void ba_cost_sum_kernel(const double* __restrict__ partials, int n, d
   if (lane == 0) *cost = s;
 }
 
+// Kernel shape: PBK_BA_VARIANT = "<OPL><MINB>" (observations per lane, CTAs per SM), for tuning.
+struct BaLaunch {
+  void (*kernel)(BaParams);
+  int smem;
+  int tile;
+};
+static BaLaunch ba_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PBK_BA_VARIANT");
+    v = e ? atoi(e) : 22;
+  }
+  switch (v) {
+    case 13: return {ba_residual_jacobian_kernel<1, 3>, BaCfg<1>::kSmemBytes, BaCfg<1>::kTile};
+    case 14: return {ba_residual_jacobian_kernel<1, 4>, BaCfg<1>::kSmemBytes, BaCfg<1>::kTile};
+    case 23: return {ba_residual_jacobian_kernel<2, 3>, BaCfg<2>::kSmemBytes, BaCfg<2>::kTile};
+    default: return {ba_residual_jacobian_kernel<2, 2>, BaCfg<2>::kSmemBytes, BaCfg<2>::kTile};
+  }
+}
+
 static int ba_grid(const DeviceInfo* di, long long n_obs) {
-  const long long ntiles = (n_obs + 31) / 32;
-  return resident_grid(di, ba_residual_jacobian_kernel, kBaWarps * 32, 0, (ntiles + kBaWarps - 1) / kBaWarps);
+  const BaLaunch L = ba_variant();
+  const long long ntiles = (n_obs + L.tile - 1) / L.tile;
+  if (cudaFuncSetAttribute(L.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem) != cudaSuccess)
+    return -1;
+  return resident_grid(di, L.kernel, kBaWarps * 32, L.smem, (ntiles + kBaWarps - 1) / kBaWarps);
 }
 
 }  // namespace pbk
@@ -293,7 +468,9 @@ int pbk_ba_residual_jacobian(const void* obs, int64_t n_obs, const float* points
   P.n_obs = n_obs; P.n_points = n_points; P.n_cams = n_cams;
   P.fx = fx; P.fy = fy; P.cx = cx; P.cy = cy;
   const int grid = ba_grid(di, n_obs);
-  ba_residual_jacobian_kernel<<<grid, kBaWarps * 32, 0, s>>>(P);
+  const BaLaunch L = ba_variant();
+  PBK_REQUIRE(grid > 0, PBK_ECUDA, "cannot opt in to %d bytes of shared memory", L.smem);
+  L.kernel<<<grid, kBaWarps * 32, L.smem, s>>>(P);
   PBK_CHECK_LAUNCH("ba_residual_jacobian_kernel");
   if (cost != nullptr) {
     ba_cost_sum_kernel<<<1, 32, 0, s>>>(cost_partials, grid, cost);

@@ -133,6 +133,57 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
       : "memory");
 }
 
+// ---- warp-private TMA ring ----------------------------------------------------
+// Every warp owns NST shared-memory slots of one tile each and NST
+// mbarriers.  Lane 0 issues a 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) for
+// tile k+NST-1 while the warp computes tile k, so each warp keeps NST-1 tiles
+// of HBM reads in flight without holding them in registers.  Only the single
+// ragged tile at the end of the array (whose byte count is not a multiple of
+// 16) is loaded with plain loads.
+template <int TILE_BYTES, int NST>
+struct WarpRing {
+  char* slots;
+  uint64_t* bars;
+  __device__ __forceinline__ void init(char* warp_smem, uint64_t* warp_bars, int lane) {
+    slots = warp_smem;
+    bars = warp_bars;
+    if (lane == 0) {
+      for (int s = 0; s < NST; ++s) mbar_init(&bars[s], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ char* slot(int k) const { return slots + (k % NST) * TILE_BYTES; }
+  // lane 0 only; `src` 16 B aligned, full tile
+  __device__ __forceinline__ void issue(int k, const char* src) const {
+    mbar_expect_tx(&bars[k % NST], TILE_BYTES);
+    tma_load_1d(slot(k), src, TILE_BYTES, &bars[k % NST]);
+  }
+  // lane 0 only; ragged tile of `bytes` (multiple of 16, > 0)
+  __device__ __forceinline__ void issue_bytes(int k, const char* src, uint32_t bytes) const {
+    mbar_expect_tx(&bars[k % NST], bytes);
+    tma_load_1d(slot(k), src, bytes, &bars[k % NST]);
+  }
+  __device__ __forceinline__ void wait(int k) const { mbar_wait(&bars[k % NST], (uint32_t)((k / NST) & 1)); }
+};
+
+// 1-D TMA bulk store shared -> global (bulk-group completion).  Writers of the
+// shared-memory source must execute fence_proxy_async_smem() and then
+// synchronise with the issuing thread before the copy is issued.
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... and have completed entirely
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 
 // Persistent grid = what is actually resident: SMs x occupancy of `kernel`
 // (a grid larger than that runs a ragged second wave), capped by the work.

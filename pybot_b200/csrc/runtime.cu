@@ -46,9 +46,52 @@ int current_device_info(const DeviceInfo** out) {
   return PBK_OK;
 }
 
+// ---------------------------------------------------------------- HBM probe
+// mode 0: read-only (16 B loads, xor-reduced into sink), 1: write-only (16 B
+// streaming stores), 2: copy.  Measurement only: HBM3e sustains less on a
+// write-heavy mix than on the read+write copy MEASURED_PEAKS.json quotes, and
+// the BA / reproject kernels are 70-85 % writes.
+template <int MODE>
+__global__ void __launch_bounds__(256) hbm_probe_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                        long long n16, uint32_t* sink) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    if (MODE == 0) {
+      const uint4 v = ld_stream_u4(src + i);
+      acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+    } else if (MODE == 1) {
+      st_stream_u4(dst + i, make_uint4((uint32_t)i, 1u, 2u, 3u));
+    } else {
+      st_stream_u4(dst + i, ld_stream_u4(src + i));
+    }
+  }
+  if (MODE == 0 && (acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u) *sink = acc.x;   // keeps the loads alive
+}
+
 }  // namespace pbk
 
 extern "C" {
+
+int pbk_hbm_probe(int mode, const void* src, void* dst, int64_t bytes, uint32_t* sink, pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(mode >= 0 && mode <= 2 && bytes >= 16 && sink != nullptr, PBK_EINVAL, "bad arguments");
+  PBK_REQUIRE((mode == 1 || src != nullptr) && (mode == 0 || dst != nullptr), PBK_EINVAL, "NULL device pointer");
+  PBK_REQUIRE(aligned16(src) && aligned16(dst), PBK_EALIGN, "device pointers must be 16-byte aligned");
+  const DeviceInfo* di;
+  int rc = current_device_info(&di);
+  if (rc) return rc;
+  const long long n16 = bytes / 16;
+  const int grid = di->sm_count * 8;
+  cudaStream_t s = as_stream(stream);
+  const uint4* a = static_cast<const uint4*>(src);
+  uint4* b = static_cast<uint4*>(dst);
+  if (mode == 0) hbm_probe_kernel<0><<<grid, 256, 0, s>>>(a, b, n16, sink);
+  else if (mode == 1) hbm_probe_kernel<1><<<grid, 256, 0, s>>>(a, b, n16, sink);
+  else hbm_probe_kernel<2><<<grid, 256, 0, s>>>(a, b, n16, sink);
+  PBK_CHECK_LAUNCH("hbm_probe_kernel");
+  return PBK_OK;
+}
 
 int pbk_version(void) { return PBK_VERSION; }
 

@@ -40,35 +40,6 @@ struct XformParams {
   int has_scale;
 };
 
-// ---- warp-private TMA ring ----------------------------------------------------
-// Every warp owns NST shared-memory slots of one 128-point tile each and NST
-// mbarriers.  Lane 0 issues a 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) for
-// tile k+NST-1 while the warp computes tile k, so each warp keeps NST-1 tiles
-// of HBM reads in flight without holding them in registers.  Only the single
-// ragged tile at the end of the array (whose byte count is not a multiple of
-// 16) is loaded with plain loads.
-template <int TILE_BYTES, int NST>
-struct WarpRing {
-  char* slots;
-  uint64_t* bars;
-  __device__ __forceinline__ void init(char* warp_smem, uint64_t* warp_bars, int lane) {
-    slots = warp_smem;
-    bars = warp_bars;
-    if (lane == 0) {
-      for (int s = 0; s < NST; ++s) mbar_init(&bars[s], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-  }
-  __device__ __forceinline__ char* slot(int k) const { return slots + (k % NST) * TILE_BYTES; }
-  // lane 0 only; `src` 16 B aligned, full tile
-  __device__ __forceinline__ void issue(int k, const char* src) const {
-    mbar_expect_tx(&bars[k % NST], TILE_BYTES);
-    tma_load_1d(slot(k), src, TILE_BYTES, &bars[k % NST]);
-  }
-  __device__ __forceinline__ void wait(int k) const { mbar_wait(&bars[k % NST], (uint32_t)((k / NST) & 1)); }
-};
-
 // ragged tile: plain loads of `valid_bytes` (multiple of 4), zero fill to `bytes`
 __device__ __forceinline__ void warp_load_ragged(const char* __restrict__ g, char* s, int lane,
                                                  int bytes, int valid_bytes) {

@@ -312,6 +312,13 @@ def popc_probe(mode=0, ctas=None, iters=2000):
     return n.value
 
 
+def hbm_probe(mode, src, dst, sink):
+    """Launches the HBM probe (0 read / 1 write / 2 copy) over the given uint8 CUDA tensors."""
+    ref = dst if mode == 1 else src
+    _ffi.check(_ffi.lib().pbk_hbm_probe(int(mode), _ffi.ptr(src), _ffi.ptr(dst), int(ref.numel()),
+                                        _ffi.ptr(sink), _ffi.stream_ptr()))
+
+
 # ----------------------------------------------------------------------- BA
 class BAProblemDevice(object):
     """Device-resident BA inputs + outputs (allocated once, reused per eval)."""
