@@ -37,6 +37,22 @@ L2_FLUSH_BYTES = 256 << 20
 
 
 # ------------------------------------------------------------------ helpers
+def ncu_traffic(kernel, scale=1.0):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the
+    committed `ncu --set full` capture (profiles/ncu_traffic.json, written by
+    scripts/ncu_summary.py), scaled to this launch's size where the capture ran a
+    smaller problem; None if there is no capture."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        e = d["kernels"][kernel]
+        return {"bytes": e["dram_bytes"] * scale, "capture": d["tag"],
+                "captured_at": e.get("problem", ""), "scaled_by": scale}
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -163,9 +179,47 @@ def timed_steps(D, step, steps, warmup, flush=None, inner=None):
     return D.max_over_ranks(total), D.max_over_ranks(inner_ms)
 
 
+L2_NOTE = ("L2 flushed between timed steps: 256 MiB written, then 256 MiB of another buffer read so "
+           "the flush's own dirty lines are written back before the timed kernel starts")
+
+
 def make_flush(torch):
-    buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
-    return lambda: buf.zero_()
+    """Flush = write a buffer larger than L2, then read a second one: after the
+    write alone L2 is full of DIRTY lines whose write-back (126 MB, ~20 us of
+    HBM time) would be charged to the next 40-100 us kernel."""
+    from pybot_b200 import ops
+    wbuf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    rbuf = torch.zeros(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    sink = torch.zeros(4, dtype=torch.int32, device="cuda")
+
+    def flush():
+        wbuf.zero_()
+        ops.hbm_probe(0, rbuf, None, sink)
+    return flush
+
+
+def copy_at_size(torch, nbytes_read, nbytes_written, reps=5):
+    """HBM context for short kernels: best-of-N device time of a plain copy that
+    moves the same number of bytes (read nbytes_read, write nbytes_written is
+    approximated by a copy of (r+w)/2 bytes).  At 200-400 MB a copy reaches only
+    ~80-87 % of the multi-GB figure in MEASURED_PEAKS.json (ramp + tail)."""
+    from pybot_b200 import ops
+    half = ((nbytes_read + nbytes_written) // 2 + 15) // 16 * 16
+    a = torch.zeros(half, dtype=torch.uint8, device="cuda")
+    b = torch.empty(half, dtype=torch.uint8, device="cuda")
+    sink = torch.zeros(4, dtype=torch.int32, device="cuda")
+    best = None
+    for i in range(reps + 2):
+        e0, e1 = ev_pair(torch)
+        e0.record()
+        b.copy_(a)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            t = e0.elapsed_time(e1)
+            best = t if best is None else min(best, t)
+    del a, b, sink
+    return 2.0 * half / (best * 1e-3) / 1e9
 
 
 def ev_pair(torch):
@@ -256,7 +310,7 @@ def run_c3(D, args):
                                "(%d descriptors, %d MB), k=2 + ratio 0.75 + mutual; database sharded by "
                                "keyframe range over %d GPU(s)" % (nkf, nt_total, nt_total * 32 >> 20, D.world),
                    "nq": nq, "nt": nt_total, "shard_rows": int(shard.shape[0]),
-                   "l2": "256 MiB L2 flush between timed steps",
+                   "l2": L2_NOTE,
                    "state": "database resident in HBM; queries are the per-step input"},
         "e2e": {"value": pairs * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": "Gpairs/s",
                 "h2d_bytes_per_step": nq * 32,
@@ -271,7 +325,8 @@ def run_c3(D, args):
         res["roofline"] = {
             "bound": "popc", "kernel": "hamming_knn2_kernel (+ split merge)",
             "achieved": popc_rate / 1e12, "peak": pk["popc_per_s"] / 1e12, "unit": "Tpopc/s",
-            "frac": popc_rate / pk["popc_per_s"], "traffic": None,
+            "frac": popc_rate / pk["popc_per_s"],
+            "traffic": ncu_traffic("hamming_knn2_kernel<1>", scale=float(shard.shape[0]) / 2.5e6),
             "algorithmic": "8 POPC.32 per pair (256 bits); achieved = nq*nt_local*8 / kernel time",
             "peak_source": "pbk_popc_peak_probe mode 0, measured in this run (burst)",
             "kernel_ms": knn_ms / args.steps, "kernel_share_of_step": knn_ms / total_ms,
@@ -367,15 +422,16 @@ def run_c2(D, args, n=10_000_000):
         "ms_per_step": out["project_plain"]["ms"], "dtype": "f64 registers, f32 in/out",
         "config": {"workload": "C2 batched SE(3) transform + pinhole Camera.project of %d points "
                                "(float32 AoS in, float32 pixels out)" % n,
-                   "l2": "256 MiB L2 flush between timed steps"},
+                   "l2": L2_NOTE},
         "variants": out,
         "e2e": {"value": n * args.steps / (ems * 1e-3) / 1e6, "unit": "Mpts/s",
                 "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": n * 8},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "kernel": "project_points_kernel<float,false,false>",
                      "achieved": out["project_plain"]["GBps"], "peak": hbm, "unit": "GB/s",
-                     "frac": out["project_plain"]["GBps"] / hbm, "traffic": None, "peak_source": src,
-                     "algorithmic": "12 B in + 8 B out = 20 B/pt"},
+                     "frac": out["project_plain"]["GBps"] / hbm, "traffic": ncu_traffic("project_points_kernel<float, 0, 0>"),
+                     "peak_source": src, "algorithmic": "12 B in + 8 B out = 20 B/pt",
+                     "copy_same_bytes_GBps": copy_at_size(torch, n * 12, n * 8)},
     }
     if D.rank == 0:
         res["cpu_baseline"] = cpu_baseline_c2(X_np[:1_000_000], cam)
@@ -448,14 +504,19 @@ def run_c4(D, args):
         "ms_per_step": ms / args.steps, "scaling": "strong", "dtype": "f64 registers, f32 in/out",
         "config": {"workload": "C4 BA residual + 2x6/2x3 Jacobians: 1000 cameras, 1M points, %d "
                                "observations sharded over %d GPU(s)" % (n_obs, D.world),
-                   "l2": "256 MiB L2 flush between timed steps"},
+                   "l2": L2_NOTE},
         "e2e": {"value": n_obs * args.steps / (ems * 1e-3) / 1e6, "unit": "Mobs/s",
                 "h2d_bytes_per_step": int(rv.nbytes + tv.nbytes + pts.nbytes), "d2h_bytes_per_step": 8},
         "gpu_launches": 3 * args.steps, "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "ba_residual_jacobian_kernel", "achieved": gbps,
-                     "peak": hbm, "unit": "GB/s", "frac": gbps / hbm, "traffic": None, "peak_source": src,
+                     "peak": hbm, "unit": "GB/s", "frac": gbps / hbm,
+                     "traffic": ncu_traffic("ba_residual_jacobian_kernel") if D.world == 1 else None,
+                     "peak_source": src,
                      "algorithmic": "16 B read + 8 + 48 + 24 B written = 96 B/obs",
-                     "kernel_ms": kms / args.steps},
+                     "kernel_ms": kms / args.steps,
+                     "copy_same_bytes_GBps": copy_at_size(torch, local_obs * 16, local_obs * 80),
+                     "note": "83 % of the traffic is writes; a write-only stream of this size sustains "
+                             "~5.3 TB/s on B200 HBM3e (scripts/hbm_probe.py), below the copy figure"},
     }
     if D.rank == 0 and D.world == 1:
         res["cpu_baseline"] = cpu_baseline_c4(prob)
@@ -527,7 +588,8 @@ def run_c5(D, args, batch=64):
                 "note": "%d frames per e2e step (pinned host buffers)" % eb},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "kernel": "reproject_dense_kernel<float,true> (textured)",
-                     "achieved": gbps, "peak": hbm, "unit": "GB/s", "frac": gbps / hbm, "traffic": None,
+                     "achieved": gbps, "peak": hbm, "unit": "GB/s", "frac": gbps / hbm,
+                     "traffic": ncu_traffic("reproject_dense_kernel<float, 1>", scale=batch / 16.0),
                      "peak_source": src, "algorithmic": "4+3 B in, 12+3 B out = 22 B/pt"},
     }
     if D.rank == 0:

@@ -22,9 +22,9 @@
 //   project:   OpenCV's projectPoints loop, fp64, no FMA (oracle/model.py),
 //              one rounding to the output dtype.
 //
-// Order-preserving compaction (x[valid]) is fused: CTA tiles of 1024 points
-// take tickets in order and chain their valid counts with a decoupled
-// look-back, so the compacted outputs are written in the same pass.
+// Order-preserving compaction (x[valid]) is fused: tiles of 1024 points chain
+// their valid counts with a decoupled look-back (project_compact_kernel), so
+// the compacted outputs are written in the same pass that reads X.
 #include "pbk_common.cuh"
 
 namespace pbk {
@@ -131,16 +131,21 @@ struct Projected {
 template <typename T> struct OutPix;
 template <> struct OutPix<float> {
   using vec = float2;
-  static __device__ __forceinline__ bool in_bounds(float u, float v, int W, int H) {
-    return u >= 0.f && u < (float)W && v >= 0.f && v < (float)H;
+  static __device__ __forceinline__ float2 make(float u, float v) { return make_float2(u, v); }
+  static __device__ __forceinline__ void store_vec(float* uv, long long i, float2 p) { st_stream_f2(uv + 2 * i, p); }
+  static __device__ __forceinline__ bool in_bounds(float u, float v, float W, float H) {
+    return u >= 0.f && u < W && v >= 0.f && v < H;
   }
   static __device__ __forceinline__ void store(float* uv, long long i, float u, float v) {
     st_stream_f2(uv + 2 * i, make_float2(u, v));
   }
 };
 template <> struct OutPix<double> {
-  static __device__ __forceinline__ bool in_bounds(double u, double v, int W, int H) {
-    return u >= 0.0 && u < (double)W && v >= 0.0 && v < (double)H;
+  using vec = double2;
+  static __device__ __forceinline__ double2 make(double u, double v) { return make_double2(u, v); }
+  static __device__ __forceinline__ void store_vec(double* uv, long long i, double2 p) { store(uv, i, p.x, p.y); }
+  static __device__ __forceinline__ bool in_bounds(double u, double v, double W, double H) {
+    return u >= 0.0 && u < W && v >= 0.0 && v < H;
   }
   static __device__ __forceinline__ void store(double* uv, long long i, double u, double v) {
     double2 o = make_double2(u, v);
@@ -189,6 +194,15 @@ __device__ __forceinline__ void project_one(const pbk_project_params& P, const d
   v = __dadd_rn(__dmul_rn(y, P.fy), P.cy);
 }
 
+// depth_from_projection (camera_utils.py:736-743): z of the extrinsics * X, the
+// mul,fma,fma,fma chain of np.dot (see transform_points_kernel).
+__device__ __forceinline__ double depth_of(const pbk_project_params& P, const double X[3]) {
+  double acc = __dmul_rn(P.Rz[0], X[0]);
+  acc = __fma_rn(P.Rz[1], X[1], acc);
+  acc = __fma_rn(P.Rz[2], X[2], acc);
+  return __fma_rn(P.tz, 1.0, acc);
+}
+
 // status word of the decoupled look-back: [63:62] state, [61:0] value
 constexpr unsigned long long kStateAgg = 1ull << 62;
 constexpr unsigned long long kStatePrefix = 2ull << 62;
@@ -205,22 +219,15 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
 
 // MODE 0: plain projection (no depth, masks, count).
 // MODE 1: depth / masks / valid flags per runtime switches, outputs uncompacted.
-// MODE 2: as 1 + order-preserving compaction of uv / depth (decoupled look-back
-//         over CTA tiles of 1024 points handed out by an atomic ticket).
-// scratch layout (MODE 2): [0] ticket counter (u64), [1 .. ntiles] tile status words.
+// (the compacting variant is project_compact_kernel below)
 template <typename T, bool DIST, int MODE>
 __global__ void __launch_bounds__(kWarps * 32)
 project_points_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
                       double* __restrict__ depth, uint8_t* __restrict__ valid_out,
-                      long long* __restrict__ count, unsigned long long* __restrict__ scratch,
-                      const __grid_constant__ pbk_project_params P) {
+                      long long* __restrict__ count, const __grid_constant__ pbk_project_params P) {
   constexpr int NST = RingCfg<T>::kStages;
   constexpr int kInBytes = kTilePts * 3 * sizeof(T);
   extern __shared__ __align__(128) char dyn_smem[];
-  __shared__ int warp_count[kWarps];
-  __shared__ long long s_ticket[2];
-  __shared__ long long s_part[kWarps];
-  __shared__ int s_has[kWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t* bars = reinterpret_cast<uint64_t*>(dyn_smem + kWarps * NST * kInBytes) + warp * NST;
   WarpRing<kInBytes, NST> ring;
@@ -228,64 +235,31 @@ project_points_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
 
   const long long nfull = n / kTilePts;                    // full 128-point tiles
   const long long nwt = (n + kTilePts - 1) / kTilePts;     // warp tiles
-  const long long ncta = (n + kCtaPts - 1) / kCtaPts;      // CTA tiles (MODE 2)
   const char* Xb = reinterpret_cast<const char*>(X);
   const bool need_depth = MODE != 0 && ((depth != nullptr) || P.check_depth);
+  const T Wf = (T)P.width, Hf = (T)P.height;      // image bounds in the pixel dtype (exact: < 2^24)
 
-  // warp tile index of step k.  MODE 2: CTA tiles are handed out by an atomic
-  // ticket, exactly ONE tile ahead of the one being computed (s_ticket[k & 1]):
-  // taking several tickets at once would make a CTA sit on consecutive tiles and
-  // serialise the look-back chain of every CTA behind it.
   const long long stride = (long long)gridDim.x * kWarps;
   const long long t0 = (long long)blockIdx.x * kWarps + warp;
-  auto wtile = [&](int k) -> long long {
-    if (MODE == 2) {
-      const long long c = s_ticket[k & 1];
-      return c >= ncta ? nwt : c * kWarps + warp;
-    }
-    return t0 + (long long)k * stride;
-  };
-  if (MODE == 2) {
-    if (threadIdx.x == 0) s_ticket[0] = (long long)atomicAdd(scratch, 1ull);
-    __syncthreads();
-    if (lane == 0) {
-      const long long t = wtile(0);
-      if (t < nfull) ring.issue(0, Xb + t * kInBytes);
-    }
-  } else if (lane == 0) {
+  if (lane == 0) {
     for (int k = 0; k < NST - 1; ++k) {
-      const long long t = wtile(k);
+      const long long t = t0 + (long long)k * stride;
       if (t < nfull) ring.issue(k, Xb + t * kInBytes);
     }
   }
 
   long long local_count = 0;
-  for (int k = 0;; ++k) {
-    long long cta_tile = 0;
-    if (MODE == 2) {
-      cta_tile = s_ticket[k & 1];
-      if (cta_tile >= ncta) break;
-      if (threadIdx.x == 0) s_ticket[(k + 1) & 1] = (long long)atomicAdd(scratch, 1ull);
-      __syncthreads();                  // (A0) next ticket visible
-      if (lane == 0) {
-        const long long t = wtile(k + 1);
-        if (t < nfull) ring.issue(k + 1, Xb + t * kInBytes);
-      }
-    }
-    const long long tile = wtile(k);
-    if (MODE != 2) {
-      if (tile >= nwt) break;
-      const long long nxt = tile + (NST - 1) * stride;
-      if (lane == 0 && nxt < nfull) ring.issue(k + NST - 1, Xb + nxt * kInBytes);
-    }
+  int k = 0;
+  for (long long tile = t0; tile < nwt; tile += stride, ++k) {
+    const long long nxt = tile + (NST - 1) * stride;
+    if (lane == 0 && nxt < nfull) ring.issue(k + NST - 1, Xb + nxt * kInBytes);
     const long long first = tile * kTilePts;
     const long long rem = n - first;
-    const int npts = rem <= 0 ? 0 : (rem < kTilePts ? (int)rem : kTilePts);
+    const int npts = rem < kTilePts ? (int)rem : kTilePts;
     char* st = ring.slot(k);
     if (npts == kTilePts) ring.wait(k);
     else {
-      if (npts > 0) warp_load_ragged(Xb + first * 3 * sizeof(T), st, lane, kInBytes, npts * 3 * (int)sizeof(T));
-      else warp_load_ragged(Xb, st, lane, kInBytes, 0);
+      warp_load_ragged(Xb + first * 3 * sizeof(T), st, lane, kInBytes, npts * 3 * (int)sizeof(T));
       __syncwarp();
     }
     double Xp[4][3];
@@ -305,118 +279,309 @@ project_points_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
       if (MODE != 0) {
         bool good = (j * 32 + lane) < npts;
         if (need_depth) {
-          double acc = __dmul_rn(P.Rz[0], Xp[j][0]);
-          acc = __fma_rn(P.Rz[1], Xp[j][1], acc);
-          acc = __fma_rn(P.Rz[2], Xp[j][2], acc);
-          acc = __fma_rn(P.tz, 1.0, acc);
-          dep[j] = acc;
-          if (P.check_depth) good = good && (acc >= P.min_depth);
+          dep[j] = depth_of(P, Xp[j]);
+          if (P.check_depth) good = good && (dep[j] >= P.min_depth);
         }
-        if (P.check_bounds) good = good && OutPix<T>::in_bounds(uo[j], vo[j], P.width, P.height);
+        if (P.check_bounds) good = good && OutPix<T>::in_bounds(uo[j], vo[j], Wf, Hf);
         ok[j] = good;
       }
     }
 
-    if (MODE == 0) {
-      if (npts == kTilePts) {
+    if (npts == kTilePts) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) OutPix<T>::store(uv, first + j * 32 + lane, uo[j], vo[j]);
-      } else {
+      for (int j = 0; j < 4; ++j) OutPix<T>::store(uv, first + j * 32 + lane, uo[j], vo[j]);
+    } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j * 32 + lane < npts) OutPix<T>::store(uv, first + j * 32 + lane, uo[j], vo[j]);
-      }
-      continue;
+      for (int j = 0; j < 4; ++j)
+        if (j * 32 + lane < npts) OutPix<T>::store(uv, first + j * 32 + lane, uo[j], vo[j]);
     }
+    if (MODE == 0) continue;
 
-    unsigned m[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) m[j] = __ballot_sync(0xffffffffu, ok[j]);
-    const int wc = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
-    if (valid_out != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int p = j * 32 + lane;
-        if (p < npts) valid_out[first + p] = ok[j] ? 1 : 0;
-      }
-    }
-
-    if (MODE == 1) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int p = j * 32 + lane;
-        if (p < npts) {
-          OutPix<T>::store(uv, first + p, uo[j], vo[j]);
-          if (depth != nullptr) st_stream_d1(depth + first + p, dep[j]);
-        }
-      }
-      local_count += wc;
-      continue;
-    }
-
-    // ---- MODE 2: CTA aggregate, decoupled look-back, ordered scatter.
-    // The look-back inspects 256 predecessor tiles per round (one per thread):
-    // tiles complete at ~250 per microsecond across the chip, so a 32-wide
-    // window could not keep up and every CTA ended up waiting at the barrier.
-    if (lane == 0) warp_count[warp] = wc;
-    __syncthreads();                    // (A)
-    int agg = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) agg += warp_count[w];
-    unsigned long long* status = scratch + 1;
-    if (threadIdx.x == 0)
-      st_status(status + cta_tile, (cta_tile == 0 ? kStatePrefix : kStateAgg) | (unsigned long long)agg);
-    long long excl = 0;
-    if (cta_tile > 0) {
-      long long look = cta_tile - 1;
-      while (true) {
-        const long long idx = look - (long long)threadIdx.x;      // thread 0 = nearest predecessor
-        unsigned long long sw = kStatePrefix;                     // virtual prefix 0 before tile 0
-        if (idx >= 0) {
-          do { sw = ld_status(status + idx); } while ((sw >> 62) == 0);
-        }
-        const unsigned is_prefix = __ballot_sync(0xffffffffu, (sw >> 62) == 2);
-        long long val = (long long)(sw & kValueMask);
-        if (is_prefix && lane > __ffs(is_prefix) - 1) val = 0;   // stop at the nearest prefix
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-        if (lane == 0) {
-          s_part[warp] = val;
-          s_has[warp] = is_prefix != 0;
-        }
-        __syncthreads();                // (B1)
-        bool found = false;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-          if (!found) {
-            excl += s_part[w];
-            found = s_has[w] != 0;
-          }
-        }
-        if (found) break;
-        look -= kWarps * 32;
-        __syncthreads();                // (B2) s_part reuse
-      }
-      if (threadIdx.x == 0) st_status(status + cta_tile, kStatePrefix | (unsigned long long)(excl + agg));
-    }
-    if (threadIdx.x == 0 && cta_tile == ncta - 1 && count != nullptr) *count = excl + agg;
-    long long base = excl;
-    for (int w = 0; w < warp; ++w) base += warp_count[w];
-    const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (ok[j]) {
-        const long long o = base + __popc(m[j] & lt);
-        OutPix<T>::store(uv, o, uo[j], vo[j]);
-        if (depth != nullptr) st_stream_d1(depth + o, dep[j]);
+      const int p = j * 32 + lane;
+      local_count += __popc(__ballot_sync(0xffffffffu, ok[j]));
+      if (p < npts) {
+        if (valid_out != nullptr) valid_out[first + p] = ok[j] ? 1 : 0;
+        if (depth != nullptr) st_stream_d1(depth + first + p, dep[j]);
       }
-      base += __popc(m[j]);
     }
-    __syncthreads();                    // (C) warp_count / s_part reuse
   }
   if (MODE == 1 && count != nullptr) {
     if (lane == 0 && local_count)
       atomicAdd(reinterpret_cast<unsigned long long*>(count), (unsigned long long)local_count);
+  }
+}
+
+// Phase clocks of the compaction kernel (diagnostic; compiled in with -DPBK_COMPACT_TIMING)
+#ifdef PBK_COMPACT_TIMING
+__device__ unsigned long long g_ct_clk[16];
+#define CT_T0() long long _t0 = clock64()
+#define CT_ACC(slot)                                                        \
+  do {                                                                      \
+    const long long _t1 = clock64();                                        \
+    if (lane == 0) atomicAdd(&g_ct_clk[slot], (unsigned long long)(_t1 - _t0)); \
+    _t0 = _t1;                                                              \
+  } while (0)
+#else
+#define CT_T0() do {} while (0)
+#define CT_ACC(slot) do {} while (0)
+#endif
+
+// ------------------------------------------------- projection + x[valid]
+// Order-preserving compaction fused into the projection pass (no second read
+// of X, no library scan): a chained scan over 1024-point tiles with a
+// decoupled look-back, software-pipelined two tiles deep so that the compute
+// path never waits for another CTA.
+//
+// Persistent, co-resident CTAs (cooperative launch) of 8 compute warps + 2 scan
+// warps.  CTA b owns tiles b, b+G, b+2G ...: all CTAs work on one generation of
+// G consecutive tiles at a time, so a tile's predecessors publish their
+// aggregates when it does.
+//   compute warps read tile i from a 2-stage TMA input ring (the last warp to
+//                 consume a stage refills it), project it (thread t owns points
+//                 t + 256 k), park uv /
+//                 depth in one of three shared-memory buffers, publish the tile
+//                 aggregate (the last warp to finish does it, so it never
+//                 queues behind a look-back), then scatter tile i-2 whose base
+//                 offset has been resolved meanwhile;
+//   scan warp w   (tiles of parity w) scans the 32 (row, warp) valid counts of a
+//                 finished tile and resolves its exclusive prefix by look-back over
+//                 predecessor tiles (256 status words per probe: [63:62] state,
+//                 [61:0] count).  A look-back costs a few L2 round trips plus
+//                 the jitter of the slowest CTA of the generation (~7k clocks
+//                 measured) against ~3.5k clocks of fp64 math per tile: two
+//                 scan warps and two tiles of slack keep it off the critical
+//                 path.  Versions that waited for the prefix inside the tile,
+//                 took tickets ahead of time, or published the aggregate from
+//                 the scan warp ran 1.5-6x slower.
+// Valid points are written at base + rank; lanes of a warp hold consecutive
+// ranks, so the stores are contiguous runs.
+// scratch layout: [0] unused, [1 .. ntiles] tile status words (zeroed per call).
+constexpr int kCtWarps = 8;                          // compute warps
+constexpr int kCtThreads = kCtWarps * 32;            // 256 compute threads
+constexpr int kCtBlock = kCtThreads + 64;            // + 2 scan warps
+constexpr int kCtPpt = 4;                            // points per thread
+constexpr int kCtTile = kCtThreads * kCtPpt;         // 1024 points per tile
+constexpr int kCtSegs = kCtPpt * kCtWarps;           // 32 (row, warp) segments
+constexpr int kCtBufs = 3;                           // parked-output buffers (pipeline depth 2)
+
+template <typename T>
+struct CompactSmem {
+  static constexpr int kIn = kCtTile * 3 * (int)sizeof(T);             // one input stage
+  static constexpr int kOut = kCtTile * (2 * (int)sizeof(T) + 8);      // parked uv + depth of one tile
+  static constexpr int kBytes = 2 * kIn + kCtBufs * kOut;
+};
+
+template <typename T, bool DIST>
+__global__ void __launch_bounds__(kCtBlock, sizeof(T) == 4 ? 3 : 1)
+project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
+                       double* __restrict__ depth, uint8_t* __restrict__ valid_out,
+                       long long* __restrict__ count, unsigned long long* __restrict__ scratch,
+                       const __grid_constant__ pbk_project_params P) {
+  using SM = CompactSmem<T>;
+  using UV = typename OutPix<T>::vec;
+  extern __shared__ __align__(128) char dyn_smem[];
+  __shared__ __align__(8) uint64_t in_full[2], cnt_ready[2], base_ready[kCtBufs];
+  __shared__ long long s_base[kCtBufs];
+  __shared__ int s_cnt[kCtBufs][kCtSegs], s_excl[kCtBufs][kCtSegs], s_aggsum[2], s_arrived[2], s_consumed[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long ntiles = (n + kCtTile - 1) / kCtTile;
+  unsigned long long* status = scratch + 1;
+  // generation i of this CTA is tile i * gridDim.x + blockIdx.x
+  const int my_tiles = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  auto tile_of = [&](int i) -> long long { return (long long)i * gridDim.x + blockIdx.x; };
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&in_full[s], 1);
+      mbar_init(&cnt_ready[s], kCtWarps);
+      s_aggsum[s] = 0;
+      s_arrived[s] = 0;
+      s_consumed[s] = 0;
+    }
+    for (int q = 0; q < kCtBufs; ++q) mbar_init(&base_ready[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // input stage (i & 1) <- tile of generation i: one TMA bulk copy (plus a < 16 B
+  // tail by hand), issued by a single thread
+  auto feed = [&](int i) {
+    if (i >= my_tiles) return;
+    const int st = i & 1;
+    const long long first = tile_of(i) * kCtTile;
+    const int npts = (n - first) < kCtTile ? (int)(n - first) : kCtTile;
+    const int bytes = npts * 3 * (int)sizeof(T), bulk = bytes & ~15;
+    char* dst = dyn_smem + st * SM::kIn;
+    const char* src = reinterpret_cast<const char*>(X + first * 3);
+    for (int o = bulk; o < bytes; o += 4)
+      *reinterpret_cast<uint32_t*>(dst + o) = *reinterpret_cast<const uint32_t*>(src + o);
+    if (bulk > 0) {
+      mbar_expect_tx(&in_full[st], (uint32_t)bulk);
+      tma_load_1d(dst, src, (uint32_t)bulk, &in_full[st]);
+    } else {
+      mbar_arrive(&in_full[st]);
+    }
+  };
+  if (tid == 0) {
+    feed(0);
+    feed(1);
+  }
+
+  if (warp >= kCtWarps) {
+    // ============================================================== scan warps
+    const int w = warp - kCtWarps;                   // stage / tile parity owned by this warp
+    for (int i = w; i < my_tiles; i += 2) {
+      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+      const int q = i % kCtBufs;
+      // tile i's segment counts -> exclusive offsets, aggregate
+      CT_T0();
+      mbar_wait(&cnt_ready[w], ph);
+      CT_ACC(2);
+      const int c = s_cnt[q][lane];
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += a;
+      }
+      s_excl[q][lane] = inc - c;
+      const long long agg = __shfl_sync(0xffffffffu, inc, 31);
+      const long long tile = tile_of(i);              // its aggregate was published by the compute warps
+      long long excl = 0;
+      if (tile > 0) {
+        long long look = tile - 1;
+        bool done = false;
+        while (!done) {
+          unsigned long long sw[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const long long idx = look - (lane + 32 * j);         // position 0 = nearest predecessor
+            sw[j] = idx >= 0 ? ld_status(status + idx) : kStatePrefix;   // virtual prefix 0 before tile 0
+          }
+          long long acc = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (!done) {                                          // warp-uniform
+              const long long idx = look - (lane + 32 * j);
+              while ((sw[j] >> 62) == 0) sw[j] = ld_status(status + idx);
+              const unsigned is_prefix = __ballot_sync(0xffffffffu, (sw[j] >> 62) == 2);
+              long long val = (long long)(sw[j] & kValueMask);
+              if (is_prefix && lane > __ffs(is_prefix) - 1) val = 0;   // stop at the nearest prefix
+              acc += val;
+              done = is_prefix != 0;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          excl += acc;
+          look -= 256;
+        }
+        if (lane == 0) st_status(status + tile, kStatePrefix | (unsigned long long)(excl + agg));
+      }
+      CT_ACC(3);
+      __syncwarp();                         // every lane's s_excl store precedes the arrive
+      if (lane == 0) {
+        s_base[q] = excl;
+        if (tile == ntiles - 1 && count != nullptr) *count = excl + agg;
+        mbar_arrive(&base_ready[q]);
+      }
+    }
+    return;
+  }
+
+  // ============================================================ compute warps
+  const bool need_depth = (depth != nullptr) || P.check_depth;
+  const T Wf = (T)P.width, Hf = (T)P.height;      // image bounds in the pixel dtype (exact: < 2^24)
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned m1[kCtPpt], m2[kCtPpt];          // ballots of tiles i-1 and i-2
+  for (int i = 0; i < my_tiles + 2; ++i) {
+    unsigned m[kCtPpt];
+    CT_T0();
+    if (i < my_tiles) {
+      const int s = i & 1, q = i % kCtBufs;
+      mbar_wait(&in_full[s], (uint32_t)((i >> 1) & 1));
+      if (warp == 0) CT_ACC(4);
+      const long long tile = tile_of(i);
+      const long long first = tile * kCtTile;
+      const int npts = (n - first) < kCtTile ? (int)(n - first) : kCtTile;
+      const T* sin = reinterpret_cast<const T*>(dyn_smem + s * SM::kIn);
+      T xin[kCtPpt][3];
+#pragma unroll
+      for (int k = 0; k < kCtPpt; ++k) {
+        const T* r = sin + 3 * (k * kCtThreads + tid);
+        xin[k][0] = r[0]; xin[k][1] = r[1]; xin[k][2] = r[2];
+      }
+      __syncwarp();
+      if (lane == 0 && atomicAdd(&s_consumed[s], 1) == kCtWarps - 1) {
+        s_consumed[s] = 0;                             // last warp to read the stage refills it
+        feed(i + 2);
+      }
+      UV* suv = reinterpret_cast<UV*>(dyn_smem + 2 * SM::kIn + q * SM::kOut);
+      double* sdep = reinterpret_cast<double*>(dyn_smem + 2 * SM::kIn + q * SM::kOut + kCtTile * 2 * sizeof(T));
+#pragma unroll
+      for (int k = 0; k < kCtPpt; ++k) {
+        const int p = k * kCtThreads + tid;
+        const double Xp[3] = {(double)xin[k][0], (double)xin[k][1], (double)xin[k][2]};
+        double u, v;
+        project_one<DIST>(P, Xp, u, v);
+        const T uo = (T)u, vo = (T)v;
+        bool good = p < npts;
+        if (need_depth) {
+          const double dep = depth_of(P, Xp);
+          if (depth != nullptr) sdep[p] = dep;
+          if (P.check_depth) good = good && (dep >= P.min_depth);
+        }
+        if (P.check_bounds) good = good && OutPix<T>::in_bounds(uo, vo, Wf, Hf);
+        suv[p] = OutPix<T>::make(uo, vo);
+        m[k] = __ballot_sync(0xffffffffu, good);
+        if (lane == 0) s_cnt[q][k * kCtWarps + warp] = __popc(m[k]);
+        if (valid_out != nullptr && p < npts) valid_out[first + p] = good ? 1 : 0;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        // The tile aggregate leaves the moment the last compute warp is done - never
+        // behind a look-back, or every successor tile would inherit that delay.
+        int wsum = 0;
+#pragma unroll
+        for (int k = 0; k < kCtPpt; ++k) wsum += __popc(m[k]);
+        atomicAdd(&s_aggsum[s], wsum);
+        __threadfence_block();
+        if (atomicAdd(&s_arrived[s], 1) == kCtWarps - 1) {
+          __threadfence_block();
+          const int total = atomicExch(&s_aggsum[s], 0);
+          s_arrived[s] = 0;
+          st_status(status + tile, (tile == 0 ? kStatePrefix : kStateAgg) | (unsigned long long)total);
+        }
+        mbar_arrive(&cnt_ready[s]);
+      }
+      if (warp == 0) CT_ACC(5);
+    }
+    if (i >= 2) {
+      // scatter tile i-2 (parked by this same thread two iterations ago)
+      const int j = i - 2, q = j % kCtBufs;
+      mbar_wait(&base_ready[q], (uint32_t)((j / kCtBufs) & 1));
+      if (warp == 0) CT_ACC(6);
+      const long long base = s_base[q];
+      const UV* suv = reinterpret_cast<const UV*>(dyn_smem + 2 * SM::kIn + q * SM::kOut);
+      const double* sdep =
+          reinterpret_cast<const double*>(dyn_smem + 2 * SM::kIn + q * SM::kOut + kCtTile * 2 * sizeof(T));
+#pragma unroll
+      for (int k = 0; k < kCtPpt; ++k) {
+        if ((m2[k] >> lane) & 1u) {
+          const int p = k * kCtThreads + tid;
+          const long long o = base + s_excl[q][k * kCtWarps + warp] + __popc(m2[k] & lt);
+          OutPix<T>::store_vec(uv, o, suv[p]);
+          if (depth != nullptr) st_stream_d1(depth + o, sdep[p]);
+        }
+      }
+      if (warp == 0) CT_ACC(7);
+    }
+#pragma unroll
+    for (int k = 0; k < kCtPpt; ++k) {
+      m2[k] = m1[k];
+      m1[k] = m[k];
+    }
   }
 }
 
@@ -443,8 +608,8 @@ static int launch_transform(const void* X, int64_t n, const XformParams& P, void
 
 template <typename T, bool DIST, int MODE>
 static int launch_project(const void* X, int64_t n, const pbk_project_params& P, void* uv,
-                          double* depth, uint8_t* valid, int64_t* count, void* scratch,
-                          cudaStream_t s, const DeviceInfo* di) {
+                          double* depth, uint8_t* valid, int64_t* count, cudaStream_t s,
+                          const DeviceInfo* di) {
   constexpr int NST = RingCfg<T>::kStages;
   const int smem = kWarps * NST * kTilePts * 3 * (int)sizeof(T) + kWarps * NST * 8;
   auto kern = project_points_kernel<T, DIST, MODE>;
@@ -453,9 +618,30 @@ static int launch_project(const void* X, int64_t n, const pbk_project_params& P,
   const long long ncta = (n + kCtaPts - 1) / kCtaPts;
   const int grid = resident_grid(di, kern, kWarps * 32, smem, ncta);
   kern<<<grid, kWarps * 32, smem, s>>>(static_cast<const T*>(X), n, static_cast<T*>(uv), depth, valid,
-                                       reinterpret_cast<long long*>(count),
-                                       static_cast<unsigned long long*>(scratch), P);
+                                       reinterpret_cast<long long*>(count), P);
   PBK_CHECK_LAUNCH("project_points_kernel");
+  return PBK_OK;
+}
+
+template <typename T, bool DIST>
+static int launch_compact(const void* X, int64_t n, const pbk_project_params& P, void* uv,
+                          double* depth, uint8_t* valid, int64_t* count, void* scratch, cudaStream_t s,
+                          const DeviceInfo* di) {
+  constexpr int smem = CompactSmem<T>::kBytes;
+  auto kern = project_compact_kernel<T, DIST>;
+  int rc = opt_in_smem(kern, smem + 1024);
+  if (rc) return rc;
+  const long long ntiles = (n + kCtTile - 1) / kCtTile;
+  const int grid = resident_grid(di, kern, kCtBlock, smem, ntiles);
+  const T* Xp = static_cast<const T*>(X);
+  long long nn = n;
+  T* uvp = static_cast<T*>(uv);
+  long long* cnt = reinterpret_cast<long long*>(count);
+  unsigned long long* scr = static_cast<unsigned long long*>(scratch);
+  pbk_project_params Pc = P;
+  void* args[] = {&Xp, &nn, &uvp, &depth, &valid, &cnt, &scr, &Pc};
+  PBK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(kCtBlock), args,
+                                       smem, s));
   return PBK_OK;
 }
 
@@ -487,6 +673,17 @@ int pbk_transform_points(const void* X, int in_dtype, int64_t n, const double* R
   return launch_transform<double, float>(X, n, P, Y, s, di);
 }
 
+#ifdef PBK_COMPACT_TIMING
+PBK_API int pbk_debug_compact_clocks(unsigned long long out[16], int reset) {
+  if (cudaMemcpyFromSymbol(out, pbk::g_ct_clk, sizeof(unsigned long long) * 16) != cudaSuccess) return -2;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(pbk::g_ct_clk, z, sizeof(z)) != cudaSuccess) return -2;
+  }
+  return 0;
+}
+#endif
+
 size_t pbk_project_scratch_bytes(int64_t n) {
   if (n < 0) n = 0;
   const long long ntiles = (n + pbk::kCtaPts - 1) / pbk::kCtaPts;
@@ -502,6 +699,7 @@ int pbk_project_points(const void* X, int in_dtype, int64_t n, const pbk_project
   const pbk_project_params& P = *params;
   PBK_REQUIRE(!P.check_bounds || (P.width > 0 && P.height > 0), PBK_EINVAL,
               "check_bounds cannot proceed. Camera.shape is not set");
+  PBK_REQUIRE(P.width < (1 << 24) && P.height < (1 << 24), PBK_EINVAL, "image shape too large");
   PBK_REQUIRE(!P.compact || (count != nullptr && scratch != nullptr), PBK_EINVAL,
               "compact output needs count and scratch");
   cudaStream_t s = as_stream(stream);
@@ -527,14 +725,14 @@ int pbk_project_points(const void* X, int in_dtype, int64_t n, const pbk_project
   }
   const bool dist = P.has_distortion != 0;
   const int mode = plain ? 0 : (P.compact ? 2 : 1);
-#define PBK_DISPATCH(T)                                                                              \
-  switch (mode * 2 + (dist ? 1 : 0)) {                                                               \
-    case 0: return launch_project<T, false, 0>(X, n, P, uv, depth, valid, count, scratch, s, di);    \
-    case 1: return launch_project<T, true, 0>(X, n, P, uv, depth, valid, count, scratch, s, di);     \
-    case 2: return launch_project<T, false, 1>(X, n, P, uv, depth, valid, count, scratch, s, di);    \
-    case 3: return launch_project<T, true, 1>(X, n, P, uv, depth, valid, count, scratch, s, di);     \
-    case 4: return launch_project<T, false, 2>(X, n, P, uv, depth, valid, count, scratch, s, di);    \
-    default: return launch_project<T, true, 2>(X, n, P, uv, depth, valid, count, scratch, s, di);    \
+#define PBK_DISPATCH(T)                                                                       \
+  switch (mode * 2 + (dist ? 1 : 0)) {                                                        \
+    case 0: return launch_project<T, false, 0>(X, n, P, uv, depth, valid, count, s, di);      \
+    case 1: return launch_project<T, true, 0>(X, n, P, uv, depth, valid, count, s, di);       \
+    case 2: return launch_project<T, false, 1>(X, n, P, uv, depth, valid, count, s, di);      \
+    case 3: return launch_project<T, true, 1>(X, n, P, uv, depth, valid, count, s, di);       \
+    case 4: return launch_compact<T, false>(X, n, P, uv, depth, valid, count, scratch, s, di); \
+    default: return launch_compact<T, true>(X, n, P, uv, depth, valid, count, scratch, s, di); \
   }
   if (in_dtype == PBK_F32) { PBK_DISPATCH(float) }
   PBK_DISPATCH(double)

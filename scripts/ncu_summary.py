@@ -39,6 +39,16 @@ FULL_METRICS = [
 ]
 
 
+PROBLEMS = {
+    "hamming_knn2_kernel": "2000 queries x 2.5M rows (one 8-GPU shard of C3)",
+    "project_points_kernel": "C2: 10M float32 points",
+    "project_compact_kernel": "C2: 10M float32 points, bounds+depth masks, 73.7 % valid",
+    "transform_points_kernel": "C2: 10M float32 points -> float64",
+    "ba_residual_jacobian_kernel": "C4: 4M observations",
+    "reproject_dense_kernel": "16 frames of 3840x2160 (a quarter of a C5 step)",
+}
+
+
 def short(name):
     name = name.replace("void ", "").replace("pbk::", "")
     cut = name.find("(")
@@ -90,6 +100,7 @@ def full(tag):
     seen = {}
     for r in rows[2:]:
         seen[short(r[col["Kernel Name"]])] = r          # keep the last (warm) launch of each kernel
+    traffic = {}
     with open(os.path.join(PROF, tag + "_ncu_full_summary.md"), "w") as f:
         f.write("# %s: `ncu --set full --clock-control none` of scripts/prof_kernels.py all 1\n\n" % tag)
         f.write("One launch per hot kernel at its BASELINE.json size (hamming: one 8-GPU shard of C3 = "
@@ -118,6 +129,8 @@ def full(tag):
                 except ValueError:
                     cells.append(v)
             f.write("| `%s` | %s | %.1f |\n" % (k[:60], " | ".join(cells), (rd + wr) / 1e6))
+            traffic[k] = {"dram_bytes": rd + wr, "problem": PROBLEMS.get(k.split("<")[0], "")}
+    json.dump({"tag": tag, "kernels": traffic}, open(os.path.join(PROF, "ncu_traffic.json"), "w"), indent=1)
 
 
 def bench_line(tag):
