@@ -49,7 +49,7 @@ typedef enum pbk_status {
 } pbk_status;
 
 typedef enum pbk_dtype {
-  PBK_U8 = 0, PBK_S16 = 1, PBK_S32 = 2, PBK_F32 = 3, PBK_F64 = 4
+  PBK_U8 = 0, PBK_S16 = 1, PBK_S32 = 2, PBK_F32 = 3, PBK_F64 = 4, PBK_U16 = 5
 } pbk_dtype;
 
 typedef void* pbk_stream_t;
@@ -213,6 +213,34 @@ PBK_API int pbk_ba_residual_jacobian(const void* obs, int64_t n_obs,
                              float* r, float* J_cam, float* J_pt,
                              double* cost_partials, double* cost,
                              pbk_stream_t stream);
+
+/* ------------------------------------------- next rows
+ * DepthCamera.reconstruct, pybot/vision/camera_utils.py:1032-1036:
+ *   out[b, y, x] = (xs[x]*d, ys[y]*d, d), d = depth[b, y*skip, x*skip], float64.
+ * depth  device (batch, H, W), dtype in {U16, F32, F64}
+ * xs, ys device float64 meshes of DepthCamera._build_mesh (:1020-1030), already
+ *        sub-sampled: Ws = ceil(W/skip), Hs = ceil(H/skip) entries
+ * out    device (batch, Hs, Ws, 3) float64                                     */
+PBK_API int pbk_depth_reconstruct(const void* depth, int depth_dtype, int batch, int H, int W,
+                                  int skip, const double* xs, const double* ys, double* out,
+                                  pbk_stream_t stream);
+
+/* DepthCamera.reconstruct_sparse, camera_utils.py:1038-1041 (both axes divided
+ * by fx, as the reference does): pts (n,2) f64, depth (n,) f64 -> out (n,3) f64 */
+PBK_API int pbk_depth_reconstruct_sparse(const double* pts, const double* depth, int64_t n,
+                                         double fx, double cx, double cy, double* out,
+                                         pbk_stream_t stream);
+
+/* SceneFlow.process, pybot/vision/optflow_utils.py:129-150: project the (H,W,3)
+ * scene points dX with params (R, t, K, D; the reference uses identity
+ * extrinsics), cast to int32 like numpy, keep in-bounds hits, scatter the source
+ * grid coordinate to the hit pixel (last source wins) and subtract the grid.
+ * dX      device (H, W, 3), dtype in {F32, F64}
+ * winner  device int32 (H*W) scratch
+ * flow    device (H, W, 2) float32; NaN where no point landed                   */
+PBK_API int pbk_sceneflow(const void* dX, int dtype, int H, int W,
+                          const pbk_project_params* params, int32_t* winner, float* flow,
+                          pbk_stream_t stream);
 
 #ifdef __cplusplus
 }

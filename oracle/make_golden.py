@@ -199,6 +199,60 @@ def g0_host_algebra(ns):
         axes_names=np.array(sorted(ns.tf._AXES2TUPLE)))
 
 
+def g6_next_rows(ns):
+    """G6: DepthCamera.reconstruct / reconstruct_sparse, SceneFlow.process and
+    get_object_bbox of the real reference."""
+    import importlib
+    of = importlib.import_module("pybot.vision.optflow_utils")
+    cu = importlib.import_module("pybot.vision.camera_utils")
+    rng = np.random.default_rng(606)
+    K = syn.kitti_K()
+    H, W = 47, 155
+    K = K.copy()
+    K[:2] *= 0.5                                    # half-resolution KITTI camera
+    out = {"K": K, "shape": np.int32([H, W])}
+    d32 = rng.uniform(0.4, 30.0, (H, W)).astype(np.float32)
+    d32[3, 5] = 0.0
+    d32[4, 6] = np.nan
+    d16 = (rng.uniform(0.4, 30.0, (H, W)) * 1000).astype(np.uint16)
+    out["d32"], out["d16"] = d32, d16
+    for skip in (1, 2, 3):
+        dc = ns.DepthCamera(K, shape=(H, W), skip=skip)
+        out["depth_f32_s%d" % skip] = dc.reconstruct(d32)
+    out["depth_u16_s1"] = ns.DepthCamera(K, shape=(H, W)).reconstruct(d16)
+    dc = ns.DepthCamera(K, shape=(H, W))
+    pts = rng.uniform(0, 150, (257, 2))
+    dep = rng.uniform(0.5, 20, 257)
+    out["sparse_pts"], out["sparse_depth"] = pts, dep
+    out["sparse_out"] = dc.reconstruct_sparse(pts, dep)
+    # scene flow: a camera translating forward/sideways over a random depth field,
+    # with collisions (several points landing on one pixel), off-image points and specials
+    cam = ns.CameraIntrinsic(K, shape=(H, W))
+    sf = of.SceneFlow(cam)
+    Z = rng.uniform(4, 60, (H, W))
+    xs, ys = np.meshgrid(np.arange(W), np.arange(H))
+    for name, dt in (("f32", np.float32), ("f64", np.float64)):
+        X = np.dstack([(xs - K[0, 2]) / K[0, 0] * Z + 0.35, (ys - K[1, 2]) / K[1, 1] * Z - 0.05, Z - 0.8]).astype(dt)
+        X[0, 0] = [np.nan, 1, 1]
+        X[0, 1] = [1e30, 1, 1e-3]
+        X[0, 2] = [0, 0, 0]
+        X[0, 3] = [1, 1, -2]
+        X[5, :40] = X[6, :40]                       # forced collisions: later source wins
+        out["flow_X_" + name] = X
+        out["flow_" + name] = sf.process(X)
+    camd = ns.CameraIntrinsic(K, D=np.float64([-0.3, 0.1, 0.001, -0.002, 0.01]), shape=(H, W))
+    out["flow_D"] = camd.D
+    out["flow_dist"] = of.SceneFlow(camd).process(out["flow_X_f32"])
+    # get_object_bbox on a cluster of points in front of a posed camera
+    pose = ns.RigidTransform.from_rpyxyz(0.02, -0.05, 0.01, 0.3, -0.2, 0.5)
+    c = ns.Camera.from_intrinsics_extrinsics(ns.CameraIntrinsic(syn.kitti_K(), shape=(376, 1241)),
+                                             ns.CameraExtrinsic.from_rigid_transform(pose))
+    obj = rng.normal(0, 1.0, (1500, 3)) * [1.5, 0.6, 1.0] + [2.0, 0.0, 14.0]
+    p2, bbox, depth = cu.get_object_bbox(c, obj, subsample=3, scale=1.2)
+    out.update(bbox_pts=obj, bbox_pose=pose.matrix, bbox_p2=p2, bbox_box=bbox, bbox_depth=np.float64(depth))
+    np.savez_compressed(os.path.join(OUT, "g6_next_rows.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
@@ -208,6 +262,7 @@ def main():
     g2_transform_project(ns)
     g3_matching()
     g5_ba()
+    g6_next_rows(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

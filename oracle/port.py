@@ -218,6 +218,52 @@ def stereo_reconstruct_sparse(xyd, Q):
 
 
 # ------------------------------------------------- matching (a9, via OpenCV)
+# ------------------------------------------------- next rows
+def depth_mesh(K, shape, skip=1):
+    """DepthCamera._build_mesh camera_utils.py:1020-1030 -> (xs1d, ys1d)."""
+    K = np.asarray(K, np.float64)
+    H, W = shape
+    xs, ys = np.arange(0, W), np.arange(0, H)
+    return ((xs - K[0, 2]) * 1.0 / K[0, 0])[::skip], ((ys - K[1, 2]) * 1.0 / K[1, 1])[::skip]
+
+
+def depth_reconstruct(K, shape, skip, depth):
+    """DepthCamera.reconstruct camera_utils.py:1032-1036."""
+    xs1d, ys1d = depth_mesh(K, shape, skip)
+    xs, ys = np.meshgrid(xs1d, ys1d)
+    depth_sampled = np.asarray(depth)[::skip, ::skip]
+    assert depth_sampled.shape == xs.shape
+    return np.dstack([xs * depth_sampled, ys * depth_sampled, depth_sampled])
+
+
+def depth_reconstruct_sparse(K, pts, depth):
+    """DepthCamera.reconstruct_sparse camera_utils.py:1038-1041 (fx on both axes)."""
+    K = np.asarray(K, np.float64)
+    fx, cx, cy = K[0, 0], K[0, 2], K[1, 2]
+    return np.vstack([(pts[:, 0] - cx) * 1.0 / fx * depth,
+                      (pts[:, 1] - cy) * 1.0 / fx * depth,
+                      depth]).T
+
+
+def sceneflow_process(K, D, shape, dX, use_cv2=True):
+    """SceneFlow.process optflow_utils.py:129-150 for a camera with identity
+    extrinsics (:122)."""
+    H, W = int(shape[0]), int(shape[1])
+    xs_, ys_ = np.meshgrid(np.arange(0, W), np.arange(0, H))
+    grid_ = np.dstack([xs_, ys_]).astype(np.float32)
+    x = camera_project(K, D, [0., 0., 0., 1.], [0., 0., 0.], (H, W), np.asarray(dX).reshape(-1, 3),
+                       use_cv2=use_cv2)
+    with np.errstate(invalid="ignore"):
+        x2 = x.astype(np.int32)                                # :137
+    valid = np.bitwise_and(np.bitwise_and(x2[:, 0] >= 0, x2[:, 0] < W),
+                           np.bitwise_and(x2[:, 1] >= 0, x2[:, 1] < H))
+    xs, ys = x2[:, 0], x2[:, 1]
+    gxs, gys = xs_.ravel(), ys_.ravel()
+    new_grid = np.copy(grid_) * np.nan
+    new_grid[ys[valid], xs[valid]] = grid_[gys[valid], gxs[valid]]
+    return new_grid - grid_
+
+
 def bf_knn_match(q, train_list, k=2, threads=None):
     """cv2.BFMatcher(NORM_HAMMING).knnMatch over a keyframe collection
     (no call site in the reference).  A single matrix of

@@ -14,13 +14,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PYBOT_B200_LIB", os.path.join(_HERE, "libpybot_b200.so"))
 
 PBK_OK, PBK_EINVAL, PBK_ECUDA, PBK_EALIGN, PBK_EUNSUPPORTED = 0, -1, -2, -3, -4
-PBK_U8, PBK_S16, PBK_S32, PBK_F32, PBK_F64 = 0, 1, 2, 3, 4
+PBK_U8, PBK_S16, PBK_S32, PBK_F32, PBK_F64, PBK_U16 = 0, 1, 2, 3, 4, 5
 PBK_KEY_NONE = 0xFFFFFFFFFFFFFFFF
 PBK_BA_CAM_DOUBLES = 40
 
 _NP2PBK = {np.dtype(np.uint8): PBK_U8, np.dtype(np.int16): PBK_S16,
            np.dtype(np.int32): PBK_S32, np.dtype(np.float32): PBK_F32,
-           np.dtype(np.float64): PBK_F64}
+           np.dtype(np.float64): PBK_F64, np.dtype(np.uint16): PBK_U16}
 
 
 class ProjectParams(ctypes.Structure):
@@ -58,6 +58,9 @@ SIGNATURES = {
     "pbk_hamming_gather_best": (_i, [_vp, _i64, _u64, _vp, _i64, _vp, _vp]),
     "pbk_hamming_ratio_mutual": (_i, [_vp, _vp, _i64, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pbk_popc_peak_probe": (_i, [_i, _i, _i, _vp, ctypes.POINTER(_d), _vp]),
+    "pbk_depth_reconstruct": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pbk_depth_reconstruct_sparse": (_i, [_vp, _vp, _i64, _d, _d, _d, _vp, _vp]),
+    "pbk_sceneflow": (_i, [_vp, _i, _i, _i, ctypes.POINTER(ProjectParams), _vp, _vp, _vp]),
     "pbk_ba_camera_precompute": (_i, [_vp, _vp, _i, _vp, _vp]),
     "pbk_ba_cost_slots": (_i, [_i64]),
     "pbk_ba_residual_jacobian": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _d, _d, _d, _d,

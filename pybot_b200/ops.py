@@ -312,6 +312,74 @@ def popc_probe(mode=0, ctas=None, iters=2000):
     return n.value
 
 
+# ------------------------------------------------------- next rows (8f)
+def depth_reconstruct(depth, xs, ys, skip=1):
+    """DepthCamera.reconstruct (camera_utils.py:1032-1036).  depth: (H,W) or
+    (B,H,W) uint16/float32/float64 (other dtypes are promoted to float64 like
+    numpy does); xs (Ws,), ys (Hs,) float64 meshes.  Returns (..., Hs, Ws, 3) float64."""
+    T = _ffi.require_cuda()
+    is_t = isinstance(depth, T.Tensor)
+    dt = np.dtype(str(depth.dtype).split(".")[-1]) if is_t else np.asarray(depth).dtype
+    if dt.type not in (np.uint16, np.float32, np.float64):
+        depth = depth.to(T.float64) if is_t else np.asarray(depth, np.float64)
+        dt = np.dtype(np.float64)
+    d, on_dev = _ffi.to_device(depth)
+    if d.ndim not in (2, 3):
+        raise ValueError("depth must be (H,W) or (B,H,W)")
+    batched = d.ndim == 3
+    B = d.shape[0] if batched else 1
+    H, W = int(d.shape[-2]), int(d.shape[-1])
+    s = int(skip)
+    Hs, Ws = -(-H // s), -(-W // s)
+    xs_d, _ = _ffi.to_device(np.ascontiguousarray(xs, np.float64))
+    ys_d, _ = _ffi.to_device(np.ascontiguousarray(ys, np.float64))
+    if xs_d.numel() != Ws or ys_d.numel() != Hs:
+        raise AssertionError("depth shape %s does not match the camera mesh (%d, %d)" % ((H, W), Hs, Ws))
+    out = T.empty((B, Hs, Ws, 3), dtype=T.float64, device=d.device)
+    _ffi.check(_ffi.lib().pbk_depth_reconstruct(_ffi.ptr(d), _ffi.pbk_dtype(dt), B, H, W, s, _ffi.ptr(xs_d),
+                                                _ffi.ptr(ys_d), _ffi.ptr(out), _ffi.stream_ptr()))
+    if not batched:
+        out = out[0]
+    return _finish(out, on_dev)
+
+
+def depth_reconstruct_sparse(pts, depth, fx, cx, cy):
+    """DepthCamera.reconstruct_sparse (camera_utils.py:1038-1041)."""
+    T = _ffi.require_cuda()
+    p, on_dev = _ffi.to_device(pts, np.float64)
+    d, _ = _ffi.to_device(depth, np.float64)
+    if p.ndim != 2 or p.shape[1] < 2 or d.shape[0] != p.shape[0]:
+        raise ValueError("expected pts (N,2) and depth (N,)")
+    p = p[:, :2].contiguous()
+    out = T.empty((p.shape[0], 3), dtype=T.float64, device=p.device)
+    _ffi.check(_ffi.lib().pbk_depth_reconstruct_sparse(_ffi.ptr(p), _ffi.ptr(d.contiguous()), p.shape[0], float(fx),
+                                                       float(cx), float(cy), _ffi.ptr(out), _ffi.stream_ptr()))
+    return _finish(out, on_dev)
+
+
+def sceneflow(dX, params):
+    """SceneFlow.process (optflow_utils.py:129-150) for (H,W,3) float32/float64
+    scene points and a prepared ProjectParams block.  Returns (H,W,2) float32."""
+    T = _ffi.require_cuda()
+    is_t = isinstance(dX, T.Tensor)
+    if not is_t:
+        dX = np.asarray(dX)
+        if dX.dtype not in (np.float32, np.float64):
+            dX = dX.astype(np.float64)
+    elif dX.dtype not in (T.float32, T.float64):
+        dX = dX.to(T.float64)
+    d, on_dev = _ffi.to_device(dX)
+    if d.ndim != 3 or d.shape[2] != 3:
+        raise ValueError("dX must be (H, W, 3)")
+    H, W = int(d.shape[0]), int(d.shape[1])
+    winner = T.empty((max(H * W, 1),), dtype=T.int32, device=d.device)
+    flow = T.empty((H, W, 2), dtype=T.float32, device=d.device)
+    dt = _ffi.PBK_F32 if d.dtype == T.float32 else _ffi.PBK_F64
+    _ffi.check(_ffi.lib().pbk_sceneflow(_ffi.ptr(d), dt, H, W, ctypes.byref(params), _ffi.ptr(winner),
+                                        _ffi.ptr(flow), _ffi.stream_ptr()))
+    return _finish(flow, on_dev)
+
+
 def hbm_probe(mode, src, dst, sink):
     """Launches the HBM probe (0 read / 1 write / 2 copy) over the given uint8 CUDA tensors."""
     ref = dst if mode == 1 else src

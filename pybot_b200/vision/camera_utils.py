@@ -66,6 +66,29 @@ def get_bounded_projection(camera, pts, subsample=10, return_depth=False):
                           return_valid=True)
 
 
+def get_object_bbox(camera, pts, subsample=10, scale=1.0, min_height=10, min_width=10):
+    """Reference :309-349: projected points, their [l, t, r, b] box and median
+    depth, or [None]*3.  The projection + bounds compaction runs fused on the
+    GPU (get_bounded_projection); the box logic is scalar host work."""
+    pts2d, valid = get_bounded_projection(camera, pts, subsample=subsample)
+    if not len(pts2d):
+        return [None] * 3
+    x0, x1 = int(max(0, np.min(pts2d[:, 0]))), int(min(camera.shape[1] - 1, np.max(pts2d[:, 0])))
+    y0, y1 = int(max(0, np.min(pts2d[:, 1]))), int(min(camera.shape[0] - 1, np.max(pts2d[:, 1])))
+    xmed, ymed = np.median(pts2d[:, 0]), np.median(pts2d[:, 1])
+    if (xmed >= 0 and ymed >= 0 and xmed <= camera.shape[1] and ymed < camera.shape[0]) and \
+       (y1 - y0) >= min_height and (x1 - x0) >= min_width:
+        depth = get_median_depth(camera, pts, subsample=subsample)
+        if depth < 0:
+            return [None] * 3
+        if scale != 1.0:
+            w2, h2 = (scale - 1.0) * (x1 - x0) / 2, (scale - 1.0) * (y1 - y0) / 2
+            x0, x1 = int(max(0, x0 - w2)), int(min(x1 + w2, camera.shape[1] - 1))
+            y0, y1 = int(max(0, y0 - h2)), int(min(y1 + h2, camera.shape[0] - 1))
+        return pts2d.astype(np.int32), np.float32([x0, y0, x1, y1]), depth
+    return [None] * 3
+
+
 class CameraIntrinsic(object):
     def __init__(self, K, D=np.zeros(5, dtype=np.float64), shape=None):
         """K: 3x3 calibration; D: distortion; shape: (H, W[, C])."""
@@ -330,3 +353,36 @@ class StereoCamera(Camera):
     def set_pose(self, left_pose):
         super(StereoCamera, self).set_pose(left_pose)
         self.right.set_pose(self.left.oplus(RigidTransform.from_rpyxyz(0, 0, 0, self.baseline, 0, 0)))
+
+
+class DepthCamera(CameraIntrinsic):
+    """Reference :1010-1048.  reconstruct() turns a depth image into an organised
+    float64 cloud dstack([xs*d, ys*d, d]) on the GPU (pbk_depth_reconstruct) with
+    the same precomputed meshes as the reference's _build_mesh."""
+
+    def __init__(self, K, shape=(480, 640), skip=1, D=np.zeros(5, dtype=np.float64)):
+        CameraIntrinsic.__init__(self, K, D)
+        self.shape = shape
+        self.skip = skip
+        self._build_mesh(shape=shape)
+
+    def _build_mesh(self, shape):
+        H, W = shape
+        xs, ys = np.arange(0, W), np.arange(0, H)
+        self.xs1d = ((xs - self.cx) * 1.0 / self.fx)[::self.skip]       # reference :1024-1027
+        self.ys1d = ((ys - self.cy) * 1.0 / self.fy)[::self.skip]
+        self.xs, self.ys = np.meshgrid(self.xs1d, self.ys1d)
+
+    def reconstruct(self, depth):
+        """(H,W) [or (B,H,W)] depth -> (Hs,Ws,3) float64."""
+        return ops.depth_reconstruct(depth, self.xs1d, self.ys1d, self.skip)
+
+    def reconstruct_sparse(self, pts, depth):
+        return ops.depth_reconstruct_sparse(pts, depth, self.fx, self.cx, self.cy)
+
+    def save(self, filename):
+        raise NotImplementedError()
+
+    @classmethod
+    def load(cls, filename):
+        raise NotImplementedError()

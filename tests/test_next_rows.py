@@ -1,0 +1,119 @@
+"""DepthCamera.reconstruct / reconstruct_sparse, SceneFlow.process,
+get_object_bbox.  Golden outputs come from the real reference
+(oracle/make_golden.py g6_next_rows).  CPU tests pin the oracle port; GPU tests
+pin the CUDA path - bit-exact, all of it is either fp64 mul/div or integer."""
+import numpy as np
+import pytest
+
+from oracle import port
+
+
+@pytest.fixture(scope="module")
+def g6(golden_dir):
+    return np.load(golden_dir + "/g6_next_rows.npz")
+
+
+def _same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype, (a.shape, b.shape, a.dtype, b.dtype)
+    nan = np.isnan(b)
+    assert np.array_equal(np.isnan(a), nan)
+    assert np.array_equal(a[~nan], b[~nan])
+
+
+# ------------------------------------------------------------------ oracle (CPU)
+def test_port_depth_reconstruct_matches_reference(g6):
+    K, shape = g6["K"], tuple(g6["shape"])
+    for skip in (1, 2, 3):
+        _same(port.depth_reconstruct(K, shape, skip, g6["d32"]), g6["depth_f32_s%d" % skip])
+    _same(port.depth_reconstruct(K, shape, 1, g6["d16"]), g6["depth_u16_s1"])
+    _same(port.depth_reconstruct_sparse(K, g6["sparse_pts"], g6["sparse_depth"]), g6["sparse_out"])
+
+
+@pytest.mark.parametrize("use_cv2", [True, False])
+def test_port_sceneflow_matches_reference(g6, use_cv2):
+    K, shape = g6["K"], tuple(g6["shape"])
+    _same(port.sceneflow_process(K, np.zeros(5), shape, g6["flow_X_f32"], use_cv2=use_cv2), g6["flow_f32"])
+    _same(port.sceneflow_process(K, np.zeros(5), shape, g6["flow_X_f64"], use_cv2=use_cv2), g6["flow_f64"])
+    _same(port.sceneflow_process(K, g6["flow_D"], shape, g6["flow_X_f32"], use_cv2=use_cv2), g6["flow_dist"])
+
+
+# --------------------------------------------------------------------- CUDA (GPU)
+@pytest.mark.gpu
+def test_depth_camera_reconstruct_golden(g6):
+    from pybot_b200.vision.camera_utils import DepthCamera
+    K, shape = g6["K"], tuple(int(v) for v in g6["shape"])
+    for skip in (1, 2, 3):
+        _same(DepthCamera(K, shape=shape, skip=skip).reconstruct(g6["d32"]), g6["depth_f32_s%d" % skip])
+    dc = DepthCamera(K, shape=shape)
+    _same(dc.reconstruct(g6["d16"]), g6["depth_u16_s1"])
+    _same(dc.reconstruct(g6["d32"].astype(np.float64)), g6["depth_f32_s1"])      # f32 values are exact in f64
+    _same(dc.reconstruct_sparse(g6["sparse_pts"], g6["sparse_depth"]), g6["sparse_out"])
+    with pytest.raises(AssertionError):
+        dc.reconstruct(g6["d32"][:-1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 1), (3, 5), (2, 63), (1, 64), (7, 65), (480, 640)])
+def test_depth_camera_shapes_and_batches(shape):
+    import torch
+    from pybot_b200 import synthetic as syn
+    from pybot_b200.vision.camera_utils import DepthCamera
+    rng = np.random.default_rng(sum(shape))
+    K = syn.kitti_K()
+    d = rng.uniform(0.3, 40, (3,) + shape).astype(np.float32)
+    dc = DepthCamera(K, shape=shape)
+    got = dc.reconstruct(d)                                           # batched
+    for b in range(3):
+        _same(got[b], port.depth_reconstruct(K, shape, 1, d[b]))
+    dev = dc.reconstruct(torch.from_numpy(d[0]).cuda())               # device in -> device out
+    assert dev.is_cuda
+    _same(dev.cpu().numpy(), port.depth_reconstruct(K, shape, 1, d[0]))
+
+
+@pytest.mark.gpu
+def test_sceneflow_golden(g6):
+    from pybot_b200.vision.camera_utils import CameraIntrinsic
+    from pybot_b200.vision.optflow_utils import SceneFlow
+    K, shape = g6["K"], tuple(int(v) for v in g6["shape"])
+    sf = SceneFlow(CameraIntrinsic(K, shape=shape))
+    _same(sf.process(g6["flow_X_f32"]), g6["flow_f32"])
+    _same(sf.process(g6["flow_X_f64"]), g6["flow_f64"])
+    sfd = SceneFlow(CameraIntrinsic(K, D=g6["flow_D"], shape=shape))
+    _same(sfd.process(g6["flow_X_f32"]), g6["flow_dist"])
+    with pytest.raises(ValueError):
+        sf.process(g6["flow_X_f32"][:-1])
+
+
+@pytest.mark.gpu
+def test_sceneflow_kitti_frame_vs_port():
+    """Full KITTI frame: a forward-moving camera over the C1 depth field."""
+    from pybot_b200 import synthetic as syn
+    from pybot_b200.vision.camera_utils import CameraIntrinsic, StereoCamera
+    from pybot_b200.vision.optflow_utils import SceneFlow
+    H, W = syn.KITTI_SHAPE
+    K = syn.kitti_K()
+    cam = StereoCamera.from_calib_params(syn.KITTI_FX, syn.KITTI_FX, syn.KITTI_CX, syn.KITTI_CY,
+                                         baseline_px=syn.KITTI_BASELINE_PX, shape=(H, W))
+    X = cam.reconstruct(syn.c1_frame())                               # (H,W,3) float32, with inf/NaN specials
+    X = -X                                                            # Q negates X, Y, W: put the cloud in front
+    X[..., 2] = np.abs(X[..., 2]) - 1.0                               # camera moved 1 m forward
+    got = SceneFlow(CameraIntrinsic(K, shape=(H, W))).process(X)
+    _same(got, port.sceneflow_process(K, np.zeros(5), (H, W), X))
+    hit = ~np.isnan(got[..., 0])
+    assert 0.2 < hit.mean() < 0.99
+
+
+@pytest.mark.gpu
+def test_get_object_bbox_golden(g6):
+    from pybot_b200 import synthetic as syn
+    from pybot_b200.geometry import RigidTransform
+    from pybot_b200.vision.camera_utils import (Camera, CameraExtrinsic, CameraIntrinsic, get_object_bbox)
+    pose = RigidTransform.from_matrix(g6["bbox_pose"])
+    c = Camera.from_intrinsics_extrinsics(CameraIntrinsic(syn.kitti_K(), shape=(376, 1241)),
+                                          CameraExtrinsic.from_rigid_transform(pose))
+    p2, bbox, depth = get_object_bbox(c, g6["bbox_pts"], subsample=3, scale=1.2)
+    assert np.array_equal(p2, g6["bbox_p2"]) and p2.dtype == np.int32
+    assert np.array_equal(bbox, g6["bbox_box"]) and bbox.dtype == np.float32
+    assert depth == float(g6["bbox_depth"])
+    assert get_object_bbox(c, g6["bbox_pts"] - [0, 0, 200.0]) == [None] * 3     # behind the camera: nothing in view
