@@ -616,6 +616,71 @@ def cpu_baseline_c5(cam, disp, im):
                       "camera_utils.py:987-989) on %d 4K frames, %.1f s" % (n, dt)}
 
 
+# ------------------------------------------------- next rows
+def run_next_rows(D, args):
+    """DepthCamera.reconstruct on a batch of 4K depth frames and SceneFlow.process
+    on one 4K frame (the callers either side of project / reconstruct)."""
+    import torch
+    from oracle import port
+    from pybot_b200.vision.camera_utils import CameraIntrinsic, DepthCamera
+    from pybot_b200.vision.optflow_utils import SceneFlow
+    hbm, src = measured_peaks()
+    H, W = syn.UHD_SHAPE
+    K = np.array([[syn.UHD_FX, 0, syn.UHD_CX], [0, syn.UHD_FX, syn.UHD_CY], [0, 0, 1.0]])
+    g = torch.Generator(device="cuda").manual_seed(1006)
+    out = {}
+
+    batch = 16
+    depth = torch.rand((batch, H, W), device="cuda", generator=g) * 76 + 4
+    dc = DepthCamera(K, shape=(H, W))
+
+    def dstep(rec):
+        return dc.reconstruct(depth)
+    ms, _ = timed_steps(D, dstep, args.steps, args.warmup)              # 3.7 GB/step >> L2
+    npx = batch * H * W
+    d_np = depth[0].cpu().numpy()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        port.depth_reconstruct(K, (H, W), 1, d_np)
+    cpu_dt = (time.perf_counter() - t0) / 3
+    out["depth_camera_reconstruct"] = {
+        "workload": "%d depth frames of %dx%d float32 -> organised float64 cloud per step" % (batch, W, H),
+        "Mpts_per_s": npx * args.steps / (ms * 1e-3) / 1e6, "ms": ms / args.steps,
+        "roofline": {"bound": "hbm", "kernel": "depth_reconstruct_dense_kernel<float>",
+                     "achieved": npx * 28.0 * args.steps / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": npx * 28.0 * args.steps / (ms * 1e-3) / 1e9 / hbm, "peak_source": src,
+                     "algorithmic": "4 B in + 24 B out = 28 B/pt (86 % writes)"},
+        "cpu_baseline": {"value": H * W / cpu_dt / 1e6, "unit": "Mpts/s", "cores": 1, "kind": "port",
+                         "sample": "oracle.port.depth_reconstruct (numpy, camera_utils.py:1032-1036) on one 4K frame"}}
+    del depth
+
+    Z = torch.rand((H, W), device="cuda", generator=g) * 56 + 4
+    xs = (torch.arange(W, device="cuda", dtype=torch.float32) - syn.UHD_CX) / syn.UHD_FX
+    ys = (torch.arange(H, device="cuda", dtype=torch.float32) - syn.UHD_CY) / syn.UHD_FX
+    dX = torch.stack([xs[None, :] * Z + 0.35, ys[:, None] * Z - 0.05, Z - 0.8], dim=2).contiguous()
+    sf = SceneFlow(CameraIntrinsic(K, shape=(H, W)))
+    flush = make_flush(torch)
+
+    def fstep(rec):
+        return sf.process(dX)
+    ms2, _ = timed_steps(D, fstep, args.steps, args.warmup, flush)
+    Hk, Wk = syn.KITTI_SHAPE
+    Kk = syn.kitti_K()
+    dXk = dX[:Hk, :Wk].cpu().numpy()
+    t0 = time.perf_counter()
+    port.sceneflow_process(Kk, np.zeros(5), (Hk, Wk), dXk)
+    cpu_dt = time.perf_counter() - t0
+    out["sceneflow_process"] = {
+        "workload": "one %dx%d frame of float32 scene points per step" % (W, H),
+        "Mpts_per_s": H * W * args.steps / (ms2 * 1e-3) / 1e6, "ms": ms2 / args.steps,
+        "algorithmic": "12 B in + 8 B flow out (+ 4 B winner map written and read) per pixel",
+        "GBps": H * W * 28.0 * args.steps / (ms2 * 1e-3) / 1e9, "l2": L2_NOTE,
+        "cpu_baseline": {"value": Hk * Wk / cpu_dt / 1e6, "unit": "Mpts/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": "oracle.port.sceneflow_process (cv2.projectPoints + numpy passes, "
+                                   "optflow_utils.py:129-150) on one %dx%d frame" % (Wk, Hk)}}
+    return out
+
+
 # ------------------------------------------------------------ reference arm
 def run_reference(args):
     """The reference's CPU implementation of the headline path on the host
@@ -696,6 +761,10 @@ def main():
                 also[w] = {"error": repr(e)}
             import torch
             torch.cuda.empty_cache()
+        try:
+            also["next_rows"] = run_next_rows(D, sub)
+        except Exception as e:
+            also["next_rows"] = {"error": repr(e)}
         line["also"] = also
     if D.rank == 0:
         print(json.dumps(line))

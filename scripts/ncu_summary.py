@@ -46,6 +46,8 @@ PROBLEMS = {
     "transform_points_kernel": "C2: 10M float32 points -> float64",
     "ba_residual_jacobian_kernel": "C4: 4M observations",
     "reproject_dense_kernel": "16 frames of 3840x2160 (a quarter of a C5 step)",
+    "depth_reconstruct_dense_kernel": "16 depth frames of 3840x2160 float32",
+    "sceneflow_scatter_kernel": "one 3840x2160 frame of float32 scene points",
 }
 
 

@@ -1,7 +1,7 @@
 """Launches each hot kernel at its BASELINE.json size with device-resident
 inputs; meant to run under ncu (see profiles/README.md) or standalone.
 
-    python scripts/prof_kernels.py [hamming|project|compact|transform|ba|reproject|all] [reps]
+    python scripts/prof_kernels.py [hamming|project|compact|transform|ba|reproject|depth|flow|all] [reps]
 """
 import os
 import sys
@@ -76,3 +76,21 @@ if which in ("reproject", "all"):
     disp = torch.rand((B, H, W), device="cuda", generator=g) * 250 + 1
     im = torch.randint(0, 256, (B, H, W, 3), device="cuda", dtype=torch.uint8, generator=g)
     timed("reproject", lambda: cam.reconstruct_with_texture(disp, im))
+
+if which in ("depth", "flow", "all"):
+    from pybot_b200.vision.camera_utils import CameraIntrinsic, DepthCamera
+    from pybot_b200.vision.optflow_utils import SceneFlow
+    H, W = syn.UHD_SHAPE
+    K = np.array([[syn.UHD_FX, 0, syn.UHD_CX], [0, syn.UHD_FX, syn.UHD_CY], [0, 0, 1.0]])
+    if which in ("depth", "all"):
+        depth = torch.rand((16, H, W), device="cuda", generator=g) * 76 + 4
+        dc = DepthCamera(K, shape=(H, W))
+        timed("depth", lambda: dc.reconstruct(depth))
+        del depth
+    if which in ("flow", "all"):
+        Z = torch.rand((H, W), device="cuda", generator=g) * 56 + 4
+        xs = (torch.arange(W, device="cuda", dtype=torch.float32) - syn.UHD_CX) / syn.UHD_FX
+        ys = (torch.arange(H, device="cuda", dtype=torch.float32) - syn.UHD_CY) / syn.UHD_FX
+        dX = torch.stack([xs[None, :] * Z + 0.35, ys[:, None] * Z - 0.05, Z - 0.8], dim=2).contiguous()
+        sf = SceneFlow(CameraIntrinsic(K, shape=(H, W)))
+        timed("flow", lambda: sf.process(dX))
