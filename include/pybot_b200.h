@@ -199,8 +199,9 @@ PBK_API int pbk_popc_peak_probe(int mode, int ctas, int iters, uint32_t* sink,
  *   cam_blocks (C, PBK_BA_CAM_DOUBLES) f64 device: R(9) t(3) dR/dr(27).
  * ba_residual_jacobian: obs (O,4) {int32 cam, int32 pt, f32 u, f32 v} device,
  *   points (P,3) f32 device -> r (O,2) f32, J_cam (O,2,6) f32, J_pt (O,2,3)
- *   f32 (any may be NULL), cost_partials (pbk_ba_cost_slots(O),) f64 device,
- *   cost (1,) f64 device = sum ||r||^2 (deterministic two-stage sum).
+ *   f32 (any may be NULL), cost_partials (pbk_ba_cost_slots(O),) f64 device, ZERO on the
+ *   first call (the kernel leaves it reusable), cost (1,) f64 device = sum ||r||^2
+ *   (deterministic: per-CTA partials added in fixed order by the last CTA).
  */
 #define PBK_BA_CAM_DOUBLES 40
 PBK_API int pbk_ba_camera_precompute(const float* rvec, const float* tvec, int n_cams,

@@ -12,15 +12,15 @@
 // streaming kernel is HBM-write-bound: 16 B read + 80 B written per
 // observation; points (12 B each) are gathered through L2 one tile ahead and the
 // warp's camera block (320 B) is cached in shared memory.  One warp owns 64
-// observations (2 per lane): the 16 B observation records load coalesced
-// (prefetched two tiles ahead), fp64 math in registers with every camera
+// observations (2 per lane): the 16 B observation records arrive through a
+// per-warp TMA ring (three tiles in flight), fp64 math in registers with every camera
 // coefficient read once for both observations, r / J_cam / J_pt rows are written
 // to a warp-private shared-memory stage and leave as TMA bulk stores
 // (cp.async.bulk shared -> global), which keeps the output bytes off the LSU
 // data path - the first version of this kernel was L1-wavefront-bound (ncu
 // l1tex 83 %), not HBM-bound.  sum ||r||^2 is reduced warp -> CTA -> one fp64
-// partial per CTA, summed in fixed order by a second tiny kernel
-// (deterministic, no atomics).
+// partial per CTA; the last CTA to finish adds the partials in fixed order
+// (deterministic, no floating-point atomics, no second launch).
 #include <stdlib.h>
 
 #include "pbk_common.cuh"
@@ -82,7 +82,8 @@ struct BaParams {
   float* r;
   float* Jc;
   float* Jp;
-  double* partials;
+  double* partials;           // [gridDim.x] per-CTA sums + [gridDim.x] a u64 arrival counter (zero between calls)
+  double* cost;
   long long n_obs;
   long long n_points;
   int n_cams;
@@ -374,21 +375,29 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
   for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
   if (lane == 0) warp_cost[warp] = cost;
   __syncthreads();
-  if (threadIdx.x == 0 && P.partials != nullptr) {
+  if (P.partials == nullptr) return;
+  __shared__ int s_last;
+  unsigned long long* arrived = reinterpret_cast<unsigned long long*>(P.partials + gridDim.x);
+  if (threadIdx.x == 0) {
     double s = 0.0;
     for (int w = 0; w < kBaWarps; ++w) s += warp_cost[w];
     P.partials[blockIdx.x] = s;
+    __threadfence();
+    s_last = atomicAdd(arrived, 1ull) == gridDim.x - 1;
   }
-}
-
-__global__ void ba_cost_sum_kernel(const double* __restrict__ partials, int n, double* __restrict__ cost) {
-  // one warp, fixed order: lane-strided partial sums then a shuffle tree
-  const int lane = threadIdx.x;
-  double s = 0.0;
-  for (int i = lane; i < n; i += 32) s += partials[i];
+  __syncthreads();
+  // The last CTA to finish adds the per-CTA partials in a FIXED order (lane-strided
+  // sums, then a shuffle tree): deterministic, no floating-point atomics, and no
+  // second launch for an 8-byte result.
+  if (s_last && warp == 0 && P.cost != nullptr) {
+    __threadfence();
+    double s = 0.0;
+    for (int i = lane; i < (int)gridDim.x; i += 32) s += __ldcg(P.partials + i);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) *cost = s;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) *P.cost = s;
+  }
+  if (s_last && threadIdx.x == 0) *arrived = 0ull;      // ready for the next call
 }
 
 // Kernel shape: PBK_BA_VARIANT = "<OPL><MINB>" (observations per lane, CTAs per SM), for tuning.
@@ -439,7 +448,8 @@ int pbk_ba_cost_slots(int64_t n_obs) {
   using namespace pbk;
   const DeviceInfo* di;
   if (current_device_info(&di)) return -1;
-  return ba_grid(di, n_obs > 0 ? n_obs : 1);
+  const int g = ba_grid(di, n_obs > 0 ? n_obs : 1);
+  return g < 0 ? g : g + 1;            // + the arrival counter
 }
 
 int pbk_ba_residual_jacobian(const void* obs, int64_t n_obs, const float* points, int64_t n_points,
@@ -464,7 +474,7 @@ int pbk_ba_residual_jacobian(const void* obs, int64_t n_obs, const float* points
   BaParams P;
   P.obs = static_cast<const int4*>(obs);
   P.points = points; P.cams = cam_blocks;
-  P.r = r; P.Jc = J_cam; P.Jp = J_pt; P.partials = cost_partials;
+  P.r = r; P.Jc = J_cam; P.Jp = J_pt; P.partials = cost_partials; P.cost = cost;
   P.n_obs = n_obs; P.n_points = n_points; P.n_cams = n_cams;
   P.fx = fx; P.fy = fy; P.cx = cx; P.cy = cy;
   const int grid = ba_grid(di, n_obs);
@@ -472,10 +482,6 @@ int pbk_ba_residual_jacobian(const void* obs, int64_t n_obs, const float* points
   PBK_REQUIRE(grid > 0, PBK_ECUDA, "cannot opt in to %d bytes of shared memory", L.smem);
   L.kernel<<<grid, kBaWarps * 32, L.smem, s>>>(P);
   PBK_CHECK_LAUNCH("ba_residual_jacobian_kernel");
-  if (cost != nullptr) {
-    ba_cost_sum_kernel<<<1, 32, 0, s>>>(cost_partials, grid, cost);
-    PBK_CHECK_LAUNCH("ba_cost_sum_kernel");
-  }
   return PBK_OK;
 }
 
