@@ -46,11 +46,21 @@ def ncu_traffic(kernel, scale=1.0):
     try:
         with open(p) as f:
             d = json.load(f)
-        e = d["kernels"][kernel]
-        return {"bytes": e["dram_bytes"] * scale, "capture": d["tag"],
-                "captured_at": e.get("problem", ""), "scaled_by": scale}
+        return float(d["kernels"][kernel]["dram_bytes"]) * scale
     except Exception:
         return None
+
+
+def ncu_traffic_note(kernel, scale=1.0):
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        e = d["kernels"][kernel]
+        return ("dram read+write bytes per launch from profiles/%s_ncu_full_summary.md (captured on: %s)%s"
+                % (d["tag"], e.get("problem", ""), "" if scale == 1.0 else ", scaled x%g to this launch" % scale))
+    except Exception:
+        return "no ncu capture"
 
 
 def measured_peaks():
@@ -327,6 +337,7 @@ def run_c3(D, args):
             "achieved": popc_rate / 1e12, "peak": pk["popc_per_s"] / 1e12, "unit": "Tpopc/s",
             "frac": popc_rate / pk["popc_per_s"],
             "traffic": ncu_traffic("hamming_knn2_kernel<1>", scale=float(shard.shape[0]) / 2.5e6),
+            "traffic_source": ncu_traffic_note("hamming_knn2_kernel<1>", scale=float(shard.shape[0]) / 2.5e6),
             "algorithmic": "8 POPC.32 per pair (256 bits); achieved = nq*nt_local*8 / kernel time",
             "peak_source": "pbk_popc_peak_probe mode 0, measured in this run (burst)",
             "kernel_ms": knn_ms / args.steps, "kernel_share_of_step": knn_ms / total_ms,
@@ -430,6 +441,7 @@ def run_c2(D, args, n=10_000_000):
         "roofline": {"bound": "hbm", "kernel": "project_points_kernel<float,false,false>",
                      "achieved": out["project_plain"]["GBps"], "peak": hbm, "unit": "GB/s",
                      "frac": out["project_plain"]["GBps"] / hbm, "traffic": ncu_traffic("project_points_kernel<float, 0, 0>"),
+                     "traffic_source": ncu_traffic_note("project_points_kernel<float, 0, 0>"),
                      "peak_source": src, "algorithmic": "12 B in + 8 B out = 20 B/pt",
                      "copy_same_bytes_GBps": copy_at_size(torch, n * 12, n * 8)},
     }
@@ -510,7 +522,8 @@ def run_c4(D, args):
         "gpu_launches": 3 * args.steps, "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "ba_residual_jacobian_kernel", "achieved": gbps,
                      "peak": hbm, "unit": "GB/s", "frac": gbps / hbm,
-                     "traffic": ncu_traffic("ba_residual_jacobian_kernel") if D.world == 1 else None,
+                     "traffic": ncu_traffic("ba_residual_jacobian_kernel<2, 2>") if D.world == 1 else None,
+                     "traffic_source": ncu_traffic_note("ba_residual_jacobian_kernel<2, 2>"),
                      "peak_source": src,
                      "algorithmic": "16 B read + 8 + 48 + 24 B written = 96 B/obs",
                      "kernel_ms": kms / args.steps,
@@ -590,6 +603,7 @@ def run_c5(D, args, batch=64):
         "roofline": {"bound": "hbm", "kernel": "reproject_dense_kernel<float,true> (textured)",
                      "achieved": gbps, "peak": hbm, "unit": "GB/s", "frac": gbps / hbm,
                      "traffic": ncu_traffic("reproject_dense_kernel<float, 1>", scale=batch / 16.0),
+                     "traffic_source": ncu_traffic_note("reproject_dense_kernel<float, 1>", scale=batch / 16.0),
                      "peak_source": src, "algorithmic": "4+3 B in, 12+3 B out = 22 B/pt"},
     }
     if D.rank == 0:

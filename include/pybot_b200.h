@@ -243,6 +243,20 @@ PBK_API int pbk_sceneflow(const void* dX, int dtype, int H, int W,
                           const pbk_project_params* params, int32_t* winner, float* flow,
                           pbk_stream_t stream);
 
+/* sampson_error, pybot/vision/camera_utils.py:52-68: F host 9 doubles row-major,
+ * pts1 / pts2 device (n,2) float64 -> err (n,) float64 =
+ * (x1^T F x2)^2 / ((F x1)_0^2 + (F x1)_1^2 + (F x2)_0^2 + (F x2)_1^2), exactly the
+ * reference's expression (it uses F x2, not F^T x2).                           */
+PBK_API int pbk_sampson_error(const double* F, const double* pts1, const double* pts2, int64_t n,
+                              double* err, pbk_stream_t stream);
+
+/* Point-cloud colours in the viewer wire format: get_color_arr,
+ * pybot/externals/draw_helpers.py:35-53, for uint8 (n_px,3) images -> float32
+ * (n_px,3) = c / 255.0 with optional B<->R flip; this is the block arr_msg
+ * (pybot/externals/pb.py:35) serialises as msg.colors.                          */
+PBK_API int pbk_wire_colors(const uint8_t* bgr, int64_t n_px, int flip_rb, float* out,
+                            pbk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -253,6 +253,46 @@ def g6_next_rows(ns):
     np.savez_compressed(os.path.join(OUT, "g6_next_rows.npz"), **out)
 
 
+def _reference_functions(relpath, names, extra_globals):
+    """Executes selected top-level function definitions of a reference module
+    whose import fails here (pybot.externals needs protobuf 3.4 generated code):
+    the function bodies that run are the reference's own source."""
+    import ast
+    src = open(os.path.join(ref_loader.REFERENCE_ROOT, relpath)).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    mod = ast.Module(body=keep, type_ignores=[])
+    g = dict(extra_globals)
+    exec(compile(mod, relpath, "exec"), g)
+    return g
+
+
+def g7_epipolar_wire(ns):
+    """G7: sampson_error / filter_sampson_error / Camera.F and the viewer colour
+    wire format (get_color_arr) of the real reference."""
+    import importlib
+    cu = importlib.import_module("pybot.vision.camera_utils")
+    rng = np.random.default_rng(707)
+    K = syn.kitti_K()
+    mk = lambda *rp: ns.Camera.from_intrinsics_extrinsics(          # noqa: E731
+        ns.CameraIntrinsic(K, shape=(376, 1241)),
+        ns.CameraExtrinsic.from_rigid_transform(ns.RigidTransform.from_rpyxyz(*rp)))
+    rp1, rp2 = (0.01, -0.02, 0.03, 0.1, 0.0, 0.2), (-0.02, 0.05, 0.0, -0.4, 0.05, 0.9)
+    c1, c2 = mk(*rp1), mk(*rp2)
+    F = c1.F(c2)
+    X = rng.uniform([-10, -2, 5], [10, 2, 40], (300, 3))
+    p1 = c1.project(X)
+    p2 = c2.project(X) + rng.normal(0, 1.5, (300, 2))
+    err = cu.sampson_error(F, p2, p1)
+    f1, f2, ids = cu.filter_sampson_error(c1, c2, p1, p2, np.arange(300), error=4)
+    g = _reference_functions("pybot/externals/draw_helpers.py", ("reshape_arr", "get_color_arr"), {"np": np})
+    im = rng.integers(0, 256, (7, 9, 3), dtype=np.uint8)
+    np.savez_compressed(
+        os.path.join(OUT, "g7_epipolar_wire.npz"), rp1=np.float64(rp1), rp2=np.float64(rp2), F=F, p1=p1, p2=p2,
+        err=err, inlier_ids=ids, wire_im=im, wire_rgb=g["get_color_arr"](im.copy(), im.size // 3, flip_rb=False),
+        wire_flip=g["get_color_arr"](im.copy(), im.size // 3, flip_rb=True))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
@@ -263,6 +303,7 @@ def main():
     g3_matching()
     g5_ba()
     g6_next_rows(ns)
+    g7_epipolar_wire(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -264,6 +264,26 @@ def sceneflow_process(K, D, shape, dX, use_cv2=True):
     return new_grid - grid_
 
 
+def sampson_error(F, pts1, pts2):
+    """camera_utils.py:52-68, verbatim arithmetic (N x N product and its diagonal)."""
+    x1 = np.hstack([pts1, np.ones((len(pts1), 1))]).T          # unproject_points :37-39
+    x2 = np.hstack([pts2, np.ones((len(pts2), 1))]).T
+    Fx1 = np.dot(F, x1)
+    Fx2 = np.dot(F, x2)
+    denom = Fx1[0]**2 + Fx1[1]**2 + Fx2[0]**2 + Fx2[1]**2
+    return (np.diag(x1.T.dot(Fx2)))**2 / denom
+
+
+def wire_colors(carr, flip_rb=False):
+    """get_color_arr externals/draw_helpers.py:35-53 for an array argument."""
+    carr = carr.reshape(-1, 3) if carr.ndim == 3 else carr      # reshape_arr :29-33
+    carr = carr.copy()
+    if flip_rb:
+        b, r = carr[:, 0], carr[:, 2]
+        carr[:, 0], carr[:, 2] = r.copy(), b.copy()
+    return carr.astype(np.float32) / 255.0 if carr.dtype == np.uint8 else carr.astype(np.float32)
+
+
 def bf_knn_match(q, train_list, k=2, threads=None):
     """cv2.BFMatcher(NORM_HAMMING).knnMatch over a keyframe collection
     (no call site in the reference).  A single matrix of

@@ -61,6 +61,8 @@ SIGNATURES = {
     "pbk_depth_reconstruct": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pbk_depth_reconstruct_sparse": (_i, [_vp, _vp, _i64, _d, _d, _d, _vp, _vp]),
     "pbk_sceneflow": (_i, [_vp, _i, _i, _i, ctypes.POINTER(ProjectParams), _vp, _vp, _vp]),
+    "pbk_sampson_error": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "pbk_wire_colors": (_i, [_vp, _i64, _i, _vp, _vp]),
     "pbk_ba_camera_precompute": (_i, [_vp, _vp, _i, _vp, _vp]),
     "pbk_ba_cost_slots": (_i, [_i64]),
     "pbk_ba_residual_jacobian": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _d, _d, _d, _d,

@@ -10,6 +10,10 @@
 //      The reference does this as a cv2.projectPoints call plus five numpy
 //      passes over H*W points; here it is one projection+scatter kernel and one
 //      resolve kernel, and only the (H,W,2) flow leaves the device.
+//  * sampson_error / filter_sampson_error            pybot/vision/camera_utils.py:52-90
+//      epipolar filter between matching and triangulation; diagonal only.
+//  * viewer wire colours                             pybot/externals/draw_helpers.py:35-59,
+//      float32 RGB in [0,1] exactly as arr_msg ships them  pybot/externals/pb.py:18-38
 #include "pbk_common.cuh"
 #include "project_math.cuh"
 
@@ -164,9 +168,103 @@ sceneflow_resolve_kernel(const int* __restrict__ winner, int n, int W, float2* _
   flow[c] = o;
 }
 
+struct SampsonParams {
+  double F[9];
+};
+
+// ---------------------------------------------------------------- sampson_error
+// camera_utils.py:52-68.  The reference forms the full N x N product
+// x1^T (F x2) and keeps its diagonal; only the diagonal is computed here.
+// Products follow the k = 0,1,2 FMA chain of the 3-term dot products numpy's
+// BLAS runs (see transform_points_kernel).
+__global__ void __launch_bounds__(256)
+sampson_error_kernel(const double* __restrict__ p1, const double* __restrict__ p2, long long n,
+                     const __grid_constant__ SampsonParams P, double* __restrict__ err) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x1[3] = {p1[2 * i], p1[2 * i + 1], 1.0}, x2[3] = {p2[2 * i], p2[2 * i + 1], 1.0};
+  double a[3], b[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    a[r] = __fma_rn(P.F[3 * r + 2], x1[2], __fma_rn(P.F[3 * r + 1], x1[1], __dmul_rn(P.F[3 * r], x1[0])));
+    b[r] = __fma_rn(P.F[3 * r + 2], x2[2], __fma_rn(P.F[3 * r + 1], x2[1], __dmul_rn(P.F[3 * r], x2[0])));
+  }
+  const double denom = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(a[0], a[0]), __dmul_rn(a[1], a[1])),
+                                           __dmul_rn(b[0], b[0])), __dmul_rn(b[1], b[1]));
+  const double d = __fma_rn(x1[2], b[2], __fma_rn(x1[1], b[1], __dmul_rn(x1[0], b[0])));
+  err[i] = __ddiv_rn(__dmul_rn(d, d), denom);
+}
+
+// ------------------------------------------------------- viewer wire colours
+// get_color_arr (externals/draw_helpers.py:35-53) for uint8 images: optional
+// B<->R flip, then carr.astype(float32) / 255.0 - the float32 (N,3) block
+// arr_msg (externals/pb.py:35) sends as msg.colors.  4 pixels (12 B in, 48 B out)
+// per thread.
+__global__ void __launch_bounds__(256)
+wire_colors_kernel(const uint8_t* __restrict__ bgr, long long n_px, int flip_rb, float* __restrict__ out) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // group of 4 pixels
+  const long long p0 = q * 4;
+  if (p0 >= n_px) return;
+  if (p0 + 4 <= n_px) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(bgr + p0 * 3);
+    const uint32_t w0 = ld_stream_u1(src), w1 = ld_stream_u1(src + 1), w2 = ld_stream_u1(src + 2);
+    uint8_t c[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { c[k] = (w0 >> (8 * k)) & 0xff; c[4 + k] = (w1 >> (8 * k)) & 0xff; c[8 + k] = (w2 >> (8 * k)) & 0xff; }
+    float f[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint8_t c0 = c[3 * k], c1 = c[3 * k + 1], c2 = c[3 * k + 2];
+      f[3 * k] = __fdiv_rn((float)(flip_rb ? c2 : c0), 255.0f);
+      f[3 * k + 1] = __fdiv_rn((float)c1, 255.0f);
+      f[3 * k + 2] = __fdiv_rn((float)(flip_rb ? c0 : c2), 255.0f);
+    }
+    float4* dst = reinterpret_cast<float4*>(out + p0 * 3);
+    st_stream_f4(dst, make_float4(f[0], f[1], f[2], f[3]));
+    st_stream_f4(dst + 1, make_float4(f[4], f[5], f[6], f[7]));
+    st_stream_f4(dst + 2, make_float4(f[8], f[9], f[10], f[11]));
+  } else {
+    for (long long p = p0; p < n_px; ++p) {
+      const uint8_t c0 = bgr[3 * p], c1 = bgr[3 * p + 1], c2 = bgr[3 * p + 2];
+      out[3 * p] = __fdiv_rn((float)(flip_rb ? c2 : c0), 255.0f);
+      out[3 * p + 1] = __fdiv_rn((float)c1, 255.0f);
+      out[3 * p + 2] = __fdiv_rn((float)(flip_rb ? c0 : c2), 255.0f);
+    }
+  }
+}
+
 }  // namespace pbk
 
 extern "C" {
+
+int pbk_sampson_error(const double* F, const double* pts1, const double* pts2, int64_t n, double* err,
+                      pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(n >= 0 && F != nullptr, PBK_EINVAL, "bad arguments");
+  if (n == 0) return PBK_OK;
+  PBK_REQUIRE(pts1 && pts2 && err, PBK_EINVAL, "NULL device pointer");
+  SampsonParams P;
+  for (int i = 0; i < 9; ++i) P.F[i] = F[i];
+  const long long blocks = (n + 255) / 256;
+  PBK_REQUIRE(blocks < (1ll << 31), PBK_EINVAL, "n too large");
+  sampson_error_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(pts1, pts2, n, P, err);
+  PBK_CHECK_LAUNCH("sampson_error_kernel");
+  return PBK_OK;
+}
+
+int pbk_wire_colors(const uint8_t* bgr, int64_t n_px, int flip_rb, float* out, pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(n_px >= 0, PBK_EINVAL, "negative size");
+  if (n_px == 0) return PBK_OK;
+  PBK_REQUIRE(bgr && out, PBK_EINVAL, "NULL device pointer");
+  PBK_REQUIRE(aligned16(bgr) && aligned16(out), PBK_EALIGN, "device pointers must be 16-byte aligned");
+  const long long groups = (n_px + 3) / 4, blocks = (groups + 255) / 256;
+  PBK_REQUIRE(blocks < (1ll << 31), PBK_EINVAL, "too many pixels");
+  wire_colors_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(bgr, n_px, flip_rb, out);
+  PBK_CHECK_LAUNCH("wire_colors_kernel");
+  return PBK_OK;
+}
+
 
 int pbk_depth_reconstruct(const void* depth, int depth_dtype, int batch, int H, int W, int skip,
                           const double* xs, const double* ys, double* out, pbk_stream_t stream) {

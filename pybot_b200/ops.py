@@ -380,6 +380,32 @@ def sceneflow(dX, params):
     return _finish(flow, on_dev)
 
 
+def sampson_error(F, pts1, pts2):
+    """camera_utils.py:52-68 for (N,2) point arrays; returns (N,) float64."""
+    T = _ffi.require_cuda()
+    a, on_dev = _ffi.to_device(pts1, np.float64)
+    b, _ = _ffi.to_device(pts2, np.float64)
+    if a.ndim != 2 or a.shape[1] != 2 or tuple(b.shape) != tuple(a.shape):
+        raise AssertionError("pts1 and pts2 must both be (N, 2)")
+    Fh, Fp = _ffi.host_f64(F, 9)
+    err = T.empty((a.shape[0],), dtype=T.float64, device=a.device)
+    _ffi.check(_ffi.lib().pbk_sampson_error(Fp, _ffi.ptr(a), _ffi.ptr(b), a.shape[0], _ffi.ptr(err),
+                                            _ffi.stream_ptr()))
+    return _finish(err, on_dev)
+
+
+def wire_colors(im, flip_rb=False):
+    """uint8 (..., 3) colours -> float32 (N,3) in [0,1] (get_color_arr, draw_helpers.py:35-53)."""
+    T = _ffi.require_cuda()
+    c, on_dev = _ffi.to_device(im)
+    if c.dtype != T.uint8 or c.shape[-1] != 3:
+        raise ValueError("colours must be uint8 (..., 3)")
+    n = c.numel() // 3
+    out = T.empty((n, 3), dtype=T.float32, device=c.device)
+    _ffi.check(_ffi.lib().pbk_wire_colors(_ffi.ptr(c), n, int(bool(flip_rb)), _ffi.ptr(out), _ffi.stream_ptr()))
+    return _finish(out, on_dev)
+
+
 def hbm_probe(mode, src, dst, sink):
     """Launches the HBM probe (0 read / 1 write / 2 copy) over the given uint8 CUDA tensors."""
     ref = dst if mode == 1 else src

@@ -66,6 +66,29 @@ def get_bounded_projection(camera, pts, subsample=10, return_depth=False):
                           return_valid=True)
 
 
+def unproject_points(pts):
+    """Reference :37-39."""
+    pts = np.asarray(pts)
+    assert pts.ndim == 2 and pts.shape[1] == 2
+    return np.hstack([pts, np.ones((len(pts), 1))])
+
+
+def sampson_error(F, pts1, pts2):
+    """Squared Sampson error of reference :52-68 (the same expression, including
+    its use of F*x2); only the diagonal of x1^T (F x2) is formed, on the GPU."""
+    return ops.sampson_error(F, pts1, pts2)
+
+
+def filter_sampson_error(cam1, cam2, pts1, pts2, matched_ids, error=4):
+    """Reference :71-90: keep the matches whose Sampson error is below `error`."""
+    F = cam1.F(cam2)
+    err = np.asarray(sampson_error(F, pts2, pts1))
+    inliers, = np.where(np.fabs(err) < error)
+    pts1, pts2, matched_ids = pts1[inliers], pts2[inliers], matched_ids[inliers]
+    assert len(pts1) == len(pts2) == len(matched_ids)
+    return pts1, pts2, matched_ids
+
+
 def get_object_bbox(camera, pts, subsample=10, scale=1.0, min_height=10, min_width=10):
     """Reference :309-349: projected points, their [l, t, r, b] box and median
     depth, or [None]*3.  The projection + bounds compaction runs fused on the
@@ -193,6 +216,16 @@ class Camera(CameraIntrinsic, CameraExtrinsic):
     @property
     def P(self):
         return self.K.dot(self.Rt)
+
+    def F(self, other):
+        """Fundamental matrix with respect to `other` (reference :777-808, H&Z
+        eq. 17.3): F[i, j] = det of the rows of P left after removing row j of
+        self.P stacked on those left after removing row i of other.P.  Host-side
+        scalar work (nine 4x4 determinants)."""
+        rows = ([1, 2], [2, 0], [0, 1])
+        P1, P2 = np.asarray(self.P), np.asarray(other.P)
+        return np.float64([[np.linalg.det(np.vstack([P1[rows[j], :], P2[rows[i], :]])) for j in range(3)]
+                           for i in range(3)])
 
     @classmethod
     def simulate(cls):

@@ -117,3 +117,55 @@ def test_get_object_bbox_golden(g6):
     assert np.array_equal(bbox, g6["bbox_box"]) and bbox.dtype == np.float32
     assert depth == float(g6["bbox_depth"])
     assert get_object_bbox(c, g6["bbox_pts"] - [0, 0, 200.0]) == [None] * 3     # behind the camera: nothing in view
+
+
+# ------------------------------------------------- sampson error / wire colours
+@pytest.fixture(scope="module")
+def g7(golden_dir):
+    return np.load(golden_dir + "/g7_epipolar_wire.npz")
+
+
+def test_port_sampson_and_wire_match_reference(g7):
+    assert np.array_equal(port.sampson_error(g7["F"], g7["p2"], g7["p1"]), g7["err"])
+    _same(port.wire_colors(g7["wire_im"], False), g7["wire_rgb"])
+    _same(port.wire_colors(g7["wire_im"], True), g7["wire_flip"])
+
+
+def _cams(g7):
+    from pybot_b200 import synthetic as syn
+    from pybot_b200.geometry import RigidTransform
+    from pybot_b200.vision.camera_utils import Camera, CameraExtrinsic, CameraIntrinsic
+    mk = lambda rp: Camera.from_intrinsics_extrinsics(              # noqa: E731
+        CameraIntrinsic(syn.kitti_K(), shape=(376, 1241)),
+        CameraExtrinsic.from_rigid_transform(RigidTransform.from_rpyxyz(*rp)))
+    return mk(g7["rp1"]), mk(g7["rp2"])
+
+
+def test_fundamental_matrix_matches_reference(g7):
+    """Camera.F is host-side (nine 4x4 determinants): same values as the reference."""
+    c1, c2 = _cams(g7)
+    np.testing.assert_allclose(c1.F(c2), g7["F"], rtol=1e-12, atol=1e-9 * np.abs(g7["F"]).max())
+
+
+@pytest.mark.gpu
+def test_sampson_error_golden(g7):
+    from pybot_b200.vision.camera_utils import filter_sampson_error, sampson_error
+    err = sampson_error(g7["F"], g7["p2"], g7["p1"])
+    assert err.dtype == np.float64 and err.shape == g7["err"].shape
+    np.testing.assert_allclose(err, g7["err"], rtol=1e-12)          # fp64; BLAS summation order is the only freedom
+    c1, c2 = _cams(g7)
+    f1, f2, ids = filter_sampson_error(c1, c2, g7["p1"], g7["p2"], np.arange(len(g7["p1"])), error=4)
+    assert np.array_equal(ids, g7["inlier_ids"])
+    assert np.array_equal(f1, g7["p1"][ids]) and np.array_equal(f2, g7["p2"][ids])
+    big = np.random.default_rng(1).uniform(0, 1000, (1_000_003, 2))      # the reference would need an N x N matrix
+    e = sampson_error(g7["F"], big, big[::-1].copy())
+    assert np.isfinite(e).all() and (e >= 0).all()
+
+
+@pytest.mark.gpu
+def test_wire_colors_golden(g7):
+    from pybot_b200 import ops
+    _same(ops.wire_colors(g7["wire_im"], False), g7["wire_rgb"])
+    _same(ops.wire_colors(g7["wire_im"], True), g7["wire_flip"])
+    im = np.random.default_rng(2).integers(0, 256, (333, 517, 3), dtype=np.uint8)      # n_px not a multiple of 4
+    _same(ops.wire_colors(im, True), port.wire_colors(im, True))
