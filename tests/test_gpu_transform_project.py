@@ -177,3 +177,46 @@ def test_compaction_full_size_properties():
     assert torch.equal(uv_c, uv_f[valid]) and torch.equal(d_c, d_f[valid])
     inb = (uv_c[:, 0] >= 0) & (uv_c[:, 0] < 1241) & (uv_c[:, 1] >= 0) & (uv_c[:, 1] < 376)
     assert bool(inb.all()) and bool((d_c >= 0.1).all())
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 1023, 1024, 1025, 2047, 3073, 444 * 1024 + 7, 2 * 444 * 1024 + 1021,
+                               3 * 444 * 1024 + 2])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_compaction_ragged_sizes_equal_boolean_indexing(n, dtype):
+    """The pipelined compaction kernel (1, 2, 3 ... generations of tiles per CTA,
+    ragged last tile with a byte count that is not a multiple of 16) must equal
+    boolean indexing of the uncompacted outputs, bit for bit."""
+    import torch
+    from pybot_b200 import ops
+    from pybot_b200.geometry import RigidTransform
+    g = torch.Generator(device="cuda").manual_seed(n)
+    X = torch.rand((n, 3), device="cuda", generator=g, dtype=torch.float64)
+    X[:, 0] = X[:, 0] * 80 - 40
+    X[:, 1] = X[:, 1] * 6 - 3
+    X[:, 2] = X[:, 2] * 78 + 2
+    X = X.to(torch.float32 if dtype == np.float32 else torch.float64)
+    T = RigidTransform.from_rpyxyz(*syn.C2_RPYXYZ).to_matrix()
+    kw = dict(shape=syn.KITTI_SHAPE, check_bounds=True, check_depth=True, return_depth=True, return_valid=True)
+    uv, dep, valid, count = ops.Projector(T[:3, :3], T[:3, 3], syn.kitti_K(), **kw).run(X)
+    uv0, dep0, valid0, count0 = ops.Projector(T[:3, :3], T[:3, 3], syn.kitti_K(), compact=False, **kw).run(X)
+    m = int(count.item())
+    assert m == int(count0.item()) == int(valid0.sum().item())
+    assert torch.equal(valid, valid0)
+    keep = valid0.bool()
+    assert torch.equal(uv[:m], uv0[keep]) and torch.equal(dep[:m], dep0[keep])
+
+
+def test_compaction_all_and_none_valid():
+    import torch
+    from pybot_b200 import ops
+    n = 50_000
+    X = torch.zeros((n, 3), device="cuda")
+    X[:, 2] = 10.0                                    # every point projects to (cx, cy): all valid
+    K = syn.kitti_K()
+    kw = dict(shape=syn.KITTI_SHAPE, check_bounds=True, check_depth=True, return_depth=True, return_valid=True)
+    uv, dep, valid, count = ops.Projector(np.eye(3), np.zeros(3), K, **kw).run(X)
+    assert int(count.item()) == n and bool(valid.all())
+    assert torch.equal(uv[:, 0], torch.full((n,), np.float32(K[0, 2]), device="cuda"))
+    X[:, 2] = -1.0                                    # behind the camera: none valid
+    uv, dep, valid, count = ops.Projector(np.eye(3), np.zeros(3), K, **kw).run(X, fresh=True)
+    assert int(count.item()) == 0 and not bool(valid.any())
