@@ -22,53 +22,86 @@ namespace pbk {
 // ------------------------------------------------------ DepthCamera.reconstruct
 template <typename T> __device__ __forceinline__ double depth_as_double(T v) { return (double)v; }
 
+// four consecutive depth samples starting at a 4-aligned element index, one vector load
+template <typename T> struct Depth4;
+template <> struct Depth4<float> {
+  static __device__ __forceinline__ void load(const float* p, double d[4]) {
+    const float4 v = ld_stream_f4(p);
+    d[0] = (double)v.x; d[1] = (double)v.y; d[2] = (double)v.z; d[3] = (double)v.w;
+  }
+};
+template <> struct Depth4<uint16_t> {
+  static __device__ __forceinline__ void load(const uint16_t* p, double d[4]) {
+    const uint2 v = ld_stream_u2(p);
+    d[0] = (double)(v.x & 0xffffu); d[1] = (double)(v.x >> 16);
+    d[2] = (double)(v.y & 0xffffu); d[3] = (double)(v.y >> 16);
+  }
+};
+template <> struct Depth4<double> {
+  static __device__ __forceinline__ void load(const double* p, double d[4]) {
+    const uint4 a = ld_stream_u4(p), b = ld_stream_u4(p + 2);
+    d[0] = __hiloint2double((int)a.y, (int)a.x); d[1] = __hiloint2double((int)a.w, (int)a.z);
+    d[2] = __hiloint2double((int)b.y, (int)b.x); d[3] = __hiloint2double((int)b.w, (int)b.z);
+  }
+};
+
 constexpr int kDcWarps = 8;
-constexpr int kDcTile = 64;                  // output pixels per warp tile (2 per lane)
+constexpr int kDcTile = 128;                 // output pixels per warp tile (4 per lane)
 
 __device__ __forceinline__ void st_stream_d2(void* p, double a, double b) {
   asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 
-// skip == 1: flat stream over batch*H*W pixels.  One warp owns 64 consecutive
-// pixels; lane l computes pixels 2l, 2l+1 (48 B of output), the records are
-// transposed through a warp-private stage so every global store is a coalesced
-// 16 B row.  4 B in + 24 B out per pixel (float32 depth): HBM-write-bound.
+// skip == 1: flat stream over batch*H*W pixels.  One warp owns 128 consecutive
+// pixels; lane l computes pixels 4l .. 4l+3 (one 16 B load of float32 depth, 96 B
+// of output) and writes them to a warp-private stage that leaves as ONE TMA bulk
+// store of 3 KB (cp.async.bulk shared -> global): no LDS / STG for the outputs.
+// Two stages alternate so a tile can be written while the previous one drains.
+// 4 B in + 24 B out per pixel (float32 depth): HBM-write-bound.
+constexpr int kDcPpl = 4;                    // pixels per lane
 template <typename T>
 __global__ void __launch_bounds__(kDcWarps * 32)
 depth_reconstruct_dense_kernel(const T* __restrict__ depth, long long total, int W, int H,
                                const double* __restrict__ xs, const double* __restrict__ ys,
                                double* __restrict__ out) {
-  __shared__ __align__(16) double stage[kDcWarps][kDcTile * 3];
+  __shared__ __align__(128) double stage[kDcWarps][2][kDcTile * 3];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* st = stage[warp];
   const long long ntiles = total / kDcTile;
   const long long stride = (long long)gridDim.x * kDcWarps;
-  for (long long tile = (long long)blockIdx.x * kDcWarps + warp; tile < ntiles; tile += stride) {
-    const long long p0 = tile * kDcTile + 2 * lane;
+  int it = 0;
+  for (long long tile = (long long)blockIdx.x * kDcWarps + warp; tile < ntiles; tile += stride, ++it) {
+    const long long p0 = tile * kDcTile + kDcPpl * lane;
+    double d[kDcPpl];
+    Depth4<T>::load(depth + p0, d);
     const long long row = p0 / W;
     int x = (int)(p0 - row * W);
     int y = (int)(row % H);
-    const double d0 = depth_as_double(depth[p0]), d1 = depth_as_double(depth[p0 + 1]);
-    const double xa = __ldg(xs + x), ya = __ldg(ys + y);
-    int x1 = x + 1, y1 = y;
-    if (x1 == W) { x1 = 0; y1 = (y + 1 == H) ? 0 : y + 1; }
-    const double xb = __ldg(xs + x1), yb = __ldg(ys + y1);
-    double2* s2 = reinterpret_cast<double2*>(st);
-    s2[lane * 3 + 0] = make_double2(__dmul_rn(xa, d0), __dmul_rn(ya, d0));
-    s2[lane * 3 + 1] = make_double2(d0, __dmul_rn(xb, d1));
-    s2[lane * 3 + 2] = make_double2(__dmul_rn(yb, d1), d1);
+    double* st = stage[warp][it & 1];
+    // the bulk store that used this stage two tiles ago must have drained it
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
     __syncwarp();
-    double* dst = out + tile * (kDcTile * 3);
+    double o[kDcPpl * 3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const double2 v = s2[j * 32 + lane];
-      st_stream_d2(dst + (j * 32 + lane) * 2, v.x, v.y);
+    for (int k = 0; k < kDcPpl; ++k) {
+      o[3 * k] = __dmul_rn(__ldg(xs + x), d[k]);
+      o[3 * k + 1] = __dmul_rn(__ldg(ys + y), d[k]);
+      o[3 * k + 2] = d[k];
+      if (++x == W) { x = 0; if (++y == H) y = 0; }
     }
+    double2* s2 = reinterpret_cast<double2*>(st) + lane * (kDcPpl * 3 / 2);
+#pragma unroll
+    for (int j = 0; j < kDcPpl * 3 / 2; ++j) s2[j] = make_double2(o[2 * j], o[2 * j + 1]);
+    fence_proxy_async_smem();
     __syncwarp();
+    if (lane == 0) {
+      tma_store_1d(out + tile * (kDcTile * 3), st, kDcTile * 24);
+      tma_store_commit();
+    }
   }
+  if (lane == 0) tma_store_wait_all();
 }
 
-// One output pixel per thread: skip > 1 and the < 64-pixel tail of the dense kernel.
+// One output pixel per thread: skip > 1 and the < 128-pixel tail of the dense kernel.
 template <typename T>
 __global__ void __launch_bounds__(256)
 depth_reconstruct_generic_kernel(const T* __restrict__ depth, int W, int H, int skip, int Ws, int Hs,

@@ -331,8 +331,9 @@ def depth_reconstruct(depth, xs, ys, skip=1):
     H, W = int(d.shape[-2]), int(d.shape[-1])
     s = int(skip)
     Hs, Ws = -(-H // s), -(-W // s)
-    xs_d, _ = _ffi.to_device(np.ascontiguousarray(xs, np.float64))
-    ys_d, _ = _ffi.to_device(np.ascontiguousarray(ys, np.float64))
+    # meshes may be passed as float64 CUDA tensors (DepthCamera caches them per device)
+    xs_d = xs if isinstance(xs, T.Tensor) else _ffi.to_device(np.ascontiguousarray(xs, np.float64))[0]
+    ys_d = ys if isinstance(ys, T.Tensor) else _ffi.to_device(np.ascontiguousarray(ys, np.float64))[0]
     if xs_d.numel() != Ws or ys_d.numel() != Hs:
         raise AssertionError("depth shape %s does not match the camera mesh (%d, %d)" % ((H, W), Hs, Ws))
     out = T.empty((B, Hs, Ws, 3), dtype=T.float64, device=d.device)
@@ -459,17 +460,23 @@ class BAProblemDevice(object):
         self.partials = T.zeros((max(slots, 1),), dtype=T.float64, device=dev)
         self.cost = T.zeros((1,), dtype=T.float64, device=dev)
 
-    def evaluate(self):
-        """One residual + Jacobian evaluation (asynchronous on the current stream)."""
+    def evaluate(self, events=None):
+        """One residual + Jacobian evaluation (asynchronous on the current stream).
+        `events`: optional (start, end) CUDA events recorded around the streaming
+        kernel alone (the per-camera precompute stays outside), for roofline timing."""
         L = _ffi.lib()
         s = _ffi.stream_ptr()
         _ffi.check(L.pbk_ba_camera_precompute(_ffi.ptr(self.rvec), _ffi.ptr(self.tvec), self.n_cams,
                                               _ffi.ptr(self.cam_blocks), s))
+        if events is not None:
+            events[0].record()
         _ffi.check(L.pbk_ba_residual_jacobian(
             _ffi.ptr(self.obs), self.n_obs, _ffi.ptr(self.points), self.n_points,
             _ffi.ptr(self.cam_blocks), self.n_cams, self.fx, self.fy, self.cx, self.cy,
             _ffi.ptr(self.r), _ffi.ptr(self.Jc), _ffi.ptr(self.Jp), _ffi.ptr(self.partials),
             _ffi.ptr(self.cost), s))
+        if events is not None:
+            events[1].record()
         return self
 
 

@@ -405,10 +405,15 @@ class DepthCamera(CameraIntrinsic):
         self.xs1d = ((xs - self.cx) * 1.0 / self.fx)[::self.skip]       # reference :1024-1027
         self.ys1d = ((ys - self.cy) * 1.0 / self.fy)[::self.skip]
         self.xs, self.ys = np.meshgrid(self.xs1d, self.ys1d)
+        self._mesh_dev = None
 
     def reconstruct(self, depth):
         """(H,W) [or (B,H,W)] depth -> (Hs,Ws,3) float64."""
-        return ops.depth_reconstruct(depth, self.xs1d, self.ys1d, self.skip)
+        if getattr(self, "_mesh_dev", None) is None:
+            from .. import _ffi
+            self._mesh_dev = (_ffi.to_device(np.ascontiguousarray(self.xs1d, np.float64))[0],
+                              _ffi.to_device(np.ascontiguousarray(self.ys1d, np.float64))[0])
+        return ops.depth_reconstruct(depth, self._mesh_dev[0], self._mesh_dev[1], self.skip)
 
     def reconstruct_sparse(self, pts, depth):
         return ops.depth_reconstruct_sparse(pts, depth, self.fx, self.cx, self.cy)
