@@ -378,6 +378,73 @@ def cpu_baseline_c3(q, db, per_kf, sample_kf=500):
                       % (engine, len(q), sample_kf * per_kf, sample_kf, dt)}
 
 
+# ------------------------------------------------------------ workload C1
+def run_c1(D, args):
+    """C1, the reference's own per-frame case: one KITTI-shaped stereo frame
+    (1241x376 disparity -> XYZ) + 2000x2000 ORB match with ratio + mutual.  At this
+    size the GPU is launch-latency-bound: what is reported is the per-frame
+    LATENCY through the public API with host (pinned) arrays in and numpy out."""
+    import torch
+    from oracle import port
+    from pybot_b200 import _ffi
+    from pybot_b200.vision.camera_utils import StereoCamera
+    from pybot_b200.vision.matcher import knn_ratio_mutual
+    H, W = syn.KITTI_SHAPE
+    cam = StereoCamera.from_calib_params(syn.KITTI_FX, syn.KITTI_FX, syn.KITTI_CX, syn.KITTI_CY,
+                                         baseline_px=syn.KITTI_BASELINE_PX, shape=(H, W))
+    disp_np = syn.c1_frame()
+    q_np, t_np = syn.orb_pair()
+    disp = _ffi.pinned_empty(disp_np.shape, np.float32)
+    q = _ffi.pinned_empty(q_np.shape, np.uint8)
+    t = _ffi.pinned_empty(t_np.shape, np.uint8)
+    disp[:], q[:], t[:] = disp_np, q_np, t_np
+    steps = max(args.steps, 20)
+
+    def frame(rec):
+        X = cam.reconstruct(disp)
+        m = knn_ratio_mutual(q, t, 0.75)
+        return X, m
+    ms, _ = timed_steps(D, frame, steps, args.warmup)
+
+    dq, dt_, dd = (torch.from_numpy(a).cuda() for a in (q_np, t_np, disp_np))
+
+    def resident(rec):
+        return cam.reconstruct(dd), knn_ratio_mutual(dq, dt_, 0.75)
+    ms_dev, _ = timed_steps(D, resident, steps, args.warmup)
+
+    # the same frame with a prepared, CUDA-graph-captured matcher (buffers allocated once)
+    from pybot_b200 import ops
+    pm = ops.PreparedMatcher(len(q_np), len(t_np), 0.75)
+
+    def graphed(rec):
+        X = cam.reconstruct(disp)
+        idx, dist, r_ok, m_ok, valid = pm.run(q, t)
+        return X, _ffi.to_host(idx), _ffi.to_host(dist), _ffi.to_host(valid)
+    ms_graph, _ = timed_steps(D, graphed, steps, args.warmup)
+
+    def graphed_resident(rec):
+        return cam.reconstruct(dd), pm.run(dq, dt_)
+    ms_graph_dev, _ = timed_steps(D, graphed_resident, steps, args.warmup)
+
+    Q = cam.Q
+    port.stereo_reconstruct(disp_np, Q)
+    port.knn_ratio_mutual(q_np, [t_np], 0.75)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        port.stereo_reconstruct(disp_np, Q)
+        port.knn_ratio_mutual(q_np, [t_np], 0.75)
+    cpu_ms = (time.perf_counter() - t0) / 5 * 1e3
+    return {"workload": "C1 one KITTI frame: %dx%d disparity -> XYZ + 2000x2000 ORB k=2 + ratio + mutual" % (W, H),
+            "latency_ms_host_arrays": ms / steps, "latency_ms_device_resident": ms_dev / steps,
+            "latency_ms_host_arrays_cuda_graph": ms_graph / steps,
+            "latency_ms_device_resident_cuda_graph": ms_graph_dev / steps,
+            "frames_per_s": 1e3 * steps / ms, "h2d_bytes": int(disp_np.nbytes + q_np.nbytes + t_np.nbytes),
+            "d2h_bytes": int(H * W * 12 + 2000 * 25),
+            "cpu_baseline": {"value": cpu_ms, "unit": "ms/frame", "cores": os.cpu_count(), "kind": "port",
+                             "sample": "cv2.reprojectImageTo3D + cv2.BFMatcher k=2 + ratio + mutual (oracle.port), "
+                                       "same frame, mean of 5"}}
+
+
 # ------------------------------------------------------------ workload C2
 def run_c2(D, args, n=10_000_000):
     import torch
@@ -774,6 +841,10 @@ def main():
                 also[w] = {"error": repr(e)}
             import torch
             torch.cuda.empty_cache()
+        try:
+            also["c1"] = run_c1(D, sub)
+        except Exception as e:
+            also["c1"] = {"error": repr(e)}
         try:
             also["next_rows"] = run_next_rows(D, sub)
         except Exception as e:

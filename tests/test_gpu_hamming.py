@@ -146,3 +146,24 @@ def test_full_size_properties_c3_shard():
 def test_popc_probe_runs():
     from pybot_b200 import ops
     assert ops.popc_probe(mode=0, ctas=148, iters=10) == 16 * 8 * 10 * 256 * 148
+
+
+def test_prepared_matcher_cuda_graph_equals_eager():
+    """PreparedMatcher (buffers allocated once, launches captured in a CUDA graph) on several
+    frames: identical to the eager pipeline and to the oracle."""
+    import torch
+    from oracle import model
+    from pybot_b200 import ops
+    pm = ops.PreparedMatcher(2000, 2000, 0.75)
+    assert pm.graph is not None
+    for seed in (1, 2, 3):
+        q, t = syn.orb_pair(seed=seed)
+        got = [x.cpu().numpy() for x in pm.run(q, t)]
+        want = model.ratio_mutual(q, t, 0.75)
+        for a, b in zip(got, want):
+            assert np.array_equal(np.asarray(a).astype(np.int64), np.asarray(b).astype(np.int64))
+        eager = ops.knn_ratio_mutual(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda(), 0.75)
+        for a, b in zip(pm.run(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()), eager):
+            assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        pm.run(q[:10], t)
