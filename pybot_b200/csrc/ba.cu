@@ -21,8 +21,6 @@
 // l1tex 83 %), not HBM-bound.  sum ||r||^2 is reduced warp -> CTA -> one fp64
 // partial per CTA; the last CTA to finish adds the partials in fixed order
 // (deterministic, no floating-point atomics, no second launch).
-#include <stdlib.h>
-
 #include "pbk_common.cuh"
 
 namespace pbk {
@@ -400,24 +398,16 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
   if (s_last && threadIdx.x == 0) *arrived = 0ull;      // ready for the next call
 }
 
-// Kernel shape: PBK_BA_VARIANT = "<OPL><MINB>" (observations per lane, CTAs per SM), for tuning.
+// Kernel shape: 2 observations per lane, 2 CTAs per SM (128 registers).  Measured
+// alternatives on C4 (4M observations): <2,3> 80 registers with spills 148 us,
+// <1,3> 93 us, <1,4> 107 us against 90 us for this one (3-launch step).
 struct BaLaunch {
   void (*kernel)(BaParams);
   int smem;
   int tile;
 };
 static BaLaunch ba_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("PBK_BA_VARIANT");
-    v = e ? atoi(e) : 22;
-  }
-  switch (v) {
-    case 13: return {ba_residual_jacobian_kernel<1, 3>, BaCfg<1>::kSmemBytes, BaCfg<1>::kTile};
-    case 14: return {ba_residual_jacobian_kernel<1, 4>, BaCfg<1>::kSmemBytes, BaCfg<1>::kTile};
-    case 23: return {ba_residual_jacobian_kernel<2, 3>, BaCfg<2>::kSmemBytes, BaCfg<2>::kTile};
-    default: return {ba_residual_jacobian_kernel<2, 2>, BaCfg<2>::kSmemBytes, BaCfg<2>::kTile};
-  }
+  return {ba_residual_jacobian_kernel<2, 2>, BaCfg<2>::kSmemBytes, BaCfg<2>::kTile};
 }
 
 static int ba_grid(const DeviceInfo* di, long long n_obs) {

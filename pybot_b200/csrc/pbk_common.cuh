@@ -93,16 +93,6 @@ __device__ __forceinline__ void st_stream_d1(void* p, double v) {
   asm volatile("st.global.cs.f64 [%0], %1;" :: "l"(p), "d"(v) : "memory");
 }
 
-// Grid for a streaming kernel: enough resident CTAs to cover every SM
-// `ctas_per_sm` times, never more than the work needs.
-static inline int stream_grid(const DeviceInfo* di, long long work_items,
-                              int ctas_per_sm) {
-  long long g = (long long)di->sm_count * ctas_per_sm;
-  if (g > work_items) g = work_items;
-  if (g < 1) g = 1;
-  return (int)g;
-}
-
 // ------------------------------------------------------------ TMA / mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
