@@ -215,6 +215,28 @@ PBK_API int pbk_ba_residual_jacobian(const void* obs, int64_t n_obs,
                              double* cost_partials, double* cost,
                              pbk_stream_t stream);
 
+/* Sharded BA: the same kernel with the sum-all-reduce of the cost
+ * FUSED in - the last CTA stores this rank's cost into every peer's exchange
+ * buffer over NVLink peer memory, waits for all peers' stores and adds the
+ * `world` values in rank order (bit-identical on every rank).  No NCCL call on
+ * the data path.
+ * peer_slots  host array of `world` device pointers: peer_slots[p] is rank p's
+ *             exchange buffer AS MAPPED INTO THIS PROCESS (e.g. torch symmetric
+ *             memory buffer_ptrs), >= PBK_BA_EXCHANGE_WORDS(world) uint64, zeroed
+ *             before the first call
+ * seq         call counter, identical on all ranks, 1, 2, 3 ...
+ * cost        receives the GLOBAL cost on every rank (NaN if a peer did not
+ *             arrive within ~2 s).  Every rank must own >= 1 observation.      */
+#define PBK_BA_EXCHANGE_WORDS(world) (4 * (world))
+PBK_API int pbk_ba_residual_jacobian_dist(const void* obs, int64_t n_obs,
+                             const float* points, int64_t n_points,
+                             const double* cam_blocks, int n_cams,
+                             double fx, double fy, double cx, double cy,
+                             float* r, float* J_cam, float* J_pt,
+                             double* cost_partials, double* cost,
+                             const uint64_t* peer_slots, int rank, int world,
+                             uint64_t seq, pbk_stream_t stream);
+
 /* ------------------------------------------- next rows
  * DepthCamera.reconstruct, pybot/vision/camera_utils.py:1032-1036:
  *   out[b, y, x] = (xs[x]*d, ys[y]*d, d), d = depth[b, y*skip, x*skip], float64.

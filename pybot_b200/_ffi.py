@@ -67,6 +67,8 @@ SIGNATURES = {
     "pbk_ba_cost_slots": (_i, [_i64]),
     "pbk_ba_residual_jacobian": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _d, _d, _d, _d,
                                       _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pbk_ba_residual_jacobian_dist": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _d, _d, _d, _d,
+                                           _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _u64, _vp]),
 }
 
 _lib = None

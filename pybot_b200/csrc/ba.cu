@@ -26,6 +26,7 @@
 namespace pbk {
 
 constexpr int kBaWarps = 8;
+constexpr int kBaMaxWorld = 16;
 constexpr int kCam = PBK_BA_CAM_DOUBLES;   // R(9) t(3) dRdr(27) pad(1)
 
 __global__ void __launch_bounds__(128)
@@ -82,6 +83,11 @@ struct BaParams {
   float* Jp;
   double* partials;           // [gridDim.x] per-CTA sums + [gridDim.x] a u64 arrival counter (zero between calls)
   double* cost;
+  // multi-GPU cost exchange over peer-mapped memory (world > 1): peers[p] = rank p's exchange
+  // buffer as mapped here, 2 (call parity) x world x {value bits, sequence number} u64 words
+  unsigned long long* peers[kBaMaxWorld];
+  int rank, world;
+  unsigned long long seq;
   long long n_obs;
   long long n_points;
   int n_cams;
@@ -393,6 +399,34 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
     for (int i = lane; i < (int)gridDim.x; i += 32) s += __ldcg(P.partials + i);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (P.world > 1) {
+      // Fused sum-all-reduce over NVLink peer memory: lane p stores this rank's cost and
+      // then the call's sequence number into rank p's exchange buffer; lane q then waits
+      // for rank q's sequence number in the LOCAL buffer and reads its cost.  All ranks add
+      // the world values in rank order, so the result is bit-identical everywhere.  Slots
+      // alternate with the call parity: a rank can only reuse a slot after every peer has
+      // finished the call in between, i.e. has read the previous value.
+      const int par = (int)(P.seq & 1ull);
+      if (lane < P.world) {
+        unsigned long long* slot = P.peers[lane] + (size_t)(par * P.world + P.rank) * 2;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot), "l"((unsigned long long)__double_as_longlong(s)) : "memory");
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot + 1), "l"(P.seq) : "memory");
+      }
+      double v = 0.0;
+      if (lane < P.world) {
+        const unsigned long long* mine = P.peers[P.rank] + (size_t)(par * P.world + lane) * 2;
+        unsigned long long got = 0, bits = 0x7ff8000000000000ull;          // NaN if a peer never arrives
+        const long long t0 = clock64();
+        do {
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(mine + 1) : "memory");
+        } while (got != P.seq && clock64() - t0 < (4ll << 30));              // ~2 s bound instead of a hang
+        if (got == P.seq) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(bits) : "l"(mine) : "memory");
+        v = __longlong_as_double((long long)bits);
+      }
+      s = 0.0;
+      for (int q = 0; q < P.world; ++q) s += __shfl_sync(0xffffffffu, v, q);
+    }
     if (lane == 0) *P.cost = s;
   }
   if (s_last && threadIdx.x == 0) *arrived = 0ull;      // ready for the next call
@@ -442,18 +476,22 @@ int pbk_ba_cost_slots(int64_t n_obs) {
   return g < 0 ? g : g + 1;            // + the arrival counter
 }
 
-int pbk_ba_residual_jacobian(const void* obs, int64_t n_obs, const float* points, int64_t n_points,
-                             const double* cam_blocks, int n_cams, double fx, double fy, double cx,
-                             double cy, float* r, float* J_cam, float* J_pt, double* cost_partials,
-                             double* cost, pbk_stream_t stream) {
+static int ba_launch(const void* obs, int64_t n_obs, const float* points, int64_t n_points,
+                     const double* cam_blocks, int n_cams, double fx, double fy, double cx, double cy, float* r,
+                     float* J_cam, float* J_pt, double* cost_partials, double* cost, const uint64_t* peer_slots,
+                     int rank, int world, uint64_t seq, pbk_stream_t stream) {
   using namespace pbk;
   PBK_REQUIRE(n_obs >= 0 && n_points >= 0 && n_cams >= 0, PBK_EINVAL, "negative size");
   PBK_REQUIRE((cost == nullptr) || (cost_partials != nullptr), PBK_EINVAL, "cost needs cost_partials");
+  PBK_REQUIRE(world >= 1 && world <= kBaMaxWorld && rank >= 0 && rank < world, PBK_EINVAL, "bad rank/world");
+  PBK_REQUIRE(world == 1 || (peer_slots != nullptr && cost != nullptr && seq >= 1), PBK_EINVAL,
+              "the fused exchange needs peer buffers, a cost output and seq >= 1");
   cudaStream_t s = as_stream(stream);
-  if (n_obs == 0) {
+  if (n_obs == 0 && world == 1) {
     if (cost != nullptr) PBK_CUDA(cudaMemsetAsync(cost, 0, 8, s));
     return PBK_OK;
   }
+  PBK_REQUIRE(n_obs > 0, PBK_EINVAL, "a rank of a sharded problem needs at least one observation");
   PBK_REQUIRE(n_cams > 0 && n_points > 0, PBK_EINVAL, "observations without cameras or points");
   PBK_REQUIRE(obs && points && cam_blocks, PBK_EINVAL, "NULL device pointer");
   PBK_REQUIRE(aligned16(obs) && aligned16(r) && aligned16(J_cam) && aligned16(J_pt) && aligned16(cam_blocks),
@@ -467,12 +505,32 @@ int pbk_ba_residual_jacobian(const void* obs, int64_t n_obs, const float* points
   P.r = r; P.Jc = J_cam; P.Jp = J_pt; P.partials = cost_partials; P.cost = cost;
   P.n_obs = n_obs; P.n_points = n_points; P.n_cams = n_cams;
   P.fx = fx; P.fy = fy; P.cx = cx; P.cy = cy;
+  P.rank = rank; P.world = world; P.seq = seq;
+  for (int p = 0; p < kBaMaxWorld; ++p)
+    P.peers[p] = (world > 1 && p < world) ? reinterpret_cast<unsigned long long*>(peer_slots[p]) : nullptr;
   const int grid = ba_grid(di, n_obs);
   const BaLaunch L = ba_variant();
   PBK_REQUIRE(grid > 0, PBK_ECUDA, "cannot opt in to %d bytes of shared memory", L.smem);
   L.kernel<<<grid, kBaWarps * 32, L.smem, s>>>(P);
   PBK_CHECK_LAUNCH("ba_residual_jacobian_kernel");
   return PBK_OK;
+}
+
+int pbk_ba_residual_jacobian(const void* obs, int64_t n_obs, const float* points, int64_t n_points,
+                             const double* cam_blocks, int n_cams, double fx, double fy, double cx,
+                             double cy, float* r, float* J_cam, float* J_pt, double* cost_partials,
+                             double* cost, pbk_stream_t stream) {
+  return ba_launch(obs, n_obs, points, n_points, cam_blocks, n_cams, fx, fy, cx, cy, r, J_cam, J_pt,
+                   cost_partials, cost, nullptr, 0, 1, 0, stream);
+}
+
+int pbk_ba_residual_jacobian_dist(const void* obs, int64_t n_obs, const float* points, int64_t n_points,
+                                  const double* cam_blocks, int n_cams, double fx, double fy, double cx,
+                                  double cy, float* r, float* J_cam, float* J_pt, double* cost_partials,
+                                  double* cost, const uint64_t* peer_slots, int rank, int world, uint64_t seq,
+                                  pbk_stream_t stream) {
+  return ba_launch(obs, n_obs, points, n_points, cam_blocks, n_cams, fx, fy, cx, cy, r, J_cam, J_pt,
+                   cost_partials, cost, peer_slots, rank, world, seq, stream);
 }
 
 }  // extern "C"

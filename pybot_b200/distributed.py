@@ -12,8 +12,11 @@ gloo in the CPU tests) for the plumbing.
   is sum-all-reduced (every other rank contributes zeros), then every rank runs
   the tiny reverse pass locally.
 * BA residual/Jacobian: observations are split into contiguous chunks; cameras
-  and points are replicated; the only exchange is an all-reduce of the fp64
-  cost.
+  and points are replicated; the only exchange is the sum-all-reduce of the fp64
+  cost, which is FUSED into the streaming kernel: its last CTA stores the rank's
+  cost into every peer's symmetric-memory buffer over NVLink and adds the peers'
+  values in rank order (no NCCL call on the data path; an NCCL all-reduce remains
+  as the alternative and is what the CPU tests drive).
 
 Per-frame reprojection / projection do not shard (replicas only).
 
@@ -96,11 +99,42 @@ class ShardedKeyframeMatcher(object):
         return self.kernels.ratio_mutual(keys, rev, ratio)
 
 
+class PeerCostExchange(object):
+    """Peer-mapped exchange buffer for the fused BA cost all-reduce
+    (pbk_ba_residual_jacobian_dist): a torch symmetric-memory allocation whose
+    per-rank addresses are handed to the kernel, which stores / polls them over
+    NVLink itself.  Collective: every rank of `group` must construct it."""
+
+    def __init__(self, group=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm_mem.empty(max(64, 4 * self.world), dtype=torch.int64, device=dev)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group=group)
+        torch.cuda.synchronize()
+        dist.barrier(group)                                  # every buffer is zero before the first store
+        self.ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+        self.seq = 0
+
+    def next_seq(self):
+        self.seq += 1
+        return self.seq
+
+
 class ShardedBA(object):
-    """This rank's contiguous chunk of the observations of a BA problem."""
+    """This rank's contiguous chunk of the observations of a BA problem.
+
+    exchange: "p2p" fuses the cost all-reduce into the kernel over NVLink peer
+    memory (default on the CUDA path when world > 1), "nccl" uses a one-element
+    NCCL all-reduce after the kernel (also what the gloo CPU tests drive)."""
 
     def __init__(self, rvecs, tvecs, K, points, obs_cam, obs_pt, obs_uv, group=None,
-                 problem_factory=None):
+                 problem_factory=None, exchange=None):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
@@ -108,14 +142,23 @@ class ShardedBA(object):
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         lo, hi = shard_range(len(obs_cam), self.rank, self.world)
         self.range = (lo, hi)
+        cuda_path = problem_factory is None
         if problem_factory is None:
             from .ops import BAProblemDevice as problem_factory
         self.problem = problem_factory(rvecs, tvecs, K, points, obs_cam[lo:hi], obs_pt[lo:hi],
                                        obs_uv[lo:hi])
+        if exchange is None:
+            exchange = "p2p" if (cuda_path and self.world > 1) else "nccl"
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        self.exchange = PeerCostExchange(group) if (exchange == "p2p" and self.world > 1) else None
 
     def evaluate(self):
         """Evaluates the local residuals/Jacobians (they stay on the owning
         rank) and returns the global cost tensor (1,) float64, all-reduced."""
+        if self.exchange is not None:
+            self.problem.evaluate(exchange=self.exchange)      # cost is already global
+            return self.problem.cost
         self.problem.evaluate()
         cost = self.problem.cost
         if self.world > 1:

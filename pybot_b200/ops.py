@@ -536,21 +536,30 @@ class BAProblemDevice(object):
         self.partials = T.zeros((max(slots, 1),), dtype=T.float64, device=dev)
         self.cost = T.zeros((1,), dtype=T.float64, device=dev)
 
-    def evaluate(self, events=None):
+    def evaluate(self, events=None, exchange=None):
         """One residual + Jacobian evaluation (asynchronous on the current stream).
         `events`: optional (start, end) CUDA events recorded around the streaming
-        kernel alone (the per-camera precompute stays outside), for roofline timing."""
+        kernel alone (the per-camera precompute stays outside), for roofline timing.
+        `exchange`: a distributed.PeerCostExchange - the kernel then also performs the
+        sum-all-reduce of the cost over NVLink peer memory and self.cost is GLOBAL."""
         L = _ffi.lib()
         s = _ffi.stream_ptr()
         _ffi.check(L.pbk_ba_camera_precompute(_ffi.ptr(self.rvec), _ffi.ptr(self.tvec), self.n_cams,
                                               _ffi.ptr(self.cam_blocks), s))
         if events is not None:
             events[0].record()
-        _ffi.check(L.pbk_ba_residual_jacobian(
-            _ffi.ptr(self.obs), self.n_obs, _ffi.ptr(self.points), self.n_points,
-            _ffi.ptr(self.cam_blocks), self.n_cams, self.fx, self.fy, self.cx, self.cy,
-            _ffi.ptr(self.r), _ffi.ptr(self.Jc), _ffi.ptr(self.Jp), _ffi.ptr(self.partials),
-            _ffi.ptr(self.cost), s))
+        if exchange is not None:
+            _ffi.check(L.pbk_ba_residual_jacobian_dist(
+                _ffi.ptr(self.obs), self.n_obs, _ffi.ptr(self.points), self.n_points,
+                _ffi.ptr(self.cam_blocks), self.n_cams, self.fx, self.fy, self.cx, self.cy,
+                _ffi.ptr(self.r), _ffi.ptr(self.Jc), _ffi.ptr(self.Jp), _ffi.ptr(self.partials),
+                _ffi.ptr(self.cost), exchange.ptrs, exchange.rank, exchange.world, exchange.next_seq(), s))
+        else:
+            _ffi.check(L.pbk_ba_residual_jacobian(
+                _ffi.ptr(self.obs), self.n_obs, _ffi.ptr(self.points), self.n_points,
+                _ffi.ptr(self.cam_blocks), self.n_cams, self.fx, self.fy, self.cx, self.cy,
+                _ffi.ptr(self.r), _ffi.ptr(self.Jc), _ffi.ptr(self.Jp), _ffi.ptr(self.partials),
+                _ffi.ptr(self.cost), s))
         if events is not None:
             events[1].record()
         return self

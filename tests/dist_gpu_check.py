@@ -38,8 +38,16 @@ def main():
     assert int(want[0][9, 0]) == 123 and int(want[0][9, 1]) == 40_123
 
     prob = syn.c4_problem(n_cams=50, n_points=20_000)
-    sb = ShardedBA(*prob)
+    sb = ShardedBA(*prob)                                 # fused peer-memory exchange
+    assert sb.exchange is not None
     cost = float(sb.evaluate().item())
+    for _ in range(5):                                    # repeated calls: sequence numbers / slot parity
+        assert float(sb.evaluate().item()) == cost
+    nccl_cost = float(ShardedBA(*prob, exchange="nccl").evaluate().item())
+    assert abs(nccl_cost - cost) <= 1e-12 * cost
+    gathered = [None] * world
+    dist.all_gather_object(gathered, cost)
+    assert all(c == gathered[0] for c in gathered), "ranks disagree on the fused cost"
     whole = ops.BAProblemDevice(*prob).evaluate()
     ref = float(whole.cost.item())
     assert abs(cost - ref) <= 1e-12 * ref, (cost, ref)
