@@ -280,29 +280,38 @@ def run_c3(D, args):
     flush = make_flush(torch)
 
     def step(rec):
+        if D.world > 1:
+            # sharded: both exchanges (top-2 keys, matched rows) are fused into the kernels
+            # over NVLink peer memory; the events bracket the shard scan + its key exchange
+            ev = ev_pair(torch) if rec is not None else None
+            out = m.match(q_dev, 0.75, events=ev)
+            if rec is not None:
+                rec.append(ev)
+            return out
         if rec is not None:
             a, b = ev_pair(torch)
             a.record()
-            keys_local = m.local_keys(q_dev)
+            keys = m.local_keys(q_dev)
             b.record()
             rec.append((a, b))
         else:
-            keys_local = m.local_keys(q_dev)
-        if D.world > 1:
-            g = torch.empty((D.world * keys_local.shape[0], 2), dtype=keys_local.dtype, device="cuda")
-            D.dist.all_gather_into_tensor(g, keys_local)
-            keys = ops.hamming_merge(g.view(D.world, -1, 2))
-        else:
-            keys = keys_local
+            keys = m.local_keys(q_dev)
         rows = ops.hamming_gather_best(shard, keys, m.shard_base)
-        if D.world > 1:
-            D.dist.all_reduce(rows, op=D.dist.ReduceOp.SUM)
         rev = ops.hamming_knn2_keys(rows, q_dev, 0)
         return ops.hamming_ratio_mutual(keys, rev, 0.75)
 
     sampler = ClockSampler(D.local).start() if D.rank == 0 else None
     total_ms, knn_ms = timed_steps(D, step, args.steps, args.warmup, flush)
     clocks = sampler.stop() if sampler else None
+    variants = {}
+    if D.world > 1:
+        m_nccl = ShardedKeyframeMatcher(shard, lo_kf * per_kf, exchange="nccl")
+
+        def step_nccl(rec):
+            return m_nccl.match(q_dev, 0.75)
+        ms_n, _ = timed_steps(D, step_nccl, args.steps, args.warmup, flush)
+        variants["nccl_allgather_allreduce_between_kernels"] = {
+            "Gpairs_per_s": float(nq) * nkf * per_kf * args.steps / (ms_n * 1e-3) / 1e9, "ms": ms_n / args.steps}
 
     # end to end through the public API: pinned host queries in, numpy results out
     def e2e_step(rec):
@@ -311,7 +320,7 @@ def run_c3(D, args):
     e2e_ms, _ = timed_steps(D, e2e_step, args.steps, args.warmup, flush)
 
     pairs = float(nq) * nt_total
-    launches = (6 if D.world == 1 else 7) * args.steps
+    launches = (6 if D.world == 1 else 9) * args.steps
     res = {
         "metric": "hamming_knn_k2_ratio_mutual", "unit": "Gpairs/s",
         "value": pairs * args.steps / (total_ms * 1e-3) / 1e9,
@@ -327,6 +336,9 @@ def run_c3(D, args):
                 "d2h_bytes_per_step": nq * (2 * 8 + 2 * 4 + 1)},
         "gpu_launches": launches,
         "clocks": clocks,
+        "exchange": ("top-2 keys and matched rows pushed to every peer from inside the kernels over NVLink peer "
+                     "memory (symmetric memory); no NCCL call in the step" if D.world > 1 else "none (1 GPU)"),
+        "variants": variants,
     }
     if D.rank == 0:
         pk = probe_peaks(D)

@@ -181,6 +181,31 @@ PBK_API int pbk_hamming_ratio_mutual(const uint64_t* keys, const uint64_t* rev_k
                              uint8_t* mutual_ok, uint8_t* valid,
                              pbk_stream_t stream);
 
+/* Sharded matching with the exchanges FUSED into the kernels: the
+ * split-merge kernel stores this rank's top-2 keys into every peer's exchange
+ * buffer over NVLink peer memory, the gather kernel does the same with the
+ * matched train rows it owns; the consumers wait for the peers' sequence
+ * numbers.  No NCCL call on the data path; results are bit-identical to
+ * pbk_hamming_knn2 over the whole database.
+ * peer_bufs    host array of `world` device pointers: peer_bufs[p] = rank p's
+ *              exchange buffer AS MAPPED INTO THIS PROCESS, each >=
+ *              pbk_hamming_exchange_words(nq, world) uint64, zeroed before the
+ *              first call
+ * seq          call counter, identical on all ranks, 1, 2, 3 ... ; one value is
+ *              shared by the knn2_dist and gather_best_dist calls of a frame
+ * done_counter device uint32[1], zero before the first call
+ * knn2_dist:        keys (nq,2) = GLOBAL top-2 on every rank
+ * gather_best_dist: rows (nq,32) = the matched train rows on every rank          */
+PBK_API size_t pbk_hamming_exchange_words(int64_t nq, int world);
+PBK_API int pbk_hamming_knn2_dist(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt,
+                     uint64_t train_base, uint64_t* keys, void* scratch,
+                     const uint64_t* peer_bufs, int rank, int world, uint64_t seq,
+                     uint32_t* done_counter, pbk_stream_t stream);
+PBK_API int pbk_hamming_gather_best_dist(const uint8_t* t, int64_t nt, uint64_t train_base,
+                     const uint64_t* keys, int64_t nq, uint8_t* rows,
+                     const uint64_t* peer_bufs, int rank, int world, uint64_t seq,
+                     uint32_t* done_counter, pbk_stream_t stream);
+
 /* popc-pipe peak probe (measurement only): ctas x 256 threads run `iters`
  * rounds of mode 0: independent POPC chains; 1: POPC + one LOP3 each;
  * 2 / 3: the matcher's inner instruction mix (8 / 4 POPC per pair) on

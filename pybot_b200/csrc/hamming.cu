@@ -47,6 +47,7 @@ constexpr int kKeyShift = 23;                   // local row index < 2^23
 constexpr uint32_t kKeyMul = (1u << kKeyShift) + 1u;
 constexpr uint32_t kLocalNone = 0xFFFFFFFFu;
 constexpr long long kMaxSplitRows = 1ll << kKeyShift;
+constexpr int kHMaxWorld = 16;                  // ranks of the fused multi-GPU exchange
 
 struct HammingParams {
   const uint8_t* q;
@@ -308,6 +309,152 @@ hamming_ratio_mutual_kernel(const unsigned long long* __restrict__ keys,
   if (valid != nullptr) valid[i] = r_ok && m_ok;
 }
 
+// ------------------------------------------ multi-GPU exchange over peer memory
+// The sharded matcher needs two exchanges per query frame: every rank's local
+// top-2 keys (nq x 16 B) to all ranks, and the matched train rows (32 B each,
+// owned by exactly one rank) to all ranks for the mutual check.  Both are fused
+// into the kernels that produce the data: they store straight into every peer's
+// exchange buffer over NVLink (peer-mapped symmetric memory) and publish a
+// sequence number; the consuming kernel waits for the `world` sequence numbers.
+// Exchange buffer layout (u64 words), two copies selected by the call parity:
+//   keys  [2][world][nq][2]   local top-2 keys of every rank
+//   rows  [2][nq][4]          matched 256-bit train rows
+//   flags [2][2][world]       sequence number per (phase, producing rank)
+// A rank reuses a copy only after every peer has finished the call in between.
+struct HammingPeers {
+  unsigned long long* buf[kHMaxWorld];
+  long long nq;
+  int rank, world;
+  unsigned long long seq;
+};
+__device__ __forceinline__ size_t hx_keys(const HammingPeers& X, int par, int r) {
+  return ((size_t)par * X.world + r) * (size_t)X.nq * 2;
+}
+__device__ __forceinline__ size_t hx_rows(const HammingPeers& X, int par) {
+  return (size_t)2 * X.world * X.nq * 2 + (size_t)par * X.nq * 4;
+}
+__device__ __forceinline__ size_t hx_flags(const HammingPeers& X, int par, int phase) {
+  return (size_t)2 * X.world * X.nq * 2 + (size_t)2 * X.nq * 4 + ((size_t)par * 2 + phase) * X.world;
+}
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// the last CTA of a producing kernel publishes the sequence number to every peer
+__device__ __forceinline__ void hx_publish(const HammingPeers& X, int phase, unsigned int* done_counter) {
+  __shared__ int s_last;
+  __threadfence_system();                      // this thread's peer stores are visible system-wide
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {
+    __threadfence_system();
+    if ((int)threadIdx.x < X.world) {
+      unsigned long long* f = X.buf[threadIdx.x] + hx_flags(X, (int)(X.seq & 1ull), phase) + X.rank;
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(X.seq) : "memory");
+    }
+    if (threadIdx.x == 0) *done_counter = 0u;  // ready for the next call
+  }
+}
+// every CTA of a consuming kernel waits until all ranks have published `phase`
+// (bounded: ~2 s, after which the call's results are garbage instead of a hang)
+__device__ __forceinline__ void hx_wait(const HammingPeers& X, int phase) {
+  if ((int)threadIdx.x < X.world) {
+    const unsigned long long* f = X.buf[X.rank] + hx_flags(X, (int)(X.seq & 1ull), phase) + threadIdx.x;
+    unsigned long long got = 0;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(f) : "memory");
+    } while (got != X.seq && clock64() - t0 < (4ll << 30));
+  }
+  __syncthreads();
+}
+
+// split merge of this rank's partial keys + push of the result to every peer
+__global__ void __launch_bounds__(256)
+hamming_merge_push_kernel(const unsigned long long* __restrict__ partial, int parts,
+                          const __grid_constant__ HammingPeers X, unsigned int* done_counter) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < X.nq) {
+    unsigned long long b1 = PBK_KEY_NONE, b2 = PBK_KEY_NONE;
+    for (int p = 0; p < parts; ++p) {
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(partial + ((long long)p * X.nq + i) * 2);
+      unsigned long long mx = max(b1, v.x);
+      b1 = min(b1, v.x);
+      b2 = min(b2, mx);
+      mx = max(b1, v.y);
+      b1 = min(b1, v.y);
+      b2 = min(b2, mx);
+    }
+    const size_t off = hx_keys(X, (int)(X.seq & 1ull), X.rank) + (size_t)i * 2;
+    for (int p = 0; p < X.world; ++p) {
+      st_sys_u64(X.buf[p] + off, b1);
+      st_sys_u64(X.buf[p] + off + 1, b2);
+    }
+  }
+  hx_publish(X, 0, done_counter);
+}
+
+// wait for every rank's keys, then global top-2 by unsigned min (same order on every rank)
+__global__ void __launch_bounds__(256)
+hamming_merge_world_kernel(const __grid_constant__ HammingPeers X, unsigned long long* __restrict__ keys) {
+  hx_wait(X, 0);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= X.nq) return;
+  const unsigned long long* mine = X.buf[X.rank];
+  unsigned long long b1 = PBK_KEY_NONE, b2 = PBK_KEY_NONE;
+  for (int r = 0; r < X.world; ++r) {
+    const unsigned long long* src = mine + hx_keys(X, (int)(X.seq & 1ull), r) + (size_t)i * 2;
+    const unsigned long long vx = __ldcv(src), vy = __ldcv(src + 1);
+    unsigned long long mx = max(b1, vx);
+    b1 = min(b1, vx);
+    b2 = min(b2, mx);
+    mx = max(b1, vy);
+    b1 = min(b1, vy);
+    b2 = min(b2, mx);
+  }
+  *reinterpret_cast<ulonglong2*>(keys + i * 2) = make_ulonglong2(b1, b2);
+}
+
+// the owner of each matched train row pushes it to every peer (rank 0 pushes zeros for "no match")
+__global__ void __launch_bounds__(256)
+hamming_gather_push_kernel(const uint8_t* __restrict__ t, long long nt, unsigned long long train_base,
+                           const unsigned long long* __restrict__ keys, const __grid_constant__ HammingPeers X,
+                           unsigned int* done_counter) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < X.nq) {
+    const unsigned long long k = keys[2 * i];
+    const unsigned long long g = k & 0xffffffffull;
+    const bool none = k == PBK_KEY_NONE;
+    const bool own = !none && g >= train_base && g - train_base < (unsigned long long)nt;
+    if (own || (none && X.rank == 0)) {
+      ulonglong2 a = make_ulonglong2(0, 0), b = a;
+      if (own) {
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(t + (g - train_base) * 32);
+        a = src[0];
+        b = src[1];
+      }
+      const size_t off = hx_rows(X, (int)(X.seq & 1ull)) + (size_t)i * 4;
+      for (int p = 0; p < X.world; ++p) {
+        unsigned long long* dst = X.buf[p] + off;
+        st_sys_u64(dst, a.x); st_sys_u64(dst + 1, a.y); st_sys_u64(dst + 2, b.x); st_sys_u64(dst + 3, b.y);
+      }
+    }
+  }
+  hx_publish(X, 1, done_counter);
+}
+
+// wait for every rank's rows, then copy the matched rows out of the exchange buffer
+__global__ void __launch_bounds__(256)
+hamming_rows_world_kernel(const __grid_constant__ HammingPeers X, uint8_t* __restrict__ rows) {
+  hx_wait(X, 1);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= X.nq) return;
+  const unsigned long long* src = X.buf[X.rank] + hx_rows(X, (int)(X.seq & 1ull)) + (size_t)i * 4;
+  ulonglong2* dst = reinterpret_cast<ulonglong2*>(rows + i * 32);
+  dst[0] = make_ulonglong2(__ldcv(src), __ldcv(src + 1));
+  dst[1] = make_ulonglong2(__ldcv(src + 2), __ldcv(src + 3));
+}
+
 // ------------------------------------------------------- popc pipe probe
 // mode 0: pure POPC chains (8 independent per thread) -> popc-pipe peak
 // mode 1: POPC + one LOP3 per POPC (checks POPC/ALU overlap)
@@ -487,6 +634,87 @@ int pbk_hamming_ratio_mutual(const uint64_t* keys, const uint64_t* rev_keys, int
       reinterpret_cast<const unsigned long long*>(keys), reinterpret_cast<const unsigned long long*>(rev_keys),
       nq, ratio, reinterpret_cast<long long*>(idx), dist, ratio_ok, mutual_ok, valid);
   PBK_CHECK_LAUNCH("hamming_ratio_mutual_kernel");
+  return PBK_OK;
+}
+
+size_t pbk_hamming_exchange_words(int64_t nq, int world) {
+  if (nq < 0 || world < 1) return 0;
+  return (size_t)2 * world * nq * 2 + (size_t)2 * nq * 4 + (size_t)4 * world;
+}
+
+static int fill_peers(pbk::HammingPeers* X, const uint64_t* peer_bufs, int64_t nq, int rank, int world,
+                      uint64_t seq) {
+  using namespace pbk;
+  PBK_REQUIRE(world >= 2 && world <= kHMaxWorld && rank >= 0 && rank < world, PBK_EINVAL, "bad rank/world");
+  PBK_REQUIRE(peer_bufs != nullptr && seq >= 1, PBK_EINVAL, "the fused exchange needs peer buffers and seq >= 1");
+  for (int p = 0; p < kHMaxWorld; ++p)
+    X->buf[p] = p < world ? reinterpret_cast<unsigned long long*>(peer_bufs[p]) : nullptr;
+  X->nq = nq; X->rank = rank; X->world = world; X->seq = seq;
+  return PBK_OK;
+}
+
+int pbk_hamming_knn2_dist(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, uint64_t train_base,
+                          uint64_t* keys, void* scratch, const uint64_t* peer_bufs, int rank, int world,
+                          uint64_t seq, uint32_t* done_counter, pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(nq > 0 && nt >= 0, PBK_EINVAL, "bad sizes");
+  PBK_REQUIRE(q != nullptr && keys != nullptr && scratch != nullptr && done_counter != nullptr, PBK_EINVAL,
+              "NULL device pointer");
+  PBK_REQUIRE(nt == 0 || t != nullptr, PBK_EINVAL, "NULL train pointer");
+  PBK_REQUIRE(aligned16(q) && aligned16(t) && aligned16(keys) && aligned16(scratch), PBK_EALIGN,
+              "device pointers must be 16-byte aligned");
+  PBK_REQUIRE(train_base + (uint64_t)nt <= (1ull << 32), PBK_EINVAL, "global train row index must fit 32 bits");
+  HammingPeers X;
+  int rc = fill_peers(&X, peer_bufs, nq, rank, world, seq);
+  if (rc) return rc;
+  const DeviceInfo* di;
+  rc = current_device_info(&di);
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  int splits;
+  long long rps;
+  rc = plan(di, nq, nt, &splits, &rps);
+  if (rc) return rc;
+  HammingParams P;
+  P.q = q; P.t = t; P.partial = static_cast<unsigned long long*>(scratch);
+  P.nq = nq; P.nt = nt; P.rows_per_split = rps; P.train_base = train_base; P.splits = splits;
+  const int smem = kStages * kStageBytes + kQTile * 32 + (kStages + 1) * 8;
+  const dim3 grid((unsigned)((nq + kQTile - 1) / kQTile), (unsigned)splits);
+  if (hamming_variant() == 0) {
+    PBK_CUDA(cudaFuncSetAttribute(hamming_knn2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    hamming_knn2_kernel<0><<<grid, kHThreads, smem, s>>>(P);
+  } else {
+    PBK_CUDA(cudaFuncSetAttribute(hamming_knn2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    hamming_knn2_kernel<1><<<grid, kHThreads, smem, s>>>(P);
+  }
+  PBK_CHECK_LAUNCH("hamming_knn2_kernel");
+  const unsigned blocks = (unsigned)((nq + 255) / 256);
+  hamming_merge_push_kernel<<<blocks, 256, 0, s>>>(P.partial, splits, X, done_counter);
+  PBK_CHECK_LAUNCH("hamming_merge_push_kernel");
+  hamming_merge_world_kernel<<<blocks, 256, 0, s>>>(X, reinterpret_cast<unsigned long long*>(keys));
+  PBK_CHECK_LAUNCH("hamming_merge_world_kernel");
+  return PBK_OK;
+}
+
+int pbk_hamming_gather_best_dist(const uint8_t* t, int64_t nt, uint64_t train_base, const uint64_t* keys,
+                                 int64_t nq, uint8_t* rows, const uint64_t* peer_bufs, int rank, int world,
+                                 uint64_t seq, uint32_t* done_counter, pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(nt >= 0 && nq > 0, PBK_EINVAL, "bad sizes");
+  PBK_REQUIRE(keys != nullptr && rows != nullptr && done_counter != nullptr && (nt == 0 || t != nullptr),
+              PBK_EINVAL, "NULL device pointer");
+  PBK_REQUIRE(aligned16(t) && aligned16(keys) && aligned16(rows), PBK_EALIGN,
+              "device pointers must be 16-byte aligned");
+  HammingPeers X;
+  int rc = fill_peers(&X, peer_bufs, nq, rank, world, seq);
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  const unsigned blocks = (unsigned)((nq + 255) / 256);
+  hamming_gather_push_kernel<<<blocks, 256, 0, s>>>(t, nt, train_base,
+                                                    reinterpret_cast<const unsigned long long*>(keys), X, done_counter);
+  PBK_CHECK_LAUNCH("hamming_gather_push_kernel");
+  hamming_rows_world_kernel<<<blocks, 256, 0, s>>>(X, rows);
+  PBK_CHECK_LAUNCH("hamming_rows_world_kernel");
   return PBK_OK;
 }
 

@@ -5,12 +5,15 @@ gloo in the CPU tests) for the plumbing.
 
 * Loop-closure matching: the keyframe database is split into contiguous
   keyframe ranges, one per rank; queries are replicated.  Every rank computes
-  its top-2 packed keys ``(distance << 32 | global_row)``, the 32 KB results are
-  all-gathered and merged with the same unsigned min the kernel uses, so the
-  result is bit-identical to the single-GPU scan.  For the mutual check the
-  owner of each matched train row contributes it to a (nq,32) uint8 buffer that
-  is sum-all-reduced (every other rank contributes zeros), then every rank runs
-  the tiny reverse pass locally.
+  its top-2 packed keys ``(distance << 32 | global_row)``; the 32 KB results
+  reach every rank and are merged with the same unsigned min the kernel uses, so
+  the result is bit-identical to the single-GPU scan.  For the mutual check the
+  owner of each matched train row sends it to every rank, then every rank runs
+  the tiny reverse pass locally.  Both exchanges are FUSED into the producing
+  kernels (stores into the peers' symmetric-memory buffers over NVLink + a
+  sequence number the consumer waits for); the NCCL variant (all-gather of the
+  keys, sum-all-reduce of an owner-filled row buffer) remains as the alternative
+  and is what the CPU tests drive.
 * BA residual/Jacobian: observations are split into contiguous chunks; cameras
   and points are replicated; the only exchange is the sum-all-reduce of the fp64
   cost, which is FUSED into the streaming kernel: its last CTA stores the rank's
@@ -56,11 +59,41 @@ class _CudaMatchKernels(object):
         return ops.hamming_ratio_mutual(keys, rev, ratio)
 
 
+class PeerKeyExchange(object):
+    """Peer-mapped exchange buffer of the fused matcher exchanges
+    (pbk_hamming_knn2_dist / pbk_hamming_gather_best_dist) for `nq` queries: a
+    torch symmetric-memory allocation whose per-rank addresses are handed to the
+    kernels.  Collective: every rank of `group` must construct it."""
+
+    def __init__(self, nq, group=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.nq, self.world, self.rank = int(nq), dist.get_world_size(group), dist.get_rank(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        words = int(_ffi.lib().pbk_hamming_exchange_words(self.nq, self.world))
+        self.buf = symm_mem.empty(max(words, 64), dtype=torch.int64, device=dev)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group=group)
+        self.done = torch.zeros(4, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier(group)                                  # every buffer is zero before the first store
+        self.ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+        self.seq = 0
+
+
 class ShardedKeyframeMatcher(object):
     """Holds this rank's shard of the keyframe database and matches replicated
-    queries against the whole database."""
+    queries against the whole database.
 
-    def __init__(self, shard, shard_base, group=None, kernels=None):
+    exchange: "p2p" fuses both exchanges (top-2 keys, matched rows) into the
+    kernels over NVLink peer memory (default on the CUDA path when world > 1);
+    "nccl" all-gathers / all-reduces with NCCL between the kernels (also what the
+    gloo CPU tests drive)."""
+
+    def __init__(self, shard, shard_base, group=None, kernels=None, exchange=None):
         """shard: (n_local, 32) uint8 tensor on this rank's device;
         shard_base: global row index of shard[0]."""
         import torch.distributed as dist
@@ -68,9 +101,16 @@ class ShardedKeyframeMatcher(object):
         self.group = group
         self.shard = shard
         self.shard_base = int(shard_base)
+        cuda_path = kernels is None
         self.kernels = kernels if kernels is not None else _CudaMatchKernels()
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if exchange is None:
+            exchange = "p2p" if (cuda_path and self.world > 1) else "nccl"
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        self.fused = exchange == "p2p" and self.world > 1
+        self._px = None
 
     def local_keys(self, q):
         return self.kernels.knn2(q, self.shard, self.shard_base)
@@ -87,8 +127,44 @@ class ShardedKeyframeMatcher(object):
         self.dist.all_gather_into_tensor(gathered, local.contiguous(), group=self.group)
         return self.kernels.merge(gathered.view((self.world,) + tuple(local.shape)))
 
-    def match(self, q, ratio=0.75, mutual=True):
-        """idx (nq,2) global rows, dist (nq,2), ratio_ok, mutual_ok, valid."""
+    def _match_fused(self, q, ratio, mutual, events=None):
+        """knn2 -> [keys pushed to all peers] -> world merge -> gather -> [rows pushed
+        to all peers] -> reverse knn2 -> ratio/mutual, without a collective call."""
+        import ctypes
+        from . import ops
+        T = _ffi.torch()
+        nq, nt = int(q.shape[0]), int(self.shard.shape[0])
+        if self._px is None or self._px.nq != nq:
+            self._px = PeerKeyExchange(nq, self.group)               # collective, once per query count
+        px = self._px
+        px.seq += 1
+        L, s = _ffi.lib(), _ffi.stream_ptr()
+        splits, nbytes = ctypes.c_int(0), ctypes.c_size_t(0)
+        _ffi.check(L.pbk_hamming_plan(nq, nt, ctypes.byref(splits), ctypes.byref(nbytes)))
+        scratch = T.empty((max(int(nbytes.value), 16),), dtype=T.uint8, device=q.device)
+        keys = T.empty((nq, 2), dtype=T.int64, device=q.device)
+        if events is not None:
+            events[0].record()
+        _ffi.check(L.pbk_hamming_knn2_dist(_ffi.ptr(q), nq, _ffi.ptr(self.shard) if nt else None, nt,
+                                           self.shard_base, _ffi.ptr(keys), _ffi.ptr(scratch), px.ptrs, px.rank,
+                                           px.world, px.seq, _ffi.ptr(px.done), s))
+        if events is not None:
+            events[1].record()
+        rev = None
+        if mutual:
+            rows = T.empty((nq, 32), dtype=T.uint8, device=q.device)
+            _ffi.check(L.pbk_hamming_gather_best_dist(_ffi.ptr(self.shard) if nt else None, nt, self.shard_base,
+                                                      _ffi.ptr(keys), nq, _ffi.ptr(rows), px.ptrs, px.rank,
+                                                      px.world, px.seq, _ffi.ptr(px.done), s))
+            rev = ops.hamming_knn2_keys(rows, q, 0)
+        return ops.hamming_ratio_mutual(keys, rev, ratio)
+
+    def match(self, q, ratio=0.75, mutual=True, events=None):
+        """idx (nq,2) global rows, dist (nq,2), ratio_ok, mutual_ok, valid.
+        `events` (fused path): (start, end) CUDA events recorded around the scan of
+        this rank's shard including its key exchange."""
+        if self.fused and int(q.shape[0]) > 0:
+            return self._match_fused(q, ratio, mutual, events)
         keys = self.global_keys(q)
         rev = None
         if mutual:

@@ -30,11 +30,20 @@ def main():
     q[9] = db[123]
     lo, hi = shard_range(nkf, rank, world)
     shard = torch.from_numpy(db[lo * per_kf:hi * per_kf]).cuda()
-    m = ShardedKeyframeMatcher(shard, lo * per_kf)
-    got = m.match(torch.from_numpy(q).cuda(), 0.75)
     want = ops.knn_ratio_mutual(torch.from_numpy(q).cuda(), torch.from_numpy(db).cuda(), 0.75)
+    m = ShardedKeyframeMatcher(shard, lo * per_kf)         # fused peer-memory exchanges
+    assert m.fused
+    for rep in range(4):                                   # repeated frames: sequence numbers / buffer parity
+        got = m.match(torch.from_numpy(q).cuda(), 0.75)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b), "fused sharded matching differs from the single-GPU scan"
+    got = ShardedKeyframeMatcher(shard, lo * per_kf, exchange="nccl").match(torch.from_numpy(q).cuda(), 0.75)
     for a, b in zip(got, want):
-        assert torch.equal(a, b), "sharded matching differs from the single-GPU scan"
+        assert torch.equal(a, b), "NCCL sharded matching differs from the single-GPU scan"
+    q2 = q[:500].copy()                                    # a different query count re-creates the exchange
+    got = m.match(torch.from_numpy(q2).cuda(), 0.75)
+    for a, b in zip(got, ops.knn_ratio_mutual(torch.from_numpy(q2).cuda(), torch.from_numpy(db).cuda(), 0.75)):
+        assert torch.equal(a, b)
     assert int(want[0][9, 0]) == 123 and int(want[0][9, 1]) == 40_123
 
     prob = syn.c4_problem(n_cams=50, n_points=20_000)
