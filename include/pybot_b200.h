@@ -297,6 +297,40 @@ PBK_API int pbk_sceneflow(const void* dX, int dtype, int H, int W,
 PBK_API int pbk_sampson_error(const double* F, const double* pts1, const double* pts2, int64_t n,
                               double* err, pbk_stream_t stream);
 
+/* triangulate_points, pybot/vision/camera_utils.py:108-116:
+ * cv2.triangulatePoints(P1, P2, x1, x2).T dehomogenised.  P1, P2 host 12 doubles
+ * (3x4 row-major); x1, x2 device (n,2), dtype in {F32, F64}; out device (n,3) of
+ * the same dtype.  One-sided Jacobi SVD per point, ~1e-14 relative of OpenCV.    */
+PBK_API int pbk_triangulate_points(const double* P1, const double* P2, const void* x1,
+                                   const void* x2, int dtype, int64_t n, void* out,
+                                   pbk_stream_t stream);
+
+/* CameraIntrinsic.undistort_points / ray / reconstruct,
+ * pybot/vision/camera_utils.py:499-538.                                         */
+typedef struct pbk_ray_params {
+  double fx, fy, cx, cy;   /* camera matrix K (skew ignored, like OpenCV)                 */
+  double k[8];             /* k1 k2 p1 p2 k3 k4 k5 k6                                      */
+  double P[9];             /* new camera matrix of cv2.undistortPoints(P=...), row-major   */
+  double rot[9];           /* Quaternion.rotate coefficient rows (quaternion.py:69-85):
+                            * out_i = 2*(rot[3i]*v0 + rot[3i+1]*v1 + rot[3i+2]*v2) + v_i    */
+  int32_t undistort;       /* ray: run undistort_points first                 (:505)       */
+  int32_t rotate;          /* ray: extrinsics.rotate_vec                      (:511-512)   */
+  int32_t normalize;       /* ray: divide by the Euclidean norm               (:514-515)   */
+  int32_t scale_by_z;      /* reconstruct: multiply by pts[:, 2]              (:519-524)   */
+} pbk_ray_params;
+
+/* cv2.undistortPoints(pts.astype(float32), K, D, P=P) (:536-537): five fixed-point
+ * iterations of the inverse distortion in fp64, then P; float32 out, bit-exact.
+ * pts device (n, stride) rows of dtype in {F32, F64}, stride >= 2 elements.      */
+PBK_API int pbk_undistort_points(const void* pts, int dtype, int stride, int64_t n,
+                                 const pbk_ray_params* params, float* out, pbk_stream_t stream);
+
+/* ray()/reconstruct(): [(u-cx)/fx, (v-cy)/fy, 1] (optionally of the undistorted
+ * float32 pixel), rotated, normalised, scaled by the row's third element.
+ * out device (n,3) float64.                                                      */
+PBK_API int pbk_camera_rays(const void* pts, int dtype, int stride, int64_t n,
+                            const pbk_ray_params* params, double* out, pbk_stream_t stream);
+
 /* Point-cloud colours in the viewer wire format: get_color_arr,
  * pybot/externals/draw_helpers.py:35-53, for uint8 (n_px,3) images -> float32
  * (n_px,3) = c / 255.0 with optional B<->R flip; this is the block arr_msg

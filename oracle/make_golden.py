@@ -293,6 +293,57 @@ def g7_epipolar_wire(ns):
         wire_flip=g["get_color_arr"](im.copy(), im.size // 3, flip_rb=True))
 
 
+def g8_rays_triangulate(ns):
+    """G8: CameraIntrinsic.undistort_points / ray / reconstruct and
+    triangulate_points of the real reference."""
+    import importlib
+    cu = importlib.import_module("pybot.vision.camera_utils")
+    rng = np.random.default_rng(808)
+    K = syn.kitti_K()
+    out = {"K": K}
+    pts = rng.uniform([-60, -40], [1300, 420], (600, 2))
+    pts[:4] = [[K[0, 2], K[1, 2]], [0, 0], [1240.5, 375.5], [-1e4, 3e4]]
+    out["pts"] = pts
+    rp = (0.3, -0.2, 0.7, 0.5, -0.1, 1.2)
+    pose = ns.RigidTransform.from_rpyxyz(*rp)
+    out["pose_rpyxyz"] = np.float64(rp)
+    dists = {"d0": np.zeros(5), "d5": np.float64([-0.3, 0.1, 0.001, -0.002, 0.01]),
+             "d4": np.float64([-0.37, 0.2, 0.0005, 0.0003]),
+             "d8": np.float64([0.1, -0.05, 0.001, 0.002, 0.003, 0.01, 0.02, -0.003]),
+             "dneg": np.float64([-0.9, 0.1, 0, 0, 0])}            # icdist < 0 branch far from the centre
+    for name, D in dists.items():
+        out["D_" + name] = D
+        ci = ns.CameraIntrinsic(K, D=D, shape=(376, 1241))
+        out["und_" + name] = ci.undistort_points(pts)
+        out["ray_" + name] = ci.ray(pts)
+    ci = ns.CameraIntrinsic(K, D=dists["d5"], shape=(376, 1241))
+    cam = ns.Camera.from_intrinsics_extrinsics(ci, ns.CameraExtrinsic.from_rigid_transform(pose))
+    out["ray_raw_f64"] = ci.ray(pts, undistort=False)
+    out["ray_raw_f32"] = ci.ray(pts.astype(np.float32), undistort=False)
+    out["ray_norm"] = ci.ray(pts, normalize=True)
+    out["ray_rot"] = cam.ray(pts, rotate=True)
+    out["ray_rot_norm"] = cam.ray(pts, undistort=False, rotate=True, normalize=True)
+    xyZ = np.hstack([pts, rng.uniform(0.5, 40, (len(pts), 1))])
+    out["xyZ"] = xyZ
+    out["rec"] = ci.reconstruct(xyZ)
+    out["rec_raw"] = ci.reconstruct(xyZ, undistort=False)
+    # triangulation: two posed KITTI cameras, exact and noisy correspondences, f64 and f32
+    mk = lambda *rp: ns.Camera.from_intrinsics_extrinsics(          # noqa: E731
+        ns.CameraIntrinsic(K, shape=(376, 1241)),
+        ns.CameraExtrinsic.from_rigid_transform(ns.RigidTransform.from_rpyxyz(*rp)))
+    rp1, rp2 = (0.01, -0.02, 0.03, 0.1, 0.0, 0.2), (-0.02, 0.05, 0.0, -0.4, 0.05, 0.9)
+    c1, c2 = mk(*rp1), mk(*rp2)
+    X = rng.uniform([-10, -2, 5], [10, 2, 40], (500, 3))
+    p1, p2 = c1.project(X), c2.project(X)
+    p2n = p2 + rng.normal(0, 1.0, p2.shape)
+    out.update(tri_rp1=np.float64(rp1), tri_rp2=np.float64(rp2), tri_P1=c1.P, tri_P2=c2.P, tri_X=X,
+               tri_p1=p1, tri_p2=p2, tri_p2n=p2n,
+               tri_exact=cu.triangulate_points(c1, p1, c2, p2),
+               tri_noisy=cu.triangulate_points(c1, p1, c2, p2n),
+               tri_f32=cu.triangulate_points(c1, p1.astype(np.float32), c2, p2n.astype(np.float32)))
+    np.savez_compressed(os.path.join(OUT, "g8_rays_triangulate.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
@@ -304,6 +355,7 @@ def main():
     g5_ba()
     g6_next_rows(ns)
     g7_epipolar_wire(ns)
+    g8_rays_triangulate(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -274,6 +274,53 @@ def sampson_error(F, pts1, pts2):
     return (np.diag(x1.T.dot(Fx2)))**2 / denom
 
 
+def triangulate_points(P1, P2, pts1, pts2, use_cv2=True):
+    """camera_utils.py:108-116."""
+    if use_cv2 and cv2 is not None:
+        X = cv2.triangulatePoints(P1, P2, pts1.reshape(-1, 1, 2), pts2.reshape(-1, 1, 2)).T
+    else:
+        X = model.triangulate_points(P1, P2, pts1, pts2).T
+    return X[:, :3] / X[:, 3].reshape(-1, 1)
+
+
+def undistort_points(K, D, pts, use_cv2=True):
+    """CameraIntrinsic.undistort_points camera_utils.py:529-538."""
+    if use_cv2 and cv2 is not None:
+        out = cv2.undistortPoints(pts.reshape(-1, 1, 2).astype(np.float32), K, D, P=K)
+        return out.reshape(-1, 2)
+    return model.undistort_points(pts, K, D, P=K)
+
+
+def quaternion_rotate(q, v):
+    """Quaternion.rotate quaternion.py:69-85."""
+    qx, qy, qz, qw = q
+    ab, ac, ad = qw * qx, qw * qy, qw * qz
+    nbb, bc, bd = -qx * qx, qx * qy, qx * qz
+    ncc, cd, ndd = -qy * qy, qy * qz, -qz * qz
+    return np.array((2 * ((ncc + ndd) * v[0] + (bc - ad) * v[1] + (ac + bd) * v[2]) + v[0],
+                     2 * ((ad + bc) * v[0] + (nbb + ndd) * v[1] + (cd - ab) * v[2]) + v[1],
+                     2 * ((bd - ac) * v[0] + (ab + cd) * v[1] + (nbb + ncc) * v[2]) + v[2]))
+
+
+def camera_ray(K, D, pts, undistort=True, rotate_xyzw=None, normalize=False, use_cv2=True):
+    """CameraIntrinsic.ray camera_utils.py:499-517 (rotate: extrinsics.rotate_vec,
+    rigid_transform.py:181-186)."""
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    upts = undistort_points(K, D, pts, use_cv2) if undistort else pts
+    ret = np.hstack([np.hstack([(upts[:, :1] - cx) / fx, (upts[:, 1:2] - cy) / fy]),
+                     np.ones((len(upts), 1))])                 # unproject_points :37-39
+    if rotate_xyzw is not None:
+        ret = np.vstack([quaternion_rotate(rotate_xyzw, v_) for v_ in ret])
+    if normalize:
+        ret = ret / np.linalg.norm(ret, axis=1)[:, np.newaxis]
+    return ret
+
+
+def intrinsic_reconstruct(K, D, xyZ, undistort=True, use_cv2=True):
+    """CameraIntrinsic.reconstruct camera_utils.py:519-524."""
+    return camera_ray(K, D, xyZ[:, :2], undistort=undistort, use_cv2=use_cv2) * xyZ[:, 2:3]
+
+
 def wire_colors(carr, flip_rb=False):
     """get_color_arr externals/draw_helpers.py:35-53 for an array argument."""
     carr = carr.reshape(-1, 3) if carr.ndim == 3 else carr      # reshape_arr :29-33

@@ -37,6 +37,16 @@ class ProjectParams(ctypes.Structure):
     ]
 
 
+class RayParams(ctypes.Structure):
+    """struct pbk_ray_params."""
+    _fields_ = [
+        ("fx", ctypes.c_double), ("fy", ctypes.c_double), ("cx", ctypes.c_double), ("cy", ctypes.c_double),
+        ("k", ctypes.c_double * 8), ("P", ctypes.c_double * 9), ("rot", ctypes.c_double * 9),
+        ("undistort", ctypes.c_int32), ("rotate", ctypes.c_int32),
+        ("normalize", ctypes.c_int32), ("scale_by_z", ctypes.c_int32),
+    ]
+
+
 _vp, _i, _i64, _u64, _d, _sz = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
                                 ctypes.c_uint64, ctypes.c_double, ctypes.c_size_t)
 
@@ -65,6 +75,9 @@ SIGNATURES = {
     "pbk_depth_reconstruct_sparse": (_i, [_vp, _vp, _i64, _d, _d, _d, _vp, _vp]),
     "pbk_sceneflow": (_i, [_vp, _i, _i, _i, ctypes.POINTER(ProjectParams), _vp, _vp, _vp]),
     "pbk_sampson_error": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "pbk_triangulate_points": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp]),
+    "pbk_undistort_points": (_i, [_vp, _i, _i, _i64, ctypes.POINTER(RayParams), _vp, _vp]),
+    "pbk_camera_rays": (_i, [_vp, _i, _i, _i64, ctypes.POINTER(RayParams), _vp, _vp]),
     "pbk_wire_colors": (_i, [_vp, _i64, _i, _vp, _vp]),
     "pbk_ba_camera_precompute": (_i, [_vp, _vp, _i, _vp, _vp]),
     "pbk_ba_cost_slots": (_i, [_i64]),

@@ -12,6 +12,10 @@
 //      resolve kernel, and only the (H,W,2) flow leaves the device.
 //  * sampson_error / filter_sampson_error            pybot/vision/camera_utils.py:52-90
 //      epipolar filter between matching and triangulation; diagonal only.
+//  * triangulate_points                              pybot/vision/camera_utils.py:108-116
+//      cv2.triangulatePoints (DLT + 4x4 SVD per point) + dehomogenisation.
+//  * CameraIntrinsic.undistort_points / ray / reconstruct  pybot/vision/camera_utils.py:499-538
+//      cv2.undistortPoints (5 fixed-point iterations, fp64) + ray / rotate / normalise / *Z.
 //  * viewer wire colours                             pybot/externals/draw_helpers.py:35-59,
 //      float32 RGB in [0,1] exactly as arr_msg ships them  pybot/externals/pb.py:18-38
 #include "pbk_common.cuh"
@@ -228,6 +232,190 @@ sampson_error_kernel(const double* __restrict__ p1, const double* __restrict__ p
   err[i] = __ddiv_rn(__dmul_rn(d, d), denom);
 }
 
+// -------------------------------------------------------- triangulate_points
+// camera_utils.py:108-116: X = cv2.triangulatePoints(P1, P2, x1, x2).T ; X[:, :3] / X[:, 3].
+// Per point the 4x4 DLT matrix A = [x1*P1[2]-P1[0]; y1*P1[2]-P1[1]; x2*P2[2]-P2[0];
+// y2*P2[2]-P2[1]] and its right singular vector of the smallest singular value, by
+// the one-sided (Hestenes) Jacobi SVD OpenCV uses for small matrices; everything
+// stays in registers (fully unrolled column pairs).  Agrees with cv2 to ~1e-14
+// relative; parity is a tolerance (an SVD has no bit-exact contract).
+struct TriParams {
+  double P1[12], P2[12];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+triangulate_kernel(const T* __restrict__ x1, const T* __restrict__ x2, long long n,
+                   const __grid_constant__ TriParams P, T* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const double u1 = (double)x1[2 * idx], v1 = (double)x1[2 * idx + 1];
+  const double u2 = (double)x2[2 * idx], v2 = (double)x2[2 * idx + 1];
+  double U[4][4], V[4][4];                      // U[row][col]: columns are rotated
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    U[0][c] = u1 * P.P1[8 + c] - P.P1[c];
+    U[1][c] = v1 * P.P1[8 + c] - P.P1[4 + c];
+    U[2][c] = u2 * P.P2[8 + c] - P.P2[c];
+    U[3][c] = v2 * P.P2[8 + c] - P.P2[4 + c];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) V[r][c] = (r == c) ? 1.0 : 0.0;
+  }
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    bool changed = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = i + 1; j < 4; ++j) {
+        double a = 0.0, b = 0.0, p = 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          a = fma(U[r][i], U[r][i], a);
+          b = fma(U[r][j], U[r][j], b);
+          p = fma(U[r][i], U[r][j], p);
+        }
+        if (fabs(p) > 2.220446049250313e-16 * sqrt(a * b) && fabs(p) > 1e-300) {
+          const double p2 = p * 2.0, beta = a - b, gamma = hypot(p2, beta);
+          double c, s;
+          if (beta < 0.0) {
+            const double delta = (gamma - beta) * 0.5;
+            s = sqrt(delta / gamma);
+            c = p / (gamma * s);
+          } else {
+            c = sqrt((gamma + beta) / (gamma * 2.0));
+            s = p / (gamma * c);
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const double ui = U[r][i], uj = U[r][j], vi = V[r][i], vj = V[r][j];
+            U[r][i] = fma(c, ui, s * uj);
+            U[r][j] = fma(-s, ui, c * uj);
+            V[r][i] = fma(c, vi, s * vj);
+            V[r][j] = fma(-s, vi, c * vj);
+          }
+          changed = true;
+        }
+      }
+    }
+    if (!changed) break;
+  }
+  // column with the smallest norm = smallest singular value
+  double best = 0.0, X[4] = {0.0, 0.0, 0.0, 1.0};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    double nrm = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) nrm = fma(U[r][c], U[r][c], nrm);
+    if (c == 0 || nrm < best) {
+      best = nrm;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) X[r] = V[r][c];
+    }
+  }
+  // cv2 returns the homogeneous point in the input depth; the reference divides in that dtype
+  const T w = (T)X[3];
+  out[3 * idx + 0] = (T)X[0] / w;
+  out[3 * idx + 1] = (T)X[1] / w;
+  out[3 * idx + 2] = (T)X[2] / w;
+}
+
+// ------------------------------------------- undistort_points / ray / reconstruct
+// camera_utils.py:499-538.  cv2.undistortPoints with the default criteria runs
+// exactly five iterations of x <- (x0 - delta(x)) / cdist(x) in fp64 and rounds
+// once to float32; every product and sum below is rounded separately in OpenCV's
+// order (oracle/model.py undistort_points), so the float32 pixels are bit-exact.
+__device__ __forceinline__ void undistort_one(const pbk_ray_params& P, double u, double v, float& ou, float& ov) {
+  const double* k = P.k;
+  const double ifx = __ddiv_rn(1.0, P.fx), ify = __ddiv_rn(1.0, P.fy);
+  double x = __dmul_rn(__dsub_rn(u, P.cx), ifx), y = __dmul_rn(__dsub_rn(v, P.cy), ify);
+  const double x0 = x, y0 = y;
+#pragma unroll 1
+  for (int j = 0; j < 5; ++j) {
+    const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+    const double num = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k[7], r2), k[6]), r2), k[5]), r2));
+    const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k[4], r2), k[1]), r2), k[0]), r2));
+    const double icdist = __ddiv_rn(num, den);
+    if (icdist < 0.0) {                      // OpenCV: give up, keep the pinhole estimate
+      x = x0;
+      y = y0;
+      break;
+    }
+    const double dx = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, k[2]), x), y),
+                                __dmul_rn(k[3], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x))));
+    const double dy = __dadd_rn(__dmul_rn(k[2], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))),
+                                __dmul_rn(__dmul_rn(__dmul_rn(2.0, k[3]), x), y));
+    x = __dmul_rn(__dsub_rn(x0, dx), icdist);
+    y = __dmul_rn(__dsub_rn(y0, dy), icdist);
+  }
+  const double xx = __dadd_rn(__dadd_rn(__dmul_rn(P.P[0], x), __dmul_rn(P.P[1], y)), P.P[2]);
+  const double yy = __dadd_rn(__dadd_rn(__dmul_rn(P.P[3], x), __dmul_rn(P.P[4], y)), P.P[5]);
+  const double ww = __ddiv_rn(1.0, __dadd_rn(__dadd_rn(__dmul_rn(P.P[6], x), __dmul_rn(P.P[7], y)), P.P[8]));
+  ou = (float)__dmul_rn(xx, ww);
+  ov = (float)__dmul_rn(yy, ww);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+undistort_points_kernel(const T* __restrict__ pts, int stride, long long n,
+                        const __grid_constant__ pbk_ray_params P, float2* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // pts.astype(np.float32) first (:537)
+  const float u = (float)pts[i * stride], v = (float)pts[i * stride + 1];
+  float2 o;
+  undistort_one(P, (double)u, (double)v, o.x, o.y);
+  out[i] = o;
+}
+
+// One point per thread; the (256,3) float64 block leaves through shared memory as
+// contiguous 16 B stores (a lane-per-point store would be 24 B strided).
+template <typename T>
+__global__ void __launch_bounds__(256)
+camera_rays_kernel(const T* __restrict__ pts, int stride, long long n,
+                   const __grid_constant__ pbk_ray_params P, double* __restrict__ out) {
+  __shared__ __align__(16) double stage[256 * 3];
+  const long long base = (long long)blockIdx.x * 256;
+  const long long i = base + threadIdx.x;
+  if (i < n) {
+    double u, v;
+    if (P.undistort) {
+      float fu, fv;
+      undistort_one(P, (double)(float)pts[i * stride], (double)(float)pts[i * stride + 1], fu, fv);
+      u = (double)fu;
+      v = (double)fv;
+    } else {
+      u = (double)pts[i * stride];
+      v = (double)pts[i * stride + 1];
+    }
+    double r[3] = {__ddiv_rn(__dsub_rn(u, P.cx), P.fx), __ddiv_rn(__dsub_rn(v, P.cy), P.fy), 1.0};
+    if (P.rotate) {                                    // Quaternion.rotate, quaternion.py:69-85
+      double q[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        q[a] = __dadd_rn(__dmul_rn(2.0, __dadd_rn(__dadd_rn(__dmul_rn(P.rot[3 * a], r[0]), __dmul_rn(P.rot[3 * a + 1], r[1])),
+                                                  __dmul_rn(P.rot[3 * a + 2], r[2]))), r[a]);
+      r[0] = q[0]; r[1] = q[1]; r[2] = q[2];
+    }
+    if (P.normalize) {                                 // np.linalg.norm(axis=1): sqrt((a+b)+c)
+      const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(r[0], r[0]), __dmul_rn(r[1], r[1])), __dmul_rn(r[2], r[2])));
+      r[0] = __ddiv_rn(r[0], nrm); r[1] = __ddiv_rn(r[1], nrm); r[2] = __ddiv_rn(r[2], nrm);
+    }
+    if (P.scale_by_z) {
+      const double z = (double)pts[i * stride + 2];
+      r[0] = __dmul_rn(r[0], z); r[1] = __dmul_rn(r[1], z); r[2] = __dmul_rn(r[2], z);
+    }
+    stage[3 * threadIdx.x] = r[0];
+    stage[3 * threadIdx.x + 1] = r[1];
+    stage[3 * threadIdx.x + 2] = r[2];
+  }
+  __syncthreads();
+  const long long left = n - base;
+  const int cnt = (int)(left < 256 ? left : 256) * 3;      // doubles in this block; base*24 B is 16 B aligned
+  double* dst = out + base * 3;
+  for (int e = 2 * threadIdx.x; e + 1 < cnt; e += 512) st_stream_d2(dst + e, stage[e], stage[e + 1]);
+  if ((cnt & 1) && threadIdx.x == 0) st_stream_d1(dst + cnt - 1, stage[cnt - 1]);
+}
+
 // ------------------------------------------------------- viewer wire colours
 // get_color_arr (externals/draw_helpers.py:35-53) for uint8 images: optional
 // B<->R flip, then carr.astype(float32) / 255.0 - the float32 (N,3) block
@@ -282,6 +470,68 @@ int pbk_sampson_error(const double* F, const double* pts1, const double* pts2, i
   PBK_REQUIRE(blocks < (1ll << 31), PBK_EINVAL, "n too large");
   sampson_error_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(pts1, pts2, n, P, err);
   PBK_CHECK_LAUNCH("sampson_error_kernel");
+  return PBK_OK;
+}
+
+int pbk_triangulate_points(const double* P1, const double* P2, const void* x1, const void* x2, int dtype,
+                           int64_t n, void* out, pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(n >= 0 && P1 != nullptr && P2 != nullptr, PBK_EINVAL, "bad arguments");
+  PBK_REQUIRE(dtype == PBK_F32 || dtype == PBK_F64, PBK_EINVAL, "points must be float32 or float64");
+  if (n == 0) return PBK_OK;
+  PBK_REQUIRE(x1 && x2 && out, PBK_EINVAL, "NULL device pointer");
+  TriParams P;
+  for (int i = 0; i < 12; ++i) { P.P1[i] = P1[i]; P.P2[i] = P2[i]; }
+  const long long blocks = (n + 127) / 128;
+  PBK_REQUIRE(blocks < (1ll << 31), PBK_EINVAL, "n too large");
+  cudaStream_t s = as_stream(stream);
+  if (dtype == PBK_F32)
+    triangulate_kernel<float><<<(int)blocks, 128, 0, s>>>(static_cast<const float*>(x1), static_cast<const float*>(x2), n, P, static_cast<float*>(out));
+  else
+    triangulate_kernel<double><<<(int)blocks, 128, 0, s>>>(static_cast<const double*>(x1), static_cast<const double*>(x2), n, P, static_cast<double*>(out));
+  PBK_CHECK_LAUNCH("triangulate_kernel");
+  return PBK_OK;
+}
+
+static int check_ray_args(const void* pts, int dtype, int stride, int64_t n, const pbk_ray_params* params,
+                          const void* out, int min_stride) {
+  PBK_REQUIRE(n >= 0 && params != nullptr, PBK_EINVAL, "bad arguments");
+  PBK_REQUIRE(dtype == PBK_F32 || dtype == PBK_F64, PBK_EINVAL, "points must be float32 or float64");
+  PBK_REQUIRE(stride >= min_stride, PBK_EINVAL, "row stride too small for the requested columns");
+  PBK_REQUIRE(n == 0 || (pts && out), PBK_EINVAL, "NULL device pointer");
+  PBK_REQUIRE((n + 255) / 256 < (1ll << 31), PBK_EINVAL, "n too large");
+  return PBK_OK;
+}
+
+int pbk_undistort_points(const void* pts, int dtype, int stride, int64_t n, const pbk_ray_params* params,
+                         float* out, pbk_stream_t stream) {
+  using namespace pbk;
+  const int rc = check_ray_args(pts, dtype, stride, n, params, out, 2);
+  if (rc != PBK_OK || n == 0) return rc;
+  PBK_REQUIRE((reinterpret_cast<uintptr_t>(out) & 7) == 0, PBK_EALIGN, "out must be 8-byte aligned");
+  const int blocks = (int)((n + 255) / 256);
+  cudaStream_t s = as_stream(stream);
+  if (dtype == PBK_F32)
+    undistort_points_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(pts), stride, n, *params, reinterpret_cast<float2*>(out));
+  else
+    undistort_points_kernel<double><<<blocks, 256, 0, s>>>(static_cast<const double*>(pts), stride, n, *params, reinterpret_cast<float2*>(out));
+  PBK_CHECK_LAUNCH("undistort_points_kernel");
+  return PBK_OK;
+}
+
+int pbk_camera_rays(const void* pts, int dtype, int stride, int64_t n, const pbk_ray_params* params, double* out,
+                    pbk_stream_t stream) {
+  using namespace pbk;
+  const int rc = check_ray_args(pts, dtype, stride, n, params, out, (params && params->scale_by_z) ? 3 : 2);
+  if (rc != PBK_OK || n == 0) return rc;
+  PBK_REQUIRE(aligned16(out), PBK_EALIGN, "out must be 16-byte aligned");
+  const int blocks = (int)((n + 255) / 256);
+  cudaStream_t s = as_stream(stream);
+  if (dtype == PBK_F32)
+    camera_rays_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(pts), stride, n, *params, out);
+  else
+    camera_rays_kernel<double><<<blocks, 256, 0, s>>>(static_cast<const double*>(pts), stride, n, *params, out);
+  PBK_CHECK_LAUNCH("camera_rays_kernel");
   return PBK_OK;
 }
 

@@ -471,6 +471,91 @@ def sampson_error(F, pts1, pts2):
     return _finish(err, on_dev)
 
 
+def triangulate_points(P1, P2, pts1, pts2):
+    """camera_utils.py:108-116: (N,2) correspondences + two 3x4 projection matrices
+    -> (N,3) points, float32 or float64 like the inputs (cv2.triangulatePoints
+    keeps float32 only when both point sets are float32)."""
+    T = _ffi.require_cuda()
+
+    def _is32(x):
+        return (x.dtype == T.float32) if isinstance(x, T.Tensor) else (np.asarray(x).dtype == np.float32)
+    dt = np.float32 if (_is32(pts1) and _is32(pts2)) else np.float64
+    a, on_dev = _ffi.to_device(pts1, dt)
+    b, _ = _ffi.to_device(pts2, dt)
+    a, b = a.reshape(-1, 2).contiguous(), b.reshape(-1, 2).contiguous()
+    if tuple(a.shape) != tuple(b.shape):
+        raise AssertionError("pts1 and pts2 must have the same shape")
+    P1h, p1 = _ffi.host_f64(P1, 12)                  # host arrays stay alive through the call
+    P2h, p2 = _ffi.host_f64(P2, 12)
+    out = T.empty((a.shape[0], 3), dtype=a.dtype, device=a.device)
+    _ffi.check(_ffi.lib().pbk_triangulate_points(p1, p2, _ffi.ptr(a), _ffi.ptr(b), _ffi.pbk_dtype(dt), a.shape[0],
+                                                 _ffi.ptr(out), _ffi.stream_ptr()))
+    del P1h, P2h
+    return _finish(out, on_dev)
+
+
+def _ray_params(K, D, P=None, rot=None, undistort=True, normalize=False, scale_by_z=False):
+    prm = _ffi.RayParams()
+    K = np.asarray(K, np.float64)
+    prm.fx, prm.fy, prm.cx, prm.cy = float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+    k = np.zeros(8)
+    if D is not None:
+        Dv = np.asarray(D, np.float64).ravel()
+        if Dv.size > 8:
+            raise NotImplementedError("thin-prism / tilt distortion (>8 coefficients) is not supported")
+        if Dv.size not in (0, 4, 5, 8):
+            raise ValueError("distortion must have 4, 5 or 8 coefficients")
+        k[:Dv.size] = Dv
+    prm.k[:] = k.tolist()
+    prm.P[:] = np.asarray(K if P is None else P, np.float64)[:3, :3].reshape(9).tolist()
+    prm.rot[:] = (np.zeros(9) if rot is None else np.asarray(rot, np.float64).reshape(9)).tolist()
+    prm.undistort, prm.rotate = int(bool(undistort)), int(rot is not None)
+    prm.normalize, prm.scale_by_z = int(bool(normalize)), int(bool(scale_by_z))
+    return prm
+
+
+def _rows_in(pts, min_cols):
+    """(n, c>=min_cols) float32/float64 device rows; other dtypes go through float64."""
+    T = _ffi.require_cuda()
+    if isinstance(pts, T.Tensor):
+        x = pts if pts.dtype in (T.float32, T.float64) else pts.to(T.float64)
+    else:
+        x = np.asarray(pts)
+        if x.dtype not in (np.float32, np.float64):
+            x = x.astype(np.float64)
+    if x.ndim != 2 or x.shape[1] < min_cols:
+        raise ValueError("expected an (N, >=%d) array, got %s" % (min_cols, tuple(x.shape)))
+    return _ffi.to_device(x)
+
+
+def undistort_points(pts, K, D, P=None):
+    """cv2.undistortPoints(pts.astype(float32), K, D, P=K) (camera_utils.py:529-538)
+    -> (N,2) float32, bit-exact."""
+    T = _ffi.require_cuda()
+    if not isinstance(pts, T.Tensor):
+        pts = np.asarray(pts).reshape(-1, 2)
+    x, on_dev = _rows_in(pts, 2)
+    prm = _ray_params(K, D, P)
+    out = T.empty((x.shape[0], 2), dtype=T.float32, device=x.device)
+    dt = np.float32 if x.dtype == T.float32 else np.float64
+    _ffi.check(_ffi.lib().pbk_undistort_points(_ffi.ptr(x), _ffi.pbk_dtype(dt), x.shape[1], x.shape[0],
+                                               ctypes.byref(prm), _ffi.ptr(out), _ffi.stream_ptr()))
+    return _finish(out, on_dev)
+
+
+def camera_rays(pts, K, D, undistort=True, rot=None, normalize=False, scale_by_z=False):
+    """CameraIntrinsic.ray / reconstruct (camera_utils.py:499-524) -> (N,3) float64.
+    rot: the 3x3 coefficient rows of Quaternion.rotate or None."""
+    T = _ffi.require_cuda()
+    x, on_dev = _rows_in(pts, 3 if scale_by_z else 2)
+    prm = _ray_params(K, D, None, rot, undistort, normalize, scale_by_z)
+    out = T.empty((x.shape[0], 3), dtype=T.float64, device=x.device)
+    dt = np.float32 if x.dtype == T.float32 else np.float64
+    _ffi.check(_ffi.lib().pbk_camera_rays(_ffi.ptr(x), _ffi.pbk_dtype(dt), x.shape[1], x.shape[0],
+                                          ctypes.byref(prm), _ffi.ptr(out), _ffi.stream_ptr()))
+    return _finish(out, on_dev)
+
+
 def wire_colors(im, flip_rb=False):
     """uint8 (..., 3) colours -> float32 (N,3) in [0,1] (get_color_arr, draw_helpers.py:35-53)."""
     T = _ffi.require_cuda()

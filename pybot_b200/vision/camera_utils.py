@@ -66,6 +66,14 @@ def get_bounded_projection(camera, pts, subsample=10, return_depth=False):
                           return_valid=True)
 
 
+def triangulate_points(cam1, pts1, cam2, pts2):
+    """Triangulate 2-D correspondences from two views (reference :108-116); the
+    per-point DLT + 4x4 SVD of cv2.triangulatePoints runs on the GPU."""
+    assert isinstance(cam1, Camera) and isinstance(cam2, Camera)
+    assert isinstance(pts1, np.ndarray) and isinstance(pts2, np.ndarray)
+    return ops.triangulate_points(np.asarray(cam1.P), np.asarray(cam2.P), pts1, pts2)
+
+
 def unproject_points(pts):
     """Reference :37-39."""
     pts = np.asarray(pts)
@@ -162,6 +170,33 @@ class CameraIntrinsic(object):
         x = np.asarray(x)
         return np.where((x[:, 0] >= 0) & (x[:, 0] < self.shape[1])
                         & (x[:, 1] >= 0) & (x[:, 1] < self.shape[0]))[0]
+
+    # ------------------------------------------- rays (reference :499-538), on the GPU
+    def undistort_points(self, pts):
+        """cv2.undistortPoints(pts.astype(float32), K, D, P=K) -> (N,2) float32 (:529-538)."""
+        return ops.undistort_points(pts, self.K, self.D, P=self.K)
+
+    def _rotate_rows(self):
+        """Coefficient rows of Quaternion.rotate (quaternion.py:69-85) for the
+        extrinsics' quaternion, formed in the reference's own order."""
+        qx, qy, qz, qw = self.extrinsics.quat.q
+        ab, ac, ad = qw * qx, qw * qy, qw * qz
+        nbb, bc, bd = -qx * qx, qx * qy, qx * qz
+        ncc, cd, ndd = -qy * qy, qy * qz, -qz * qz
+        return np.float64([[ncc + ndd, bc - ad, ac + bd],
+                           [ad + bc, nbb + ndd, cd - ab],
+                           [bd - ac, ab + cd, nbb + ncc]])
+
+    def ray(self, pts, undistort=True, rotate=False, normalize=False):
+        """Rays [(u-cx)/fx, (v-cy)/fy, 1] through the (optionally undistorted)
+        pixels, optionally rotated into the camera's viewpoint and normalised
+        (:499-517); one kernel, (N,3) float64."""
+        return ops.camera_rays(pts, self.K, self.D, undistort=undistort,
+                               rot=self._rotate_rows() if rotate else None, normalize=normalize)
+
+    def reconstruct(self, xyZ, undistort=True):
+        """(N,3) [x, y, Z] -> ray(x, y) * Z (:519-524)."""
+        return ops.camera_rays(xyZ, self.K, self.D, undistort=undistort, scale_by_z=True)
 
 
 class CameraExtrinsic(RigidTransform):

@@ -169,3 +169,159 @@ def test_wire_colors_golden(g7):
     _same(ops.wire_colors(g7["wire_im"], True), g7["wire_flip"])
     im = np.random.default_rng(2).integers(0, 256, (333, 517, 3), dtype=np.uint8)      # n_px not a multiple of 4
     _same(ops.wire_colors(im, True), port.wire_colors(im, True))
+
+
+# ------------------------------------ undistort_points / ray / reconstruct / triangulate
+@pytest.fixture(scope="module")
+def g8(golden_dir):
+    return np.load(golden_dir + "/g8_rays_triangulate.npz")
+
+
+_DISTS = ("d0", "d5", "d4", "d8", "dneg")
+
+
+def _pose_xyzw(g8):
+    """Quaternion the reference ends up rotating with: pose -> Camera -> .extrinsics
+    (two matrix round trips; host algebra only, pinned by g0)."""
+    return _g8_cams(g8)[1].extrinsics.quat.q
+
+
+@pytest.mark.parametrize("use_cv2", [True, False])
+def test_port_rays_match_reference(g8, use_cv2):
+    K, pts = g8["K"], g8["pts"]
+    for name in _DISTS:
+        D = g8["D_" + name]
+        _same(port.undistort_points(K, D, pts, use_cv2), g8["und_" + name])
+        _same(port.camera_ray(K, D, pts, use_cv2=use_cv2), g8["ray_" + name])
+    D = g8["D_d5"]
+    q = _pose_xyzw(g8)
+    _same(port.camera_ray(K, D, pts, undistort=False), g8["ray_raw_f64"])
+    _same(port.camera_ray(K, D, pts.astype(np.float32), undistort=False), g8["ray_raw_f32"])
+    _same(port.camera_ray(K, D, pts, normalize=True, use_cv2=use_cv2), g8["ray_norm"])
+    _same(port.camera_ray(K, D, pts, rotate_xyzw=q, use_cv2=use_cv2), g8["ray_rot"])
+    _same(port.camera_ray(K, D, pts, undistort=False, rotate_xyzw=q, normalize=True), g8["ray_rot_norm"])
+    _same(port.intrinsic_reconstruct(K, D, g8["xyZ"], use_cv2=use_cv2), g8["rec"])
+    _same(port.intrinsic_reconstruct(K, D, g8["xyZ"], undistort=False), g8["rec_raw"])
+
+
+def test_model_undistort_is_bit_exact_vs_cv2():
+    cv2 = pytest.importorskip("cv2")
+    from oracle import model
+    from pybot_b200 import synthetic as syn
+    K = syn.kitti_K()
+    rng = np.random.default_rng(88)
+    pts = rng.uniform([-100, -100], [1400, 500], (200_000, 2))
+    for D in ([-0.3, 0.1, 0.001, -0.002, 0.01], [-0.37, 0.2, 0.0005, 0.0003],
+              [0.1, -0.05, 0.001, 0.002, 0.003, 0.01, 0.02, -0.003], [-0.9, 0.1, 0, 0, 0]):
+        D = np.float64(D)
+        ref = cv2.undistortPoints(pts.reshape(-1, 1, 2).astype(np.float32), K, D, P=K).reshape(-1, 2)
+        _same(model.undistort_points(pts, K, D, P=K), ref)
+
+
+@pytest.mark.parametrize("use_cv2", [True, False])
+def test_port_triangulate_matches_reference(g8, use_cv2):
+    P1, P2 = g8["tri_P1"], g8["tri_P2"]
+    for got, want, tol in (
+            (port.triangulate_points(P1, P2, g8["tri_p1"], g8["tri_p2"], use_cv2), g8["tri_exact"], 1e-6),
+            (port.triangulate_points(P1, P2, g8["tri_p1"], g8["tri_p2n"], use_cv2), g8["tri_noisy"], 1e-9)):
+        assert got.dtype == want.dtype and got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=tol, atol=tol)
+    np.testing.assert_allclose(g8["tri_exact"], g8["tri_X"], atol=1e-6)       # noise-free pairs recover the points
+    got = port.triangulate_points(P1, P2, g8["tri_p1"].astype(np.float32), g8["tri_p2n"].astype(np.float32), use_cv2)
+    assert got.dtype == np.float32
+    np.testing.assert_allclose(got, g8["tri_f32"], rtol=2e-5, atol=1e-5)
+
+
+def _g8_cams(g8):
+    from pybot_b200.geometry import RigidTransform
+    from pybot_b200.vision.camera_utils import Camera, CameraExtrinsic, CameraIntrinsic
+    ci = CameraIntrinsic(g8["K"], D=g8["D_d5"], shape=(376, 1241))
+    cam = Camera.from_intrinsics_extrinsics(
+        ci, CameraExtrinsic.from_rigid_transform(RigidTransform.from_rpyxyz(*g8["pose_rpyxyz"])))
+    return ci, cam
+
+
+@pytest.mark.gpu
+def test_undistort_and_rays_golden(g8):
+    """Bit-exact against the reference's cv2.undistortPoints + numpy ray arithmetic."""
+    from pybot_b200.vision.camera_utils import CameraIntrinsic
+    K, pts = g8["K"], g8["pts"]
+    for name in _DISTS:
+        ci = CameraIntrinsic(K, D=g8["D_" + name], shape=(376, 1241))
+        _same(ci.undistort_points(pts), g8["und_" + name])
+        _same(ci.ray(pts), g8["ray_" + name])
+    ci, cam = _g8_cams(g8)
+    _same(ci.ray(pts, undistort=False), g8["ray_raw_f64"])
+    _same(ci.ray(pts.astype(np.float32), undistort=False), g8["ray_raw_f32"])
+    _same(ci.ray(pts, normalize=True), g8["ray_norm"])
+    _same(cam.ray(pts, rotate=True), g8["ray_rot"])
+    _same(cam.ray(pts, undistort=False, rotate=True, normalize=True), g8["ray_rot_norm"])
+    _same(ci.reconstruct(g8["xyZ"]), g8["rec"])
+    _same(ci.reconstruct(g8["xyZ"], undistort=False), g8["rec_raw"])
+    with pytest.raises(AttributeError):
+        ci.ray(pts, rotate=True)                                   # no extrinsics on a bare intrinsic, like the reference
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [0, 1, 255, 256, 257, 100_003])
+def test_rays_ragged_sizes_vs_port(n, g8):
+    import torch
+    ci, cam = _g8_cams(g8)
+    rng = np.random.default_rng(n)
+    xyZ = np.hstack([rng.uniform([-50, -50], [1300, 430], (n, 2)), rng.uniform(0.5, 60, (n, 1))])
+    K, D = g8["K"], g8["D_d5"]
+    q = _pose_xyzw(g8)
+    if n == 0:                       # cv2.undistortPoints asserts on an empty array; here: empty out
+        assert ci.undistort_points(xyZ[:, :2]).shape == (0, 2)
+        assert cam.ray(xyZ[:, :2], rotate=True).shape == (0, 3) and ci.reconstruct(xyZ).shape == (0, 3)
+        return
+    _same(ci.undistort_points(xyZ[:, :2]), port.undistort_points(K, D, xyZ[:, :2]).reshape(-1, 2))
+    _same(cam.ray(xyZ[:, :2], rotate=True, normalize=True),
+          port.camera_ray(K, D, xyZ[:, :2], rotate_xyzw=q, normalize=True).reshape(-1, 3))
+    _same(ci.reconstruct(xyZ), port.intrinsic_reconstruct(K, D, xyZ).reshape(-1, 3))
+    dev = ci.reconstruct(torch.from_numpy(xyZ).cuda())               # device in -> device out
+    assert dev.is_cuda
+    _same(dev.cpu().numpy(), port.intrinsic_reconstruct(K, D, xyZ).reshape(-1, 3))
+
+
+@pytest.mark.gpu
+def test_triangulate_points_golden(g8):
+    """cv2.triangulatePoints is an SVD: parity is a tolerance (1e-9 relative in
+    float64 on noisy pairs, where the null vector is well separated; the exact
+    pairs are rank-deficient by construction, compared at 1e-6 like cv2 itself
+    against the true points)."""
+    from pybot_b200 import synthetic as syn
+    from pybot_b200.geometry import RigidTransform
+    from pybot_b200.vision.camera_utils import (Camera, CameraExtrinsic, CameraIntrinsic, triangulate_points)
+    mk = lambda rp: Camera.from_intrinsics_extrinsics(              # noqa: E731
+        CameraIntrinsic(syn.kitti_K(), shape=(376, 1241)),
+        CameraExtrinsic.from_rigid_transform(RigidTransform.from_rpyxyz(*rp)))
+    c1, c2 = mk(g8["tri_rp1"]), mk(g8["tri_rp2"])
+    np.testing.assert_allclose(c1.P, g8["tri_P1"], rtol=1e-12, atol=1e-12)
+    got = triangulate_points(c1, g8["tri_p1"], c2, g8["tri_p2n"])
+    assert got.dtype == np.float64 and got.shape == g8["tri_noisy"].shape
+    np.testing.assert_allclose(got, g8["tri_noisy"], rtol=1e-9, atol=1e-9)
+    got = triangulate_points(c1, g8["tri_p1"], c2, g8["tri_p2"])
+    np.testing.assert_allclose(got, g8["tri_exact"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(got, g8["tri_X"], atol=1e-6)
+    got = triangulate_points(c1, g8["tri_p1"].astype(np.float32), c2, g8["tri_p2n"].astype(np.float32))
+    assert got.dtype == np.float32
+    np.testing.assert_allclose(got, g8["tri_f32"], rtol=2e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [0, 1, 127, 128, 129, 200_001])
+def test_triangulate_ragged_sizes_vs_port(n, g8):
+    from pybot_b200 import ops
+    rng = np.random.default_rng(n + 5)
+    P1, P2 = g8["tri_P1"], g8["tri_P2"]
+    X = rng.uniform([-10, -2, 5], [10, 2, 40], (n, 3))
+    Xh = np.hstack([X, np.ones((n, 1))])
+    p1 = (Xh @ P1.T)
+    p2 = (Xh @ P2.T)
+    p1 = p1[:, :2] / p1[:, 2:] + rng.normal(0, 0.7, (n, 2))
+    p2 = p2[:, :2] / p2[:, 2:] + rng.normal(0, 0.7, (n, 2))
+    got = ops.triangulate_points(P1, P2, p1, p2)
+    assert got.shape == (n, 3) and got.dtype == np.float64
+    if n:
+        np.testing.assert_allclose(got, port.triangulate_points(P1, P2, p1, p2), rtol=1e-9, atol=1e-9)
