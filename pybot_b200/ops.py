@@ -9,7 +9,7 @@ import ctypes
 
 import numpy as np
 
-from . import _ffi
+from . import _ffi, _pipeline
 
 _NP = {"float32": np.float32, "float64": np.float64}
 
@@ -38,19 +38,47 @@ def _finish(tensor, on_device):
 
 
 # ---------------------------------------------------------------- transform
+def _host_points(X):
+    """Host (n,3) float32/float64 array for the pipelined path, or None when X is a tensor."""
+    T = _ffi.torch()
+    if isinstance(X, T.Tensor):
+        return None
+    X = np.asarray(X)
+    if X.dtype not in (np.float32, np.float64):
+        X = X.astype(np.float64)             # like np.hstack with float64 ones
+    if X.ndim != 2 or X.shape[1] != 3:
+        raise ValueError("expected an (N, 3) point array, got %s" % (tuple(X.shape),))
+    return _pipeline.as_host_tensor(X)
+
+
 def transform_points(X, R, t, scale=1.0, out_dtype=np.float64, out=None):
     """Y = scale * R @ X + t for (N,3) points.  Reference:
     RigidTransform.__mul__ (rigid_transform.py:139-141) returns float64.
-    `out`: optional preallocated (N,3) CUDA tensor of out_dtype."""
+    `out`: optional preallocated (N,3) CUDA tensor of out_dtype.  Host arrays
+    are streamed in row chunks (upload, kernel and download overlapped)."""
     T = _ffi.require_cuda()
-    Xd, on_dev = _points_in(X)
-    n = Xd.shape[0]
-    Y = out if out is not None else T.empty((n, 3), dtype=_tdtype(T, out_dtype), device=Xd.device)
     Rt = np.concatenate([np.asarray(R, np.float64).reshape(9), np.asarray(t, np.float64).reshape(3)])
     Rt, Rt_p = _ffi.host_f64(Rt, 12)
-    _ffi.check(_ffi.lib().pbk_transform_points(
-        _ffi.ptr(Xd), _ffi.pbk_dtype(_NP[str(Xd.dtype).split(".")[-1]]), n, Rt_p,
-        float(scale), _ffi.ptr(Y), _ffi.pbk_dtype(out_dtype), _ffi.stream_ptr()))
+    L = _ffi.lib()
+
+    def launch(Xd, Y):
+        _ffi.check(L.pbk_transform_points(
+            _ffi.ptr(Xd), _ffi.pbk_dtype(_NP[str(Xd.dtype).split(".")[-1]]), Xd.shape[0], Rt_p,
+            float(scale), _ffi.ptr(Y), _ffi.pbk_dtype(out_dtype), _ffi.stream_ptr()))
+
+    Xh = _host_points(X) if out is None else None
+    if Xh is not None:
+        n = Xh.shape[0]
+        chunks = _pipeline.plan(n, Xh.element_size() * 3 + np.dtype(out_dtype).itemsize * 3, 1024)
+        if len(chunks) > 1:
+            Xd = T.empty((n, 3), dtype=Xh.dtype, device="cuda")
+            Y = T.empty((n, 3), dtype=_tdtype(T, out_dtype), device="cuda")
+            res = _pipeline.stream_rows(chunks, [Xh], [Xd], lambda lo, hi: launch(Xd[lo:hi], Y[lo:hi]), [Y],
+                                        [_pipeline.host_out((n, 3), Y.dtype)])
+            return res[0]
+    Xd, on_dev = _points_in(X)
+    Y = out if out is not None else T.empty((Xd.shape[0], 3), dtype=_tdtype(T, out_dtype), device=Xd.device)
+    launch(Xd, Y)
     return _finish(Y, on_dev)
 
 
@@ -137,10 +165,34 @@ def project_points(X, R, t, K, D=None, Rz=None, tz=None, shape=None, check_bound
     Returns (uv, depth or None, valid or None, count).  With compact=True uv
     and depth hold only the valid points, in input order (camera_utils.py:727-732).
     """
-    Xd, on_dev = _points_in(X)
-    n = Xd.shape[0]
     pr = Projector(R, t, K, D, Rz, tz, shape, check_bounds, check_depth, return_depth, return_valid,
                    min_depth, compact)
+    Xh = _host_points(X) if not (pr.masked or return_valid) else None
+    if Xh is not None:
+        # no masks -> rows are independent: stream the host array through in chunks
+        n = Xh.shape[0]
+        chunks = _pipeline.plan(n, Xh.element_size() * 5 + (8 if return_depth else 0), 1024)
+        if len(chunks) > 1:
+            T = _ffi.torch()
+            Xd = T.empty((n, 3), dtype=Xh.dtype, device="cuda")
+            uv = T.empty((n, 2), dtype=Xh.dtype, device="cuda")
+            dev_out, host_res = [uv], [_pipeline.host_out((n, 2), uv.dtype)]
+            dp = None
+            if return_depth:
+                dp = T.empty((n,), dtype=T.float64, device="cuda")
+                dev_out.append(dp)
+                host_res.append(_pipeline.host_out((n,), T.float64))
+            in_dt = _ffi.PBK_F32 if Xd.dtype == T.float32 else _ffi.PBK_F64
+            L = _ffi.lib()
+
+            def launch(lo, hi):
+                _ffi.check(L.pbk_project_points(
+                    _ffi.ptr(Xd[lo:hi]), in_dt, hi - lo, ctypes.byref(pr.params), _ffi.ptr(uv[lo:hi]),
+                    _ffi.ptr(dp[lo:hi]) if dp is not None else None, None, None, None, _ffi.stream_ptr()))
+            res = _pipeline.stream_rows(chunks, [Xh], [Xd], launch, dev_out, host_res)
+            return res[0], (res[1] if return_depth else None), None, n
+    Xd, on_dev = _points_in(X)
+    n = Xd.shape[0]
     uv, depth, valid, count = pr.run(Xd)
     m = n
     if pr.masked:
@@ -175,17 +227,55 @@ def reproject_disparity(disp, Q, sample=1, bgr=None):
             "float64 disparity is not supported (cv2.reprojectImageTo3D rejects it as well)")
     if dt.type not in _DISP_DTYPES:
         raise TypeError("disparity dtype must be uint8, int16, int32 or float32; got %s" % dt)
+    s = int(sample)
+    if s < 1:
+        raise ValueError("sample must be >= 1")
+    Qh, Qp = _ffi.host_f32(Q, 16)
+    L = _ffi.lib()
+
+    def launch(d, c, xyz, c_out):
+        _ffi.check(L.pbk_reproject_disp(
+            _ffi.ptr(d), _ffi.pbk_dtype(dt), d.shape[0], int(d.shape[1]), int(d.shape[2]), Qp, s, _ffi.ptr(xyz),
+            _ffi.ptr(c), _ffi.ptr(c_out), _ffi.stream_ptr()))
+
+    if not is_t and np.ndim(disp) == 3 and (bgr is None or not isinstance(bgr, T.Tensor)):
+        # a batch of host frames: frames are independent -> stream them through in groups
+        dh = _pipeline.as_host_tensor(disp)
+        B, H, W = (int(v) for v in dh.shape)
+        Hs, Ws = -(-H // s), -(-W // s)
+        ch = None
+        if bgr is not None:
+            ch = _pipeline.as_host_tensor(bgr)
+            if ch.dtype != T.uint8 or tuple(ch.shape) != (B, H, W, 3):
+                raise ValueError("colour image must be uint8 (H, W, 3) matching the disparity")
+        per_frame = H * W * (dh.element_size() + (3 if ch is not None else 0)) + Hs * Ws * (12 + (3 if ch is not None else 0))
+        chunks = _pipeline.plan(B, per_frame)
+        if len(chunks) > 1:
+            d = T.empty((B, H, W), dtype=dh.dtype, device="cuda")
+            xyz = T.empty((B, Hs, Ws, 3), dtype=T.float32, device="cuda")
+            host_in, dev_in, dev_out = [dh], [d], [xyz]
+            host_res = [_pipeline.host_out(xyz.shape, T.float32)]
+            c = c_out = None
+            if ch is not None:
+                c = T.empty((B, H, W, 3), dtype=T.uint8, device="cuda")
+                c_out = T.empty((B, Hs, Ws, 3), dtype=T.uint8, device="cuda")
+                host_in.append(ch)
+                dev_in.append(c)
+                dev_out.append(c_out)
+                host_res.append(_pipeline.host_out(c_out.shape, T.uint8))
+            res = _pipeline.stream_rows(
+                chunks, host_in, dev_in,
+                lambda lo, hi: launch(d[lo:hi], c[lo:hi] if c is not None else None, xyz[lo:hi],
+                                      c_out[lo:hi] if c_out is not None else None),
+                dev_out, host_res)
+            return res[0] if ch is None else (res[0], res[1])
     d, on_dev = _ffi.to_device(disp)
     if d.ndim not in (2, 3):
         raise ValueError("disparity must be (H,W) or (B,H,W)")
     batched = d.ndim == 3
     B = d.shape[0] if batched else 1
     H, W = int(d.shape[-2]), int(d.shape[-1])
-    s = int(sample)
-    if s < 1:
-        raise ValueError("sample must be >= 1")
     Hs, Ws = -(-H // s), -(-W // s)
-    Qh, Qp = _ffi.host_f32(Q, 16)
     xyz = T.empty((B, Hs, Ws, 3), dtype=T.float32, device=d.device)
     c = c_out = None
     if bgr is not None:
@@ -193,9 +283,7 @@ def reproject_disparity(disp, Q, sample=1, bgr=None):
         if c.dtype != T.uint8 or tuple(c.shape[-3:]) != (H, W, 3):
             raise ValueError("colour image must be uint8 (H, W, 3) matching the disparity")
         c_out = T.empty((B, Hs, Ws, 3), dtype=T.uint8, device=d.device)
-    _ffi.check(_ffi.lib().pbk_reproject_disp(
-        _ffi.ptr(d), _ffi.pbk_dtype(dt), B, H, W, Qp, s, _ffi.ptr(xyz), _ffi.ptr(c), _ffi.ptr(c_out),
-        _ffi.stream_ptr()))
+    launch(d.reshape(B, H, W), c, xyz, c_out)
     if not batched:
         xyz = xyz[0]
         c_out = c_out[0] if c_out is not None else None
@@ -399,22 +487,43 @@ def depth_reconstruct(depth, xs, ys, skip=1):
     if dt.type not in (np.uint16, np.float32, np.float64):
         depth = depth.to(T.float64) if is_t else np.asarray(depth, np.float64)
         dt = np.dtype(np.float64)
+    s = int(skip)
+    L = _ffi.lib()
+
+    def meshes(H, W):
+        Hs, Ws = -(-H // s), -(-W // s)
+        # meshes may be passed as float64 CUDA tensors (DepthCamera caches them per device)
+        xs_d = xs if isinstance(xs, T.Tensor) else _ffi.to_device(np.ascontiguousarray(xs, np.float64))[0]
+        ys_d = ys if isinstance(ys, T.Tensor) else _ffi.to_device(np.ascontiguousarray(ys, np.float64))[0]
+        if xs_d.numel() != Ws or ys_d.numel() != Hs:
+            raise AssertionError("depth shape %s does not match the camera mesh (%d, %d)" % ((H, W), Hs, Ws))
+        return Hs, Ws, xs_d, ys_d
+
+    def launch(d, out, xs_d, ys_d):
+        _ffi.check(L.pbk_depth_reconstruct(_ffi.ptr(d), _ffi.pbk_dtype(dt), d.shape[0], int(d.shape[1]),
+                                           int(d.shape[2]), s, _ffi.ptr(xs_d), _ffi.ptr(ys_d), _ffi.ptr(out),
+                                           _ffi.stream_ptr()))
+
+    if not is_t and np.ndim(depth) == 3:
+        # a batch of host frames: stream frame groups (upload / kernel / download overlapped)
+        dh = _pipeline.as_host_tensor(depth)
+        B, H, W = (int(v) for v in dh.shape)
+        Hs, Ws, xs_d, ys_d = meshes(H, W)
+        chunks = _pipeline.plan(B, H * W * dh.element_size() + Hs * Ws * 24)
+        if len(chunks) > 1:
+            d = T.empty((B, H, W), dtype=dh.dtype, device="cuda")
+            out = T.empty((B, Hs, Ws, 3), dtype=T.float64, device="cuda")
+            return _pipeline.stream_rows(chunks, [dh], [d], lambda lo, hi: launch(d[lo:hi], out[lo:hi], xs_d, ys_d),
+                                         [out], [_pipeline.host_out(out.shape, T.float64)])[0]
     d, on_dev = _ffi.to_device(depth)
     if d.ndim not in (2, 3):
         raise ValueError("depth must be (H,W) or (B,H,W)")
     batched = d.ndim == 3
     B = d.shape[0] if batched else 1
     H, W = int(d.shape[-2]), int(d.shape[-1])
-    s = int(skip)
-    Hs, Ws = -(-H // s), -(-W // s)
-    # meshes may be passed as float64 CUDA tensors (DepthCamera caches them per device)
-    xs_d = xs if isinstance(xs, T.Tensor) else _ffi.to_device(np.ascontiguousarray(xs, np.float64))[0]
-    ys_d = ys if isinstance(ys, T.Tensor) else _ffi.to_device(np.ascontiguousarray(ys, np.float64))[0]
-    if xs_d.numel() != Ws or ys_d.numel() != Hs:
-        raise AssertionError("depth shape %s does not match the camera mesh (%d, %d)" % ((H, W), Hs, Ws))
+    Hs, Ws, xs_d, ys_d = meshes(H, W)
     out = T.empty((B, Hs, Ws, 3), dtype=T.float64, device=d.device)
-    _ffi.check(_ffi.lib().pbk_depth_reconstruct(_ffi.ptr(d), _ffi.pbk_dtype(dt), B, H, W, s, _ffi.ptr(xs_d),
-                                                _ffi.ptr(ys_d), _ffi.ptr(out), _ffi.stream_ptr()))
+    launch(d.reshape(B, H, W), out, xs_d, ys_d)
     if not batched:
         out = out[0]
     return _finish(out, on_dev)
