@@ -119,7 +119,11 @@ __device__ __forceinline__ void ba_load_point(const BaParams& P, uint32_t raw, f
   int pt = (int)raw;            // out-of-range indices are clamped (the wrapper validates them)
   pt = pt < 0 ? 0 : ((long long)pt >= P.n_points ? (int)(P.n_points - 1) : pt);
   const float* pp = P.points + 3ll * pt;
-  p[0] = __ldg(pp); p[1] = __ldg(pp + 1); p[2] = __ldg(pp + 2);
+  // volatile: these loads must not be hoisted above the conversion of the previous
+  // tile's points (see process()), or both tiles' loads share a scoreboard
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(p[0]) : "l"(pp));
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(p[1]) : "l"(pp + 1));
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(p[2]) : "l"(pp + 2));
 }
 
 // Residual + Jacobian blocks of N observations that share the camera block C
@@ -129,21 +133,20 @@ __device__ __forceinline__ void ba_load_point(const BaParams& P, uint32_t raw, f
 // observation falls with N.  Results go straight to the warp's stage:
 //   J_cam row [lane-slot*12, +12), J_pt row [slot*6, +6), r [slot*2, +2).
 template <int N, int TILE>
-__device__ __forceinline__ void ba_eval(const double* C, const BaParams& P, const float (&pt)[N][3],
+__device__ __forceinline__ void ba_eval(const double* C, const BaParams& P, const double (&X)[N][3],
                                         const uint4 (&ob)[N], const int (&slot)[N], const bool (&act)[N],
                                         const bool (&live)[N], char* st, double& cost) {
   const double2* C2 = reinterpret_cast<const double2*>(C);
   float4* sJc = reinterpret_cast<float4*>(st);
   float2* sJp = reinterpret_cast<float2*>(st + TILE * 48);
   float2* sR = reinterpret_cast<float2*>(st + TILE * 72);
-  double X[N][3], a[N], b[N], cc[N], d[N];
+  double a[N], b[N], cc[N], d[N];
   {
     const double2 c0 = C2[0], c1 = C2[1], c2 = C2[2], c3 = C2[3], c4 = C2[4], c5 = C2[5];
     const double R0 = c0.x, R1 = c0.y, R2 = c1.x, R3 = c1.y, R4 = c2.x, R5 = c2.y, R6 = c3.x, R7 = c3.y,
                  R8 = c4.x, t0 = c4.y, t1 = c5.x, t2 = c5.y;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      X[j][0] = (double)pt[j][0]; X[j][1] = (double)pt[j][1]; X[j][2] = (double)pt[j][2];
       const double uo = (double)__uint_as_float(ob[j].z), vo = (double)__uint_as_float(ob[j].w);
       const double xc = fma(R0, X[j][0], fma(R1, X[j][1], fma(R2, X[j][2], t0)));
       const double yc = fma(R3, X[j][0], fma(R4, X[j][1], fma(R5, X[j][2], t1)));
@@ -284,13 +287,25 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
     }
   };
 
-  // one tile: `pt` holds its points, `ptn` receives the next tile's
-  auto process = [&](int k, const float (&pt)[kBaOpl][3], float (&ptn)[kBaOpl][3]) {
+  // one tile: `pt` holds its points on entry and the next tile's on exit.  The
+  // points are converted to fp64 FIRST and only then are the next tile's gathers
+  // issued into the same registers: issued the other way round, the conversions
+  // wait on a scoreboard shared with the brand-new loads (11 % of the stall samples).
+  float pt[kBaOpl][3];
+  auto process = [&](int k) {
     const long long o0 = (t_begin + k) * kBaTile;
     if (lane == 0 && k + kBaRingStages - 1 < my_tiles) issue(k + kBaRingStages - 1);
+    double Xd[kBaOpl][3];
+#pragma unroll
+    for (int j = 0; j < kBaOpl; ++j)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        Xd[j][i] = (double)pt[j][i];
+        asm volatile("" : "+d"(Xd[j][i]));
+      }
     if (k + 1 < my_tiles) {
       ring.wait(k + 1);
-      gather(k + 1, ptn);
+      gather(k + 1, pt);
     }
     uint4 ob[kBaOpl];
     int cam[kBaOpl], slot[kBaOpl];
@@ -320,7 +335,7 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
       bool act[kBaOpl];
 #pragma unroll
       for (int j = 0; j < kBaOpl; ++j) act[j] = true;
-      ba_eval<kBaOpl, kBaTile>(C, P, pt, ob, slot, act, live, st, cost);
+      ba_eval<kBaOpl, kBaTile>(C, P, Xd, ob, slot, act, live, st, cost);
     } else {
       // a tile that straddles cameras takes one pass per distinct camera of each 32-record row
 #pragma unroll
@@ -329,7 +344,7 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
         while (todo) {
           const int c = __shfl_sync(0xffffffffu, cam[j], __ffs(todo) - 1);
           load_cam(c);
-          const float p1[1][3] = {{pt[j][0], pt[j][1], pt[j][2]}};
+          const double p1[1][3] = {{Xd[j][0], Xd[j][1], Xd[j][2]}};
           const uint4 o1[1] = {ob[j]};
           const int s1[1] = {slot[j]};
           const bool a1[1] = {(cam[j] == c) && ((todo >> lane) & 1u)};
@@ -363,15 +378,11 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
     }
   };
 
-  float ptA[kBaOpl][3], ptB[kBaOpl][3];
   if (my_tiles > 0) {
     ring.wait(0);
-    gather(0, ptA);
+    gather(0, pt);
   }
-  for (int k = 0; k < my_tiles; k += 2) {       // ping-pong: no register rotation between tiles
-    process(k, ptA, ptB);
-    if (k + 1 < my_tiles) process(k + 1, ptB, ptA);
-  }
+  for (int k = 0; k < my_tiles; ++k) process(k);
   if (lane == 0) tma_store_wait_all();
 
   // cost: warp -> CTA -> partial

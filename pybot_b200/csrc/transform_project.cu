@@ -219,14 +219,13 @@ project_points_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
     __syncwarp();                       // slot may be refilled from here on
 
     T uo[4], vo[4];
-    double dep[4];
+    double dep[4], ud[4], vd[4];
     bool ok[4];
+    project_many<DIST, 4>(P, Xp, ud, vd);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      double u, v;
-      project_one<DIST>(P, Xp[j], u, v);
-      uo[j] = (T)u;
-      vo[j] = (T)v;
+      uo[j] = (T)ud[j];
+      vo[j] = (T)vd[j];
       if (MODE != 0) {
         bool good = (j * 32 + lane) < npts;
         if (need_depth) {
