@@ -780,6 +780,62 @@ def run_next_rows(D, args):
         "cpu_baseline": {"value": Hk * Wk / cpu_dt / 1e6, "unit": "Mpts/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": "oracle.port.sceneflow_process (cv2.projectPoints + numpy passes, "
                                    "optflow_utils.py:129-150) on one %dx%d frame" % (Wk, Hk)}}
+    del dX, Z
+
+    # CameraIntrinsic.reconstruct (undistort + ray * Z) on one 4K frame of pixels
+    ci = CameraIntrinsic(K, D=np.float64([-0.3, 0.1, 0.001, -0.002, 0.01]), shape=(H, W))
+    xyZ = torch.rand((H * W, 3), device="cuda", generator=g, dtype=torch.float32)
+    xyZ[:, 0] *= W
+    xyZ[:, 1] *= H
+    xyZ[:, 2] = xyZ[:, 2] * 56 + 4
+
+    def rstep(rec):
+        return ci.reconstruct(xyZ)
+    ms3, _ = timed_steps(D, rstep, args.steps, args.warmup, flush)
+    sample = xyZ[:1_000_000].cpu().numpy()
+    t0 = time.perf_counter()
+    port.intrinsic_reconstruct(K, ci.D, sample)
+    cpu_dt = time.perf_counter() - t0
+    out["intrinsic_reconstruct"] = {
+        "workload": "CameraIntrinsic.reconstruct (cv2.undistortPoints + ray * Z) of %d float32 [x, y, Z] rows" % (H * W),
+        "Mpts_per_s": H * W * args.steps / (ms3 * 1e-3) / 1e6, "ms": ms3 / args.steps,
+        "algorithmic": "12 B in + 24 B out per point", "GBps": H * W * 36.0 * args.steps / (ms3 * 1e-3) / 1e9,
+        "l2": L2_NOTE,
+        "cpu_baseline": {"value": len(sample) / cpu_dt / 1e6, "unit": "Mpts/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": "oracle.port.intrinsic_reconstruct (cv2.undistortPoints + numpy, "
+                                   "camera_utils.py:499-538) on 1M rows"}}
+    del xyZ
+
+    # triangulate_points: 4M correspondences between two posed KITTI cameras
+    from pybot_b200 import ops
+    from pybot_b200.geometry import RigidTransform
+    from pybot_b200.vision.camera_utils import Camera, CameraExtrinsic
+    Kk = syn.kitti_K()
+    mk = lambda *rp: Camera.from_intrinsics_extrinsics(                     # noqa: E731
+        CameraIntrinsic(Kk, shape=syn.KITTI_SHAPE), CameraExtrinsic.from_rigid_transform(RigidTransform.from_rpyxyz(*rp)))
+    c1, c2 = mk(0.01, -0.02, 0.03, 0.1, 0.0, 0.2), mk(-0.02, 0.05, 0.0, -0.4, 0.05, 0.9)
+    nt = 4_000_000
+    Xw = torch.rand((nt, 3), device="cuda", generator=g, dtype=torch.float64)
+    Xw[:, 0] = Xw[:, 0] * 20 - 10
+    Xw[:, 1] = Xw[:, 1] * 4 - 2
+    Xw[:, 2] = Xw[:, 2] * 35 + 5
+    p1 = c1.project(Xw) + torch.randn((nt, 2), device="cuda", generator=g, dtype=torch.float64) * 0.5
+    p2 = c2.project(Xw) + torch.randn((nt, 2), device="cuda", generator=g, dtype=torch.float64) * 0.5
+    P1, P2 = np.asarray(c1.P), np.asarray(c2.P)
+
+    def tstep(rec):
+        return ops.triangulate_points(P1, P2, p1, p2)
+    ms4, _ = timed_steps(D, tstep, args.steps, args.warmup, flush)
+    a, b = p1[:200_000].cpu().numpy(), p2[:200_000].cpu().numpy()
+    t0 = time.perf_counter()
+    port.triangulate_points(P1, P2, a, b)
+    cpu_dt = time.perf_counter() - t0
+    out["triangulate_points"] = {
+        "workload": "%d float64 correspondences, two 3x4 cameras (per-point 4x4 Jacobi SVD)" % nt,
+        "Mpts_per_s": nt * args.steps / (ms4 * 1e-3) / 1e6, "ms": ms4 / args.steps,
+        "algorithmic": "32 B in + 24 B out per point; compute-bound (fp64 Jacobi sweeps)", "l2": L2_NOTE,
+        "cpu_baseline": {"value": len(a) / cpu_dt / 1e6, "unit": "Mpts/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": "cv2.triangulatePoints + dehomogenisation (camera_utils.py:108-116) on 200k pairs"}}
     return out
 
 

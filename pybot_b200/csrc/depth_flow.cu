@@ -174,35 +174,99 @@ __device__ __forceinline__ int cast_i32_like_numpy(T v) {
   return (int)d;                       // cvt.rzi
 }
 
+// Four consecutive points per thread: 48 B (float32) arrive as three 16 B loads
+// (the per-point version issued twelve 4 B loads at a 12 B stride and fetched every
+// sector three times through L1), then project_many interleaves the four fp64 chains.
+template <typename T> struct Pts4;
+template <> struct Pts4<float> {
+  static __device__ __forceinline__ void load(const float* p, double (&X)[4][3]) {
+    const float4 a = ld_stream_f4(p), b = ld_stream_f4(p + 4), c = ld_stream_f4(p + 8);
+    const float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int k = 0; k < 12; ++k) X[k / 3][k % 3] = (double)v[k];
+  }
+};
+template <> struct Pts4<double> {
+  static __device__ __forceinline__ void load(const double* p, double (&X)[4][3]) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const uint4 a = ld_stream_u4(p + 2 * k);
+      X[(2 * k) / 3][(2 * k) % 3] = __hiloint2double((int)a.y, (int)a.x);
+      X[(2 * k + 1) / 3][(2 * k + 1) % 3] = __hiloint2double((int)a.w, (int)a.z);
+    }
+  }
+};
+
 template <typename T, bool DIST>
 __global__ void __launch_bounds__(256)
 sceneflow_scatter_kernel(const T* __restrict__ dX, int n, int W, int H,
                          const __grid_constant__ pbk_project_params P, int* __restrict__ winner) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double X[3] = {(double)dX[3ll * i], (double)dX[3ll * i + 1], (double)dX[3ll * i + 2]};
-  double u, v;
-  project_one<DIST>(P, X, u, v);
-  const int xi = cast_i32_like_numpy<T>((T)u), yi = cast_i32_like_numpy<T>((T)v);
-  // new_grid[ys[valid], xs[valid]] = grid[gys[valid], gxs[valid]]: on repeated
-  // targets numpy keeps the LAST source in index order -> max source index
-  if (xi >= 0 && xi < W && yi >= 0 && yi < H) atomicMax(winner + yi * W + xi, i);
+  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i0 >= n) return;
+  double X[4][3], u[4], v[4];
+  const int cnt = n - i0 < 4 ? n - i0 : 4;
+  if (cnt == 4) {
+    Pts4<T>::load(dX + 3ll * i0, X);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) X[j][k] = j < cnt ? (double)dX[3ll * (i0 + j) + k] : 1.0;
+  }
+  project_many<DIST, 4>(P, X, u, v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int xi = cast_i32_like_numpy<T>((T)u[j]), yi = cast_i32_like_numpy<T>((T)v[j]);
+    // new_grid[ys[valid], xs[valid]] = grid[gys[valid], gxs[valid]]: on repeated
+    // targets numpy keeps the LAST source in index order -> max source index
+    if (j < cnt && xi >= 0 && xi < W && yi >= 0 && yi < H) atomicMax(winner + yi * W + xi, i0 + j);
+  }
 }
 
+// n / W for 0 <= n < 2^31 by multiply-high (Granlund-Montgomery round-up variant):
+// q = (umulhi(m, n) + n) >> s with s = ceil(log2 W), m = floor(2^32 (2^s - W) / W) + 1.
+struct FastDiv {
+  uint32_t m;
+  int s;
+};
+__device__ __forceinline__ int fast_div(int n, FastDiv d) {
+  return (int)((__umulhi(d.m, (uint32_t)n) + (uint32_t)n) >> d.s);
+}
+
+// four consecutive cells per thread: one 16 B load of winners, two 16 B stores of flow
 __global__ void __launch_bounds__(256)
-sceneflow_resolve_kernel(const int* __restrict__ winner, int n, int W, float2* __restrict__ flow) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
-  const int w = winner[c];
-  float2 o;
-  if (w < 0) {
-    o.x = o.y = __int_as_float(0x7fc00000);          // untouched cells stay NaN
+sceneflow_resolve_kernel(const int* __restrict__ winner, int n, int W, FastDiv dW, float* __restrict__ flow) {
+  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c0 >= n) return;
+  int w[4];
+  const int cnt = n - c0 < 4 ? n - c0 : 4;
+  if (cnt == 4) {
+    const uint4 v = ld_stream_u4(winner + c0);
+    w[0] = (int)v.x; w[1] = (int)v.y; w[2] = (int)v.z; w[3] = (int)v.w;
   } else {
-    // (source grid coordinate) - (this cell's grid coordinate), float32 like the reference
-    o.x = (float)(w % W) - (float)(c % W);
-    o.y = (float)(w / W) - (float)(c / W);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = j < cnt ? winner[c0 + j] : -1;
   }
-  flow[c] = o;
+  int cy = fast_div(c0, dW), cx = c0 - cy * W;
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (w[j] < 0) {
+      o[2 * j] = o[2 * j + 1] = __int_as_float(0x7fc00000);          // untouched cells stay NaN
+    } else {
+      // (source grid coordinate) - (this cell's grid coordinate), float32 like the reference
+      const int wy = fast_div(w[j], dW), wx = w[j] - wy * W;
+      o[2 * j] = (float)wx - (float)cx;
+      o[2 * j + 1] = (float)wy - (float)cy;
+    }
+    if (++cx == W) { cx = 0; ++cy; }
+  }
+  if (cnt == 4) {
+    st_stream_f4(flow + 2ll * c0, make_float4(o[0], o[1], o[2], o[3]));
+    st_stream_f4(flow + 2ll * c0 + 4, make_float4(o[4], o[5], o[6], o[7]));
+  } else {
+    for (int j = 0; j < cnt; ++j) { flow[2ll * (c0 + j)] = o[2 * j]; flow[2ll * (c0 + j) + 1] = o[2 * j + 1]; }
+  }
 }
 
 struct SampsonParams {
@@ -591,8 +655,9 @@ int pbk_sceneflow(const void* dX, int dtype, int H, int W, const pbk_project_par
   PBK_REQUIRE(dX && winner && flow, PBK_EINVAL, "NULL device pointer");
   PBK_REQUIRE(aligned16(flow), PBK_EALIGN, "device pointers must be 16-byte aligned");
   cudaStream_t s = as_stream(stream);
+  PBK_REQUIRE(aligned16(dX) && aligned16(winner), PBK_EALIGN, "device pointers must be 16-byte aligned");
   PBK_CUDA(cudaMemsetAsync(winner, 0xff, (size_t)n * 4, s));          // -1 = no source
-  const int blocks = (int)((n + 255) / 256);
+  const int blocks = (int)(((n + 3) / 4 + 255) / 256);
   const bool dist = params->has_distortion != 0;
   if (dtype == PBK_F32) {
     if (dist) sceneflow_scatter_kernel<float, true><<<blocks, 256, 0, s>>>(static_cast<const float*>(dX), (int)n, W, H, *params, winner);
@@ -602,7 +667,11 @@ int pbk_sceneflow(const void* dX, int dtype, int H, int W, const pbk_project_par
     else sceneflow_scatter_kernel<double, false><<<blocks, 256, 0, s>>>(static_cast<const double*>(dX), (int)n, W, H, *params, winner);
   }
   PBK_CHECK_LAUNCH("sceneflow_scatter_kernel");
-  sceneflow_resolve_kernel<<<blocks, 256, 0, s>>>(winner, (int)n, W, reinterpret_cast<float2*>(flow));
+  FastDiv dW;
+  dW.s = 0;
+  while ((1ll << dW.s) < W) ++dW.s;
+  dW.m = (uint32_t)((((1ull << dW.s) - (unsigned long long)W) << 32) / (unsigned long long)W + 1ull);
+  sceneflow_resolve_kernel<<<blocks, 256, 0, s>>>(winner, (int)n, W, dW, flow);
   PBK_CHECK_LAUNCH("sceneflow_resolve_kernel");
   return PBK_OK;
 }
