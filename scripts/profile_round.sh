@@ -10,7 +10,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 BENCH="python bench.py --steps 3 --warmup 3"
 $BENCH > $OUT/${TAG}_bench_plain.json 2> $OUT/${TAG}_bench_plain.err &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv \
     --log-file $OUT/${TAG}_launches.csv $BENCH > $OUT/${TAG}_bench_under_ncu.log 2>&1
 echo "launch list rc=$?"
 PROF="python scripts/prof_kernels.py all 1"
