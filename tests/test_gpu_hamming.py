@@ -167,3 +167,43 @@ def test_prepared_matcher_cuda_graph_equals_eager():
             assert torch.equal(a, b)
     with pytest.raises(ValueError):
         pm.run(q[:10], t)
+
+
+def test_all_rows_tied_and_extreme_distances():
+    """Every train row identical (every pair tied), across stage tiles, train splits
+    and a ragged last tile: the two LOWEST rows win for every query, at distance 0,
+    d and 256 (the complement) - the packed-key range end to end."""
+    from pybot_b200.vision.matcher import knn_ratio_mutual
+    rng = np.random.default_rng(11)
+    nt = 300_001
+    row = rng.integers(0, 256, 32, dtype=np.uint8)
+    t = np.tile(row, (nt, 1))
+    q = rng.integers(0, 256, (700, 32), dtype=np.uint8)
+    q[0] = row                                   # distance 0
+    q[1] = ~row                                  # distance 256
+    idx, dist, r_ok, m_ok, valid = knn_ratio_mutual(q, t, 0.75)
+    d = np.unpackbits(q ^ row, axis=1).sum(1)
+    assert np.array_equal(idx, np.tile(np.int64([0, 1]), (700, 1)))
+    assert np.array_equal(dist, np.stack([d, d], 1)) and dist[0, 0] == 0 and dist[1, 0] == 256
+    assert not r_ok[1:].any()                    # d1 == d2 never passes the ratio test (0 < 0.75*0 is false too)
+
+
+def test_duplicates_on_tile_and_split_boundaries():
+    """Exact copies of a query planted on both sides of every 256-row stage boundary
+    in a window, and at the very end: the top-2 are the two lowest planted rows."""
+    from oracle import c_oracle
+    from pybot_b200.vision.matcher import knn_ratio_mutual
+    rng = np.random.default_rng(12)
+    nt = 1_000_003
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    q = rng.integers(0, 256, (513, 32), dtype=np.uint8)     # one more than a query tile
+    planted = {}
+    for i, base in enumerate(range(256 * 7, nt - 600, 61_184)):        # 61184 = 239 * 256
+        rows = [base - 1, base, base + 255, base + 256, nt - 1 - i]
+        t[rows] = q[i]
+        planted[i] = sorted(rows)
+    idx, dist, _, _, _ = knn_ratio_mutual(q, t, 0.75)
+    for i, rows in planted.items():
+        assert list(idx[i]) == rows[:2] and list(dist[i]) == [0, 0], (i, idx[i], rows)
+    ridx, rdist = c_oracle.hamming_knn2(q[:64], t)
+    assert np.array_equal(idx[:64], ridx) and np.array_equal(dist[:64], rdist)
