@@ -23,6 +23,7 @@ from . import _ffi
 MIN_BYTES = 8 << 20          # below this a single chunk (latency, not bandwidth, dominates)
 CHUNK_BYTES = 12 << 20       # per-chunk bytes moved over PCIe (in + out)
 MAX_CHUNKS = 32
+COMPACT_CHUNK_BYTES = 48 << 20   # masked project: the host waits for a count per chunk, so fewer, larger chunks
 
 STAGE_THREADS = max(1, min(8, (os.cpu_count() or 2) // 2))
 
@@ -52,14 +53,14 @@ def _side_streams(device):
     return _streams[key]
 
 
-def plan(n_rows, bytes_per_row, row_align=1):
+def plan(n_rows, bytes_per_row, row_align=1, chunk_bytes=None):
     """Chunk boundaries [(lo, hi), ...] for n_rows rows; one chunk when small."""
     total = n_rows * bytes_per_row
     if n_rows <= 0:
         return []
     if total < MIN_BYTES:
         return [(0, n_rows)]
-    k = int(min(MAX_CHUNKS, max(2, total // CHUNK_BYTES)))
+    k = int(min(MAX_CHUNKS, max(2, total // (chunk_bytes or CHUNK_BYTES))))
     rows = -(-n_rows // k)
     rows = -(-rows // row_align) * row_align
     return [(lo, min(lo + rows, n_rows)) for lo in range(0, n_rows, rows)]

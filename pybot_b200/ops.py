@@ -191,6 +191,11 @@ def project_points(X, R, t, K, D=None, Rz=None, tz=None, shape=None, check_bound
                     _ffi.ptr(dp[lo:hi]) if dp is not None else None, None, None, None, _ffi.stream_ptr()))
             res = _pipeline.stream_rows(chunks, [Xh], [Xd], launch, dev_out, host_res)
             return res[0], (res[1] if return_depth else None), None, n
+    Xh = _host_points(X) if (pr.masked and pr.compact) else None
+    if Xh is not None:
+        res = _project_compact_streamed(pr, Xh, return_depth, return_valid)
+        if res is not None:
+            return res
     Xd, on_dev = _points_in(X)
     n = Xd.shape[0]
     uv, depth, valid, count = pr.run(Xd)
@@ -209,6 +214,69 @@ def project_points(X, R, t, K, D=None, Rz=None, tz=None, shape=None, check_bound
     if not on_dev and outs[2] is not None:
         outs[2] = outs[2].view(np.bool_)
     return outs[0], outs[1], outs[2], m
+
+
+def _project_compact_streamed(pr, Xh, return_depth, return_valid):
+    """Camera.project with masks from a HOST array: x[valid] is a global prefix, so
+    every row chunk is compacted on its own (one launch, its own count) and the
+    chunk's valid rows are downloaded to the running offset of the host result as
+    soon as its 8-byte count has arrived.  All uploads and launches are enqueued
+    first; the host then only waits for counts, so the copies of chunk i-1 (down)
+    and chunk i+1 (up) overlap chunk i's kernel.  Returns None for small inputs."""
+    T = _ffi.torch()
+    n = Xh.shape[0]
+    es = Xh.element_size()
+    chunks = _pipeline.plan(n, es * 5 + (8 if return_depth else 0) + 1, 1024, _pipeline.COMPACT_CHUNK_BYTES)
+    if len(chunks) < 2:
+        return None
+    L = _ffi.lib()
+    cur = T.cuda.current_stream()
+    s_in, s_out = _pipeline._side_streams(T.device("cuda", T.cuda.current_device()))
+    s_in.wait_stream(cur)
+    s_out.wait_stream(cur)
+    Xd = T.empty((n, 3), dtype=Xh.dtype, device="cuda")
+    uv = T.empty((n, 2), dtype=Xh.dtype, device="cuda")
+    dp = T.empty((n,), dtype=T.float64, device="cuda") if return_depth else None
+    vd = T.empty((n,), dtype=T.uint8, device="cuda") if return_valid else None
+    counts = T.zeros((len(chunks),), dtype=T.int64, device="cuda")
+    counts_h = _pipeline.host_out((len(chunks),), T.int64)
+    rows = max(hi - lo for lo, hi in chunks)
+    scratch = T.empty((max(L.pbk_project_scratch_bytes(rows), 16),), dtype=T.uint8, device="cuda")
+    uv_h = _pipeline.host_out((n, 2), uv.dtype)
+    dp_h = _pipeline.host_out((n,), T.float64) if return_depth else None
+    vd_h = _pipeline.host_out((n,), T.uint8) if return_valid else None
+    Xs = Xh if Xh.is_pinned() else _pipeline.host_out(Xh.shape, Xh.dtype)
+    in_dt = _ffi.PBK_F32 if Xd.dtype == T.float32 else _ffi.PBK_F64
+    done = []
+    for c, (lo, hi) in enumerate(chunks):
+        if Xs is not Xh:
+            _pipeline._stage_rows(Xs, Xh, lo, hi)
+        with T.cuda.stream(s_in):
+            Xd[lo:hi].copy_(Xs[lo:hi], non_blocking=True)
+            ev_in = s_in.record_event()
+        cur.wait_event(ev_in)
+        _ffi.check(L.pbk_project_points(
+            _ffi.ptr(Xd[lo:hi]), in_dt, hi - lo, ctypes.byref(pr.params), _ffi.ptr(uv[lo:hi]),
+            _ffi.ptr(dp[lo:hi]) if dp is not None else None, _ffi.ptr(vd[lo:hi]) if vd is not None else None,
+            _ffi.ptr(counts[c:c + 1]), _ffi.ptr(scratch), _ffi.stream_ptr()))
+        counts_h[c:c + 1].copy_(counts[c:c + 1], non_blocking=True)
+        done.append(cur.record_event())
+    m = 0
+    for c, (lo, hi) in enumerate(chunks):
+        done[c].synchronize()
+        mc = int(counts_h[c])
+        s_out.wait_event(done[c])
+        with T.cuda.stream(s_out):
+            if mc:
+                uv_h[m:m + mc].copy_(uv[lo:lo + mc], non_blocking=True)
+                if dp is not None:
+                    dp_h[m:m + mc].copy_(dp[lo:lo + mc], non_blocking=True)
+            if vd is not None:
+                vd_h[lo:hi].copy_(vd[lo:hi], non_blocking=True)
+        m += mc
+    s_out.synchronize()
+    return (uv_h.numpy()[:m], dp_h.numpy()[:m] if dp_h is not None else None,
+            vd_h.numpy().view(np.bool_) if vd_h is not None else None, m)
 
 
 # ---------------------------------------------------------------- reproject

@@ -45,11 +45,13 @@ def main():
     pose = RigidTransform.from_rpyxyz(*syn.C2_RPYXYZ)
     cam = Camera.from_intrinsics_extrinsics(CameraIntrinsic(syn.kitti_K(), shape=syn.KITTI_SHAPE),
                                             CameraExtrinsic.from_rigid_transform(pose))
-    for cb in (4, 8, 12, 24, 48):
-        _pipeline.CHUNK_BYTES = cb << 20
-        both("C2 project 10M pinned, chunk %d MB" % cb, lambda: cam.project(X), n * 20)
-    _pipeline.CHUNK_BYTES = 12 << 20
+    both("C2 project 10M pinned", lambda: cam.project(X), n * 20)
     both("C2 transform 10M pinned (f64 out)", lambda: pose * X, n * 36)
+    for cb in (12, 24, 32, 48, 64):
+        _pipeline.COMPACT_CHUNK_BYTES = cb << 20
+        both("C2 project x[valid]+depth+valid, %d MB chunks" % cb,
+             lambda: cam.project(X, check_bounds=True, check_depth=True, return_depth=True, return_valid=True), n * 25)
+    _pipeline.COMPACT_CHUNK_BYTES = 48 << 20
     Xu = np.array(X)                                     # pageable
     both("C2 project 10M pageable", lambda: cam.project(Xu), n * 20)
     H, W = syn.UHD_SHAPE

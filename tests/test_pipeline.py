@@ -45,9 +45,14 @@ def test_transform_and_project_host_stream_equals_device_path(pinned, dtype):
     uv2, depth = cam.project(X, return_depth=True)
     uvd, depthd = cam.project(Xd, return_depth=True)
     assert np.array_equal(uv2, uvd.cpu().numpy()) and np.array_equal(depth, depthd.cpu().numpy())
-    # masked / compacted calls keep the single-launch path and still agree
+    # masked calls: every chunk is compacted on its own and lands at the running offset
     a = cam.project(X, check_bounds=True, check_depth=True)
     assert np.array_equal(a, cam.project(Xd, check_bounds=True, check_depth=True).cpu().numpy())
+    x, dep, valid = cam.project(X, check_bounds=True, check_depth=True, return_depth=True, return_valid=True)
+    xd, depd, validd = cam.project(Xd, check_bounds=True, check_depth=True, return_depth=True, return_valid=True)
+    assert valid.dtype == np.bool_ and np.array_equal(valid, validd.cpu().numpy())
+    assert np.array_equal(x, xd.cpu().numpy()) and np.array_equal(dep, depd.cpu().numpy())
+    assert len(x) == int(valid.sum()) and 0.7 < valid.mean() < 0.78
 
 
 @pytest.mark.gpu
