@@ -310,17 +310,24 @@ __device__ unsigned long long g_ct_clk[16];
 // scratch layout: [0] unused, [1 .. ntiles] tile status words (zeroed per call).
 constexpr int kCtWarps = 8;                          // compute warps
 constexpr int kCtThreads = kCtWarps * 32;            // 256 compute threads
-constexpr int kCtBlock = kCtThreads + 64;            // + 2 scan warps
+constexpr int kCtScan = 2;                           // scan warps (one look-back each in flight); must be <= buffers
+constexpr int kCtBlock = kCtThreads + 32 * kCtScan;
 constexpr int kCtPpt = 4;                            // points per thread
 constexpr int kCtTile = kCtThreads * kCtPpt;         // 1024 points per tile
 constexpr int kCtSegs = kCtPpt * kCtWarps;           // 32 (row, warp) segments
-constexpr int kCtBufs = 3;                           // parked-output buffers (pipeline depth 2)
+// parked-output buffers (pipeline depth = buffers - 1 tiles of slack between a
+// tile's projection and its scatter).  Measured for float32: 5 buffers + 4 scan
+// warps at 2 CTAs/SM (4 tiles of slack) 0.105 ms against 0.102 ms for 3 buffers + 2
+// scan warps at 3 CTAs/SM - the extra slack is paid for with a third of the
+// compute warps, so the shallower pipeline with more CTAs stays.
+template <typename T> struct CtBufs { static constexpr int value = 3; };
+static_assert(kCtScan <= CtBufs<float>::value, "a scan warp may only wait one mbarrier phase ahead");
 
 template <typename T>
 struct CompactSmem {
   static constexpr int kIn = kCtTile * 3 * (int)sizeof(T);             // one input stage
   static constexpr int kOut = kCtTile * (2 * (int)sizeof(T) + 8);      // parked uv + depth of one tile
-  static constexpr int kBytes = 2 * kIn + kCtBufs * kOut;
+  static constexpr int kBytes = 2 * kIn + CtBufs<T>::value * kOut;
 };
 
 template <typename T, bool DIST>
@@ -331,10 +338,14 @@ project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
                        const __grid_constant__ pbk_project_params P) {
   using SM = CompactSmem<T>;
   using UV = typename OutPix<T>::vec;
+  constexpr int kCtBufs = CtBufs<T>::value;
   extern __shared__ __align__(128) char dyn_smem[];
-  __shared__ __align__(8) uint64_t in_full[2], cnt_ready[2], base_ready[kCtBufs];
+  // barriers and aggregate slots are per parked buffer: tile i + kCtBufs cannot be
+  // projected before tile i has been scattered, so a slot is never shared by two
+  // live tiles however far the compute warps drift apart
+  __shared__ __align__(8) uint64_t in_full[2], cnt_ready[kCtBufs], base_ready[kCtBufs];
   __shared__ long long s_base[kCtBufs];
-  __shared__ int s_cnt[kCtBufs][kCtSegs], s_excl[kCtBufs][kCtSegs], s_aggsum[2], s_arrived[2], s_consumed[2];
+  __shared__ int s_cnt[kCtBufs][kCtSegs], s_excl[kCtBufs][kCtSegs], s_aggsum[kCtBufs], s_arrived[kCtBufs], s_consumed[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long ntiles = (n + kCtTile - 1) / kCtTile;
   unsigned long long* status = scratch + 1;
@@ -345,12 +356,14 @@ project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&in_full[s], 1);
-      mbar_init(&cnt_ready[s], kCtWarps);
-      s_aggsum[s] = 0;
-      s_arrived[s] = 0;
       s_consumed[s] = 0;
     }
-    for (int q = 0; q < kCtBufs; ++q) mbar_init(&base_ready[q], 1);
+    for (int q = 0; q < kCtBufs; ++q) {
+      mbar_init(&cnt_ready[q], kCtWarps);
+      mbar_init(&base_ready[q], 1);
+      s_aggsum[q] = 0;
+      s_arrived[q] = 0;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -380,13 +393,13 @@ project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
 
   if (warp >= kCtWarps) {
     // ============================================================== scan warps
-    const int w = warp - kCtWarps;                   // stage / tile parity owned by this warp
-    for (int i = w; i < my_tiles; i += 2) {
-      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+    const int w = warp - kCtWarps;                   // this warp resolves tiles w, w + kCtScan, ...
+    for (int i = w; i < my_tiles; i += kCtScan) {
       const int q = i % kCtBufs;
+      const uint32_t ph = (uint32_t)((i / kCtBufs) & 1);
       // tile i's segment counts -> exclusive offsets, aggregate
       CT_T0();
-      mbar_wait(&cnt_ready[w], ph);
+      mbar_wait(&cnt_ready[q], ph);
       CT_ACC(2);
       const int c = s_cnt[q][lane];
       int inc = c;
@@ -444,8 +457,9 @@ project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
   const bool need_depth = (depth != nullptr) || P.check_depth;
   const T Wf = (T)P.width, Hf = (T)P.height;      // image bounds in the pixel dtype (exact: < 2^24)
   const unsigned lt = (1u << lane) - 1u;
-  unsigned m1[kCtPpt], m2[kCtPpt];          // ballots of tiles i-1 and i-2
-  for (int i = 0; i < my_tiles + 2; ++i) {
+  constexpr int kLag = kCtBufs - 1;         // a tile is scattered kLag iterations after its projection
+  unsigned mh[kLag][kCtPpt];                // ballots of tiles i-1 .. i-kLag
+  for (int i = 0; i < my_tiles + kLag; ++i) {
     unsigned m[kCtPpt];
     CT_T0();
     if (i < my_tiles) {
@@ -495,21 +509,21 @@ project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
         int wsum = 0;
 #pragma unroll
         for (int k = 0; k < kCtPpt; ++k) wsum += __popc(m[k]);
-        atomicAdd(&s_aggsum[s], wsum);
+        atomicAdd(&s_aggsum[q], wsum);
         __threadfence_block();
-        if (atomicAdd(&s_arrived[s], 1) == kCtWarps - 1) {
+        if (atomicAdd(&s_arrived[q], 1) == kCtWarps - 1) {
           __threadfence_block();
-          const int total = atomicExch(&s_aggsum[s], 0);
-          s_arrived[s] = 0;
+          const int total = atomicExch(&s_aggsum[q], 0);
+          s_arrived[q] = 0;
           st_status(status + tile, (tile == 0 ? kStatePrefix : kStateAgg) | (unsigned long long)total);
         }
-        mbar_arrive(&cnt_ready[s]);
+        mbar_arrive(&cnt_ready[q]);
       }
       if (warp == 0) CT_ACC(5);
     }
-    if (i >= 2) {
-      // scatter tile i-2 (parked by this same thread two iterations ago)
-      const int j = i - 2, q = j % kCtBufs;
+    if (i >= kLag) {
+      // scatter tile i-kLag (parked by this same thread kLag iterations ago)
+      const int j = i - kLag, q = j % kCtBufs;
       mbar_wait(&base_ready[q], (uint32_t)((j / kCtBufs) & 1));
       if (warp == 0) CT_ACC(6);
       const long long base = s_base[q];
@@ -518,9 +532,9 @@ project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
           reinterpret_cast<const double*>(dyn_smem + 2 * SM::kIn + q * SM::kOut + kCtTile * 2 * sizeof(T));
 #pragma unroll
       for (int k = 0; k < kCtPpt; ++k) {
-        if ((m2[k] >> lane) & 1u) {
+        if ((mh[kLag - 1][k] >> lane) & 1u) {
           const int p = k * kCtThreads + tid;
-          const long long o = base + s_excl[q][k * kCtWarps + warp] + __popc(m2[k] & lt);
+          const long long o = base + s_excl[q][k * kCtWarps + warp] + __popc(mh[kLag - 1][k] & lt);
           OutPix<T>::store_vec(uv, o, suv[p]);
           if (depth != nullptr) st_stream_d1(depth + o, sdep[p]);
         }
@@ -529,8 +543,9 @@ project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
     }
 #pragma unroll
     for (int k = 0; k < kCtPpt; ++k) {
-      m2[k] = m1[k];
-      m1[k] = m[k];
+#pragma unroll
+      for (int a = kLag - 1; a > 0; --a) mh[a][k] = mh[a - 1][k];
+      mh[0][k] = m[k];
     }
   }
 }
