@@ -167,6 +167,28 @@ __device__ __forceinline__ unsigned long long ld_status(const unsigned long long
 __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// sum of the published 64-bit status words st[0 .. n) (values only): the eight loads
+// of a lane are issued before the first one is examined
+__device__ __forceinline__ long long sum_aggregates(const unsigned long long* st, long long n, int lane) {
+  long long acc = 0;
+  for (long long c0 = 0; c0 < n; c0 += 256) {
+    unsigned long long sw[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long idx = c0 + lane + 32 * j;
+      sw[j] = idx < n ? ld_status(st + idx) : kStateAgg;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long idx = c0 + lane + 32 * j;
+      while ((sw[j] >> 62) == 0) sw[j] = ld_status(st + idx);
+      acc += (long long)(sw[j] & kValueMask);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
 
 // MODE 0: plain projection (no depth, masks, count).
 // MODE 1: depth / masks / valid flags per runtime switches, outputs uncompacted.
@@ -280,38 +302,40 @@ __device__ unsigned long long g_ct_clk[16];
 
 // ------------------------------------------------- projection + x[valid]
 // Order-preserving compaction fused into the projection pass (no second read
-// of X, no library scan): a chained scan over 1024-point tiles with a
-// decoupled look-back, software-pipelined two tiles deep so that the compute
-// path never waits for another CTA.
+// of X, no library scan): a two-level scan over 1024-point tiles, software-
+// pipelined two tiles deep.
 //
 // Persistent, co-resident CTAs (cooperative launch) of 8 compute warps + 2 scan
-// warps.  CTA b owns tiles b, b+G, b+2G ...: all CTAs work on one generation of
-// G consecutive tiles at a time, so a tile's predecessors publish their
-// aggregates when it does.
+// warps + 1 chain warp.  CTA b owns tiles b, b+G, b+2G ...: all CTAs work on one
+// generation of G consecutive tiles at a time.
 //   compute warps read tile i from a 2-stage TMA input ring (the last warp to
 //                 consume a stage refills it), project it (thread t owns points
-//                 t + 256 k), park uv /
-//                 depth in one of three shared-memory buffers, publish the tile
-//                 aggregate (the last warp to finish does it, so it never
-//                 queues behind a look-back), then scatter tile i-2 whose base
-//                 offset has been resolved meanwhile;
+//                 t + 256 k), park uv / depth in one of three shared-memory
+//                 buffers, publish the tile aggregate (the last warp to finish
+//                 does it), then scatter tile i-2 whose base offset has been
+//                 resolved meanwhile;
 //   scan warp w   (tiles of parity w) scans the 32 (row, warp) valid counts of a
-//                 finished tile and resolves its exclusive prefix by look-back over
-//                 predecessor tiles (256 status words per probe: [63:62] state,
-//                 [61:0] count).  A look-back costs a few L2 round trips plus
-//                 the jitter of the slowest CTA of the generation (~7k clocks
-//                 measured) against ~3.5k clocks of fp64 math per tile: two
-//                 scan warps and two tiles of slack keep it off the critical
-//                 path.  Versions that waited for the prefix inside the tile,
-//                 took tickets ahead of time, or published the aggregate from
-//                 the scan warp ran 1.5-6x slower.
+//                 finished tile; its exclusive offset is the prefix of its
+//                 GENERATION plus the aggregates of the tiles of the same
+//                 generation before it (<= G status words, all loads in flight
+//                 together with the generation prefix): no tile waits for another
+//                 tile's look-back;
+//   chain warp    (CTA 0 only) is the one serial dependency: it sums the G
+//                 aggregates of generation g as they appear and publishes the
+//                 prefix of generation g+1 - one L2 round trip per generation.
+// History: a per-tile decoupled look-back (every tile resolving against its
+// predecessors' prefixes) made the prefix frontier advance one generation per ~3
+// dependent L2 round trips, 0.100 ms; this form 0.095 ms.  Versions that waited for
+// the prefix inside the tile, took tickets ahead of time, or published the aggregate
+// from the scan warp ran 1.5-6x slower.
 // Valid points are written at base + rank; lanes of a warp hold consecutive
 // ranks, so the stores are contiguous runs.
-// scratch layout: [0] unused, [1 .. ntiles] tile status words (zeroed per call).
+// scratch layout (zeroed per call): [0] unused, [1 .. ntiles] tile aggregate words, then
+// one prefix word per generation.
 constexpr int kCtWarps = 8;                          // compute warps
 constexpr int kCtThreads = kCtWarps * 32;            // 256 compute threads
 constexpr int kCtScan = 2;                           // scan warps (one look-back each in flight); must be <= buffers
-constexpr int kCtBlock = kCtThreads + 32 * kCtScan;
+constexpr int kCtBlock = kCtThreads + 32 * kCtScan + 32;     // + the chain warp (works in CTA 0 only)
 constexpr int kCtPpt = 4;                            // points per thread
 constexpr int kCtTile = kCtThreads * kCtPpt;         // 1024 points per tile
 constexpr int kCtSegs = kCtPpt * kCtWarps;           // 32 (row, warp) segments
@@ -348,7 +372,8 @@ project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
   __shared__ int s_cnt[kCtBufs][kCtSegs], s_excl[kCtBufs][kCtSegs], s_aggsum[kCtBufs], s_arrived[kCtBufs], s_consumed[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long ntiles = (n + kCtTile - 1) / kCtTile;
-  unsigned long long* status = scratch + 1;
+  unsigned long long* status = scratch + 1;                // one aggregate word per tile
+  unsigned long long* gen_prefix = scratch + 1 + ntiles;   // one prefix word per generation of gridDim.x tiles
   // generation i of this CTA is tile i * gridDim.x + blockIdx.x
   const int my_tiles = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
   auto tile_of = [&](int i) -> long long { return (long long)i * gridDim.x + blockIdx.x; };
@@ -391,6 +416,23 @@ project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
     feed(1);
   }
 
+  if (warp == kCtWarps + kCtScan) {
+    // ============================================================== chain warp
+    // CTA 0 only: publishes the exclusive prefix of every generation of gridDim.x
+    // tiles.  A generation's total needs only its tiles' aggregates (published by
+    // the compute warps, no look-back involved), so this loop is the one serial
+    // dependency of the kernel and it advances one L2 round trip per generation.
+    if (blockIdx.x != 0) return;
+    long long running = 0;
+    for (long long g0 = 0, g = 0; g0 < ntiles; g0 += gridDim.x, ++g) {
+      if (lane == 0) st_status(gen_prefix + g, kStatePrefix | (unsigned long long)running);
+      const long long g1 = (g0 + gridDim.x) < ntiles ? (g0 + gridDim.x) : ntiles;
+      const long long acc = sum_aggregates(status + g0, g1 - g0, lane);
+      running += acc;
+    }
+    if (lane == 0 && count != nullptr) *count = running;
+    return;
+  }
   if (warp >= kCtWarps) {
     // ============================================================== scan warps
     const int w = warp - kCtWarps;                   // this warp resolves tiles w, w + kCtScan, ...
@@ -411,42 +453,19 @@ project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
       s_excl[q][lane] = inc - c;
       const long long agg = __shfl_sync(0xffffffffu, inc, 31);
       const long long tile = tile_of(i);              // its aggregate was published by the compute warps
-      long long excl = 0;
-      if (tile > 0) {
-        long long look = tile - 1;
-        bool done = false;
-        while (!done) {
-          unsigned long long sw[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const long long idx = look - (lane + 32 * j);         // position 0 = nearest predecessor
-            sw[j] = idx >= 0 ? ld_status(status + idx) : kStatePrefix;   // virtual prefix 0 before tile 0
-          }
-          long long acc = 0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (!done) {                                          // warp-uniform
-              const long long idx = look - (lane + 32 * j);
-              while ((sw[j] >> 62) == 0) sw[j] = ld_status(status + idx);
-              const unsigned is_prefix = __ballot_sync(0xffffffffu, (sw[j] >> 62) == 2);
-              long long val = (long long)(sw[j] & kValueMask);
-              if (is_prefix && lane > __ffs(is_prefix) - 1) val = 0;   // stop at the nearest prefix
-              acc += val;
-              done = is_prefix != 0;
-            }
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-          excl += acc;
-          look -= 256;
-        }
-        if (lane == 0) st_status(status + tile, kStatePrefix | (unsigned long long)(excl + agg));
-      }
+      // exclusive offset = prefix of generation i (from the chain warp) + the
+      // aggregates of the tiles of the SAME generation before this one.  No tile
+      // waits on another tile's look-back: the only serial chain is the chain warp's
+      // running sum of generation totals.
+      const long long g0 = (long long)i * gridDim.x;  // first tile of generation i
+      unsigned long long gp = ld_status(gen_prefix + i);          // in flight together with the aggregates
+      const long long acc = sum_aggregates(status + g0, tile - g0, lane);
+      while ((gp >> 62) == 0) gp = ld_status(gen_prefix + i);
+      const long long excl = (long long)(gp & kValueMask) + acc;
       CT_ACC(3);
       __syncwarp();                         // every lane's s_excl store precedes the arrive
       if (lane == 0) {
         s_base[q] = excl;
-        if (tile == ntiles - 1 && count != nullptr) *count = excl + agg;
         mbar_arrive(&base_ready[q]);
       }
     }
@@ -515,7 +534,7 @@ project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
           __threadfence_block();
           const int total = atomicExch(&s_aggsum[q], 0);
           s_arrived[q] = 0;
-          st_status(status + tile, (tile == 0 ? kStatePrefix : kStateAgg) | (unsigned long long)total);
+          st_status(status + tile, kStateAgg | (unsigned long long)total);
         }
         mbar_arrive(&cnt_ready[q]);
       }
@@ -652,7 +671,7 @@ PBK_API int pbk_debug_compact_clocks(unsigned long long out[16], int reset) {
 size_t pbk_project_scratch_bytes(int64_t n) {
   if (n < 0) n = 0;
   const long long ntiles = (n + pbk::kCtaPts - 1) / pbk::kCtaPts;
-  return (size_t)(ntiles + 2) * 8;
+  return (size_t)(2 * ntiles + 4) * 8;          // tile status words + one prefix word per generation
 }
 
 int pbk_project_points(const void* X, int in_dtype, int64_t n, const pbk_project_params* params,
