@@ -190,6 +190,18 @@ __device__ __forceinline__ long long sum_aggregates(const unsigned long long* st
   return acc;
 }
 
+// Valid flags of four 32-point rows (ballots m[0..3], row r = points base + 32 r ..)
+// as 128 bytes of 0/1: lane l writes the four flags (l % 8) * 4 .. + 3 of row l / 8 as
+// one 32-bit word - one coalesced 128 B store per warp instead of four rows of
+// single-byte stores.  `row_stride` = distance between the rows in points.
+__device__ __forceinline__ void store_valid_rows(uint8_t* dst, const unsigned (&m)[4], int row_stride, int lane) {
+  const int r = lane >> 3;
+  const unsigned mr = r == 0 ? m[0] : (r == 1 ? m[1] : (r == 2 ? m[2] : m[3]));
+  const unsigned nib = (mr >> ((lane & 7) * 4)) & 0xFu;
+  const unsigned word = (nib * 0x00204081u) & 0x01010101u;      // bit i -> byte i
+  *reinterpret_cast<unsigned*>(dst + (size_t)r * row_stride + (lane & 7) * 4) = word;
+}
+
 // MODE 0: plain projection (no depth, masks, count).
 // MODE 1: depth / masks / valid flags per runtime switches, outputs uncompacted.
 // (the compacting variant is project_compact_kernel below)
@@ -211,6 +223,7 @@ project_points_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
   const char* Xb = reinterpret_cast<const char*>(X);
   const bool need_depth = MODE != 0 && ((depth != nullptr) || P.check_depth);
   const T Wf = (T)P.width, Hf = (T)P.height;      // image bounds in the pixel dtype (exact: < 2^24)
+  const bool valid_words = (reinterpret_cast<uintptr_t>(valid_out) & 3) == 0;
 
   const long long stride = (long long)gridDim.x * kWarps;
   const long long t0 = (long long)blockIdx.x * kWarps + warp;
@@ -269,13 +282,21 @@ project_points_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
     }
     if (MODE == 0) continue;
 
+    unsigned mv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int p = j * 32 + lane;
-      local_count += __popc(__ballot_sync(0xffffffffu, ok[j]));
-      if (p < npts) {
-        if (valid_out != nullptr) valid_out[first + p] = ok[j] ? 1 : 0;
-        if (depth != nullptr) st_stream_d1(depth + first + p, dep[j]);
+      mv[j] = __ballot_sync(0xffffffffu, ok[j]);
+      local_count += __popc(mv[j]);
+      if (p < npts && depth != nullptr) st_stream_d1(depth + first + p, dep[j]);
+    }
+    if (valid_out != nullptr) {
+      if (npts == kTilePts && valid_words) {
+        store_valid_rows(valid_out + first, mv, 32, lane);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j * 32 + lane < npts) valid_out[first + j * 32 + lane] = ok[j] ? 1 : 0;
       }
     }
   }
@@ -502,6 +523,7 @@ project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
       }
       UV* suv = reinterpret_cast<UV*>(dyn_smem + 2 * SM::kIn + q * SM::kOut);
       double* sdep = reinterpret_cast<double*>(dyn_smem + 2 * SM::kIn + q * SM::kOut + kCtTile * 2 * sizeof(T));
+      const bool valid_words_tile = npts == kCtTile && (reinterpret_cast<uintptr_t>(valid_out) & 3) == 0;
 #pragma unroll
       for (int k = 0; k < kCtPpt; ++k) {
         const int p = k * kCtThreads + tid;
@@ -519,8 +541,9 @@ project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
         suv[p] = OutPix<T>::make(uo, vo);
         m[k] = __ballot_sync(0xffffffffu, good);
         if (lane == 0) s_cnt[q][k * kCtWarps + warp] = __popc(m[k]);
-        if (valid_out != nullptr && p < npts) valid_out[first + p] = good ? 1 : 0;
+        if (valid_out != nullptr && !valid_words_tile && p < npts) valid_out[first + p] = good ? 1 : 0;
       }
+      if (valid_out != nullptr && valid_words_tile) store_valid_rows(valid_out + first + warp * 32, m, kCtThreads, lane);
       __syncwarp();
       if (lane == 0) {
         // The tile aggregate leaves the moment the last compute warp is done - never
