@@ -31,22 +31,44 @@ class DMatch(object):
 class KeyframeDatabase(object):
     """A collection of per-keyframe descriptor matrices resident in HBM as one
     contiguous (N,32) uint8 tensor + row offsets (global row = offset[imgIdx]
-    + trainIdx, the ordering BFMatcher.add([...]) uses)."""
+    + trainIdx, the ordering BFMatcher.add([...]) uses).
+
+    Loop closure adds one keyframe (2000 rows, 64 KB) and then matches against
+    everything so far, thousands of times: rows are appended in place into a
+    buffer that grows geometrically, so an add costs its own bytes and `flat` is a
+    view - never a concatenation of the whole database."""
+
+    MIN_CAPACITY = 1 << 16          # rows (2 MB)
 
     def __init__(self):
-        self._chunks = []
         self._host = []
-        self._flat = None
+        self._buf = None            # (capacity, 32) uint8 on the device
+        self._n = 0
         self.offsets = np.zeros(1, np.int64)
 
-    def add(self, descriptors):
+    def reserve(self, rows):
+        """Make room for `rows` descriptors in total (e.g. the expected session length)."""
         T = _ffi.require_cuda()
+        cap = 0 if self._buf is None else self._buf.shape[0]
+        if rows <= cap:
+            return
+        new_cap = max(int(rows), self.MIN_CAPACITY, cap + cap // 2)
+        buf = T.empty((new_cap, 32), dtype=T.uint8, device="cuda")
+        if self._n:
+            buf[:self._n].copy_(self._buf[:self._n])
+        self._buf = buf
+
+    def add(self, descriptors):
+        _ffi.require_cuda()
         for d in descriptors:
             dd = ops._desc_in(d)
-            self._chunks.append(dd)
+            k = int(dd.shape[0])
+            if k:
+                self.reserve(self._n + k)
+                self._buf[self._n:self._n + k].copy_(dd)
+                self._n += k
             self._host.append(d)
-            self.offsets = np.append(self.offsets, self.offsets[-1] + dd.shape[0])
-        self._flat = None
+            self.offsets = np.append(self.offsets, self.offsets[-1] + k)
 
     def clear(self):
         self.__init__()
@@ -60,15 +82,9 @@ class KeyframeDatabase(object):
     @property
     def flat(self):
         T = _ffi.require_cuda()
-        if self._flat is None:
-            if len(self._chunks) == 1:
-                self._flat = self._chunks[0]
-            elif self._chunks:
-                self._flat = T.cat(self._chunks, 0)
-                self._chunks = [self._flat]          # keep one copy in HBM
-            else:
-                self._flat = T.empty((0, 32), dtype=T.uint8, device="cuda")
-        return self._flat
+        if self._buf is None:
+            return T.empty((0, 32), dtype=T.uint8, device="cuda")
+        return self._buf[:self._n]
 
     def split_global(self, g):
         """global rows -> (imgIdx, trainIdx)."""

@@ -207,3 +207,35 @@ def test_duplicates_on_tile_and_split_boundaries():
         assert list(idx[i]) == rows[:2] and list(dist[i]) == [0, 0], (i, idx[i], rows)
     ridx, rdist = c_oracle.hamming_knn2(q[:64], t)
     assert np.array_equal(idx[:64], ridx) and np.array_equal(dist[:64], rdist)
+
+
+def test_keyframe_database_grows_in_place():
+    """Keyframes appended one at a time (across several capacity doublings) give the
+    same global rows as one flat matrix; appends within capacity do not move the data."""
+    from pybot_b200.vision.matcher import BFMatcher, KeyframeDatabase
+    rng = np.random.default_rng(21)
+    q = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    kfs = [rng.integers(0, 256, (int(n), 32), dtype=np.uint8) for n in rng.integers(1, 9000, 40)]
+    kfs[7][3] = q[5]
+    kfs[31][0] = q[5]                                      # same descriptor in two keyframes: lower image wins
+    m = BFMatcher()
+    ptrs = set()
+    for kf in kfs:
+        m.add([kf])
+        ptrs.add(m.db.flat.data_ptr())
+    assert len(m.db) == sum(len(k) for k in kfs) and len(ptrs) <= 6      # geometric growth, not one copy per add
+    got = m.knnMatch(q, k=2)
+    flat = np.concatenate(kfs)
+    idx, dist, _, _, _ = __import__("pybot_b200.vision.matcher", fromlist=["x"]).knn_ratio_mutual(q, flat, 0.75)
+    off = np.cumsum([0] + [len(k) for k in kfs])
+    for i in (0, 5, 17, 299):
+        g = [off[d.imgIdx] + d.trainIdx for d in got[i]]
+        assert g == list(idx[i]) and [int(d.distance) for d in got[i]] == list(dist[i])
+    assert (got[5][0].imgIdx, got[5][0].trainIdx, got[5][1].imgIdx, got[5][1].trainIdx) == (7, 3, 31, 0)
+    db = KeyframeDatabase()
+    db.reserve(1_000_000)
+    p0 = db.flat.data_ptr() if len(db) else None
+    db.add(kfs[:3])
+    p1 = db.flat.data_ptr()
+    db.add(kfs[3:])
+    assert db.flat.data_ptr() == p1 and p0 is None
