@@ -35,8 +35,13 @@
 namespace pbk {
 
 constexpr int kHThreads = 128;
-constexpr int kRQ = 4;                          // queries per thread
+constexpr int kRQ = 4;                          // queries per thread (throughput shape)
 constexpr int kQTile = kHThreads * kRQ;         // 512 queries per CTA
+// Per-frame problems (C1: 2000 x 2000) give the throughput shape 4 query tiles x 8
+// stage-sized splits = 32 CTAs on 148 SMs, each scoring 256 rows x 4 queries per
+// thread (26 us for 4 M pairs).  The latency shape keeps ONE query per thread:
+// 4x the CTAs, a quarter of the work per thread.
+constexpr int kRQSmall = 1;
 constexpr int kTR = 256;                        // train rows per stage
 constexpr int kStages = 4;
 constexpr int kStageBytes = kTR * 32;
@@ -122,23 +127,24 @@ __device__ __forceinline__ void top2_insert(uint32_t& k1, uint32_t& k2, uint32_t
 }
 
 // Scores `nrows` staged rows (FULL: exactly kTR) against the thread's 4 queries.
-template <int VARIANT, bool FULL>
+template <int VARIANT, bool FULL, int RQ>
 __device__ __forceinline__ void score_tile(const uint4* __restrict__ tile, int nrows, uint32_t rowkey,
-                                           const uint32_t (&qr)[kRQ][8], uint32_t (&k1)[kRQ],
-                                           uint32_t (&k2)[kRQ]) {
+                                           const uint32_t (&qr)[RQ][8], uint32_t (&k1)[RQ],
+                                           uint32_t (&k2)[RQ]) {
   const int n = FULL ? kTR : nrows;
 #pragma unroll 4
   for (int j = 0; j < n; ++j) {
     const uint4 a = tile[2 * j], b = tile[2 * j + 1];
 #pragma unroll
-    for (int r = 0; r < kRQ; ++r) top2_insert(k1[r], k2[r], pair_key<VARIANT>(qr[r], a, b, rowkey));
+    for (int r = 0; r < RQ; ++r) top2_insert(k1[r], k2[r], pair_key<VARIANT>(qr[r], a, b, rowkey));
     ++rowkey;
   }
 }
 
-template <int VARIANT>
+template <int VARIANT, int RQ = kRQ>
 __global__ void __launch_bounds__(kHThreads, 4)
 hamming_knn2_kernel(const __grid_constant__ HammingParams P) {
+  constexpr int kRQ = RQ, kQTile = kHThreads * RQ;      // shadow the throughput-shape constants
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* ring = smem;                                   // kStages * kStageBytes
   uint8_t* qstage = smem + kStages * kStageBytes;         // kQTile * 32
@@ -213,8 +219,8 @@ hamming_knn2_kernel(const __grid_constant__ HammingParams P) {
       }
       __syncthreads();
     }
-    if (nrows == kTR) score_tile<VARIANT, true>(tile, kTR, (uint32_t)r_base, qr, k1, k2);
-    else score_tile<VARIANT, false>(tile, nrows, (uint32_t)r_base, qr, k1, k2);
+    if (nrows == kTR) score_tile<VARIANT, true, kRQ>(tile, kTR, (uint32_t)r_base, qr, k1, k2);
+    else score_tile<VARIANT, false, kRQ>(tile, nrows, (uint32_t)r_base, qr, k1, k2);
     __syncthreads();   // everyone is done with slot s before it is refilled
   }
 
@@ -521,9 +527,16 @@ static int hamming_variant() {
   return g_variant;
 }
 
-static int plan(const DeviceInfo* di, long long nq, long long nt, int* splits, long long* rows_per_split) {
-  const long long qtiles = (nq + kQTile - 1) / kQTile;
+static int plan(const DeviceInfo* di, long long nq, long long nt, int* splits, long long* rows_per_split,
+                int* rq = nullptr) {
   const long long target = (long long)di->sm_count * 4;            // 4 CTAs (16 warps) per SM
+  const long long stages = (nt + kTR - 1) / kTR;
+  // queries per thread: 4, unless even one-stage splits leave SMs without a CTA
+  const long long qt4 = (nq + kQTile - 1) / kQTile;
+  const int rqv = (qt4 * (stages > 0 ? stages : 1) < di->sm_count) ? kRQSmall : kRQ;
+  if (rq) *rq = rqv;
+  const long long qtile = (long long)kHThreads * rqv;
+  const long long qtiles = (nq + qtile - 1) / qtile;
   long long s = qtiles > 0 ? (target + qtiles - 1) / qtiles : 1;
   const long long max_by_rows = (nt + kTR - 1) / kTR;              // >= one stage per split
   if (s > max_by_rows) s = max_by_rows;
@@ -540,6 +553,28 @@ static int plan(const DeviceInfo* di, long long nq, long long nt, int* splits, l
   return PBK_OK;
 }
 
+}  // namespace pbk
+
+namespace pbk {
+// launches the scoring kernel in the shape plan() chose
+static int launch_knn2(const HammingParams& P, int rq, cudaStream_t s) {
+  const int qtile = kHThreads * rq;
+  const int smem = kStages * kStageBytes + qtile * 32 + (kStages + 1) * 8;
+  const dim3 grid((unsigned)((P.nq + qtile - 1) / qtile), (unsigned)P.splits);
+#define PBK_KNN2(V, R)                                                                                      \
+  do {                                                                                                      \
+    PBK_CUDA(cudaFuncSetAttribute(hamming_knn2_kernel<V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    hamming_knn2_kernel<V, R><<<grid, kHThreads, smem, s>>>(P);                                             \
+  } while (0)
+  if (hamming_variant() == 0) {
+    if (rq == kRQ) PBK_KNN2(0, kRQ); else PBK_KNN2(0, kRQSmall);
+  } else {
+    if (rq == kRQ) PBK_KNN2(1, kRQ); else PBK_KNN2(1, kRQSmall);
+  }
+#undef PBK_KNN2
+  PBK_CHECK_LAUNCH("hamming_knn2_kernel");
+  return PBK_OK;
+}
 }  // namespace pbk
 
 extern "C" {
@@ -572,23 +607,15 @@ int pbk_hamming_knn2(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt,
   int rc = current_device_info(&di);
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
-  int splits;
+  int splits, rq;
   long long rps;
-  rc = plan(di, nq, nt, &splits, &rps);
+  rc = plan(di, nq, nt, &splits, &rps, &rq);
   if (rc) return rc;
   HammingParams P;
   P.q = q; P.t = t; P.partial = static_cast<unsigned long long*>(scratch);
   P.nq = nq; P.nt = nt; P.rows_per_split = rps; P.train_base = train_base; P.splits = splits;
-  const int smem = kStages * kStageBytes + kQTile * 32 + (kStages + 1) * 8;
-  const dim3 grid((unsigned)((nq + kQTile - 1) / kQTile), (unsigned)splits);
-  if (hamming_variant() == 0) {
-    PBK_CUDA(cudaFuncSetAttribute(hamming_knn2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    hamming_knn2_kernel<0><<<grid, kHThreads, smem, s>>>(P);
-  } else {
-    PBK_CUDA(cudaFuncSetAttribute(hamming_knn2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    hamming_knn2_kernel<1><<<grid, kHThreads, smem, s>>>(P);
-  }
-  PBK_CHECK_LAUNCH("hamming_knn2_kernel");
+  rc = launch_knn2(P, rq, s);
+  if (rc) return rc;
   hamming_merge_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(P.partial, splits, nq,
                                                                     reinterpret_cast<unsigned long long*>(keys));
   PBK_CHECK_LAUNCH("hamming_merge_kernel");
@@ -671,23 +698,15 @@ int pbk_hamming_knn2_dist(const uint8_t* q, int64_t nq, const uint8_t* t, int64_
   rc = current_device_info(&di);
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
-  int splits;
+  int splits, rq;
   long long rps;
-  rc = plan(di, nq, nt, &splits, &rps);
+  rc = plan(di, nq, nt, &splits, &rps, &rq);
   if (rc) return rc;
   HammingParams P;
   P.q = q; P.t = t; P.partial = static_cast<unsigned long long*>(scratch);
   P.nq = nq; P.nt = nt; P.rows_per_split = rps; P.train_base = train_base; P.splits = splits;
-  const int smem = kStages * kStageBytes + kQTile * 32 + (kStages + 1) * 8;
-  const dim3 grid((unsigned)((nq + kQTile - 1) / kQTile), (unsigned)splits);
-  if (hamming_variant() == 0) {
-    PBK_CUDA(cudaFuncSetAttribute(hamming_knn2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    hamming_knn2_kernel<0><<<grid, kHThreads, smem, s>>>(P);
-  } else {
-    PBK_CUDA(cudaFuncSetAttribute(hamming_knn2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    hamming_knn2_kernel<1><<<grid, kHThreads, smem, s>>>(P);
-  }
-  PBK_CHECK_LAUNCH("hamming_knn2_kernel");
+  rc = launch_knn2(P, rq, s);
+  if (rc) return rc;
   const unsigned blocks = (unsigned)((nq + 255) / 256);
   hamming_merge_push_kernel<<<blocks, 256, 0, s>>>(P.partial, splits, X, done_counter);
   PBK_CHECK_LAUNCH("hamming_merge_push_kernel");

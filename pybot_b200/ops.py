@@ -207,7 +207,7 @@ def project_points(X, R, t, K, D=None, Rz=None, tz=None, shape=None, check_bound
         if depth is not None:
             depth = depth[:m]
     if valid is not None:
-        valid = valid.bool() if on_dev else valid
+        valid = valid.view(_ffi.torch().bool) if on_dev else valid
     outs = [_finish(uv, on_dev),
             _finish(depth, on_dev) if depth is not None else None,
             (_finish(valid, on_dev) if valid is not None else None)]
@@ -435,7 +435,8 @@ def hamming_ratio_mutual(keys, rev_keys, ratio):
     _ffi.check(_ffi.lib().pbk_hamming_ratio_mutual(
         _ffi.ptr(keys), _ffi.ptr(rev_keys), nq, float(ratio), _ffi.ptr(idx), _ffi.ptr(dist),
         _ffi.ptr(flags[0]), _ffi.ptr(flags[1]), _ffi.ptr(flags[2]), _ffi.stream_ptr()))
-    return idx, dist, flags[0, :nq].bool(), flags[1, :nq].bool(), flags[2, :nq].bool()
+    fb = flags.view(T.bool)                  # the kernel writes 0/1 bytes: reinterpret, no conversion launches
+    return idx, dist, fb[0, :nq], fb[1, :nq], fb[2, :nq]
 
 
 def knn_ratio_mutual(q, t, ratio=0.75, train_base=0, mutual=True):
@@ -529,7 +530,8 @@ class PreparedMatcher(object):
         elif self.nq > 0:
             self._launch()
         n = self.nq
-        return self.idx[:n], self.dist[:n], self.flags[0, :n].bool(), self.flags[1, :n].bool(), self.flags[2, :n].bool()
+        fb = self.flags.view(T.bool)
+        return self.idx[:n], self.dist[:n], fb[0, :n], fb[1, :n], fb[2, :n]
 
 
 def popc_probe(mode=0, ctas=None, iters=2000):
