@@ -46,9 +46,18 @@ def ncu_traffic(kernel, scale=1.0):
     try:
         with open(p) as f:
             d = json.load(f)
-        return float(d["kernels"][kernel]["dram_bytes"]) * scale
+        return float(_traffic_entry(d, kernel)["dram_bytes"]) * scale
     except Exception:
         return None
+
+
+def _traffic_entry(d, kernel):
+    """Exact kernel name, else the first captured kernel whose name starts with it
+    (template arguments differ between kernel variants)."""
+    ks = d["kernels"]
+    if kernel in ks:
+        return ks[kernel]
+    return next(v for k, v in ks.items() if k.startswith(kernel))
 
 
 def ncu_traffic_note(kernel, scale=1.0):
@@ -56,7 +65,7 @@ def ncu_traffic_note(kernel, scale=1.0):
     try:
         with open(p) as f:
             d = json.load(f)
-        e = d["kernels"][kernel]
+        e = _traffic_entry(d, kernel)
         return ("dram read+write bytes per launch from profiles/%s_ncu_full_summary.md (captured on: %s)%s"
                 % (d["tag"], e.get("problem", ""), "" if scale == 1.0 else ", scaled x%g to this launch" % scale))
     except Exception:
@@ -239,15 +248,18 @@ def ev_pair(torch):
 # ------------------------------------------------------- popc / alu peaks
 def probe_peaks(D):
     """Measured integer-pipe ceilings on this GPU, in this run (burst, ~20 ms
-    each): mode 0 = pure POPC chains -> popc-pipe peak; modes 2 / 3 = the
-    matcher's own inner loop (8-POPC / carry-save 4-POPC) over a resident
-    shared-memory tile with 4 CTAs per SM and no global traffic -> the
-    instruction-mix ceiling of the kernel."""
+    each): mode 0 = pure POPC chains -> popc-pipe peak; modes 2 / 3 / 4 = the
+    matcher's own inner loop (8-POPC / carry-save 4-POPC / carry-save with the packed
+    u16x2 top-2 network the kernel ships) over a resident shared-memory tile with
+    4 CTAs per SM and no global traffic -> the instruction-mix ceiling of the kernel;
+    mode 5 = the same loop with the top-2 network reduced to one min per two pairs
+    (what is left when selection is free: the XOR/CSA/POPC floor)."""
     from pybot_b200 import ops
     torch = D.torch
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     out = {}
-    for mode, ctas, iters in ((0, sms * 8, 4000), (2, sms * 4, 100), (3, sms * 4, 200)):
+    for mode, ctas, iters in ((0, sms * 8, 4000), (2, sms * 4, 100), (3, sms * 4, 200), (4, sms * 4, 200),
+                              (5, sms * 4, 200)):
         best = 0.0
         for _ in range(3):
             a, b = ev_pair(torch)
@@ -258,7 +270,8 @@ def probe_peaks(D):
             best = max(best, n / (a.elapsed_time(b) * 1e-3))
         out[mode] = best
     return {"popc_per_s": out[0], "sm_count": sms,
-            "pairs_per_s_mix8popc": out[2] / 8.0, "pairs_per_s_mix4popc_csa": out[3] / 4.0}
+            "pairs_per_s_mix8popc": out[2] / 8.0, "pairs_per_s_mix4popc_csa": out[3] / 4.0,
+            "pairs_per_s_mix4popc_csa_u16x2": out[4] / 4.0, "pairs_per_s_no_selection": out[5] / 4.0}
 
 
 # ------------------------------------------------------------ workload C3
@@ -348,19 +361,22 @@ def run_c3(D, args):
             "bound": "popc", "kernel": "hamming_knn2_kernel (+ split merge)",
             "achieved": popc_rate / 1e12, "peak": pk["popc_per_s"] / 1e12, "unit": "Tpopc/s",
             "frac": popc_rate / pk["popc_per_s"],
-            "traffic": ncu_traffic("hamming_knn2_kernel<1>", scale=float(shard.shape[0]) / 2.5e6),
-            "traffic_source": ncu_traffic_note("hamming_knn2_kernel<1>", scale=float(shard.shape[0]) / 2.5e6),
+            "traffic": ncu_traffic("hamming_knn2_kernel", scale=float(shard.shape[0]) / 2.5e6),
+            "traffic_source": ncu_traffic_note("hamming_knn2_kernel", scale=float(shard.shape[0]) / 2.5e6),
             "algorithmic": "8 POPC.32 per pair (256 bits); achieved = nq*nt_local*8 / kernel time",
             "peak_source": "pbk_popc_peak_probe mode 0, measured in this run (burst)",
             "kernel_ms": knn_ms / args.steps, "kernel_share_of_step": knn_ms / total_ms,
-            "note": "the kernel issues 4 POPC + 13 LOP3 + 3 VIMNMX per pair (carry-save compression of "
-                    "the 8 words), so the algorithmic popc rate can exceed the popc-pipe peak; ALU and "
-                    "POPC pipes are both ~0.25 clk/pair/SM - see mix ceilings (same inner loop on a "
-                    "resident smem tile)",
+            "note": "the kernel issues 4 POPC + 13 LOP3 + 1.5 VIMNMX.U16x2 + 4 IMAD per pair (carry-save "
+                    "compression of the 8 words; two queries' 16-bit keys share a register in the top-2 "
+                    "network), so the algorithmic popc rate can exceed the popc-pipe peak; the POPC "
+                    "(XU) pipe is the binding one at 0.25 clk/pair/SM - see mix ceilings (same inner "
+                    "loops on a resident smem tile)",
             "mix_ceiling_gpairs": {"8popc": pk["pairs_per_s_mix8popc"] / 1e9,
-                                   "4popc_csa": pk["pairs_per_s_mix4popc_csa"] / 1e9},
+                                   "4popc_csa": pk["pairs_per_s_mix4popc_csa"] / 1e9,
+                                   "4popc_csa_u16x2": pk["pairs_per_s_mix4popc_csa_u16x2"] / 1e9,
+                                   "4popc_csa_no_selection": pk["pairs_per_s_no_selection"] / 1e9},
             "frac_of_register_mix_ceiling": (local_pairs * args.steps / (knn_ms * 1e-3))
-            / pk["pairs_per_s_mix4popc_csa"],
+            / pk["pairs_per_s_mix4popc_csa_u16x2"],
         }
         if D.world == 1:
             res["cpu_baseline"] = cpu_baseline_c3(q_np, db_np, per_kf)

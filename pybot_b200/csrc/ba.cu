@@ -102,10 +102,14 @@ struct BaCfg {
   static constexpr int kStJp = kTile * 48;            //                       J_pt rows
   static constexpr int kStR = kStJp + kTile * 24;     //                       residuals
   static constexpr int kStage = kStR + kTile * 8;     // 80 B per observation
+#ifndef PBK_BA_STAGE_BUFS
+#define PBK_BA_STAGE_BUFS 1
+#endif
+  static constexpr int kStageBufs = PBK_BA_STAGE_BUFS; // output stages per warp (bulk stores of tile k-1 drain while tile k is computed)
   static constexpr int kRingStages = 3;
   static constexpr int kObsBytes = kTile * 16;        // one tile of observation records
   // dynamic shared memory layout
-  static constexpr int kSmemRing = kBaWarps * kStage;
+  static constexpr int kSmemRing = kBaWarps * kStageBufs * kStage;
   static constexpr int kSmemCam = kSmemRing + kBaWarps * kRingStages * kObsBytes;
   static constexpr int kSmemBars = kSmemCam + kBaWarps * kCam * 8;
   static constexpr int kSmemCost = kSmemBars + kBaWarps * kRingStages * 8;
@@ -117,13 +121,20 @@ __device__ __forceinline__ uint4 ba_load_obs(const BaParams& P, long long i) {
 }
 __device__ __forceinline__ void ba_load_point(const BaParams& P, uint32_t raw, float (&p)[3]) {
   int pt = (int)raw;            // out-of-range indices are clamped (the wrapper validates them)
+#ifdef PBK_BA_PROBE_NOGATHER
+  pt = (int)((threadIdx.x + blockIdx.x * 256) & 0xffff);      // probe: coalesced, L1-resident "gather"
+#endif
   pt = pt < 0 ? 0 : ((long long)pt >= P.n_points ? (int)(P.n_points - 1) : pt);
   const float* pp = P.points + 3ll * pt;
   // volatile: these loads must not be hoisted above the conversion of the previous
   // tile's points (see process()), or both tiles' loads share a scoreboard
-  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(p[0]) : "l"(pp));
-  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(p[1]) : "l"(pp + 1));
-  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(p[2]) : "l"(pp + 2));
+  // the 12 MB point array is re-read ~4x while 320 MB of outputs stream through L2: keep it
+  // resident (evict_last); measured 84.2 -> 82.0 us on C4
+  const uint64_t pol = l2_policy_evict_last();
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(p[0]) : "l"(pp), "l"(pol));
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(p[1]) : "l"(pp + 1), "l"(pol));
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(p[2]) : "l"(pp + 2), "l"(pol));
+
 }
 
 // Residual + Jacobian blocks of N observations that share the camera block C
@@ -140,6 +151,25 @@ __device__ __forceinline__ void ba_eval(const double* C, const BaParams& P, cons
   float4* sJc = reinterpret_cast<float4*>(st);
   float2* sJp = reinterpret_cast<float2*>(st + TILE * 48);
   float2* sR = reinterpret_cast<float2*>(st + TILE * 72);
+#ifdef PBK_BA_PROBE_NOMATH
+  // probe: the memory skeleton alone (records in, gathers, stage writes, bulk stores out)
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    if (act[j]) {
+      const float x0 = (float)X[j][0], x1 = (float)X[j][1], x2 = (float)X[j][2] + (float)C[0];
+      const float uo = __uint_as_float(ob[j].z), vo = __uint_as_float(ob[j].w);
+      if (live[j]) cost += (double)uo;
+      sR[slot[j]] = make_float2(uo, vo);
+      sJp[slot[j] * 3 + 0] = make_float2(x0, x1);
+      sJp[slot[j] * 3 + 1] = make_float2(x2, x0);
+      sJp[slot[j] * 3 + 2] = make_float2(x1, x2);
+      sJc[slot[j] * 3 + 0] = make_float4(x0, x1, x2, uo);
+      sJc[slot[j] * 3 + 1] = make_float4(x1, x2, uo, x0);
+      sJc[slot[j] * 3 + 2] = make_float4(x2, uo, x0, x1);
+    }
+  }
+  return;
+#endif
   double a[N], b[N], cc[N], d[N];
   {
     const double2 c0 = C2[0], c1 = C2[1], c2 = C2[2], c3 = C2[3], c4 = C2[4], c5 = C2[5];
@@ -229,14 +259,15 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
                 kBaSmemRing = Cfg::kSmemRing, kBaSmemCam = Cfg::kSmemCam, kBaSmemBars = Cfg::kSmemBars,
                 kBaSmemCost = Cfg::kSmemCost;
   extern __shared__ __align__(128) char ba_smem[];
-  char (*stage)[kBaStage] = reinterpret_cast<char (*)[kBaStage]>(ba_smem);
+  constexpr int kBaStageBufs = Cfg::kStageBufs;
+  char (*stage)[kBaStageBufs * kBaStage] = reinterpret_cast<char (*)[kBaStageBufs * kBaStage]>(ba_smem);
   char (*obs_ring)[kBaRingStages * kBaObsBytes] =
       reinterpret_cast<char (*)[kBaRingStages * kBaObsBytes]>(ba_smem + kBaSmemRing);
   double (*cam_cache)[kCam] = reinterpret_cast<double (*)[kCam]>(ba_smem + kBaSmemCam);
   uint64_t (*ring_bars)[kBaRingStages] = reinterpret_cast<uint64_t (*)[kBaRingStages]>(ba_smem + kBaSmemBars);
   double* warp_cost = reinterpret_cast<double*>(ba_smem + kBaSmemCost);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  char* st = stage[warp];
+  char* const st_base = stage[warp];
   const double* C = cam_cache[warp];
   double cost = 0.0;
   int cached_cam = -1;
@@ -324,8 +355,10 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
     }
     const bool uniform = __all_sync(0xffffffffu, same) && c0 >= 0 && c0 < P.n_cams;
 
-    // the previous tile's bulk stores must have drained the stage before it is rewritten
-    if (lane == 0) tma_store_wait_read();
+    // the bulk stores that last read this stage buffer (tile k - kStageBufs) must have drained it
+    // before it is rewritten; the stores of the tiles in between may still be in flight
+    char* const st = st_base + (k % kBaStageBufs) * kBaStage;
+    if (lane == 0) tma_store_wait_read_but<kBaStageBufs - 1>();
     __syncwarp();
 
     if (uniform) {

@@ -27,6 +27,12 @@
 //  * top-2 selection is a 3-instruction min/max network on a packed 32-bit key
 //    (distance * (2^23+1) + local row): rows are scanned in ascending order and the
 //    key order is lexicographic, so ties resolve to the lowest train index.
+//    VARIANT 2 (default for the 4-queries-per-thread shape) runs that network on
+//    16-bit keys, two queries per register (VIMNMX.U16x2: 1.5 instead of 3 ALU
+//    instructions per pair), over 128-row blocks whose winners are folded into the
+//    32-bit keys; 966 -> 996 Gpairs/s on a 2.5 M-row shard.  With selection removed
+//    altogether the loop runs only 3 % faster again: 4 POPC per pair on the 16-lane
+//    XU pipe is then the bound.
 //  * each CTA emits (distance << 32 | global row) u64 keys per query; a merge
 //    kernel reduces the splits (and, multi-GPU, the all-gathered shards) with
 //    the same unsigned min - bit-identical to a single ascending scan.
@@ -100,7 +106,7 @@ __device__ __forceinline__ void derive_row(uint4& a, uint4& b) {
 template <int VARIANT>
 __device__ __forceinline__ uint32_t pair_key(const uint32_t* q, const uint4& a, const uint4& b,
                                              uint32_t rowkey) {
-  if (VARIANT == 0) {
+  if constexpr (VARIANT == 0) {
     const uint32_t d = __popc(q[0] ^ a.x) + __popc(q[1] ^ a.y) + __popc(q[2] ^ a.z) + __popc(q[3] ^ a.w) +
                        __popc(q[4] ^ b.x) + __popc(q[5] ^ b.y) + __popc(q[6] ^ b.z) + __popc(q[7] ^ b.w);
     return mad_u32(d, kKeyMul, rowkey);
@@ -120,6 +126,34 @@ __device__ __forceinline__ uint32_t pair_key(const uint32_t* q, const uint4& a, 
   }
 }
 
+// VARIANT 2: two queries' keys ride in one register as u16 halves so that the top-2 network is
+// 3 VIMNMX.U16x2 per TWO pairs.  A 16-bit key = distance * 129 + row-in-block (row < 128) keeps
+// the (distance, row) order for distances up to 256 (max 33151; 0xFFFF = none), so the tile is
+// scored in 128-row blocks whose packed top-2 are folded into the 32-bit keys once per block.
+constexpr int kBlk = 128;
+constexpr uint32_t kMul16 = kBlk + 1;
+// popc weights of one derived-form pair, summed with IMADs (FMA pipe) onto `acc`
+__device__ __forceinline__ uint32_t pair_acc(const uint32_t* q, const uint4& a, const uint4& b, uint32_t mul,
+                                             uint32_t acc) {
+  const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x3 = q[2] ^ a.z, x4 = q[3] ^ a.w;
+  const uint32_t x7 = q[4] ^ b.x;
+  const uint32_t sa = q[5] ^ b.y, sb = q[6] ^ b.z, sc = q[7] ^ b.w;
+  const uint32_t ca = carry_from_sum(x0, x1, sa);
+  const uint32_t cb = carry_from_sum(x3, x4, sb);
+  const uint32_t cc = carry_from_sum(sa, sb, sc);
+  const uint32_t sd = xor3(ca, cb, cc), cd = maj3(ca, cb, cc);
+  acc = mad_u32(__popc(x7), mul, acc);
+  acc = mad_u32(__popc(sc), mul, acc);
+  acc = mad_u32(__popc(sd), 2u * mul, acc);
+  return mad_u32(__popc(cd), 4u * mul, acc);
+}
+__device__ __forceinline__ void top2_insert_u16x2(uint32_t& k1, uint32_t& k2, uint32_t key) {
+  uint32_t mx;
+  asm("max.u16x2 %0, %1, %2;" : "=r"(mx) : "r"(k1), "r"(key));
+  asm("min.u16x2 %0, %1, %2;" : "=r"(k1) : "r"(k1), "r"(key));
+  asm("min.u16x2 %0, %1, %2;" : "=r"(k2) : "r"(k2), "r"(mx));
+}
+
 __device__ __forceinline__ void top2_insert(uint32_t& k1, uint32_t& k2, uint32_t key) {
   const uint32_t mx = max(k1, key);
   k1 = min(k1, key);
@@ -131,6 +165,57 @@ template <int VARIANT, bool FULL, int RQ>
 __device__ __forceinline__ void score_tile(const uint4* __restrict__ tile, int nrows, uint32_t rowkey,
                                            const uint32_t (&qr)[RQ][8], uint32_t (&k1)[RQ],
                                            uint32_t (&k2)[RQ]) {
+  if constexpr (VARIANT == 3) {
+    // probe only: packed keys reduced with ONE min per two pairs (no second-best) - the ceiling
+    // of the XOR/CSA/POPC/IMAD part of the loop
+    uint32_t rk = rowkey;
+#pragma unroll 4
+    for (int j = 0; j < kTR; ++j) {
+      const uint4 a = tile[2 * j], b = tile[2 * j + 1];
+#pragma unroll
+      for (int h = 0; h < RQ / 2; ++h) {
+        const uint32_t lo = pair_acc(qr[2 * h], a, b, kMul16, rk);
+        const uint32_t key = pair_acc(qr[2 * h + 1], a, b, kMul16 << 16, lo);
+        asm("min.u16x2 %0, %1, %2;" : "=r"(k1[2 * h]) : "r"(k1[2 * h]), "r"(key));
+      }
+      rk += 0x10001u;
+    }
+    return;
+  }
+  if constexpr (VARIANT == 2 && RQ % 2 == 0) {
+    for (int b0 = 0; b0 < kTR; b0 += kBlk) {
+      const int n = FULL ? kBlk : (nrows - b0 < kBlk ? nrows - b0 : kBlk);
+      if (!FULL && n <= 0) break;
+      uint32_t p1[RQ / 2], p2[RQ / 2];
+#pragma unroll
+      for (int h = 0; h < RQ / 2; ++h) p1[h] = p2[h] = 0xFFFFFFFFu;
+      const uint4* blk = tile + 2 * b0;
+      uint32_t rk = 0;                       // row-in-block in both halves
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) {
+        const uint4 a = blk[2 * j], b = blk[2 * j + 1];
+#pragma unroll
+        for (int h = 0; h < RQ / 2; ++h) {
+          const uint32_t lo = pair_acc(qr[2 * h], a, b, kMul16, rk);
+          top2_insert_u16x2(p1[h], p2[h], pair_acc(qr[2 * h + 1], a, b, kMul16 << 16, lo));
+        }
+        rk += 0x10001u;
+      }
+      // fold the block's packed top-2 into the 32-bit keys (0xFFFF -> none, which never wins)
+#pragma unroll
+      for (int r = 0; r < RQ; ++r) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t pk = c == 0 ? p1[r / 2] : p2[r / 2];
+          const uint32_t v = (r & 1) ? (pk >> 16) : (pk & 0xFFFFu);
+          const uint32_t d = v / kMul16;
+          const uint32_t key = v == 0xFFFFu ? kLocalNone : d * (kKeyMul - kMul16) + v + rowkey + (uint32_t)b0;
+          top2_insert(k1[r], k2[r], key);
+        }
+      }
+    }
+    return;
+  }
   const int n = FULL ? kTR : nrows;
 #pragma unroll 4
   for (int j = 0; j < n; ++j) {
@@ -188,7 +273,7 @@ hamming_knn2_kernel(const __grid_constant__ HammingParams P) {
     const uint4* src = reinterpret_cast<const uint4*>(qstage + (r * kHThreads + tid) * 32);
     const uint4 a = src[0], b = src[1];
     uint4 da = a, db = b;
-    if (VARIANT == 1) derive_row(da, db);
+    if (VARIANT >= 1) derive_row(da, db);
     qr[r][0] = da.x; qr[r][1] = da.y; qr[r][2] = da.z; qr[r][3] = da.w;
     qr[r][4] = db.x; qr[r][5] = db.y; qr[r][6] = db.z; qr[r][7] = db.w;
   }
@@ -205,7 +290,7 @@ hamming_knn2_kernel(const __grid_constant__ HammingParams P) {
     const long long r_base = (long long)it * kTR;
     const int nrows = (int)((rows - r_base) < kTR ? (rows - r_base) : kTR);
     uint4* tile = reinterpret_cast<uint4*>(ring + s * kStageBytes);
-    if (VARIANT == 1) {
+    if (VARIANT >= 1) {
       // rewrite the staged rows to derived form, two rows per thread, in place
 #pragma unroll
       for (int h = 0; h < kTR / kHThreads; ++h) {
@@ -484,7 +569,7 @@ __global__ void __launch_bounds__(MODE >= 2 ? kHThreads : 256) popc_probe_kernel
       for (int w = 0; w < 8; ++w) qr[r][w] = (threadIdx.x * 8 + w + r * 977) * 2246822519u + sink[w];
     }
     for (int it = 0; it < iters; ++it)
-      score_tile<MODE == 2 ? 0 : 1, true>(tile, kTR, (uint32_t)it * kTR, qr, k1, k2);
+      score_tile<MODE - 2, true>(tile, kTR, (uint32_t)it * kTR, qr, k1, k2);
     uint32_t acc = 0;
 #pragma unroll
     for (int r = 0; r < kRQ; ++r) acc ^= k1[r] ^ k2[r];
@@ -522,7 +607,7 @@ static int g_variant = -1;
 static int hamming_variant() {
   if (g_variant < 0) {
     const char* e = getenv("PBK_HAMMING_VARIANT");
-    g_variant = (e && e[0] == '0') ? 0 : 1;
+    g_variant = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
   }
   return g_variant;
 }
@@ -568,6 +653,8 @@ static int launch_knn2(const HammingParams& P, int rq, cudaStream_t s) {
   } while (0)
   if (hamming_variant() == 0) {
     if (rq == kRQ) PBK_KNN2(0, kRQ); else PBK_KNN2(0, kRQSmall);
+  } else if (hamming_variant() == 2 && rq == kRQ) {
+    PBK_KNN2(2, kRQ);
   } else {
     if (rq == kRQ) PBK_KNN2(1, kRQ); else PBK_KNN2(1, kRQSmall);
   }
@@ -749,6 +836,8 @@ int pbk_popc_peak_probe(int mode, int ctas, int iters, uint32_t* sink, double* p
     case 1: popc_probe_kernel<1><<<ctas, 256, 0, s>>>(iters, sink); per_thread = 16.0 * 8; break;
     case 2: popc_probe_kernel<2><<<ctas, kHThreads, 0, s>>>(iters, sink); per_thread = kRQ * kTR * 8.0; threads = kHThreads; break;
     case 3: popc_probe_kernel<3><<<ctas, kHThreads, 0, s>>>(iters, sink); per_thread = kRQ * kTR * 4.0; threads = kHThreads; break;
+    case 4: popc_probe_kernel<4><<<ctas, kHThreads, 0, s>>>(iters, sink); per_thread = kRQ * kTR * 4.0; threads = kHThreads; break;
+    case 5: popc_probe_kernel<5><<<ctas, kHThreads, 0, s>>>(iters, sink); per_thread = kRQ * kTR * 4.0; threads = kHThreads; break;
     default: PBK_REQUIRE(false, PBK_EINVAL, "bad probe mode %d", mode);
   }
   PBK_CHECK_LAUNCH("popc_probe_kernel");

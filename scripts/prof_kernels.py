@@ -20,9 +20,32 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 g = torch.Generator(device="cuda").manual_seed(1)
 
 
+FLUSH = os.environ.get("PROF_FLUSH", "0") == "1"
+_fa = _fb = None
+
+
 def timed(name, fn):
+    """PROF_FLUSH=1: L2 flushed between reps (as bench.py does), per-rep events, median + min."""
+    global _fa, _fb
     fn()
     torch.cuda.synchronize()
+    if FLUSH:
+        if _fa is None:
+            _fa = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+            _fb = torch.ones(256 << 20, dtype=torch.uint8, device="cuda")
+        ts = []
+        for _ in range(reps):
+            _fa.fill_(1)
+            _fb.sum()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        print("%-12s %.4f ms median  %.4f min (flushed, %d reps)" % (name, ts[len(ts) // 2], ts[0], reps))
+        return
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(reps):

@@ -81,9 +81,11 @@ def test_ragged_sizes(nq, nt):
     _check_against_model(q, t)
 
 
-@pytest.mark.parametrize("variant", ["0", "1"])
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
 def test_both_popc_variants_agree(variant):
-    """PBK_HAMMING_VARIANT selects 8-POPC vs carry-save 4-POPC scoring: same keys."""
+    """PBK_HAMMING_VARIANT selects 8-POPC / carry-save 4-POPC / carry-save with the packed
+    u16x2 top-2 network: same keys.  The second problem is large enough for the
+    4-queries-per-thread shape (the only one variant 2 applies to) and is full of ties."""
     import subprocess, sys
     code = (
         "import numpy as np, sys; sys.path.insert(0, %r);"
@@ -92,6 +94,11 @@ def test_both_popc_variants_agree(variant):
         "q,t = syn.low_entropy_pair(seed=3, nq=700, nt=3000);"
         "a = knn_ratio_mutual(q,t); b = model.ratio_mutual(q,t);"
         "assert all(np.array_equal(np.asarray(x).astype(np.int64), np.asarray(y).astype(np.int64)) for x,y in zip(a,b));"
+        "from oracle import c_oracle;"
+        "q,t = syn.low_entropy_pair(seed=4, nq=700, nt=50021);"
+        "t[130] = ~q[5]; t[40000] = q[5]; t[40001] = q[5]; t[127] = q[9]; t[128] = q[9];"
+        "idx, dist = knn_ratio_mutual(q,t)[:2]; ridx, rdist = c_oracle.hamming_knn2(q,t);"
+        "assert np.array_equal(idx, ridx) and np.array_equal(dist, rdist);"
         "print('ok')") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, PBK_HAMMING_VARIANT=variant)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
