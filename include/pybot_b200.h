@@ -262,6 +262,22 @@ PBK_API int pbk_ba_residual_jacobian_dist(const void* obs, int64_t n_obs,
                              const uint64_t* peer_slots, int rank, int world,
                              uint64_t seq, pbk_stream_t stream);
 
+/* One call for one evaluation: pbk_ba_camera_precompute into cam_blocks followed by
+ * pbk_ba_residual_jacobian (world == 1, peer_slots NULL, seq ignored) or
+ * pbk_ba_residual_jacobian_dist (world > 1), the second kernel launched with programmatic
+ * stream serialization so that its prologue (barrier setup, first record tiles and point
+ * gathers) overlaps the precompute instead of waiting behind it.  Same kernels, same
+ * arithmetic, bit-identical outputs.                                                     */
+PBK_API int pbk_ba_evaluate(const void* obs, int64_t n_obs,
+                             const float* points, int64_t n_points,
+                             const float* rvec, const float* tvec, int n_cams,
+                             double* cam_blocks,
+                             double fx, double fy, double cx, double cy,
+                             float* r, float* J_cam, float* J_pt,
+                             double* cost_partials, double* cost,
+                             const uint64_t* peer_slots, int rank, int world,
+                             uint64_t seq, pbk_stream_t stream);
+
 /* ------------------------------------------- next rows
  * DepthCamera.reconstruct, pybot/vision/camera_utils.py:1032-1036:
  *   out[b, y, x] = (xs[x]*d, ys[y]*d, d), d = depth[b, y*skip, x*skip], float64.

@@ -85,6 +85,8 @@ SIGNATURES = {
                                       _vp, _vp, _vp, _vp, _vp, _vp]),
     "pbk_ba_residual_jacobian_dist": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _d, _d, _d, _d,
                                            _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _u64, _vp]),
+    "pbk_ba_evaluate": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i, _vp, _d, _d, _d, _d,
+                             _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _u64, _vp]),
 }
 
 _lib = None

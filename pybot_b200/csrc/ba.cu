@@ -32,6 +32,10 @@ constexpr int kCam = PBK_BA_CAM_DOUBLES;   // R(9) t(3) dRdr(27) pad(1)
 __global__ void __launch_bounds__(128)
 ba_camera_precompute_kernel(const float* __restrict__ rvec, const float* __restrict__ tvec, int n,
                             double* __restrict__ blocks) {
+  // programmatic dependent launch: let the streaming kernel (pbk_ba_evaluate launches it with
+  // the programmatic-serialization attribute) start its prologue now; it executes
+  // griddepcontrol.wait before it reads the first camera block.  No-op otherwise.
+  asm volatile("griddepcontrol.launch_dependents;");
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
   const double rx = rvec[3 * c], ry = rvec[3 * c + 1], rz = rvec[3 * c + 2];
@@ -415,6 +419,11 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
     ring.wait(0);
     gather(0, pt);
   }
+  // Launched behind the camera precompute with programmatic stream serialization
+  // (pbk_ba_evaluate), everything above - barrier init, the first record tiles, the first
+  // point gathers, none of which the precompute writes - has overlapped its tail; the camera
+  // blocks are complete and visible after this.  A no-op for an ordinary launch.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int k = 0; k < my_tiles; ++k) process(k);
   if (lane == 0) tma_store_wait_all();
 
@@ -523,7 +532,7 @@ int pbk_ba_cost_slots(int64_t n_obs) {
 static int ba_launch(const void* obs, int64_t n_obs, const float* points, int64_t n_points,
                      const double* cam_blocks, int n_cams, double fx, double fy, double cx, double cy, float* r,
                      float* J_cam, float* J_pt, double* cost_partials, double* cost, const uint64_t* peer_slots,
-                     int rank, int world, uint64_t seq, pbk_stream_t stream) {
+                     int rank, int world, uint64_t seq, pbk_stream_t stream, bool after_precompute = false) {
   using namespace pbk;
   PBK_REQUIRE(n_obs >= 0 && n_points >= 0 && n_cams >= 0, PBK_EINVAL, "negative size");
   PBK_REQUIRE((cost == nullptr) || (cost_partials != nullptr), PBK_EINVAL, "cost needs cost_partials");
@@ -555,7 +564,22 @@ static int ba_launch(const void* obs, int64_t n_obs, const float* points, int64_
   const int grid = ba_grid(di, n_obs);
   const BaLaunch L = ba_variant();
   PBK_REQUIRE(grid > 0, PBK_ECUDA, "cannot opt in to %d bytes of shared memory", L.smem);
-  L.kernel<<<grid, kBaWarps * 32, L.smem, s>>>(P);
+  if (after_precompute) {
+    // may begin while the precompute kernel in front of it is still running (see the kernel)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kBaWarps * 32);
+    cfg.dynamicSmemBytes = L.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PBK_CUDA(cudaLaunchKernelEx(&cfg, L.kernel, P));
+  } else {
+    L.kernel<<<grid, kBaWarps * 32, L.smem, s>>>(P);
+  }
   PBK_CHECK_LAUNCH("ba_residual_jacobian_kernel");
   return PBK_OK;
 }
@@ -566,6 +590,17 @@ int pbk_ba_residual_jacobian(const void* obs, int64_t n_obs, const float* points
                              double* cost, pbk_stream_t stream) {
   return ba_launch(obs, n_obs, points, n_points, cam_blocks, n_cams, fx, fy, cx, cy, r, J_cam, J_pt,
                    cost_partials, cost, nullptr, 0, 1, 0, stream);
+}
+
+int pbk_ba_evaluate(const void* obs, int64_t n_obs, const float* points, int64_t n_points, const float* rvec,
+                    const float* tvec, int n_cams, double* cam_blocks, double fx, double fy, double cx, double cy,
+                    float* r, float* J_cam, float* J_pt, double* cost_partials, double* cost,
+                    const uint64_t* peer_slots, int rank, int world, uint64_t seq, pbk_stream_t stream) {
+  int rc = pbk_ba_camera_precompute(rvec, tvec, n_cams, cam_blocks, stream);
+  if (rc) return rc;
+  return ba_launch(obs, n_obs, points, n_points, cam_blocks, n_cams, fx, fy, cx, cy, r, J_cam, J_pt,
+                   cost_partials, cost, world > 1 ? peer_slots : nullptr, rank, world, seq, stream,
+                   /*after_precompute=*/n_cams > 0);
 }
 
 int pbk_ba_residual_jacobian_dist(const void* obs, int64_t n_obs, const float* points, int64_t n_points,

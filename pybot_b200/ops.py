@@ -802,30 +802,37 @@ class BAProblemDevice(object):
 
     def evaluate(self, events=None, exchange=None):
         """One residual + Jacobian evaluation (asynchronous on the current stream).
+        Without `events` it is ONE C-ABI call (pbk_ba_evaluate): the per-camera precompute,
+        then the streaming kernel launched with programmatic stream serialization so its
+        prologue overlaps the precompute.
         `events`: optional (start, end) CUDA events recorded around the streaming
-        kernel alone (the per-camera precompute stays outside), for roofline timing.
+        kernel alone (two separate calls, the precompute stays outside), for roofline timing.
         `exchange`: a distributed.PeerCostExchange - the kernel then also performs the
         sum-all-reduce of the cost over NVLink peer memory and self.cost is GLOBAL."""
         L = _ffi.lib()
         s = _ffi.stream_ptr()
+        out = (_ffi.ptr(self.r), _ffi.ptr(self.Jc), _ffi.ptr(self.Jp), _ffi.ptr(self.partials),
+               _ffi.ptr(self.cost))
+        K = (self.fx, self.fy, self.cx, self.cy)
+        if events is None:
+            ex = ((exchange.ptrs, exchange.rank, exchange.world, exchange.next_seq())
+                  if exchange is not None else (None, 0, 1, 0))
+            _ffi.check(L.pbk_ba_evaluate(
+                _ffi.ptr(self.obs), self.n_obs, _ffi.ptr(self.points), self.n_points,
+                _ffi.ptr(self.rvec), _ffi.ptr(self.tvec), self.n_cams, _ffi.ptr(self.cam_blocks),
+                *(K + out + ex + (s,))))
+            return self
         _ffi.check(L.pbk_ba_camera_precompute(_ffi.ptr(self.rvec), _ffi.ptr(self.tvec), self.n_cams,
                                               _ffi.ptr(self.cam_blocks), s))
-        if events is not None:
-            events[0].record()
+        events[0].record()
+        head = (_ffi.ptr(self.obs), self.n_obs, _ffi.ptr(self.points), self.n_points,
+                _ffi.ptr(self.cam_blocks), self.n_cams) + K + out
         if exchange is not None:
             _ffi.check(L.pbk_ba_residual_jacobian_dist(
-                _ffi.ptr(self.obs), self.n_obs, _ffi.ptr(self.points), self.n_points,
-                _ffi.ptr(self.cam_blocks), self.n_cams, self.fx, self.fy, self.cx, self.cy,
-                _ffi.ptr(self.r), _ffi.ptr(self.Jc), _ffi.ptr(self.Jp), _ffi.ptr(self.partials),
-                _ffi.ptr(self.cost), exchange.ptrs, exchange.rank, exchange.world, exchange.next_seq(), s))
+                *(head + (exchange.ptrs, exchange.rank, exchange.world, exchange.next_seq(), s))))
         else:
-            _ffi.check(L.pbk_ba_residual_jacobian(
-                _ffi.ptr(self.obs), self.n_obs, _ffi.ptr(self.points), self.n_points,
-                _ffi.ptr(self.cam_blocks), self.n_cams, self.fx, self.fy, self.cx, self.cy,
-                _ffi.ptr(self.r), _ffi.ptr(self.Jc), _ffi.ptr(self.Jp), _ffi.ptr(self.partials),
-                _ffi.ptr(self.cost), s))
-        if events is not None:
-            events[1].record()
+            _ffi.check(L.pbk_ba_residual_jacobian(*(head + (s,))))
+        events[1].record()
         return self
 
 

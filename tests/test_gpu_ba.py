@@ -55,6 +55,28 @@ def test_c4_shaped_problem_vs_oracle():
     _close(Jc.reshape(-1, 12), m[1].reshape(-1, 12))
 
 
+def test_one_call_evaluate_equals_two_launch_form():
+    """pbk_ba_evaluate (precompute + streaming kernel launched with programmatic stream
+    serialization, the kernel's prologue overlapping the precompute) against the two separate
+    calls: bit-identical, also when the cameras change between evaluations (the kernel must
+    not read camera blocks of the previous evaluation)."""
+    import torch
+    from pybot_b200 import ops
+    prob = syn.c4_problem(n_cams=300, n_points=40000)
+    p = ops.BAProblemDevice(*prob)
+    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    for it in range(4):
+        p.rvec.mul_(1.0 + 0.01 * it)
+        p.tvec.add_(0.001 * it)
+        p.evaluate()
+        got = [t.clone() for t in (p.r, p.Jc, p.Jp, p.cost)]
+        p.cam_blocks.zero_()
+        p.evaluate(events=ev)
+        for a, b in zip(got, (p.r, p.Jc, p.Jp, p.cost)):
+            assert torch.equal(a, b)
+        assert float(p.cost.item()) > 0
+
+
 @pytest.mark.parametrize("n_obs", [1, 31, 32, 33, 100, 257])
 def test_ragged_observation_counts(n_obs):
     from pybot_b200.vision.ba import ba_residual_jacobian
