@@ -81,6 +81,23 @@ def test_ragged_sizes(nq, nt):
     _check_against_model(q, t)
 
 
+@pytest.mark.parametrize("nq,nt", [(520, 150 * 256 + 200), (700, 160 * 256 + 128), (513, 149 * 256 + 129),
+                                   (2000, 148 * 256 + 1)])
+def test_ragged_last_tile_in_the_throughput_shape(nq, nt):
+    """Sizes that take the 4-queries-per-thread shape (packed 16-bit top-2 over 128-row blocks)
+    and end in a partial tile whose second block is ragged / empty / one row; ties planted across
+    the block and tile boundaries of that last tile.  Checked against the C restatement."""
+    from oracle import c_oracle
+    from pybot_b200.vision.matcher import knn_ratio_mutual
+    q, t = syn.low_entropy_pair(seed=nq + nt, nq=nq, nt=nt)
+    last = (nt // 256) * 256
+    for k, row in enumerate((last - 1, last, min(last + 127, nt - 1), min(last + 128, nt - 1), nt - 1)):
+        t[row] = q[k % 3]
+    idx, dist = knn_ratio_mutual(q, t)[:2]
+    ridx, rdist = c_oracle.hamming_knn2(q, t)
+    assert np.array_equal(idx, ridx) and np.array_equal(dist, rdist)
+
+
 @pytest.mark.parametrize("variant", ["0", "1", "2"])
 def test_both_popc_variants_agree(variant):
     """PBK_HAMMING_VARIANT selects 8-POPC / carry-save 4-POPC / carry-save with the packed
