@@ -313,6 +313,14 @@ PBK_API int pbk_sceneflow(const void* dX, int dtype, int H, int W,
 PBK_API int pbk_sampson_error(const double* F, const double* pts1, const double* pts2, int64_t n,
                               double* err, pbk_stream_t stream);
 
+/* epipolar_line, pybot/vision/camera_utils.py:352-357
+ * (cv2.computeCorrespondEpilines(x, 1, F)): F host 9 doubles row-major, pts device (n,2)
+ * float32 / float64 -> lines (n,3) of the same dtype, l = F [x y 1]^T scaled so that
+ * a^2 + b^2 = 1 (unscaled when a = b = 0); double arithmetic in OpenCV's order, one
+ * rounding to the point dtype.                                                      */
+PBK_API int pbk_epipolar_lines(const double* F, const void* pts, int dtype, int64_t n, void* lines,
+                               pbk_stream_t stream);
+
 /* triangulate_points, pybot/vision/camera_utils.py:108-116:
  * cv2.triangulatePoints(P1, P2, x1, x2).T dehomogenised.  P1, P2 host 12 doubles
  * (3x4 row-major); x1, x2 device (n,2), dtype in {F32, F64}; out device (n,3) of

@@ -344,6 +344,46 @@ def g8_rays_triangulate(ns):
     np.savez_compressed(os.path.join(OUT, "g8_rays_triangulate.npz"), **out)
 
 
+def g9_epipolar_helpers(ns):
+    """G9: the small callers either side of matching in the real reference - epipolar_line
+    (cv2.computeCorrespondEpilines), Camera.E, compute_essential / compute_epipole /
+    decompose_E, project_points / unproject / skew, and the frame helpers of
+    rigid_transform.py (tf_construct, tf_construct_3pt, tf_compose, normalize_vec, skew).
+    camera_utils.skew (:47-49) and with it Camera.E (:809-815) raise NameError in the reference
+    (`array` is never imported) and so does compute_epipole (:234-242, `linalg`): nothing to
+    pin for those three."""
+    import importlib
+    cu = importlib.import_module("pybot.vision.camera_utils")
+    rt = importlib.import_module("pybot.geometry.rigid_transform")
+    rng = np.random.default_rng(909)
+    K = syn.kitti_K()
+    mk = lambda *rp: ns.Camera.from_intrinsics_extrinsics(          # noqa: E731
+        ns.CameraIntrinsic(K, shape=(376, 1241)),
+        ns.CameraExtrinsic.from_rigid_transform(ns.RigidTransform.from_rpyxyz(*rp)))
+    rp1, rp2 = (0.01, -0.02, 0.03, 0.1, 0.0, 0.2), (-0.02, 0.05, 0.0, -0.4, 0.05, 0.9)
+    c1, c2 = mk(*rp1), mk(*rp2)
+    F = c1.F(c2)
+    x64 = rng.uniform([0, 0], [1241, 376], (500, 2))
+    x64[:3] = [[0, 0], [1240.5, 375.5], [607.1928, 185.2157]]
+    x32 = x64.astype(np.float32)
+    Fz = np.zeros((3, 3))
+    Fz[2] = [1.0, 2.0, 3.0]                                   # a = b = 0: lines left unscaled
+    E = cu.compute_essential(F, K)
+    R1, R2, t = cu.decompose_E(E)
+    X = rng.uniform([-10, -2, 5], [10, 2, 40], (50, 3))
+    v1, v2 = rt.normalize_vec(rng.normal(size=3)), rt.normalize_vec(rng.normal(size=3))
+    p3 = rng.normal(size=(3, 3))
+    sk, dV = rt.skew(v1, return_dv=True)
+    T3 = rt.tf_construct_3pt(p3[0], p3[1], p3[2])
+    np.savez_compressed(
+        os.path.join(OUT, "g9_epipolar_helpers.npz"), rp1=np.float64(rp1), rp2=np.float64(rp2), F=F, x64=x64,
+        lines64=cu.epipolar_line(F, x64), lines32=cu.epipolar_line(F, x32), Fz=Fz,
+        lines_z=cu.epipolar_line(Fz, x64[:8]), E=E, R1=R1, R2=R2,
+        t=t, X=X, proj=cu.project_points(X), unproj=cu.unproject(X[0]), deproj=cu.project(X[0]),
+        v1=v1, v2=v2, tfc=rt.tf_construct(v1, v2), skew_rt=sk, skew_dv=dV, p3=p3,
+        T3=T3.to_matrix(), tcomp=rt.tf_compose(R1, t))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
@@ -356,6 +396,7 @@ def main():
     g6_next_rows(ns)
     g7_epipolar_wire(ns)
     g8_rays_triangulate(ns)
+    g9_epipolar_helpers(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -362,3 +362,17 @@ def triangulate_points(P1, P2, x1, x2):
                   b[:, :1] * P2[2] - P2[0], b[:, 1:] * P2[2] - P2[1]], axis=1)     # (n,4,4)
     X = np.linalg.svd(A)[2][:, 3, :]
     return (X.astype(np.float32) if f32 else X).T
+
+
+def epipolar_lines(F, pts):
+    """cv2.computeCorrespondEpilines(pts, 1, F) restated (calib3d fundam.cpp): per point
+    l = F [x y 1]^T in double, products and sums rounded separately left to right, scaled by
+    1 / sqrt(a^2 + b^2) (by 1 when that is zero), one rounding to the point dtype."""
+    pts = np.asarray(pts)
+    f = np.asarray(F, np.float64).reshape(9)
+    x, y = pts[:, 0].astype(np.float64), pts[:, 1].astype(np.float64)
+    l = [(f[3 * r] * x + f[3 * r + 1] * y) + f[3 * r + 2] for r in range(3)]
+    nu = l[0] * l[0] + l[1] * l[1]
+    with np.errstate(divide="ignore"):
+        nu = np.where(nu != 0, 1.0 / np.sqrt(nu), 1.0)
+    return np.stack([l[0] * nu, l[1] * nu, l[2] * nu], 1).astype(pts.dtype)

@@ -274,6 +274,11 @@ def sampson_error(F, pts1, pts2):
     return (np.diag(x1.T.dot(Fx2)))**2 / denom
 
 
+def epipolar_line(F_10, x_0):
+    """camera_utils.py:352-357: the same cv2 call the reference makes."""
+    return cv2.computeCorrespondEpilines(x_0.reshape(-1, 1, 2), 1, F_10).reshape(-1, 3)
+
+
 def triangulate_points(P1, P2, pts1, pts2, use_cv2=True):
     """camera_utils.py:108-116."""
     if use_cv2 and cv2 is not None:

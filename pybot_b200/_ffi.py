@@ -75,6 +75,7 @@ SIGNATURES = {
     "pbk_depth_reconstruct_sparse": (_i, [_vp, _vp, _i64, _d, _d, _d, _vp, _vp]),
     "pbk_sceneflow": (_i, [_vp, _i, _i, _i, ctypes.POINTER(ProjectParams), _vp, _vp, _vp]),
     "pbk_sampson_error": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "pbk_epipolar_lines": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "pbk_triangulate_points": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp]),
     "pbk_undistort_points": (_i, [_vp, _i, _i, _i64, ctypes.POINTER(RayParams), _vp, _vp]),
     "pbk_camera_rays": (_i, [_vp, _i, _i, _i64, ctypes.POINTER(RayParams), _vp, _vp]),

@@ -296,6 +296,28 @@ sampson_error_kernel(const double* __restrict__ p1, const double* __restrict__ p
   err[i] = __ddiv_rn(__dmul_rn(d, d), denom);
 }
 
+// ------------------------------------------------------------- epipolar_line
+// camera_utils.py:352-357: cv2.computeCorrespondEpilines(x.reshape(-1,1,2), 1, F).reshape(-1,3).
+// OpenCV evaluates l = F [x y 1]^T in double with separately rounded products and sums
+// (left to right), scales by 1/sqrt(a^2 + b^2) (1 when that is zero) and rounds once to the
+// point dtype; the same operation order here makes the lines bit-identical.
+template <typename T>
+__global__ void __launch_bounds__(256)
+epipolar_lines_kernel(const T* __restrict__ pts, long long n, const __grid_constant__ SampsonParams P,
+                      T* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = (double)pts[2 * i], y = (double)pts[2 * i + 1];
+  double l[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    l[r] = __dadd_rn(__dadd_rn(__dmul_rn(P.F[3 * r], x), __dmul_rn(P.F[3 * r + 1], y)), P.F[3 * r + 2]);
+  double nu = __dadd_rn(__dmul_rn(l[0], l[0]), __dmul_rn(l[1], l[1]));
+  nu = (nu != 0.0) ? __ddiv_rn(1.0, __dsqrt_rn(nu)) : 1.0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) out[3 * i + r] = (T)__dmul_rn(l[r], nu);
+}
+
 // -------------------------------------------------------- triangulate_points
 // camera_utils.py:108-116: X = cv2.triangulatePoints(P1, P2, x1, x2).T ; X[:, :3] / X[:, 3].
 // Per point the 4x4 DLT matrix A = [x1*P1[2]-P1[0]; y1*P1[2]-P1[1]; x2*P2[2]-P2[0];
@@ -534,6 +556,25 @@ int pbk_sampson_error(const double* F, const double* pts1, const double* pts2, i
   PBK_REQUIRE(blocks < (1ll << 31), PBK_EINVAL, "n too large");
   sampson_error_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(pts1, pts2, n, P, err);
   PBK_CHECK_LAUNCH("sampson_error_kernel");
+  return PBK_OK;
+}
+
+int pbk_epipolar_lines(const double* F, const void* pts, int dtype, int64_t n, void* lines, pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(n >= 0 && F != nullptr, PBK_EINVAL, "bad arguments");
+  PBK_REQUIRE(dtype == PBK_F32 || dtype == PBK_F64, PBK_EINVAL, "points must be float32 or float64");
+  if (n == 0) return PBK_OK;
+  PBK_REQUIRE(pts && lines, PBK_EINVAL, "NULL device pointer");
+  SampsonParams P;
+  for (int i = 0; i < 9; ++i) P.F[i] = F[i];
+  const long long blocks = (n + 255) / 256;
+  PBK_REQUIRE(blocks < (1ll << 31), PBK_EINVAL, "n too large");
+  cudaStream_t s = as_stream(stream);
+  if (dtype == PBK_F32)
+    epipolar_lines_kernel<float><<<(int)blocks, 256, 0, s>>>(static_cast<const float*>(pts), n, P, static_cast<float*>(lines));
+  else
+    epipolar_lines_kernel<double><<<(int)blocks, 256, 0, s>>>(static_cast<const double*>(pts), n, P, static_cast<double*>(lines));
+  PBK_CHECK_LAUNCH("epipolar_lines_kernel");
   return PBK_OK;
 }
 

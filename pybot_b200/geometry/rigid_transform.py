@@ -18,6 +18,48 @@ from .quaternion import Quaternion
 from .. import ops
 
 
+def normalize_vec(v):
+    """v / ||v||_2 (reference rigid_transform.py:15-17)."""
+    return v * 1.0 / np.linalg.norm(v)
+
+
+def skew(v, return_dv=False):
+    """float32 cross-product matrix [v]_x, optionally with d vec([v]_x) / dv (9x3)
+    (reference rigid_transform.py:20-48)."""
+    sk = np.float32([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+    if not return_dv:
+        return sk
+    dV = np.float32([[0, 0, 0], [0, 0, -1], [0, 1, 0], [0, 0, 1], [0, 0, 0], [-1, 0, 0],
+                     [0, -1, 0], [1, 0, 0], [0, 0, 0]])
+    return sk, dV
+
+
+def tf_construct(vec1, vec2):
+    """Rotation whose columns are vx = v1, vy = vz x vx, vz = v1 x v2, each normalised
+    (reference rigid_transform.py:51-79)."""
+    assert np.linalg.norm(vec1) - 1.0 < 1e-6
+    assert np.linalg.norm(vec2) - 1.0 < 1e-6
+    v1, v2 = normalize_vec(vec1.copy()), normalize_vec(vec2.copy())
+    vz = normalize_vec(np.cross(v1, v2))
+    vy = normalize_vec(np.cross(vz, v1))
+    return np.vstack([v1, vy, vz]).T
+
+
+def tf_construct_3pt(p1, p2, p3, origin=None):
+    """Pose of the triad through three points (reference rigid_transform.py:82-91)."""
+    v1, v2 = p1 - p2, p2 - p3
+    R = tf_construct(v1 / np.linalg.norm(v1), v2 / np.linalg.norm(v2))
+    return RigidTransform.from_Rt(R, p2 if origin is None else origin)
+
+
+def tf_compose(R, t):
+    """[R t; 0 1] (reference rigid_transform.py:93-98)."""
+    T = np.eye(4)
+    T[:3, :3] = R.copy()
+    T[:3, 3] = t.copy()
+    return T
+
+
 def rpyxyz(roll, pitch, yaw, x, y, z, axes="rxyz"):
     return RigidTransform.from_rpyxyz(roll, pitch, yaw, x, y, z, axes=axes)
 

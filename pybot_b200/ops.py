@@ -650,6 +650,21 @@ def sampson_error(F, pts1, pts2):
     return _finish(err, on_dev)
 
 
+def epipolar_lines(F, pts):
+    """camera_utils.py:352-357 (cv2.computeCorrespondEpilines(x, 1, F)): (N,2) float32 /
+    float64 points -> (N,3) normalised lines of the same dtype."""
+    T = _ffi.require_cuda()
+    is32 = (pts.dtype == T.float32) if isinstance(pts, T.Tensor) else (np.asarray(pts).dtype == np.float32)
+    dt = np.float32 if is32 else np.float64
+    a, on_dev = _ffi.to_device(pts, dt)
+    a = a.reshape(-1, 2).contiguous()
+    Fh, Fp = _ffi.host_f64(F, 9)
+    out = T.empty((a.shape[0], 3), dtype=a.dtype, device=a.device)
+    _ffi.check(_ffi.lib().pbk_epipolar_lines(Fp, _ffi.ptr(a), _ffi.PBK_F32 if is32 else _ffi.PBK_F64,
+                                             a.shape[0], _ffi.ptr(out), _ffi.stream_ptr()))
+    return _finish(out, on_dev)
+
+
 def triangulate_points(P1, P2, pts1, pts2):
     """camera_utils.py:108-116: (N,2) correspondences + two 3x4 projection matrices
     -> (N,3) points, float32 or float64 like the inputs (cv2.triangulatePoints

@@ -74,6 +74,75 @@ def triangulate_points(cam1, pts1, cam2, pts2):
     return ops.triangulate_points(np.asarray(cam1.P), np.asarray(cam2.P), pts1, pts2)
 
 
+def colvec(vec):
+    """Reference :17-19."""
+    return vec.reshape(-1, 1)
+
+
+def rowvec(vec):
+    """Reference :22-24."""
+    return vec.reshape(1, -1)
+
+
+def unproject(a):
+    """Homogenise a vector (reference :27-29)."""
+    return np.append(a, 1)
+
+
+def project(a):
+    """De-homogenise a vector (reference :32-34)."""
+    return a[:-1] / float(a[-1])
+
+
+def project_points(pts):
+    """Rows [x, y, z] -> [x / z, y / z] (reference :42-44)."""
+    return pts[:, :2] / colvec(pts[:, 2])
+
+
+def skew(a):
+    """[a]_x with a x v = [a]_x v (reference :47-49)."""
+    return np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+
+
+def compute_essential(F, K):
+    """E = K^T F K (reference :229-231)."""
+    return (K.T).dot(F).dot(K)
+
+
+def compute_epipole(F):
+    """Right epipole: null vector of F scaled to e[2] = 1 (reference :234-242)."""
+    _, _, V = np.linalg.svd(F)
+    e = V[-1]
+    return e / e[2]
+
+
+def decompose_E(E):
+    """The two rotations and the unit translation of an essential matrix
+    (reference :177-203; no cheirality check there either)."""
+    U, _, Vt = np.linalg.svd(E)
+    W = np.float32([[0, -1, 0], [1, 0, 0], [0, 0, 1]])
+    t = U[:, 2] / np.linalg.norm(U[:, 2])
+    assert np.fabs(np.linalg.norm(t) - 1.0) < 1e-6
+    R1 = U.dot(W).dot(Vt)
+    if np.linalg.det(R1) < 0:
+        R1 = -R1
+    R2 = U.dot(W.T).dot(Vt)
+    if np.linalg.det(R2) < 0:
+        R2 = -R2
+    return R1, R2, t
+
+
+def recover_pose(E, pts1, pts2, K, distance_threshold, mask):
+    """Reference :206-207 raises too."""
+    raise NotImplementedError()
+
+
+def epipolar_line(F_10, x_0):
+    """l_1 = F_10 x_0, scaled to a^2 + b^2 = 1 (reference :352-357,
+    cv2.computeCorrespondEpilines(x, 1, F)): one GPU pass, bit-identical lines."""
+    return ops.epipolar_lines(F_10, x_0)
+
+
 def unproject_points(pts):
     """Reference :37-39."""
     pts = np.asarray(pts)
@@ -318,6 +387,14 @@ class Camera(CameraIntrinsic, CameraExtrinsic):
     def depth_from_projection(self, X):
         """z of p_cw * X (reference :736-743)."""
         return (self.extrinsics * X)[:, 2]
+
+    def E(self, other):
+        """[t]_x R of this camera (reference :809-815; `other` is unused there too)."""
+        return skew(self.t).dot(self.R)
+
+    def triangulate(self, pts, other_cam, other_pts):
+        """Reference :817-818."""
+        return triangulate_points(self, pts, other_cam, other_pts)
 
     def center(self):
         if self.cx is None:

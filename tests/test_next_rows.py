@@ -5,7 +5,7 @@ pin the CUDA path - bit-exact, all of it is either fp64 mul/div or integer."""
 import numpy as np
 import pytest
 
-from oracle import port
+from oracle import model, port
 
 
 @pytest.fixture(scope="module")
@@ -325,3 +325,87 @@ def test_triangulate_ragged_sizes_vs_port(n, g8):
     assert got.shape == (n, 3) and got.dtype == np.float64
     if n:
         np.testing.assert_allclose(got, port.triangulate_points(P1, P2, p1, p2), rtol=1e-9, atol=1e-9)
+
+
+# ------------------------------- epipolar lines and the small helpers around matching
+@pytest.fixture(scope="module")
+def g9(golden_dir):
+    return np.load(golden_dir + "/g9_epipolar_helpers.npz")
+
+
+def test_model_and_port_epipolar_lines_match_reference(g9):
+    """The numpy restatement of cv2.computeCorrespondEpilines is bit-identical to what the
+    reference's epipolar_line returned (float64 and float32 points, degenerate a = b = 0)."""
+    x32 = g9["x64"].astype(np.float32)
+    _same(model.epipolar_lines(g9["F"], g9["x64"]), g9["lines64"])
+    _same(model.epipolar_lines(g9["F"], x32), g9["lines32"])
+    _same(model.epipolar_lines(g9["Fz"], g9["x64"][:8]), g9["lines_z"])
+    if port.cv2 is not None:
+        _same(port.epipolar_line(g9["F"], g9["x64"]), g9["lines64"])
+        _same(port.epipolar_line(g9["F"], x32), g9["lines32"])
+
+
+def test_host_helpers_match_reference(g9):
+    """colvec / rowvec / unproject / project / project_points / compute_essential / decompose_E and
+    rigid_transform's normalize_vec / skew / tf_construct / tf_construct_3pt / tf_compose: same
+    values as the reference.  camera_utils.skew, Camera.E and compute_epipole raise NameError
+    there (missing imports), so those three are checked against their definitions."""
+    from pybot_b200 import synthetic as syn
+    from pybot_b200.geometry import rigid_transform as rt
+    from pybot_b200.vision import camera_utils as cu
+    X = g9["X"]
+    _same(cu.project_points(X), g9["proj"])
+    _same(cu.unproject(X[0]), g9["unproj"])
+    _same(cu.project(X[0]), g9["deproj"])
+    assert cu.colvec(X[0]).shape == (3, 1) and cu.rowvec(X[0]).shape == (1, 3)
+    E = cu.compute_essential(g9["F"], syn.kitti_K())
+    _same(E, g9["E"])
+    R1, R2, t = cu.decompose_E(E)
+    _same(R1, g9["R1"]), _same(R2, g9["R2"]), _same(t, g9["t"])
+    v1, v2 = g9["v1"], g9["v2"]
+    _same(rt.tf_construct(v1, v2), g9["tfc"])
+    sk, dV = rt.skew(v1, return_dv=True)
+    _same(sk, g9["skew_rt"]), _same(dV, g9["skew_dv"])
+    assert sk.dtype == np.float32
+    _same(rt.normalize_vec(v1 * 3.0), v1 * 3.0 / np.linalg.norm(v1 * 3.0))
+    p3 = g9["p3"]
+    _same(rt.tf_construct_3pt(p3[0], p3[1], p3[2]).to_matrix(), g9["T3"])
+    _same(rt.tf_compose(g9["R1"], g9["t"]), g9["tcomp"])
+    # the three the reference cannot run
+    w = np.array([0.3, -1.2, 2.0])
+    np.testing.assert_allclose(cu.skew(v1).dot(w), np.cross(v1, w), rtol=0, atol=1e-15)
+    e = cu.compute_epipole(g9["F"])
+    assert e[2] == 1.0 and np.abs(g9["F"].dot(e)).max() < 1e-9 * np.abs(g9["F"]).max() * np.abs(e).max()
+    c1, c2 = _cams(g9)
+    _same(c2.E(c1), cu.skew(c2.t).dot(c2.R))
+    with pytest.raises(NotImplementedError):
+        cu.recover_pose(E, None, None, None, None, None)
+
+
+@pytest.mark.gpu
+def test_epipolar_line_golden(g9):
+    """epipolar_line (cv2.computeCorrespondEpilines) on the GPU: bit-identical lines."""
+    from pybot_b200.vision.camera_utils import epipolar_line
+    l64 = epipolar_line(g9["F"], g9["x64"])
+    assert l64.dtype == np.float64 and l64.shape == (500, 3)
+    _same(l64, g9["lines64"])
+    l32 = epipolar_line(g9["F"], g9["x64"].astype(np.float32))
+    assert l32.dtype == np.float32
+    _same(l32, g9["lines32"])
+    _same(epipolar_line(g9["Fz"], g9["x64"][:8]), g9["lines_z"])
+    assert epipolar_line(g9["F"], np.zeros((0, 2))).shape == (0, 3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,dt", [(1, np.float64), (255, np.float32), (257, np.float64), (100_003, np.float32)])
+def test_epipolar_line_ragged_sizes_vs_model(g9, n, dt):
+    import torch
+    from pybot_b200 import ops
+    rng = np.random.default_rng(n)
+    x = rng.uniform([-50, -50], [1300, 400], (n, 2)).astype(dt)
+    want = model.epipolar_lines(g9["F"], x)
+    _same(ops.epipolar_lines(g9["F"], x), want)
+    got = ops.epipolar_lines(g9["F"], torch.from_numpy(x).cuda())         # device in -> device out
+    assert got.is_cuda and np.array_equal(got.cpu().numpy(), want)
+    if port.cv2 is not None:
+        _same(port.epipolar_line(g9["F"], x), want)
