@@ -355,17 +355,27 @@ __device__ unsigned long long g_ct_clk[16];
 // one prefix word per generation.
 constexpr int kCtWarps = 8;                          // compute warps
 constexpr int kCtThreads = kCtWarps * 32;            // 256 compute threads
-constexpr int kCtScan = 2;                           // scan warps (one look-back each in flight); must be <= buffers
+// Shape knobs (scripts/build_variants.py builds A/B libraries from them).  Measured on C2
+// (10 M points, flushed): 3 CTAs/SM x 3 buffers, one point at a time 0.0952 ms; 2 CTAs/SM x 5
+// buffers with the projection batched in pairs (80 registers, no spills) 0.0932 ms - shipped;
+// batched by four (spills) 0.0973, four scan warps 0.1096, 6 buffers + 3 scan warps 0.1239.
+#ifndef PBK_CT_SCAN
+#define PBK_CT_SCAN 2
+#endif
+#ifndef PBK_CT_BUFS
+#define PBK_CT_BUFS 5
+#endif
+#ifndef PBK_CT_MINB
+#define PBK_CT_MINB 2
+#endif
+constexpr int kCtScan = PBK_CT_SCAN;                           // scan warps (one look-back each in flight); must be <= buffers
 constexpr int kCtBlock = kCtThreads + 32 * kCtScan + 32;     // + the chain warp (works in CTA 0 only)
 constexpr int kCtPpt = 4;                            // points per thread
 constexpr int kCtTile = kCtThreads * kCtPpt;         // 1024 points per tile
 constexpr int kCtSegs = kCtPpt * kCtWarps;           // 32 (row, warp) segments
 // parked-output buffers (pipeline depth = buffers - 1 tiles of slack between a
-// tile's projection and its scatter).  Measured for float32: 5 buffers + 4 scan
-// warps at 2 CTAs/SM (4 tiles of slack) 0.105 ms against 0.102 ms for 3 buffers + 2
-// scan warps at 3 CTAs/SM - the extra slack is paid for with a third of the
-// compute warps, so the shallower pipeline with more CTAs stays.
-template <typename T> struct CtBufs { static constexpr int value = 3; };
+// tile's projection and its scatter); see the shape knobs above for what was measured.
+template <typename T> struct CtBufs { static constexpr int value = PBK_CT_BUFS; };
 static_assert(kCtScan <= CtBufs<float>::value, "a scan warp may only wait one mbarrier phase ahead");
 
 template <typename T>
@@ -376,7 +386,7 @@ struct CompactSmem {
 };
 
 template <typename T, bool DIST>
-__global__ void __launch_bounds__(kCtBlock, sizeof(T) == 4 ? 3 : 1)
+__global__ void __launch_bounds__(kCtBlock, sizeof(T) == 4 ? PBK_CT_MINB : 1)
 project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
                        double* __restrict__ depth, uint8_t* __restrict__ valid_out,
                        long long* __restrict__ count, unsigned long long* __restrict__ scratch,
@@ -524,6 +534,29 @@ project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
       UV* suv = reinterpret_cast<UV*>(dyn_smem + 2 * SM::kIn + q * SM::kOut);
       double* sdep = reinterpret_cast<double*>(dyn_smem + 2 * SM::kIn + q * SM::kOut + kCtTile * 2 * sizeof(T));
       const bool valid_words_tile = npts == kCtTile && (reinterpret_cast<uintptr_t>(valid_out) & 3) == 0;
+#ifndef PBK_CT_BATCH
+#define PBK_CT_BATCH 2
+#endif
+#if PBK_CT_BATCH > 0
+      constexpr int kB = PBK_CT_BATCH;          // points projected side by side (shared reciprocal slow path)
+      double ub[kCtPpt], vb[kCtPpt];
+#pragma unroll
+      for (int k0 = 0; k0 < kCtPpt; k0 += kB) {
+        double Xb[kB][3], u2[kB], v2[kB];
+#pragma unroll
+        for (int j = 0; j < kB; ++j) {
+          Xb[j][0] = (double)xin[k0 + j][0]; Xb[j][1] = (double)xin[k0 + j][1]; Xb[j][2] = (double)xin[k0 + j][2];
+        }
+        project_many<DIST, kB>(P, Xb, u2, v2);
+#pragma unroll
+        for (int j = 0; j < kB; ++j) { ub[k0 + j] = u2[j]; vb[k0 + j] = v2[j]; }
+      }
+#pragma unroll
+      for (int k = 0; k < kCtPpt; ++k) {
+        const int p = k * kCtThreads + tid;
+        const double Xp[3] = {(double)xin[k][0], (double)xin[k][1], (double)xin[k][2]};
+        const T uo = (T)ub[k], vo = (T)vb[k];
+#else
 #pragma unroll
       for (int k = 0; k < kCtPpt; ++k) {
         const int p = k * kCtThreads + tid;
@@ -531,6 +564,7 @@ project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
         double u, v;
         project_one<DIST>(P, Xp, u, v);
         const T uo = (T)u, vo = (T)v;
+#endif
         bool good = p < npts;
         if (need_depth) {
           const double dep = depth_of(P, Xp);
