@@ -4,7 +4,7 @@
 """
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-os.environ["PYBOT_B200_LIB"] = os.path.join(ROOT, "build", "libpbk_timing.so")
+os.environ["PYBOT_B200_LIB"] = os.environ.get("PYBOT_B200_LIB", os.path.join(ROOT, "scripts", "probes", "_bin", "libpbk_timing.so"))
 sys.path.insert(0, ROOT)
 import torch
 from pybot_b200 import _ffi, ops, synthetic as syn
