@@ -383,7 +383,7 @@ def run_c3(D, args):
     return res
 
 
-def cpu_baseline_c3(q, db, per_kf, sample_kf=500):
+def cpu_baseline_c3(q, db, per_kf, sample_kf=5000):
     """cv2.BFMatcher k=2 + ratio + mutual (what a pybot user runs) on a bounded
     sample of the same database, all host threads."""
     from oracle import port
