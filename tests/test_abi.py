@@ -44,6 +44,27 @@ def test_sass_uses_tma_bulk_copy_for_the_matcher():
     assert "UBLKCP" in body and "POPC" in body and "SYNCS" in body
 
 
+def test_sass_of_the_shipped_matcher_and_ba_kernels():
+    """What DESIGN.md claims about the shipped kernels is in the SASS: the database-scan matcher
+    runs its top-2 network on packed 16-bit keys (VIMNMX.U16x2) with 4 POPC per pair in the
+    unrolled loop; the BA kernel streams records in and Jacobians out with TMA bulk copies
+    (UBLKCP in both directions) and waits for its grid dependency (programmatic launch)."""
+    import subprocess
+    from pybot_b200 import _ffi
+    out = subprocess.run(["cuobjdump", "-sass", _ffi.LIB_PATH], capture_output=True, text=True).stdout
+    funcs = out.split("Function : ")
+    knn = [f for f in funcs if "hamming_knn2_kernelILi2ELi4E" in f.split("\n", 1)[0]]
+    assert len(knn) == 1
+    assert "VIMNMX.U16x2" in knn[0] and "UBLKCP" in knn[0]
+    assert knn[0].count("POPC") >= 64              # 4 rows x 4 queries x 4 POPC per unrolled iteration
+    ba = [f for f in funcs if "ba_residual_jacobian_kernel" in f.split("\n", 1)[0]]
+    assert len(ba) == 1
+    assert "UBLKCP.S.G" in ba[0] and "UBLKCP.G.S" in ba[0]      # TMA in and out
+    assert "ACQBULK" in ba[0]                                    # griddepcontrol.wait
+    pre = [f for f in funcs if "ba_camera_precompute_kernel" in f.split("\n", 1)[0]]
+    assert len(pre) == 1 and "PREEXIT" in pre[0]                 # griddepcontrol.launch_dependents
+
+
 def test_compute_without_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():
