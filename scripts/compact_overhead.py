@@ -1,4 +1,4 @@
-"""Compaction kernel: time vs size (fixed launch/memset/ramp overhead vs per-point cost).
+"""Projection kernels (compacting, masks, plain): time vs size (fixed launch/memset/ramp overhead vs per-point cost).
     python scripts/compact_overhead.py"""
 import os
 import sys
@@ -19,9 +19,12 @@ for n in (1024, 100_000, 1_000_000, 2_500_000, 5_000_000, 10_000_000, 20_000_000
     X[:, 0] = X[:, 0] * 80 - 40
     X[:, 1] = X[:, 1] * 6 - 3
     X[:, 2] = X[:, 2] * 78 + 2
-    for name, kw in (("compact", {}), ("masks", {"compact": False})):
-        pr = ops.Projector(T[:3, :3], T[:3, 3], syn.kitti_K(), shape=syn.KITTI_SHAPE, check_bounds=True,
-                           check_depth=True, return_depth=True, return_valid=True, **kw)
+    for name, kw in (("compact", {}), ("masks", {"compact": False}), ("plain", None)):
+        if kw is None:
+            pr = ops.Projector(T[:3, :3], T[:3, 3], syn.kitti_K())
+        else:
+            pr = ops.Projector(T[:3, :3], T[:3, 3], syn.kitti_K(), shape=syn.KITTI_SHAPE, check_bounds=True,
+                               check_depth=True, return_depth=True, return_valid=True, **kw)
         pr.run(X)
         torch.cuda.synchronize()
         ts = []
