@@ -60,6 +60,41 @@ def _traffic_entry(d, kernel):
     return next(v for k, v in ks.items() if k.startswith(kernel))
 
 
+def digest(*arrays):
+    """sha256 over the raw bytes of the result arrays (numpy or CUDA tensors), in order."""
+    import hashlib
+    h = hashlib.sha256()
+    for a in arrays:
+        if not isinstance(a, np.ndarray):
+            a = a.detach().cpu().numpy()
+        a = np.ascontiguousarray(a)
+        h.update(str(a.dtype).encode() + str(a.shape).encode())
+        h.update(a.view(np.uint8).reshape(-1).data)
+    return h.hexdigest()
+
+
+def source_sha(fname):
+    """sha256 (first 16 hex) of a kernel source file: ncu captures record it, so a capture
+    made from a different version of the kernel is reported as stale."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "pybot_b200", "csrc", fname), "rb") as f:
+            return hashlib.sha256(f.read()).hexdigest()[:16]
+    except OSError:
+        return None
+
+
+def ncu_traffic_stale(source_file):
+    """True when profiles/ncu_traffic.json was captured from another version of `source_file`
+    (or does not say), None without a capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            d = json.load(f)
+    except Exception:
+        return None
+    return d.get("source_sha", {}).get(source_file) != source_sha(source_file)
+
+
 def ncu_traffic_note(kernel, scale=1.0):
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
@@ -245,42 +280,37 @@ def ev_pair(torch):
     return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
-# ------------------------------------------------------- popc / alu peaks
+# ------------------------------------------------------- popc pipe peak
 def probe_peaks(D):
-    """Measured integer-pipe ceilings on this GPU, in this run (burst, ~20 ms
-    each): mode 0 = pure POPC chains -> popc-pipe peak; modes 2 / 3 / 4 = the
-    matcher's own inner loop (8-POPC / carry-save 4-POPC / carry-save with the packed
-    u16x2 top-2 network the kernel ships) over a resident shared-memory tile with
-    4 CTAs per SM and no global traffic -> the instruction-mix ceiling of the kernel;
-    mode 5 = the same loop with the top-2 network reduced to one min per two pairs
-    (what is left when selection is free: the XOR/CSA/POPC floor)."""
+    """Measured POPC-pipe peak of this GPU, in this run: independent POPC chains, 8 CTAs of
+    256 threads per SM, best of 3 launches of ~20 ms each (the pipe issues 16 POPC per clock
+    per SM: 148 x 16 x 1.965 GHz = 4.65 Tpopc/s nominal)."""
     from pybot_b200 import ops
     torch = D.torch
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    out = {}
-    for mode, ctas, iters in ((0, sms * 8, 4000), (2, sms * 4, 100), (3, sms * 4, 200), (4, sms * 4, 200),
-                              (5, sms * 4, 200)):
-        best = 0.0
-        for _ in range(3):
-            a, b = ev_pair(torch)
-            a.record()
-            n = ops.popc_probe(mode=mode, ctas=ctas, iters=iters)
-            b.record()
-            torch.cuda.synchronize()
-            best = max(best, n / (a.elapsed_time(b) * 1e-3))
-        out[mode] = best
-    return {"popc_per_s": out[0], "sm_count": sms,
-            "pairs_per_s_mix8popc": out[2] / 8.0, "pairs_per_s_mix4popc_csa": out[3] / 4.0,
-            "pairs_per_s_mix4popc_csa_u16x2": out[4] / 4.0, "pairs_per_s_no_selection": out[5] / 4.0}
+    best = 0.0
+    for _ in range(3):
+        a, b = ev_pair(torch)
+        a.record()
+        n = ops.popc_probe(mode=0, ctas=sms * 8, iters=4000)
+        b.record()
+        torch.cuda.synchronize()
+        best = max(best, n / (a.elapsed_time(b) * 1e-3))
+    return {"popc_per_s": best, "sm_count": sms}
 
 
 # ------------------------------------------------------------ workload C3
+# POPC.32 the shipped kernel issues per descriptor pair (carry-save compression of the eight XOR
+# words into four of weight 1, 1, 2, 4: profiles/r02_hamming_inner_loop.md counts them in the SASS)
+POPC_ISSUED_PER_PAIR = 4
+
+
 def run_c3(D, args):
     import torch
     from pybot_b200 import _ffi, ops
     from pybot_b200.distributed import ShardedKeyframeMatcher, shard_range
+    from pybot_b200.vision.matcher import BFMatcher
     nq, per_kf, nkf = 2000, 2000, args.keyframes
-    q_host, db_host = None, None
     lo_kf, hi_kf = shard_range(nkf, D.rank, D.world)
     # every rank generates the same seeded database and keeps its keyframe range
     q_np, db_np = syn.c3_database(nq=nq, n_keyframes=nkf, per_kf=per_kf)
@@ -316,6 +346,8 @@ def run_c3(D, args):
     sampler = ClockSampler(D.local).start() if D.rank == 0 else None
     total_ms, knn_ms = timed_steps(D, step, args.steps, args.warmup, flush)
     clocks = sampler.stop() if sampler else None
+    result = [_ffi.to_host(x) for x in step(None)]          # idx, dist, ratio_ok, mutual_ok, valid
+    m.check()
     variants = {}
     if D.world > 1:
         m_nccl = ShardedKeyframeMatcher(shard, lo_kf * per_kf, exchange="nccl")
@@ -326,11 +358,23 @@ def run_c3(D, args):
         variants["nccl_allgather_allreduce_between_kernels"] = {
             "Gpairs_per_s": float(nq) * nkf * per_kf * args.steps / (ms_n * 1e-3) / 1e9, "ms": ms_n / args.steps}
 
-    # end to end through the public API: pinned host queries in, numpy results out
+    # end to end through the array API: pinned host queries in, numpy results out
     def e2e_step(rec):
         idx, dist, r_ok, m_ok, valid = m.match(torch.from_numpy(q_pin).to("cuda", non_blocking=True))
         return [_ffi.to_host(x) for x in (idx, dist, valid)]
     e2e_ms, _ = timed_steps(D, e2e_step, args.steps, args.warmup, flush)
+
+    # ... and through the cv2-shaped facade: BFMatcher.knnMatch(host queries, k=2) over the
+    # resident (sharded) collection -> rows of DMatch (imgIdx / trainIdx / distance)
+    bf = BFMatcher.from_resident(shard, per_kf, shard_base=lo_kf * per_kf, n_images_total=nkf,
+                                 group=True if D.world > 1 else None)
+    if D.world > 1 and m._px is not None:
+        bf._sharded[0].use_exchange(m._px)                  # same queries: share the peer buffers
+
+    def e2e_knn_step(rec):
+        return bf.knnMatch(q_pin, k=2)
+    knn_api_ms, _ = timed_steps(D, e2e_knn_step, args.steps, args.warmup, flush)
+    api_rows = e2e_knn_step(None)
 
     pairs = float(nq) * nt_total
     launches = (6 if D.world == 1 else 9) * args.steps
@@ -346,46 +390,85 @@ def run_c3(D, args):
                    "state": "database resident in HBM; queries are the per-step input"},
         "e2e": {"value": pairs * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": "Gpairs/s",
                 "h2d_bytes_per_step": nq * 32,
-                "d2h_bytes_per_step": nq * (2 * 8 + 2 * 4 + 1)},
+                "d2h_bytes_per_step": nq * (2 * 8 + 2 * 4 + 1),
+                "api": "ShardedKeyframeMatcher.match (array API: idx, dist, valid as numpy)"},
+        "e2e_knnMatch": {"value": pairs * args.steps / (knn_api_ms * 1e-3) / 1e9, "unit": "Gpairs/s",
+                         "ms_per_step": knn_api_ms / args.steps,
+                         "h2d_bytes_per_step": nq * 32, "d2h_bytes_per_step": nq * (2 * 8 + 2 * 4 + 3),
+                         "api": "BFMatcher.knnMatch(host queries, k=2) over the resident collection -> "
+                                "KnnMatches (rows of DMatch, built on access)"},
         "gpu_launches": launches,
         "clocks": clocks,
         "exchange": ("top-2 keys and matched rows pushed to every peer from inside the kernels over NVLink peer "
                      "memory (symmetric memory); no NCCL call in the step" if D.world > 1 else "none (1 GPU)"),
         "variants": variants,
     }
+    # ------------------------------------------------------------ parity, in the record
+    dg = digest(*result)
+    parity = {"checked": "idx, dist, ratio_ok, mutual_ok, valid (all %d queries)" % nq}
+    api_ok = (len(api_rows) == nq and all(
+        [(d.imgIdx * per_kf + d.trainIdx, int(d.distance)) for d in api_rows[i]] ==
+        [(int(result[0][i, j]), int(result[1][i, j])) for j in range(2)] for i in range(0, nq, 97)))
+    parity["knnMatch_rows_equal_array_api"] = bool(api_ok)
+    if D.world > 1:
+        # every rank holds the same global result; rank 0 also scans the WHOLE database on its
+        # own GPU (outside the timed region) and requires bit-equality with the sharded result
+        all_dg = [None] * D.world
+        D.dist.all_gather_object(all_dg, dg)
+        parity["ranks_agree"] = bool(all(x == all_dg[0] for x in all_dg))
+        if D.rank == 0:
+            db_dev = torch.from_numpy(db_np).cuda()
+            whole = [_ffi.to_host(x) for x in ops.knn_ratio_mutual(q_dev, db_dev, 0.75)]
+            parity["vs_single_gpu_scan"] = bool(all(np.array_equal(a, b) for a, b in zip(result, whole)))
+            parity["rows"] = nt_total
+            parity["bit_exact"] = bool(parity["vs_single_gpu_scan"] and parity["ranks_agree"] and api_ok)
+            parity["reference"] = ("single-GPU scan of the whole database on rank 0 (itself checked against "
+                                   "cv2.BFMatcher in the N=1 line: equal result_digest)")
+            del db_dev
     if D.rank == 0:
         pk = probe_peaks(D)
         local_pairs = float(nq) * float(shard.shape[0])
-        popc_rate = local_pairs * 8 * args.steps / (knn_ms * 1e-3)
+        pair_rate = local_pairs * args.steps / (knn_ms * 1e-3)
         res["roofline"] = {
-            "bound": "popc", "kernel": "hamming_knn2_kernel (+ split merge)",
-            "achieved": popc_rate / 1e12, "peak": pk["popc_per_s"] / 1e12, "unit": "Tpopc/s",
-            "frac": popc_rate / pk["popc_per_s"],
+            "bound": "popc", "kernel": "hamming_knn2_kernel<2,4> (+ split merge)",
+            "achieved": pair_rate * POPC_ISSUED_PER_PAIR / 1e12, "peak": pk["popc_per_s"] / 1e12, "unit": "Tpopc/s",
+            "frac": pair_rate * POPC_ISSUED_PER_PAIR / pk["popc_per_s"],
+            "frac_algorithmic": pair_rate * 8 / pk["popc_per_s"],
             "traffic": ncu_traffic("hamming_knn2_kernel", scale=float(shard.shape[0]) / 2.5e6),
             "traffic_source": ncu_traffic_note("hamming_knn2_kernel", scale=float(shard.shape[0]) / 2.5e6),
-            "algorithmic": "8 POPC.32 per pair (256 bits); achieved = nq*nt_local*8 / kernel time",
+            "traffic_stale": ncu_traffic_stale("hamming.cu"),
+            "algorithmic": "frac = POPC.32 ISSUED (4 per pair: the eight XOR words are carry-save-compressed "
+                           "into four of weight 1,1,2,4; SASS counts in profiles/r02_hamming_inner_loop.md) / "
+                           "measured popc-pipe peak = utilisation of the binding (XU) pipe; frac_algorithmic "
+                           "= the SURVEY 8(d) figure, 8 POPC per 256-bit pair / the same peak (> 1 because "
+                           "the kernel issues half of them)",
             "peak_source": "pbk_popc_peak_probe mode 0, measured in this run (burst)",
             "kernel_ms": knn_ms / args.steps, "kernel_share_of_step": knn_ms / total_ms,
-            "note": "the kernel issues 4 POPC + 13 LOP3 + 1.5 VIMNMX.U16x2 + 4 IMAD per pair (carry-save "
-                    "compression of the 8 words; two queries' 16-bit keys share a register in the top-2 "
-                    "network), so the algorithmic popc rate can exceed the popc-pipe peak; the POPC "
-                    "(XU) pipe is the binding one at 0.25 clk/pair/SM - see mix ceilings (same inner "
-                    "loops on a resident smem tile)",
-            "mix_ceiling_gpairs": {"8popc": pk["pairs_per_s_mix8popc"] / 1e9,
-                                   "4popc_csa": pk["pairs_per_s_mix4popc_csa"] / 1e9,
-                                   "4popc_csa_u16x2": pk["pairs_per_s_mix4popc_csa_u16x2"] / 1e9,
-                                   "4popc_csa_no_selection": pk["pairs_per_s_no_selection"] / 1e9},
-            "frac_of_register_mix_ceiling": (local_pairs * args.steps / (knn_ms * 1e-3))
-            / pk["pairs_per_s_mix4popc_csa_u16x2"],
+            "Gpairs_per_s_kernel": pair_rate / 1e9,
         }
         if D.world == 1:
-            res["cpu_baseline"] = cpu_baseline_c3(q_np, db_np, per_kf)
+            base, cpu_result = cpu_baseline_c3(q_np, db_np, per_kf, args.parity_keyframes)
+            res["cpu_baseline"] = base
+            kf = min(args.parity_keyframes, nkf)
+            if kf == nkf:
+                mine = result
+            else:                           # the same rows on the GPU (outside the timed region)
+                mine = [_ffi.to_host(x) for x in ops.knn_ratio_mutual(q_dev, shard[:kf * per_kf], 0.75)]
+            same = [bool(np.array_equal(np.asarray(a).astype(np.int64), np.asarray(b).astype(np.int64)))
+                    for a, b in zip(mine, cpu_result)]
+            parity.update({"rows": kf * per_kf, "bit_exact": bool(all(same) and api_ok),
+                           "reference": "cv2.BFMatcher(NORM_HAMMING).add(%d keyframes).knnMatch(q, k=2) + ratio + "
+                                        "mutual (oracle.port) on the same rows: the cpu_baseline run" % kf,
+                           "per_output": dict(zip(("idx", "dist", "ratio_ok", "mutual_ok", "valid"), same))})
+        res["parity"] = parity
+        res["result_digest"] = dg
     return res
 
 
-def cpu_baseline_c3(q, db, per_kf, sample_kf=5000):
-    """cv2.BFMatcher k=2 + ratio + mutual (what a pybot user runs) on a bounded
-    sample of the same database, all host threads."""
+def cpu_baseline_c3(q, db, per_kf, sample_kf=10_000):
+    """cv2.BFMatcher k=2 + ratio + mutual (what a pybot user runs) on the first `sample_kf`
+    keyframes of the same database (default: all of them), all host threads.  Returns the
+    baseline record and the result arrays (the parity reference)."""
     from oracle import port
     try:
         import cv2
@@ -398,12 +481,12 @@ def cpu_baseline_c3(q, db, per_kf, sample_kf=5000):
     kfs = [db[i * per_kf:(i + 1) * per_kf] for i in range(sample_kf)]
     port.knn_ratio_mutual(q[:64], kfs[:2], 0.75)
     t0 = time.perf_counter()
-    port.knn_ratio_mutual(q, kfs, 0.75)
+    out = port.knn_ratio_mutual(q, kfs, 0.75)
     dt = time.perf_counter() - t0
-    return {"value": len(q) * sample_kf * per_kf / dt / 1e9, "unit": "Gpairs/s", "cores": threads,
-            "kind": "port",
-            "sample": "%s k=2 + ratio + mutual via oracle.port, %d q x %d rows (%d keyframes), %.1f s"
-                      % (engine, len(q), sample_kf * per_kf, sample_kf, dt)}
+    return ({"value": len(q) * sample_kf * per_kf / dt / 1e9, "unit": "Gpairs/s", "cores": threads,
+             "kind": "port",
+             "sample": "%s k=2 + ratio + mutual via oracle.port, %d q x %d rows (%d keyframes), %.1f s"
+                       % (engine, len(q), sample_kf * per_kf, sample_kf, dt)}, out)
 
 
 # ------------------------------------------------------------ workload C1
@@ -510,7 +593,20 @@ def run_c2(D, args, n=10_000_000):
     bpp = 12 + 1 + 16.0 * m_valid / n
     out["project_masks_compact"] = {"Mpts_per_s": n * args.steps / (ms2 * 1e-3) / 1e6,
                                     "ms": ms2 / args.steps, "bytes_per_pt": bpp, "valid_frac": m_valid / n,
-                                    "GBps": n * bpp * args.steps / (ms2 * 1e-3) / 1e9}
+                                    "GBps": n * bpp * args.steps / (ms2 * 1e-3) / 1e9,
+                                    "frac_hbm": n * bpp * args.steps / (ms2 * 1e-3) / 1e9 / hbm,
+                                    "kernel": "project_compact_kernel<float,false>: fp32 classification + X' "
+                                              "compaction, grid barrier, dense fp64 projection, per chunk",
+                                    "traffic": ncu_traffic("project_compact_kernel<float, 0>"),
+                                    "traffic_stale": ncu_traffic_stale("transform_project.cu")}
+    pr_mask_nc = ops.Projector(Rp, t, K, None, Rz=Rz, tz=tz, shape=syn.KITTI_SHAPE, check_bounds=True,
+                               check_depth=True, return_depth=True, return_valid=True, compact=False)
+
+    def masked_nc(rec):
+        return pr_mask_nc.run(X)
+    ms2b, _ = timed_steps(D, masked_nc, args.steps, args.warmup, flush)
+    out["project_masks_uncompacted"] = {"Mpts_per_s": n * args.steps / (ms2b * 1e-3) / 1e6, "ms": ms2b / args.steps,
+                                        "bytes_per_pt": 29, "GBps": n * 29.0 * args.steps / (ms2b * 1e-3) / 1e9}
 
     Y64 = torch.empty((n, 3), dtype=torch.float64, device="cuda")
 
@@ -531,12 +627,16 @@ def run_c2(D, args, n=10_000_000):
                    "l2": L2_NOTE},
         "variants": out,
         "e2e": {"value": n * args.steps / (ems * 1e-3) / 1e6, "unit": "Mpts/s",
-                "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": n * 8},
+                "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": n * 8,
+                "bound": "PCIe: 200 MB cross the host link per step (upload, kernel and download of 12 MB chunks "
+                         "overlapped on three streams); the kernel itself is %.0fx faster"
+                         % (out["project_plain"]["Mpts_per_s"] / (n * args.steps / (ems * 1e-3) / 1e6))},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "kernel": "project_points_kernel<float,false,false>",
                      "achieved": out["project_plain"]["GBps"], "peak": hbm, "unit": "GB/s",
                      "frac": out["project_plain"]["GBps"] / hbm, "traffic": ncu_traffic("project_points_kernel<float, 0, 0>"),
                      "traffic_source": ncu_traffic_note("project_points_kernel<float, 0, 0>"),
+                     "traffic_stale": ncu_traffic_stale("transform_project.cu"),
                      "peak_source": src, "algorithmic": "12 B in + 8 B out = 20 B/pt",
                      "copy_same_bytes_GBps": copy_at_size(torch, n * 12, n * 8)},
     }
@@ -565,22 +665,36 @@ def cpu_baseline_c2(X, cam):
 
 
 # ------------------------------------------------------------ workload C4
-def run_c4(D, args):
+def run_c4(D, args, weak=False):
+    """C4.  Strong scaling: the 4 M observations are split into equal contiguous chunks over the
+    ranks.  weak=True: every rank owns one whole C4 block (its own 1000 cameras' worth of 4 M
+    observations; cameras and points replicated as always), i.e. 4 M observations PER GPU - the
+    'large BA observation sets' case; the global cost is then world x the block's cost."""
     import torch
-    from pybot_b200 import _ffi
-    from pybot_b200.distributed import ShardedBA
+    from pybot_b200 import _ffi, ops
+    from pybot_b200.distributed import PeerCostExchange, ShardedBA
     hbm, src = measured_peaks()
     prob = syn.c4_problem()
     rv, tv, K, pts, oc, op, uv = prob
-    n_obs = len(oc)
-    sb = ShardedBA(*prob)
+    n_obs = len(oc) * (D.world if weak else 1)
+    if weak and D.world > 1:
+        sb = ShardedBA.__new__(ShardedBA)                  # this rank's block IS its chunk
+        sb.dist, sb.group, sb.world, sb.rank = D.dist, None, D.world, D.rank
+        sb.range = (D.rank * len(oc), (D.rank + 1) * len(oc))
+        sb.problem = ops.BAProblemDevice(*prob)
+        sb.exchange = PeerCostExchange(None)
+    else:
+        sb = ShardedBA(*prob)
     flush = make_flush(torch)
 
     def step(rec):
-        # one pbk_ba_evaluate call: camera precompute + streaming kernel (launched with
-        # programmatic stream serialization; world > 1: the cost all-reduce is fused into the
-        # kernel over NVLink peer memory)
+        # ONE kernel per evaluation (camera-sorted observations: the streaming kernel derives its
+        # CTAs' camera blocks in its prologue; world > 1: the cost all-reduce is fused into the
+        # same kernel over NVLink peer memory)
         return sb.evaluate()
+
+    def step_graph(rec):
+        return sb.evaluate(graph=True)
 
     def kernel_only(rec):
         a, b = ev_pair(torch)
@@ -590,10 +704,12 @@ def run_c4(D, args):
         return sb.problem.cost
     sampler = ClockSampler(D.local).start() if D.rank == 0 else None
     ms, _ = timed_steps(D, step, args.steps, args.warmup, flush)
+    ms_g, _ = timed_steps(D, step_graph, args.steps, args.warmup, flush)
     _, kms = timed_steps(D, kernel_only, args.steps, args.warmup, flush)
     clocks = sampler.stop() if sampler else None
-    variants = {}
-    if D.world > 1:
+    cost = sb.cost_host()
+    variants = {"cuda_graph_replay": {"Mobs_per_s": n_obs * args.steps / (ms_g * 1e-3) / 1e6, "ms": ms_g / args.steps}}
+    if D.world > 1 and not weak:
         sb_nccl = ShardedBA(*prob, exchange="nccl")
 
         def step_nccl(rec):
@@ -616,47 +732,101 @@ def run_c4(D, args):
     ems, _ = timed_steps(D, e2e, args.steps, args.warmup, flush)
     local_obs = P.n_obs
     gbps = local_obs * 96.0 * args.steps / (kms * 1e-3) / 1e9
+    step_ms = ms / args.steps
+    hbm_ms = local_obs * 96.0 / (hbm * 1e9) * 1e3
     res = {
         "metric": "ba_residual_jacobian", "unit": "Mobs/s", "value": n_obs * args.steps / (ms * 1e-3) / 1e6,
-        "ms_per_step": ms / args.steps, "scaling": "strong", "dtype": "f64 registers, f32 in/out",
-        "config": {"workload": "C4 BA residual + 2x6/2x3 Jacobians: 1000 cameras, 1M points, %d "
-                               "observations sharded over %d GPU(s)" % (n_obs, D.world),
+        "ms_per_step": step_ms, "scaling": "weak" if weak else "strong", "dtype": "f64 registers, f32 in/out",
+        "config": {"workload": "C4 BA residual + 2x6/2x3 Jacobians: 1000 cameras, 1M points, %d observations "
+                               "%s over %d GPU(s)" % (n_obs, "(one 4M block per GPU)" if weak else "sharded", D.world),
                    "l2": L2_NOTE},
         "e2e": {"value": n_obs * args.steps / (ems * 1e-3) / 1e6, "unit": "Mobs/s",
                 "h2d_bytes_per_step": int(rv.nbytes + tv.nbytes + pts.nbytes), "d2h_bytes_per_step": 8},
-        "gpu_launches": 2 * args.steps, "clocks": clocks,
+        "gpu_launches": args.steps, "clocks": clocks,
         "exchange": ("cost sum-all-reduce fused into the kernel over NVLink peer memory (symmetric memory), "
                      "no NCCL call in the step" if D.world > 1 else "none (1 GPU)"),
         "variants": variants,
-        "roofline": {"bound": "hbm", "kernel": "ba_residual_jacobian_kernel<2,2>, timed alone in its own loop (the "
-                                               "step also runs ba_camera_precompute_kernel, ~6 us, "
-                                               "overlapped with the kernel's prologue)", "achieved": gbps,
+        "limiter": {"hbm_ms_at_measured_peak": hbm_ms, "step_ms": step_ms, "fixed_ms": step_ms - hbm_ms,
+                    "note": ("step = HBM time of this rank's %d observations x 96 B + launch / ramp / tail / last-CTA cost "
+                             "reduction%s" % (local_obs, " + one NVLink release/acquire round trip and the wait for "
+                                              "the slowest rank" if D.world > 1 else ""))},
+        "roofline": {"bound": "hbm", "kernel": "ba_residual_jacobian_kernel<2,2> (one kernel per evaluation: camera "
+                                               "blocks derived in its prologue)", "achieved": gbps,
                      "peak": hbm, "unit": "GB/s", "frac": gbps / hbm,
+                     "frac_full_step": local_obs * 96.0 / (step_ms * 1e-3) / 1e9 / hbm,
                      "traffic": ncu_traffic("ba_residual_jacobian_kernel<2, 2>") if D.world == 1 else None,
                      "traffic_source": ncu_traffic_note("ba_residual_jacobian_kernel<2, 2>"),
+                     "traffic_stale": ncu_traffic_stale("ba.cu"),
                      "peak_source": src,
                      "algorithmic": "16 B read + 8 + 48 + 24 B written = 96 B/obs",
                      "kernel_ms": kms / args.steps,
                      "copy_same_bytes_GBps": copy_at_size(torch, local_obs * 16, local_obs * 80),
-                     "note": "83 % of the traffic is writes; a write-only stream of this size sustains "
-                             "~5.3 TB/s on B200 HBM3e (scripts/hbm_probe.py), below the copy figure"},
+                     "note": "frac: streaming kernel behind the stand-alone precompute, timed alone; "
+                             "frac_full_step: the one-kernel evaluation a caller gets.  83 % of the traffic is "
+                             "writes; a write-only stream of this size sustains ~5.3 TB/s on B200 HBM3e "
+                             "(scripts/hbm_probe.py), below the copy figure"},
     }
-    if D.rank == 0 and D.world == 1:
-        res["cpu_baseline"] = cpu_baseline_c4(prob)
+    # ------------------------------------------------------------ parity, in the record
+    whole = ops.BAProblemDevice(*prob).evaluate()             # the whole block on this GPU, outside the timed region
+    a, b = (0, len(oc)) if weak else sb.range
+    same = bool(torch.equal(P.r, whole.r[a:b]) and torch.equal(P.Jc, whole.Jc[a:b]) and torch.equal(P.Jp, whole.Jp[a:b]))
+    ref_cost = float(whole.cost.item()) * (D.world if weak else 1)
+    cost_ok = bool(abs(cost - ref_cost) <= 1e-12 * abs(ref_cost))
+    parity = {"slices_equal_single_gpu": same, "cost_rel_err_vs_single_gpu": abs(cost - ref_cost) / abs(ref_cost)}
+    if D.world > 1:
+        flags = [None] * D.world
+        D.dist.all_gather_object(flags, (same, cost))
+        same = all(f[0] for f in flags)
+        parity["ranks_agree_on_cost"] = bool(all(f[1] == flags[0][1] for f in flags))
+        parity["slices_equal_single_gpu"] = bool(same)
+        cost_ok = cost_ok and parity["ranks_agree_on_cost"]
+    if D.rank == 0:
+        res["result_digest"] = digest(whole.r, whole.Jc, whole.Jp)
+        parity["obs"] = int(n_obs)
+        if D.world == 1:
+            base, tol = cpu_baseline_c4(prob, whole=whole)
+            res["cpu_baseline"] = base
+            parity.update(tol)
+            parity["bit_exact"] = None
+            parity["within_tolerance"] = bool(tol["r_within_1e-4px_plus_1e-5rel"] and tol["max_rel_J"] <= 1e-5
+                                              and cost_ok and same)
+            parity["tolerance"] = "north star: residual 1e-4 px, Jacobians 1e-5 relative (fp32 outputs)"
+        else:
+            parity["bit_exact"] = bool(same and cost_ok)
+            parity["reference"] = "single-GPU evaluation of the whole problem (N=1 line: same result_digest)"
+        res["parity"] = parity
+    del whole
     return res
 
 
-def cpu_baseline_c4(prob, n_cams=100):
+def cpu_baseline_c4(prob, n_cams=100, whole=None):
+    """cv2.projectPoints with its Jacobian, looped per camera, on the observations of the first
+    `n_cams` cameras.  With `whole` (the GPU evaluation) also returns the worst differences."""
     from oracle import port
     rv, tv, K, pts, oc, op, uv = prob
     sel = oc < n_cams
     port.ba_residual_jacobian(rv, tv, K, pts, oc[:100], op[:100], uv[:100])
     t0 = time.perf_counter()
-    port.ba_residual_jacobian(rv, tv, K, pts, oc[sel], op[sel], uv[sel])
+    rr, rJc, rJp, rcost = port.ba_residual_jacobian(rv, tv, K, pts, oc[sel], op[sel], uv[sel])
     dt = time.perf_counter() - t0
-    return {"value": int(sel.sum()) / dt / 1e6, "unit": "Mobs/s", "cores": 1, "kind": "port",
+    base = {"value": int(sel.sum()) / dt / 1e6, "unit": "Mobs/s", "cores": 1, "kind": "port",
             "sample": "cv2.projectPoints with Jacobian looped per camera (oracle.port), first %d "
                       "cameras = %d obs, %.1f s" % (n_cams, int(sel.sum()), dt)}
+    if whole is None:
+        return base
+    idx = np.nonzero(sel)[0]
+    assert idx[-1] == len(idx) - 1                        # sorted by camera: a prefix
+    m = len(idx)
+    r, Jc, Jp = (x[:m].cpu().numpy().astype(np.float64) for x in (whole.r, whole.Jc, whole.Jp))
+
+    def rel(a, b):
+        a, b = a.reshape(m, -1), np.asarray(b, np.float64).reshape(m, -1)
+        return float((np.abs(a - b) / (np.abs(b).max(axis=1, keepdims=True) + 1e-30)).max())
+    return base, {"rows_vs_cv2": int(m), "max_abs_r_px": float(np.abs(r - rr).max()),
+                  "r_within_1e-4px_plus_1e-5rel": bool(np.allclose(r, rr, rtol=1e-5, atol=1e-4)),
+                  "max_rel_J": max(rel(Jc, rJc), rel(Jp, rJp)),
+                  "reference": "cv2.projectPoints (x, Jacobian) per camera on the first %d cameras' observations "
+                               "(oracle.port): the cpu_baseline run" % n_cams}
 
 
 # ------------------------------------------------------------ workload C5
@@ -708,12 +878,14 @@ def run_c5(D, args, batch=64):
                                     "GBps": npx * 16.0 * args.steps / (ms2 * 1e-3) / 1e9}},
         "e2e": {"value": eb * H * W * esteps / (ems * 1e-3) / 1e6, "unit": "Mpts/s",
                 "h2d_bytes_per_step": eb * H * W * 7, "d2h_bytes_per_step": eb * H * W * 15,
+                "bound": "PCIe: 22 B per point cross the host link (frame groups streamed on three streams)",
                 "note": "%d frames per e2e step (pinned host buffers)" % eb},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "kernel": "reproject_dense_kernel<float,true> (textured)",
                      "achieved": gbps, "peak": hbm, "unit": "GB/s", "frac": gbps / hbm,
                      "traffic": ncu_traffic("reproject_dense_kernel<float, 1>", scale=batch / 16.0),
                      "traffic_source": ncu_traffic_note("reproject_dense_kernel<float, 1>", scale=batch / 16.0),
+                     "traffic_stale": ncu_traffic_stale("reproject.cu"),
                      "peak_source": src, "algorithmic": "4+3 B in, 12+3 B out = 22 B/pt"},
     }
     if D.rank == 0:
@@ -909,6 +1081,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4", "c5"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--keyframes", type=int, default=10_000)
+    ap.add_argument("--parity-keyframes", type=int, default=10_000,
+                    help="keyframes of the C3 database the cv2 baseline / parity reference scans (N=1)")
     ap.add_argument("--no-also", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -936,7 +1110,8 @@ def main():
             try:
                 r = runners[w](D, sub)
                 also[w] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "e2e",
-                                             "roofline", "cpu_baseline", "variants") if k in r}
+                                             "roofline", "cpu_baseline", "variants", "limiter", "parity",
+                                             "result_digest") if k in r}
             except Exception as e:          # report, never hide
                 also[w] = {"error": repr(e)}
             import torch
@@ -949,6 +1124,24 @@ def main():
             also["next_rows"] = run_next_rows(D, sub)
         except Exception as e:
             also["next_rows"] = {"error": repr(e)}
+        line["also"] = also
+    if not args.no_also and D.world > 1 and args.workload == "c3":
+        # the other sharded path of BASELINE.json (config 4) on the same ranks: strong scaling
+        # (4 M observations split over the GPUs) and weak scaling (4 M observations per GPU)
+        also = {}
+        sub = argparse.Namespace(**vars(args))
+        sub.steps = max(args.steps, 20)
+        import torch
+        for name, weak in (("c4_strong", False), ("c4_weak", True)):
+            torch.cuda.empty_cache()
+            try:
+                r = run_c4(D, sub, weak=weak)
+                also[name] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "e2e",
+                                                "roofline", "variants", "limiter", "parity", "result_digest",
+                                                "exchange") if k in r}
+                also[name]["steps"] = sub.steps
+            except Exception as e:          # report, never hide
+                also[name] = {"error": repr(e)}
         line["also"] = also
     if D.rank == 0:
         print(json.dumps(line))

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PBK_VERSION 100
+#define PBK_VERSION 200
 
 #if defined(__GNUC__)
 #define PBK_API __attribute__((visibility("default")))
@@ -57,6 +57,12 @@ typedef void* pbk_stream_t;
 /* ---------------------------------------------------------------- runtime */
 PBK_API int pbk_version(void);
 PBK_API const char* pbk_last_error_string(void);
+/* Bound of the cross-GPU waits of the fused exchanges (pbk_hamming_*_dist,
+ * pbk_ba_*: world > 1), default ~2 s.  A peer that does not arrive within the bound
+ * makes the call fail: its `status` word is set to PBK_STATUS_PEER_TIMEOUT and the
+ * outputs are poisoned (no-match keys, zero rows, NaN cost) - never stale data.   */
+#define PBK_STATUS_PEER_TIMEOUT 1u
+PBK_API int pbk_set_exchange_timeout_ms(double ms);
 /* props[0]=SM count, [1]=cc major, [2]=cc minor, [3]=max smem/block optin,
  * [4]=L2 bytes, [5]=SM clock kHz, [6]=memory clock kHz, [7]=bus width bits */
 PBK_API int pbk_device_props(int device, int64_t props[8]);
@@ -129,9 +135,13 @@ typedef struct pbk_project_params {
  * depth    device (n,) float64 or NULL
  * valid    device (n,) uint8 or NULL (never compacted)
  * count    device int64[1] or NULL: number of valid points (needed if compact)
- * scratch  device, >= pbk_project_scratch_bytes(n) bytes, only if compact
+ * scratch  device, >= pbk_project_scratch_bytes(n, in_dtype) bytes, only if compact:
+ *          64 B of control words, the per-CTA counts and the L2-resident region the
+ *          classified points of one chunk are compacted into before they are projected
+ *          (two phases in one cooperative kernel; see csrc/transform_project.cu).
+ *          The environment variable PBK_COMPACT_CHUNK_MB (default 40) sets the chunk size.
  */
-PBK_API size_t pbk_project_scratch_bytes(int64_t n);
+PBK_API size_t pbk_project_scratch_bytes(int64_t n, int in_dtype);
 PBK_API int pbk_project_points(const void* X, int in_dtype, int64_t n,
                        const pbk_project_params* params,
                        void* uv, double* depth, uint8_t* valid,
@@ -194,17 +204,22 @@ PBK_API int pbk_hamming_ratio_mutual(const uint64_t* keys, const uint64_t* rev_k
  * seq          call counter, identical on all ranks, 1, 2, 3 ... ; one value is
  *              shared by the knn2_dist and gather_best_dist calls of a frame
  * done_counter device uint32[1], zero before the first call
+ * status       uint32[1] the kernels can write (device memory, or pinned host memory
+ *              mapped into the device so the host can poll it without a copy), zero
+ *              before the first call; set to PBK_STATUS_PEER_TIMEOUT when a peer's data
+ *              did not arrive within the bound - the call's outputs are then all
+ *              "no match" (keys PBK_KEY_NONE, rows zero).  May be NULL.
  * knn2_dist:        keys (nq,2) = GLOBAL top-2 on every rank
  * gather_best_dist: rows (nq,32) = the matched train rows on every rank          */
 PBK_API size_t pbk_hamming_exchange_words(int64_t nq, int world);
 PBK_API int pbk_hamming_knn2_dist(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt,
                      uint64_t train_base, uint64_t* keys, void* scratch,
                      const uint64_t* peer_bufs, int rank, int world, uint64_t seq,
-                     uint32_t* done_counter, pbk_stream_t stream);
+                     uint32_t* done_counter, uint32_t* status, pbk_stream_t stream);
 PBK_API int pbk_hamming_gather_best_dist(const uint8_t* t, int64_t nt, uint64_t train_base,
                      const uint64_t* keys, int64_t nq, uint8_t* rows,
                      const uint64_t* peer_bufs, int rank, int world, uint64_t seq,
-                     uint32_t* done_counter, pbk_stream_t stream);
+                     uint32_t* done_counter, uint32_t* status, pbk_stream_t stream);
 
 /* popc-pipe peak probe (measurement only): ctas x 256 threads run `iters`
  * rounds of mode 0: independent POPC chains; 1: POPC + one LOP3 each;
@@ -224,7 +239,8 @@ PBK_API int pbk_popc_peak_probe(int mode, int ctas, int iters, uint32_t* sink,
  *   cam_blocks (C, PBK_BA_CAM_DOUBLES) f64 device: R(9) t(3) dR/dr(27).
  * ba_residual_jacobian: obs (O,4) {int32 cam, int32 pt, f32 u, f32 v} device,
  *   points (P,3) f32 device -> r (O,2) f32, J_cam (O,2,6) f32, J_pt (O,2,3)
- *   f32 (any may be NULL), cost_partials (pbk_ba_cost_slots(O),) f64 device, ZERO on the
+ *   f32 (any may be NULL), cost_partials (pbk_ba_cost_slots(O),) f64 device (per-CTA sums,
+ *   an arrival counter and the device-resident call sequence), ZERO on the
  *   first call (the kernel leaves it reusable), cost (1,) f64 device = sum ||r||^2
  *   (deterministic: per-CTA partials added in fixed order by the last CTA).
  */
@@ -249,9 +265,14 @@ PBK_API int pbk_ba_residual_jacobian(const void* obs, int64_t n_obs,
  *             exchange buffer AS MAPPED INTO THIS PROCESS (e.g. torch symmetric
  *             memory buffer_ptrs), >= PBK_BA_EXCHANGE_WORDS(world) uint64, zeroed
  *             before the first call
- * seq         call counter, identical on all ranks, 1, 2, 3 ...
+ * seq         call counter, identical on all ranks, 1, 2, 3 ... ; 0 = use the
+ *             device-resident counter kept behind cost_partials (every rank then
+ *             simply makes the same number of calls; this is what lets a captured
+ *             CUDA graph replay the call)
+ * status      uint32[1] the kernel can write (device or mapped pinned host memory), zero
+ *             before the first call, set to PBK_STATUS_PEER_TIMEOUT on a timeout; may be NULL
  * cost        receives the GLOBAL cost on every rank (NaN if a peer did not
- *             arrive within ~2 s).  Every rank must own >= 1 observation.      */
+ *             arrive within the bound).  Every rank must own >= 1 observation.  */
 #define PBK_BA_EXCHANGE_WORDS(world) (4 * (world))
 PBK_API int pbk_ba_residual_jacobian_dist(const void* obs, int64_t n_obs,
                              const float* points, int64_t n_points,
@@ -260,15 +281,20 @@ PBK_API int pbk_ba_residual_jacobian_dist(const void* obs, int64_t n_obs,
                              float* r, float* J_cam, float* J_pt,
                              double* cost_partials, double* cost,
                              const uint64_t* peer_slots, int rank, int world,
-                             uint64_t seq, pbk_stream_t stream);
+                             uint64_t seq, uint32_t* status, pbk_stream_t stream);
 
-/* One call for one evaluation: pbk_ba_camera_precompute into cam_blocks followed by
- * pbk_ba_residual_jacobian (world == 1, peer_slots NULL, seq ignored) or
- * pbk_ba_residual_jacobian_dist (world > 1), the second kernel launched with programmatic
- * stream serialization so that its prologue (barrier setup, first record tiles and point
- * gathers) overlaps the precompute instead of waiting behind it.  Same kernels, same
- * arithmetic, bit-identical outputs.                                                     */
-PBK_API int pbk_ba_evaluate(const void* obs, int64_t n_obs,
+/* One call for one evaluation, straight from rvec / tvec.
+ * obs_sorted != 0 (the observations are sorted by camera index - the caller checks): ONE
+ *   kernel.  Every CTA of the streaming kernel derives, in its prologue, the camera blocks
+ *   its own observation range references (its eight warps, one camera each, lane-parallel
+ *   Rodrigues) into cam_blocks while its first record tiles are in flight - no precompute
+ *   launch, no launch boundary inside the step; only the blocks of referenced cameras are
+ *   (re)written.
+ * obs_sorted == 0: pbk_ba_camera_precompute followed by the streaming kernel launched with
+ *   programmatic stream serialization so that its prologue overlaps the precompute.
+ * world == 1: peer_slots NULL, seq / status ignored.  Same arithmetic on both routes (the
+ * camera block is one device function), bit-identical outputs.                            */
+PBK_API int pbk_ba_evaluate(const void* obs, int64_t n_obs, int obs_sorted,
                              const float* points, int64_t n_points,
                              const float* rvec, const float* tvec, int n_cams,
                              double* cam_blocks,
@@ -276,7 +302,7 @@ PBK_API int pbk_ba_evaluate(const void* obs, int64_t n_obs,
                              float* r, float* J_cam, float* J_pt,
                              double* cost_partials, double* cost,
                              const uint64_t* peer_slots, int rank, int world,
-                             uint64_t seq, pbk_stream_t stream);
+                             uint64_t seq, uint32_t* status, pbk_stream_t stream);
 
 /* ------------------------------------------- next rows
  * DepthCamera.reconstruct, pybot/vision/camera_utils.py:1032-1036:

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("PYBOT_B200_LIB", os.path.join(_HERE, "libpybot_b200.s
 PBK_OK, PBK_EINVAL, PBK_ECUDA, PBK_EALIGN, PBK_EUNSUPPORTED = 0, -1, -2, -3, -4
 PBK_U8, PBK_S16, PBK_S32, PBK_F32, PBK_F64, PBK_U16 = 0, 1, 2, 3, 4, 5
 PBK_KEY_NONE = 0xFFFFFFFFFFFFFFFF
+PBK_STATUS_PEER_TIMEOUT = 1
 PBK_BA_CAM_DOUBLES = 40
 
 _NP2PBK = {np.dtype(np.uint8): PBK_U8, np.dtype(np.int16): PBK_S16,
@@ -59,7 +60,8 @@ SIGNATURES = {
     "pbk_reproject_disp": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "pbk_reproject_sparse": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "pbk_transform_points": (_i, [_vp, _i, _i64, _vp, _d, _vp, _i, _vp]),
-    "pbk_project_scratch_bytes": (_sz, [_i64]),
+    "pbk_set_exchange_timeout_ms": (_i, [_d]),
+    "pbk_project_scratch_bytes": (_sz, [_i64, _i]),
     "pbk_project_points": (_i, [_vp, _i, _i64, ctypes.POINTER(ProjectParams),
                                 _vp, _vp, _vp, _vp, _vp, _vp]),
     "pbk_hamming_plan": (_i, [_i64, _i64, ctypes.POINTER(_i), ctypes.POINTER(_sz)]),
@@ -68,8 +70,8 @@ SIGNATURES = {
     "pbk_hamming_gather_best": (_i, [_vp, _i64, _u64, _vp, _i64, _vp, _vp]),
     "pbk_hamming_ratio_mutual": (_i, [_vp, _vp, _i64, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pbk_hamming_exchange_words": (_sz, [_i64, _i]),
-    "pbk_hamming_knn2_dist": (_i, [_vp, _i64, _vp, _i64, _u64, _vp, _vp, _vp, _i, _i, _u64, _vp, _vp]),
-    "pbk_hamming_gather_best_dist": (_i, [_vp, _i64, _u64, _vp, _i64, _vp, _vp, _i, _i, _u64, _vp, _vp]),
+    "pbk_hamming_knn2_dist": (_i, [_vp, _i64, _vp, _i64, _u64, _vp, _vp, _vp, _i, _i, _u64, _vp, _vp, _vp]),
+    "pbk_hamming_gather_best_dist": (_i, [_vp, _i64, _u64, _vp, _i64, _vp, _vp, _i, _i, _u64, _vp, _vp, _vp]),
     "pbk_popc_peak_probe": (_i, [_i, _i, _i, _vp, ctypes.POINTER(_d), _vp]),
     "pbk_depth_reconstruct": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pbk_depth_reconstruct_sparse": (_i, [_vp, _vp, _i64, _d, _d, _d, _vp, _vp]),
@@ -85,9 +87,9 @@ SIGNATURES = {
     "pbk_ba_residual_jacobian": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _d, _d, _d, _d,
                                       _vp, _vp, _vp, _vp, _vp, _vp]),
     "pbk_ba_residual_jacobian_dist": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _d, _d, _d, _d,
-                                           _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _u64, _vp]),
-    "pbk_ba_evaluate": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i, _vp, _d, _d, _d, _d,
-                             _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _u64, _vp]),
+                                           _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _u64, _vp, _vp]),
+    "pbk_ba_evaluate": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _vp, _i, _vp, _d, _d, _d, _d,
+                             _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _u64, _vp, _vp]),
 }
 
 _lib = None
@@ -186,6 +188,27 @@ def to_host(tensor):
     out.copy_(tensor, non_blocking=True)
     t.cuda.current_stream().synchronize()
     return out.numpy()
+
+
+class StatusWord(object):
+    """uint32 status word the fused-exchange kernels write on failure: pinned host memory
+    mapped into the device (UVA), so the host polls it without a copy or a synchronisation."""
+
+    def __init__(self):
+        t = require_cuda()
+        self.word = t.zeros(4, dtype=t.int32, pin_memory=True)
+        self.ptr = ctypes.c_void_p(self.word.data_ptr())
+
+    def check(self, what):
+        """Raises if a kernel reported a failure (call after the stream has been synchronised,
+        or at the next call: the word is sticky until cleared here)."""
+        code = int(self.word[0])
+        if code:
+            self.word[0] = 0
+            if code == PBK_STATUS_PEER_TIMEOUT:
+                raise PbkError("libpybot_b200: %s: a peer rank did not arrive within the exchange timeout "
+                               "(outputs of that call are poisoned: no-match keys / zero rows / NaN cost)" % what)
+            raise PbkError("libpybot_b200: %s failed with device status %d" % (what, code))
 
 
 def pinned_empty(shape, dtype):

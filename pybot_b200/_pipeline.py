@@ -53,13 +53,31 @@ def _side_streams(device):
     return _streams[key]
 
 
-def plan(n_rows, bytes_per_row, row_align=1, chunk_bytes=None):
-    """Chunk boundaries [(lo, hi), ...] for n_rows rows; one chunk when small."""
+def pointer_row_align(plane_row_bytes):
+    """Smallest row count r such that r * b is a multiple of 16 for every per-row byte stride b:
+    the kernels require 16-byte aligned pointers, and a chunk starts at row lo of every plane."""
+    import math
+    r = 1
+    for b in plane_row_bytes:
+        b = int(b)
+        if b > 0:
+            need = 16 // math.gcd(16, b)
+            r = r * need // math.gcd(r, need)
+    return r
+
+
+def plan(n_rows, bytes_per_row, row_align=1, chunk_bytes=None, plane_row_bytes=()):
+    """Chunk boundaries [(lo, hi), ...] for n_rows rows; one chunk when small.
+    plane_row_bytes: the per-row byte stride of EVERY input and output plane the chunks are
+    sliced from (a KITTI uint8 frame is 466616 B: chunks must then start on even frames)."""
+    import math
     total = n_rows * bytes_per_row
     if n_rows <= 0:
         return []
     if total < MIN_BYTES:
         return [(0, n_rows)]
+    pa = pointer_row_align(plane_row_bytes)
+    row_align = row_align * pa // math.gcd(row_align, pa)
     k = int(min(MAX_CHUNKS, max(2, total // (chunk_bytes or CHUNK_BYTES))))
     rows = -(-n_rows // k)
     rows = -(-rows // row_align) * row_align

@@ -29,6 +29,55 @@ constexpr int kBaWarps = 8;
 constexpr int kBaMaxWorld = 16;
 constexpr int kCam = PBK_BA_CAM_DOUBLES;   // R(9) t(3) dRdr(27) pad(1)
 
+// One camera block = R (9), t (3), dR/dr (27), pad: OpenCV's Rodrigues closed form in fp64,
+// computed by ONE WARP (entry e of the 36 on lane e % 32): the latency is that of a single
+// sincos + a dozen dependent fp64 operations instead of a 300-operation serial chain.  Used
+// by the stand-alone precompute kernel and by the prologue of the streaming kernel (same
+// function, same SASS: the two routes give bit-identical blocks).
+__device__ __forceinline__ double sel3(int i, double a, double b, double c) { return i == 0 ? a : (i == 1 ? b : c); }
+
+__device__ __noinline__ void ba_camera_block_warp(const float* __restrict__ rvec, const float* __restrict__ tvec,
+                                                  int c, double* __restrict__ o, int lane) {
+  const double rx = rvec[3 * c], ry = rvec[3 * c + 1], rz = rvec[3 * c + 2];
+  if (lane < 3) o[9 + lane] = (double)tvec[3 * c + lane];
+  if (lane == 3) o[39] = 0.0;
+  const double theta = sqrt(rx * rx + ry * ry + rz * rz);
+  const bool tiny = theta < 2.220446049250313e-16;
+  double s = 0.0, c_ = 1.0;
+  if (!tiny) sincos(theta, &s, &c_);
+  const double c1 = 1.0 - c_, itheta = tiny ? 0.0 : 1.0 / theta;
+  const double u0 = rx * itheta, u1 = ry * itheta, u2 = rz * itheta;
+  for (int e = lane; e < 36; e += 32) {
+    const int k = e < 9 ? e : (e - 9) % 9, i = e < 9 ? 0 : (e - 9) / 9;
+    const int row = k / 3, col = k % 3;
+    const double Ik = row == col ? 1.0 : 0.0;
+    const double ur = sel3(row, u0, u1, u2), uc = sel3(col, u0, u1, u2);
+    const double rrt = ur * uc;
+    // [u]x: entry (row, col) = -+ u_m, m the third index; sign - for (0,1) (1,2) (2,0)
+    const int m = 3 - row - col;
+    const double sgn = row == col ? 0.0 : (((col - row + 3) % 3 == 1) ? -1.0 : 1.0);
+    const double r_x = row == col ? 0.0 : sgn * sel3(m, u0, u1, u2);
+    double v;
+    if (e < 9) {
+      v = tiny ? Ik : c_ * Ik + c1 * rrt + s * r_x;
+    } else {
+      const double d_r_x = (row != col && m == i) ? sgn : 0.0;          // d [u]x / d u_i
+      if (tiny) {
+        v = d_r_x;
+      } else {
+        const double ri = sel3(i, u0, u1, u2);
+        const double drrt = (row == i ? uc : 0.0) + (col == i ? ur : 0.0);
+        const double a0 = -s * ri, a1 = (s - 2 * c1 * itheta) * ri, a2 = c1 * itheta,
+                     a3 = (c_ - s * itheta) * ri, a4 = s * itheta;
+        v = a0 * Ik + a1 * rrt + a2 * drrt + a3 * r_x + a4 * d_r_x;
+      }
+    }
+    o[e < 9 ? e : e + 3] = v;
+  }
+}
+
+// stand-alone precompute (callers that keep the two-kernel route, unsorted observations):
+// one warp per camera
 __global__ void __launch_bounds__(128)
 ba_camera_precompute_kernel(const float* __restrict__ rvec, const float* __restrict__ tvec, int n,
                             double* __restrict__ blocks) {
@@ -36,62 +85,33 @@ ba_camera_precompute_kernel(const float* __restrict__ rvec, const float* __restr
   // the programmatic-serialization attribute) start its prologue now; it executes
   // griddepcontrol.wait before it reads the first camera block.  No-op otherwise.
   asm volatile("griddepcontrol.launch_dependents;");
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (c >= n) return;
-  const double rx = rvec[3 * c], ry = rvec[3 * c + 1], rz = rvec[3 * c + 2];
-  double* o = blocks + (long long)c * kCam;
-  o[9] = tvec[3 * c];
-  o[10] = tvec[3 * c + 1];
-  o[11] = tvec[3 * c + 2];
-  o[39] = 0.0;
-  const double theta = sqrt(rx * rx + ry * ry + rz * rz);
-  double R[9], J[27];
-  if (theta < 2.220446049250313e-16) {
-    for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
-    for (int i = 0; i < 27; ++i) J[i] = 0.0;
-    J[5] = -1; J[7] = 1; J[9 + 2] = 1; J[9 + 6] = -1; J[18 + 1] = -1; J[18 + 3] = 1;
-  } else {
-    double s, c_;
-    sincos(theta, &s, &c_);
-    const double c1 = 1.0 - c_, itheta = 1.0 / theta;
-    const double u[3] = {rx * itheta, ry * itheta, rz * itheta};
-    const double rrt[9] = {u[0] * u[0], u[0] * u[1], u[0] * u[2], u[0] * u[1], u[1] * u[1],
-                           u[1] * u[2], u[0] * u[2], u[1] * u[2], u[2] * u[2]};
-    const double r_x[9] = {0, -u[2], u[1], u[2], 0, -u[0], -u[1], u[0], 0};
-    const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    for (int k = 0; k < 9; ++k) R[k] = c_ * I[k] + c1 * rrt[k] + s * r_x[k];
-    const double drrt[27] = {u[0] + u[0], u[1], u[2], u[1], 0, 0, u[2], 0, 0,
-                             0, u[0], 0, u[0], u[1] + u[1], u[2], 0, u[2], 0,
-                             0, 0, u[0], 0, 0, u[1], u[0], u[1], u[2] + u[2]};
-    const double d_r_x[27] = {0, 0, 0, 0, 0, -1, 0, 1, 0,
-                              0, 0, 1, 0, 0, 0, -1, 0, 0,
-                              0, -1, 0, 1, 0, 0, 0, 0, 0};
-    for (int i = 0; i < 3; ++i) {
-      const double ri = u[i];
-      const double a0 = -s * ri, a1 = (s - 2 * c1 * itheta) * ri, a2 = c1 * itheta,
-                   a3 = (c_ - s * itheta) * ri, a4 = s * itheta;
-      for (int k = 0; k < 9; ++k)
-        J[i * 9 + k] = a0 * I[k] + a1 * rrt[k] + a2 * drrt[i * 9 + k] + a3 * r_x[k] + a4 * d_r_x[i * 9 + k];
-    }
-  }
-  for (int i = 0; i < 9; ++i) o[i] = R[i];
-  for (int i = 0; i < 27; ++i) o[12 + i] = J[i];
+  ba_camera_block_warp(rvec, tvec, c, blocks + (long long)c * kCam, threadIdx.x & 31);
 }
 
 struct BaParams {
   const int4* obs;            // {cam, pt, u bits, v bits}
   const float* points;
   const double* cams;
+  // fused camera precompute (observations sorted by camera): every CTA derives the blocks of
+  // the cameras ITS observation range references into cams_w (== cams) in its prologue
+  const float* rvec;
+  const float* tvec;
+  double* cams_w;
   float* r;
   float* Jc;
   float* Jp;
-  double* partials;           // [gridDim.x] per-CTA sums + [gridDim.x] a u64 arrival counter (zero between calls)
+  double* partials;           // [gridDim.x] per-CTA sums, [gridDim.x] a u64 arrival counter (zero between
+                              // calls), [gridDim.x + 1] the device-resident call sequence (seq == 0)
   double* cost;
   // multi-GPU cost exchange over peer-mapped memory (world > 1): peers[p] = rank p's exchange
   // buffer as mapped here, 2 (call parity) x world x {value bits, sequence number} u64 words
   unsigned long long* peers[kBaMaxWorld];
   int rank, world;
-  unsigned long long seq;
+  unsigned long long seq;     // 0: use (and advance) the device-resident sequence in `partials`
+  long long timeout_clk;      // bound of the peer wait (SM clocks)
+  uint32_t* status;           // set to kStatusPeerTimeout when the wait ran into the bound
   long long n_obs;
   long long n_points;
   int n_cams;
@@ -316,7 +336,7 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
       __syncwarp();
       if (lane < kCam / 2)
         reinterpret_cast<double2*>(cam_cache[warp])[lane] =
-            __ldg(reinterpret_cast<const double2*>(P.cams + (long long)c * kCam) + lane);
+            __ldcg(reinterpret_cast<const double2*>(P.cams + (long long)c * kCam) + lane);
       cached_cam = c;
       __syncwarp();
     }
@@ -419,8 +439,28 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
     ring.wait(0);
     gather(0, pt);
   }
-  // Launched behind the camera precompute with programmatic stream serialization
-  // (pbk_ba_evaluate), everything above - barrier init, the first record tiles, the first
+  if (P.cams_w != nullptr) {
+    // Fused precompute: the observations are sorted by camera, so the tiles of this CTA
+    // reference the cameras [first record's, last record's] - typically 1-5 - and its eight
+    // warps derive those blocks now (one warp per camera, lane-parallel Rodrigues) while the
+    // first record tiles and point gathers issued above are in flight.  Other CTAs may write
+    // the same block with the same bits.  No second kernel, no launch boundary in the step.
+    const long long ta = (long long)blockIdx.x * kBaWarps * ntiles / nwarps;
+    const long long tb = ((long long)blockIdx.x + 1) * kBaWarps * ntiles / nwarps;
+    if (tb > ta) {
+      const long long oa = ta * kBaTile;
+      long long ob = tb * kBaTile;
+      ob = (ob < P.n_obs ? ob : P.n_obs) - 1;
+      int ca = __ldg(reinterpret_cast<const int*>(P.obs + oa)), cb = __ldg(reinterpret_cast<const int*>(P.obs + ob));
+      ca = ca < 0 ? 0 : (ca >= P.n_cams ? P.n_cams - 1 : ca);
+      cb = cb < 0 ? 0 : (cb >= P.n_cams ? P.n_cams - 1 : cb);
+      for (int c = ca + warp; c <= cb; c += kBaWarps)
+        ba_camera_block_warp(P.rvec, P.tvec, c, P.cams_w + (long long)c * kCam, lane);
+    }
+    __syncthreads();              // this CTA's blocks are visible to all of its warps
+  }
+  // Launched behind the stand-alone camera precompute with programmatic stream serialization
+  // (two-kernel route), everything above - barrier init, the first record tiles, the first
   // point gathers, none of which the precompute writes - has overlapped its tail; the camera
   // blocks are complete and visible after this.  A no-op for an ordinary launch.
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -459,12 +499,18 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
       // the world values in rank order, so the result is bit-identical everywhere.  Slots
       // alternate with the call parity: a rank can only reuse a slot after every peer has
       // finished the call in between, i.e. has read the previous value.
-      const int par = (int)(P.seq & 1ull);
+      // the call sequence is either the caller's (identical on all ranks) or the device-resident
+      // counter behind the arrival word, which lets a captured CUDA graph replay the call
+      unsigned long long* dev_seq = arrived + 1;
+      const unsigned long long seq = P.seq != 0 ? P.seq : (*dev_seq + 1ull);
+      __syncwarp();
+      if (lane == 0 && P.seq == 0) *dev_seq = seq;
+      const int par = (int)(seq & 1ull);
       if (lane < P.world) {
         unsigned long long* slot = P.peers[lane] + (size_t)(par * P.world + P.rank) * 2;
         asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot), "l"((unsigned long long)__double_as_longlong(s)) : "memory");
         __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot + 1), "l"(P.seq) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot + 1), "l"(seq) : "memory");
       }
       double v = 0.0;
       if (lane < P.world) {
@@ -473,8 +519,9 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
         const long long t0 = clock64();
         do {
           asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(mine + 1) : "memory");
-        } while (got != P.seq && clock64() - t0 < (4ll << 30));              // ~2 s bound instead of a hang
-        if (got == P.seq) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(bits) : "l"(mine) : "memory");
+        } while (got != seq && clock64() - t0 < P.timeout_clk);              // bounded instead of a hang
+        if (got == seq) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(bits) : "l"(mine) : "memory");
+        else raise_status(P.status, kStatusPeerTimeout);                     // the cost is NaN and the host raises
         v = __longlong_as_double((long long)bits);
       }
       s = 0.0;
@@ -497,12 +544,15 @@ static BaLaunch ba_variant() {
   return {ba_residual_jacobian_kernel<2, 2>, BaCfg<2>::kSmemBytes, BaCfg<2>::kTile};
 }
 
+// resident grid of the streaming kernel; < 0 on failure (shared-memory opt-in and occupancy
+// are resolved once per device)
 static int ba_grid(const DeviceInfo* di, long long n_obs) {
   const BaLaunch L = ba_variant();
   const long long ntiles = (n_obs + L.tile - 1) / L.tile;
-  if (cudaFuncSetAttribute(L.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem) != cudaSuccess)
-    return -1;
-  return resident_grid(di, L.kernel, kBaWarps * 32, L.smem, (ntiles + kBaWarps - 1) / kBaWarps);
+  static KernelCache kc;
+  int per_sm;
+  if (kc.setup(di, L.kernel, kBaWarps * 32, L.smem, &per_sm) != PBK_OK) return -1;
+  return resident_grid(di, per_sm, (ntiles + kBaWarps - 1) / kBaWarps);
 }
 
 }  // namespace pbk
@@ -515,8 +565,7 @@ int pbk_ba_camera_precompute(const float* rvec, const float* tvec, int n_cams, d
   PBK_REQUIRE(n_cams >= 0, PBK_EINVAL, "negative camera count");
   if (n_cams == 0) return PBK_OK;
   PBK_REQUIRE(rvec && tvec && cam_blocks, PBK_EINVAL, "NULL device pointer");
-  ba_camera_precompute_kernel<<<(n_cams + 127) / 128, 128, 0, as_stream(stream)>>>(rvec, tvec, n_cams,
-                                                                                  cam_blocks);
+  ba_camera_precompute_kernel<<<(n_cams + 3) / 4, 128, 0, as_stream(stream)>>>(rvec, tvec, n_cams, cam_blocks);
   PBK_CHECK_LAUNCH("ba_camera_precompute_kernel");
   return PBK_OK;
 }
@@ -526,19 +575,23 @@ int pbk_ba_cost_slots(int64_t n_obs) {
   const DeviceInfo* di;
   if (current_device_info(&di)) return -1;
   const int g = ba_grid(di, n_obs > 0 ? n_obs : 1);
-  return g < 0 ? g : g + 1;            // + the arrival counter
+  return g < 0 ? g : g + 2;            // + the arrival counter + the device-resident call sequence
 }
 
+// fuse_rvec / fuse_tvec non-NULL: the streaming kernel derives the camera blocks itself (sorted
+// observations); after_precompute: it was launched behind the stand-alone precompute kernel
 static int ba_launch(const void* obs, int64_t n_obs, const float* points, int64_t n_points,
-                     const double* cam_blocks, int n_cams, double fx, double fy, double cx, double cy, float* r,
+                     double* cam_blocks, int n_cams, double fx, double fy, double cx, double cy, float* r,
                      float* J_cam, float* J_pt, double* cost_partials, double* cost, const uint64_t* peer_slots,
-                     int rank, int world, uint64_t seq, pbk_stream_t stream, bool after_precompute = false) {
+                     int rank, int world, uint64_t seq, uint32_t* status, pbk_stream_t stream,
+                     const float* fuse_rvec = nullptr, const float* fuse_tvec = nullptr,
+                     bool after_precompute = false) {
   using namespace pbk;
   PBK_REQUIRE(n_obs >= 0 && n_points >= 0 && n_cams >= 0, PBK_EINVAL, "negative size");
   PBK_REQUIRE((cost == nullptr) || (cost_partials != nullptr), PBK_EINVAL, "cost needs cost_partials");
   PBK_REQUIRE(world >= 1 && world <= kBaMaxWorld && rank >= 0 && rank < world, PBK_EINVAL, "bad rank/world");
-  PBK_REQUIRE(world == 1 || (peer_slots != nullptr && cost != nullptr && seq >= 1), PBK_EINVAL,
-              "the fused exchange needs peer buffers, a cost output and seq >= 1");
+  PBK_REQUIRE(world == 1 || (peer_slots != nullptr && cost != nullptr), PBK_EINVAL,
+              "the fused exchange needs peer buffers and a cost output");
   cudaStream_t s = as_stream(stream);
   if (n_obs == 0 && world == 1) {
     if (cost != nullptr) PBK_CUDA(cudaMemsetAsync(cost, 0, 8, s));
@@ -555,10 +608,13 @@ static int ba_launch(const void* obs, int64_t n_obs, const float* points, int64_
   BaParams P;
   P.obs = static_cast<const int4*>(obs);
   P.points = points; P.cams = cam_blocks;
+  P.rvec = fuse_rvec; P.tvec = fuse_tvec; P.cams_w = (fuse_rvec != nullptr) ? cam_blocks : nullptr;
   P.r = r; P.Jc = J_cam; P.Jp = J_pt; P.partials = cost_partials; P.cost = cost;
   P.n_obs = n_obs; P.n_points = n_points; P.n_cams = n_cams;
   P.fx = fx; P.fy = fy; P.cx = cx; P.cy = cy;
   P.rank = rank; P.world = world; P.seq = seq;
+  P.timeout_clk = exchange_timeout_clk();
+  P.status = status;
   for (int p = 0; p < kBaMaxWorld; ++p)
     P.peers[p] = (world > 1 && p < world) ? reinterpret_cast<unsigned long long*>(peer_slots[p]) : nullptr;
   const int grid = ba_grid(di, n_obs);
@@ -588,18 +644,26 @@ int pbk_ba_residual_jacobian(const void* obs, int64_t n_obs, const float* points
                              const double* cam_blocks, int n_cams, double fx, double fy, double cx,
                              double cy, float* r, float* J_cam, float* J_pt, double* cost_partials,
                              double* cost, pbk_stream_t stream) {
-  return ba_launch(obs, n_obs, points, n_points, cam_blocks, n_cams, fx, fy, cx, cy, r, J_cam, J_pt,
-                   cost_partials, cost, nullptr, 0, 1, 0, stream);
+  return ba_launch(obs, n_obs, points, n_points, const_cast<double*>(cam_blocks), n_cams, fx, fy, cx, cy, r, J_cam,
+                   J_pt, cost_partials, cost, nullptr, 0, 1, 0, nullptr, stream);
 }
 
-int pbk_ba_evaluate(const void* obs, int64_t n_obs, const float* points, int64_t n_points, const float* rvec,
-                    const float* tvec, int n_cams, double* cam_blocks, double fx, double fy, double cx, double cy,
-                    float* r, float* J_cam, float* J_pt, double* cost_partials, double* cost,
-                    const uint64_t* peer_slots, int rank, int world, uint64_t seq, pbk_stream_t stream) {
+int pbk_ba_evaluate(const void* obs, int64_t n_obs, int obs_sorted, const float* points, int64_t n_points,
+                    const float* rvec, const float* tvec, int n_cams, double* cam_blocks, double fx, double fy,
+                    double cx, double cy, float* r, float* J_cam, float* J_pt, double* cost_partials, double* cost,
+                    const uint64_t* peer_slots, int rank, int world, uint64_t seq, uint32_t* status,
+                    pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(n_cams == 0 || (rvec && tvec), PBK_EINVAL, "NULL device pointer");
+  const uint64_t* peers = world > 1 ? peer_slots : nullptr;
+  if (obs_sorted && n_cams > 0 && n_obs > 0)
+    // ONE kernel: every CTA derives the camera blocks its (camera-sorted) observations reference
+    return ba_launch(obs, n_obs, points, n_points, cam_blocks, n_cams, fx, fy, cx, cy, r, J_cam, J_pt,
+                     cost_partials, cost, peers, rank, world, seq, status, stream, rvec, tvec);
   int rc = pbk_ba_camera_precompute(rvec, tvec, n_cams, cam_blocks, stream);
   if (rc) return rc;
   return ba_launch(obs, n_obs, points, n_points, cam_blocks, n_cams, fx, fy, cx, cy, r, J_cam, J_pt,
-                   cost_partials, cost, world > 1 ? peer_slots : nullptr, rank, world, seq, stream,
+                   cost_partials, cost, peers, rank, world, seq, status, stream, nullptr, nullptr,
                    /*after_precompute=*/n_cams > 0);
 }
 
@@ -607,9 +671,9 @@ int pbk_ba_residual_jacobian_dist(const void* obs, int64_t n_obs, const float* p
                                   const double* cam_blocks, int n_cams, double fx, double fy, double cx,
                                   double cy, float* r, float* J_cam, float* J_pt, double* cost_partials,
                                   double* cost, const uint64_t* peer_slots, int rank, int world, uint64_t seq,
-                                  pbk_stream_t stream) {
-  return ba_launch(obs, n_obs, points, n_points, cam_blocks, n_cams, fx, fy, cx, cy, r, J_cam, J_pt,
-                   cost_partials, cost, peer_slots, rank, world, seq, stream);
+                                  uint32_t* status, pbk_stream_t stream) {
+  return ba_launch(obs, n_obs, points, n_points, const_cast<double*>(cam_blocks), n_cams, fx, fy, cx, cy, r, J_cam,
+                   J_pt, cost_partials, cost, peer_slots, rank, world, seq, status, stream);
 }
 
 }  // extern "C"

@@ -145,7 +145,11 @@ static int launch_depth(const void* depth_v, int batch, int H, int W, int skip, 
     const long long ntiles = total / kDcTile;
     if (ntiles > 0) {
       auto kern = depth_reconstruct_dense_kernel<T>;
-      const int grid = resident_grid(di, kern, kDcWarps * 32, 0, (ntiles + kDcWarps - 1) / kDcWarps);
+      static KernelCache kc;
+      int per_sm;
+      const int rc = kc.setup(di, kern, kDcWarps * 32, 0, &per_sm);
+      if (rc) return rc;
+      const int grid = resident_grid(di, per_sm, (ntiles + kDcWarps - 1) / kDcWarps);
       kern<<<grid, kDcWarps * 32, 0, s>>>(depth, total, W, H, xs, ys, out);
       PBK_CHECK_LAUNCH("depth_reconstruct_dense_kernel");
     }

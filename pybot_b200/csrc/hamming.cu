@@ -302,6 +302,9 @@ hamming_knn2_kernel(const __grid_constant__ HammingParams P) {
           tile[2 * row + 1] = b;
         }
       }
+      // these generic-proxy stores are later overwritten by the TMA refill of the slot (async
+      // proxy): the writer orders them across the proxies before the barriers that precede it
+      fence_proxy_async_smem();
       __syncthreads();
     }
     if (nrows == kTR) score_tile<VARIANT, true, kRQ>(tile, kTR, (uint32_t)r_base, qr, k1, k2);
@@ -417,6 +420,8 @@ struct HammingPeers {
   long long nq;
   int rank, world;
   unsigned long long seq;
+  long long timeout_clk;        // bound of the spin waits (SM clocks)
+  uint32_t* status;             // set to kStatusPeerTimeout when a wait ran into the bound
 };
 __device__ __forceinline__ size_t hx_keys(const HammingPeers& X, int par, int r) {
   return ((size_t)par * X.world + r) * (size_t)X.nq * 2;
@@ -446,18 +451,24 @@ __device__ __forceinline__ void hx_publish(const HammingPeers& X, int phase, uns
     if (threadIdx.x == 0) *done_counter = 0u;  // ready for the next call
   }
 }
-// every CTA of a consuming kernel waits until all ranks have published `phase`
-// (bounded: ~2 s, after which the call's results are garbage instead of a hang)
-__device__ __forceinline__ void hx_wait(const HammingPeers& X, int phase) {
+// every CTA of a consuming kernel waits until all ranks have published `phase`.  The wait is
+// bounded (X.timeout_clk, ~2 s by default): a peer that never arrives makes the call FAIL -
+// *X.status is set (the host wrapper raises on it) and the caller poisons its outputs
+// (no-match keys / zero rows) instead of consuming stale exchange words.  Returns true when
+// every rank's data has arrived.
+__device__ __forceinline__ bool hx_wait(const HammingPeers& X, int phase) {
+  bool ok = true;
   if ((int)threadIdx.x < X.world) {
     const unsigned long long* f = X.buf[X.rank] + hx_flags(X, (int)(X.seq & 1ull), phase) + threadIdx.x;
     unsigned long long got = 0;
     const long long t0 = clock64();
     do {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(f) : "memory");
-    } while (got != X.seq && clock64() - t0 < (4ll << 30));
+    } while (got != X.seq && clock64() - t0 < X.timeout_clk);
+    ok = got == X.seq;
+    if (!ok) raise_status(X.status, kStatusPeerTimeout);
   }
-  __syncthreads();
+  return __syncthreads_and(ok) != 0;
 }
 
 // split merge of this rank's partial keys + push of the result to every peer
@@ -488,12 +499,12 @@ hamming_merge_push_kernel(const unsigned long long* __restrict__ partial, int pa
 // wait for every rank's keys, then global top-2 by unsigned min (same order on every rank)
 __global__ void __launch_bounds__(256)
 hamming_merge_world_kernel(const __grid_constant__ HammingPeers X, unsigned long long* __restrict__ keys) {
-  hx_wait(X, 0);
+  const bool ok = hx_wait(X, 0);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= X.nq) return;
   const unsigned long long* mine = X.buf[X.rank];
   unsigned long long b1 = PBK_KEY_NONE, b2 = PBK_KEY_NONE;
-  for (int r = 0; r < X.world; ++r) {
+  for (int r = 0; ok && r < X.world; ++r) {
     const unsigned long long* src = mine + hx_keys(X, (int)(X.seq & 1ull), r) + (size_t)i * 2;
     const unsigned long long vx = __ldcv(src), vy = __ldcv(src + 1);
     unsigned long long mx = max(b1, vx);
@@ -537,13 +548,13 @@ hamming_gather_push_kernel(const uint8_t* __restrict__ t, long long nt, unsigned
 // wait for every rank's rows, then copy the matched rows out of the exchange buffer
 __global__ void __launch_bounds__(256)
 hamming_rows_world_kernel(const __grid_constant__ HammingPeers X, uint8_t* __restrict__ rows) {
-  hx_wait(X, 1);
+  const bool ok = hx_wait(X, 1);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= X.nq) return;
   const unsigned long long* src = X.buf[X.rank] + hx_rows(X, (int)(X.seq & 1ull)) + (size_t)i * 4;
   ulonglong2* dst = reinterpret_cast<ulonglong2*>(rows + i * 32);
-  dst[0] = make_ulonglong2(__ldcv(src), __ldcv(src + 1));
-  dst[1] = make_ulonglong2(__ldcv(src + 2), __ldcv(src + 3));
+  dst[0] = ok ? make_ulonglong2(__ldcv(src), __ldcv(src + 1)) : make_ulonglong2(0, 0);
+  dst[1] = ok ? make_ulonglong2(__ldcv(src + 2), __ldcv(src + 3)) : make_ulonglong2(0, 0);
 }
 
 // ------------------------------------------------------- popc pipe probe
@@ -603,13 +614,15 @@ __global__ void __launch_bounds__(MODE >= 2 ? kHThreads : 256) popc_probe_kernel
   sink[8 + blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
-static int g_variant = -1;
+static std::atomic<int> g_variant{-1};
 static int hamming_variant() {
-  if (g_variant < 0) {
+  int v = g_variant.load(std::memory_order_relaxed);
+  if (v < 0) {
     const char* e = getenv("PBK_HAMMING_VARIANT");
-    g_variant = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+    v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+    g_variant.store(v, std::memory_order_relaxed);      // idempotent: every thread computes the same value
   }
-  return g_variant;
+  return v;
 }
 
 static int plan(const DeviceInfo* di, long long nq, long long nt, int* splits, long long* rows_per_split,
@@ -641,26 +654,24 @@ static int plan(const DeviceInfo* di, long long nq, long long nt, int* splits, l
 }  // namespace pbk
 
 namespace pbk {
-// launches the scoring kernel in the shape plan() chose
-static int launch_knn2(const HammingParams& P, int rq, cudaStream_t s) {
-  const int qtile = kHThreads * rq;
-  const int smem = kStages * kStageBytes + qtile * 32 + (kStages + 1) * 8;
+// launches the scoring kernel in the shape plan() chose (shared-memory opt-in cached per device)
+template <int V, int R>
+static int launch_knn2_as(const HammingParams& P, const DeviceInfo* di, cudaStream_t s) {
+  constexpr int qtile = kHThreads * R;
+  constexpr int smem = kStages * kStageBytes + qtile * 32 + (kStages + 1) * 8;
+  static KernelCache kc;
+  const int rc = kc.setup(di, hamming_knn2_kernel<V, R>, kHThreads, smem, nullptr);
+  if (rc) return rc;
   const dim3 grid((unsigned)((P.nq + qtile - 1) / qtile), (unsigned)P.splits);
-#define PBK_KNN2(V, R)                                                                                      \
-  do {                                                                                                      \
-    PBK_CUDA(cudaFuncSetAttribute(hamming_knn2_kernel<V, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-    hamming_knn2_kernel<V, R><<<grid, kHThreads, smem, s>>>(P);                                             \
-  } while (0)
-  if (hamming_variant() == 0) {
-    if (rq == kRQ) PBK_KNN2(0, kRQ); else PBK_KNN2(0, kRQSmall);
-  } else if (hamming_variant() == 2 && rq == kRQ) {
-    PBK_KNN2(2, kRQ);
-  } else {
-    if (rq == kRQ) PBK_KNN2(1, kRQ); else PBK_KNN2(1, kRQSmall);
-  }
-#undef PBK_KNN2
+  hamming_knn2_kernel<V, R><<<grid, kHThreads, smem, s>>>(P);
   PBK_CHECK_LAUNCH("hamming_knn2_kernel");
   return PBK_OK;
+}
+static int launch_knn2(const HammingParams& P, int rq, const DeviceInfo* di, cudaStream_t s) {
+  const int v = hamming_variant();
+  if (v == 0) return rq == kRQ ? launch_knn2_as<0, kRQ>(P, di, s) : launch_knn2_as<0, kRQSmall>(P, di, s);
+  if (v == 2 && rq == kRQ) return launch_knn2_as<2, kRQ>(P, di, s);
+  return rq == kRQ ? launch_knn2_as<1, kRQ>(P, di, s) : launch_knn2_as<1, kRQSmall>(P, di, s);
 }
 }  // namespace pbk
 
@@ -701,7 +712,7 @@ int pbk_hamming_knn2(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt,
   HammingParams P;
   P.q = q; P.t = t; P.partial = static_cast<unsigned long long*>(scratch);
   P.nq = nq; P.nt = nt; P.rows_per_split = rps; P.train_base = train_base; P.splits = splits;
-  rc = launch_knn2(P, rq, s);
+  rc = launch_knn2(P, rq, di, s);
   if (rc) return rc;
   hamming_merge_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(P.partial, splits, nq,
                                                                     reinterpret_cast<unsigned long long*>(keys));
@@ -757,19 +768,21 @@ size_t pbk_hamming_exchange_words(int64_t nq, int world) {
 }
 
 static int fill_peers(pbk::HammingPeers* X, const uint64_t* peer_bufs, int64_t nq, int rank, int world,
-                      uint64_t seq) {
+                      uint64_t seq, uint32_t* status) {
   using namespace pbk;
   PBK_REQUIRE(world >= 2 && world <= kHMaxWorld && rank >= 0 && rank < world, PBK_EINVAL, "bad rank/world");
   PBK_REQUIRE(peer_bufs != nullptr && seq >= 1, PBK_EINVAL, "the fused exchange needs peer buffers and seq >= 1");
   for (int p = 0; p < kHMaxWorld; ++p)
     X->buf[p] = p < world ? reinterpret_cast<unsigned long long*>(peer_bufs[p]) : nullptr;
   X->nq = nq; X->rank = rank; X->world = world; X->seq = seq;
+  X->timeout_clk = exchange_timeout_clk();
+  X->status = status;
   return PBK_OK;
 }
 
 int pbk_hamming_knn2_dist(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, uint64_t train_base,
                           uint64_t* keys, void* scratch, const uint64_t* peer_bufs, int rank, int world,
-                          uint64_t seq, uint32_t* done_counter, pbk_stream_t stream) {
+                          uint64_t seq, uint32_t* done_counter, uint32_t* status, pbk_stream_t stream) {
   using namespace pbk;
   PBK_REQUIRE(nq > 0 && nt >= 0, PBK_EINVAL, "bad sizes");
   PBK_REQUIRE(q != nullptr && keys != nullptr && scratch != nullptr && done_counter != nullptr, PBK_EINVAL,
@@ -779,7 +792,7 @@ int pbk_hamming_knn2_dist(const uint8_t* q, int64_t nq, const uint8_t* t, int64_
               "device pointers must be 16-byte aligned");
   PBK_REQUIRE(train_base + (uint64_t)nt <= (1ull << 32), PBK_EINVAL, "global train row index must fit 32 bits");
   HammingPeers X;
-  int rc = fill_peers(&X, peer_bufs, nq, rank, world, seq);
+  int rc = fill_peers(&X, peer_bufs, nq, rank, world, seq, status);
   if (rc) return rc;
   const DeviceInfo* di;
   rc = current_device_info(&di);
@@ -792,7 +805,7 @@ int pbk_hamming_knn2_dist(const uint8_t* q, int64_t nq, const uint8_t* t, int64_
   HammingParams P;
   P.q = q; P.t = t; P.partial = static_cast<unsigned long long*>(scratch);
   P.nq = nq; P.nt = nt; P.rows_per_split = rps; P.train_base = train_base; P.splits = splits;
-  rc = launch_knn2(P, rq, s);
+  rc = launch_knn2(P, rq, di, s);
   if (rc) return rc;
   const unsigned blocks = (unsigned)((nq + 255) / 256);
   hamming_merge_push_kernel<<<blocks, 256, 0, s>>>(P.partial, splits, X, done_counter);
@@ -804,7 +817,7 @@ int pbk_hamming_knn2_dist(const uint8_t* q, int64_t nq, const uint8_t* t, int64_
 
 int pbk_hamming_gather_best_dist(const uint8_t* t, int64_t nt, uint64_t train_base, const uint64_t* keys,
                                  int64_t nq, uint8_t* rows, const uint64_t* peer_bufs, int rank, int world,
-                                 uint64_t seq, uint32_t* done_counter, pbk_stream_t stream) {
+                                 uint64_t seq, uint32_t* done_counter, uint32_t* status, pbk_stream_t stream) {
   using namespace pbk;
   PBK_REQUIRE(nt >= 0 && nq > 0, PBK_EINVAL, "bad sizes");
   PBK_REQUIRE(keys != nullptr && rows != nullptr && done_counter != nullptr && (nt == 0 || t != nullptr),
@@ -812,7 +825,7 @@ int pbk_hamming_gather_best_dist(const uint8_t* t, int64_t nt, uint64_t train_ba
   PBK_REQUIRE(aligned16(t) && aligned16(keys) && aligned16(rows), PBK_EALIGN,
               "device pointers must be 16-byte aligned");
   HammingPeers X;
-  int rc = fill_peers(&X, peer_bufs, nq, rank, world, seq);
+  int rc = fill_peers(&X, peer_bufs, nq, rank, world, seq, status);
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
   const unsigned blocks = (unsigned)((nq + 255) / 256);

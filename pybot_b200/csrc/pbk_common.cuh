@@ -5,6 +5,9 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "../../include/pybot_b200.h"
 
 namespace pbk {
@@ -184,6 +187,14 @@ struct WarpRing {
     mbar_expect_tx(&bars[k % NST], bytes);
     tma_load_1d(slot(k), src, bytes, &bars[k % NST]);
   }
+  // lane 0 only; full tile with an L2 eviction-policy hint
+  __device__ __forceinline__ void issue_hint(int k, const char* src, uint64_t pol) const {
+    mbar_expect_tx(&bars[k % NST], TILE_BYTES);
+    tma_load_1d_hint(slot(k), src, TILE_BYTES, &bars[k % NST], pol);
+  }
+  // lane 0 only; slot k is filled by hand (ragged tile): completes its barrier phase so that
+  // the parity bookkeeping of later uses of the slot stays in step
+  __device__ __forceinline__ void skip(int k) const { mbar_arrive(&bars[k % NST]); }
   __device__ __forceinline__ void wait(int k) const { mbar_wait(&bars[k % NST], (uint32_t)((k / NST) & 1)); }
 };
 
@@ -210,19 +221,57 @@ __device__ __forceinline__ void tma_store_wait_read_but() {
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 
-// Persistent grid = what is actually resident: SMs x occupancy of `kernel`
+// Launch facts of one kernel (one template instantiation), resolved ONCE per device: the
+// shared-memory opt-in (cudaFuncSetAttribute) and the occupancy query are host-side driver
+// calls of several microseconds each - per call they were a visible part of a 30-80 us step.
+// A launch site keeps a `static KernelCache` and calls setup(); thread-safe.
+constexpr int kMaxDevices = 64;
+struct KernelCache {
+  std::atomic<int> ready[kMaxDevices];
+  int per_sm[kMaxDevices];
+  std::mutex mu;
+  // returns 0 or a pbk_status; *blocks_per_sm = resident CTAs per SM for (threads, dyn_smem)
+  template <typename K>
+  int setup(const DeviceInfo* di, K kernel, int threads, int dyn_smem, int* blocks_per_sm) {
+    const int dev = di->device;
+    if (!ready[dev].load(std::memory_order_acquire)) {
+      std::lock_guard<std::mutex> lock(mu);
+      if (!ready[dev].load(std::memory_order_relaxed)) {
+        if (dyn_smem > 48 * 1024)
+          PBK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, (size_t)dyn_smem) != cudaSuccess ||
+            n < 1)
+          n = 1;
+        per_sm[dev] = n;
+        ready[dev].store(1, std::memory_order_release);
+      }
+    }
+    if (blocks_per_sm) *blocks_per_sm = per_sm[dev];
+    return PBK_OK;
+  }
+};
+
+// Persistent grid = what is actually resident: SMs x occupancy of the kernel
 // (a grid larger than that runs a ragged second wave), capped by the work.
-template <typename K>
-static inline int resident_grid(const DeviceInfo* di, K kernel, int threads, size_t dyn_smem,
-                                long long work_items) {
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess ||
-      per_sm < 1)
-    per_sm = 1;
-  long long g = (long long)di->sm_count * per_sm;
+static inline int resident_grid(const DeviceInfo* di, int per_sm, long long work_items) {
+  long long g = (long long)di->sm_count * (per_sm < 1 ? 1 : per_sm);
   if (g > work_items) g = work_items;
   if (g < 1) g = 1;
   return (int)g;
+}
+
+// ------------------------------------------------ fused multi-GPU exchanges
+// Bound of the cross-GPU spin waits in SM clocks (default ~2 s; pbk_set_exchange_timeout_ms).
+long long exchange_timeout_clk();
+// A wait that ran into the bound sets *status (device memory or mapped pinned host memory)
+// to one of these; the host wrapper raises.
+constexpr uint32_t kStatusPeerTimeout = 1u;
+__device__ __forceinline__ void raise_status(uint32_t* status, uint32_t code) {
+  if (status != nullptr) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(status), "r"(code) : "memory");
+    __threadfence_system();
+  }
 }
 
 }  // namespace pbk

@@ -255,7 +255,11 @@ static int launch_reproject(const void* disp_v, int batch, int H, int W, const R
       const long long ctas_needed = (ntiles + kWarpsPerCta - 1) / kWarpsPerCta;
       const bool fast = q_is_stereo_sparse(P.q);
       auto kern = fast ? reproject_dense_kernel<T, true> : reproject_dense_kernel<T, false>;
-      const int grid = resident_grid(di, kern, kWarpsPerCta * 32, 0, ctas_needed);
+      static KernelCache kc[2];
+      int per_sm;
+      const int rc = kc[fast ? 1 : 0].setup(di, kern, kWarpsPerCta * 32, 0, &per_sm);
+      if (rc) return rc;
+      const int grid = resident_grid(di, per_sm, ctas_needed);
       const long long stride_px = (long long)grid * kWarpsPerCta * kTilePx;
       P.dx = (int)(stride_px % W);
       P.dy = (int)((stride_px / W) % H);

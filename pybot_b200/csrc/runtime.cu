@@ -20,15 +20,21 @@ int cuda_fail(cudaError_t e, const char* what) {
   return PBK_ECUDA;
 }
 
-static DeviceInfo g_info[64];
-static bool g_info_ok[64];
+static DeviceInfo g_info[kMaxDevices];
+static std::atomic<int> g_info_ok[kMaxDevices];
+static std::mutex g_info_mu;
+
+// default ~2 s at 1.965 GHz
+static std::atomic<long long> g_exchange_timeout_clk{4ll << 30};
+long long exchange_timeout_clk() { return g_exchange_timeout_clk.load(std::memory_order_relaxed); }
 
 int current_device_info(const DeviceInfo** out) {
   int dev = -1;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
-  PBK_REQUIRE(dev >= 0 && dev < 64, PBK_EINVAL, "device index %d out of range", dev);
-  if (!g_info_ok[dev]) {
+  PBK_REQUIRE(dev >= 0 && dev < kMaxDevices, PBK_EINVAL, "device index %d out of range", dev);
+  if (!g_info_ok[dev].load(std::memory_order_acquire)) {
+    std::lock_guard<std::mutex> lock(g_info_mu);
     DeviceInfo d;
     d.device = dev;
     PBK_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -40,7 +46,7 @@ int current_device_info(const DeviceInfo** out) {
                 "libpybot_b200 is built for sm_100a only; device %d is sm_%d%d",
                 dev, d.cc_major, d.cc_minor);
     g_info[dev] = d;
-    g_info_ok[dev] = true;
+    g_info_ok[dev].store(1, std::memory_order_release);     // the struct is complete before the flag
   }
   *out = &g_info[dev];
   return PBK_OK;
@@ -94,6 +100,14 @@ int pbk_hbm_probe(int mode, const void* src, void* dst, int64_t bytes, uint32_t*
 }
 
 int pbk_version(void) { return PBK_VERSION; }
+
+int pbk_set_exchange_timeout_ms(double ms) {
+  PBK_REQUIRE(ms > 0.0 && ms < 3.6e6, PBK_EINVAL, "timeout must be in (0, 1 h)");
+  // clock64() counts SM clocks; 2 GHz is an upper bound of the B200 boost clock, so the wait
+  // is never shorter than asked
+  pbk::g_exchange_timeout_clk.store((long long)(ms * 2.0e6), std::memory_order_relaxed);
+  return PBK_OK;
+}
 
 const char* pbk_last_error_string(void) { return pbk::g_err; }
 

@@ -304,332 +304,296 @@ project_points_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
     if (lane == 0 && local_count)
       atomicAdd(reinterpret_cast<unsigned long long*>(count), (unsigned long long)local_count);
   }
+  // no masks: every point is valid (written from the device: a host-sourced copy would be
+  // illegal under stream capture)
+  if (MODE == 0 && count != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *count = n;
 }
-
-// Phase clocks of the compaction kernel (diagnostic; compiled in with -DPBK_COMPACT_TIMING)
-#ifdef PBK_COMPACT_TIMING
-__device__ unsigned long long g_ct_clk[16];
-#define CT_T0() long long _t0 = clock64()
-#define CT_ACC(slot)                                                        \
-  do {                                                                      \
-    const long long _t1 = clock64();                                        \
-    if (lane == 0) atomicAdd(&g_ct_clk[slot], (unsigned long long)(_t1 - _t0)); \
-    _t0 = _t1;                                                              \
-  } while (0)
-#else
-#define CT_T0() do {} while (0)
-#define CT_ACC(slot) do {} while (0)
-#endif
 
 // ------------------------------------------------- projection + x[valid]
-// Order-preserving compaction fused into the projection pass (no second read
-// of X, no library scan): a two-level scan over 1024-point tiles, software-
-// pipelined two tiles deep.
+// Camera.project(check_bounds / check_depth) returns x[valid]: an order-preserving
+// compaction (camera_utils.py:727-732).  Two phases per chunk of X inside ONE persistent
+// cooperative kernel, one grid barrier per chunk:
 //
-// Persistent, co-resident CTAs (cooperative launch) of 8 compute warps + 2 scan
-// warps + 1 chain warp.  CTA b owns tiles b, b+G, b+2G ...: all CTAs work on one
-// generation of G consecutive tiles at a time.
-//   compute warps read tile i from a 2-stage TMA input ring (the last warp to
-//                 consume a stage refills it), project it (thread t owns points
-//                 t + 256 k), park uv / depth in one of three shared-memory
-//                 buffers, publish the tile aggregate (the last warp to finish
-//                 does it), then scatter tile i-2 whose base offset has been
-//                 resolved meanwhile;
-//   scan warp w   (tiles of parity w) scans the 32 (row, warp) valid counts of a
-//                 finished tile; its exclusive offset is the prefix of its
-//                 GENERATION plus the aggregates of the tiles of the same
-//                 generation before it (<= G status words, all loads in flight
-//                 together with the generation prefix): no tile waits for another
-//                 tile's look-back;
-//   chain warp    (CTA 0 only) is the one serial dependency: it sums the G
-//                 aggregates of generation g as they appear and publishes the
-//                 prefix of generation g+1 - one L2 round trip per generation.
-// History: a per-tile decoupled look-back (every tile resolving against its
-// predecessors' prefixes) made the prefix frontier advance one generation per ~3
-// dependent L2 round trips, 0.100 ms; this form 0.095 ms.  Versions that waited for
-// the prefix inside the tile, took tickets ahead of time, or published the aggregate
-// from the scan warp ran 1.5-6x slower.
-// Valid points are written at base + rank; lanes of a warp hold consecutive
-// ranks, so the stores are contiguous runs.
-// scratch layout (zeroed per call): [0] unused, [1 .. ntiles] tile aggregate words, then
-// one prefix word per generation.
-constexpr int kCtWarps = 8;                          // compute warps
-constexpr int kCtThreads = kCtWarps * 32;            // 256 compute threads
-// Shape knobs (scripts/build_variants.py builds A/B libraries from them).  Measured on C2
-// (10 M points, flushed): 3 CTAs/SM x 3 buffers, one point at a time 0.0952 ms; 2 CTAs/SM x 5
-// buffers with the projection batched in pairs (80 registers, no spills) 0.0932 ms - shipped;
-// batched by four (spills) 0.0973, four scan warps 0.1096, 6 buffers + 3 scan warps 0.1239.
-#ifndef PBK_CT_SCAN
-#define PBK_CT_SCAN 2
+//  phase A  classifies every point of the chunk.  Validity is a handful of sign tests on
+//           LINEAR forms of X - |fx xc + (cx - W/2) zc| < (W/2)|zc| and the v / depth
+//           analogues - evaluated in fp32 FMAs (30 instructions per point instead of ~90 in
+//           fp64) with a rigorous error band b = kappa (|X|+|Y|+|Z|+1): outside the band the
+//           fp32 sign IS the reference's decision; the rare point inside it (~1e-5 of C2, also
+//           NaN / inf / z ~ 0) takes the exact fp64 route of the uncompacted kernel.  The
+//           valid points' coordinates are written, in order, to the front of the warp's own
+//           scratch region X' (tile-run-local compaction: no offsets from other warps are
+//           needed), the 0/1 flags to valid_out, and the warp's count to shared memory.
+//  barrier  every CTA publishes its count; after the barrier each CTA reads the <= 2 x 148
+//           counts, and a warp's output offset is chunk base + counts before it.
+//  phase B  is the PLAIN dense projection over X' (L2-resident: a chunk's X' is <= 40 MB):
+//           fp64 in OpenCV's order, fully coalesced uv / depth stores at the final offsets.
+//           No ballots, no parking, no look-back, and the fp64 work is proportional to the
+//           number of VALID points.
+//
+// HBM traffic = the algorithmic bytes (X once, flags, compacted outputs); X' lives in L2.
+// History: a single-pass decoupled look-back over 1024-point tiles with
+// parked outputs ran at 93 us on C2 however it was shaped - every tile's base depends on all
+// earlier tiles, and the fp64 projection of a tile had to finish before its count existed.
+constexpr int kCpWarps = 8;
+constexpr int kCpThreads = kCpWarps * 32;
+#ifndef PBK_CP_MINB
+#define PBK_CP_MINB 2
 #endif
-#ifndef PBK_CT_BUFS
-#define PBK_CT_BUFS 5
+#ifndef PBK_CP_CHUNK_MB
+#define PBK_CP_CHUNK_MB 40
 #endif
-#ifndef PBK_CT_MINB
-#define PBK_CT_MINB 2
-#endif
-constexpr int kCtScan = PBK_CT_SCAN;                           // scan warps (one look-back each in flight); must be <= buffers
-constexpr int kCtBlock = kCtThreads + 32 * kCtScan + 32;     // + the chain warp (works in CTA 0 only)
-constexpr int kCtPpt = 4;                            // points per thread
-constexpr int kCtTile = kCtThreads * kCtPpt;         // 1024 points per tile
-constexpr int kCtSegs = kCtPpt * kCtWarps;           // 32 (row, warp) segments
-// parked-output buffers (pipeline depth = buffers - 1 tiles of slack between a
-// tile's projection and its scatter); see the shape knobs above for what was measured.
-template <typename T> struct CtBufs { static constexpr int value = PBK_CT_BUFS; };
-static_assert(kCtScan <= CtBufs<float>::value, "a scan warp may only wait one mbarrier phase ahead");
 
-template <typename T>
-struct CompactSmem {
-  static constexpr int kIn = kCtTile * 3 * (int)sizeof(T);             // one input stage
-  static constexpr int kOut = kCtTile * (2 * (int)sizeof(T) + 8);      // parked uv + depth of one tile
-  static constexpr int kBytes = 2 * kIn + CtBufs<T>::value * kOut;
+struct ClassifyParams {
+  float z[4];        // zc            = z . (X, Y, Z, 1)
+  float cu[4];       // fx xc + (cx - W/2) zc
+  float cv[4];       // fy yc + (cy - H/2) zc
+  float d[4];        // depth - min_depth
+  float hw, hh;      // W/2, H/2
+  float kappa;       // band = kappa * (|X| + |Y| + |Z| + 1)
 };
 
+// scratch layout of the compacting kernel (bytes): [0] grid-barrier counter (u32), [64 ..) two
+// arrays of kCpMaxGrid CTA counts (call parity of the chunk), [kCpCtlBytes ..) the X' region
+constexpr int kCpMaxGrid = 2048;
+constexpr size_t kCpCtlBytes = 64 + 2 * kCpMaxGrid * 4;       // 16448, a multiple of 64
+
+template <typename T> struct CpTile {
+  static constexpr int kBytes = kTilePts * 3 * (int)sizeof(T);
+};
+
+// exact validity of one point: the arithmetic of project_points_kernel<T, DIST, 1>
 template <typename T, bool DIST>
-__global__ void __launch_bounds__(kCtBlock, sizeof(T) == 4 ? PBK_CT_MINB : 1)
-project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
-                       double* __restrict__ depth, uint8_t* __restrict__ valid_out,
-                       long long* __restrict__ count, unsigned long long* __restrict__ scratch,
-                       const __grid_constant__ pbk_project_params P) {
-  using SM = CompactSmem<T>;
-  using UV = typename OutPix<T>::vec;
-  constexpr int kCtBufs = CtBufs<T>::value;
-  extern __shared__ __align__(128) char dyn_smem[];
-  // barriers and aggregate slots are per parked buffer: tile i + kCtBufs cannot be
-  // projected before tile i has been scattered, so a slot is never shared by two
-  // live tiles however far the compute warps drift apart
-  __shared__ __align__(8) uint64_t in_full[2], cnt_ready[kCtBufs], base_ready[kCtBufs];
-  __shared__ long long s_base[kCtBufs];
-  __shared__ int s_cnt[kCtBufs][kCtSegs], s_excl[kCtBufs][kCtSegs], s_aggsum[kCtBufs], s_arrived[kCtBufs], s_consumed[2];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long ntiles = (n + kCtTile - 1) / kCtTile;
-  unsigned long long* status = scratch + 1;                // one aggregate word per tile
-  unsigned long long* gen_prefix = scratch + 1 + ntiles;   // one prefix word per generation of gridDim.x tiles
-  // generation i of this CTA is tile i * gridDim.x + blockIdx.x
-  const int my_tiles = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-  auto tile_of = [&](int i) -> long long { return (long long)i * gridDim.x + blockIdx.x; };
-
-  if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&in_full[s], 1);
-      s_consumed[s] = 0;
-    }
-    for (int q = 0; q < kCtBufs; ++q) {
-      mbar_init(&cnt_ready[q], kCtWarps);
-      mbar_init(&base_ready[q], 1);
-      s_aggsum[q] = 0;
-      s_arrived[q] = 0;
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+__device__ __noinline__ bool exact_valid(const pbk_project_params& P, T x, T y, T z) {
+  const double Xp[3] = {(double)x, (double)y, (double)z};
+  bool good = true;
+  if (P.check_depth) good = depth_of(P, Xp) >= P.min_depth;
+  if (P.check_bounds) {
+    double u, v;
+    project_one<DIST>(P, Xp, u, v);
+    good = good && OutPix<T>::in_bounds((T)u, (T)v, (T)P.width, (T)P.height);
   }
-  __syncthreads();
-  // input stage (i & 1) <- tile of generation i: one TMA bulk copy (plus a < 16 B
-  // tail by hand), issued by a single thread
-  auto feed = [&](int i) {
-    if (i >= my_tiles) return;
-    const int st = i & 1;
-    const long long first = tile_of(i) * kCtTile;
-    const int npts = (n - first) < kCtTile ? (int)(n - first) : kCtTile;
-    const int bytes = npts * 3 * (int)sizeof(T), bulk = bytes & ~15;
-    char* dst = dyn_smem + st * SM::kIn;
-    const char* src = reinterpret_cast<const char*>(X + first * 3);
-    for (int o = bulk; o < bytes; o += 4)
-      *reinterpret_cast<uint32_t*>(dst + o) = *reinterpret_cast<const uint32_t*>(src + o);
-    if (bulk > 0) {
-      mbar_expect_tx(&in_full[st], (uint32_t)bulk);
-      tma_load_1d(dst, src, (uint32_t)bulk, &in_full[st]);
-    } else {
-      mbar_arrive(&in_full[st]);
-    }
-  };
-  if (tid == 0) {
-    feed(0);
-    feed(1);
-  }
-
-  if (warp == kCtWarps + kCtScan) {
-    // ============================================================== chain warp
-    // CTA 0 only: publishes the exclusive prefix of every generation of gridDim.x
-    // tiles.  A generation's total needs only its tiles' aggregates (published by
-    // the compute warps, no look-back involved), so this loop is the one serial
-    // dependency of the kernel and it advances one L2 round trip per generation.
-    if (blockIdx.x != 0) return;
-    long long running = 0;
-    for (long long g0 = 0, g = 0; g0 < ntiles; g0 += gridDim.x, ++g) {
-      if (lane == 0) st_status(gen_prefix + g, kStatePrefix | (unsigned long long)running);
-      const long long g1 = (g0 + gridDim.x) < ntiles ? (g0 + gridDim.x) : ntiles;
-      const long long acc = sum_aggregates(status + g0, g1 - g0, lane);
-      running += acc;
-    }
-    if (lane == 0 && count != nullptr) *count = running;
-    return;
-  }
-  if (warp >= kCtWarps) {
-    // ============================================================== scan warps
-    const int w = warp - kCtWarps;                   // this warp resolves tiles w, w + kCtScan, ...
-    for (int i = w; i < my_tiles; i += kCtScan) {
-      const int q = i % kCtBufs;
-      const uint32_t ph = (uint32_t)((i / kCtBufs) & 1);
-      // tile i's segment counts -> exclusive offsets, aggregate
-      CT_T0();
-      mbar_wait(&cnt_ready[q], ph);
-      CT_ACC(2);
-      const int c = s_cnt[q][lane];
-      int inc = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int a = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += a;
-      }
-      s_excl[q][lane] = inc - c;
-      const long long agg = __shfl_sync(0xffffffffu, inc, 31);
-      const long long tile = tile_of(i);              // its aggregate was published by the compute warps
-      // exclusive offset = prefix of generation i (from the chain warp) + the
-      // aggregates of the tiles of the SAME generation before this one.  No tile
-      // waits on another tile's look-back: the only serial chain is the chain warp's
-      // running sum of generation totals.
-      const long long g0 = (long long)i * gridDim.x;  // first tile of generation i
-      unsigned long long gp = ld_status(gen_prefix + i);          // in flight together with the aggregates
-      const long long acc = sum_aggregates(status + g0, tile - g0, lane);
-      while ((gp >> 62) == 0) gp = ld_status(gen_prefix + i);
-      const long long excl = (long long)(gp & kValueMask) + acc;
-      CT_ACC(3);
-      __syncwarp();                         // every lane's s_excl store precedes the arrive
-      if (lane == 0) {
-        s_base[q] = excl;
-        mbar_arrive(&base_ready[q]);
-      }
-    }
-    return;
-  }
-
-  // ============================================================ compute warps
-  const bool need_depth = (depth != nullptr) || P.check_depth;
-  const T Wf = (T)P.width, Hf = (T)P.height;      // image bounds in the pixel dtype (exact: < 2^24)
-  const unsigned lt = (1u << lane) - 1u;
-  constexpr int kLag = kCtBufs - 1;         // a tile is scattered kLag iterations after its projection
-  unsigned mh[kLag][kCtPpt];                // ballots of tiles i-1 .. i-kLag
-  for (int i = 0; i < my_tiles + kLag; ++i) {
-    unsigned m[kCtPpt];
-    CT_T0();
-    if (i < my_tiles) {
-      const int s = i & 1, q = i % kCtBufs;
-      mbar_wait(&in_full[s], (uint32_t)((i >> 1) & 1));
-      if (warp == 0) CT_ACC(4);
-      const long long tile = tile_of(i);
-      const long long first = tile * kCtTile;
-      const int npts = (n - first) < kCtTile ? (int)(n - first) : kCtTile;
-      const T* sin = reinterpret_cast<const T*>(dyn_smem + s * SM::kIn);
-      T xin[kCtPpt][3];
-#pragma unroll
-      for (int k = 0; k < kCtPpt; ++k) {
-        const T* r = sin + 3 * (k * kCtThreads + tid);
-        xin[k][0] = r[0]; xin[k][1] = r[1]; xin[k][2] = r[2];
-      }
-      __syncwarp();
-      if (lane == 0 && atomicAdd(&s_consumed[s], 1) == kCtWarps - 1) {
-        s_consumed[s] = 0;                             // last warp to read the stage refills it
-        feed(i + 2);
-      }
-      UV* suv = reinterpret_cast<UV*>(dyn_smem + 2 * SM::kIn + q * SM::kOut);
-      double* sdep = reinterpret_cast<double*>(dyn_smem + 2 * SM::kIn + q * SM::kOut + kCtTile * 2 * sizeof(T));
-      const bool valid_words_tile = npts == kCtTile && (reinterpret_cast<uintptr_t>(valid_out) & 3) == 0;
-#ifndef PBK_CT_BATCH
-#define PBK_CT_BATCH 2
-#endif
-#if PBK_CT_BATCH > 0
-      constexpr int kB = PBK_CT_BATCH;          // points projected side by side (shared reciprocal slow path)
-      double ub[kCtPpt], vb[kCtPpt];
-#pragma unroll
-      for (int k0 = 0; k0 < kCtPpt; k0 += kB) {
-        double Xb[kB][3], u2[kB], v2[kB];
-#pragma unroll
-        for (int j = 0; j < kB; ++j) {
-          Xb[j][0] = (double)xin[k0 + j][0]; Xb[j][1] = (double)xin[k0 + j][1]; Xb[j][2] = (double)xin[k0 + j][2];
-        }
-        project_many<DIST, kB>(P, Xb, u2, v2);
-#pragma unroll
-        for (int j = 0; j < kB; ++j) { ub[k0 + j] = u2[j]; vb[k0 + j] = v2[j]; }
-      }
-#pragma unroll
-      for (int k = 0; k < kCtPpt; ++k) {
-        const int p = k * kCtThreads + tid;
-        const double Xp[3] = {(double)xin[k][0], (double)xin[k][1], (double)xin[k][2]};
-        const T uo = (T)ub[k], vo = (T)vb[k];
-#else
-#pragma unroll
-      for (int k = 0; k < kCtPpt; ++k) {
-        const int p = k * kCtThreads + tid;
-        const double Xp[3] = {(double)xin[k][0], (double)xin[k][1], (double)xin[k][2]};
-        double u, v;
-        project_one<DIST>(P, Xp, u, v);
-        const T uo = (T)u, vo = (T)v;
-#endif
-        bool good = p < npts;
-        if (need_depth) {
-          const double dep = depth_of(P, Xp);
-          if (depth != nullptr) sdep[p] = dep;
-          if (P.check_depth) good = good && (dep >= P.min_depth);
-        }
-        if (P.check_bounds) good = good && OutPix<T>::in_bounds(uo, vo, Wf, Hf);
-        suv[p] = OutPix<T>::make(uo, vo);
-        m[k] = __ballot_sync(0xffffffffu, good);
-        if (lane == 0) s_cnt[q][k * kCtWarps + warp] = __popc(m[k]);
-        if (valid_out != nullptr && !valid_words_tile && p < npts) valid_out[first + p] = good ? 1 : 0;
-      }
-      if (valid_out != nullptr && valid_words_tile) store_valid_rows(valid_out + first + warp * 32, m, kCtThreads, lane);
-      __syncwarp();
-      if (lane == 0) {
-        // The tile aggregate leaves the moment the last compute warp is done - never
-        // behind a look-back, or every successor tile would inherit that delay.
-        int wsum = 0;
-#pragma unroll
-        for (int k = 0; k < kCtPpt; ++k) wsum += __popc(m[k]);
-        atomicAdd(&s_aggsum[q], wsum);
-        __threadfence_block();
-        if (atomicAdd(&s_arrived[q], 1) == kCtWarps - 1) {
-          __threadfence_block();
-          const int total = atomicExch(&s_aggsum[q], 0);
-          s_arrived[q] = 0;
-          st_status(status + tile, kStateAgg | (unsigned long long)total);
-        }
-        mbar_arrive(&cnt_ready[q]);
-      }
-      if (warp == 0) CT_ACC(5);
-    }
-    if (i >= kLag) {
-      // scatter tile i-kLag (parked by this same thread kLag iterations ago)
-      const int j = i - kLag, q = j % kCtBufs;
-      mbar_wait(&base_ready[q], (uint32_t)((j / kCtBufs) & 1));
-      if (warp == 0) CT_ACC(6);
-      const long long base = s_base[q];
-      const UV* suv = reinterpret_cast<const UV*>(dyn_smem + 2 * SM::kIn + q * SM::kOut);
-      const double* sdep =
-          reinterpret_cast<const double*>(dyn_smem + 2 * SM::kIn + q * SM::kOut + kCtTile * 2 * sizeof(T));
-#pragma unroll
-      for (int k = 0; k < kCtPpt; ++k) {
-        if ((mh[kLag - 1][k] >> lane) & 1u) {
-          const int p = k * kCtThreads + tid;
-          const long long o = base + s_excl[q][k * kCtWarps + warp] + __popc(mh[kLag - 1][k] & lt);
-          OutPix<T>::store_vec(uv, o, suv[p]);
-          if (depth != nullptr) st_stream_d1(depth + o, sdep[p]);
-        }
-      }
-      if (warp == 0) CT_ACC(7);
-    }
-#pragma unroll
-    for (int k = 0; k < kCtPpt; ++k) {
-#pragma unroll
-      for (int a = kLag - 1; a > 0; --a) mh[a][k] = mh[a - 1][k];
-      mh[0][k] = m[k];
-    }
-  }
+  return good;
 }
 
-template <typename K>
-static int opt_in_smem(K kernel, int bytes) {
-  if (bytes > 48 * 1024) PBK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  return PBK_OK;
+__device__ __forceinline__ float lin4(const float (&c)[4], float x, float y, float z) {
+  return fmaf(c[0], x, fmaf(c[1], y, fmaf(c[2], z, c[3])));
+}
+
+// all CTAs of the (co-resident) grid; the counter only grows: target = gridDim.x * (#barriers so far)
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <typename T, bool DIST>
+__global__ void __launch_bounds__(kCpThreads, PBK_CP_MINB)
+project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv, double* __restrict__ depth,
+                       uint8_t* __restrict__ valid_out, long long* __restrict__ count,
+                       unsigned char* __restrict__ scratch, long long tiles_per_chunk,
+                       const __grid_constant__ pbk_project_params P, const __grid_constant__ ClassifyParams C) {
+  constexpr int NST = RingCfg<T>::kStages;
+  constexpr int kInBytes = CpTile<T>::kBytes;
+  extern __shared__ __align__(128) char dyn_smem[];
+  __shared__ int s_wtot[kCpWarps];
+  __shared__ long long s_red[2][kCpWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dyn_smem + kCpWarps * NST * kInBytes) + warp * NST;
+  WarpRing<kInBytes, NST> ring;
+  ring.init(dyn_smem + warp * NST * kInBytes, bars, lane);
+
+  unsigned* bar_ctr = reinterpret_cast<unsigned*>(scratch);
+  int* cta_tot = reinterpret_cast<int*>(scratch + 64);
+  char* xprime = reinterpret_cast<char*>(scratch + kCpCtlBytes);
+
+  const long long ntiles = (n + kTilePts - 1) / kTilePts;
+  const long long nfull = n / kTilePts;
+  const int nchunks = (int)((ntiles + tiles_per_chunk - 1) / tiles_per_chunk);
+  const long long NW = (long long)gridDim.x * kCpWarps, gw = (long long)blockIdx.x * kCpWarps + warp;
+  // this warp's run of tiles inside ANY chunk (clipped to the chunk's length): the same
+  // offsets in every chunk, so its X' region is private to it for the whole kernel
+  const long long run_a = gw * tiles_per_chunk / NW, run_b = (gw + 1) * tiles_per_chunk / NW;
+  char* const xp_mine = xprime + run_a * kInBytes;
+  const char* Xb = reinterpret_cast<const char*>(X);
+  const unsigned lt = (1u << lane) - 1u;
+  const bool valid_words = (reinterpret_cast<uintptr_t>(valid_out) & 3) == 0;
+  const uint64_t pol_stream = l2_policy_evict_first();
+
+  long long out_base = 0;          // valid points of the chunks before this one (identical in all CTAs)
+  int k = 0;                       // ring sequence number, continues across phases and chunks
+  for (int c = 0; c < nchunks; ++c) {
+    const long long chunk_t0 = (long long)c * tiles_per_chunk;
+    const long long chunk_tiles = (ntiles - chunk_t0) < tiles_per_chunk ? (ntiles - chunk_t0) : tiles_per_chunk;
+    const long long a = run_a < chunk_tiles ? run_a : chunk_tiles, b = run_b < chunk_tiles ? run_b : chunk_tiles;
+    const int my = (int)(b - a);
+
+    // ================================================================ phase A
+    int wtot = 0;
+    {
+      const long long t0 = chunk_t0 + a;
+      if (lane == 0)
+        for (int i = 0; i < NST - 1 && i < my; ++i)
+          if (t0 + i < nfull) ring.issue_hint(k + i, Xb + (t0 + i) * kInBytes, pol_stream);
+      for (int i = 0; i < my; ++i, ++k) {
+        const long long tile = t0 + i;
+        if (lane == 0 && i + NST - 1 < my && tile + NST - 1 < nfull)
+          ring.issue_hint(k + NST - 1, Xb + (tile + NST - 1) * kInBytes, pol_stream);
+        const long long first = tile * kTilePts;
+        const int npts = (n - first) < kTilePts ? (int)(n - first) : kTilePts;
+        char* st = ring.slot(k);
+        if (tile >= nfull) {
+          warp_load_ragged(Xb + first * 3 * sizeof(T), st, lane, kInBytes, npts * 3 * (int)sizeof(T));
+          __syncwarp();
+          if (lane == 0) ring.skip(k);        // keep the slot's barrier phase in step
+        }
+        ring.wait(k);
+        T xin[4][3];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const T* r = reinterpret_cast<const T*>(st) + 3 * (j * 32 + lane);
+          xin[j][0] = r[0]; xin[j][1] = r[1]; xin[j][2] = r[2];
+        }
+        __syncwarp();                       // slot may be refilled from here on
+        bool ok[4], amb[4];
+        bool any_amb = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (DIST) {
+            ok[j] = false;
+            amb[j] = true;
+          } else {
+            const float x = (float)xin[j][0], y = (float)xin[j][1], z = (float)xin[j][2];
+            const float band = C.kappa * (fabsf(x) + fabsf(y) + fabsf(z) + 1.0f);
+            bool in = true, out = false;
+            if (P.check_depth) {
+              const float ld = lin4(C.d, x, y, z);
+              in = ld > band;
+              out = ld < -band;
+            }
+            if (P.check_bounds) {
+              const float zc = fabsf(lin4(C.z, x, y, z));
+              const float lu = fabsf(lin4(C.cu, x, y, z)), lv = fabsf(lin4(C.cv, x, y, z));
+              const float hw = C.hw * zc, hh = C.hh * zc;
+              const bool zdef = zc > band;
+              in = in && zdef && (lu < hw - band) && (lv < hh - band);
+              out = out || (zdef && ((lu > hw + band) || (lv > hh + band)));
+            }
+            ok[j] = in && !out;
+            amb[j] = !(in || out);          // NaN / inf / borderline: neither is provable
+          }
+          if (j * 32 + lane >= npts) { ok[j] = false; amb[j] = false; }
+          any_amb = any_amb || amb[j];
+        }
+        if (__any_sync(0xffffffffu, any_amb)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (amb[j]) ok[j] = exact_valid<T, DIST>(P, xin[j][0], xin[j][1], xin[j][2]);
+        }
+        unsigned mv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mv[j] = __ballot_sync(0xffffffffu, ok[j]);
+        if (valid_out != nullptr) {
+          if (npts == kTilePts && valid_words) {
+            store_valid_rows(valid_out + first, mv, 32, lane);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j * 32 + lane < npts) valid_out[first + j * 32 + lane] = ok[j] ? 1 : 0;
+          }
+        }
+        // the warp's valid points, in order, to the front of its X' region
+        T* xp = reinterpret_cast<T*>(xp_mine);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (ok[j]) {
+            T* dst = xp + 3ll * (wtot + __popc(mv[j] & lt));
+            dst[0] = xin[j][0]; dst[1] = xin[j][1]; dst[2] = xin[j][2];
+          }
+          wtot += __popc(mv[j]);
+        }
+      }
+    }
+    if (lane == 0) s_wtot[warp] = wtot;
+    // X' was written with generic-proxy stores and is read back by TMA (async proxy)
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < kCpWarps; ++w) tot += s_wtot[w];
+      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(cta_tot + (c & 1) * kCpMaxGrid + blockIdx.x), "r"(tot) : "memory");
+    }
+    grid_barrier(bar_ctr, gridDim.x * (unsigned)(c + 1));
+
+    // ================================================================ offsets
+    long long before = 0, total = 0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kCpThreads) {
+      int v;
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cta_tot + (c & 1) * kCpMaxGrid + i) : "memory");
+      total += v;
+      if (i < (int)blockIdx.x) before += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      before += __shfl_xor_sync(0xffffffffu, before, o);
+      total += __shfl_xor_sync(0xffffffffu, total, o);
+    }
+    if (lane == 0) { s_red[0][warp] = before; s_red[1][warp] = total; }
+    __syncthreads();
+    long long my_out = out_base;
+#pragma unroll
+    for (int w = 0; w < kCpWarps; ++w) {
+      my_out += s_red[0][w];
+      out_base += s_red[1][w];
+      if (w < warp) my_out += s_wtot[w];
+    }
+
+    // ================================================================ phase B
+    {
+      asm volatile("fence.proxy.async;" ::: "memory");
+      const int nt = (wtot + kTilePts - 1) / kTilePts;
+      auto bytes_of = [&](int t) -> uint32_t {
+        const int pts = (wtot - t * kTilePts) < kTilePts ? (wtot - t * kTilePts) : kTilePts;
+        return (uint32_t)((pts * 3 * (int)sizeof(T) + 15) & ~15);
+      };
+      if (lane == 0)
+        for (int t = 0; t < NST - 1 && t < nt; ++t) ring.issue_bytes(k + t, xp_mine + (long long)t * kInBytes, bytes_of(t));
+      for (int t = 0; t < nt; ++t, ++k) {
+        if (lane == 0 && t + NST - 1 < nt)
+          ring.issue_bytes(k + NST - 1, xp_mine + (long long)(t + NST - 1) * kInBytes, bytes_of(t + NST - 1));
+        const int pts = (wtot - t * kTilePts) < kTilePts ? (wtot - t * kTilePts) : kTilePts;
+        ring.wait(k);
+        char* st = ring.slot(k);
+        double Xp[4][3];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j * 32 + lane < pts) stage_read_point<T>(st, j * 32 + lane, Xp[j]);
+          else { Xp[j][0] = 0.0; Xp[j][1] = 0.0; Xp[j][2] = 1.0; }
+        }
+        __syncwarp();
+        double ud[4], vd[4];
+        project_many<DIST, 4>(P, Xp, ud, vd);
+        const long long o0 = my_out + (long long)t * kTilePts;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j * 32 + lane < pts) {
+            OutPix<T>::store(uv, o0 + j * 32 + lane, (T)ud[j], (T)vd[j]);
+            if (depth != nullptr) st_stream_d1(depth + o0 + j * 32 + lane, depth_of(P, Xp[j]));
+          }
+        }
+      }
+    }
+    __syncthreads();        // s_wtot / s_red are rewritten by the next chunk
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && count != nullptr) *count = out_base;
 }
 
 template <typename TI, typename TO>
@@ -638,10 +602,12 @@ static int launch_transform(const void* X, int64_t n, const XformParams& P, void
   constexpr int NST = RingCfg<TI>::kStages;
   const int smem = kWarps * (NST * kTilePts * 3 * (int)sizeof(TI) + kTilePts * 3 * (int)sizeof(TO)) + kWarps * NST * 8;
   auto kern = transform_points_kernel<TI, TO>;
-  int rc = opt_in_smem(kern, smem);
+  static KernelCache kc;
+  int per_sm;
+  int rc = kc.setup(di, kern, kWarps * 32, smem, &per_sm);
   if (rc) return rc;
   const long long ntiles = (n + kTilePts - 1) / kTilePts;
-  const int grid = resident_grid(di, kern, kWarps * 32, smem, (ntiles + kWarps - 1) / kWarps);
+  const int grid = resident_grid(di, per_sm, (ntiles + kWarps - 1) / kWarps);
   kern<<<grid, kWarps * 32, smem, s>>>(static_cast<const TI*>(X), n, static_cast<TO*>(Y), P);
   PBK_CHECK_LAUNCH("transform_points_kernel");
   return PBK_OK;
@@ -654,34 +620,84 @@ static int launch_project(const void* X, int64_t n, const pbk_project_params& P,
   constexpr int NST = RingCfg<T>::kStages;
   const int smem = kWarps * NST * kTilePts * 3 * (int)sizeof(T) + kWarps * NST * 8;
   auto kern = project_points_kernel<T, DIST, MODE>;
-  int rc = opt_in_smem(kern, smem);
+  static KernelCache kc;
+  int per_sm;
+  int rc = kc.setup(di, kern, kWarps * 32, smem, &per_sm);
   if (rc) return rc;
   const long long ncta = (n + kCtaPts - 1) / kCtaPts;
-  const int grid = resident_grid(di, kern, kWarps * 32, smem, ncta);
+  const int grid = resident_grid(di, per_sm, ncta);
   kern<<<grid, kWarps * 32, smem, s>>>(static_cast<const T*>(X), n, static_cast<T*>(uv), depth, valid,
                                        reinterpret_cast<long long*>(count), P);
   PBK_CHECK_LAUNCH("project_points_kernel");
   return PBK_OK;
 }
 
+static void classify_params(const pbk_project_params& P, ClassifyParams* C) {
+  // linear forms in double, rounded once to float; kappa covers the fp32 evaluation (<= 5 x
+  // 2^-24 of max|coefficient| x (|X|+|Y|+|Z|+1), inputs rounded to float included), the fp32
+  // rounding of (W/2)|zc|, and the final rounding of the reference's pixel to the output dtype
+  // (2^-24 |u| |zc|), with a > 4x margin
+  const double W = P.width, H = P.height;
+  const double zr[4] = {P.R[6], P.R[7], P.R[8], P.t[2]};
+  const double xr[4] = {P.R[0], P.R[1], P.R[2], P.t[0]};
+  const double yr[4] = {P.R[3], P.R[4], P.R[5], P.t[1]};
+  double mz = 0, mu = 0, mv = 0, md = 0;
+  for (int i = 0; i < 4; ++i) {
+    const double cu = P.fx * xr[i] + (P.cx - 0.5 * W) * zr[i];
+    const double cv = P.fy * yr[i] + (P.cy - 0.5 * H) * zr[i];
+    const double d = i < 3 ? P.Rz[i] : (P.tz - P.min_depth);
+    C->z[i] = (float)zr[i]; C->cu[i] = (float)cu; C->cv[i] = (float)cv; C->d[i] = (float)d;
+    mz = fmax(mz, fabs(zr[i]));
+    mu = fmax(mu, fabs(P.fx * xr[i]) + (fabs(P.cx) + W) * fabs(zr[i]));
+    mv = fmax(mv, fabs(P.fy * yr[i]) + (fabs(P.cy) + H) * fabs(zr[i]));
+    md = fmax(md, i < 3 ? fabs(P.Rz[i]) : fabs(P.tz) + fabs(P.min_depth));
+  }
+  C->hw = (float)(0.5 * W);
+  C->hh = (float)(0.5 * H);
+  C->kappa = (float)(4e-6 * fmax(fmax(mu + W * mz, mv + H * mz), fmax(md, mz)));
+}
+
+static long long compact_tiles_per_chunk(long long n, size_t elem) {
+  long long mb = PBK_CP_CHUNK_MB;
+  if (const char* e = getenv("PBK_COMPACT_CHUNK_MB")) {
+    const long long v = atoll(e);
+    if (v >= 1 && v <= 4096) mb = v;
+  }
+  const long long tile_bytes = (long long)kTilePts * 3 * (long long)elem;
+  const long long ntiles = (n + kTilePts - 1) / kTilePts;
+  long long cap = (mb << 20) / tile_bytes;
+  if (cap < 1) cap = 1;
+  const long long nchunks = (ntiles + cap - 1) / cap;
+  long long tpc = nchunks > 0 ? (ntiles + nchunks - 1) / nchunks : 1;       // equal chunks
+  return tpc < 1 ? 1 : tpc;
+}
+
 template <typename T, bool DIST>
 static int launch_compact(const void* X, int64_t n, const pbk_project_params& P, void* uv,
                           double* depth, uint8_t* valid, int64_t* count, void* scratch, cudaStream_t s,
                           const DeviceInfo* di) {
-  constexpr int smem = CompactSmem<T>::kBytes;
+  constexpr int NST = RingCfg<T>::kStages;
+  constexpr int smem = kCpWarps * NST * CpTile<T>::kBytes + kCpWarps * NST * 8;
   auto kern = project_compact_kernel<T, DIST>;
-  int rc = opt_in_smem(kern, smem + 1024);
+  static KernelCache kc;
+  int per_sm;
+  int rc = kc.setup(di, kern, kCpThreads, smem, &per_sm);
   if (rc) return rc;
-  const long long ntiles = (n + kCtTile - 1) / kCtTile;
-  const int grid = resident_grid(di, kern, kCtBlock, smem, ntiles);
+  const long long ntiles = (n + kTilePts - 1) / kTilePts;
+  int grid = resident_grid(di, per_sm, (ntiles + kCpWarps - 1) / kCpWarps);
+  if (grid > kCpMaxGrid) grid = kCpMaxGrid;
   const T* Xp = static_cast<const T*>(X);
   long long nn = n;
   T* uvp = static_cast<T*>(uv);
   long long* cnt = reinterpret_cast<long long*>(count);
-  unsigned long long* scr = static_cast<unsigned long long*>(scratch);
+  unsigned char* scr = static_cast<unsigned char*>(scratch);
+  long long tpc = compact_tiles_per_chunk(n, sizeof(T));
   pbk_project_params Pc = P;
-  void* args[] = {&Xp, &nn, &uvp, &depth, &valid, &cnt, &scr, &Pc};
-  PBK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(kCtBlock), args,
+  ClassifyParams C;
+  classify_params(P, &C);
+  PBK_CUDA(cudaMemsetAsync(scratch, 0, 64, s));                  // the grid-barrier counter
+  void* args[] = {&Xp, &nn, &uvp, &depth, &valid, &cnt, &scr, &tpc, &Pc, &C};
+  PBK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(kCpThreads), args,
                                        smem, s));
   return PBK_OK;
 }
@@ -725,10 +741,13 @@ PBK_API int pbk_debug_compact_clocks(unsigned long long out[16], int reset) {
 }
 #endif
 
-size_t pbk_project_scratch_bytes(int64_t n) {
+size_t pbk_project_scratch_bytes(int64_t n, int in_dtype) {
   if (n < 0) n = 0;
-  const long long ntiles = (n + pbk::kCtaPts - 1) / pbk::kCtaPts;
-  return (size_t)(2 * ntiles + 4) * 8;          // tile status words + one prefix word per generation
+  const size_t elem = in_dtype == PBK_F64 ? 8 : 4;
+  const long long tpc = pbk::compact_tiles_per_chunk(n, elem);
+  // control words + the X' region of one chunk (+ one tile of slack for the 16-byte rounding of
+  // the last bulk copy)
+  return pbk::kCpCtlBytes + (size_t)(tpc + 1) * pbk::kTilePts * 3 * elem;
 }
 
 int pbk_project_points(const void* X, int in_dtype, int64_t n, const pbk_project_params* params,
@@ -755,15 +774,9 @@ int pbk_project_points(const void* X, int in_dtype, int64_t n, const pbk_project
   int rc = current_device_info(&di);
   if (rc) return rc;
   const bool plain = !P.compact && !P.check_depth && !P.check_bounds && depth == nullptr && valid == nullptr;
-  if (P.compact) PBK_CUDA(cudaMemsetAsync(scratch, 0, pbk_project_scratch_bytes(n), s));
-  else if (count != nullptr) {
-    if (plain) {
-      const int64_t all = n;            // pageable source: staged before the call returns
-      PBK_CUDA(cudaMemcpyAsync(count, &all, 8, cudaMemcpyHostToDevice, s));
-    } else {
-      PBK_CUDA(cudaMemsetAsync(count, 0, 8, s));
-    }
-  }
+  // plain: the kernel writes count = n itself; masks: the warps add into a zeroed word;
+  // compact: the kernel writes the total
+  if (!P.compact && !plain && count != nullptr) PBK_CUDA(cudaMemsetAsync(count, 0, 8, s));
   const bool dist = P.has_distortion != 0;
   const int mode = plain ? 0 : (P.compact ? 2 : 1);
 #define PBK_DISPATCH(T)                                                                       \

@@ -63,15 +63,29 @@ class PeerKeyExchange(object):
     """Peer-mapped exchange buffer of the fused matcher exchanges
     (pbk_hamming_knn2_dist / pbk_hamming_gather_best_dist) for `nq` queries: a
     torch symmetric-memory allocation whose per-rank addresses are handed to the
-    kernels.  Collective: every rank of `group` must construct it."""
+    kernels.  Collective: every rank of `group` must construct it.
 
-    def __init__(self, nq, group=None):
+    `status` is the word the kernels set when a peer does not arrive within the
+    exchange timeout (pbk_set_exchange_timeout_ms); `check()` raises on it."""
+
+    def __init__(self, nq, group=None, _emulated=None):
         import ctypes
         import torch
+        self.nq = int(nq)
+        self.seq = 0
+        self.status = _ffi.StatusWord()
+        if _emulated is not None:
+            # (rank, world, buffers): `world` ranks of ONE process on one device, each with its
+            # own stream - the single-GPU tests of the exchange protocol
+            self.rank, self.world, bufs = _emulated
+            self.buf = bufs[self.rank]
+            self.done = torch.zeros(4, dtype=torch.int32, device=self.buf.device)
+            self.ptrs = (ctypes.c_uint64 * self.world)(*[int(b.data_ptr()) for b in bufs])
+            return
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         group = group if group is not None else dist.group.WORLD
-        self.nq, self.world, self.rank = int(nq), dist.get_world_size(group), dist.get_rank(group)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         dev = torch.device("cuda", torch.cuda.current_device())
         words = int(_ffi.lib().pbk_hamming_exchange_words(self.nq, self.world))
         self.buf = symm_mem.empty(max(words, 64), dtype=torch.int64, device=dev)
@@ -81,7 +95,17 @@ class PeerKeyExchange(object):
         torch.cuda.synchronize()
         dist.barrier(group)                                  # every buffer is zero before the first store
         self.ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
-        self.seq = 0
+
+    @classmethod
+    def emulated(cls, nq, world):
+        """`world` exchanges that share plain device buffers of the current device."""
+        import torch
+        words = int(_ffi.lib().pbk_hamming_exchange_words(int(nq), int(world)))
+        bufs = [torch.zeros(max(words, 64), dtype=torch.int64, device="cuda") for _ in range(world)]
+        return [cls(nq, _emulated=(r, world, bufs)) for r in range(world)]
+
+    def check(self):
+        self.status.check("fused key/row exchange of the sharded matcher")
 
 
 class ShardedKeyframeMatcher(object):
@@ -112,6 +136,17 @@ class ShardedKeyframeMatcher(object):
         self.fused = exchange == "p2p" and self.world > 1
         self._px = None
 
+    def use_exchange(self, px):
+        """Adopt a prepared PeerKeyExchange (e.g. an emulated one): rank / world come from it."""
+        self._px, self.rank, self.world, self.fused = px, px.rank, px.world, True
+        return self
+
+    def check(self):
+        """Raises RuntimeError if a fused exchange of an EARLIER, finished call timed out
+        (call after synchronising; match() also checks at its start)."""
+        if self._px is not None:
+            self._px.check()
+
     def local_keys(self, q):
         return self.kernels.knn2(q, self.shard, self.shard_base)
 
@@ -137,6 +172,7 @@ class ShardedKeyframeMatcher(object):
         if self._px is None or self._px.nq != nq:
             self._px = PeerKeyExchange(nq, self.group)               # collective, once per query count
         px = self._px
+        px.check()                                                   # a timeout of the previous call
         px.seq += 1
         L, s = _ffi.lib(), _ffi.stream_ptr()
         splits, nbytes = ctypes.c_int(0), ctypes.c_size_t(0)
@@ -147,7 +183,7 @@ class ShardedKeyframeMatcher(object):
             events[0].record()
         _ffi.check(L.pbk_hamming_knn2_dist(_ffi.ptr(q), nq, _ffi.ptr(self.shard) if nt else None, nt,
                                            self.shard_base, _ffi.ptr(keys), _ffi.ptr(scratch), px.ptrs, px.rank,
-                                           px.world, px.seq, _ffi.ptr(px.done), s))
+                                           px.world, px.seq, _ffi.ptr(px.done), px.status.ptr, s))
         if events is not None:
             events[1].record()
         rev = None
@@ -155,7 +191,7 @@ class ShardedKeyframeMatcher(object):
             rows = T.empty((nq, 32), dtype=T.uint8, device=q.device)
             _ffi.check(L.pbk_hamming_gather_best_dist(_ffi.ptr(self.shard) if nt else None, nt, self.shard_base,
                                                       _ffi.ptr(keys), nq, _ffi.ptr(rows), px.ptrs, px.rank,
-                                                      px.world, px.seq, _ffi.ptr(px.done), s))
+                                                      px.world, px.seq, _ffi.ptr(px.done), px.status.ptr, s))
             rev = ops.hamming_knn2_keys(rows, q, 0)
         return ops.hamming_ratio_mutual(keys, rev, ratio)
 
@@ -174,16 +210,30 @@ class ShardedKeyframeMatcher(object):
             rev = self.kernels.knn2(rows, q, 0)
         return self.kernels.ratio_mutual(keys, rev, ratio)
 
+    def match_host(self, q, ratio=0.75, mutual=True):
+        """match() with numpy results; raises RuntimeError if a peer timed out in this call."""
+        out = [_ffi.to_host(x) for x in self.match(q, ratio, mutual)]
+        self.check()
+        return out
+
 
 class PeerCostExchange(object):
     """Peer-mapped exchange buffer for the fused BA cost all-reduce
-    (pbk_ba_residual_jacobian_dist): a torch symmetric-memory allocation whose
+    (pbk_ba_evaluate / pbk_ba_residual_jacobian_dist): a torch symmetric-memory allocation whose
     per-rank addresses are handed to the kernel, which stores / polls them over
-    NVLink itself.  Collective: every rank of `group` must construct it."""
+    NVLink itself.  Collective: every rank of `group` must construct it.  The call
+    sequence lives on the device (behind the problem's cost partials), so the call can
+    be replayed from a CUDA graph."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, _emulated=None):
         import ctypes
         import torch
+        self.status = _ffi.StatusWord()
+        if _emulated is not None:
+            self.rank, self.world, bufs = _emulated
+            self.buf = bufs[self.rank]
+            self.ptrs = (ctypes.c_uint64 * self.world)(*[int(b.data_ptr()) for b in bufs])
+            return
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         group = group if group is not None else dist.group.WORLD
@@ -195,11 +245,16 @@ class PeerCostExchange(object):
         torch.cuda.synchronize()
         dist.barrier(group)                                  # every buffer is zero before the first store
         self.ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
-        self.seq = 0
 
-    def next_seq(self):
-        self.seq += 1
-        return self.seq
+    @classmethod
+    def emulated(cls, world):
+        """`world` exchanges sharing plain device buffers of the current device (tests)."""
+        import torch
+        bufs = [torch.zeros(max(64, 4 * world), dtype=torch.int64, device="cuda") for _ in range(world)]
+        return [cls(_emulated=(r, world, bufs)) for r in range(world)]
+
+    def check(self):
+        self.status.check("fused cost all-reduce of the sharded BA")
 
 
 class ShardedBA(object):
@@ -229,11 +284,19 @@ class ShardedBA(object):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
         self.exchange = PeerCostExchange(group) if (exchange == "p2p" and self.world > 1) else None
 
-    def evaluate(self):
+    def evaluate(self, graph=False):
         """Evaluates the local residuals/Jacobians (they stay on the owning
-        rank) and returns the global cost tensor (1,) float64, all-reduced."""
+        rank) and returns the global cost tensor (1,) float64, all-reduced.
+        graph=True (CUDA path) replays the evaluation from a captured CUDA graph."""
         if self.exchange is not None:
-            self.problem.evaluate(exchange=self.exchange)      # cost is already global
+            self.exchange.check()                              # a timeout of an earlier call
+            if graph:
+                self.problem.evaluate_graphed(exchange=self.exchange)
+            else:
+                self.problem.evaluate(exchange=self.exchange)  # cost is already global
+            return self.problem.cost
+        if graph and self.world == 1:
+            self.problem.evaluate_graphed()
             return self.problem.cost
         self.problem.evaluate()
         cost = self.problem.cost
@@ -241,3 +304,10 @@ class ShardedBA(object):
             cost = cost.clone()
             self.dist.all_reduce(cost, op=self.dist.ReduceOp.SUM, group=self.group)
         return cost
+
+    def cost_host(self, graph=False):
+        """evaluate() -> float; raises RuntimeError if a peer timed out in this call."""
+        v = float(self.evaluate(graph=graph).item())
+        if self.exchange is not None:
+            self.exchange.check()
+        return v

@@ -135,7 +135,8 @@ class Projector(object):
             count = T.empty((1,), dtype=T.int64, device=Xd.device)
             scratch = None
             if self.compact:
-                nbytes = _ffi.lib().pbk_project_scratch_bytes(n)
+                nbytes = _ffi.lib().pbk_project_scratch_bytes(
+                    n, _ffi.PBK_F32 if Xd.dtype == T.float32 else _ffi.PBK_F64)
                 scratch = T.empty((max(nbytes, 16),), dtype=T.uint8, device=Xd.device)
             self._bufs = (key, uv, depth, valid, count, scratch)
         return self._bufs[1:]
@@ -241,7 +242,8 @@ def _project_compact_streamed(pr, Xh, return_depth, return_valid):
     counts = T.zeros((len(chunks),), dtype=T.int64, device="cuda")
     counts_h = _pipeline.host_out((len(chunks),), T.int64)
     rows = max(hi - lo for lo, hi in chunks)
-    scratch = T.empty((max(L.pbk_project_scratch_bytes(rows), 16),), dtype=T.uint8, device="cuda")
+    scratch = T.empty((max(L.pbk_project_scratch_bytes(
+        rows, _ffi.PBK_F32 if Xh.dtype == T.float32 else _ffi.PBK_F64), 16),), dtype=T.uint8, device="cuda")
     uv_h = _pipeline.host_out((n, 2), uv.dtype)
     dp_h = _pipeline.host_out((n,), T.float64) if return_depth else None
     vd_h = _pipeline.host_out((n,), T.uint8) if return_valid else None
@@ -317,7 +319,9 @@ def reproject_disparity(disp, Q, sample=1, bgr=None):
             if ch.dtype != T.uint8 or tuple(ch.shape) != (B, H, W, 3):
                 raise ValueError("colour image must be uint8 (H, W, 3) matching the disparity")
         per_frame = H * W * (dh.element_size() + (3 if ch is not None else 0)) + Hs * Ws * (12 + (3 if ch is not None else 0))
-        chunks = _pipeline.plan(B, per_frame)
+        # chunk starts must keep every plane's pointer 16-byte aligned (odd-sized uint8 frames)
+        planes = [H * W * dh.element_size(), Hs * Ws * 12] + ([H * W * 3, Hs * Ws * 3] if ch is not None else [])
+        chunks = _pipeline.plan(B, per_frame, plane_row_bytes=planes)
         if len(chunks) > 1:
             d = T.empty((B, H, W), dtype=dh.dtype, device="cuda")
             xyz = T.empty((B, Hs, Ws, 3), dtype=T.float32, device="cuda")
@@ -579,7 +583,8 @@ def depth_reconstruct(depth, xs, ys, skip=1):
         dh = _pipeline.as_host_tensor(depth)
         B, H, W = (int(v) for v in dh.shape)
         Hs, Ws, xs_d, ys_d = meshes(H, W)
-        chunks = _pipeline.plan(B, H * W * dh.element_size() + Hs * Ws * 24)
+        chunks = _pipeline.plan(B, H * W * dh.element_size() + Hs * Ws * 24,
+                                plane_row_bytes=[H * W * dh.element_size(), Hs * Ws * 24])
         if len(chunks) > 1:
             d = T.empty((B, H, W), dtype=dh.dtype, device="cuda")
             out = T.empty((B, Hs, Ws, 3), dtype=T.float64, device="cuda")
@@ -792,6 +797,7 @@ class BAProblemDevice(object):
             obs[:, 0], obs[:, 1] = oc, op
             obs[:, 2:] = ouv.contiguous().view(T.int32)
             self.obs = obs
+            self.sorted_by_camera = bool(oc.numel() < 2 or bool((oc[1:] >= oc[:-1]).all()))
         else:
             oc = np.asarray(obs_cam, np.int32)
             op = np.asarray(obs_pt, np.int32)
@@ -802,6 +808,8 @@ class BAProblemDevice(object):
             packed[:, 0], packed[:, 1] = oc, op
             packed[:, 2:] = np.ascontiguousarray(obs_uv, np.float32).view(np.int32)
             self.obs, _ = _ffi.to_device(packed)
+            # camera-sorted observations (the usual BA layout) take the one-kernel route
+            self.sorted_by_camera = bool(oc.size < 2 or np.all(oc[1:] >= oc[:-1]))
         self.n_obs = int(self.obs.shape[0])
         O = max(self.n_obs, 1)
         dev = "cuda"
@@ -812,14 +820,16 @@ class BAProblemDevice(object):
         slots = _ffi.lib().pbk_ba_cost_slots(self.n_obs)
         if slots < 0:
             _ffi.check(_ffi.PBK_ECUDA)
-        self.partials = T.zeros((max(slots, 1),), dtype=T.float64, device=dev)
+        self.partials = T.zeros((max(slots, 2),), dtype=T.float64, device=dev)
         self.cost = T.zeros((1,), dtype=T.float64, device=dev)
+        self._graph = None
 
-    def evaluate(self, events=None, exchange=None):
+    def evaluate(self, events=None, exchange=None, two_kernels=False):
         """One residual + Jacobian evaluation (asynchronous on the current stream).
-        Without `events` it is ONE C-ABI call (pbk_ba_evaluate): the per-camera precompute,
-        then the streaming kernel launched with programmatic stream serialization so its
-        prologue overlaps the precompute.
+        Without `events` it is ONE C-ABI call (pbk_ba_evaluate) and, for camera-sorted
+        observations, ONE kernel: the streaming kernel derives the camera blocks its CTAs need
+        in its prologue.  Unsorted observations (or two_kernels=True) run the per-camera
+        precompute first, the streaming kernel launched with programmatic stream serialization.
         `events`: optional (start, end) CUDA events recorded around the streaming
         kernel alone (two separate calls, the precompute stays outside), for roofline timing.
         `exchange`: a distributed.PeerCostExchange - the kernel then also performs the
@@ -830,10 +840,13 @@ class BAProblemDevice(object):
                _ffi.ptr(self.cost))
         K = (self.fx, self.fy, self.cx, self.cy)
         if events is None:
-            ex = ((exchange.ptrs, exchange.rank, exchange.world, exchange.next_seq())
-                  if exchange is not None else (None, 0, 1, 0))
+            # seq = 0: the call sequence of the fused exchange lives on the device, so the
+            # same call can be captured in a CUDA graph and replayed
+            ex = ((exchange.ptrs, exchange.rank, exchange.world, 0, exchange.status.ptr)
+                  if exchange is not None else (None, 0, 1, 0, None))
             _ffi.check(L.pbk_ba_evaluate(
-                _ffi.ptr(self.obs), self.n_obs, _ffi.ptr(self.points), self.n_points,
+                _ffi.ptr(self.obs), self.n_obs, int(self.sorted_by_camera and not two_kernels),
+                _ffi.ptr(self.points), self.n_points,
                 _ffi.ptr(self.rvec), _ffi.ptr(self.tvec), self.n_cams, _ffi.ptr(self.cam_blocks),
                 *(K + out + ex + (s,))))
             return self
@@ -844,10 +857,30 @@ class BAProblemDevice(object):
                 _ffi.ptr(self.cam_blocks), self.n_cams) + K + out
         if exchange is not None:
             _ffi.check(L.pbk_ba_residual_jacobian_dist(
-                *(head + (exchange.ptrs, exchange.rank, exchange.world, exchange.next_seq(), s))))
+                *(head + (exchange.ptrs, exchange.rank, exchange.world, 0, exchange.status.ptr, s))))
         else:
             _ffi.check(L.pbk_ba_residual_jacobian(*(head + (s,))))
         events[1].record()
+        return self
+
+    def evaluate_graphed(self, exchange=None):
+        """evaluate() replayed from a CUDA graph captured on first use (fixed buffers; the
+        inputs rvec / tvec / points are updated in place between calls).  One graph launch
+        instead of a ctypes call + kernel launch per LM iteration."""
+        T = self.T
+        if self._graph is None or self._graph[1] is not exchange:
+            side = T.cuda.Stream()
+            side.wait_stream(T.cuda.current_stream())
+            with T.cuda.stream(side):
+                self.evaluate(exchange=exchange)           # warm-up outside capture (attributes, lazy init)
+            T.cuda.current_stream().wait_stream(side)
+            T.cuda.synchronize()
+            g = T.cuda.CUDAGraph()
+            with T.cuda.graph(g):
+                self.evaluate(exchange=exchange)
+            self._graph = (g, exchange)
+            return self                                     # the warm-up call WAS this evaluation
+        self._graph[0].replay()
         return self
 
 

@@ -28,6 +28,57 @@ class DMatch(object):
             self.queryIdx, self.trainIdx, self.imgIdx, self.distance)
 
 
+class KnnMatches(object):
+    """What knnMatch returns: a read-only sequence of rows of DMatch (row i = the <= k
+    neighbours of query i, ascending distance), exactly the shape cv2 returns, backed by the
+    result ARRAYS.  DMatch objects are built when a row is indexed or iterated, not in the
+    call: 4000 Python objects per frame cost more host time than the whole 8-GPU database
+    scan.  `.arrays` exposes the columns for vectorised use (Lowe ratio in one numpy line).
+    Compares equal to the equivalent list of lists."""
+    __slots__ = ("_q", "_tr", "_img", "_dist", "_n", "arrays")
+
+    def __init__(self, query_rows, trainIdx, imgIdx, dist, counts, arrays=None):
+        self._q, self._tr, self._img, self._dist, self._n = query_rows, trainIdx, imgIdx, dist, counts
+        self.arrays = arrays
+
+    def __len__(self):
+        return len(self._q)
+
+    def _row(self, r):
+        i = int(self._q[r])
+        return [DMatch(i, self._tr[i, j], self._img[i, j], self._dist[i, j]) for j in range(int(self._n[r]))]
+
+    def __getitem__(self, r):
+        if isinstance(r, slice):
+            return [self._row(x) for x in range(*r.indices(len(self)))]
+        if r < 0:
+            r += len(self)
+        if not 0 <= r < len(self):
+            raise IndexError("match row out of range")
+        return self._row(r)
+
+    def __iter__(self):
+        for r in range(len(self)):
+            yield self._row(r)
+
+    def __eq__(self, other):
+        try:
+            return len(other) == len(self) and all(
+                len(a) == len(b) and all(_same_match(x, y) for x, y in zip(a, b)) for a, b in zip(self, other))
+        except TypeError:
+            return NotImplemented
+
+    def tolist(self):
+        return list(self)
+
+    def __repr__(self):
+        return "KnnMatches(%d query rows)" % len(self)
+
+
+def _same_match(a, b):
+    return (a.queryIdx, a.trainIdx, a.imgIdx, a.distance) == (b.queryIdx, b.trainIdx, b.imgIdx, b.distance)
+
+
 class KeyframeDatabase(object):
     """A collection of per-keyframe descriptor matrices resident in HBM as one
     contiguous (N,32) uint8 tensor + row offsets (global row = offset[imgIdx]
@@ -67,13 +118,29 @@ class KeyframeDatabase(object):
                 self.reserve(self._n + k)
                 self._buf[self._n:self._n + k].copy_(dd)
                 self._n += k
-            self._host.append(d)
+            if self._host is not None:
+                self._host.append(d)
             self.offsets = np.append(self.offsets, self.offsets[-1] + k)
+
+    @classmethod
+    def from_flat(cls, flat, rows_per_image):
+        """Adopt a device-resident (N,32) uint8 tensor that holds N / rows_per_image keyframes
+        of equal size back to back (no copy; getTrainDescriptors() is not available)."""
+        db = cls()
+        n = int(flat.shape[0])
+        if n % int(rows_per_image):
+            raise ValueError("the flat database is not a whole number of keyframes")
+        db._buf, db._n = flat, n
+        db.offsets = np.arange(0, n + 1, int(rows_per_image), dtype=np.int64)
+        db._host = None
+        return db
 
     def clear(self):
         self.__init__()
 
     def descriptors(self):
+        if self._host is None:
+            raise RuntimeError("this database adopted a device tensor; the host descriptors were never held")
         return list(self._host)
 
     def __len__(self):
@@ -88,51 +155,106 @@ class KeyframeDatabase(object):
 
     def split_global(self, g):
         """global rows -> (imgIdx, trainIdx)."""
-        g = np.asarray(g, np.int64)
-        img = np.searchsorted(self.offsets, g, side="right") - 1
-        img = np.clip(img, 0, max(len(self.offsets) - 2, 0))
-        return img.astype(np.int32), (g - self.offsets[img]).astype(np.int32)
+        return _split_global(self.offsets, g)
 
 
 class BFMatcher(object):
-    """cv2.BFMatcher(normType=cv2.NORM_HAMMING, crossCheck=False) replacement."""
+    """cv2.BFMatcher(normType=cv2.NORM_HAMMING, crossCheck=False) replacement.
 
-    def __init__(self, normType=NORM_HAMMING, crossCheck=False):
+    group: a torch.distributed process group (or True for the default group) shards the
+    collection across the ranks by contiguous keyframe ranges: every rank makes the SAME
+    add() / knnMatch() calls with the same arguments (the whole list of keyframes, the
+    replicated queries) and receives the same, global result - imgIdx / trainIdx index the
+    whole collection exactly as on one GPU.  The partition is (re)built by train() or by the
+    first match after an add()."""
+
+    def __init__(self, normType=NORM_HAMMING, crossCheck=False, group=None):
         if normType != NORM_HAMMING:
             raise NotImplementedError("only NORM_HAMMING (256-bit ORB descriptors) is implemented")
         self.crossCheck = bool(crossCheck)
         self.db = KeyframeDatabase()
+        self.group = group
+        self._pending = []          # sharded mode: host keyframes not yet partitioned
+        self._sharded = None        # (ShardedKeyframeMatcher, global offsets)
 
     # -- collection management (cv2.DescriptorMatcher)
     def add(self, descriptors):
-        self.db.add(descriptors)
+        if self.group is None:
+            self.db.add(descriptors)
+            return
+        for d in descriptors:
+            d = np.ascontiguousarray(d)
+            if d.dtype != np.uint8 or d.ndim != 2 or d.shape[1] != 32:
+                raise ValueError("descriptors must be (N, 32) uint8 (256-bit ORB)")
+            self._pending.append(d)
+        self._sharded = None
 
     def clear(self):
         self.db.clear()
+        self._pending, self._sharded = [], None
 
     def empty(self):
-        return len(self.db) == 0
+        return (len(self.db) == 0) if self.group is None else (len(self._pending) == 0 and self._sharded is None)
 
     def getTrainDescriptors(self):
-        return self.db.descriptors()
+        return self.db.descriptors() if self.group is None else list(self._pending)
+
+    def train(self):
+        """cv2.DescriptorMatcher.train(): sharded mode uploads this rank's contiguous keyframe
+        range of the collection; a no-op on one GPU."""
+        if self.group is None or self._sharded is not None:
+            return
+        import torch.distributed as dist
+        from ..distributed import ShardedKeyframeMatcher, shard_range
+        T = _ffi.require_cuda()
+        group = None if self.group is True else self.group
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        offsets = np.concatenate([[0], np.cumsum([len(d) for d in self._pending])]).astype(np.int64)
+        lo, hi = shard_range(len(self._pending), rank, world)
+        mine = self._pending[lo:hi]
+        rows = np.concatenate(mine) if mine else np.zeros((0, 32), np.uint8)
+        shard = T.from_numpy(np.ascontiguousarray(rows)).cuda()
+        self._sharded = (ShardedKeyframeMatcher(shard, int(offsets[lo]), group=group), offsets)
+
+    @classmethod
+    def from_resident(cls, flat, rows_per_image, shard_base=0, n_images_total=None, group=None, crossCheck=False):
+        """A matcher over descriptors ALREADY resident in HBM: `flat` (N,32) uint8 CUDA tensor of
+        equal-sized keyframes.  With `group`, `flat` is this rank's contiguous range starting at
+        global row `shard_base` of a collection of n_images_total keyframes."""
+        m = cls(NORM_HAMMING, crossCheck, group)
+        if group is None:
+            m.db = KeyframeDatabase.from_flat(flat, rows_per_image)
+            return m
+        from ..distributed import ShardedKeyframeMatcher
+        offsets = np.arange(0, (int(n_images_total) + 1) * int(rows_per_image), int(rows_per_image), dtype=np.int64)
+        m._sharded = (ShardedKeyframeMatcher(flat, int(shard_base), group=None if group is True else group), offsets)
+        return m
 
     # -- array API ---------------------------------------------------------
     def knn_arrays(self, queryDescriptors, trainDescriptors=None, ratio=None, mutual=False):
         """Top-2 as arrays: dict(idx (nq,2) global rows, imgIdx, trainIdx,
         dist (nq,2) int32, ratio_ok, mutual_ok, valid)."""
-        if trainDescriptors is not None:
-            db = KeyframeDatabase()
-            db.add([trainDescriptors])
+        r = 1.0 if ratio is None else ratio
+        if trainDescriptors is None and self.group is not None:
+            self.train()
+            sm, offsets = self._sharded
+            T = _ffi.require_cuda()
+            qd = ops._desc_in(queryDescriptors)
+            idx, dist, r_ok, m_ok, valid = sm.match_host(qd, r, mutual)
         else:
-            db = self.db
-        idx, dist, r_ok, m_ok, valid = ops.knn_ratio_mutual(
-            queryDescriptors, db.flat, ratio=1.0 if ratio is None else ratio, mutual=mutual)
-        idx, dist = np.asarray(_np(idx)), np.asarray(_np(dist))
-        img, tr = db.split_global(np.maximum(idx, 0))
+            if trainDescriptors is not None:
+                db = KeyframeDatabase()
+                db.add([trainDescriptors])
+            else:
+                db = self.db
+            offsets = db.offsets
+            idx, dist, r_ok, m_ok, valid = (_np(x) for x in ops.knn_ratio_mutual(
+                queryDescriptors, db.flat, ratio=r, mutual=mutual))
+        idx, dist = np.asarray(idx), np.asarray(dist)
+        img, tr = _split_global(offsets, np.maximum(idx, 0))
         img[idx < 0] = -1
         tr[idx < 0] = -1
-        return dict(idx=idx, imgIdx=img, trainIdx=tr, dist=dist, ratio_ok=_np(r_ok),
-                    mutual_ok=_np(m_ok), valid=_np(valid))
+        return dict(idx=idx, imgIdx=img, trainIdx=tr, dist=dist, ratio_ok=r_ok, mutual_ok=m_ok, valid=valid)
 
     # -- OpenCV API --------------------------------------------------------
     def knnMatch(self, queryDescriptors, trainDescriptors=None, k=2, mask=None, compactResult=False):
@@ -143,22 +265,26 @@ class BFMatcher(object):
         if self.crossCheck and k != 1:
             raise ValueError("crossCheck=True needs k == 1 (OpenCV asserts the same)")
         r = self.knn_arrays(queryDescriptors, trainDescriptors, mutual=self.crossCheck)
-        out = []
-        for i in range(len(r["idx"])):
-            row = []
-            for j in range(k):
-                if r["idx"][i, j] < 0:
-                    break
-                if self.crossCheck and not r["mutual_ok"][i]:
-                    break
-                row.append(DMatch(i, r["trainIdx"][i, j], r["imgIdx"][i, j], r["dist"][i, j]))
-            if row or not compactResult:
-                out.append(row)
-        return out
+        counts = (r["idx"][:, :k] >= 0).sum(1)              # fewer than k rows when the train set is smaller
+        if self.crossCheck:
+            counts = np.where(r["mutual_ok"], counts, 0)
+        rows = np.arange(len(counts))
+        if compactResult:
+            rows = rows[counts > 0]
+            counts = counts[counts > 0]
+        return KnnMatches(rows, r["trainIdx"], r["imgIdx"], r["dist"], counts, arrays=r)
 
     def match(self, queryDescriptors, trainDescriptors=None, mask=None):
         return [row[0] for row in self.knnMatch(queryDescriptors, trainDescriptors, k=1, mask=mask)
                 if row]
+
+
+def _split_global(offsets, g):
+    """global rows -> (imgIdx, trainIdx) for a collection with row offsets `offsets`."""
+    g = np.asarray(g, np.int64)
+    img = np.searchsorted(offsets, g, side="right") - 1
+    img = np.clip(img, 0, max(len(offsets) - 2, 0))
+    return img.astype(np.int32), (g - offsets[img]).astype(np.int32)
 
 
 def _np(x):

@@ -132,7 +132,12 @@ def full(tag):
                     cells.append(v)
             f.write("| `%s` | %s | %.1f |\n" % (k[:60], " | ".join(cells), (rd + wr) / 1e6))
             traffic[k] = {"dram_bytes": rd + wr, "problem": PROBLEMS.get(k.split("<")[0], "")}
-    json.dump({"tag": tag, "kernels": traffic}, open(os.path.join(PROF, "ncu_traffic.json"), "w"), indent=1)
+    sha = {}
+    sha_file = os.path.join(OUT, tag + "_source_sha.json")
+    if os.path.exists(sha_file):
+        sha = json.load(open(sha_file))
+    json.dump({"tag": tag, "source_sha": sha, "kernels": traffic},
+              open(os.path.join(PROF, "ncu_traffic.json"), "w"), indent=1)
 
 
 def bench_line(tag):

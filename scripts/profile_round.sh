@@ -8,6 +8,14 @@ set -u
 TAG=${1:-rXX}
 OUT=gpurun_out
 mkdir -p $OUT
+# the kernel sources this capture was made from (bench.py marks traffic figures of another
+# version of a kernel as stale)
+python - <<PY > $OUT/${TAG}_source_sha.json
+import hashlib, json, os
+d = "pybot_b200/csrc"
+print(json.dumps({f: hashlib.sha256(open(os.path.join(d, f), "rb").read()).hexdigest()[:16]
+                  for f in sorted(os.listdir(d)) if f.endswith((".cu", ".cuh"))}))
+PY
 BENCH="python bench.py --steps 3 --warmup 3"
 $BENCH > $OUT/${TAG}_bench_plain.json 2> $OUT/${TAG}_bench_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv \

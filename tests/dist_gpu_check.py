@@ -45,6 +45,19 @@ def main():
     for a, b in zip(got, ops.knn_ratio_mutual(torch.from_numpy(q2).cuda(), torch.from_numpy(db).cuda(), 0.75)):
         assert torch.equal(a, b)
     assert int(want[0][9, 0]) == 123 and int(want[0][9, 1]) == 40_123
+    m.check()
+
+    # the cv2-shaped facade over the sharded collection: every rank adds the WHOLE list of
+    # keyframes and gets the global result, identical to the single-GPU facade
+    from pybot_b200.vision.matcher import BFMatcher
+    kfs = [db[i * per_kf:(i + 1) * per_kf] for i in range(nkf)]
+    bf = BFMatcher(group=True)
+    bf.add(kfs)
+    got_rows = bf.knnMatch(q, k=2)
+    one = BFMatcher()
+    one.add(kfs)
+    assert got_rows == one.knnMatch(q, k=2), "sharded BFMatcher.knnMatch differs from the single-GPU facade"
+    assert (got_rows[9][0].imgIdx, got_rows[9][0].trainIdx, got_rows[9][1].imgIdx, got_rows[9][1].trainIdx) == (0, 123, 40, 123)
 
     prob = syn.c4_problem(n_cams=50, n_points=20_000)
     sb = ShardedBA(*prob)                                 # fused peer-memory exchange
@@ -52,6 +65,9 @@ def main():
     cost = float(sb.evaluate().item())
     for _ in range(5):                                    # repeated calls: sequence numbers / slot parity
         assert float(sb.evaluate().item()) == cost
+    for _ in range(4):                                    # ... and replayed from a captured CUDA graph
+        assert sb.cost_host(graph=True) == cost
+    assert float(sb.evaluate().item()) == cost            # eager again: the device-resident sequence kept in step
     nccl_cost = float(ShardedBA(*prob, exchange="nccl").evaluate().item())
     assert abs(nccl_cost - cost) <= 1e-12 * cost
     gathered = [None] * world
@@ -62,6 +78,29 @@ def main():
     assert abs(cost - ref) <= 1e-12 * ref, (cost, ref)
     a, b = sb.range
     assert torch.equal(sb.problem.r, whole.r[a:b]) and torch.equal(sb.problem.Jc, whole.Jc[a:b])
+    # a starved rank: rank 0 calls alone with a 50 ms bound -> poisoned outputs + RuntimeError,
+    # never a hang and never stale data (fresh objects: the sequence numbers diverge here)
+    from pybot_b200 import _ffi
+    dist.barrier()
+    m2 = ShardedKeyframeMatcher(shard, lo * per_kf)
+    m2.match(torch.from_numpy(q).cuda(), 0.75)             # creates the exchange collectively
+    sb2 = ShardedBA(*prob)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        _ffi.check(_ffi.lib().pbk_set_exchange_timeout_ms(50.0))
+        try:
+            m2.match_host(torch.from_numpy(q).cuda(), 0.75)
+            raise AssertionError("a starved exchange must raise")
+        except RuntimeError as e:
+            assert "did not arrive" in str(e)
+        try:
+            sb2.cost_host()
+            raise AssertionError("a starved cost exchange must raise")
+        except RuntimeError as e:
+            assert "did not arrive" in str(e)
+        assert np.isnan(float(sb2.problem.cost.item()))
+        _ffi.check(_ffi.lib().pbk_set_exchange_timeout_ms(2000.0))
     dist.barrier()
     if rank == 0:
         print("dist gpu check ok: world %d, valid matches %d, cost %.6e" % (world, int(want[4].sum()), cost))

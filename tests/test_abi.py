@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_ffi.SIGNATURES) == declared
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.pbk_version() == 100
+    assert lib.pbk_version() == 200
 
 
 def test_no_cuda_arch_other_than_sm100a():

@@ -55,26 +55,116 @@ def test_c4_shaped_problem_vs_oracle():
     _close(Jc.reshape(-1, 12), m[1].reshape(-1, 12))
 
 
-def test_one_call_evaluate_equals_two_launch_form():
-    """pbk_ba_evaluate (precompute + streaming kernel launched with programmatic stream
-    serialization, the kernel's prologue overlapping the precompute) against the two separate
-    calls: bit-identical, also when the cameras change between evaluations (the kernel must
-    not read camera blocks of the previous evaluation)."""
+def test_one_kernel_evaluate_equals_two_kernel_forms():
+    """pbk_ba_evaluate on camera-sorted observations is ONE kernel (every CTA derives the camera
+    blocks of its own observation range in its prologue).  It must equal, bit for bit, the
+    two-kernel route (stand-alone precompute + streaming kernel with programmatic stream
+    serialization) and the two separate calls - also when the cameras change between
+    evaluations (no stale camera block may be read) and from a replayed CUDA graph."""
     import torch
     from pybot_b200 import ops
     prob = syn.c4_problem(n_cams=300, n_points=40000)
     p = ops.BAProblemDevice(*prob)
+    assert p.sorted_by_camera
     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     for it in range(4):
         p.rvec.mul_(1.0 + 0.01 * it)
         p.tvec.add_(0.001 * it)
+        p.cam_blocks.zero_()
         p.evaluate()
         got = [t.clone() for t in (p.r, p.Jc, p.Jp, p.cost)]
+        for kw in (dict(two_kernels=True), dict(events=ev)):
+            p.cam_blocks.zero_()
+            p.evaluate(**kw)
+            for a, b in zip(got, (p.r, p.Jc, p.Jp, p.cost)):
+                assert torch.equal(a, b)
         p.cam_blocks.zero_()
-        p.evaluate(events=ev)
+        p.evaluate_graphed()
+        torch.cuda.synchronize()
         for a, b in zip(got, (p.r, p.Jc, p.Jp, p.cost)):
             assert torch.equal(a, b)
         assert float(p.cost.item()) > 0
+
+
+def test_few_observations_per_camera_and_camera_gaps():
+    """One-kernel route when a CTA's observation range spans MANY cameras (2 observations per
+    camera) and when some cameras have no observation at all."""
+    import torch
+    from pybot_b200 import ops
+    rng = np.random.default_rng(3)
+    rv, tv, K, pts, oc, op, uv = syn.c4_problem(n_cams=600, n_points=3000)
+    keep = np.sort(rng.permutation(len(oc))[:1200])                     # ~2 per camera, sorted order kept
+    keep = keep[(oc[keep] % 7) != 3]                                     # cameras 3, 10, 17 ... unobserved
+    p = ops.BAProblemDevice(rv, tv, K, pts, oc[keep], op[keep], uv[keep])
+    assert p.sorted_by_camera
+    p.evaluate()
+    rr, rJc, rJp, rcost = port.ba_residual_jacobian(rv, tv, K, pts, oc[keep], op[keep], uv[keep], use_cv2=False)
+    np.testing.assert_allclose(p.r.cpu().numpy(), rr, rtol=1e-5, atol=1e-4)
+    _close(p.Jc.cpu().numpy().reshape(-1, 12), rJc.reshape(-1, 12))
+    _close(p.Jp.cpu().numpy().reshape(-1, 6), rJp.reshape(-1, 6))
+    np.testing.assert_allclose(float(p.cost.item()), rcost, rtol=1e-10)
+
+
+def _emulated_sharded_ba(prob, world):
+    """`world` ranks of the fused-exchange BA on ONE GPU: one stream per rank, plain device
+    buffers as the peers' exchange buffers (the protocol is the same over NVLink)."""
+    import torch
+    from pybot_b200 import ops
+    from pybot_b200.distributed import PeerCostExchange, shard_range
+    rv, tv, K, pts, oc, op, uv = prob
+    xs = PeerCostExchange.emulated(world)
+    probs = []
+    for r in range(world):
+        lo, hi = shard_range(len(oc), r, world)
+        probs.append(ops.BAProblemDevice(rv, tv, K, pts, oc[lo:hi], op[lo:hi], uv[lo:hi]))
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    return xs, probs, streams
+
+
+def test_fused_cost_exchange_protocol_on_one_gpu():
+    """The release/acquire exchange of the sharded BA, both ranks on one device: every rank ends
+    with the same global cost, equal to the single-problem cost, call after call (slot parity,
+    device-resident sequence), eagerly and from replayed CUDA graphs."""
+    import torch
+    from pybot_b200 import ops
+    prob = syn.c4_problem(n_cams=50, n_points=20_000)
+    whole = ops.BAProblemDevice(*prob).evaluate()
+    ref = float(whole.cost.item())
+    for world in (2, 3):
+        xs, probs, streams = _emulated_sharded_ba(prob, world)
+        torch.cuda.synchronize()
+        for rep in range(5):
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    probs[r].evaluate(exchange=xs[r])
+            torch.cuda.synchronize()
+            costs = [float(p.cost.item()) for p in probs]
+            assert all(c == costs[0] for c in costs), costs
+            assert abs(costs[0] - ref) <= 1e-12 * ref
+            for x in xs:
+                x.check()
+        lo = 0
+        for p in probs:
+            assert torch.equal(p.r, whole.r[lo:lo + p.n_obs]) and torch.equal(p.Jc, whole.Jc[lo:lo + p.n_obs])
+            lo += p.n_obs
+
+
+def test_fused_cost_exchange_timeout_raises():
+    """A peer that never arrives: NaN cost, the status word is set and the wrapper raises."""
+    import torch
+    from pybot_b200 import _ffi
+    prob = syn.c4_problem(n_cams=20, n_points=2000)
+    xs, probs, streams = _emulated_sharded_ba(prob, 2)
+    _ffi.check(_ffi.lib().pbk_set_exchange_timeout_ms(20.0))
+    try:
+        probs[0].evaluate(exchange=xs[0])                 # rank 1 is starved: it never calls
+        torch.cuda.synchronize()
+        assert np.isnan(float(probs[0].cost.item()))
+        with pytest.raises(RuntimeError, match="did not arrive"):
+            xs[0].check()
+        xs[0].check()                                     # cleared
+    finally:
+        _ffi.check(_ffi.lib().pbk_set_exchange_timeout_ms(2000.0))
 
 
 @pytest.mark.parametrize("n_obs", [1, 31, 32, 33, 100, 257])

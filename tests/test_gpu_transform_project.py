@@ -220,3 +220,105 @@ def test_compaction_all_and_none_valid():
     X[:, 2] = -1.0                                    # behind the camera: none valid
     uv, dep, valid, count = ops.Projector(np.eye(3), np.zeros(3), K, **kw).run(X, fresh=True)
     assert int(count.item()) == 0 and not bool(valid.any())
+
+
+def _near_threshold_points(n, seed, pose_T, K, shape, min_depth=0.1):
+    """World points whose projections crowd the decision thresholds of Camera.project: pixels
+    within +-0.02 px (and +-1e-6 px) of the four image borders, depths within +-1e-6 of
+    min_depth, z ~ 0, z < 0, NaN and inf rows."""
+    rng = np.random.default_rng(seed)
+    H, W = shape
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    z = rng.uniform(0.5, 80, n)
+    u = rng.uniform(0, W, n)
+    v = rng.uniform(0, H, n)
+    k = n // 8
+    spread = np.where(rng.random(n) < 0.5, 0.02, 1e-6)
+    edge = rng.uniform(-1, 1, n) * spread
+    u[:k] = 0 + edge[:k]
+    u[k:2 * k] = W + edge[k:2 * k]
+    v[2 * k:3 * k] = 0 + edge[2 * k:3 * k]
+    v[3 * k:4 * k] = H + edge[3 * k:4 * k]
+    z[4 * k:5 * k] = min_depth + rng.uniform(-1, 1, k) * 1e-6
+    z[5 * k:5 * k + 50] = rng.uniform(-1e-7, 1e-7, 50)
+    z[5 * k + 50:5 * k + 100] = -rng.uniform(0.1, 50, 50)
+    Xc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    Rm, t = pose_T[:3, :3], pose_T[:3, 3]
+    Xw = (Xc - t) @ Rm                     # inverse of Xc = R Xw + t
+    Xw[5 * k + 100] = np.nan
+    Xw[5 * k + 101, 0] = np.inf
+    Xw[5 * k + 102] = 0.0
+    Xw[5 * k + 103] = [1e30, -1e30, 1e30]
+    return Xw
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("checks", [(True, True), (True, False), (False, True)])
+def test_compaction_classifier_at_the_thresholds(dtype, checks, monkeypatch):
+    """The fp32 classifier of the compacting kernel must agree with the exact fp64 validity of
+    the uncompacted kernel (itself pinned to the reference by golden g2) on points crowded
+    around every threshold, with several chunks per launch."""
+    import torch
+    from pybot_b200 import ops
+    from pybot_b200.geometry import RigidTransform
+    monkeypatch.setenv("PBK_COMPACT_CHUNK_MB", "1")            # 7+ chunks: the barrier / offset path
+    check_bounds, check_depth = checks
+    K = syn.kitti_K()
+    for pose in (RigidTransform.from_rpyxyz(*syn.C2_RPYXYZ), RigidTransform.identity(),
+                 RigidTransform.from_rpyxyz(1.0, -0.7, 2.5, 30.0, -12.0, 4.0)):
+        T = pose.to_matrix()
+        Xw = _near_threshold_points(600_000, 7, T, K, syn.KITTI_SHAPE)
+        X = torch.from_numpy(Xw.astype(dtype)).cuda()
+        kw = dict(shape=syn.KITTI_SHAPE, check_bounds=check_bounds, check_depth=check_depth, return_depth=True,
+                  return_valid=True)
+        uv, dep, valid, count = ops.Projector(T[:3, :3], T[:3, 3], K, **kw).run(X)
+        uv0, dep0, valid0, count0 = ops.Projector(T[:3, :3], T[:3, 3], K, compact=False, **kw).run(X)
+        m = int(count.item())
+        assert torch.equal(valid, valid0)
+        assert m == int(count0.item()) == int(valid0.sum().item())
+        keep = valid0.bool()
+        assert torch.equal(uv[:m], uv0[keep]) and torch.equal(dep[:m], dep0[keep])
+        assert 0.05 < m / len(Xw) < 0.95
+
+
+def test_projector_runs_under_cuda_graph_capture():
+    """Projector.run (plain and compacting) captured in a CUDA graph and replayed on new
+    inputs: nothing in the call may read host memory asynchronously or allocate."""
+    import torch
+    from pybot_b200 import ops
+    from pybot_b200.geometry import RigidTransform
+    T = RigidTransform.from_rpyxyz(*syn.C2_RPYXYZ).to_matrix()
+    K = syn.kitti_K()
+    n = 300_000
+    X = torch.from_numpy(syn.c2_points(n=n)).cuda()
+    for kw in (dict(), dict(shape=syn.KITTI_SHAPE, check_bounds=True, check_depth=True, return_depth=True,
+                            return_valid=True)):
+        pr = ops.Projector(T[:3, :3], T[:3, 3], K, **kw)
+        ref = [None if t is None else t.clone() for t in pr.run(X)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            pr.run(X)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = pr.run(X)
+        for t in out:
+            if t is not None:
+                t.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        m = int(ref[3].item())
+        assert int(out[3].item()) == m
+        assert torch.equal(out[0][:m], ref[0][:m])
+        if ref[2] is not None:
+            assert torch.equal(out[2], ref[2]) and torch.equal(out[1][:m], ref[1][:m])
+        # replay on different points through the same buffers
+        X2 = X.flip(0).contiguous()
+        want = [None if t is None else t.clone() for t in ops.Projector(T[:3, :3], T[:3, 3], K, **kw).run(X2)]
+        X.copy_(X2)
+        g.replay()
+        torch.cuda.synchronize()
+        m2 = int(want[3].item())
+        assert int(out[3].item()) == m2 and torch.equal(out[0][:m2], want[0][:m2])

@@ -18,6 +18,53 @@ def test_plan_covers_rows_once_and_respects_alignment():
         assert len(ch) <= _pipeline.MAX_CHUNKS
 
 
+def test_plan_keeps_every_plane_pointer_16_byte_aligned():
+    """KITTI 376x1241 uint8 disparity is 466616 B per frame (mod 16 = 8) and its colour plane
+    1399848 B (mod 16 = 8): chunks must start on frames where every plane's offset is a
+    multiple of 16 (the kernels reject unaligned pointers)."""
+    H, W = 376, 1241
+    assert _pipeline.pointer_row_align([H * W]) == 2 and _pipeline.pointer_row_align([H * W * 4]) == 1
+    assert _pipeline.pointer_row_align([1001 * 1001 * 4, 1001 * 1001 * 24]) == 4
+    assert _pipeline.pointer_row_align([3, 12, 16]) == 16
+    for B in (2, 5, 7, 33, 64):
+        for planes in ([H * W, H * W * 12], [H * W, H * W * 12, H * W * 3, H * W * 3], [1001 * 1001 * 4, 1001 * 1001 * 24]):
+            ch = _pipeline.plan(B, sum(planes) * 40, plane_row_bytes=planes)       # x40: force several chunks
+            assert ch[0][0] == 0 and ch[-1][1] == B
+            for lo, hi in ch:
+                assert lo < hi and all((lo * p) % 16 == 0 for p in planes), (B, planes, ch)
+            for (a, b), (c, d) in zip(ch[:-1], ch[1:]):
+                assert b == c
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [2, 5])
+def test_uint8_kitti_frames_with_colour_stream_through_unaligned_frame_sizes(B):
+    """2- and 5-frame uint8 KITTI batches (frame stride 8 mod 16) with a colour plane."""
+    from pybot_b200 import synthetic as syn
+    from pybot_b200.vision.camera_utils import DepthCamera, StereoCamera
+    H, W = syn.KITTI_SHAPE
+    cam = StereoCamera.from_calib_params(syn.KITTI_FX, syn.KITTI_FX, syn.KITTI_CX, syn.KITTI_CY,
+                                         baseline_px=syn.KITTI_BASELINE_PX, shape=(H, W))
+    rng = np.random.default_rng(B)
+    disp = rng.integers(0, 256, (B, H, W), dtype=np.uint8)
+    im = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    old = _pipeline.MIN_BYTES
+    _pipeline.MIN_BYTES = 1 << 20                         # make even 2 frames take the streamed path
+    try:
+        col, xyz = cam.reconstruct_with_texture(disp, im)
+        plain = cam.reconstruct(disp)
+        dc = DepthCamera(syn.kitti_K(), shape=(1001, 1001))
+        depth = rng.uniform(0.3, 40, (B, 1001, 1001)).astype(np.float32)
+        got = dc.reconstruct(depth)
+    finally:
+        _pipeline.MIN_BYTES = old
+    for b in range(B):
+        c1, x1 = cam.reconstruct_with_texture(disp[b], im[b])
+        assert np.array_equal(col[b], c1) and np.array_equal(xyz[b], x1, equal_nan=True)
+        assert np.array_equal(plain[b], cam.reconstruct(disp[b]), equal_nan=True)
+        assert np.array_equal(got[b], dc.reconstruct(depth[b]))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
