@@ -237,7 +237,7 @@ struct KernelCache {
     if (!ready[dev].load(std::memory_order_acquire)) {
       std::lock_guard<std::mutex> lock(mu);
       if (!ready[dev].load(std::memory_order_relaxed)) {
-        if (dyn_smem > 48 * 1024)
+        if (dyn_smem > 32 * 1024)        // static + dynamic beyond 48 KB needs the opt-in as well
           PBK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
         int n = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, (size_t)dyn_smem) != cudaSuccess ||

@@ -25,6 +25,8 @@
 // Order-preserving compaction (x[valid]) is fused: tiles of 1024 points chain
 // their valid counts with a decoupled look-back (project_compact_kernel), so
 // the compacted outputs are written in the same pass that reads X.
+#include <type_traits>
+
 #include "pbk_common.cuh"
 #include "project_math.cuh"
 
@@ -309,39 +311,365 @@ project_points_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
   if (MODE == 0 && count != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *count = n;
 }
 
+// Phase clocks of the compaction kernel (diagnostic; compiled in with -DPBK_COMPACT_TIMING)
+#ifdef PBK_COMPACT_TIMING
+__device__ unsigned long long g_ct_clk[16];
+#define CT_T0() long long _t0 = clock64()
+#define CT_ACC(slot)                                                        \
+  do {                                                                      \
+    const long long _t1 = clock64();                                        \
+    if (lane == 0) atomicAdd(&g_ct_clk[slot], (unsigned long long)(_t1 - _t0)); \
+    _t0 = _t1;                                                              \
+  } while (0)
+#else
+#define CT_T0() do {} while (0)
+#define CT_ACC(slot) do {} while (0)
+#endif
+
+// --------------------------------- projection + x[valid], single pass (look-back)
+// Order-preserving compaction fused into the projection pass (no second read
+// of X, no library scan): a two-level scan over 1024-point tiles, software-
+// pipelined two tiles deep.
+//
+// Persistent, co-resident CTAs (cooperative launch) of 8 compute warps + 2 scan
+// warps + 1 chain warp.  CTA b owns tiles b, b+G, b+2G ...: all CTAs work on one
+// generation of G consecutive tiles at a time.
+//   compute warps read tile i from a 2-stage TMA input ring (the last warp to
+//                 consume a stage refills it), project it (thread t owns points
+//                 t + 256 k), park uv / depth in one of three shared-memory
+//                 buffers, publish the tile aggregate (the last warp to finish
+//                 does it), then scatter tile i-2 whose base offset has been
+//                 resolved meanwhile;
+//   scan warp w   (tiles of parity w) scans the 32 (row, warp) valid counts of a
+//                 finished tile; its exclusive offset is the prefix of its
+//                 GENERATION plus the aggregates of the tiles of the same
+//                 generation before it (<= G status words, all loads in flight
+//                 together with the generation prefix): no tile waits for another
+//                 tile's look-back;
+//   chain warp    (CTA 0 only) is the one serial dependency: it sums the G
+//                 aggregates of generation g as they appear and publishes the
+//                 prefix of generation g+1 - one L2 round trip per generation.
+// History: a per-tile decoupled look-back (every tile resolving against its
+// predecessors' prefixes) made the prefix frontier advance one generation per ~3
+// dependent L2 round trips, 0.100 ms; this form 0.095 ms.  Versions that waited for
+// the prefix inside the tile, took tickets ahead of time, or published the aggregate
+// from the scan warp ran 1.5-6x slower.
+// Valid points are written at base + rank; lanes of a warp hold consecutive
+// ranks, so the stores are contiguous runs.
+// scratch layout (zeroed per call): [0] unused, [1 .. ntiles] tile aggregate words, then
+// one prefix word per generation.
+constexpr int kCtWarps = 8;                          // compute warps
+constexpr int kCtThreads = kCtWarps * 32;            // 256 compute threads
+// Shape knobs (scripts/build_variants.py builds A/B libraries from them).  Measured on C2
+// (10 M points, flushed): 3 CTAs/SM x 3 buffers, one point at a time 0.0952 ms; 2 CTAs/SM x 5
+// buffers with the projection batched in pairs (80 registers, no spills) 0.0932 ms - shipped;
+// batched by four (spills) 0.0973, four scan warps 0.1096, 6 buffers + 3 scan warps 0.1239.
+#ifndef PBK_CT_SCAN
+#define PBK_CT_SCAN 2
+#endif
+#ifndef PBK_CT_BUFS
+#define PBK_CT_BUFS 5
+#endif
+#ifndef PBK_CT_MINB
+#define PBK_CT_MINB 2
+#endif
+constexpr int kCtScan = PBK_CT_SCAN;                           // scan warps (one look-back each in flight); must be <= buffers
+constexpr int kCtBlock = kCtThreads + 32 * kCtScan + 32;     // + the chain warp (works in CTA 0 only)
+constexpr int kCtPpt = 4;                            // points per thread
+constexpr int kCtTile = kCtThreads * kCtPpt;         // 1024 points per tile
+constexpr int kCtSegs = kCtPpt * kCtWarps;           // 32 (row, warp) segments
+// parked-output buffers (pipeline depth = buffers - 1 tiles of slack between a
+// tile's projection and its scatter); see the shape knobs above for what was measured.
+template <typename T> struct CtBufs { static constexpr int value = PBK_CT_BUFS; };
+static_assert(kCtScan <= CtBufs<float>::value, "a scan warp may only wait one mbarrier phase ahead");
+
+template <typename T>
+struct CompactSmem {
+  static constexpr int kIn = kCtTile * 3 * (int)sizeof(T);             // one input stage
+  static constexpr int kOut = kCtTile * (2 * (int)sizeof(T) + 8);      // parked uv + depth of one tile
+  static constexpr int kBytes = 2 * kIn + CtBufs<T>::value * kOut;
+};
+
+template <typename T, bool DIST>
+__global__ void __launch_bounds__(kCtBlock, sizeof(T) == 4 ? PBK_CT_MINB : 1)
+project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
+                       double* __restrict__ depth, uint8_t* __restrict__ valid_out,
+                       long long* __restrict__ count, unsigned long long* __restrict__ scratch,
+                       const __grid_constant__ pbk_project_params P) {
+  using SM = CompactSmem<T>;
+  using UV = typename OutPix<T>::vec;
+  constexpr int kCtBufs = CtBufs<T>::value;
+  extern __shared__ __align__(128) char dyn_smem[];
+  // barriers and aggregate slots are per parked buffer: tile i + kCtBufs cannot be
+  // projected before tile i has been scattered, so a slot is never shared by two
+  // live tiles however far the compute warps drift apart
+  __shared__ __align__(8) uint64_t in_full[2], cnt_ready[kCtBufs], base_ready[kCtBufs];
+  __shared__ long long s_base[kCtBufs];
+  __shared__ int s_cnt[kCtBufs][kCtSegs], s_excl[kCtBufs][kCtSegs], s_aggsum[kCtBufs], s_arrived[kCtBufs], s_consumed[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long ntiles = (n + kCtTile - 1) / kCtTile;
+  unsigned long long* status = scratch + 1;                // one aggregate word per tile
+  unsigned long long* gen_prefix = scratch + 1 + ntiles;   // one prefix word per generation of gridDim.x tiles
+  // generation i of this CTA is tile i * gridDim.x + blockIdx.x
+  const int my_tiles = blockIdx.x < ntiles ? (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  auto tile_of = [&](int i) -> long long { return (long long)i * gridDim.x + blockIdx.x; };
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&in_full[s], 1);
+      s_consumed[s] = 0;
+    }
+    for (int q = 0; q < kCtBufs; ++q) {
+      mbar_init(&cnt_ready[q], kCtWarps);
+      mbar_init(&base_ready[q], 1);
+      s_aggsum[q] = 0;
+      s_arrived[q] = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // input stage (i & 1) <- tile of generation i: one TMA bulk copy (plus a < 16 B
+  // tail by hand), issued by a single thread
+  auto feed = [&](int i) {
+    if (i >= my_tiles) return;
+    const int st = i & 1;
+    const long long first = tile_of(i) * kCtTile;
+    const int npts = (n - first) < kCtTile ? (int)(n - first) : kCtTile;
+    const int bytes = npts * 3 * (int)sizeof(T), bulk = bytes & ~15;
+    char* dst = dyn_smem + st * SM::kIn;
+    const char* src = reinterpret_cast<const char*>(X + first * 3);
+    for (int o = bulk; o < bytes; o += 4)
+      *reinterpret_cast<uint32_t*>(dst + o) = *reinterpret_cast<const uint32_t*>(src + o);
+    if (bulk > 0) {
+      mbar_expect_tx(&in_full[st], (uint32_t)bulk);
+      tma_load_1d(dst, src, (uint32_t)bulk, &in_full[st]);
+    } else {
+      mbar_arrive(&in_full[st]);
+    }
+  };
+  if (tid == 0) {
+    feed(0);
+    feed(1);
+  }
+
+  if (warp == kCtWarps + kCtScan) {
+    // ============================================================== chain warp
+    // CTA 0 only: publishes the exclusive prefix of every generation of gridDim.x
+    // tiles.  A generation's total needs only its tiles' aggregates (published by
+    // the compute warps, no look-back involved), so this loop is the one serial
+    // dependency of the kernel and it advances one L2 round trip per generation.
+    if (blockIdx.x != 0) return;
+    long long running = 0;
+    for (long long g0 = 0, g = 0; g0 < ntiles; g0 += gridDim.x, ++g) {
+      if (lane == 0) st_status(gen_prefix + g, kStatePrefix | (unsigned long long)running);
+      const long long g1 = (g0 + gridDim.x) < ntiles ? (g0 + gridDim.x) : ntiles;
+      const long long acc = sum_aggregates(status + g0, g1 - g0, lane);
+      running += acc;
+    }
+    if (lane == 0 && count != nullptr) *count = running;
+    return;
+  }
+  if (warp >= kCtWarps) {
+    // ============================================================== scan warps
+    const int w = warp - kCtWarps;                   // this warp resolves tiles w, w + kCtScan, ...
+    for (int i = w; i < my_tiles; i += kCtScan) {
+      const int q = i % kCtBufs;
+      const uint32_t ph = (uint32_t)((i / kCtBufs) & 1);
+      // tile i's segment counts -> exclusive offsets, aggregate
+      CT_T0();
+      mbar_wait(&cnt_ready[q], ph);
+      CT_ACC(2);
+      const int c = s_cnt[q][lane];
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += a;
+      }
+      s_excl[q][lane] = inc - c;
+      const long long agg = __shfl_sync(0xffffffffu, inc, 31);
+      const long long tile = tile_of(i);              // its aggregate was published by the compute warps
+      // exclusive offset = prefix of generation i (from the chain warp) + the
+      // aggregates of the tiles of the SAME generation before this one.  No tile
+      // waits on another tile's look-back: the only serial chain is the chain warp's
+      // running sum of generation totals.
+      const long long g0 = (long long)i * gridDim.x;  // first tile of generation i
+      unsigned long long gp = ld_status(gen_prefix + i);          // in flight together with the aggregates
+      const long long acc = sum_aggregates(status + g0, tile - g0, lane);
+      while ((gp >> 62) == 0) gp = ld_status(gen_prefix + i);
+      const long long excl = (long long)(gp & kValueMask) + acc;
+      CT_ACC(3);
+      __syncwarp();                         // every lane's s_excl store precedes the arrive
+      if (lane == 0) {
+        s_base[q] = excl;
+        mbar_arrive(&base_ready[q]);
+      }
+    }
+    return;
+  }
+
+  // ============================================================ compute warps
+  const bool need_depth = (depth != nullptr) || P.check_depth;
+  const T Wf = (T)P.width, Hf = (T)P.height;      // image bounds in the pixel dtype (exact: < 2^24)
+  const unsigned lt = (1u << lane) - 1u;
+  constexpr int kLag = kCtBufs - 1;         // a tile is scattered kLag iterations after its projection
+  unsigned mh[kLag][kCtPpt];                // ballots of tiles i-1 .. i-kLag
+  for (int i = 0; i < my_tiles + kLag; ++i) {
+    unsigned m[kCtPpt];
+    CT_T0();
+    if (i < my_tiles) {
+      const int s = i & 1, q = i % kCtBufs;
+      mbar_wait(&in_full[s], (uint32_t)((i >> 1) & 1));
+      if (warp == 0) CT_ACC(4);
+      const long long tile = tile_of(i);
+      const long long first = tile * kCtTile;
+      const int npts = (n - first) < kCtTile ? (int)(n - first) : kCtTile;
+      const T* sin = reinterpret_cast<const T*>(dyn_smem + s * SM::kIn);
+      T xin[kCtPpt][3];
+#pragma unroll
+      for (int k = 0; k < kCtPpt; ++k) {
+        const T* r = sin + 3 * (k * kCtThreads + tid);
+        xin[k][0] = r[0]; xin[k][1] = r[1]; xin[k][2] = r[2];
+      }
+      __syncwarp();
+      if (lane == 0 && atomicAdd(&s_consumed[s], 1) == kCtWarps - 1) {
+        s_consumed[s] = 0;                             // last warp to read the stage refills it
+        feed(i + 2);
+      }
+      UV* suv = reinterpret_cast<UV*>(dyn_smem + 2 * SM::kIn + q * SM::kOut);
+      double* sdep = reinterpret_cast<double*>(dyn_smem + 2 * SM::kIn + q * SM::kOut + kCtTile * 2 * sizeof(T));
+      const bool valid_words_tile = npts == kCtTile && (reinterpret_cast<uintptr_t>(valid_out) & 3) == 0;
+#ifndef PBK_CT_BATCH
+#define PBK_CT_BATCH 2
+#endif
+#if PBK_CT_BATCH > 0
+      constexpr int kB = PBK_CT_BATCH;          // points projected side by side (shared reciprocal slow path)
+      double ub[kCtPpt], vb[kCtPpt];
+#pragma unroll
+      for (int k0 = 0; k0 < kCtPpt; k0 += kB) {
+        double Xb[kB][3], u2[kB], v2[kB];
+#pragma unroll
+        for (int j = 0; j < kB; ++j) {
+          Xb[j][0] = (double)xin[k0 + j][0]; Xb[j][1] = (double)xin[k0 + j][1]; Xb[j][2] = (double)xin[k0 + j][2];
+        }
+        project_many<DIST, kB>(P, Xb, u2, v2);
+#pragma unroll
+        for (int j = 0; j < kB; ++j) { ub[k0 + j] = u2[j]; vb[k0 + j] = v2[j]; }
+      }
+#pragma unroll
+      for (int k = 0; k < kCtPpt; ++k) {
+        const int p = k * kCtThreads + tid;
+        const double Xp[3] = {(double)xin[k][0], (double)xin[k][1], (double)xin[k][2]};
+        const T uo = (T)ub[k], vo = (T)vb[k];
+#else
+#pragma unroll
+      for (int k = 0; k < kCtPpt; ++k) {
+        const int p = k * kCtThreads + tid;
+        const double Xp[3] = {(double)xin[k][0], (double)xin[k][1], (double)xin[k][2]};
+        double u, v;
+        project_one<DIST>(P, Xp, u, v);
+        const T uo = (T)u, vo = (T)v;
+#endif
+        bool good = p < npts;
+        if (need_depth) {
+          const double dep = depth_of(P, Xp);
+          if (depth != nullptr) sdep[p] = dep;
+          if (P.check_depth) good = good && (dep >= P.min_depth);
+        }
+        if (P.check_bounds) good = good && OutPix<T>::in_bounds(uo, vo, Wf, Hf);
+        suv[p] = OutPix<T>::make(uo, vo);
+        m[k] = __ballot_sync(0xffffffffu, good);
+        if (lane == 0) s_cnt[q][k * kCtWarps + warp] = __popc(m[k]);
+        if (valid_out != nullptr && !valid_words_tile && p < npts) valid_out[first + p] = good ? 1 : 0;
+      }
+      if (valid_out != nullptr && valid_words_tile) store_valid_rows(valid_out + first + warp * 32, m, kCtThreads, lane);
+      __syncwarp();
+      if (lane == 0) {
+        // The tile aggregate leaves the moment the last compute warp is done - never
+        // behind a look-back, or every successor tile would inherit that delay.
+        int wsum = 0;
+#pragma unroll
+        for (int k = 0; k < kCtPpt; ++k) wsum += __popc(m[k]);
+        atomicAdd(&s_aggsum[q], wsum);
+        __threadfence_block();
+        if (atomicAdd(&s_arrived[q], 1) == kCtWarps - 1) {
+          __threadfence_block();
+          const int total = atomicExch(&s_aggsum[q], 0);
+          s_arrived[q] = 0;
+          st_status(status + tile, kStateAgg | (unsigned long long)total);
+        }
+        mbar_arrive(&cnt_ready[q]);
+      }
+      if (warp == 0) CT_ACC(5);
+    }
+    if (i >= kLag) {
+      // scatter tile i-kLag (parked by this same thread kLag iterations ago)
+      const int j = i - kLag, q = j % kCtBufs;
+      mbar_wait(&base_ready[q], (uint32_t)((j / kCtBufs) & 1));
+      if (warp == 0) CT_ACC(6);
+      const long long base = s_base[q];
+      const UV* suv = reinterpret_cast<const UV*>(dyn_smem + 2 * SM::kIn + q * SM::kOut);
+      const double* sdep =
+          reinterpret_cast<const double*>(dyn_smem + 2 * SM::kIn + q * SM::kOut + kCtTile * 2 * sizeof(T));
+#pragma unroll
+      for (int k = 0; k < kCtPpt; ++k) {
+        if ((mh[kLag - 1][k] >> lane) & 1u) {
+          const int p = k * kCtThreads + tid;
+          const long long o = base + s_excl[q][k * kCtWarps + warp] + __popc(mh[kLag - 1][k] & lt);
+          OutPix<T>::store_vec(uv, o, suv[p]);
+          if (depth != nullptr) st_stream_d1(depth + o, sdep[p]);
+        }
+      }
+      if (warp == 0) CT_ACC(7);
+    }
+#pragma unroll
+    for (int k = 0; k < kCtPpt; ++k) {
+#pragma unroll
+      for (int a = kLag - 1; a > 0; --a) mh[a][k] = mh[a - 1][k];
+      mh[0][k] = m[k];
+    }
+  }
+}
+
+
 // ------------------------------------------------- projection + x[valid]
 // Camera.project(check_bounds / check_depth) returns x[valid]: an order-preserving
-// compaction (camera_utils.py:727-732).  Two phases per chunk of X inside ONE persistent
-// cooperative kernel, one grid barrier per chunk:
+// compaction (camera_utils.py:727-732).  Two kernels per chunk of X (<= 128 MB, so that what
+// the first writes is still in L2 when the second reads it):
 //
-//  phase A  classifies every point of the chunk.  Validity is a handful of sign tests on
-//           LINEAR forms of X - |fx xc + (cx - W/2) zc| < (W/2)|zc| and the v / depth
-//           analogues - evaluated in fp32 FMAs (30 instructions per point instead of ~90 in
-//           fp64) with a rigorous error band b = kappa (|X|+|Y|+|Z|+1): outside the band the
-//           fp32 sign IS the reference's decision; the rare point inside it (~1e-5 of C2, also
-//           NaN / inf / z ~ 0) takes the exact fp64 route of the uncompacted kernel.  The
-//           valid points' coordinates are written, in order, to the front of the warp's own
-//           scratch region X' (tile-run-local compaction: no offsets from other warps are
-//           needed), the 0/1 flags to valid_out, and the warp's count to shared memory.
-//  barrier  every CTA publishes its count; after the barrier each CTA reads the <= 2 x 148
-//           counts, and a warp's output offset is chunk base + counts before it.
-//  phase B  is the PLAIN dense projection over X' (L2-resident: a chunk's X' is <= 40 MB):
-//           fp64 in OpenCV's order, fully coalesced uv / depth stores at the final offsets.
-//           No ballots, no parking, no look-back, and the fp64 work is proportional to the
-//           number of VALID points.
+//  compact_classify_kernel  decides every point and compacts the valid ones.  Validity is a
+//      handful of sign tests on LINEAR forms of X - |fx xc + (cx - W/2) zc| < (W/2)|zc| and
+//      the v / depth analogues - evaluated in fp32 FMAs (~30 instructions per point instead of
+//      ~90 in fp64) with a rigorous error band b = kappa (|X|+|Y|+|Z|+1): outside the band the
+//      fp32 sign IS the reference's decision; the rare point inside it (~1e-5 of C2; also NaN,
+//      inf, z ~ 0) takes the exact fp64 route of the uncompacted kernel.  A lane owns four
+//      CONSECUTIVE points (48 contiguous bytes = three 16 B loads straight into registers: no
+//      staging, no barriers), so its 0/1 flags leave as one 32-bit store.  The valid points of
+//      a 128-point tile are packed, in order, through a warp-private shared-memory stage into
+//      the tile's slot of the scratch region X' (16 B stores), the tile's count into tile_cnt.
+//      Tiles are dealt to warps in contiguous RUNS; the last CTA to finish turns the run totals
+//      into output offsets (exclusive scan of <= 9.5 k integers) and writes the total count.
+//  project_compacted_kernel is the PLAIN dense projection over the X' tiles (L2 hits): fp64 in
+//      OpenCV's order, fully coalesced uv / depth stores at run offset + running count.  No
+//      ballots, no parking, no look-back, and the fp64 work is proportional to the number of
+//      VALID points.
 //
 // HBM traffic = the algorithmic bytes (X once, flags, compacted outputs); X' lives in L2.
-// History: a single-pass decoupled look-back over 1024-point tiles with
-// parked outputs ran at 93 us on C2 however it was shaped - every tile's base depends on all
-// earlier tiles, and the fp64 projection of a tile had to finish before its count existed.
+// History: a single-pass decoupled look-back over 1024-point tiles with parked
+// outputs ran at 93 us on C2 however it was shaped - every tile's base depends on all earlier
+// tiles and the fp64 projection of a tile had to finish before its count existed; a first
+// two-phase form inside one cooperative kernel (TMA rings in both phases, 120 registers, 16
+// warps per SM) spent 430 warp instructions per 128-point tile in the classification phase
+// alone (61 us) - ring bookkeeping, not arithmetic.
 constexpr int kCpWarps = 8;
 constexpr int kCpThreads = kCpWarps * 32;
-#ifndef PBK_CP_MINB
-#define PBK_CP_MINB 2
+#ifndef PBK_CP_MINB_A
+#define PBK_CP_MINB_A 4
 #endif
 #ifndef PBK_CP_CHUNK_MB
-#define PBK_CP_CHUNK_MB 40
+#define PBK_CP_CHUNK_MB 128
 #endif
+constexpr int kCpMaxRuns = 16384;
 
 struct ClassifyParams {
   float z[4];        // zc            = z . (X, Y, Z, 1)
@@ -352,13 +680,17 @@ struct ClassifyParams {
   float kappa;       // band = kappa * (|X| + |Y| + |Z| + 1)
 };
 
-// scratch layout of the compacting kernel (bytes): [0] grid-barrier counter (u32), [64 ..) two
-// arrays of kCpMaxGrid CTA counts (call parity of the chunk), [kCpCtlBytes ..) the X' region
-constexpr int kCpMaxGrid = 2048;
-constexpr size_t kCpCtlBytes = 64 + 2 * kCpMaxGrid * 4;       // 16448, a multiple of 64
+// scratch layout (bytes): [0] arrival counter of the classify kernel (u32, zero between calls)
+// [64 ..) run totals int[kCpMaxRuns], run offsets i64[kCpMaxRuns], then tile counts u8[tiles of a
+// chunk] (256 B aligned), then the X' tiles of one chunk
+constexpr size_t kCpOffTot = 64;
+constexpr size_t kCpOffBase = kCpOffTot + (size_t)kCpMaxRuns * 4;
+constexpr size_t kCpOffCnt = kCpOffBase + (size_t)kCpMaxRuns * 8;
+static inline size_t cp_off_xprime(long long tiles) { return kCpOffCnt + (((size_t)tiles + 255) & ~(size_t)255); }
 
 template <typename T> struct CpTile {
   static constexpr int kBytes = kTilePts * 3 * (int)sizeof(T);
+  static constexpr int kVecs = kBytes / 16 / 32;        // 16 B vectors per lane: 3 (float) / 6 (double)
 };
 
 // exact validity of one point: the arithmetic of project_points_kernel<T, DIST, 1>
@@ -379,221 +711,269 @@ __device__ __forceinline__ float lin4(const float (&c)[4], float x, float y, flo
   return fmaf(c[0], x, fmaf(c[1], y, fmaf(c[2], z, c[3])));
 }
 
-// all CTAs of the (co-resident) grid; the counter only grows: target = gridDim.x * (#barriers so far)
-__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(ctr, 1u);
-    unsigned v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    } while (v < target);
-    __threadfence();
-  }
-  __syncthreads();
+// Validity of one point by the fp32 linear forms.  decided = every test is farther than the
+// error band from its threshold (then `in` IS the reference's decision); undecided points
+// (borderline, NaN - band is then NaN -, inf, z ~ 0) take the exact route.  Branch-free: a
+// disabled check has neutral constants (classify_params): depth form = +huge, |zc| form =
+// +huge with hw = hh = 1 (pixel forms identically 0: always far inside).
+__device__ __forceinline__ void classify_point(const ClassifyParams& C, float x, float y, float z, bool& in,
+                                               bool& decided) {
+  const float band = fmaf(C.kappa, fabsf(x), fmaf(C.kappa, fabsf(y), fmaf(C.kappa, fabsf(z), C.kappa)));
+  const float ld = lin4(C.d, x, y, z);
+  const float zc = fabsf(lin4(C.z, x, y, z));
+  const float tu = fmaf(C.hw, zc, -fabsf(lin4(C.cu, x, y, z)));     // > 0: inside the image columns
+  const float tv = fmaf(C.hh, zc, -fabsf(lin4(C.cv, x, y, z)));     // > 0: inside the image rows
+  in = (ld > 0.f) && (tu > 0.f) && (tv > 0.f);
+  decided = fminf(fminf(fabsf(ld), zc), fminf(fabsf(tu), fabsf(tv))) > band;
 }
 
+// the rare route for one row of a tile: lanes with an undecided point redo it exactly
 template <typename T, bool DIST>
-__global__ void __launch_bounds__(kCpThreads, PBK_CP_MINB)
-project_compact_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv, double* __restrict__ depth,
-                       uint8_t* __restrict__ valid_out, long long* __restrict__ count,
-                       unsigned char* __restrict__ scratch, long long tiles_per_chunk,
-                       const __grid_constant__ pbk_project_params P, const __grid_constant__ ClassifyParams C) {
-  constexpr int NST = RingCfg<T>::kStages;
-  constexpr int kInBytes = CpTile<T>::kBytes;
-  extern __shared__ __align__(128) char dyn_smem[];
-  __shared__ int s_wtot[kCpWarps];
-  __shared__ long long s_red[2][kCpWarps];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dyn_smem + kCpWarps * NST * kInBytes) + warp * NST;
-  WarpRing<kInBytes, NST> ring;
-  ring.init(dyn_smem + warp * NST * kInBytes, bars, lane);
+__device__ __noinline__ bool resolve_point(const pbk_project_params& P, const ClassifyParams& C, const T* pt) {
+  const T x = pt[0], y = pt[1], z = pt[2];
+  bool in = false, decided = false;
+  if (!DIST) classify_point(C, (float)x, (float)y, (float)z, in, decided);
+  if (!decided) in = exact_valid<T, DIST>(P, x, y, z);
+  return in;
+}
 
-  unsigned* bar_ctr = reinterpret_cast<unsigned*>(scratch);
-  int* cta_tot = reinterpret_cast<int*>(scratch + 64);
-  char* xprime = reinterpret_cast<char*>(scratch + kCpCtlBytes);
+constexpr int kCpRing = 3;      // input tiles in flight per warp (TMA bulk copies: no registers held)
+
+template <typename T, bool DIST>
+__global__ void __launch_bounds__(kCpThreads, PBK_CP_MINB_A)
+compact_classify_kernel(const T* __restrict__ X, long long n, uint8_t* __restrict__ valid_out,
+                        unsigned char* __restrict__ scratch, long long xprime_off, int n_runs,
+                        long long* __restrict__ count, const __grid_constant__ pbk_project_params P,
+                        const __grid_constant__ ClassifyParams C) {
+  constexpr int kInBytes = CpTile<T>::kBytes;
+  constexpr int NV = CpTile<T>::kVecs;                     // 16 B vectors per lane and tile
+  // dynamic shared memory per warp: kCpRing input slots + one compaction stage; then the ring barriers
+  extern __shared__ __align__(128) char dyn_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  char* const ringw = dyn_smem + warp * (kCpRing + 1) * kInBytes;
+  T* const sg = reinterpret_cast<T*>(ringw + kCpRing * kInBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dyn_smem + kCpWarps * (kCpRing + 1) * kInBytes) + warp * kCpRing;
+  WarpRing<kInBytes, kCpRing> ring;
+  ring.init(ringw, bars, lane);
+  unsigned* done_ctr = reinterpret_cast<unsigned*>(scratch);
+  int* run_tot = reinterpret_cast<int*>(scratch + kCpOffTot);
+  long long* run_base = reinterpret_cast<long long*>(scratch + kCpOffBase);
+  uint8_t* tile_cnt = scratch + kCpOffCnt;
+  char* xprime = reinterpret_cast<char*>(scratch) + xprime_off;
 
   const long long ntiles = (n + kTilePts - 1) / kTilePts;
   const long long nfull = n / kTilePts;
-  const int nchunks = (int)((ntiles + tiles_per_chunk - 1) / tiles_per_chunk);
-  const long long NW = (long long)gridDim.x * kCpWarps, gw = (long long)blockIdx.x * kCpWarps + warp;
-  // this warp's run of tiles inside ANY chunk (clipped to the chunk's length): the same
-  // offsets in every chunk, so its X' region is private to it for the whole kernel
-  const long long run_a = gw * tiles_per_chunk / NW, run_b = (gw + 1) * tiles_per_chunk / NW;
-  char* const xp_mine = xprime + run_a * kInBytes;
+  const int NW = (int)gridDim.x * kCpWarps, gw = (int)blockIdx.x * kCpWarps + warp;
   const char* Xb = reinterpret_cast<const char*>(X);
   const unsigned lt = (1u << lane) - 1u;
   const bool valid_words = (reinterpret_cast<uintptr_t>(valid_out) & 3) == 0;
-  const uint64_t pol_stream = l2_policy_evict_first();
+  const uint64_t pol_stream = l2_policy_evict_first();     // X is read once: do not let it push X' out of L2
 
-  long long out_base = 0;          // valid points of the chunks before this one (identical in all CTAs)
-  int k = 0;                       // ring sequence number, continues across phases and chunks
-  for (int c = 0; c < nchunks; ++c) {
-    const long long chunk_t0 = (long long)c * tiles_per_chunk;
-    const long long chunk_tiles = (ntiles - chunk_t0) < tiles_per_chunk ? (ntiles - chunk_t0) : tiles_per_chunk;
-    const long long a = run_a < chunk_tiles ? run_a : chunk_tiles, b = run_b < chunk_tiles ? run_b : chunk_tiles;
-    const int my = (int)(b - a);
-
-    // ================================================================ phase A
+  int k = 0;                                               // ring sequence number
+  for (int run = gw; run < n_runs; run += NW) {
+    const long long ta = (long long)run * ntiles / n_runs, tb = ((long long)run + 1) * ntiles / n_runs;
+    const int my = (int)(tb - ta);
     int wtot = 0;
-    {
-      const long long t0 = chunk_t0 + a;
-      if (lane == 0)
-        for (int i = 0; i < NST - 1 && i < my; ++i)
-          if (t0 + i < nfull) ring.issue_hint(k + i, Xb + (t0 + i) * kInBytes, pol_stream);
-      for (int i = 0; i < my; ++i, ++k) {
-        const long long tile = t0 + i;
-        if (lane == 0 && i + NST - 1 < my && tile + NST - 1 < nfull)
-          ring.issue_hint(k + NST - 1, Xb + (tile + NST - 1) * kInBytes, pol_stream);
-        const long long first = tile * kTilePts;
-        const int npts = (n - first) < kTilePts ? (int)(n - first) : kTilePts;
-        char* st = ring.slot(k);
-        if (tile >= nfull) {
-          warp_load_ragged(Xb + first * 3 * sizeof(T), st, lane, kInBytes, npts * 3 * (int)sizeof(T));
-          __syncwarp();
-          if (lane == 0) ring.skip(k);        // keep the slot's barrier phase in step
-        }
-        ring.wait(k);
-        T xin[4][3];
+    if (lane == 0)
+      for (int d = 0; d < kCpRing - 1 && d < my; ++d)
+        if (ta + d < nfull) ring.issue_hint(k + d, Xb + (ta + d) * kInBytes, pol_stream);
+    for (int i = 0; i < my; ++i, ++k) {
+      const long long tile = ta + i;
+      const long long first = tile * kTilePts;
+      const bool ragged = tile >= nfull;
+      if (lane == 0 && i + kCpRing - 1 < my && tile + kCpRing - 1 < nfull)
+        ring.issue_hint(k + kCpRing - 1, Xb + (tile + kCpRing - 1) * kInBytes, pol_stream);
+      char* const st = ring.slot(k);
+      if (ragged) {
+        const int npts = (int)(n - first);
+        warp_load_ragged(Xb + first * 3 * sizeof(T), st, lane, kInBytes, npts * 3 * (int)sizeof(T));
+        __syncwarp();
+        if (lane == 0) ring.skip(k);          // keep the slot's barrier phase in step
+      }
+      ring.wait(k);
+      // lane l owns points l, l + 32, l + 64, l + 96 of the tile (3-word stride: conflict-free)
+      const T* pts = reinterpret_cast<const T*>(st) + 3 * lane;
+      unsigned mv[4];
+      bool undecided = DIST;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bool in = false, decided = false;
+        if (!DIST) classify_point(C, (float)pts[96 * j], (float)pts[96 * j + 1], (float)pts[96 * j + 2], in, decided);
+        mv[j] = __ballot_sync(0xffffffffu, in);
+        undecided = undecided || !decided;
+      }
+      if (__any_sync(0xffffffffu, undecided)) {
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) mv[j] = __ballot_sync(0xffffffffu, resolve_point<T, DIST>(P, C, pts + 96 * j));
+      }
+      if (ragged) {
+        const int npts = (int)(n - first);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const T* r = reinterpret_cast<const T*>(st) + 3 * (j * 32 + lane);
-          xin[j][0] = r[0]; xin[j][1] = r[1]; xin[j][2] = r[2];
-        }
-        __syncwarp();                       // slot may be refilled from here on
-        bool ok[4], amb[4];
-        bool any_amb = false;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (DIST) {
-            ok[j] = false;
-            amb[j] = true;
-          } else {
-            const float x = (float)xin[j][0], y = (float)xin[j][1], z = (float)xin[j][2];
-            const float band = C.kappa * (fabsf(x) + fabsf(y) + fabsf(z) + 1.0f);
-            bool in = true, out = false;
-            if (P.check_depth) {
-              const float ld = lin4(C.d, x, y, z);
-              in = ld > band;
-              out = ld < -band;
-            }
-            if (P.check_bounds) {
-              const float zc = fabsf(lin4(C.z, x, y, z));
-              const float lu = fabsf(lin4(C.cu, x, y, z)), lv = fabsf(lin4(C.cv, x, y, z));
-              const float hw = C.hw * zc, hh = C.hh * zc;
-              const bool zdef = zc > band;
-              in = in && zdef && (lu < hw - band) && (lv < hh - band);
-              out = out || (zdef && ((lu > hw + band) || (lv > hh + band)));
-            }
-            ok[j] = in && !out;
-            amb[j] = !(in || out);          // NaN / inf / borderline: neither is provable
-          }
-          if (j * 32 + lane >= npts) { ok[j] = false; amb[j] = false; }
-          any_amb = any_amb || amb[j];
-        }
-        if (__any_sync(0xffffffffu, any_amb)) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (amb[j]) ok[j] = exact_valid<T, DIST>(P, xin[j][0], xin[j][1], xin[j][2]);
-        }
-        unsigned mv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mv[j] = __ballot_sync(0xffffffffu, ok[j]);
-        if (valid_out != nullptr) {
-          if (npts == kTilePts && valid_words) {
-            store_valid_rows(valid_out + first, mv, 32, lane);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j * 32 + lane < npts) valid_out[first + j * 32 + lane] = ok[j] ? 1 : 0;
-          }
-        }
-        // the warp's valid points, in order, to the front of its X' region
-        T* xp = reinterpret_cast<T*>(xp_mine);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (ok[j]) {
-            T* dst = xp + 3ll * (wtot + __popc(mv[j] & lt));
-            dst[0] = xin[j][0]; dst[1] = xin[j][1]; dst[2] = xin[j][2];
-          }
-          wtot += __popc(mv[j]);
+          const int live = npts - j * 32;
+          mv[j] &= live >= 32 ? 0xffffffffu : (live <= 0 ? 0u : ((1u << live) - 1u));
         }
       }
-    }
-    if (lane == 0) s_wtot[warp] = wtot;
-    // X' was written with generic-proxy stores and is read back by TMA (async proxy)
-    asm volatile("fence.proxy.async;" ::: "memory");
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int tot = 0;
+      if (valid_out != nullptr) {
+        if (!ragged && valid_words) {
+          store_valid_rows(valid_out + first, mv, 32, lane);
+        } else {
+          const int npts = ragged ? (int)(n - first) : kTilePts;
 #pragma unroll
-      for (int w = 0; w < kCpWarps; ++w) tot += s_wtot[w];
-      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(cta_tot + (c & 1) * kCpMaxGrid + blockIdx.x), "r"(tot) : "memory");
+          for (int j = 0; j < 4; ++j)
+            if (j * 32 + lane < npts) valid_out[first + j * 32 + lane] = (uint8_t)((mv[j] >> lane) & 1u);
+        }
+      }
+      // the tile's valid points, in order, to the warp's stage
+      __syncwarp();                         // the previous tile's copy-out has finished reading the stage
+      int cnt = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if ((mv[j] >> lane) & 1u) {
+          T* dst = sg + 3 * (cnt + __popc(mv[j] & lt));
+          dst[0] = pts[96 * j]; dst[1] = pts[96 * j + 1]; dst[2] = pts[96 * j + 2];
+        }
+        cnt += __popc(mv[j]);
+      }
+      __syncwarp();                         // (also: every lane is done with the ring slot)
+      // stage -> the tile's X' slot: 16-byte vectors, rounded up (the slot is a full tile wide)
+      {
+        const int nvec = (cnt * 3 * (int)sizeof(T) + 15) >> 4;
+        const uint4* s4 = reinterpret_cast<const uint4*>(sg);
+        uint4* d4 = reinterpret_cast<uint4*>(xprime + tile * kInBytes);
+#pragma unroll
+        for (int m = 0; m < NV; ++m) {
+          const int v = m * 32 + lane;
+          if (v < nvec) d4[v] = s4[v];
+        }
+      }
+      if (lane == 0) tile_cnt[tile] = (uint8_t)cnt;       // cnt <= 128 (128 -> 0x80)
+      wtot += cnt;
     }
-    grid_barrier(bar_ctr, gridDim.x * (unsigned)(c + 1));
+    if (lane == 0) run_tot[run] = wtot;
+  }
 
-    // ================================================================ offsets
-    long long before = 0, total = 0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += kCpThreads) {
-      int v;
-      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cta_tot + (c & 1) * kCpMaxGrid + i) : "memory");
-      total += v;
-      if (i < (int)blockIdx.x) before += v;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      before += __shfl_xor_sync(0xffffffffu, before, o);
-      total += __shfl_xor_sync(0xffffffffu, total, o);
-    }
-    if (lane == 0) { s_red[0][warp] = before; s_red[1][warp] = total; }
+  // ---- the last CTA to finish turns the run totals into output offsets
+  __shared__ int s_last;
+  __shared__ long long s_scan[kCpThreads];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(done_ctr, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const long long base0 = (count != nullptr) ? *count : 0;       // valid points of the chunks before this one
+  const int per = (n_runs + kCpThreads - 1) / kCpThreads;
+  const int r0 = threadIdx.x * per, r1 = (r0 + per) < n_runs ? (r0 + per) : n_runs;
+  long long mine = 0;
+  for (int r = r0; r < r1; ++r) mine += __ldcg(run_tot + r);
+  s_scan[threadIdx.x] = mine;
+  __syncthreads();
+  for (int o = 1; o < kCpThreads; o <<= 1) {
+    const long long v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
     __syncthreads();
-    long long my_out = out_base;
-#pragma unroll
-    for (int w = 0; w < kCpWarps; ++w) {
-      my_out += s_red[0][w];
-      out_base += s_red[1][w];
-      if (w < warp) my_out += s_wtot[w];
-    }
+    s_scan[threadIdx.x] += v;
+    __syncthreads();
+  }
+  long long run = base0 + s_scan[threadIdx.x] - mine;
+  for (int r = r0; r < r1; ++r) {
+    run_base[r] = run;
+    run += __ldcg(run_tot + r);
+  }
+  if (threadIdx.x == kCpThreads - 1 && count != nullptr) *count = base0 + s_scan[kCpThreads - 1];
+  if (threadIdx.x == 0) *done_ctr = 0u;                  // ready for the next launch
+}
 
-    // ================================================================ phase B
-    {
-      asm volatile("fence.proxy.async;" ::: "memory");
-      const int nt = (wtot + kTilePts - 1) / kTilePts;
-      auto bytes_of = [&](int t) -> uint32_t {
-        const int pts = (wtot - t * kTilePts) < kTilePts ? (wtot - t * kTilePts) : kTilePts;
-        return (uint32_t)((pts * 3 * (int)sizeof(T) + 15) & ~15);
-      };
-      if (lane == 0)
-        for (int t = 0; t < NST - 1 && t < nt; ++t) ring.issue_bytes(k + t, xp_mine + (long long)t * kInBytes, bytes_of(t));
-      for (int t = 0; t < nt; ++t, ++k) {
-        if (lane == 0 && t + NST - 1 < nt)
-          ring.issue_bytes(k + NST - 1, xp_mine + (long long)(t + NST - 1) * kInBytes, bytes_of(t + NST - 1));
-        const int pts = (wtot - t * kTilePts) < kTilePts ? (wtot - t * kTilePts) : kTilePts;
-        ring.wait(k);
-        char* st = ring.slot(k);
-        double Xp[4][3];
+// The plain projection over the compacted tiles of one chunk.  B-warp w takes the runs w,
+// w + (its grid's warps), ... of the classify kernel's partition.
+template <typename T, bool DIST>
+__global__ void __launch_bounds__(kWarps * 32)
+project_compacted_kernel(long long n, T* __restrict__ uv, double* __restrict__ depth,
+                         const unsigned char* __restrict__ scratch, long long xprime_off, int n_runs,
+                         const __grid_constant__ pbk_project_params P) {
+  constexpr int NST = RingCfg<T>::kStages;
+  constexpr int kInBytes = CpTile<T>::kBytes;
+  extern __shared__ __align__(128) char dyn_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dyn_smem + kWarps * NST * kInBytes) + warp * NST;
+  WarpRing<kInBytes, NST> ring;
+  ring.init(dyn_smem + warp * NST * kInBytes, bars, lane);
+  const long long* run_base = reinterpret_cast<const long long*>(scratch + kCpOffBase);
+  const uint8_t* tile_cnt = scratch + kCpOffCnt;
+  const char* xprime = reinterpret_cast<const char*>(scratch) + xprime_off;
+  const long long ntiles = (n + kTilePts - 1) / kTilePts;
+  const int NW = (int)gridDim.x * kWarps, gw = (int)blockIdx.x * kWarps + warp;
+
+  int k = 0;                      // ring sequence number
+  for (int run = gw; run < n_runs; run += NW) {
+    const long long ta = (long long)run * ntiles / n_runs, tb = ((long long)run + 1) * ntiles / n_runs;
+    const int my = (int)(tb - ta);
+    long long out = run_base[run];
+    // counts of the run's tiles, 32 at a time in the lanes' registers
+    int cnts = 0, cnts_lo = -1;
+    auto count_of = [&](int i) -> int {       // all lanes call it with the same i, ascending
+      if ((i >> 5) != cnts_lo) {
+        cnts_lo = i >> 5;
+        const int t = cnts_lo * 32 + lane;
+        cnts = t < my ? (int)tile_cnt[ta + t] : 0;
+      }
+      return __shfl_sync(0xffffffffu, cnts, i & 31);
+    };
+    auto issue = [&](int i, int kk, int cn) {  // lane 0
+      const uint32_t bytes = (uint32_t)((cn * 3 * (int)sizeof(T) + 15) & ~15);
+      if (bytes) ring.issue_bytes(kk, xprime + (ta + i) * kInBytes, bytes);
+      else ring.skip(kk);
+    };
+    // software pipeline: tile i + NST - 1 is requested while tile i is projected.  The counts of
+    // the tiles in flight are kept in a small register queue so that count_of() is only ever
+    // called with ascending i.
+    int q[NST];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j * 32 + lane < pts) stage_read_point<T>(st, j * 32 + lane, Xp[j]);
+    for (int d = 0; d < NST; ++d) q[d] = 0;
+#pragma unroll
+    for (int d = 0; d < NST - 1; ++d) {
+      if (d < my) {
+        q[d] = count_of(d);
+        if (lane == 0) issue(d, k + d, q[d]);
+      }
+    }
+    for (int i = 0; i < my; ++i, ++k) {
+      if (i + NST - 1 < my) {
+        q[NST - 1] = count_of(i + NST - 1);
+        if (lane == 0) issue(i + NST - 1, k + NST - 1, q[NST - 1]);
+      }
+      const int cnt = q[0];
+#pragma unroll
+      for (int d = 0; d < NST - 1; ++d) q[d] = q[d + 1];
+      ring.wait(k);
+      const char* st = ring.slot(k);
+      const int rows = (cnt + 31) >> 5;
+      const long long o0 = out;
+      out += cnt;
+      auto emit = [&](auto NR) {
+        constexpr int R = decltype(NR)::value;
+        double Xp[R][3], ud[R], vd[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          if (j * 32 + lane < cnt) stage_read_point<T>(st, j * 32 + lane, Xp[j]);
           else { Xp[j][0] = 0.0; Xp[j][1] = 0.0; Xp[j][2] = 1.0; }
         }
-        __syncwarp();
-        double ud[4], vd[4];
-        project_many<DIST, 4>(P, Xp, ud, vd);
-        const long long o0 = my_out + (long long)t * kTilePts;
+        project_many<DIST, R>(P, Xp, ud, vd);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j * 32 + lane < pts) {
+        for (int j = 0; j < R; ++j) {
+          if (j * 32 + lane < cnt) {
             OutPix<T>::store(uv, o0 + j * 32 + lane, (T)ud[j], (T)vd[j]);
             if (depth != nullptr) st_stream_d1(depth + o0 + j * 32 + lane, depth_of(P, Xp[j]));
           }
         }
-      }
+      };
+      if (rows == 4) emit(std::integral_constant<int, 4>());
+      else if (rows == 3) emit(std::integral_constant<int, 3>());
+      else if (rows == 2) emit(std::integral_constant<int, 2>());
+      else if (rows == 1) emit(std::integral_constant<int, 1>());
+      __syncwarp();                       // slot may be refilled from here on
     }
-    __syncthreads();        // s_wtot / s_red are rewritten by the next chunk
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && count != nullptr) *count = out_base;
 }
 
 template <typename TI, typename TO>
@@ -632,6 +1012,32 @@ static int launch_project(const void* X, int64_t n, const pbk_project_params& P,
   return PBK_OK;
 }
 
+template <typename T, bool DIST>
+static int launch_compact_lookback(const void* X, int64_t n, const pbk_project_params& P, void* uv,
+                          double* depth, uint8_t* valid, int64_t* count, void* scratch, cudaStream_t s,
+                          const DeviceInfo* di) {
+  constexpr int smem = CompactSmem<T>::kBytes;
+  auto kern = project_compact_kernel<T, DIST>;
+  static KernelCache kc;
+  int per_sm;
+  int rc = kc.setup(di, kern, kCtBlock, smem, &per_sm);
+  if (rc) return rc;
+  const long long ntiles = (n + kCtTile - 1) / kCtTile;
+  const int grid = resident_grid(di, per_sm, ntiles);
+  PBK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)(2 * ntiles + 4) * 8, s));       // status words
+  const T* Xp = static_cast<const T*>(X);
+  long long nn = n;
+  T* uvp = static_cast<T*>(uv);
+  long long* cnt = reinterpret_cast<long long*>(count);
+  unsigned long long* scr = static_cast<unsigned long long*>(scratch);
+  pbk_project_params Pc = P;
+  void* args[] = {&Xp, &nn, &uvp, &depth, &valid, &cnt, &scr, &Pc};
+  PBK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(kCtBlock), args,
+                                       smem, s));
+  return PBK_OK;
+}
+
+
 static void classify_params(const pbk_project_params& P, ClassifyParams* C) {
   // linear forms in double, rounded once to float; kappa covers the fp32 evaluation (<= 5 x
   // 2^-24 of max|coefficient| x (|X|+|Y|+|Z|+1), inputs rounded to float included), the fp32
@@ -654,51 +1060,83 @@ static void classify_params(const pbk_project_params& P, ClassifyParams* C) {
   }
   C->hw = (float)(0.5 * W);
   C->hh = (float)(0.5 * H);
+  if (!P.check_depth) {                 // depth form: always provably inside
+    C->d[0] = C->d[1] = C->d[2] = 0.f;
+    C->d[3] = 1e30f;
+    md = 0;
+  }
+  if (!P.check_bounds) {                // |zc| = 1e30 >> band, pixel forms 0 < 1e30 - band
+    for (int i = 0; i < 3; ++i) C->z[i] = C->cu[i] = C->cv[i] = 0.f;
+    C->z[3] = 1e30f;
+    C->cu[3] = C->cv[3] = 0.f;
+    C->hw = C->hh = 1.f;
+    mu = mv = mz = 0;
+  }
   C->kappa = (float)(4e-6 * fmax(fmax(mu + W * mz, mv + H * mz), fmax(md, mz)));
 }
 
-static long long compact_tiles_per_chunk(long long n, size_t elem) {
+// points per chunk: both kernels of a chunk run back to back so that X' is read from L2
+static long long compact_chunk_points(long long n, size_t elem) {
   long long mb = PBK_CP_CHUNK_MB;
   if (const char* e = getenv("PBK_COMPACT_CHUNK_MB")) {
     const long long v = atoll(e);
     if (v >= 1 && v <= 4096) mb = v;
   }
-  const long long tile_bytes = (long long)kTilePts * 3 * (long long)elem;
-  const long long ntiles = (n + kTilePts - 1) / kTilePts;
-  long long cap = (mb << 20) / tile_bytes;
-  if (cap < 1) cap = 1;
-  const long long nchunks = (ntiles + cap - 1) / cap;
-  long long tpc = nchunks > 0 ? (ntiles + nchunks - 1) / nchunks : 1;       // equal chunks
-  return tpc < 1 ? 1 : tpc;
+  long long cap = ((mb << 20) / (3 * (long long)elem)) / kTilePts * kTilePts;
+  if (cap < kTilePts) cap = kTilePts;
+  if (n <= cap) return n > 0 ? n : 1;
+  const long long nchunks = (n + cap - 1) / cap;
+  const long long per = (n + nchunks - 1) / nchunks;                       // equal chunks ...
+  return (per + kTilePts - 1) / kTilePts * kTilePts;                      // ... of whole tiles
+}
+
+// which compaction: 1 = single pass with look-back (default: 93 us on C2), 2 = classify + dense
+// projection kernels (104 us so far).  PBK_COMPACT_IMPL overrides.
+static int compact_impl() {
+  const char* e = getenv("PBK_COMPACT_IMPL");           // read per call: tests switch it
+  return (e && e[0] == '2') ? 2 : 1;
 }
 
 template <typename T, bool DIST>
 static int launch_compact(const void* X, int64_t n, const pbk_project_params& P, void* uv,
                           double* depth, uint8_t* valid, int64_t* count, void* scratch, cudaStream_t s,
                           const DeviceInfo* di) {
+  if (compact_impl() == 1) return launch_compact_lookback<T, DIST>(X, n, P, uv, depth, valid, count, scratch, s, di);
   constexpr int NST = RingCfg<T>::kStages;
-  constexpr int smem = kCpWarps * NST * CpTile<T>::kBytes + kCpWarps * NST * 8;
-  auto kern = project_compact_kernel<T, DIST>;
-  static KernelCache kc;
-  int per_sm;
-  int rc = kc.setup(di, kern, kCpThreads, smem, &per_sm);
+  constexpr int smem_a = kCpWarps * (kCpRing + 1) * CpTile<T>::kBytes + kCpWarps * kCpRing * 8;
+  constexpr int smem_b = kWarps * NST * CpTile<T>::kBytes + kWarps * NST * 8;
+  auto kern_a = compact_classify_kernel<T, DIST>;
+  auto kern_b = project_compacted_kernel<T, DIST>;
+  static KernelCache kc_a, kc_b;
+  int per_sm_a, per_sm_b;
+  int rc = kc_a.setup(di, kern_a, kCpThreads, smem_a, &per_sm_a);
   if (rc) return rc;
-  const long long ntiles = (n + kTilePts - 1) / kTilePts;
-  int grid = resident_grid(di, per_sm, (ntiles + kCpWarps - 1) / kCpWarps);
-  if (grid > kCpMaxGrid) grid = kCpMaxGrid;
-  const T* Xp = static_cast<const T*>(X);
-  long long nn = n;
-  T* uvp = static_cast<T*>(uv);
-  long long* cnt = reinterpret_cast<long long*>(count);
-  unsigned char* scr = static_cast<unsigned char*>(scratch);
-  long long tpc = compact_tiles_per_chunk(n, sizeof(T));
-  pbk_project_params Pc = P;
+  rc = kc_b.setup(di, kern_b, kWarps * 32, smem_b, &per_sm_b);
+  if (rc) return rc;
   ClassifyParams C;
   classify_params(P, &C);
-  PBK_CUDA(cudaMemsetAsync(scratch, 0, 64, s));                  // the grid-barrier counter
-  void* args[] = {&Xp, &nn, &uvp, &depth, &valid, &cnt, &scr, &tpc, &Pc, &C};
-  PBK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(kCpThreads), args,
-                                       smem, s));
+  unsigned char* scr = static_cast<unsigned char*>(scratch);
+  long long* cnt = reinterpret_cast<long long*>(count);
+  const long long chunk = compact_chunk_points(n, sizeof(T));
+  const long long chunk_tiles = (chunk + kTilePts - 1) / kTilePts;
+  const long long xoff = (long long)cp_off_xprime(chunk_tiles);
+  PBK_CUDA(cudaMemsetAsync(scratch, 0, 64, s));                  // the arrival counter
+  PBK_CUDA(cudaMemsetAsync(count, 0, 8, s));                     // running total across chunks
+  for (long long c0 = 0; c0 < n; c0 += chunk) {
+    const long long nc = (n - c0) < chunk ? (n - c0) : chunk;
+    const long long ntiles = (nc + kTilePts - 1) / kTilePts;
+    const int grid_a = resident_grid(di, per_sm_a, (ntiles + kCpWarps - 1) / kCpWarps);
+    long long runs = (long long)grid_a * kCpWarps;
+    if (runs > ntiles) runs = ntiles;
+    if (runs > kCpMaxRuns) runs = kCpMaxRuns;
+    const int grid_b = resident_grid(di, per_sm_b, (runs + kWarps - 1) / kWarps);
+    const T* Xc = static_cast<const T*>(X) + c0 * 3;
+    kern_a<<<grid_a, kCpThreads, smem_a, s>>>(Xc, nc, valid ? valid + c0 : nullptr, scr, xoff, (int)runs, cnt, P, C);
+    PBK_CHECK_LAUNCH("compact_classify_kernel");
+    // the projection writes at absolute offsets (run offsets include the chunks before)
+    kern_b<<<grid_b, kWarps * 32, smem_b, s>>>(nc, static_cast<T*>(uv), depth, scr, xoff, (int)runs, P);
+    PBK_CHECK_LAUNCH("project_compacted_kernel");
+  }
   return PBK_OK;
 }
 
@@ -744,10 +1182,13 @@ PBK_API int pbk_debug_compact_clocks(unsigned long long out[16], int reset) {
 size_t pbk_project_scratch_bytes(int64_t n, int in_dtype) {
   if (n < 0) n = 0;
   const size_t elem = in_dtype == PBK_F64 ? 8 : 4;
-  const long long tpc = pbk::compact_tiles_per_chunk(n, elem);
-  // control words + the X' region of one chunk (+ one tile of slack for the 16-byte rounding of
-  // the last bulk copy)
-  return pbk::kCpCtlBytes + (size_t)(tpc + 1) * pbk::kTilePts * 3 * elem;
+  const long long chunk = pbk::compact_chunk_points(n, elem);
+  const long long tiles = (chunk + pbk::kTilePts - 1) / pbk::kTilePts;
+  // two-kernel form: control words + run totals / offsets + per-tile counts + the X' tiles of one chunk
+  const size_t two = pbk::cp_off_xprime(tiles) + (size_t)tiles * pbk::kTilePts * 3 * elem;
+  // single-pass form: tile status words + one prefix word per generation
+  const size_t one = (size_t)(2 * ((n + pbk::kCtaPts - 1) / pbk::kCtaPts) + 4) * 8;
+  return pbk::compact_impl() == 1 ? one : (two > one ? two : one);
 }
 
 int pbk_project_points(const void* X, int in_dtype, int64_t n, const pbk_project_params* params,

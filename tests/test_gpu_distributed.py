@@ -33,6 +33,19 @@ def _emulated_matchers(db, per_kf, nkf, nq, world):
         lo, hi = shard_range(nkf, r, world)
         shard = torch.from_numpy(db[lo * per_kf:hi * per_kf]).cuda()
         ms.append(ShardedKeyframeMatcher(shard, lo * per_kf).use_exchange(xs[r]))
+    # Load every kernel of the fused path before the ranks run concurrently: in ONE process the
+    # first launch of a kernel (lazy module loading) can block the host behind a kernel that is
+    # spinning for a peer that has not been launched yet.  One call per rank with a 1 ms bound
+    # (they time out against each other), then clear the status words.
+    from pybot_b200 import _ffi
+    _ffi.check(_ffi.lib().pbk_set_exchange_timeout_ms(1.0))
+    qw = torch.zeros((nq, 32), dtype=torch.uint8, device="cuda")
+    for m in ms:
+        m.match(qw, 0.75)
+    torch.cuda.synchronize()
+    for x in xs:
+        x.status.word.zero_()
+    _ffi.check(_ffi.lib().pbk_set_exchange_timeout_ms(2000.0))
     return ms, [torch.cuda.Stream() for _ in range(world)]
 
 

@@ -10,6 +10,23 @@ pytestmark = pytest.mark.gpu
 POSES = ("c2", "ident", "big")
 
 
+@pytest.fixture(params=["lookback", "two_kernel"])
+def compact_impl(request, monkeypatch):
+    """Both compaction implementations behind Camera.project(check_*): the single-pass look-back
+    kernel (default) and the classify + dense-projection pair (PBK_COMPACT_IMPL=2)."""
+    monkeypatch.setenv("PBK_COMPACT_IMPL", "2" if request.param == "two_kernel" else "1")
+    return request.param
+
+
+def _same_bits(a, b):
+    """torch.equal on the raw bits (NaN pixels of points that pass a depth-only check compare equal)."""
+    import torch
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    it = {4: torch.int32, 8: torch.int64}[a.element_size()]
+    return bool(torch.equal(a.contiguous().view(it), b.contiguous().view(it)))
+
+
 def _bits_equal(a, b):
     a, b = np.asarray(a), np.asarray(b)
     assert a.shape == b.shape and a.dtype == b.dtype, (a.shape, b.shape, a.dtype, b.dtype)
@@ -94,7 +111,7 @@ def test_project_plain_matches_reference(g2, name):
 
 
 @pytest.mark.parametrize("name", POSES)
-def test_project_masks_and_compaction(g2, name):
+def test_project_masks_and_compaction(g2, name, compact_impl):
     cam = _camera(g2, name)
     x, d, v = cam.project(g2["X"], check_bounds=True, check_depth=True, return_depth=True,
                           return_valid=True)
@@ -107,7 +124,7 @@ def test_project_masks_and_compaction(g2, name):
     assert _bits_equal(x2, g2["projd_%s_x" % name])
 
 
-def test_project_edge_cases(g2):
+def test_project_edge_cases(g2, compact_impl):
     from pybot_b200.vision.camera_utils import Camera, CameraIntrinsic
     cam = Camera.from_intrinsics(CameraIntrinsic(g2["K"], shape=syn.KITTI_SHAPE))
     x = cam.project(g2["edge_X"])
@@ -132,7 +149,7 @@ def test_check_bounds_without_shape_raises(g2):
         cam.project(g2["X"], check_bounds=True)
 
 
-def test_project_vs_oracle_seeded_200k():
+def test_project_vs_oracle_seeded_200k(compact_impl):
     """C2 distribution at 200k points against the oracle port (cv2 when importable)."""
     from pybot_b200.vision.camera_utils import Camera, CameraIntrinsic, CameraExtrinsic
     from pybot_b200.geometry import RigidTransform
@@ -153,7 +170,7 @@ def test_project_vs_oracle_seeded_200k():
     assert np.array_equal(got[2], ref2[2]) and _bits_equal(got[0], ref2[0])
 
 
-def test_compaction_full_size_properties():
+def test_compaction_full_size_properties(compact_impl):
     """C2 full size (10M): compaction is order-preserving and complete; checked
     against the uncompacted output of the same kernel family."""
     import torch
@@ -182,7 +199,7 @@ def test_compaction_full_size_properties():
 @pytest.mark.parametrize("n", [1, 2, 3, 1023, 1024, 1025, 2047, 3073, 444 * 1024 + 7, 2 * 444 * 1024 + 1021,
                                3 * 444 * 1024 + 2])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_compaction_ragged_sizes_equal_boolean_indexing(n, dtype):
+def test_compaction_ragged_sizes_equal_boolean_indexing(n, dtype, compact_impl):
     """The pipelined compaction kernel (1, 2, 3 ... generations of tiles per CTA,
     ragged last tile with a byte count that is not a multiple of 16) must equal
     boolean indexing of the uncompacted outputs, bit for bit."""
@@ -206,7 +223,7 @@ def test_compaction_ragged_sizes_equal_boolean_indexing(n, dtype):
     assert torch.equal(uv[:m], uv0[keep]) and torch.equal(dep[:m], dep0[keep])
 
 
-def test_compaction_all_and_none_valid():
+def test_compaction_all_and_none_valid(compact_impl):
     import torch
     from pybot_b200 import ops
     n = 50_000
@@ -254,7 +271,7 @@ def _near_threshold_points(n, seed, pose_T, K, shape, min_depth=0.1):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("checks", [(True, True), (True, False), (False, True)])
-def test_compaction_classifier_at_the_thresholds(dtype, checks, monkeypatch):
+def test_compaction_classifier_at_the_thresholds(dtype, checks, monkeypatch, compact_impl):
     """The fp32 classifier of the compacting kernel must agree with the exact fp64 validity of
     the uncompacted kernel (itself pinned to the reference by golden g2) on points crowded
     around every threshold, with several chunks per launch."""
@@ -277,11 +294,11 @@ def test_compaction_classifier_at_the_thresholds(dtype, checks, monkeypatch):
         assert torch.equal(valid, valid0)
         assert m == int(count0.item()) == int(valid0.sum().item())
         keep = valid0.bool()
-        assert torch.equal(uv[:m], uv0[keep]) and torch.equal(dep[:m], dep0[keep])
+        assert _same_bits(uv[:m], uv0[keep]) and _same_bits(dep[:m], dep0[keep])
         assert 0.05 < m / len(Xw) < 0.95
 
 
-def test_projector_runs_under_cuda_graph_capture():
+def test_projector_runs_under_cuda_graph_capture(compact_impl):
     """Projector.run (plain and compacting) captured in a CUDA graph and replayed on new
     inputs: nothing in the call may read host memory asynchronously or allocate."""
     import torch
