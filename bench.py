@@ -595,8 +595,9 @@ def run_c2(D, args, n=10_000_000):
                                     "ms": ms2 / args.steps, "bytes_per_pt": bpp, "valid_frac": m_valid / n,
                                     "GBps": n * bpp * args.steps / (ms2 * 1e-3) / 1e9,
                                     "frac_hbm": n * bpp * args.steps / (ms2 * 1e-3) / 1e9 / hbm,
-                                    "kernel": "project_compact_kernel<float,false>: fp32 classification + X' "
-                                              "compaction, grid barrier, dense fp64 projection, per chunk",
+                                    "kernel": ("compact_classify_kernel + project_compacted_kernel (PBK_COMPACT_IMPL=2)"
+                                               if os.environ.get("PBK_COMPACT_IMPL", "1")[:1] == "2" else
+                                               "project_compact_kernel<float,false> (single pass, decoupled look-back)"),
                                     "traffic": ncu_traffic("project_compact_kernel<float, 0>"),
                                     "traffic_stale": ncu_traffic_stale("transform_project.cu")}
     pr_mask_nc = ops.Projector(Rp, t, K, None, Rz=Rz, tz=tz, shape=syn.KITTI_SHAPE, check_bounds=True,

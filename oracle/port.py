@@ -336,6 +336,32 @@ def wire_colors(carr, flip_rb=False):
     return carr.astype(np.float32) / 255.0 if carr.dtype == np.uint8 else carr.astype(np.float32)
 
 
+# OpenCV asserts imgCount * 2^18 < INT_MAX in knnMatchImpl (matchers.cpp:856): a collection may
+# hold at most 8191 images.  The C3 database has 10 000 keyframes.
+BF_MAX_IMAGES = 8000
+
+
+def _bf_knn_match_grouped(q, train_list, k):
+    """A collection of more than 8191 images: BFMatcher over consecutive groups of images, and
+    the groups' top-k merged by (distance, global row) - the order BFMatcher itself produces
+    inside a collection (ties to the lowest (imgIdx, trainIdx))."""
+    offs = np.concatenate([[0], np.cumsum([len(t) for t in train_list])])
+    parts = []
+    for g0 in range(0, len(train_list), BF_MAX_IMAGES):
+        idx, img, dist = bf_knn_match(q, train_list[g0:g0 + BF_MAX_IMAGES], k)
+        idx = np.where(idx >= 0, idx + offs[g0], -1)
+        img = np.where(img >= 0, img + g0, -1)
+        parts.append((idx, img, dist))
+    idx = np.concatenate([p[0] for p in parts], 1)
+    img = np.concatenate([p[1] for p in parts], 1)
+    dist = np.concatenate([p[2] for p in parts], 1)
+    big = np.iinfo(np.int64).max
+    key = np.where(idx >= 0, dist.astype(np.int64) * (1 << 40) + idx, big)
+    order = np.argsort(key, axis=1, kind="stable")[:, :k]
+    take = lambda a: np.take_along_axis(a, order, 1)      # noqa: E731
+    return take(idx), take(img), take(dist)
+
+
 def bf_knn_match(q, train_list, k=2, threads=None):
     """cv2.BFMatcher(NORM_HAMMING).knnMatch over a keyframe collection
     (no call site in the reference).  A single matrix of
@@ -348,6 +374,8 @@ def bf_knn_match(q, train_list, k=2, threads=None):
         return idx.astype(np.int64), np.zeros_like(idx), dist
     if threads is not None:
         cv2.setNumThreads(threads)
+    if len(train_list) > BF_MAX_IMAGES:
+        return _bf_knn_match_grouped(q, train_list, k)
     bf = cv2.BFMatcher(cv2.NORM_HAMMING)
     bf.add([np.ascontiguousarray(t) for t in train_list])
     res = bf.knnMatch(np.ascontiguousarray(q), k=k)

@@ -37,10 +37,18 @@ constexpr int kCam = PBK_BA_CAM_DOUBLES;   // R(9) t(3) dRdr(27) pad(1)
 __device__ __forceinline__ double sel3(int i, double a, double b, double c) { return i == 0 ? a : (i == 1 ? b : c); }
 
 __device__ __noinline__ void ba_camera_block_warp(const float* __restrict__ rvec, const float* __restrict__ tvec,
-                                                  int c, double* __restrict__ o, int lane) {
+                                                  int c, double* __restrict__ o, double* o2, int lane) {
+  // o: the camera's block in global memory; o2: optional second copy (a warp's shared-memory cache)
   const double rx = rvec[3 * c], ry = rvec[3 * c + 1], rz = rvec[3 * c + 2];
-  if (lane < 3) o[9 + lane] = (double)tvec[3 * c + lane];
-  if (lane == 3) o[39] = 0.0;
+  if (lane < 3) {
+    const double t = (double)tvec[3 * c + lane];
+    o[9 + lane] = t;
+    if (o2 != nullptr) o2[9 + lane] = t;
+  }
+  if (lane == 3) {
+    o[39] = 0.0;
+    if (o2 != nullptr) o2[39] = 0.0;
+  }
   const double theta = sqrt(rx * rx + ry * ry + rz * rz);
   const bool tiny = theta < 2.220446049250313e-16;
   double s = 0.0, c_ = 1.0;
@@ -73,6 +81,7 @@ __device__ __noinline__ void ba_camera_block_warp(const float* __restrict__ rvec
       }
     }
     o[e < 9 ? e : e + 3] = v;
+    if (o2 != nullptr) o2[e < 9 ? e : e + 3] = v;
   }
 }
 
@@ -87,7 +96,7 @@ ba_camera_precompute_kernel(const float* __restrict__ rvec, const float* __restr
   asm volatile("griddepcontrol.launch_dependents;");
   const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (c >= n) return;
-  ba_camera_block_warp(rvec, tvec, c, blocks + (long long)c * kCam, threadIdx.x & 31);
+  ba_camera_block_warp(rvec, tvec, c, blocks + (long long)c * kCam, nullptr, threadIdx.x & 31);
 }
 
 struct BaParams {
@@ -439,25 +448,24 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
     ring.wait(0);
     gather(0, pt);
   }
-  if (P.cams_w != nullptr) {
-    // Fused precompute: the observations are sorted by camera, so the tiles of this CTA
-    // reference the cameras [first record's, last record's] - typically 1-5 - and its eight
-    // warps derive those blocks now (one warp per camera, lane-parallel Rodrigues) while the
-    // first record tiles and point gathers issued above are in flight.  Other CTAs may write
-    // the same block with the same bits.  No second kernel, no launch boundary in the step.
-    const long long ta = (long long)blockIdx.x * kBaWarps * ntiles / nwarps;
-    const long long tb = ((long long)blockIdx.x + 1) * kBaWarps * ntiles / nwarps;
-    if (tb > ta) {
-      const long long oa = ta * kBaTile;
-      long long ob = tb * kBaTile;
-      ob = (ob < P.n_obs ? ob : P.n_obs) - 1;
-      int ca = __ldg(reinterpret_cast<const int*>(P.obs + oa)), cb = __ldg(reinterpret_cast<const int*>(P.obs + ob));
-      ca = ca < 0 ? 0 : (ca >= P.n_cams ? P.n_cams - 1 : ca);
-      cb = cb < 0 ? 0 : (cb >= P.n_cams ? P.n_cams - 1 : cb);
-      for (int c = ca + warp; c <= cb; c += kBaWarps)
-        ba_camera_block_warp(P.rvec, P.tvec, c, P.cams_w + (long long)c * kCam, lane);
-    }
-    __syncthreads();              // this CTA's blocks are visible to all of its warps
+  if (P.cams_w != nullptr && my_tiles > 0) {
+    // Fused precompute: the observations are sorted by camera, so the tiles of THIS WARP
+    // reference the cameras [its first record's, its last record's] - one or two at C4 - and
+    // the warp derives those blocks now (lane-parallel Rodrigues) while the record tiles and
+    // point gathers issued above are in flight: the first one straight into its shared-memory
+    // cache, all of them into cam_blocks (read back by this same warp when its camera changes;
+    // other warps may write the same block with the same bits).  No second kernel, no launch
+    // boundary, no CTA barrier in the step.
+    const long long oa = t_begin * kBaTile;
+    long long ob = t_end * kBaTile;
+    ob = (ob < P.n_obs ? ob : P.n_obs) - 1;
+    int ca = __ldg(reinterpret_cast<const int*>(P.obs + oa)), cb = __ldg(reinterpret_cast<const int*>(P.obs + ob));
+    ca = ca < 0 ? 0 : (ca >= P.n_cams ? P.n_cams - 1 : ca);
+    cb = cb < 0 ? 0 : (cb >= P.n_cams ? P.n_cams - 1 : cb);
+    for (int c = ca; c <= cb; ++c)
+      ba_camera_block_warp(P.rvec, P.tvec, c, P.cams_w + (long long)c * kCam, c == ca ? cam_cache[warp] : nullptr, lane);
+    cached_cam = ca;
+    __syncwarp();                 // the warp's blocks (shared and global) are visible to all of its lanes
   }
   // Launched behind the stand-alone camera precompute with programmatic stream serialization
   // (two-kernel route), everything above - barrier init, the first record tiles, the first

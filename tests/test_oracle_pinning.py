@@ -159,3 +159,23 @@ def test_synthetic_generators_are_seeded():
     assert np.array_equal(q1, q2) and np.array_equal(d1, d2)
     rv, tv, K, pts, oc, op, uv = syn.c4_problem(n_cams=10, n_points=100)
     assert len(oc) == 400 and (np.diff(oc) >= 0).all()
+
+
+def test_grouped_bfmatcher_equals_one_collection(monkeypatch):
+    """OpenCV caps a collection at 8191 images (matchers.cpp:856); the port then runs BFMatcher
+    over groups of images and merges by (distance, global row).  On tie-heavy descriptors the
+    grouped result must equal the single-collection result exactly."""
+    pytest.importorskip("cv2")
+    from oracle import port
+    rng = np.random.default_rng(5)
+    q = rng.integers(0, 4, (300, 32), dtype=np.uint8)
+    kfs = [rng.integers(0, 4, (int(n), 32), dtype=np.uint8) for n in rng.integers(1, 80, 29)]
+    kfs[20][0] = kfs[3][1] = q[7]                         # duplicate across groups: lower image wins
+    whole = port.bf_knn_match(q, kfs, 2)
+    monkeypatch.setattr(port, "BF_MAX_IMAGES", 6)
+    grouped = port.bf_knn_match(q, kfs, 2)
+    for a, b in zip(whole, grouped):
+        assert np.array_equal(a, b)
+    assert (whole[2][:, 0] == whole[2][:, 1]).mean() > 0.2
+    for a, b in zip(port.knn_ratio_mutual(q, kfs, 0.8), (lambda: (monkeypatch.undo(), port.knn_ratio_mutual(q, kfs, 0.8))[1])()):
+        assert np.array_equal(a, b)
