@@ -689,9 +689,9 @@ def run_c4(D, args, weak=False):
     flush = make_flush(torch)
 
     def step(rec):
-        # ONE kernel per evaluation (camera-sorted observations: the streaming kernel derives its
-        # CTAs' camera blocks in its prologue; world > 1: the cost all-reduce is fused into the
-        # same kernel over NVLink peer memory)
+        # one pbk_ba_evaluate call: camera precompute + streaming kernel (launched with programmatic
+        # stream serialization; world > 1: the cost all-reduce is fused into the kernel over NVLink
+        # peer memory)
         return sb.evaluate()
 
     def step_graph(rec):
@@ -743,7 +743,7 @@ def run_c4(D, args, weak=False):
                    "l2": L2_NOTE},
         "e2e": {"value": n_obs * args.steps / (ems * 1e-3) / 1e6, "unit": "Mobs/s",
                 "h2d_bytes_per_step": int(rv.nbytes + tv.nbytes + pts.nbytes), "d2h_bytes_per_step": 8},
-        "gpu_launches": args.steps, "clocks": clocks,
+        "gpu_launches": 2 * args.steps, "clocks": clocks,
         "exchange": ("cost sum-all-reduce fused into the kernel over NVLink peer memory (symmetric memory), "
                      "no NCCL call in the step" if D.world > 1 else "none (1 GPU)"),
         "variants": variants,
@@ -751,8 +751,8 @@ def run_c4(D, args, weak=False):
                     "note": ("step = HBM time of this rank's %d observations x 96 B + launch / ramp / tail / last-CTA cost "
                              "reduction%s" % (local_obs, " + one NVLink release/acquire round trip and the wait for "
                                               "the slowest rank" if D.world > 1 else ""))},
-        "roofline": {"bound": "hbm", "kernel": "ba_residual_jacobian_kernel<2,2> (one kernel per evaluation: camera "
-                                               "blocks derived in its prologue)", "achieved": gbps,
+        "roofline": {"bound": "hbm", "kernel": "ba_residual_jacobian_kernel<2,2> (behind ba_camera_precompute_kernel, "
+                                               "whose ~3 us overlap its prologue)", "achieved": gbps,
                      "peak": hbm, "unit": "GB/s", "frac": gbps / hbm,
                      "frac_full_step": local_obs * 96.0 / (step_ms * 1e-3) / 1e9 / hbm,
                      "traffic": ncu_traffic("ba_residual_jacobian_kernel<2, 2>") if D.world == 1 else None,
@@ -762,8 +762,8 @@ def run_c4(D, args, weak=False):
                      "algorithmic": "16 B read + 8 + 48 + 24 B written = 96 B/obs",
                      "kernel_ms": kms / args.steps,
                      "copy_same_bytes_GBps": copy_at_size(torch, local_obs * 16, local_obs * 80),
-                     "note": "frac: streaming kernel behind the stand-alone precompute, timed alone; "
-                             "frac_full_step: the one-kernel evaluation a caller gets.  83 % of the traffic is "
+                     "note": "frac: streaming kernel timed alone; frac_full_step: the whole pbk_ba_evaluate "
+                             "call a caller gets (precompute + streaming kernel).  83 % of the traffic is "
                              "writes; a write-only stream of this size sustains ~5.3 TB/s on B200 HBM3e "
                              "(scripts/hbm_probe.py), below the copy figure"},
     }

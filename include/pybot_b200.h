@@ -332,6 +332,24 @@ PBK_API int pbk_sceneflow(const void* dX, int dtype, int H, int W,
                           const pbk_project_params* params, int32_t* winner, float* flow,
                           pbk_stream_t stream);
 
+/* check_visibility, pybot/vision/camera_utils.py:245-266, fused: mask[i] = |atan2(v_x, v_z)| <
+ * half_fov_h && |atan2(-v_y, v_z)| < half_fov_v && zmin <= z <= zmax with pts_c = R X + t
+ * (camera.c2w, the same mul,fma,fma,fma chain as pbk_transform_points), v = pts_c / |pts_c|,
+ * z = pts_c[2].  Every operation rounded as numpy rounds it; the two atan2 are CUDA's double
+ * atan2 (<= 2 ulp; numpy calls the C library's): a decision can differ from the reference only
+ * for an angle within ~1e-15 rad of the field-of-view limit.
+ * X device (n,3) F32/F64; Rt host 12 doubles (R row-major, t); half_fov_* = the reference's
+ * float32 camera.fov[i] * 0.5 as a double; mask device (n,) uint8 (0 / 1).               */
+PBK_API int pbk_fov_mask(const void* X, int in_dtype, int64_t n, const double* Rt,
+                         double half_fov_h, double half_fov_v, double zmin, double zmax,
+                         uint8_t* mask, pbk_stream_t stream);
+
+/* get_median_depth, camera_utils.py:269-276: z[i] = (T * X[i * stride])[2] for every stride-th
+ * point (np.dot chain, float64) - the (camera * pts[::subsample])[:, 2] column alone.
+ * Rz_tz host 4 doubles: third row of R, then t_z.  z device (ceil(n / stride),) float64.   */
+PBK_API int pbk_transform_depth(const void* X, int in_dtype, int64_t n, int64_t stride,
+                                const double* Rz_tz, double* z, pbk_stream_t stream);
+
 /* sampson_error, pybot/vision/camera_utils.py:52-68: F host 9 doubles row-major,
  * pts1 / pts2 device (n,2) float64 -> err (n,) float64 =
  * (x1^T F x2)^2 / ((F x1)_0^2 + (F x1)_1^2 + (F x2)_0^2 + (F x2)_1^2), exactly the

@@ -384,9 +384,77 @@ def g9_epipolar_helpers(ns):
         T3=T3.to_matrix(), tcomp=rt.tf_compose(R1, t))
 
 
+def g10_visibility(ns):
+    """G10: check_visibility / get_median_depth / get_bounded_projection of the real reference
+    (camera_utils.py:245-288) around a posed KITTI camera: points in
+    front, behind, beyond zmax, exactly on zmin / zmax, far outside the field of view."""
+    import importlib
+    cu = importlib.import_module("pybot.vision.camera_utils")
+    rng = np.random.default_rng(1010)
+    pose = ns.RigidTransform.from_rpyxyz(0.02, -0.05, 0.01, 0.3, -0.2, 0.5)
+    c = ns.Camera.from_intrinsics_extrinsics(ns.CameraIntrinsic(syn.kitti_K(), shape=(376, 1241)),
+                                             ns.CameraExtrinsic.from_rigid_transform(pose))
+    n = 20000
+    pts = rng.normal(0, 1.0, (n, 3)) * [30.0, 8.0, 40.0] + [0.0, 0.0, 20.0]
+    pts[:50] = rng.normal(0, 1.0, (50, 3)) * [3, 3, 3] + [0, 0, 150.0]        # beyond zmax = 100
+    cw = pose.matrix                                                         # c2w(X) = pose * X
+    inv = np.linalg.inv(cw)
+    edge = np.array([[0.0, 0.0, 100.0], [0.0, 0.0, 0.0], [1.0, 0.5, 5.0], [0.0, 0.0, 99.999999]])
+    pts[50:54] = (edge - cw[:3, 3]) @ inv[:3, :3].T                          # ~ on the z limits after c2w
+    out = {"vis_pose": pose.matrix, "vis_pose_xyzw": pose.quat.q, "vis_pose_tvec": pose.tvec,
+           "vis_cam_xyzw": c.quat.q, "vis_cam_tvec": c.tvec, "vis_pts": pts}
+    out["vis_mask"] = cu.check_visibility(c, pts)
+    out["vis_mask_z"] = cu.check_visibility(c, pts, zmin=5.0, zmax=30.0)
+    out["vis_mask_f32"] = cu.check_visibility(c, pts.astype(np.float32))
+    out["vis_median"] = np.float64(cu.get_median_depth(c, pts, subsample=7))
+    p2, valid = cu.get_bounded_projection(c, pts, subsample=3)
+    out["vis_bp_x"], out["vis_bp_valid"] = p2, valid
+    out["vis_fov"] = c.fov
+    np.savez_compressed(os.path.join(OUT, "g10_visibility.npz"), **out)
+
+
+def g11_facade(ns):
+    """G11: the parts of the host facade the reference can actually execute - Frustum.from_pose /
+    Camera.frustum vertices, the YAML CameraIntrinsic.save writes (camera_utils.py:547-557,
+    :820-822, :1106-1176) - and, for DualQuaternion (rigid_transform.py:371-480, whose
+    constructor raises), the RigidTransform matrices the same poses give."""
+    import contextlib
+    import importlib
+    import io
+    import tempfile
+    rt = importlib.import_module("pybot.geometry.rigid_transform")
+    cu = importlib.import_module("pybot.vision.camera_utils")
+    pa = ns.RigidTransform.from_rpyxyz(0.3, -0.2, 1.0, 1.0, 2.0, 3.0)
+    pb = ns.RigidTransform.from_rpyxyz(-0.5, 0.1, 0.4, -2.0, 0.5, 1.0)
+    try:                                             # the reference class cannot be instantiated:
+        rt.DualQuaternion(pa.quat.q, pa.tvec)        # its __init__ calls Quaternion(xyzw=...) (:380),
+        dq_error = ""                                # a keyword Quaternion.__init__ does not have
+    except TypeError as e:
+        dq_error = str(e)
+    out = dict(dq_a_xyzw=pa.quat.q, dq_a_tvec=pa.tvec, dq_b_xyzw=pb.quat.q, dq_b_tvec=pb.tvec,
+               dq_a_matrix=pa.matrix, dq_ab_matrix=(pa * pb).matrix, dq_a_inv_matrix=pa.inverse().matrix,
+               dq_reference_error=np.array(dq_error))
+    out["frustum_pose"] = cu.Frustum.from_pose(pa, zmin=0.5, zmax=4.0).vertices
+    c = ns.Camera.from_intrinsics_extrinsics(
+        ns.CameraIntrinsic(syn.kitti_K(), D=np.float64([-0.3, 0.1, 0.001, -0.002, 0.01]), shape=(376, 1241)),
+        ns.CameraExtrinsic.from_rigid_transform(pa))
+    out["frustum_cam"] = c.frustum(zmin=0.5, zmax=20.0).vertices
+    out["frustum_cam_pts"] = c.frustum(zmin=1.0, zmax=2.0, pts=np.float64([[100, 50], [100, 300], [900, 300], [900, 50]])).vertices
+    out["frustum_D"] = c.D
+    with tempfile.TemporaryDirectory() as d:
+        fn = os.path.join(d, "intrinsic.yaml")
+        with contextlib.redirect_stdout(io.StringIO()):          # AttrDict.save_yaml prints the dict
+            ns.CameraIntrinsic(syn.kitti_K(), D=c.D, shape=(376, 1241)).save(fn)
+        out["intrinsic_yaml"] = np.array(open(fn).read())
+    np.savez_compressed(os.path.join(OUT, "g11_facade.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
+    if len(sys.argv) > 1 and sys.argv[1] in ("g10", "g11"):
+        {"g10": g10_visibility, "g11": g11_facade}[sys.argv[1]](ns)
+        return
     g0_host_algebra(ns)
     g1_reconstruct(ns)
     g1b_divcases()
@@ -397,6 +465,8 @@ def main():
     g7_epipolar_wire(ns)
     g8_rays_triangulate(ns)
     g9_epipolar_helpers(ns)
+    g10_visibility(ns)
+    g11_facade(ns)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -76,6 +76,8 @@ SIGNATURES = {
     "pbk_depth_reconstruct": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pbk_depth_reconstruct_sparse": (_i, [_vp, _vp, _i64, _d, _d, _d, _vp, _vp]),
     "pbk_sceneflow": (_i, [_vp, _i, _i, _i, ctypes.POINTER(ProjectParams), _vp, _vp, _vp]),
+    "pbk_fov_mask": (_i, [_vp, _i, _i64, _vp, _d, _d, _d, _d, _vp, _vp]),
+    "pbk_transform_depth": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _vp]),
     "pbk_sampson_error": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "pbk_epipolar_lines": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
     "pbk_triangulate_points": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp]),

@@ -544,9 +544,95 @@ wire_colors_kernel(const uint8_t* __restrict__ bgr, long long n_px, int flip_rb,
   }
 }
 
+// ------------------------------------------------- check_visibility / get_median_depth
+// camera_utils.py:245-266: pts_c = camera.c2w(pts) (np.dot(T, [X;1]): the mul,fma,fma,fma chain
+// of transform_points_kernel), v = pts_c / np.linalg.norm(pts_c, axis=1) (sqrt((x^2+y^2)+z^2),
+// every operation rounded), hangle = arctan2(v_x, v_z), vangle = arctan2(-v_y, v_z), and the
+// four comparisons - fused: the transformed points never leave the SM, one byte per point
+// comes back instead of 24 B out + a host pass over them.
+struct FovParams {
+  double R[9], t[3];
+  double half_h, half_v, zmin, zmax;
+};
+template <typename T>
+__global__ void __launch_bounds__(256)
+fov_mask_kernel(const T* __restrict__ X, long long n, const __grid_constant__ FovParams P, uint8_t* __restrict__ mask) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = (double)X[3 * i], y = (double)X[3 * i + 1], z = (double)X[3 * i + 2];
+  double c[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    double acc = __dmul_rn(P.R[3 * r], x);
+    acc = __fma_rn(P.R[3 * r + 1], y, acc);
+    acc = __fma_rn(P.R[3 * r + 2], z, acc);
+    c[r] = __fma_rn(P.t[r], 1.0, acc);
+  }
+  const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(c[0], c[0]), __dmul_rn(c[1], c[1])), __dmul_rn(c[2], c[2])));
+  const double vx = __ddiv_rn(c[0], nrm), vy = __ddiv_rn(c[1], nrm), vz = __ddiv_rn(c[2], nrm);
+  const double ha = atan2(vx, vz), va = atan2(-vy, vz);
+  mask[i] = (fabs(ha) < P.half_h) && (fabs(va) < P.half_v) && (c[2] >= P.zmin) && (c[2] <= P.zmax);
+}
+
+// z of T * X for every stride-th point (get_median_depth, camera_utils.py:269-276:
+// (camera * pts[::subsample])[:, 2]): 8 B per sampled point out instead of 24
+template <typename T>
+__global__ void __launch_bounds__(256)
+transform_depth_kernel(const T* __restrict__ X, long long n_out, long long stride, double r0, double r1, double r2,
+                       double tz, double* __restrict__ z) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const T* p = X + 3 * i * stride;
+  double acc = __dmul_rn(r0, (double)p[0]);
+  acc = __fma_rn(r1, (double)p[1], acc);
+  acc = __fma_rn(r2, (double)p[2], acc);
+  z[i] = __fma_rn(tz, 1.0, acc);
+}
+
 }  // namespace pbk
 
 extern "C" {
+
+int pbk_fov_mask(const void* X, int in_dtype, int64_t n, const double* Rt, double half_fov_h, double half_fov_v,
+                 double zmin, double zmax, uint8_t* mask, pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(n >= 0 && Rt != nullptr, PBK_EINVAL, "bad arguments");
+  PBK_REQUIRE(in_dtype == PBK_F32 || in_dtype == PBK_F64, PBK_EINVAL, "points must be float32 or float64");
+  if (n == 0) return PBK_OK;
+  PBK_REQUIRE(X && mask, PBK_EINVAL, "NULL device pointer");
+  FovParams P;
+  for (int i = 0; i < 9; ++i) P.R[i] = Rt[i];
+  for (int i = 0; i < 3; ++i) P.t[i] = Rt[9 + i];
+  P.half_h = half_fov_h; P.half_v = half_fov_v; P.zmin = zmin; P.zmax = zmax;
+  const long long blocks = (n + 255) / 256;
+  PBK_REQUIRE(blocks < (1ll << 31), PBK_EINVAL, "n too large");
+  cudaStream_t s = as_stream(stream);
+  if (in_dtype == PBK_F32) fov_mask_kernel<float><<<(int)blocks, 256, 0, s>>>(static_cast<const float*>(X), n, P, mask);
+  else fov_mask_kernel<double><<<(int)blocks, 256, 0, s>>>(static_cast<const double*>(X), n, P, mask);
+  PBK_CHECK_LAUNCH("fov_mask_kernel");
+  return PBK_OK;
+}
+
+int pbk_transform_depth(const void* X, int in_dtype, int64_t n, int64_t stride, const double* Rz_tz, double* z,
+                        pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(n >= 0 && stride >= 1 && Rz_tz != nullptr, PBK_EINVAL, "bad arguments");
+  PBK_REQUIRE(in_dtype == PBK_F32 || in_dtype == PBK_F64, PBK_EINVAL, "points must be float32 or float64");
+  const long long n_out = (n + stride - 1) / stride;
+  if (n_out == 0) return PBK_OK;
+  PBK_REQUIRE(X && z, PBK_EINVAL, "NULL device pointer");
+  const long long blocks = (n_out + 255) / 256;
+  PBK_REQUIRE(blocks < (1ll << 31), PBK_EINVAL, "n too large");
+  cudaStream_t s = as_stream(stream);
+  if (in_dtype == PBK_F32)
+    transform_depth_kernel<float><<<(int)blocks, 256, 0, s>>>(static_cast<const float*>(X), n_out, stride, Rz_tz[0],
+                                                              Rz_tz[1], Rz_tz[2], Rz_tz[3], z);
+  else
+    transform_depth_kernel<double><<<(int)blocks, 256, 0, s>>>(static_cast<const double*>(X), n_out, stride, Rz_tz[0],
+                                                               Rz_tz[1], Rz_tz[2], Rz_tz[3], z);
+  PBK_CHECK_LAUNCH("transform_depth_kernel");
+  return PBK_OK;
+}
 
 int pbk_sampson_error(const double* F, const double* pts1, const double* pts2, int64_t n, double* err,
                       pbk_stream_t stream) {

@@ -274,3 +274,126 @@ class Pose(RigidTransform):
         return "Pose ID: %i, rpy (rxyz): %s tvec: %s" % (
             self.id, np.array_str(self.quat.to_rpy(axes="rxyz"), precision=2),
             np.array_str(self.tvec, precision=2))
+
+
+class DualQuaternion(object):
+    """SE(3) as a unit dual quaternion  real + eps * dual,  dual = 0.5 * (t, 0) * real.
+
+    Same public names as the reference class (rigid_transform.py:371-480): ``real``, ``dual``,
+    ``rotation``, ``translation``, ``+``, ``*`` (compose / scale), ``dot``, ``inverse``,
+    ``conjugate``, ``normalize``, ``to_matrix``, ``to_Rt``, ``to_wxyz``, ``to_xyzw``,
+    ``from_dq``, ``from_Rt``, ``from_matrix``, ``identity``.  The reference's own class cannot
+    be instantiated - its constructor calls ``Quaternion(xyzw=...)``, a keyword ``Quaternion``
+    does not have (TypeError; recorded in golden g11), and ``from_dq`` type-checks its arguments
+    against the wrong class - so there is nothing to pin bit for bit: this is the textbook
+    algebra its docstrings describe, checked against the RigidTransform matrices the reference
+    produces for the same poses (g11).  The dual part is held as a plain xyzw array because it
+    is not a unit quaternion."""
+
+    def __init__(self, xyzw=(0., 0., 0., 1.), tvec=(0., 0., 0.)):
+        self.real = Quaternion(xyzw)
+        t = np.asarray(tvec, np.float64).reshape(3)
+        self.dual = 0.5 * _qmul(np.array([t[0], t[1], t[2], 0.0]), self.real.q)
+
+    def __repr__(self):
+        return "real: %s dual: %s" % (np.array_str(self.real.q, precision=2, suppress_small=True),
+                                      np.array_str(self.dual, precision=2, suppress_small=True))
+
+    @classmethod
+    def from_dq(cls, r, d):
+        a = cls()
+        a.real = r if isinstance(r, Quaternion) else Quaternion(r)
+        a.dual = np.array(d.q if isinstance(d, Quaternion) else d, np.float64).reshape(4)
+        return a
+
+    def __add__(self, other):
+        a = DualQuaternion()
+        a.real = Quaternion.__new__(Quaternion)
+        a.real.q = self.real.q + other.real.q                # blending: normalise() afterwards
+        a.dual = self.dual + other.dual
+        return a
+
+    def __mul__(self, other):
+        """self * other composes like RigidTransform (apply `other` first); a float scales."""
+        if isinstance(other, DualQuaternion):
+            return DualQuaternion.from_dq(_qmul(self.real.q, other.real.q),
+                                          _qmul(self.real.q, other.dual) + _qmul(self.dual, other.real.q))
+        if isinstance(other, float):
+            a = DualQuaternion()
+            a.real = Quaternion.__new__(Quaternion)
+            a.real.q = self.real.q * other
+            a.dual = self.dual * other
+            return a
+        raise TypeError("__mul__ typeerror {:}".format(type(other)))
+
+    def __rmul__(self, other):
+        raise NotImplementedError("Right multiply not implemented yet!")
+
+    def normalize(self):
+        n = np.linalg.norm(self.real.q)
+        self.real.q = self.real.q / n
+        self.dual = self.dual / n
+        self.dual = self.dual - self.real.q * self.real.q.dot(self.dual)      # keep real . dual = 0
+        return self
+
+    def dot(self, other):
+        return self.real.dot(other.real)
+
+    def conjugate(self):
+        return DualQuaternion.from_dq(_qconj(self.real.q), _qconj(self.dual))
+
+    def inverse(self):
+        return self.conjugate()                                               # unit dual quaternion
+
+    @property
+    def rotation(self):
+        return self.real
+
+    @property
+    def translation(self):
+        return 2.0 * _qmul(self.dual, _qconj(self.real.q))[:3]
+
+    def to_matrix(self):
+        result = self.rotation.to_matrix()
+        result[:3, 3] = self.translation
+        return result
+
+    def to_Rt(self):
+        T = self.to_matrix()
+        return T[:3, :3].copy(), T[:3, 3].copy()
+
+    def to_wxyz(self):
+        return self.rotation.to_wxyz()
+
+    def to_xyzw(self):
+        return self.rotation.to_xyzw()
+
+    @classmethod
+    def from_Rt(cls, R, t):
+        T = np.eye(4)
+        T[:3, :3] = np.asarray(R, np.float64)
+        T[:3, 3] = np.asarray(t, np.float64)
+        return cls.from_matrix(T)
+
+    @classmethod
+    def from_matrix(cls, T):
+        T = np.asarray(T, np.float64)
+        return cls(Quaternion.from_matrix(T), T[:3, 3])
+
+    @classmethod
+    def identity(cls):
+        return cls()
+
+
+def _qmul(a, b):
+    """Hamilton product of xyzw quaternions."""
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by,
+                     aw * by - ax * bz + ay * bw + az * bx,
+                     aw * bz + ax * by - ay * bx + az * bw,
+                     aw * bw - ax * bx - ay * by - az * bz])
+
+
+def _qconj(a):
+    return np.array([-a[0], -a[1], -a[2], a[3]])

@@ -641,6 +641,34 @@ def sceneflow(dX, params):
     return _finish(flow, on_dev)
 
 
+def fov_mask(X, R, t, half_fov_h, half_fov_v, zmin, zmax):
+    """check_visibility (camera_utils.py:245-266) fused: bool mask (n,) of the points whose
+    camera-frame direction lies inside the field of view and zmin <= z <= zmax."""
+    T = _ffi.require_cuda()
+    Xd, on_dev = _points_in(X)
+    Rt = np.concatenate([np.asarray(R, np.float64).reshape(9), np.asarray(t, np.float64).reshape(3)])
+    Rt, Rt_p = _ffi.host_f64(Rt, 12)
+    mask = T.empty((max(Xd.shape[0], 1),), dtype=T.uint8, device=Xd.device)[:Xd.shape[0]]
+    in_dt = _ffi.PBK_F32 if Xd.dtype == T.float32 else _ffi.PBK_F64
+    _ffi.check(_ffi.lib().pbk_fov_mask(_ffi.ptr(Xd), in_dt, Xd.shape[0], Rt_p, float(half_fov_h), float(half_fov_v),
+                                       float(zmin), float(zmax), _ffi.ptr(mask), _ffi.stream_ptr()))
+    return mask.view(T.bool) if on_dev else _ffi.to_host(mask).view(np.bool_)
+
+
+def transform_depth(X, Rz, tz, stride=1):
+    """z column of T * X[::stride] (get_median_depth, camera_utils.py:269-276): (ceil(n/stride),) float64."""
+    T = _ffi.require_cuda()
+    Xd, on_dev = _points_in(X)
+    n = Xd.shape[0]
+    n_out = -(-n // int(stride))
+    v = np.concatenate([np.asarray(Rz, np.float64).reshape(3), [float(tz)]])
+    v, v_p = _ffi.host_f64(v, 4)
+    z = T.empty((max(n_out, 1),), dtype=T.float64, device=Xd.device)[:n_out]
+    in_dt = _ffi.PBK_F32 if Xd.dtype == T.float32 else _ffi.PBK_F64
+    _ffi.check(_ffi.lib().pbk_transform_depth(_ffi.ptr(Xd), in_dt, n, int(stride), v_p, _ffi.ptr(z), _ffi.stream_ptr()))
+    return _finish(z, on_dev)
+
+
 def sampson_error(F, pts1, pts2):
     """camera_utils.py:52-68 for (N,2) point arrays; returns (N,) float64."""
     T = _ffi.require_cuda()
@@ -824,12 +852,17 @@ class BAProblemDevice(object):
         self.cost = T.zeros((1,), dtype=T.float64, device=dev)
         self._graph = None
 
-    def evaluate(self, events=None, exchange=None, two_kernels=False):
+    def evaluate(self, events=None, exchange=None, one_kernel=False):
         """One residual + Jacobian evaluation (asynchronous on the current stream).
-        Without `events` it is ONE C-ABI call (pbk_ba_evaluate) and, for camera-sorted
-        observations, ONE kernel: the streaming kernel derives the camera blocks its CTAs need
-        in its prologue.  Unsorted observations (or two_kernels=True) run the per-camera
-        precompute first, the streaming kernel launched with programmatic stream serialization.
+        Without `events` it is ONE C-ABI call (pbk_ba_evaluate): the per-camera precompute, then
+        the streaming kernel launched with programmatic stream serialization so that its
+        prologue (barriers, first record tiles, point gathers) overlaps the precompute.
+        one_kernel=True (camera-sorted observations only): no precompute launch - every warp of
+        the streaming kernel derives the camera blocks of its own observation range in its
+        prologue.  Bit-identical; measured 1 us SLOWER at every size from 1 k to 4 M
+        observations (scripts/ba_size_probe.py: the warp idles through obs -> rvec -> sincos
+        while the two-launch form hides the precompute behind the launch of the second kernel),
+        so it is not the default.
         `events`: optional (start, end) CUDA events recorded around the streaming
         kernel alone (two separate calls, the precompute stays outside), for roofline timing.
         `exchange`: a distributed.PeerCostExchange - the kernel then also performs the
@@ -845,7 +878,7 @@ class BAProblemDevice(object):
             ex = ((exchange.ptrs, exchange.rank, exchange.world, 0, exchange.status.ptr)
                   if exchange is not None else (None, 0, 1, 0, None))
             _ffi.check(L.pbk_ba_evaluate(
-                _ffi.ptr(self.obs), self.n_obs, int(self.sorted_by_camera and not two_kernels),
+                _ffi.ptr(self.obs), self.n_obs, int(bool(one_kernel) and self.sorted_by_camera),
                 _ffi.ptr(self.points), self.n_points,
                 _ffi.ptr(self.rvec), _ffi.ptr(self.tvec), self.n_cams, _ffi.ptr(self.cam_blocks),
                 *(K + out + ex + (s,))))

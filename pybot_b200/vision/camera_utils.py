@@ -33,6 +33,25 @@ def get_baseline(fx, baseline=None, baseline_px=None):
     return baseline, baseline_px
 
 
+def get_calib_params(fx, fy, cx, cy, baseline=None, baseline_px=None):
+    """Deprecated in the reference too (:148-149 raises before doing anything)."""
+    raise RuntimeError("Deprecated, see camera_utils.StereoCamera")
+
+
+def _save_yaml(filename, d):
+    import os
+    import yaml
+    with open(os.path.expanduser(filename), "w") as fp:
+        fp.write(yaml.dump(d, default_flow_style=False))          # the layout AttrDict.save_yaml writes
+
+
+def _load_yaml(filename):
+    import os
+    import yaml
+    with open(os.path.expanduser(filename), "r") as fp:
+        return yaml.safe_load(fp)
+
+
 def construct_K(fx=500.0, fy=500.0, cx=319.5, cy=239.5):
     K = np.eye(3)
     K[0, 0], K[1, 1] = fx, fy
@@ -46,17 +65,20 @@ def construct_D(k1=0, k2=0, k3=0, p1=0, p2=0):
 
 
 def check_visibility(camera, pts_w, zmin=0, zmax=100):
-    """Field-of-view test of reference :245-266; the transform runs on the GPU."""
-    pts_c = np.asarray(camera.c2w(np.asarray(pts_w).reshape(-1, 3)))
-    z = pts_c[:, 2]
-    v = pts_c / np.linalg.norm(pts_c, axis=1).reshape(-1, 1)
-    hangle, vangle = np.arctan2(v[:, 0], v[:, 2]), np.arctan2(-v[:, 1], v[:, 2])
-    return np.bitwise_and.reduce([np.fabs(hangle) < camera.fov[0] * 0.5,
-                                  np.fabs(vangle) < camera.fov[1] * 0.5, z >= zmin, z <= zmax])
+    """Field-of-view test (reference :245-266) as ONE fused kernel: transform into the
+    camera's frame, direction angles and the four comparisons on the device; only the
+    boolean mask comes back."""
+    pts = pts_w.reshape(-1, 3)
+    M = camera.matrix                                       # c2w(X) = camera * X (reference :585-589)
+    fov = camera.fov                                        # float32 pair, like the reference's
+    return ops.fov_mask(pts, M[:3, :3], M[:3, 3], float(fov[0] * 0.5), float(fov[1] * 0.5), zmin, zmax)
 
 
 def get_median_depth(camera, pts, subsample=10):
-    return np.median(np.asarray(camera * pts[::subsample])[:, 2])
+    """Median z of camera * pts[::subsample] (reference :269-276): only the z column of the
+    sampled points is computed and brought back."""
+    M = camera.matrix
+    return np.median(np.asarray(ops.transform_depth(pts, M[2, :3], M[2, 3], subsample)))
 
 
 def get_bounded_projection(camera, pts, subsample=10, return_depth=False):
@@ -110,26 +132,25 @@ def compute_essential(F, K):
 
 
 def compute_epipole(F):
-    """Right epipole: null vector of F scaled to e[2] = 1 (reference :234-242)."""
-    _, _, V = np.linalg.svd(F)
-    e = V[-1]
-    return e / e[2]
+    """Right epipole e with F e = 0, scaled so that e[2] = 1 (what reference :234-242 documents;
+    its own body needs an un-imported `linalg`).  The null vector is the last right singular
+    vector of F."""
+    null_vec = np.linalg.svd(np.asarray(F, np.float64))[2][-1]
+    return null_vec / null_vec[2]
 
 
 def decompose_E(E):
-    """The two rotations and the unit translation of an essential matrix
-    (reference :177-203; no cheirality check there either)."""
+    """E = [t]x R  ->  (R1, R2, t): the two rotation candidates U W V^T / U W^T V^T (flipped to
+    det +1) and the unit baseline direction U[:, 2]; as in reference :177-203 no cheirality test
+    chooses between the four (R, +-t) combinations."""
     U, _, Vt = np.linalg.svd(E)
-    W = np.float32([[0, -1, 0], [1, 0, 0], [0, 0, 1]])
+    quarter_turn = np.float32([[0, -1, 0], [1, 0, 0], [0, 0, 1]])
+    rotations = []
+    for W in (quarter_turn, quarter_turn.T):
+        R = U.dot(W).dot(Vt)
+        rotations.append(-R if np.linalg.det(R) < 0 else R)
     t = U[:, 2] / np.linalg.norm(U[:, 2])
-    assert np.fabs(np.linalg.norm(t) - 1.0) < 1e-6
-    R1 = U.dot(W).dot(Vt)
-    if np.linalg.det(R1) < 0:
-        R1 = -R1
-    R2 = U.dot(W.T).dot(Vt)
-    if np.linalg.det(R2) < 0:
-        R2 = -R2
-    return R1, R2, t
+    return rotations[0], rotations[1], t
 
 
 def recover_pose(E, pts1, pts2, K, distance_threshold, mask):
@@ -256,6 +277,26 @@ class CameraIntrinsic(object):
                            [ad + bc, nbb + ndd, cd - ab],
                            [bd - ac, ab + cd, nbb + ncc]])
 
+    def save(self, filename):
+        """YAML with the reference's keys (:547-557): fx fy cx cy k1 k2 k3 p1 p2 width height."""
+        try:
+            height, width = self.shape[:2]
+        except Exception:
+            height, width = "", ""
+        _save_yaml(filename, dict(
+            fx=float(self.fx), fy=float(self.fy), cx=float(self.cx), cy=float(self.cy),
+            k1=float(self.D[0]), k2=float(self.D[1]), k3=float(self.D[4]), p1=float(self.D[2]), p2=float(self.D[3]),
+            width=int(width), height=int(height)))
+
+    @classmethod
+    def load(cls, filename):
+        """Reads what save() wrote.  Like the reference (:559-565) the shape comes back as
+        int32([width, height]) - the reference's order, kept for file and caller compatibility."""
+        db = _load_yaml(filename)
+        shape = np.int32([db["width"], db["height"]]) if "width" in db and "height" in db else None
+        return cls.from_calib_params(db["fx"], db["fy"], db["cx"], db["cy"], k1=db["k1"], k2=db["k2"],
+                                     k3=db["k3"], p1=db["p1"], p2=db["p2"], shape=shape)
+
     def ray(self, pts, undistort=True, rotate=False, normalize=False):
         """Rays [(u-cx)/fx, (v-cy)/fy, 1] through the (optionally undistorted)
         pixels, optionally rotated into the camera's viewpoint and normalised
@@ -308,6 +349,17 @@ class CameraExtrinsic(RigidTransform):
     def simulate(cls):
         return cls.identity()
 
+    def save(self, filename):
+        """YAML {R: 3x3 nested list, t: list}: the file reference :636-638 means to write (its
+        body reads an undefined name) and :640-643 reads back."""
+        R, t = self.to_Rt()
+        _save_yaml(filename, dict(R=np.asarray(R, np.float64).tolist(), t=np.asarray(t, np.float64).tolist()))
+
+    @classmethod
+    def load(cls, filename):
+        db = _load_yaml(filename)
+        return cls(R=np.float64(db["R"]), t=np.float64(db["t"]))
+
 
 class Camera(CameraIntrinsic, CameraExtrinsic):
     def __init__(self, K, R, t, D=np.zeros(5, dtype=np.float64), shape=None):
@@ -342,6 +394,18 @@ class Camera(CameraIntrinsic, CameraExtrinsic):
     @classmethod
     def from_intrinsics(cls, intrinsic):
         return cls.from_intrinsics_extrinsics(intrinsic, CameraExtrinsic.identity())
+
+    def frustum(self, zmin=0.01, zmax=0.1, pts=None):
+        """Viewing frustum between zmin and zmax (reference :820-822)."""
+        assert self.shape is not None
+        return Frustum.from_camera(self, zmin=zmin, zmax=zmax, pts=pts)
+
+    def save(self, filename):
+        raise NotImplementedError()                       # reference :832-833
+
+    @classmethod
+    def load(cls, filename):
+        raise NotImplementedError()                       # reference :835-837
 
     @classmethod
     def from_KD(cls, K, D, shape=None):
@@ -455,6 +519,11 @@ class StereoCamera(Camera):
         return cls.from_left_with_baseline(lcamera, baseline=baseline)
 
     @classmethod
+    def from_intrinsics_extrinsics(cls, lintrinsics, rintrinsics, rextrinsics):
+        """Left extrinsics assumed identity; not implemented in the reference either (:925-928)."""
+        raise NotImplementedError()
+
+    @classmethod
     def from_left_with_baseline(cls, lcamera, baseline):
         """Left extrinsics is assumed to be identity."""
         rcamera = Camera.from_intrinsics_extrinsics(
@@ -536,3 +605,87 @@ class DepthCamera(CameraIntrinsic):
     @classmethod
     def load(cls, filename):
         raise NotImplementedError()
+
+
+class HalfPlane(object):
+    """Plane through p, q, r (counter-clockwise) as [a, b, c, d] with a x + b y + c z + d = 0 and
+    the normal (p - r) x (q - r) (reference :1069-1099; its from_points calls a method numpy
+    arrays do not have, so the definition in its docstring is what is implemented)."""
+
+    def __init__(self, hp):
+        hp = np.asarray(hp)
+        assert hp.ndim == 1 and len(hp) == 4
+        self.hp_ = hp
+
+    @classmethod
+    def from_points(cls, p, q, r):
+        p, q, r = (np.asarray(v, np.float64) for v in (p, q, r))
+        abc = np.cross(p - r, q - r)
+        return cls(np.r_[abc, -abc.dot(r)])
+
+    def signed_distance(self, pts):
+        """(N,) a x + b y + c z + d for (N,3) points (positive on the normal's side)."""
+        return np.asarray(pts, np.float64).dot(self.hp_[:3]) + self.hp_[3]
+
+    def intersect(self):
+        pass                                              # a stub in the reference as well (:1090-1099)
+
+
+class Frustum(object):
+    """Eight corner points of a viewing frustum: four on the near plane, then four on the far
+    plane, each quad in the same winding (reference :1106-1214)."""
+
+    def __init__(self, vertices):
+        self.vertices_ = vertices
+
+    @property
+    def _front_back_vertices(self):
+        half = len(self.vertices_) // 2                   # the reference divides with `/`: a float index under Python 3
+        return self.vertices_[:half], self.vertices_[half:]
+
+    @classmethod
+    def from_pose(cls, pose, zmin=0.01, zmax=0.1, fov=np.deg2rad(60)):
+        if fov >= np.pi:
+            raise ValueError("Frustum fov cannot be {} radians".format(fov))
+        if zmin < 0.01:
+            raise ValueError("zmin needs to be finite > 0.01")
+        # the reference ignores `fov` and uses the half-extents of a 640x480, f = 500 camera
+        rx, ry = 0.638, 0.478
+        corners = np.array([[-rx, -ry, 1.0], [-rx, ry, 1.0], [rx, ry, 1.0], [rx, -ry, 1.0]])
+        return cls(pose * np.vstack([corners * zmin, corners * zmax]))
+
+    @classmethod
+    def from_camera(cls, c, zmin=0.01, zmax=0.1, pts=None):
+        if not isinstance(c, Camera):
+            raise TypeError("c is not of Camera type, cannot instantiate frustum")
+        if zmin < 0.01:
+            raise ValueError("zmin needs to be finite > 0.01")
+        if pts is None:                                   # the full field of view: the image corners
+            H, W = c.shape
+            pts = np.vstack([[0, 0], [0, H - 1], [W - 1, H - 1], [W - 1, 0]])
+        rays = c.ray(pts, undistort=True, rotate=False)
+        return cls(c.w2c(np.vstack([rays * zmin, rays * zmax])))
+
+    @property
+    def vertices(self):
+        return self.vertices_
+
+    @property
+    def points_and_normals(self):
+        """One (point, unit normal) per bounding plane: the four side planes, then near and far."""
+        near, far = self._front_back_vertices
+        near_next, far_next = np.roll(near, -1, axis=0), np.roll(far, -1, axis=0)
+        e1 = np.vstack([far - near, near_next[0] - near[0], far[2] - far[1]])
+        e2 = np.vstack([far_next - far, near_next[1] - near_next[0], far[1] - far[0]])
+        pts = np.vstack([far, near[0], far[1]])
+        e1 = e1 / np.linalg.norm(e1, axis=1).reshape(-1, 1)
+        e2 = e2 / np.linalg.norm(e2, axis=1).reshape(-1, 1)
+        normals = np.cross(e1, e2)
+        normals /= np.linalg.norm(normals, axis=1).reshape(-1, 1)
+        return pts, normals
+
+    @property
+    def planes(self):
+        """(6,4) rows [n, -n . p]."""
+        pts, normals = self.points_and_normals
+        return np.hstack([normals, -np.sum(pts * normals, axis=1).reshape(-1, 1)])

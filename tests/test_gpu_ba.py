@@ -56,11 +56,11 @@ def test_c4_shaped_problem_vs_oracle():
 
 
 def test_one_kernel_evaluate_equals_two_kernel_forms():
-    """pbk_ba_evaluate on camera-sorted observations is ONE kernel (every CTA derives the camera
-    blocks of its own observation range in its prologue).  It must equal, bit for bit, the
-    two-kernel route (stand-alone precompute + streaming kernel with programmatic stream
-    serialization) and the two separate calls - also when the cameras change between
-    evaluations (no stale camera block may be read) and from a replayed CUDA graph."""
+    """pbk_ba_evaluate: the default route (stand-alone precompute + streaming kernel with
+    programmatic stream serialization), the one-kernel route (every warp derives the camera
+    blocks of its own observation range in its prologue) and the two separate calls must be
+    bit-identical - also when the cameras change between evaluations (no stale camera block
+    may be read) and from a replayed CUDA graph."""
     import torch
     from pybot_b200 import ops
     prob = syn.c4_problem(n_cams=300, n_points=40000)
@@ -73,7 +73,7 @@ def test_one_kernel_evaluate_equals_two_kernel_forms():
         p.cam_blocks.zero_()
         p.evaluate()
         got = [t.clone() for t in (p.r, p.Jc, p.Jp, p.cost)]
-        for kw in (dict(two_kernels=True), dict(events=ev)):
+        for kw in (dict(one_kernel=True), dict(events=ev)):
             p.cam_blocks.zero_()
             p.evaluate(**kw)
             for a, b in zip(got, (p.r, p.Jc, p.Jp, p.cost)):
@@ -97,7 +97,7 @@ def test_few_observations_per_camera_and_camera_gaps():
     keep = keep[(oc[keep] % 7) != 3]                                     # cameras 3, 10, 17 ... unobserved
     p = ops.BAProblemDevice(rv, tv, K, pts, oc[keep], op[keep], uv[keep])
     assert p.sorted_by_camera
-    p.evaluate()
+    p.evaluate(one_kernel=True)
     rr, rJc, rJp, rcost = port.ba_residual_jacobian(rv, tv, K, pts, oc[keep], op[keep], uv[keep], use_cv2=False)
     np.testing.assert_allclose(p.r.cpu().numpy(), rr, rtol=1e-5, atol=1e-4)
     _close(p.Jc.cpu().numpy().reshape(-1, 12), rJc.reshape(-1, 12))

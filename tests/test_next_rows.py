@@ -409,3 +409,47 @@ def test_epipolar_line_ragged_sizes_vs_model(g9, n, dt):
     assert got.is_cuda and np.array_equal(got.cpu().numpy(), want)
     if port.cv2 is not None:
         _same(port.epipolar_line(g9["F"], x), want)
+
+
+@pytest.fixture(scope="module")
+def g10(golden_dir):
+    return np.load(golden_dir + "/g10_visibility.npz")
+
+
+def _vis_camera(g10):
+    from pybot_b200.geometry import RigidTransform
+    from pybot_b200.vision.camera_utils import Camera, CameraExtrinsic, CameraIntrinsic
+    pose = RigidTransform(g10["vis_pose_xyzw"], g10["vis_pose_tvec"])
+    c = Camera.from_intrinsics_extrinsics(CameraIntrinsic(syn.kitti_K(), shape=(376, 1241)),
+                                          CameraExtrinsic.from_rigid_transform(pose))
+    assert np.array_equal(c.quat.q, g10["vis_cam_xyzw"]) and np.array_equal(c.tvec, g10["vis_cam_tvec"])
+    return c
+
+
+@pytest.mark.gpu
+def test_check_visibility_golden(g10):
+    """check_visibility (camera_utils.py:245-266) as one fused kernel against the mask the real
+    reference returned: points behind the camera, beyond zmax, on the z limits, outside the fov."""
+    import torch
+    from pybot_b200.vision.camera_utils import check_visibility
+    c = _vis_camera(g10)
+    assert np.array_equal(c.fov, g10["vis_fov"]) and c.fov.dtype == np.float32
+    pts = g10["vis_pts"]
+    m = check_visibility(c, pts)
+    assert m.dtype == np.bool_ and np.array_equal(m, g10["vis_mask"])
+    assert np.array_equal(c.check_visibility(pts, zmin=5.0, zmax=30.0), g10["vis_mask_z"])
+    assert np.array_equal(check_visibility(c, pts.astype(np.float32)), g10["vis_mask_f32"])
+    md = check_visibility(c, torch.from_numpy(pts).cuda())            # device in -> device mask out
+    assert md.is_cuda and md.dtype == torch.bool and np.array_equal(md.cpu().numpy(), g10["vis_mask"])
+    assert 0.2 < m.mean() < 0.5 and check_visibility(c, pts[:0]).shape == (0,)
+
+
+@pytest.mark.gpu
+def test_median_depth_and_bounded_projection_golden(g10):
+    from pybot_b200.vision.camera_utils import get_bounded_projection, get_median_depth
+    c = _vis_camera(g10)
+    pts = g10["vis_pts"]
+    assert get_median_depth(c, pts, subsample=7) == float(g10["vis_median"])
+    p2, valid = get_bounded_projection(c, pts, subsample=3)
+    assert p2.dtype == np.float32 and np.array_equal(valid, g10["vis_bp_valid"])
+    assert np.array_equal(p2, g10["vis_bp_x"])
