@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import model, port
+from pybot_b200 import synthetic as syn
 
 
 @pytest.fixture(scope="module")
