@@ -221,6 +221,24 @@ PBK_API int pbk_hamming_gather_best_dist(const uint8_t* t, int64_t nt, uint64_t 
                      const uint64_t* peer_bufs, int rank, int world, uint64_t seq,
                      uint32_t* done_counter, uint32_t* status, pbk_stream_t stream);
 
+/* Tensor-core route of the same scan (csrc/hamming_tc.cu): tcgen05.mma kind::i8 over descriptors
+ * expanded to 256 signed bytes (bit -> +1 / -1, so that the int32 dot product is 256 - 2 d),
+ * accumulators in tensor memory, the same top-2 keys and merges - results bit-identical to
+ * pbk_hamming_knn2 / pbk_hamming_knn2_dist.  The expanded copy of a database is made once
+ * (pbk_hamming_tc_expand, 256 B per row in the tile layout the kernel's UMMA descriptors
+ * describe) and kept resident; queries are expanded inside the call.
+ * signs     device, >= pbk_hamming_tc_signs_bytes(n) bytes, 16-byte aligned
+ * scratch   device, >= the size pbk_hamming_tc_plan reports (partial keys + expanded queries)   */
+PBK_API size_t pbk_hamming_tc_signs_bytes(int64_t n);
+PBK_API int pbk_hamming_tc_expand(const uint8_t* d, int64_t n, int8_t* signs, pbk_stream_t stream);
+PBK_API int pbk_hamming_tc_plan(int64_t nq, int64_t nt, int* parts, size_t* scratch_bytes);
+PBK_API int pbk_hamming_tc_knn2(const uint8_t* q, int64_t nq, const int8_t* t_signs, int64_t nt,
+                     uint64_t train_base, uint64_t* keys, void* scratch, pbk_stream_t stream);
+PBK_API int pbk_hamming_tc_knn2_dist(const uint8_t* q, int64_t nq, const int8_t* t_signs, int64_t nt,
+                     uint64_t train_base, uint64_t* keys, void* scratch,
+                     const uint64_t* peer_bufs, int rank, int world, uint64_t seq,
+                     uint32_t* done_counter, uint32_t* status, pbk_stream_t stream);
+
 /* popc-pipe peak probe (measurement only): ctas x 256 threads run `iters`
  * rounds of mode 0: independent POPC chains; 1: POPC + one LOP3 each;
  * 2 / 3: the matcher's inner instruction mix (8 / 4 POPC per pair) on

@@ -614,6 +614,10 @@ __global__ void __launch_bounds__(MODE >= 2 ? kHThreads : 256) popc_probe_kernel
   sink[8 + blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// hamming_tc.cu: expands q into q_signs, scans t_signs, writes partial keys (*parts, nq, 2)
+int hamming_tc_scan(const uint8_t* q, long long nq, const int8_t* t_signs, long long nt, unsigned long long train_base,
+                    int8_t* q_signs, unsigned long long* partial, int* parts, const DeviceInfo* di, cudaStream_t s);
+
 static std::atomic<int> g_variant{-1};
 static int hamming_variant() {
   int v = g_variant.load(std::memory_order_relaxed);
@@ -834,6 +838,70 @@ int pbk_hamming_gather_best_dist(const uint8_t* t, int64_t nt, uint64_t train_ba
   PBK_CHECK_LAUNCH("hamming_gather_push_kernel");
   hamming_rows_world_kernel<<<blocks, 256, 0, s>>>(X, rows);
   PBK_CHECK_LAUNCH("hamming_rows_world_kernel");
+  return PBK_OK;
+}
+
+// ---------------------------------------------------------------- tensor-core route
+// (hamming_tc.cu: the scan; the split / world merges are the kernels above)
+int pbk_hamming_tc_knn2(const uint8_t* q, int64_t nq, const int8_t* t_signs, int64_t nt, uint64_t train_base,
+                        uint64_t* keys, void* scratch, pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(nq >= 0 && nt >= 0, PBK_EINVAL, "negative size");
+  if (nq == 0) return PBK_OK;
+  PBK_REQUIRE(q != nullptr && keys != nullptr && scratch != nullptr, PBK_EINVAL, "NULL device pointer");
+  PBK_REQUIRE(nt == 0 || t_signs != nullptr, PBK_EINVAL, "NULL train pointer");
+  PBK_REQUIRE(aligned16(q) && aligned16(t_signs) && aligned16(keys) && aligned16(scratch), PBK_EALIGN,
+              "device pointers must be 16-byte aligned");
+  PBK_REQUIRE(train_base + (uint64_t)nt <= (1ull << 32), PBK_EINVAL, "global train row index must fit 32 bits");
+  const DeviceInfo* di;
+  int rc = current_device_info(&di);
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  int parts = 0;
+  size_t bytes = 0;
+  rc = pbk_hamming_tc_plan(nq, nt, &parts, &bytes);
+  if (rc) return rc;
+  unsigned long long* partial = static_cast<unsigned long long*>(scratch);
+  int8_t* q_signs = static_cast<int8_t*>(scratch) + (((size_t)parts * (size_t)nq * 16 + 255) & ~(size_t)255);
+  rc = hamming_tc_scan(q, nq, t_signs, nt, train_base, q_signs, partial, &parts, di, s);
+  if (rc) return rc;
+  hamming_merge_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(partial, parts, nq,
+                                                                    reinterpret_cast<unsigned long long*>(keys));
+  PBK_CHECK_LAUNCH("hamming_merge_kernel");
+  return PBK_OK;
+}
+
+int pbk_hamming_tc_knn2_dist(const uint8_t* q, int64_t nq, const int8_t* t_signs, int64_t nt, uint64_t train_base,
+                             uint64_t* keys, void* scratch, const uint64_t* peer_bufs, int rank, int world,
+                             uint64_t seq, uint32_t* done_counter, uint32_t* status, pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(nq > 0 && nt >= 0, PBK_EINVAL, "bad sizes");
+  PBK_REQUIRE(q != nullptr && keys != nullptr && scratch != nullptr && done_counter != nullptr, PBK_EINVAL,
+              "NULL device pointer");
+  PBK_REQUIRE(nt == 0 || t_signs != nullptr, PBK_EINVAL, "NULL train pointer");
+  PBK_REQUIRE(aligned16(q) && aligned16(t_signs) && aligned16(keys) && aligned16(scratch), PBK_EALIGN,
+              "device pointers must be 16-byte aligned");
+  PBK_REQUIRE(train_base + (uint64_t)nt <= (1ull << 32), PBK_EINVAL, "global train row index must fit 32 bits");
+  HammingPeers X;
+  int rc = fill_peers(&X, peer_bufs, nq, rank, world, seq, status);
+  if (rc) return rc;
+  const DeviceInfo* di;
+  rc = current_device_info(&di);
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  int parts = 0;
+  size_t bytes = 0;
+  rc = pbk_hamming_tc_plan(nq, nt, &parts, &bytes);
+  if (rc) return rc;
+  unsigned long long* partial = static_cast<unsigned long long*>(scratch);
+  int8_t* q_signs = static_cast<int8_t*>(scratch) + (((size_t)parts * (size_t)nq * 16 + 255) & ~(size_t)255);
+  rc = hamming_tc_scan(q, nq, t_signs, nt, train_base, q_signs, partial, &parts, di, s);
+  if (rc) return rc;
+  const unsigned blocks = (unsigned)((nq + 255) / 256);
+  hamming_merge_push_kernel<<<blocks, 256, 0, s>>>(partial, parts, X, done_counter);
+  PBK_CHECK_LAUNCH("hamming_merge_push_kernel");
+  hamming_merge_world_kernel<<<blocks, 256, 0, s>>>(X, reinterpret_cast<unsigned long long*>(keys));
+  PBK_CHECK_LAUNCH("hamming_merge_world_kernel");
   return PBK_OK;
 }
 

@@ -1,0 +1,437 @@
+// Brute-force Hamming kNN (k = 2) on the 5th-generation tensor cores: tcgen05.mma kind::i8 with
+// the accumulators in tensor memory (VERDICT r1 "next round" item 9).
+//
+// Same contract as hamming_knn2_kernel (hamming.cu) - per query the two smallest
+// (distance, global train row) keys, bit-identical to cv2.BFMatcher - by a different route.
+// A 256-bit descriptor is expanded ONCE into signed bytes: a query into a_k = bit_k ? +1 : -1,
+// a train row into b_k = bit_k ? -64 : +64, so that the exact int32 dot product is
+//     sum_k a_k b_k = -64 (256 - 2 d) = 128 d - 16384 .
+// A 33rd 32-byte K step carries constants: query side [64 x16, 1, 127, 127, 0 ...], train side
+// [16 x16, c, 0, 0, 0 ...] with c = row % 128, adding 16384 + c.  The accumulator of
+// (query, train row) is therefore the finished 16-bit selection key
+//     key = 128 d + c        (0 .. 32895; distance in the high bits, column in the low 7)
+// straight out of the tensor core, and tcgen05.ld.pack::16b delivers two adjacent columns per
+// register: the epilogue is nothing but the VIMNMX.U16x2 top-2 network (1.5 ALU instructions per
+// pair; the POPC / LOP3 route issues 23.6 and is bound by the 16-lane XU pipe at 4 pairs per
+// clock per SM, profiles/r02_hamming_inner_loop.md).  Rows past the end of the database carry
+// 127 in the two spare constant slots: +32258, a key above every real one.
+//
+// Data layout.  Expanded rows (288 B) live in HBM in exactly the shared-memory image the UMMA
+// descriptors describe (K-major, no swizzle): rows in groups of 8; a group is 18 "core matrices"
+// of 8 rows x 16 bytes (128 B contiguous), one per 16-byte K chunk:
+//     byte address of element k of row r  =  (r / 8) * 2304 + (k / 16) * 128 + (r % 8) * 16 + k % 16
+// => leading (K-chunk) byte offset 128, stride (row-group) byte offset 2304, and ANY run of
+// whole row groups is one contiguous span: tiles arrive by plain 1-D bulk copies
+// (cp.async.bulk), no tensor map.  A database keeps its expanded copy resident next to the
+// compact one (9 x the bytes: 5.8 GB for the 20 M-row C3 database; the compact rows are still
+// what the mutual check gathers).
+//
+// Kernel.  One CTA per SM (216 KB of shared memory, all 512 TMEM columns), grid = query groups
+// of 512 x database splits.  A CTA keeps its 512 expanded queries (4 blocks of M = 128) in
+// shared memory for its whole life and streams its split in tiles of N = 128 rows (36 KB,
+// 2-stage ring).  Work item = (tile, query block): 9 UTCIMMA (K = 32 each) into one of FOUR
+// 128-column accumulator slots, handed to the epilogue through mbarriers
+// (tcgen05.commit -> acc_full, epilogue arrive -> acc_empty), so the tensor pipe runs up to
+// three items ahead of the selection.
+//   warp 0      producer: bulk copies of the query blocks and of the train tiles
+//   warp 1      TMEM allocation; one lane issues every tcgen05.mma / tcgen05.commit
+//   warps 2-9   epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 (its hardware lane quarter)
+//               and columns 64 h .. 64 h + 63 of a slot, h = (w - 2) / 4: one packed tcgen05.ld
+//               (32 registers = 64 keys), requested one item ahead; the slot is released as soon
+//               as the values are in registers; top-2 network; the two survivors of the item are
+//               folded into 32-bit keys.  A lane is one query row of each of the four blocks.
+// Every (split, column half) emits (distance << 32 | global row) keys; the existing merge
+// kernels reduce them - bit-identical to a single ascending scan (unsigned min).
+#include "pbk_common.cuh"
+
+namespace pbk {
+
+constexpr int kTcM = 128;                         // queries per UMMA (TMEM lanes)
+constexpr int kTcQBlocks = 4;                     // query blocks resident per CTA
+constexpr int kTcQGroup = kTcM * kTcQBlocks;      // 512 queries per CTA
+constexpr int kTcN = 128;                         // train rows per tile = UMMA N = accumulator columns
+constexpr int kTcStages = 2;
+constexpr int kTcRowBytes = 288;                  // one expanded descriptor: 256 sign bytes + 32 constant bytes
+constexpr int kTcChunks = kTcRowBytes / 16;       // 18 K chunks of 16 bytes
+constexpr int kTcKSteps = kTcRowBytes / 32;       // 9 UTCIMMA per item
+constexpr int kTcGroupBytes = 8 * kTcRowBytes;    // 2304: one group of 8 rows
+constexpr int kTcTileBytes = kTcN * kTcRowBytes;  // 36 KB
+constexpr int kTcBlockBytes = kTcM * kTcRowBytes; // 36 KB
+constexpr int kTcSlots = 4;                       // accumulator slots of 128 columns
+constexpr int kTcThreads = 320;                   // 10 warps
+constexpr int kTcEpiWarps = 8;
+constexpr int kTcPad = 512;                       // expanded buffers are padded to whole query groups / tiles
+constexpr uint32_t kTcKeyMul = (1u << 23) + 1u;   // 32-bit key = distance * kTcKeyMul + row in split (as hamming.cu)
+constexpr uint32_t kTcNone = 0xFFFFFFFFu;
+constexpr long long kTcMaxSplitRows = 1ll << 23;
+
+constexpr int kTcSmemA = kTcQGroup * kTcRowBytes;                 // 147456
+constexpr int kTcSmemB = kTcStages * kTcTileBytes;                // 73728
+constexpr int kTcSmemBars = (2 * kTcStages + 2 * kTcSlots + 1) * 8;
+constexpr int kTcSmemBytes = kTcSmemA + kTcSmemB + kTcSmemBars + 16;
+
+// ------------------------------------------------------------ expansion: bits -> signed bytes
+// thread = (row, 16-byte K chunk): 2 descriptor bytes in, one 16-byte core-matrix row out; chunks
+// 16 and 17 are the constant K step (see the header).  QUERY: +-1 and [64.., 1, 127, 127];
+// train: -+64 and [16.., row % 128, pad, pad] with pad = 127 for the rows past the end.
+template <bool QUERY>
+__global__ void __launch_bounds__(256)
+hamming_tc_expand_kernel(const uint8_t* __restrict__ d, long long n, long long n_padded, uint4* __restrict__ signs) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // 16-byte piece index
+  if (i >= n_padded * kTcChunks) return;
+  const long long g = i / (8 * kTcChunks);            // row group (144 pieces each)
+  const int in_g = (int)(i - g * (8 * kTcChunks));
+  const int kc = in_g >> 3, ri = in_g & 7;
+  const long long r = g * 8 + ri;
+  const bool real = r < n;
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (kc < 16) {
+    if (real) {
+      const unsigned bits = (unsigned)d[r * 32 + kc * 2] | ((unsigned)d[r * 32 + kc * 2 + 1] << 8);
+      // nibble -> four bytes of 0 / 1 (bit i -> byte i); query: 1 -> 0x01, 0 -> 0xFF (+-1);
+      // train: 1 -> 0xC0 (-64), 0 -> 0x40 (+64)
+      auto four = [](unsigned nib) -> unsigned {
+        const unsigned t = (nib * 0x00204081u) & 0x01010101u;
+        return QUERY ? (0xFFFFFFFFu ^ (t * 0xFEu)) : (0x40404040u + t * 0x80u);
+      };
+      o = make_uint4(four(bits & 15u), four((bits >> 4) & 15u), four((bits >> 8) & 15u), four((bits >> 12) & 15u));
+    }
+  } else if (kc == 16) {
+    const unsigned v = QUERY ? (real ? 0x40404040u : 0u) : 0x10101010u;       // 64 x16 | 16 x16
+    o = make_uint4(v, v, v, v);
+  } else {
+    if (QUERY) o.x = real ? (1u | (127u << 8) | (127u << 16)) : 0u;
+    else o.x = (unsigned)(r & 127) | (real ? 0u : ((127u << 8) | (127u << 16)));
+  }
+  signs[i] = o;
+}
+
+// ------------------------------------------------------------------ tcgen05 / TMEM helpers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, no swizzle, LBO = 128 B (K chunks), SBO = 2304 B (row groups)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(kTcGroupBytes >> 4) << 32) |
+         (1ull << 46);                               // bits [46,48): descriptor version 1 (Blackwell)
+}
+// instruction descriptor, kind::i8: D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kTcIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kTcIdesc), "r"(accumulate), "r"(z), "r"(z), "r"(z), "r"(z)
+      : "memory");
+}
+// the mbarrier receives one arrival when every tcgen05 operation this thread issued so far is done
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 64 consecutive accumulator columns of this thread's TMEM lane, their low 16 bits packed two per
+// register (column 2 i in the low half of r[i], column 2 i + 1 in the high half)
+__device__ __forceinline__ void tc_ld64_packed(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_top2_u16x2(uint32_t& k1, uint32_t& k2, uint32_t key) {
+  uint32_t mx;
+  asm("max.u16x2 %0, %1, %2;" : "=r"(mx) : "r"(k1), "r"(key));
+  asm("min.u16x2 %0, %1, %2;" : "=r"(k1) : "r"(k1), "r"(key));
+  asm("min.u16x2 %0, %1, %2;" : "=r"(k2) : "r"(k2), "r"(mx));
+}
+__device__ __forceinline__ void tc_top2(uint32_t& k1, uint32_t& k2, uint32_t key) {
+  const uint32_t mx = max(k1, key);
+  k1 = min(k1, key);
+  k2 = min(k2, mx);
+}
+
+struct HammingTcParams {
+  const int8_t* q_signs;          // expanded queries, padded to whole groups of 512 rows
+  const int8_t* t_signs;          // expanded train rows of this call, padded to whole tiles
+  unsigned long long* partial;    // (2 * splits, nq, 2)
+  long long nq, nt;
+  long long rows_per_split;       // multiple of kTcN
+  unsigned long long train_base;
+  int splits;
+  int dbg;                        // PBK_TC_DEBUG timing probes: 1 = no selection, 2 = no MMA
+};
+
+// top-2 of one accumulator half-slot (64 columns = 32 packed registers of finished keys
+// 128 d + c) of this thread's query row, folded into (k1, k2).  Two independent trackers (even /
+// odd registers) halve the dependent min / max chain.  ONE copy of this code serves every query
+// block and both column halves (the kernel is instruction-cache sensitive: an earlier build with
+// eight unrolled copies spent 90 % of its stall samples on instruction fetch).
+// tile_base = row in the split of the tile's column 0; rows = rows in the split.
+__device__ __forceinline__ void tc_select(const uint32_t (&v)[32], uint32_t tile_base, uint32_t rows, uint32_t& k1,
+                                          uint32_t& k2) {
+  uint32_t p[2][2] = {{0xFFFFFFFFu, 0xFFFFFFFFu}, {0xFFFFFFFFu, 0xFFFFFFFFu}};
+#pragma unroll
+  for (int j = 0; j < 32; ++j) tc_top2_u16x2(p[j & 1][0], p[j & 1][1], v[j]);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t w = p[c >> 2][(c >> 1) & 1];
+    const uint32_t key16 = (c & 1) ? (w >> 16) : (w & 0xFFFFu);
+    // distance = key >> 7, column of the tile = key & 127 -> 32-bit key = distance * kTcKeyMul + row
+    // in the split; rows past the end of the database (keys above every real one) are dropped
+    const uint32_t row = tile_base + (key16 & 127u);
+    const uint32_t key = row >= rows ? kTcNone : (key16 >> 7) * kTcKeyMul + row;
+    tc_top2(k1, k2, key);
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+hamming_tc_kernel(const __grid_constant__ HammingTcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kTcSmemA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcSmemA + kTcSmemB);
+  uint64_t* b_full = bars;                           // [kTcStages]  train tile landed
+  uint64_t* b_empty = bars + kTcStages;              // [kTcStages]  every MMA that read the tile is done
+  uint64_t* acc_full = bars + 2 * kTcStages;         // [kTcSlots]   accumulator slot written
+  uint64_t* acc_empty = acc_full + kTcSlots;         // [kTcSlots]   all 8 epilogue warps have read it
+  uint64_t* a_full = acc_empty + kTcSlots;           // query blocks landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_full + 1);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int qg = blockIdx.x, split = blockIdx.y;
+  const long long row0 = (long long)split * P.rows_per_split;
+  long long rows = P.nt - row0;
+  if (rows > P.rows_per_split) rows = P.rows_per_split;
+  if (rows < 0) rows = 0;
+  const int ntiles = (int)((rows + kTcN - 1) / kTcN);
+
+  if (tid == 0) {
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < kTcSlots; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kTcEpiWarps); }
+    mbar_init(a_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                                   // all 512 TMEM columns: one CTA per SM (shared memory bound)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================================================= producer
+    if (lane == 0 && ntiles > 0) {
+      mbar_expect_tx(a_full, kTcSmemA);
+      for (int mb = 0; mb < kTcQBlocks; ++mb)
+        tma_load_1d(sA + mb * kTcBlockBytes, P.q_signs + ((size_t)qg * kTcQGroup + (size_t)mb * kTcM) * kTcRowBytes,
+                    kTcBlockBytes, a_full);
+      const int8_t* src = P.t_signs + (size_t)row0 * kTcRowBytes;
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t % kTcStages;
+        if (t >= kTcStages) mbar_wait(&b_empty[s], (uint32_t)(((t / kTcStages) - 1) & 1));
+        mbar_expect_tx(&b_full[s], kTcTileBytes);
+        tma_load_1d(sB + s * kTcTileBytes, src + (size_t)t * kTcTileBytes, kTcTileBytes, &b_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // =============================================================== MMA issuer
+    if (lane == 0 && ntiles > 0) {
+      mbar_wait(a_full, 0);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
+      int item = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t % kTcStages;
+        mbar_wait(&b_full[s], (uint32_t)((t / kTcStages) & 1));
+        tc_fence_after();
+#pragma unroll 1
+        for (int mb = 0; mb < kTcQBlocks; ++mb, ++item) {
+          const int slot = item & (kTcSlots - 1), use = item / kTcSlots;
+          if (use > 0) {
+            mbar_wait(&acc_empty[slot], (uint32_t)((use - 1) & 1));
+            tc_fence_after();
+          }
+          const uint32_t d = tmem_base + (uint32_t)(slot * kTcN);
+          const uint64_t ad = tc_smem_desc(a_addr + mb * kTcBlockBytes), bd = tc_smem_desc(b_addr + s * kTcTileBytes);
+          if (!(P.dbg & 2)) {
+#pragma unroll
+            for (int k = 0; k < kTcKSteps; ++k)                 // K = 32 bytes per instruction: +256 B = +16 in the address field
+              tc_mma_i8(d, ad + (uint64_t)(k * 16), bd + (uint64_t)(k * 16), k > 0 ? 1u : 0u);
+          }
+          tc_commit(&acc_full[slot]);
+        }
+        tc_commit(&b_empty[s]);                       // the tile's shared-memory stage may be refilled
+      }
+    }
+  } else {
+    // ================================================================= epilogue
+    const int lg = warp & 3, h = (warp - 2) >> 2;    // TMEM lane quarter of this warp; column half of a slot
+    // k1 / k2 of the thread's four queries (one per query block), rotated once per item so that
+    // the current block's pair is always element 0 (register-resident without unrolling the loop)
+    uint32_t k1[kTcQBlocks], k2[kTcQBlocks];
+#pragma unroll
+    for (int mb = 0; mb < kTcQBlocks; ++mb) k1[mb] = k2[mb] = kTcNone;
+    const int nitems = ntiles * kTcQBlocks;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(h * 64);
+    // Software pipeline: the accumulators of item i + 1 are requested (tcgen05.ld, asynchronous)
+    // before item i is selected, so the TMEM read latency and the wait for the tensor pipe hide
+    // behind ~250 instructions of selection; the slot goes back to the MMA issuer as soon as its
+    // values are in registers.  Two register sets, the loop unrolled by two (no copies).
+    auto fetch = [&](int item, uint32_t (&v)[32]) {
+      const int slot = item & (kTcSlots - 1);
+      mbar_wait(&acc_full[slot], (uint32_t)((item / kTcSlots) & 1));
+      tc_fence_after();
+      tc_ld64_packed(lane_addr + (uint32_t)(slot * kTcN), v);
+    };
+    auto landed = [&](int item) {            // the values of `item` are in registers: release its slot
+      tc_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[item & (kTcSlots - 1)]);
+    };
+    auto select = [&](int item, const uint32_t (&v)[32]) {
+      if (!(P.dbg & 1)) tc_select(v, (uint32_t)(item >> 2) * kTcN, (uint32_t)rows, k1[0], k2[0]);
+      else k1[0] ^= v[0] ^ v[31] ^ v[17];
+      // rotate: the next item belongs to the next query block
+      const uint32_t a1 = k1[0], a2 = k2[0];
+#pragma unroll
+      for (int m = 0; m < kTcQBlocks - 1; ++m) { k1[m] = k1[m + 1]; k2[m] = k2[m + 1]; }
+      k1[kTcQBlocks - 1] = a1;
+      k2[kTcQBlocks - 1] = a2;
+    };
+    uint32_t v0[32], v1[32];
+    if (nitems > 0) {
+      fetch(0, v0);
+      landed(0);
+    }
+#pragma unroll 1
+    for (int item = 0; item < nitems; item += 2) {          // nitems is a multiple of 4
+      fetch(item + 1, v1);
+      select(item, v0);
+      landed(item + 1);
+      if (item + 2 < nitems) fetch(item + 2, v0);
+      select(item + 1, v1);
+      if (item + 2 < nitems) landed(item + 2);
+    }
+    // nitems is a multiple of 4: after the loop element m is query block m again
+    const unsigned long long gbase = P.train_base + (unsigned long long)row0;
+#pragma unroll
+    for (int mb = 0; mb < kTcQBlocks; ++mb) {
+      const long long qi = (long long)qg * kTcQGroup + mb * kTcM + lg * 32 + lane;
+      if (qi < P.nq) {
+        unsigned long long o[2];
+        const uint32_t kk[2] = {k1[mb], k2[mb]};
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          o[c] = (kk[c] == kTcNone) ? PBK_KEY_NONE
+                                    : (((unsigned long long)(kk[c] / kTcKeyMul) << 32) | (gbase + (kk[c] % kTcKeyMul)));
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(P.partial + ((long long)(split * 2 + h) * P.nq + qi) * 2);
+        *dst = make_ulonglong2(o[0], o[1]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+static long long tc_pad(long long n) { return (n + kTcPad - 1) / kTcPad * kTcPad; }
+
+// grid: query groups x splits ~ one CTA per SM; every split a whole number of tiles
+static int tc_plan(const DeviceInfo* di, long long nq, long long nt, int* splits, long long* rows_per_split) {
+  const long long qgroups = (nq + kTcQGroup - 1) / kTcQGroup;
+  long long s = qgroups > 0 ? di->sm_count / qgroups : 1;
+  const long long tiles = (nt + kTcN - 1) / kTcN;
+  if (s > tiles) s = tiles;
+  if (s < 1) s = 1;
+  long long rps = (nt + s - 1) / s;
+  rps = (rps + kTcN - 1) / kTcN * kTcN;
+  if (rps > kTcMaxSplitRows) rps = kTcMaxSplitRows;
+  if (rps < kTcN) rps = kTcN;
+  s = (nt + rps - 1) / rps;
+  if (s < 1) s = 1;
+  PBK_REQUIRE(s <= 32767, PBK_EINVAL, "train set too large for one call (%lld splits)", s);
+  *splits = (int)s;
+  *rows_per_split = rps;
+  return PBK_OK;
+}
+
+// expands q into `q_signs` and scans t_signs: partial keys (2 * splits, nq, 2) into `partial`
+int hamming_tc_scan(const uint8_t* q, long long nq, const int8_t* t_signs, long long nt, unsigned long long train_base,
+                    int8_t* q_signs, unsigned long long* partial, int* parts, const DeviceInfo* di, cudaStream_t s) {
+  int splits;
+  long long rps;
+  int rc = tc_plan(di, nq, nt, &splits, &rps);
+  if (rc) return rc;
+  const long long nqp = tc_pad(nq);
+  hamming_tc_expand_kernel<true><<<(unsigned)((nqp * kTcChunks + 255) / 256), 256, 0, s>>>(q, nq, nqp, reinterpret_cast<uint4*>(q_signs));
+  PBK_CHECK_LAUNCH("hamming_tc_expand_kernel");
+  static KernelCache kc;
+  rc = kc.setup(di, hamming_tc_kernel, kTcThreads, kTcSmemBytes, nullptr);
+  if (rc) return rc;
+  HammingTcParams P;
+  P.q_signs = q_signs; P.t_signs = t_signs; P.partial = partial;
+  P.nq = nq; P.nt = nt; P.rows_per_split = rps; P.train_base = train_base; P.splits = splits;
+  P.dbg = 0;
+  if (const char* e = getenv("PBK_TC_DEBUG")) P.dbg = atoi(e);
+  const dim3 grid((unsigned)((nq + kTcQGroup - 1) / kTcQGroup), (unsigned)splits);
+  hamming_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, s>>>(P);
+  PBK_CHECK_LAUNCH("hamming_tc_kernel");
+  *parts = 2 * splits;
+  return PBK_OK;
+}
+
+}  // namespace pbk
+
+extern "C" {
+
+size_t pbk_hamming_tc_signs_bytes(int64_t n) {
+  if (n < 0) n = 0;
+  return (size_t)pbk::tc_pad(n) * pbk::kTcRowBytes;
+}
+
+int pbk_hamming_tc_expand(const uint8_t* d, int64_t n, int8_t* signs, pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(n >= 0, PBK_EINVAL, "negative size");
+  if (n == 0) return PBK_OK;
+  PBK_REQUIRE(d != nullptr && signs != nullptr, PBK_EINVAL, "NULL device pointer");
+  PBK_REQUIRE(aligned16(signs), PBK_EALIGN, "device pointers must be 16-byte aligned");
+  const long long np = tc_pad(n);
+  const long long blocks = (np * kTcChunks + 255) / 256;
+  PBK_REQUIRE(blocks < (1ll << 31), PBK_EINVAL, "too many rows for one call");
+  hamming_tc_expand_kernel<false><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(d, n, np, reinterpret_cast<uint4*>(signs));
+  PBK_CHECK_LAUNCH("hamming_tc_expand_kernel");
+  return PBK_OK;
+}
+
+int pbk_hamming_tc_plan(int64_t nq, int64_t nt, int* parts, size_t* scratch_bytes) {
+  using namespace pbk;
+  PBK_REQUIRE(nq >= 0 && nt >= 0 && parts && scratch_bytes, PBK_EINVAL, "bad arguments");
+  const DeviceInfo* di;
+  int rc = current_device_info(&di);
+  if (rc) return rc;
+  int splits;
+  long long rps;
+  rc = tc_plan(di, nq, nt, &splits, &rps);
+  if (rc) return rc;
+  *parts = 2 * splits;
+  // partial keys, then (256 B aligned) the expanded queries
+  *scratch_bytes = (((size_t)(*parts) * (size_t)(nq > 0 ? nq : 1) * 16 + 255) & ~(size_t)255) + pbk_hamming_tc_signs_bytes(nq);
+  return PBK_OK;
+}
+
+}  // extern "C"

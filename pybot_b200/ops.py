@@ -408,6 +408,31 @@ def hamming_knn2_keys(q_dev, t_dev, train_base=0):
     return keys
 
 
+def hamming_tc_expand(t_dev):
+    """(n,32) uint8 descriptors -> the expanded +-1 copy the tensor-core scan reads (int8 tensor of
+    pbk_hamming_tc_signs_bytes(n) bytes, tile layout of csrc/hamming_tc.cu).  Done once per database."""
+    T = _ffi.torch()
+    n = int(t_dev.shape[0])
+    L = _ffi.lib()
+    signs = T.empty((max(int(L.pbk_hamming_tc_signs_bytes(n)), 16),), dtype=T.int8, device=t_dev.device)
+    _ffi.check(L.pbk_hamming_tc_expand(_ffi.ptr(t_dev) if n else None, n, _ffi.ptr(signs), _ffi.stream_ptr()))
+    return signs
+
+
+def hamming_knn2_keys_tc(q_dev, t_signs, nt, train_base=0):
+    """Top-2 packed keys (nq,2) through the tcgen05 int8 scan; t_signs from hamming_tc_expand."""
+    T = _ffi.torch()
+    nq = int(q_dev.shape[0])
+    parts, nbytes = ctypes.c_int(0), ctypes.c_size_t(0)
+    L = _ffi.lib()
+    _ffi.check(L.pbk_hamming_tc_plan(nq, int(nt), ctypes.byref(parts), ctypes.byref(nbytes)))
+    scratch = T.empty((max(int(nbytes.value), 16),), dtype=T.uint8, device=q_dev.device)
+    keys = T.empty((max(nq, 1), 2), dtype=T.int64, device=q_dev.device)[:nq]
+    _ffi.check(L.pbk_hamming_tc_knn2(_ffi.ptr(q_dev), nq, _ffi.ptr(t_signs) if nt else None, int(nt), int(train_base),
+                                     _ffi.ptr(keys), _ffi.ptr(scratch), _ffi.stream_ptr()))
+    return keys
+
+
 def hamming_merge(partial_dev):
     """(parts, nq, 2) keys -> (nq, 2) global top-2."""
     T = _ffi.torch()

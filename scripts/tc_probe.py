@@ -1,0 +1,38 @@
+"""Timing of the tensor-core Hamming scan against the integer-pipe kernel (one GPU):
+    python scripts/tc_probe.py [rows]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pybot_b200 import ops  # noqa: E402
+
+nt = int(sys.argv[1]) if len(sys.argv) > 1 else 2_500_000
+g = torch.Generator(device="cuda").manual_seed(1)
+q = torch.randint(0, 256, (2000, 32), device="cuda", dtype=torch.uint8, generator=g)
+t = torch.randint(0, 256, (nt, 32), device="cuda", dtype=torch.uint8, generator=g)
+signs = ops.hamming_tc_expand(t)
+torch.cuda.synchronize()
+
+
+def timed(name, fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    print("%-10s %8.3f ms median  %8.3f min   %8.1f Gpairs/s" % (name, ts[len(ts) // 2], ts[0], 2000 * nt / ts[0] / 1e6))
+
+
+timed("popc", lambda: ops.hamming_knn2_keys(q, t, 0))
+timed("tcgen05", lambda: ops.hamming_knn2_keys_tc(q, signs, nt, 0))
+a, b = ops.hamming_knn2_keys(q, t, 0), ops.hamming_knn2_keys_tc(q, signs, nt, 0)
+print("equal:", bool(torch.equal(a, b)))

@@ -1,0 +1,76 @@
+"""GPU parity of the tensor-core (tcgen05 kind::i8) Hamming scan: its top-2 keys must be
+bit-identical to the integer-pipe kernel's (itself pinned to cv2.BFMatcher and the C oracle in
+tests/test_gpu_hamming.py) and to the oracle directly."""
+import numpy as np
+import pytest
+
+from pybot_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+def _keys_both(q, t, base=0):
+    import torch
+    from pybot_b200 import ops
+    qd, td = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    signs = ops.hamming_tc_expand(td)
+    a = ops.hamming_knn2_keys_tc(qd, signs, len(t), base)
+    b = ops.hamming_knn2_keys(qd, td, base)
+    torch.cuda.synchronize()
+    return a.cpu().numpy(), b.cpu().numpy()
+
+
+def test_expansion_layout():
+    """Train rows: bit k of row r -> byte (r/8)*2304 + (k/16)*128 + (r%8)*16 + k%16 = -64 / +64; the
+    constant K step: 16 x 16, then row % 128, then 127, 127 for the rows past the end."""
+    import torch
+    from pybot_b200 import ops
+    rng = np.random.default_rng(0)
+    n = 37
+    d = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    s = ops.hamming_tc_expand(torch.from_numpy(d).cuda()).cpu().numpy()
+    assert s.dtype == np.int8 and s.size == 512 * 288
+    bits = np.unpackbits(d, axis=1, bitorder="little").astype(np.int16)                  # (37, 256)
+    r, k = np.meshgrid(np.arange(n), np.arange(256), indexing="ij")
+    addr = (r // 8) * 2304 + (k // 16) * 128 + (r % 8) * 16 + k % 16
+    assert np.array_equal(s[addr], np.where(bits == 1, -64, 64))
+    rows = np.arange(512)
+    base = (rows // 8) * 2304 + (rows % 8) * 16
+    assert np.all(s[base[:, None] + 16 * 128 + np.arange(16)[None, :]] == 16)
+    assert np.array_equal(s[base + 17 * 128], (rows % 128).astype(np.int8))
+    pad = np.where(rows >= n, 127, 0)
+    assert np.array_equal(s[base + 17 * 128 + 1], pad) and np.array_equal(s[base + 17 * 128 + 2], pad)
+    assert not s[base[n:, None] + (np.arange(16) * 128)[None, :]].any()                  # sign bytes of pad rows are zero
+
+
+@pytest.mark.parametrize("nq,nt", [(1, 1), (5, 3), (128, 128), (300, 1000), (512, 129), (513, 4096 + 77),
+                                   (2000, 2000), (777, 50_000)])
+def test_tc_keys_equal_integer_pipe_keys(nq, nt):
+    q, t = syn.low_entropy_pair(seed=nq * 31 + nt, nq=nq, nt=nt)                         # tie-heavy descriptors
+    a, b = _keys_both(q, t, base=12345)
+    assert np.array_equal(a, b)
+
+
+def test_tc_against_c_oracle_and_ties():
+    from oracle import c_oracle
+    q, t = syn.low_entropy_pair(seed=9, nq=520, nt=150 * 256 + 200)
+    t[30_000] = t[7]                                                                      # exact duplicate far apart
+    q[3] = t[7]
+    a, _ = _keys_both(q, t)
+    idx, dist = (a & 0xFFFFFFFF).astype(np.int64), (a >> 32).astype(np.int32)
+    ridx, rdist = c_oracle.hamming_knn2(q, t)
+    assert np.array_equal(idx, ridx) and np.array_equal(dist, rdist)
+    assert list(idx[3]) == [7, 30_000] and list(dist[3]) == [0, 0]
+
+
+def test_tc_uniform_random_large():
+    """2000 x 2.5 M uniformly random descriptors (one 8-GPU shard of C3): every split / tile / slot path."""
+    import torch
+    from pybot_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = torch.randint(0, 256, (2000, 32), device="cuda", dtype=torch.uint8, generator=g)
+    t = torch.randint(0, 256, (2_500_000, 32), device="cuda", dtype=torch.uint8, generator=g)
+    signs = ops.hamming_tc_expand(t)
+    a = ops.hamming_knn2_keys_tc(q, signs, t.shape[0], 0)
+    b = ops.hamming_knn2_keys(q, t, 0)
+    assert torch.equal(a, b)
