@@ -107,6 +107,17 @@ def ncu_traffic_note(kernel, scale=1.0):
         return "no ncu capture"
 
 
+def measured_bf16():
+    """Dense bf16 TFLOP/s of this pool's B200s (driver-measured burst figure), else the nominal."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        if "bf16_tflops" in d:
+            return float(d["bf16_tflops"]), "MEASURED_PEAKS.json (bf16_tflops, burst, of measured)"
+    return 2250.0, "nominal 2.25 PFLOP/s dense bf16 (no MEASURED_PEAKS.json)"
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -343,12 +354,31 @@ def run_c3(D, args):
         rev = ops.hamming_knn2_keys(rows, q_dev, 0)
         return ops.hamming_ratio_mutual(keys, rev, 0.75)
 
+    engine = "tcgen05 kind::i8 (hamming_tc_kernel)" if m.signs is not None else "integer pipe (hamming_knn2_kernel<2,4>)"
     sampler = ClockSampler(D.local).start() if D.rank == 0 else None
     total_ms, knn_ms = timed_steps(D, step, args.steps, args.warmup, flush)
     clocks = sampler.stop() if sampler else None
     result = [_ffi.to_host(x) for x in step(None)]          # idx, dist, ratio_ok, mutual_ok, valid
     m.check()
     variants = {}
+    # the integer-pipe kernel on the same shard (the north star's formulation; the shipped
+    # default for databases below 65536 rows): scan + split merge, same events
+    popc_ms = None
+    if m.signs is not None:
+        def step_popc(rec):
+            a, b = ev_pair(torch)
+            a.record()
+            k = ops.hamming_knn2_keys(q_dev, shard, m.shard_base)
+            b.record()
+            if rec is not None:
+                rec.append((a, b))
+            return k
+        _, popc_ms = timed_steps(D, step_popc, max(3, args.steps // 2), args.warmup, flush)
+        popc_ms /= max(3, args.steps // 2)
+        keys_tc = m.local_keys(q_dev)
+        variants["integer_pipe_kernel_same_shard"] = {
+            "Gpairs_per_s": float(nq) * float(shard.shape[0]) / (popc_ms * 1e-3) / 1e9, "kernel_ms": popc_ms,
+            "keys_equal_tensor_core_keys": bool(torch.equal(keys_tc, step_popc(None)))}
     if D.world > 1:
         m_nccl = ShardedKeyframeMatcher(shard, lo_kf * per_kf, exchange="nccl")
 
@@ -377,17 +407,20 @@ def run_c3(D, args):
     api_rows = e2e_knn_step(None)
 
     pairs = float(nq) * nt_total
-    launches = (6 if D.world == 1 else 9) * args.steps
+    launches = ((6 if D.world == 1 else 9) + (1 if m.signs is not None else 0)) * args.steps
     res = {
         "metric": "hamming_knn_k2_ratio_mutual", "unit": "Gpairs/s",
         "value": pairs * args.steps / (total_ms * 1e-3) / 1e9,
-        "ms_per_step": total_ms / args.steps, "scaling": "strong", "dtype": "u32 (xor/popc/int-min)",
+        "ms_per_step": total_ms / args.steps, "scaling": "strong",
+        "dtype": "s8 x s8 -> s32 (tcgen05.mma kind::i8), u16 min/max" if m.signs is not None else "u32 (xor/popc/int-min)",
+        "engine": engine,
         "config": {"workload": "C3 loop-closure: 2000 ORB queries vs %d keyframes x 2000 "
                                "(%d descriptors, %d MB), k=2 + ratio 0.75 + mutual; database sharded by "
                                "keyframe range over %d GPU(s)" % (nkf, nt_total, nt_total * 32 >> 20, D.world),
                    "nq": nq, "nt": nt_total, "shard_rows": int(shard.shape[0]),
                    "l2": L2_NOTE,
-                   "state": "database resident in HBM; queries are the per-step input"},
+                   "state": "database resident in HBM (compact rows%s); queries are the per-step input"
+                            % (" + the 288 B/row expanded copy the tensor-core scan reads" if m.signs is not None else "")},
         "e2e": {"value": pairs * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": "Gpairs/s",
                 "h2d_bytes_per_step": nq * 32,
                 "d2h_bytes_per_step": nq * (2 * 8 + 2 * 4 + 1),
@@ -418,34 +451,64 @@ def run_c3(D, args):
         parity["ranks_agree"] = bool(all(x == all_dg[0] for x in all_dg))
         if D.rank == 0:
             db_dev = torch.from_numpy(db_np).cuda()
-            whole = [_ffi.to_host(x) for x in ops.knn_ratio_mutual(q_dev, db_dev, 0.75)]
+            os.environ["PBK_HAMMING_ENGINE"] = "popc"          # the reference scan runs on the OTHER engine
+            try:
+                whole = [_ffi.to_host(x) for x in ops.knn_ratio_mutual(q_dev, db_dev, 0.75)]
+            finally:
+                del os.environ["PBK_HAMMING_ENGINE"]
             parity["vs_single_gpu_scan"] = bool(all(np.array_equal(a, b) for a, b in zip(result, whole)))
             parity["rows"] = nt_total
             parity["bit_exact"] = bool(parity["vs_single_gpu_scan"] and parity["ranks_agree"] and api_ok)
-            parity["reference"] = ("single-GPU scan of the whole database on rank 0 (itself checked against "
-                                   "cv2.BFMatcher in the N=1 line: equal result_digest)")
+            parity["reference"] = ("single-GPU scan of the whole database on rank 0 with the integer-pipe kernel "
+                                   "(the N=1 line checks the same result_digest against cv2.BFMatcher)")
             del db_dev
     if D.rank == 0:
         pk = probe_peaks(D)
         local_pairs = float(nq) * float(shard.shape[0])
         pair_rate = local_pairs * args.steps / (knn_ms * 1e-3)
-        res["roofline"] = {
-            "bound": "popc", "kernel": "hamming_knn2_kernel<2,4> (+ split merge)",
-            "achieved": pair_rate * POPC_ISSUED_PER_PAIR / 1e12, "peak": pk["popc_per_s"] / 1e12, "unit": "Tpopc/s",
-            "frac": pair_rate * POPC_ISSUED_PER_PAIR / pk["popc_per_s"],
-            "frac_algorithmic": pair_rate * 8 / pk["popc_per_s"],
-            "traffic": ncu_traffic("hamming_knn2_kernel", scale=float(shard.shape[0]) / 2.5e6),
-            "traffic_source": ncu_traffic_note("hamming_knn2_kernel", scale=float(shard.shape[0]) / 2.5e6),
-            "traffic_stale": ncu_traffic_stale("hamming.cu"),
+        popc_roof = {
+            "bound": "popc", "kernel": "hamming_knn2_kernel<2,4> (+ split merge)", "unit": "Tpopc/s",
+            "peak": pk["popc_per_s"] / 1e12, "peak_source": "pbk_popc_peak_probe mode 0, measured in this run (burst)",
             "algorithmic": "frac = POPC.32 ISSUED (4 per pair: the eight XOR words are carry-save-compressed "
                            "into four of weight 1,1,2,4; SASS counts in profiles/r02_hamming_inner_loop.md) / "
                            "measured popc-pipe peak = utilisation of the binding (XU) pipe; frac_algorithmic "
                            "= the SURVEY 8(d) figure, 8 POPC per 256-bit pair / the same peak (> 1 because "
                            "the kernel issues half of them)",
-            "peak_source": "pbk_popc_peak_probe mode 0, measured in this run (burst)",
-            "kernel_ms": knn_ms / args.steps, "kernel_share_of_step": knn_ms / total_ms,
-            "Gpairs_per_s_kernel": pair_rate / 1e9,
-        }
+            "traffic": ncu_traffic("hamming_knn2_kernel", scale=float(shard.shape[0]) / 2.5e6),
+            "traffic_source": ncu_traffic_note("hamming_knn2_kernel", scale=float(shard.shape[0]) / 2.5e6),
+            "traffic_stale": ncu_traffic_stale("hamming.cu")}
+        if m.signs is None:
+            res["roofline"] = dict(popc_roof, achieved=pair_rate * POPC_ISSUED_PER_PAIR / 1e12,
+                                   frac=pair_rate * POPC_ISSUED_PER_PAIR / pk["popc_per_s"],
+                                   frac_algorithmic=pair_rate * 8 / pk["popc_per_s"],
+                                   kernel_ms=knn_ms / args.steps, kernel_share_of_step=knn_ms / total_ms,
+                                   Gpairs_per_s_kernel=pair_rate / 1e9)
+        else:
+            bf16, bf16_src = measured_bf16()
+            int8_peak = 2.0 * bf16                      # TOP/s: B200's dense int8 rate is twice its dense bf16 rate
+            tops = pair_rate * 256 * 2 / 1e12            # algorithmic: 256 multiply-adds per 256-bit pair
+            res["roofline"] = {
+                "bound": "tensor", "kernel": "hamming_tc_kernel (tcgen05.mma kind::i8, + query expansion and split merge)",
+                "achieved": tops, "peak": int8_peak, "unit": "TOP/s", "frac": tops / int8_peak,
+                "frac_issued": tops * 288.0 / 256.0 / int8_peak,
+                "frac_of_nominal_4500": tops / 4500.0,
+                "peak_source": "2 x the dense bf16 rate of %s: the int8 tensor rate of B200 is twice its bf16 rate "
+                               "(4.5 vs 2.25 POP/s nominal)" % bf16_src,
+                "algorithmic": "256 int8 multiply-adds (2 ops each) per descriptor pair: the dot product of the +-1 "
+                               "expansions is 256 - 2 d; the kernel issues 288 (a 33rd 32-byte K step adds the "
+                               "column code and bias so that the accumulator IS the 16-bit selection key): frac_issued",
+                "traffic": ncu_traffic("hamming_tc_kernel", scale=float(shard.shape[0]) / 2.5e6),
+                "traffic_source": ncu_traffic_note("hamming_tc_kernel", scale=float(shard.shape[0]) / 2.5e6),
+                "traffic_stale": ncu_traffic_stale("hamming_tc.cu"),
+                "kernel_ms": knn_ms / args.steps, "kernel_share_of_step": knn_ms / total_ms,
+                "Gpairs_per_s_kernel": pair_rate / 1e9,
+                "integer_pipe_kernel": dict(
+                    popc_roof, kernel_ms=popc_ms,
+                    achieved=local_pairs / (popc_ms * 1e-3) * POPC_ISSUED_PER_PAIR / 1e12,
+                    frac=local_pairs / (popc_ms * 1e-3) * POPC_ISSUED_PER_PAIR / pk["popc_per_s"],
+                    frac_algorithmic=local_pairs / (popc_ms * 1e-3) * 8 / pk["popc_per_s"],
+                    note="the north star's formulation, timed on the same shard in this run; the default "
+                         "engine for databases below 65536 rows (per-frame matching)")}
         if D.world == 1:
             base, cpu_result = cpu_baseline_c3(q_np, db_np, per_kf, args.parity_keyframes)
             res["cpu_baseline"] = base

@@ -222,15 +222,19 @@ PBK_API int pbk_hamming_gather_best_dist(const uint8_t* t, int64_t nt, uint64_t 
                      uint32_t* done_counter, uint32_t* status, pbk_stream_t stream);
 
 /* Tensor-core route of the same scan (csrc/hamming_tc.cu): tcgen05.mma kind::i8 over descriptors
- * expanded to 256 signed bytes (bit -> +1 / -1, so that the int32 dot product is 256 - 2 d),
- * accumulators in tensor memory, the same top-2 keys and merges - results bit-identical to
+ * expanded to signed bytes such that the int32 dot product IS the 16-bit selection key
+ * 128 d + column (see the file header), accumulators in tensor memory, the same top-2 keys and merges - results bit-identical to
  * pbk_hamming_knn2 / pbk_hamming_knn2_dist.  The expanded copy of a database is made once
- * (pbk_hamming_tc_expand, 256 B per row in the tile layout the kernel's UMMA descriptors
- * describe) and kept resident; queries are expanded inside the call.
+ * (pbk_hamming_tc_expand, 288 B per row in the tile layout the kernel's UMMA descriptors
+ * describe, padded to a multiple of 512 rows) and kept resident; queries are expanded inside
+ * the call.  An appended database is extended in place: first_row = (old n / 512) * 512
+ * rewrites only the rows from there on (d always points at row 0).  The scan must be given
+ * the whole buffer with the nt it was expanded for (the rows past nt carry end markers).
  * signs     device, >= pbk_hamming_tc_signs_bytes(n) bytes, 16-byte aligned
  * scratch   device, >= the size pbk_hamming_tc_plan reports (partial keys + expanded queries)   */
 PBK_API size_t pbk_hamming_tc_signs_bytes(int64_t n);
-PBK_API int pbk_hamming_tc_expand(const uint8_t* d, int64_t n, int8_t* signs, pbk_stream_t stream);
+PBK_API int pbk_hamming_tc_expand(const uint8_t* d, int64_t n, int64_t first_row, int8_t* signs,
+                                  pbk_stream_t stream);
 PBK_API int pbk_hamming_tc_plan(int64_t nq, int64_t nt, int* parts, size_t* scratch_bytes);
 PBK_API int pbk_hamming_tc_knn2(const uint8_t* q, int64_t nq, const int8_t* t_signs, int64_t nt,
                      uint64_t train_base, uint64_t* keys, void* scratch, pbk_stream_t stream);

@@ -76,8 +76,10 @@ constexpr int kTcSmemBytes = kTcSmemA + kTcSmemB + kTcSmemBars + 16;
 // train: -+64 and [16.., row % 128, pad, pad] with pad = 127 for the rows past the end.
 template <bool QUERY>
 __global__ void __launch_bounds__(256)
-hamming_tc_expand_kernel(const uint8_t* __restrict__ d, long long n, long long n_padded, uint4* __restrict__ signs) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // 16-byte piece index
+hamming_tc_expand_kernel(const uint8_t* __restrict__ d, long long n, long long first_row, long long n_padded,
+                         uint4* __restrict__ signs) {
+  // 16-byte piece index; rows [first_row, n_padded) are (re)written
+  const long long i = first_row * kTcChunks + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_padded * kTcChunks) return;
   const long long g = i / (8 * kTcChunks);            // row group (144 pieces each)
   const int in_g = (int)(i - g * (8 * kTcChunks));
@@ -378,7 +380,7 @@ int hamming_tc_scan(const uint8_t* q, long long nq, const int8_t* t_signs, long 
   int rc = tc_plan(di, nq, nt, &splits, &rps);
   if (rc) return rc;
   const long long nqp = tc_pad(nq);
-  hamming_tc_expand_kernel<true><<<(unsigned)((nqp * kTcChunks + 255) / 256), 256, 0, s>>>(q, nq, nqp, reinterpret_cast<uint4*>(q_signs));
+  hamming_tc_expand_kernel<true><<<(unsigned)((nqp * kTcChunks + 255) / 256), 256, 0, s>>>(q, nq, 0, nqp, reinterpret_cast<uint4*>(q_signs));
   PBK_CHECK_LAUNCH("hamming_tc_expand_kernel");
   static KernelCache kc;
   rc = kc.setup(di, hamming_tc_kernel, kTcThreads, kTcSmemBytes, nullptr);
@@ -404,16 +406,18 @@ size_t pbk_hamming_tc_signs_bytes(int64_t n) {
   return (size_t)pbk::tc_pad(n) * pbk::kTcRowBytes;
 }
 
-int pbk_hamming_tc_expand(const uint8_t* d, int64_t n, int8_t* signs, pbk_stream_t stream) {
+int pbk_hamming_tc_expand(const uint8_t* d, int64_t n, int64_t first_row, int8_t* signs, pbk_stream_t stream) {
   using namespace pbk;
-  PBK_REQUIRE(n >= 0, PBK_EINVAL, "negative size");
-  if (n == 0) return PBK_OK;
+  PBK_REQUIRE(n >= 0 && first_row >= 0 && first_row % kTcPad == 0, PBK_EINVAL,
+              "first_row must be a non-negative multiple of %d", kTcPad);
+  if (n == 0 || first_row >= tc_pad(n)) return PBK_OK;
   PBK_REQUIRE(d != nullptr && signs != nullptr, PBK_EINVAL, "NULL device pointer");
   PBK_REQUIRE(aligned16(signs), PBK_EALIGN, "device pointers must be 16-byte aligned");
   const long long np = tc_pad(n);
-  const long long blocks = (np * kTcChunks + 255) / 256;
+  const long long blocks = ((np - first_row) * kTcChunks + 255) / 256;
   PBK_REQUIRE(blocks < (1ll << 31), PBK_EINVAL, "too many rows for one call");
-  hamming_tc_expand_kernel<false><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(d, n, np, reinterpret_cast<uint4*>(signs));
+  hamming_tc_expand_kernel<false><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(d, n, first_row, np,
+                                                                                  reinterpret_cast<uint4*>(signs));
   PBK_CHECK_LAUNCH("hamming_tc_expand_kernel");
   return PBK_OK;
 }

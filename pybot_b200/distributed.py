@@ -42,9 +42,9 @@ def shard_range(n_items, rank, world):
 class _CudaMatchKernels(object):
     """Default compute backend: libpybot_b200.so."""
 
-    def knn2(self, q, t, train_base):
+    def knn2(self, q, t, train_base, signs=None):
         from . import ops
-        return ops.hamming_knn2_keys(q, t, train_base)
+        return ops.hamming_scan_keys(q, t, train_base, signs)
 
     def merge(self, partial):
         from . import ops
@@ -135,6 +135,12 @@ class ShardedKeyframeMatcher(object):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
         self.fused = exchange == "p2p" and self.world > 1
         self._px = None
+        # large shards are scanned on the tensor cores: keep the expanded copy resident
+        self.signs = None
+        if cuda_path and int(shard.shape[0]) > 0:
+            from . import ops
+            if ops.hamming_engine(int(shard.shape[0])) == "tc":
+                self.signs = ops.hamming_tc_expand(shard)
 
     def use_exchange(self, px):
         """Adopt a prepared PeerKeyExchange (e.g. an emulated one): rank / world come from it."""
@@ -148,6 +154,8 @@ class ShardedKeyframeMatcher(object):
             self._px.check()
 
     def local_keys(self, q):
+        if self.signs is not None:
+            return self.kernels.knn2(q, self.shard, self.shard_base, self.signs)
         return self.kernels.knn2(q, self.shard, self.shard_base)
 
     def global_keys(self, q):
@@ -176,14 +184,20 @@ class ShardedKeyframeMatcher(object):
         px.seq += 1
         L, s = _ffi.lib(), _ffi.stream_ptr()
         splits, nbytes = ctypes.c_int(0), ctypes.c_size_t(0)
-        _ffi.check(L.pbk_hamming_plan(nq, nt, ctypes.byref(splits), ctypes.byref(nbytes)))
+        tc = self.signs is not None
+        _ffi.check((L.pbk_hamming_tc_plan if tc else L.pbk_hamming_plan)(nq, nt, ctypes.byref(splits), ctypes.byref(nbytes)))
         scratch = T.empty((max(int(nbytes.value), 16),), dtype=T.uint8, device=q.device)
         keys = T.empty((nq, 2), dtype=T.int64, device=q.device)
         if events is not None:
             events[0].record()
-        _ffi.check(L.pbk_hamming_knn2_dist(_ffi.ptr(q), nq, _ffi.ptr(self.shard) if nt else None, nt,
-                                           self.shard_base, _ffi.ptr(keys), _ffi.ptr(scratch), px.ptrs, px.rank,
-                                           px.world, px.seq, _ffi.ptr(px.done), px.status.ptr, s))
+        if tc:       # the shard scan on the tensor cores; same fused key exchange
+            _ffi.check(L.pbk_hamming_tc_knn2_dist(_ffi.ptr(q), nq, _ffi.ptr(self.signs), nt, self.shard_base,
+                                                  _ffi.ptr(keys), _ffi.ptr(scratch), px.ptrs, px.rank, px.world, px.seq,
+                                                  _ffi.ptr(px.done), px.status.ptr, s))
+        else:
+            _ffi.check(L.pbk_hamming_knn2_dist(_ffi.ptr(q), nq, _ffi.ptr(self.shard) if nt else None, nt,
+                                               self.shard_base, _ffi.ptr(keys), _ffi.ptr(scratch), px.ptrs, px.rank,
+                                               px.world, px.seq, _ffi.ptr(px.done), px.status.ptr, s))
         if events is not None:
             events[1].record()
         rev = None

@@ -408,19 +408,46 @@ def hamming_knn2_keys(q_dev, t_dev, train_base=0):
     return keys
 
 
-def hamming_tc_expand(t_dev):
-    """(n,32) uint8 descriptors -> the expanded +-1 copy the tensor-core scan reads (int8 tensor of
-    pbk_hamming_tc_signs_bytes(n) bytes, tile layout of csrc/hamming_tc.cu).  Done once per database."""
+TC_MIN_ROWS = 1 << 16        # below this the integer-pipe kernel's latency wins (per-frame 2000 x 2000 matching)
+
+
+def hamming_engine(nt):
+    """'tc' (tcgen05 int8 scan over the expanded database) or 'popc' (integer-pipe kernel).
+    PBK_HAMMING_ENGINE=popc|tc forces one; by default databases of >= 65536 rows take the
+    tensor-core route.  Both return bit-identical keys."""
+    import os
+    e = os.environ.get("PBK_HAMMING_ENGINE", "").lower()
+    if e in ("popc", "tc"):
+        return e
+    return "tc" if nt >= TC_MIN_ROWS else "popc"
+
+
+def hamming_tc_signs_rows(n):
+    """Rows the expanded buffer of an n-row database holds (padded to 512)."""
+    return -(-int(n) // 512) * 512
+
+
+def hamming_tc_expand(t_dev, signs=None, first_row=0):
+    """(n,32) uint8 descriptors -> the expanded signed-byte copy the tensor-core scan reads (int8
+    tensor, 288 B per row, tile layout of csrc/hamming_tc.cu).  Done once per database; with
+    `signs` (a buffer of at least pbk_hamming_tc_signs_bytes(n) bytes) and first_row (a multiple
+    of 512) only the rows from first_row on are (re)written - appending to a database."""
     T = _ffi.torch()
     n = int(t_dev.shape[0])
     L = _ffi.lib()
-    signs = T.empty((max(int(L.pbk_hamming_tc_signs_bytes(n)), 16),), dtype=T.int8, device=t_dev.device)
-    _ffi.check(L.pbk_hamming_tc_expand(_ffi.ptr(t_dev) if n else None, n, _ffi.ptr(signs), _ffi.stream_ptr()))
+    need = max(int(L.pbk_hamming_tc_signs_bytes(n)), 16)
+    if signs is None:
+        signs = T.empty((need,), dtype=T.int8, device=t_dev.device)
+    elif signs.numel() < need:
+        raise ValueError("signs buffer too small")
+    _ffi.check(L.pbk_hamming_tc_expand(_ffi.ptr(t_dev) if n else None, n, int(first_row), _ffi.ptr(signs),
+                                       _ffi.stream_ptr()))
     return signs
 
 
 def hamming_knn2_keys_tc(q_dev, t_signs, nt, train_base=0):
-    """Top-2 packed keys (nq,2) through the tcgen05 int8 scan; t_signs from hamming_tc_expand."""
+    """Top-2 packed keys (nq,2) through the tcgen05 int8 scan; t_signs from hamming_tc_expand for
+    exactly these nt rows."""
     T = _ffi.torch()
     nq = int(q_dev.shape[0])
     parts, nbytes = ctypes.c_int(0), ctypes.c_size_t(0)
@@ -431,6 +458,18 @@ def hamming_knn2_keys_tc(q_dev, t_signs, nt, train_base=0):
     _ffi.check(L.pbk_hamming_tc_knn2(_ffi.ptr(q_dev), nq, _ffi.ptr(t_signs) if nt else None, int(nt), int(train_base),
                                      _ffi.ptr(keys), _ffi.ptr(scratch), _ffi.stream_ptr()))
     return keys
+
+
+def hamming_scan_keys(q_dev, t_dev, train_base=0, signs=None):
+    """Top-2 keys of q against the database t: the tensor-core scan when `signs` (the expanded
+    copy) is given or the engine rule picks it (expanding on the fly: 288 B per row written once
+    is still cheaper than the integer-pipe scan of a large database), else the integer-pipe kernel."""
+    nt = int(t_dev.shape[0])
+    if nt > 0 and int(q_dev.shape[0]) > 0 and hamming_engine(nt) == "tc":
+        if signs is None:
+            signs = hamming_tc_expand(t_dev)
+        return hamming_knn2_keys_tc(q_dev, signs, nt, train_base)
+    return hamming_knn2_keys(q_dev, t_dev, train_base)
 
 
 def hamming_merge(partial_dev):
@@ -468,14 +507,15 @@ def hamming_ratio_mutual(keys, rev_keys, ratio):
     return idx, dist, fb[0, :nq], fb[1, :nq], fb[2, :nq]
 
 
-def knn_ratio_mutual(q, t, ratio=0.75, train_base=0, mutual=True):
+def knn_ratio_mutual(q, t, ratio=0.75, train_base=0, mutual=True, signs=None):
     """Forward k=2 + Lowe ratio + mutual check on one GPU.
     Returns numpy (idx (nq,2) int64, dist (nq,2) int32, ratio_ok, mutual_ok, valid)
-    or device tensors if q is a CUDA tensor."""
+    or device tensors if q is a CUDA tensor.  signs: the database's expanded copy
+    (hamming_tc_expand) if the caller keeps one resident."""
     T = _ffi.require_cuda()
     on_dev = isinstance(q, T.Tensor) and q.is_cuda
     qd, td = _desc_in(q), _desc_in(t)
-    keys = hamming_knn2_keys(qd, td, train_base)
+    keys = hamming_scan_keys(qd, td, train_base, signs)
     rev = None
     if mutual:
         rows = hamming_gather_best(td, keys, train_base)

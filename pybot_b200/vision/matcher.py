@@ -96,6 +96,8 @@ class KeyframeDatabase(object):
         self._buf = None            # (capacity, 32) uint8 on the device
         self._n = 0
         self.offsets = np.zeros(1, np.int64)
+        self._signs = None          # expanded copy for the tensor-core scan (ops.hamming_tc_expand)
+        self._signs_n = 0           # rows it is valid for
 
     def reserve(self, rows):
         """Make room for `rows` descriptors in total (e.g. the expected session length)."""
@@ -152,6 +154,32 @@ class KeyframeDatabase(object):
         if self._buf is None:
             return T.empty((0, 32), dtype=T.uint8, device="cuda")
         return self._buf[:self._n]
+
+    def signs(self):
+        """The expanded (288 B per row) copy the tensor-core scan reads, or None when this
+        database takes the integer-pipe route (small, or PBK_HAMMING_ENGINE=popc).  Kept
+        resident and extended in place: an append only expands the rows from the last whole
+        block of 512 on."""
+        if self._n == 0 or ops.hamming_engine(self._n) != "tc":
+            return None
+        if self._signs_n == self._n:
+            return self._signs
+        T = _ffi.require_cuda()
+        need = int(_ffi.lib().pbk_hamming_tc_signs_bytes(self._n))
+        first = 0
+        if self._signs is None or self._signs.numel() < need:
+            cap = int(_ffi.lib().pbk_hamming_tc_signs_bytes(max(self._buf.shape[0], self._n)))
+            grown = T.empty((cap,), dtype=T.int8, device="cuda")
+            if self._signs is not None and self._signs_n:
+                keep = (self._signs_n // 512) * 512 * 288
+                grown[:keep].copy_(self._signs[:keep])
+                first = (self._signs_n // 512) * 512
+            self._signs = grown
+        else:
+            first = (self._signs_n // 512) * 512
+        ops.hamming_tc_expand(self.flat, self._signs, first)
+        self._signs_n = self._n
+        return self._signs
 
     def split_global(self, g):
         """global rows -> (imgIdx, trainIdx)."""
@@ -249,7 +277,7 @@ class BFMatcher(object):
                 db = self.db
             offsets = db.offsets
             idx, dist, r_ok, m_ok, valid = (_np(x) for x in ops.knn_ratio_mutual(
-                queryDescriptors, db.flat, ratio=r, mutual=mutual))
+                queryDescriptors, db.flat, ratio=r, mutual=mutual, signs=db.signs()))
         idx, dist = np.asarray(idx), np.asarray(dist)
         img, tr = _split_global(offsets, np.maximum(idx, 0))
         img[idx < 0] = -1

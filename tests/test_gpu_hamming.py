@@ -10,6 +10,14 @@ from pybot_b200 import synthetic as syn
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["popc", "tc"])
+def engine(request, monkeypatch):
+    """Every test of this file runs on both scan engines: the integer-pipe kernel and the
+    tcgen05 int8 kernel (forced here even for tiny databases and the reverse pass)."""
+    monkeypatch.setenv("PBK_HAMMING_ENGINE", request.param)
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def g3(golden_dir):
     return np.load(golden_dir + "/g3_matching.npz")
