@@ -33,10 +33,10 @@
 // 128-column accumulator slots, handed to the epilogue through mbarriers
 // (tcgen05.commit -> acc_full, epilogue arrive -> acc_empty), so the tensor pipe runs up to
 // three items ahead of the selection.
-//   warp 0      producer: bulk copies of the query blocks and of the train tiles
-//   warp 1      TMEM allocation; one lane issues every tcgen05.mma / tcgen05.commit
-//   warps 2-9   epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 (its hardware lane quarter)
-//               and columns 64 h .. 64 h + 63 of a slot, h = (w - 2) / 4: one packed tcgen05.ld
+//   warp 9      producer: bulk copies of the query blocks and of the train tiles
+//   warp 8      TMEM allocation; one lane issues every tcgen05.mma / tcgen05.commit
+//   warps 0-7   epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 (its hardware lane quarter)
+//               and columns 64 h .. 64 h + 63 of a slot, h = w / 4: one packed tcgen05.ld
 //               (32 registers = 64 keys), requested one item ahead; the slot is released as soon
 //               as the values are in registers; top-2 network; the two survivors of the item are
 //               folded into 32-bit keys.  A lane is one query row of each of the four blocks.
@@ -51,6 +51,13 @@ constexpr int kTcQBlocks = 4;                     // query blocks resident per C
 constexpr int kTcQGroup = kTcM * kTcQBlocks;      // 512 queries per CTA
 constexpr int kTcN = 128;                         // train rows per tile = UMMA N = accumulator columns
 constexpr int kTcStages = 2;
+#ifndef PBK_TC_PARK_NS
+#define PBK_TC_PARK_NS 1000
+#endif
+#ifndef PBK_TC_PREFETCH
+#define PBK_TC_PREFETCH 4
+#endif
+constexpr int kTcPrefetch = PBK_TC_PREFETCH;      // tiles requested into L2 ahead of the shared-memory ring
 constexpr int kTcRowBytes = 288;                  // one expanded descriptor: 256 sign bytes + 32 constant bytes
 constexpr int kTcChunks = kTcRowBytes / 16;       // 18 K chunks of 16 bytes
 constexpr int kTcKSteps = kTcRowBytes / 32;       // 9 UTCIMMA per item
@@ -58,8 +65,17 @@ constexpr int kTcGroupBytes = 8 * kTcRowBytes;    // 2304: one group of 8 rows
 constexpr int kTcTileBytes = kTcN * kTcRowBytes;  // 36 KB
 constexpr int kTcBlockBytes = kTcM * kTcRowBytes; // 36 KB
 constexpr int kTcSlots = 4;                       // accumulator slots of 128 columns
-constexpr int kTcThreads = 320;                   // 10 warps
-constexpr int kTcEpiWarps = 8;
+constexpr int kTcThreads = 352;                   // 11 warps
+constexpr int kTcEpiWarps = 8;                    // warps 0-7: warp w may only touch TMEM lanes 32 (w % 4) .. +31
+// The scheduler of an SM sub-partition favours its HIGHEST warp id.  The one lane that issues
+// every tcgen05.mma sits in warp 8 (sub-partition 0, above selecting warps 0 and 4) and the
+// producer in warp 9: as warps 1 / 0 under the selecting warps the issuer was starved for issue
+// slots and the tensor pipe ran at 62 % (950 instead of 640 clocks per item).
+// TWO issuing warps (8 and 9: query blocks 0, 2 and 1, 3 of every tile): the tensor pipe accepts
+// little work ahead of what it executes, so the ~400 clocks of serial bookkeeping one thread spends
+// per item (barrier round trips, descriptor arithmetic, commits) were not hidden behind the 640
+// clocks of its nine MMAs - the pipe measured 55 % busy with one issuer.
+constexpr int kTcMmaWarp = 8, kTcMmaWarps = 2, kTcProducerWarp = 10;
 constexpr int kTcPad = 512;                       // expanded buffers are padded to whole query groups / tiles
 constexpr uint32_t kTcKeyMul = (1u << 23) + 1u;   // 32-bit key = distance * kTcKeyMul + row in split (as hamming.cu)
 constexpr uint32_t kTcNone = 0xFFFFFFFFu;
@@ -149,6 +165,20 @@ __device__ __forceinline__ void tc_ld64_packed(uint32_t taddr, uint32_t (&r)[32]
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// mbarrier wait for the warps that may sleep: try_wait with a suspend-time hint, so a waiting warp
+// parks inside the instruction instead of polling shared memory - the tensor pipe fetches its
+// operands from the same shared memory
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAITP_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONEP_%=;\n\t"
+      "bra WAITP_%=;\n\t"
+      "DONEP_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(PBK_TC_PARK_NS)
+      : "memory");
+}
+
 __device__ __forceinline__ void tc_top2_u16x2(uint32_t& k1, uint32_t& k2, uint32_t key) {
   uint32_t mx;
   asm("max.u16x2 %0, %1, %2;" : "=r"(mx) : "r"(k1), "r"(key));
@@ -169,7 +199,7 @@ struct HammingTcParams {
   long long rows_per_split;       // multiple of kTcN
   unsigned long long train_base;
   int splits;
-  int dbg;                        // PBK_TC_DEBUG timing probes: 1 = no selection, 2 = no MMA
+  int dbg;                        // PBK_TC_DEBUG timing probes (results are then wrong): 1 = no selection, 2 = no MMA
 };
 
 // top-2 of one accumulator half-slot (64 columns = 32 packed registers of finished keys
@@ -183,6 +213,14 @@ __device__ __forceinline__ void tc_select(const uint32_t (&v)[32], uint32_t tile
   uint32_t p[2][2] = {{0xFFFFFFFFu, 0xFFFFFFFFu}, {0xFFFFFFFFu, 0xFFFFFFFFu}};
 #pragma unroll
   for (int j = 0; j < 32; ++j) tc_top2_u16x2(p[j & 1][0], p[j & 1][1], v[j]);
+  // Most items cannot change a query's top-2 once a few thousand rows have been seen: the item's
+  // smallest key is compared with the current second-best (k2 >> 23 >= its distance, so
+  // (k2 >> 16) | 127 bounds every 16-bit key that could still enter) and the fold below is
+  // skipped unless some lane of the warp needs it.
+  uint32_t best;
+  asm("min.u16x2 %0, %1, %2;" : "=r"(best) : "r"(p[0][0]), "r"(p[1][0]));
+  best = min(best & 0xFFFFu, best >> 16);
+  if (!__any_sync(0xffffffffu, best <= ((k2 >> 16) | 0x7Fu))) return;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const uint32_t w = p[c >> 2][(c >> 1) & 1];
@@ -217,12 +255,12 @@ hamming_tc_kernel(const __grid_constant__ HammingTcParams P) {
   const int ntiles = (int)((rows + kTcN - 1) / kTcN);
 
   if (tid == 0) {
-    for (int s = 0; s < kTcStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], kTcMmaWarps); }
     for (int s = 0; s < kTcSlots; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kTcEpiWarps); }
     mbar_init(a_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {                                   // all 512 TMEM columns: one CTA per SM (shared memory bound)
+  if (warp == kTcMmaWarp) {                          // all 512 TMEM columns: one CTA per SM (shared memory bound)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -231,7 +269,7 @@ hamming_tc_kernel(const __grid_constant__ HammingTcParams P) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (warp == kTcProducerWarp) {
     // ================================================================= producer
     if (lane == 0 && ntiles > 0) {
       mbar_expect_tx(a_full, kTcSmemA);
@@ -239,26 +277,33 @@ hamming_tc_kernel(const __grid_constant__ HammingTcParams P) {
         tma_load_1d(sA + mb * kTcBlockBytes, P.q_signs + ((size_t)qg * kTcQGroup + (size_t)mb * kTcM) * kTcRowBytes,
                     kTcBlockBytes, a_full);
       const int8_t* src = P.t_signs + (size_t)row0 * kTcRowBytes;
+      // the two-stage ring leaves one tile time (~1.3 us) for a 36 KB load: tiles are pulled into
+      // L2 kTcPrefetch tiles ahead so that the shared-memory copy is an L2 hit
+      for (int t = 0; t < kTcPrefetch && t < ntiles; ++t)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (size_t)t * kTcTileBytes), "r"(kTcTileBytes) : "memory");
       for (int t = 0; t < ntiles; ++t) {
         const int s = t % kTcStages;
-        if (t >= kTcStages) mbar_wait(&b_empty[s], (uint32_t)(((t / kTcStages) - 1) & 1));
+        if (t + kTcPrefetch < ntiles)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (size_t)(t + kTcPrefetch) * kTcTileBytes), "r"(kTcTileBytes) : "memory");
+        if (t >= kTcStages) mbar_wait_parked(&b_empty[s], (uint32_t)(((t / kTcStages) - 1) & 1));
         mbar_expect_tx(&b_full[s], kTcTileBytes);
         tma_load_1d(sB + s * kTcTileBytes, src + (size_t)t * kTcTileBytes, kTcTileBytes, &b_full[s]);
       }
     }
-  } else if (warp == 1) {
-    // =============================================================== MMA issuer
+  } else if (warp >= kTcMmaWarp && warp < kTcMmaWarp + kTcMmaWarps) {
+    // =============================================================== MMA issuers
     if (lane == 0 && ntiles > 0) {
       mbar_wait(a_full, 0);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
-      int item = 0;
+      const int mine = warp - kTcMmaWarp;              // this issuer's query blocks: mine, mine + kTcMmaWarps
       for (int t = 0; t < ntiles; ++t) {
         const int s = t % kTcStages;
         mbar_wait(&b_full[s], (uint32_t)((t / kTcStages) & 1));
         tc_fence_after();
 #pragma unroll 1
-        for (int mb = 0; mb < kTcQBlocks; ++mb, ++item) {
+        for (int mb = mine; mb < kTcQBlocks; mb += kTcMmaWarps) {
+          const int item = t * kTcQBlocks + mb;
           const int slot = item & (kTcSlots - 1), use = item / kTcSlots;
           if (use > 0) {
             mbar_wait(&acc_empty[slot], (uint32_t)((use - 1) & 1));
@@ -278,7 +323,7 @@ hamming_tc_kernel(const __grid_constant__ HammingTcParams P) {
     }
   } else {
     // ================================================================= epilogue
-    const int lg = warp & 3, h = (warp - 2) >> 2;    // TMEM lane quarter of this warp; column half of a slot
+    const int lg = warp & 3, h = warp >> 2;          // TMEM lane quarter of this warp; column half of a slot
     // k1 / k2 of the thread's four queries (one per query block), rotated once per item so that
     // the current block's pair is always element 0 (register-resident without unrolling the loop)
     uint32_t k1[kTcQBlocks], k2[kTcQBlocks];
@@ -292,7 +337,7 @@ hamming_tc_kernel(const __grid_constant__ HammingTcParams P) {
     // values are in registers.  Two register sets, the loop unrolled by two (no copies).
     auto fetch = [&](int item, uint32_t (&v)[32]) {
       const int slot = item & (kTcSlots - 1);
-      mbar_wait(&acc_full[slot], (uint32_t)((item / kTcSlots) & 1));
+      mbar_wait_parked(&acc_full[slot], (uint32_t)((item / kTcSlots) & 1));
       tc_fence_after();
       tc_ld64_packed(lane_addr + (uint32_t)(slot * kTcN), v);
     };
@@ -345,7 +390,7 @@ hamming_tc_kernel(const __grid_constant__ HammingTcParams P) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kTcMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
