@@ -243,6 +243,13 @@ PBK_API int pbk_hamming_tc_knn2_dist(const uint8_t* q, int64_t nq, const int8_t*
                      const uint64_t* peer_bufs, int rank, int world, uint64_t seq,
                      uint32_t* done_counter, uint32_t* status, pbk_stream_t stream);
 
+/* int8 tensor-pipe peak probe (measurement only): one CTA per SM issues iters x 8
+ * tcgen05.mma kind::i8 of the matcher's shape (M 128, N 128, K 32) on resident shared memory, no
+ * data movement, no epilogue.  *macs_per_launch receives the multiply-adds issued.
+ * sink: device uint32[SM count] or NULL.                                                      */
+PBK_API int pbk_hamming_tc_peak_probe(int iters, uint32_t* sink, double* macs_per_launch,
+                                      pbk_stream_t stream);
+
 /* popc-pipe peak probe (measurement only): ctas x 256 threads run `iters`
  * rounds of mode 0: independent POPC chains; 1: POPC + one LOP3 each;
  * 2 / 3: the matcher's inner instruction mix (8 / 4 POPC per pair) on

@@ -77,6 +77,7 @@ SIGNATURES = {
     "pbk_hamming_tc_plan": (_i, [_i64, _i64, ctypes.POINTER(_i), ctypes.POINTER(_sz)]),
     "pbk_hamming_tc_knn2": (_i, [_vp, _i64, _vp, _i64, _u64, _vp, _vp, _vp]),
     "pbk_hamming_tc_knn2_dist": (_i, [_vp, _i64, _vp, _i64, _u64, _vp, _vp, _vp, _i, _i, _u64, _vp, _vp, _vp]),
+    "pbk_hamming_tc_peak_probe": (_i, [_i, _vp, ctypes.POINTER(_d), _vp]),
     "pbk_popc_peak_probe": (_i, [_i, _i, _i, _vp, ctypes.POINTER(_d), _vp]),
     "pbk_depth_reconstruct": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pbk_depth_reconstruct_sparse": (_i, [_vp, _vp, _i64, _d, _d, _d, _vp, _vp]),

@@ -17,12 +17,13 @@
 // 127 in the two spare constant slots: +32258, a key above every real one.
 //
 // Data layout.  Expanded rows (288 B) live in HBM in exactly the shared-memory image the UMMA
-// descriptors describe (K-major, no swizzle): rows in groups of 8; a group is 18 "core matrices"
-// of 8 rows x 16 bytes (128 B contiguous), one per 16-byte K chunk:
-//     byte address of element k of row r  =  (r / 8) * 2304 + (k / 16) * 128 + (r % 8) * 16 + k % 16
-// => leading (K-chunk) byte offset 128, stride (row-group) byte offset 2304, and ANY run of
-// whole row groups is one contiguous span: tiles arrive by plain 1-D bulk copies
-// (cp.async.bulk), no tensor map.  A database keeps its expanded copy resident next to the
+// descriptors describe (K-major, no swizzle), tile by tile: a tile is 128 rows = 18 planes (one
+// per 16-byte K chunk) of 128 x 16 bytes, i.e. of sixteen 8-row "core matrices" (128 B each):
+//     byte address of element k of row r  =  (r / 128) * 36864 + (k / 16) * 2048 + (r % 128) * 16 + k % 16
+// => stride (8-row group) byte offset 128, leading (K-chunk) byte offset 2048; a tile is one
+// contiguous 36 KB span and arrives by ONE plain 1-D bulk copy (cp.async.bulk), no tensor map.
+// (With the chunks of a row group adjacent instead - LBO 128, SBO 2304 - the same MMAs ran 6 %
+// slower in isolation: scripts/probes/utcimma_probe.cu.)  A database keeps its expanded copy resident next to the
 // compact one (9 x the bytes: 5.8 GB for the 20 M-row C3 database; the compact rows are still
 // what the mutual check gathers).
 //
@@ -61,7 +62,7 @@ constexpr int kTcPrefetch = PBK_TC_PREFETCH;      // tiles requested into L2 ahe
 constexpr int kTcRowBytes = 288;                  // one expanded descriptor: 256 sign bytes + 32 constant bytes
 constexpr int kTcChunks = kTcRowBytes / 16;       // 18 K chunks of 16 bytes
 constexpr int kTcKSteps = kTcRowBytes / 32;       // 9 UTCIMMA per item
-constexpr int kTcGroupBytes = 8 * kTcRowBytes;    // 2304: one group of 8 rows
+constexpr int kTcPlaneBytes = 128 * 16;           // 2048: one K chunk of the 128 rows of a tile
 constexpr int kTcTileBytes = kTcN * kTcRowBytes;  // 36 KB
 constexpr int kTcBlockBytes = kTcM * kTcRowBytes; // 36 KB
 constexpr int kTcSlots = 4;                       // accumulator slots of 128 columns
@@ -94,13 +95,13 @@ template <bool QUERY>
 __global__ void __launch_bounds__(256)
 hamming_tc_expand_kernel(const uint8_t* __restrict__ d, long long n, long long first_row, long long n_padded,
                          uint4* __restrict__ signs) {
-  // 16-byte piece index; rows [first_row, n_padded) are (re)written
+  // 16-byte piece index; rows [first_row, n_padded) are (re)written (first_row: a multiple of 512)
   const long long i = first_row * kTcChunks + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_padded * kTcChunks) return;
-  const long long g = i / (8 * kTcChunks);            // row group (144 pieces each)
-  const int in_g = (int)(i - g * (8 * kTcChunks));
-  const int kc = in_g >> 3, ri = in_g & 7;
-  const long long r = g * 8 + ri;
+  const long long tile = i / (kTcN * kTcChunks);      // 2304 pieces per tile: [K chunk][row of the tile]
+  const int in_t = (int)(i - tile * (kTcN * kTcChunks));
+  const int kc = in_t >> 7, rt = in_t & 127;
+  const long long r = tile * kTcN + rt;
   const bool real = r < n;
   uint4 o = make_uint4(0, 0, 0, 0);
   if (kc < 16) {
@@ -128,9 +129,9 @@ hamming_tc_expand_kernel(const uint8_t* __restrict__ d, long long n, long long f
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// shared-memory matrix descriptor: K-major, no swizzle, LBO = 128 B (K chunks), SBO = 2304 B (row groups)
+// shared-memory matrix descriptor: K-major, no swizzle, LBO = 2048 B (K chunks), SBO = 128 B (8-row groups)
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(kTcGroupBytes >> 4) << 32) |
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(kTcPlaneBytes >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
          (1ull << 46);                               // bits [46,48): descriptor version 1 (Blackwell)
 }
 // instruction descriptor, kind::i8: D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), both K-major,
@@ -313,8 +314,8 @@ hamming_tc_kernel(const __grid_constant__ HammingTcParams P) {
           const uint64_t ad = tc_smem_desc(a_addr + mb * kTcBlockBytes), bd = tc_smem_desc(b_addr + s * kTcTileBytes);
           if (!(P.dbg & 2)) {
 #pragma unroll
-            for (int k = 0; k < kTcKSteps; ++k)                 // K = 32 bytes per instruction: +256 B = +16 in the address field
-              tc_mma_i8(d, ad + (uint64_t)(k * 16), bd + (uint64_t)(k * 16), k > 0 ? 1u : 0u);
+            for (int k = 0; k < kTcKSteps; ++k)                 // K = 32 bytes per instruction = two planes: +4096 B = +256 in the address field
+              tc_mma_i8(d, ad + (uint64_t)(k * 256), bd + (uint64_t)(k * 256), k > 0 ? 1u : 0u);
           }
           tc_commit(&acc_full[slot]);
         }
@@ -396,6 +397,51 @@ hamming_tc_kernel(const __grid_constant__ HammingTcParams P) {
   }
 }
 
+// ------------------------------------------------------------------ int8 tensor peak probe
+// Measurement only: one CTA per SM issues `iters` x 8 UTCIMMA (M 128, N 128, K 32) on whatever its
+// shared memory holds - no data movement, no epilogue: the rate the tensor pipe sustains for the
+// matcher's instruction shape.  bench.py measures the roofline denominator with it in the same run.
+__global__ void __launch_bounds__(128, 1) hamming_tc_peak_kernel(int iters, uint32_t* sink) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 2 * kTcM * 256 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x01010101u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tptr)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = tptr;
+  if (warp == 0 && lane == 0) {
+    const uint32_t a = smem_u32(smem), b = a + kTcM * 256;
+    // 256-byte rows here (SBO 2048): the plain K-major layout
+    auto desc = [](uint32_t addr) -> uint64_t {
+      return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(2048 >> 4) << 32) | (1ull << 46);
+    };
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tc_mma_i8(tm + (uint32_t)((it & 3) * kTcN), desc(a + k * 256), desc(b + k * 256), k > 0 ? 1u : 0u);
+    }
+    tc_commit(&bar);
+    mbar_wait(&bar, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
+  }
+  if (threadIdx.x == 0 && sink != nullptr) sink[blockIdx.x] = tm;
+}
+
 static long long tc_pad(long long n) { return (n + kTcPad - 1) / kTcPad * kTcPad; }
 
 // grid: query groups x splits ~ one CTA per SM; every split a whole number of tiles
@@ -464,6 +510,22 @@ int pbk_hamming_tc_expand(const uint8_t* d, int64_t n, int64_t first_row, int8_t
   hamming_tc_expand_kernel<false><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(d, n, first_row, np,
                                                                                   reinterpret_cast<uint4*>(signs));
   PBK_CHECK_LAUNCH("hamming_tc_expand_kernel");
+  return PBK_OK;
+}
+
+int pbk_hamming_tc_peak_probe(int iters, uint32_t* sink, double* macs_per_launch, pbk_stream_t stream) {
+  using namespace pbk;
+  PBK_REQUIRE(iters > 0, PBK_EINVAL, "bad arguments");
+  const DeviceInfo* di;
+  int rc = current_device_info(&di);
+  if (rc) return rc;
+  constexpr int smem = 2 * kTcM * 256;
+  static KernelCache kc;
+  rc = kc.setup(di, hamming_tc_peak_kernel, 128, smem, nullptr);
+  if (rc) return rc;
+  hamming_tc_peak_kernel<<<di->sm_count, 128, smem, as_stream(stream)>>>(iters, sink);
+  PBK_CHECK_LAUNCH("hamming_tc_peak_kernel");
+  if (macs_per_launch) *macs_per_launch = (double)iters * 8.0 * kTcM * kTcN * 32.0 * di->sm_count;
   return PBK_OK;
 }
 

@@ -603,6 +603,15 @@ class PreparedMatcher(object):
         return self.idx[:n], self.dist[:n], fb[0, :n], fb[1, :n], fb[2, :n]
 
 
+def tc_peak_probe(iters=4000):
+    """Launches the int8 tensor-pipe probe; returns the multiply-adds of the launch."""
+    T = _ffi.require_cuda()
+    sink = T.zeros((1024,), dtype=T.int32, device="cuda")
+    n = ctypes.c_double(0)
+    _ffi.check(_ffi.lib().pbk_hamming_tc_peak_probe(int(iters), _ffi.ptr(sink), ctypes.byref(n), _ffi.stream_ptr()))
+    return n.value
+
+
 def popc_probe(mode=0, ctas=None, iters=2000):
     """Launches the popc-pipe probe; returns the POPC count of the launch."""
     T = _ffi.require_cuda()

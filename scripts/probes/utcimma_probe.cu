@@ -6,8 +6,8 @@
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint64_t desc(uint32_t a, uint32_t sbo) {
-  return (uint64_t)((a & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+__device__ __forceinline__ uint64_t desc(uint32_t a, uint32_t sbo, uint32_t lbo = 128) {
+  return (uint64_t)((a & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }
 template <int N, int MODE>      // MODE 0: back-to-back; 1: tcgen05.commit after every 8 MMAs; 2: + rotating over 4 A blocks / 2 B tiles, SBO 2304
 __global__ void __launch_bounds__(128, 1) probe(int iters, uint32_t* out) {
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(128, 1) probe(int iters, uint32_t* out) {
         const uint32_t acc = k > 0;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tm + (uint32_t)((it & 3) * (N > 128 ? 0 : N))),
-                     "l"(desc(a + k * 256, sbo)), "l"(desc(b + k * 256, sbo)), "r"(idesc), "r"(acc), "r"(z), "r"(z), "r"(z), "r"(z)
+                     "l"(MODE == 3 ? desc(a + k * 4096, 128, 2048) : desc(a + k * 256, sbo)), "l"(MODE == 3 ? desc(b + k * 4096, 128, 2048) : desc(b + k * 256, sbo)), "r"(idesc), "r"(acc), "r"(z), "r"(z), "r"(z), "r"(z)
                      : "memory");
       }
       if (MODE >= 1)
@@ -85,7 +85,7 @@ int main() {
   int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   uint32_t* out; cudaMalloc(&out, sms * 4);
   run<64>(sms, out); run<128>(sms, out); run<256>(sms, out);
-  run<128, 1>(sms, out); run<128, 2>(sms, out);
+  run<128, 1>(sms, out); run<128, 2>(sms, out); run<128, 3>(sms, out);
   cudaDeviceSynchronize();
   return 0;
 }
