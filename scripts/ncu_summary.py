@@ -30,6 +30,7 @@ FULL_METRICS = [
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu%"),
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"),
     ("launch__registers_per_thread", "regs"),
@@ -41,6 +42,7 @@ FULL_METRICS = [
 
 PROBLEMS = {
     "hamming_knn2_kernel": "2000 queries x 2.5M rows (one 8-GPU shard of C3)",
+    "hamming_tc_kernel": "2000 queries x 2.5M rows (one 8-GPU shard of C3), tcgen05 kind::i8",
     "project_points_kernel": "C2: 10M float32 points",
     "project_compact_kernel": "C2: 10M float32 points, bounds+depth masks, 73.7 % valid",
     "transform_points_kernel": "C2: 10M float32 points -> float64",

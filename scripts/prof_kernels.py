@@ -60,7 +60,9 @@ if which in ("hamming", "all"):
     q = torch.randint(0, 256, (2000, 32), device="cuda", dtype=torch.uint8, generator=g)
     db = torch.randint(0, 256, (nt, 32), device="cuda", dtype=torch.uint8, generator=g)
     timed("hamming", lambda: ops.hamming_knn2_keys(q, db, 0))
-    del db
+    signs = ops.hamming_tc_expand(db)
+    timed("hamming_tc", lambda: ops.hamming_knn2_keys_tc(q, signs, nt, 0))
+    del db, signs
 
 if which in ("project", "compact", "transform", "all"):
     n = 10_000_000
