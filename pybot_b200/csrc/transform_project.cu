@@ -142,6 +142,11 @@ template <> struct OutPix<float> {
   static __device__ __forceinline__ void store(float* uv, long long i, float u, float v) {
     st_stream_f2(uv + 2 * i, make_float2(u, v));
   }
+  // predicated (branch-free) store of one pixel at p
+  static __device__ __forceinline__ void store_if(unsigned pred, float* p, float u, float v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.global.cs.v2.f32 [%1], {%2,%3};\n\t}"
+                 ::"r"(pred), "l"(p), "f"(u), "f"(v) : "memory");
+  }
 };
 template <> struct OutPix<double> {
   using vec = double2;
@@ -154,7 +159,15 @@ template <> struct OutPix<double> {
     double2 o = make_double2(u, v);
     asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(uv + 2 * i), "d"(o.x), "d"(o.y) : "memory");
   }
+  static __device__ __forceinline__ void store_if(unsigned pred, double* p, double u, double v) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.global.cs.v2.f64 [%1], {%2,%3};\n\t}"
+                 ::"r"(pred), "l"(p), "d"(u), "d"(v) : "memory");
+  }
 };
+__device__ __forceinline__ void st_stream_d1_if(unsigned pred, double* p, double v) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q st.global.cs.f64 [%1], %2;\n\t}"
+               ::"r"(pred), "l"(p), "d"(v) : "memory");
+}
 
 // status word of the decoupled look-back: [63:62] state, [61:0] value
 constexpr unsigned long long kStateAgg = 1ull << 62;
@@ -314,6 +327,22 @@ project_points_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
 // Phase clocks of the compaction kernel (diagnostic; compiled in with -DPBK_COMPACT_TIMING)
 #ifdef PBK_COMPACT_TIMING
 __device__ unsigned long long g_ct_clk[16];
+#endif
+#ifdef PBK_EA_TIMELINE
+__device__ unsigned long long g_ea_ts[64][8];
+__device__ unsigned long long g_ea_cta[4][512];      // per CTA: publish time of generations 20 / 21, offset-seen time of 20, SM id
+__device__ __forceinline__ unsigned long long ea_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define EA_TS(gen, col) do { if ((gen) < 64) g_ea_ts[(gen)][(col)] = ea_now(); } while (0)
+#define EA_TS_MAX(gen, col) do { if ((gen) < 64) atomicMax(&g_ea_ts[(gen)][(col)], ea_now()); } while (0)
+#else
+#define EA_TS(gen, col) do {} while (0)
+#define EA_TS_MAX(gen, col) do {} while (0)
+#endif
+#ifdef PBK_COMPACT_TIMING
 #define CT_T0() long long _t0 = clock64()
 #define CT_ACC(slot)                                                        \
   do {                                                                      \
@@ -976,6 +1005,309 @@ project_compacted_kernel(long long n, T* __restrict__ uv, double* __restrict__ d
   }
 }
 
+// ============================== compaction, single pass, aggregates published EARLY
+// The look-back kernel above can publish a tile's count only after the tile's fp64 projection,
+// so the prefix chain and the arithmetic are in series and the outputs have to be parked.
+// Here the count comes from the fp32 classifier (exact by construction, see classify_point),
+// a few hundred clocks after the tile's points land and kEaAhead TILES AHEAD of the projection:
+//
+//   compute warp (8 per CTA, 128 points of the CTA's 1024-point tile each), iteration i:
+//     classify tile i + kEaAhead -> valid flags out, count to shared memory; the last of the
+//       eight warps to get there publishes the tile's aggregate                      (early)
+//     project tile i in fp64 (results stay in registers)
+//     read the tile's output offset (one word, normally long there), scatter
+//   chain warp (one: the last CTA of the grid holds nothing else): tile = i G + b, so all CTAs
+//     work on generation i together; the chain warp collects the G aggregates of a generation as they appear, scans them and
+//     writes every tile's exclusive offset.  It is the only place where generations are chained.
+//
+// The chain of generation i + kEaAhead therefore runs while generation i is being projected;
+// nothing is parked, no CTA-wide barrier is executed after the prologue.
+constexpr int kEaThreads = kWarps * 32;
+constexpr int kEaSlots = 16;                // per-tile bookkeeping in shared memory (see the static_assert)
+#ifndef PBK_EA_AHEAD
+#define PBK_EA_AHEAD 2
+#endif
+constexpr int kEaAheadMax = PBK_EA_AHEAD;
+#ifndef PBK_EA_MINB
+#define PBK_EA_MINB 2
+#endif
+#ifndef PBK_EA_BATCH
+#define PBK_EA_BATCH 4
+#endif
+// a warp in iteration k (writing the counts of tile k + kEaAhead) has seen the offset of tile k-1,
+// so every warp of the CTA has classified tile k-1 and may still be reading the counts of tile
+// k-1-kEaAhead: the slots of tiles k-1-kEaAhead .. k+kEaAhead must be distinct
+static_assert(kEaAheadMax >= 1 && 2 * kEaAheadMax + 2 <= kEaSlots, "bookkeeping slots");
+
+template <typename T> struct EarlyCfg {
+  // float64 tiles are twice as large: two tiles ahead keep two CTAs per SM
+  static constexpr int kAhead = sizeof(T) == 4 ? kEaAheadMax : (kEaAheadMax < 2 ? kEaAheadMax : 2);
+  static constexpr int kStages = kAhead + (sizeof(T) == 4 ? 3 : 2);       // input tiles per warp
+  static constexpr int kRing = kWarps * kStages * CpTile<T>::kBytes;
+  static constexpr int kBytes = kRing + kWarps * kStages * 8 + kEaSlots * 8 + kEaSlots * kWarps * 4;
+};
+constexpr int kEaPer = 14;                  // tiles of a generation per chain lane: G <= 448
+constexpr int kEaCarrySlots = 16;
+
+// arrive on an mbarrier (release, CTA scope); true for the arrival that completes the phase
+__device__ __forceinline__ bool mbar_arrive_is_last(uint64_t* bar) {
+  uint64_t state;
+  uint32_t pending;
+  asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(smem_u32(bar)) : "memory");
+  asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(pending) : "l"(state));
+  return pending == 1u;
+}
+
+template <typename T, bool DIST>
+__global__ void __launch_bounds__(kEaThreads, PBK_EA_MINB)
+project_compact_early_kernel(const T* __restrict__ X, long long n, T* __restrict__ uv,
+                             double* __restrict__ depth, uint8_t* __restrict__ valid_out,
+                             long long* __restrict__ count, unsigned long long* __restrict__ status,
+                             const __grid_constant__ pbk_project_params P,
+                             const __grid_constant__ ClassifyParams C) {
+  constexpr int NST = EarlyCfg<T>::kStages;
+  constexpr int kEaAhead = EarlyCfg<T>::kAhead;
+  constexpr int kInBytes = CpTile<T>::kBytes;
+  extern __shared__ __align__(128) char dyn_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t* ring_bars = reinterpret_cast<uint64_t*>(dyn_smem + EarlyCfg<T>::kRing);
+  uint64_t* arr = ring_bars + kWarps * NST;                         // [slot] 8 arrivals: the counts are in
+  int* cnt_w = reinterpret_cast<int*>(arr + kEaSlots);              // [slot][warp] valid points
+
+  const long long ncta = (n + kCtaPts - 1) / kCtaPts;
+  const int G = (int)gridDim.x - 1, b = (int)blockIdx.x; // G compute CTAs + the chain CTA
+  const int mine = b < G ? (int)((ncta - b + G - 1) / G) : 0;       // tiles of this CTA (G <= ncta)
+  unsigned long long* const aggw = status;               // [ncta] tile aggregates
+  unsigned long long* const prefw = status + ncta;       // [ncta] tile offsets
+
+  if (b == G) {
+    // ------------------------------------------------------------ chain CTA
+    // Warp w scans the generations w, w + 8, ... (G consecutive tiles each, kEaPer or fewer per
+    // lane): the loads, the wait for late aggregates and the scan inside a generation overlap
+    // between the warps; only the carry is handed from generation to generation, through one
+    // shared-memory word [seq : 24 | carry : 40].
+    volatile unsigned long long* carry_s = reinterpret_cast<volatile unsigned long long*>(dyn_smem);
+    if (threadIdx.x < kEaCarrySlots) carry_s[threadIdx.x] = 0ull;
+    __syncthreads();
+    const long long ngen = (ncta + G - 1) / G;
+    const int per = (G + 31) / 32;                          // <= kEaPer (launch_compact_early)
+    CT_T0();
+    for (long long k = warp; k < ngen; k += kWarps) {
+      const long long t0 = k * G;
+      const int Gi = (ncta - t0) < G ? (int)(ncta - t0) : G;
+      unsigned long long sw[kEaPer];
+#pragma unroll
+      for (int j = 0; j < kEaPer; ++j) {                    // lane owns `per` consecutive tiles
+        const int idx = lane * per + j;
+        sw[j] = (j < per && idx < Gi) ? ld_status(aggw + t0 + idx) : kStateAgg;
+      }
+      // poll every missing word of the lane together (one L2 round trip per round, not per word);
+      // politely while the generation before this one is still open
+      for (;;) {
+        bool all = true;
+#pragma unroll
+        for (int j = 0; j < kEaPer; ++j) all = all && ((sw[j] >> 62) != 0);
+        if (__all_sync(0xffffffffu, all)) break;
+        const bool critical = k == 0 || ((carry_s[k % kEaCarrySlots] >> 40) == (unsigned long long)(k & 0xffffff));
+        if (!critical) __nanosleep(200);
+#pragma unroll
+        for (int j = 0; j < kEaPer; ++j)
+          if ((sw[j] >> 62) == 0) sw[j] = ld_status(aggw + t0 + lane * per + j);
+      }
+      if (lane == 0) EA_TS(k, 1);
+      long long mine_sum = 0;
+#pragma unroll
+      for (int j = 0; j < kEaPer; ++j) mine_sum += (long long)(sw[j] & kValueMask);
+      long long incl = mine_sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      CT_ACC(8);
+      unsigned long long cw = 0;
+      if (lane == 31) {
+        if (k > 0) {
+          do { cw = carry_s[k % kEaCarrySlots]; } while ((cw >> 40) != (unsigned long long)(k & 0xffffff));
+          cw &= (1ull << 40) - 1;
+        }
+        carry_s[(k + 1) % kEaCarrySlots] = ((unsigned long long)((k + 1) & 0xffffff) << 40) | (cw + (unsigned long long)incl);
+        if (k == ngen - 1) *count = (long long)cw + incl;
+      }
+      const long long carry = (long long)__shfl_sync(0xffffffffu, cw, 31);
+      CT_ACC(9);
+      long long run = carry + incl - mine_sum;
+#pragma unroll
+      for (int j = 0; j < kEaPer; ++j) {
+        const int idx = lane * per + j;
+        if (j < per && idx < Gi) st_status(prefw + t0 + idx, kStatePrefix | (unsigned long long)run);
+        run += (long long)(sw[j] & kValueMask);
+      }
+      if (lane == 0) EA_TS(k, 2);
+      CT_ACC(10);
+    }
+    return;
+  }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kEaSlots; ++s) mbar_init(&arr[s], kWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  WarpRing<kInBytes, NST> ring;
+  ring.init(dyn_smem + warp * NST * kInBytes, ring_bars + warp * NST, lane);
+  __syncthreads();
+
+  // ---------------------------------------------------------------- compute warps
+  const char* Xb = reinterpret_cast<const char*>(X);
+  const unsigned lt = (1u << lane) - 1u;
+  const bool valid_words = (reinterpret_cast<uintptr_t>(valid_out) & 3) == 0;
+  CT_T0();
+  auto first_of = [&](int i) -> long long { return ((long long)i * G + b) * kCtaPts + warp * kTilePts; };
+  auto issue = [&](int i) {                                // lane 0
+    const long long first = first_of(i);
+    if (first + kTilePts <= n) ring.issue(i, Xb + first * 3 * sizeof(T));
+  };
+  // tile i of this warp: validity ballots of its four 32-point rows, flags out, count handed over
+  auto classify = [&](int i, unsigned (&m)[4]) {
+    const long long first = first_of(i);
+    const long long rem = n - first;
+    const int npts = rem >= kTilePts ? kTilePts : (rem > 0 ? (int)rem : 0);
+    char* const st = ring.slot(i);
+    if (npts == kTilePts) ring.wait(i);
+    else {                                                 // only ever the last tile of the array
+      warp_load_ragged(Xb + first * 3 * sizeof(T), st, lane, kInBytes, npts * 3 * (int)sizeof(T));
+      __syncwarp();
+    }
+    CT_ACC(15);
+    const T* pts = reinterpret_cast<const T*>(st) + 3 * lane;
+    bool undecided = DIST;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bool in = false, decided = false;
+      if (!DIST) classify_point(C, (float)pts[96 * j], (float)pts[96 * j + 1], (float)pts[96 * j + 2], in, decided);
+      m[j] = __ballot_sync(0xffffffffu, in);
+      undecided = undecided || !decided;
+    }
+    if (__any_sync(0xffffffffu, undecided)) {
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) m[j] = __ballot_sync(0xffffffffu, resolve_point<T, DIST>(P, C, pts + 96 * j));
+    }
+    if (npts != kTilePts) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int live = npts - j * 32;
+        m[j] &= live >= 32 ? 0xffffffffu : (live <= 0 ? 0u : ((1u << live) - 1u));
+      }
+    }
+    {
+      // lane 0 hands the count over; everything after it is warp-uniform again (a wait loop
+      // inside a lane-0-only branch leaves the warp split for the rest of the iteration)
+      const int slot = i & (kEaSlots - 1);
+      bool last = false;
+      if (lane == 0) {
+        cnt_w[slot * kWarps + warp] = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+        last = mbar_arrive_is_last(&arr[slot]);
+      }
+      if (__shfl_sync(0xffffffffu, (int)last, 0)) {        // the tile's eight counts are in
+        mbar_wait(&arr[slot], (uint32_t)((i / kEaSlots) & 1));      // (acquire; the phase is complete)
+        int agg = lane < kWarps ? cnt_w[slot * kWarps + lane] : 0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) agg += __shfl_xor_sync(0xffffffffu, agg, o);
+        if (lane == 0) {
+          st_status(aggw + (long long)i * G + b, kStateAgg | (unsigned long long)agg);
+          EA_TS_MAX(i, 5);
+          if (b == 0) EA_TS(i, 0);
+        }
+      }
+    }
+    if (valid_out != nullptr) {
+      if (npts == kTilePts && valid_words) {
+        store_valid_rows(valid_out + first, m, 32, lane);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j * 32 + lane < npts) valid_out[first + j * 32 + lane] = (uint8_t)((m[j] >> lane) & 1u);
+      }
+    }
+  };
+
+  if (lane == 0)
+    for (int d = 0; d < NST - 1 && d < mine; ++d) issue(d);
+  unsigned mq[kEaAhead + 1][4];                            // ballots of tiles i .. i + kEaAhead
+#pragma unroll
+  for (int a = 0; a <= kEaAhead; ++a)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mq[a][j] = 0u;
+#pragma unroll
+  for (int a = 0; a < kEaAhead; ++a)
+    if (a < mine) classify(a, mq[a]);
+  for (int i = 0; i < mine; ++i) {
+    if (lane == 0 && i + NST - 1 < mine) issue(i + NST - 1);     // into the slot of tile i-1
+    if (i + kEaAhead < mine) classify(i + kEaAhead, mq[kEaAhead]);
+    CT_ACC(11);
+    const unsigned (&mv)[4] = mq[0];
+    const char* st = ring.slot(i);
+    const bool any = (mv[0] | mv[1] | mv[2] | mv[3]) != 0u;
+    T uo[4] = {}, vo[4] = {};
+    double dep[4] = {};
+    if (any) {
+      // PBK_EA_BATCH points side by side: 4 interleaves four fp64 chains (fewest stalls per warp),
+      // 2 halves the live registers (three CTAs per SM instead of two)
+#pragma unroll
+      for (int j0 = 0; j0 < 4; j0 += PBK_EA_BATCH) {
+        double Xp[PBK_EA_BATCH][3], ud[PBK_EA_BATCH], vd[PBK_EA_BATCH];
+#pragma unroll
+        for (int j = 0; j < PBK_EA_BATCH; ++j) stage_read_point<T>(st, (j0 + j) * 32 + lane, Xp[j]);
+        project_many<DIST, PBK_EA_BATCH>(P, Xp, ud, vd);
+#pragma unroll
+        for (int j = 0; j < PBK_EA_BATCH; ++j) {
+          uo[j0 + j] = (T)ud[j];
+          vo[j0 + j] = (T)vd[j];
+          if (depth != nullptr) dep[j0 + j] = depth_of(P, Xp[j]);
+        }
+      }
+    }
+    __syncwarp();                                          // slot may be refilled from here on
+    CT_ACC(12);
+    // the tile's offset: published by the chain warp once every aggregate of the generation was
+    // in; the counts of the warps before this one are in shared memory since the aggregate
+    const int slot = i & (kEaSlots - 1);
+    unsigned long long w;
+    {
+      if (lane == 0 && b == 0 && warp == 0) EA_TS(i, 4);
+      const unsigned long long* pw = prefw + (long long)i * G + b;
+      do { w = ld_status(pw); } while ((w >> 62) == 0);   // every lane, one address: the warp stays whole
+      if (lane == 0 && b == 0 && warp == 0) EA_TS(i, 3);
+      if (lane == 0 && warp == 0) EA_TS_MAX(i, 6);
+    }
+    mbar_wait(&arr[slot], (uint32_t)((i / kEaSlots) & 1));          // (acquire; completed long ago)
+    int bsum = (lane < warp) ? cnt_w[slot * kWarps + lane] : 0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+    const long long o0 = (long long)(w & kValueMask) + __shfl_sync(0xffffffffu, bsum, 0);
+    CT_ACC(13);
+    if (any) {
+      T* const uvb = uv + 2 * o0;
+      double* const db = depth + o0;                       // (never dereferenced when depth is null)
+      const bool has_depth = depth != nullptr;
+      int run = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned bit = (mv[j] >> lane) & 1u;
+        const int r = run + __popc(mv[j] & lt);
+        OutPix<T>::store_if(bit, uvb + 2 * r, uo[j], vo[j]);
+        st_stream_d1_if(bit && has_depth, db + r, dep[j]);
+        run += __popc(mv[j]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < kEaAhead; ++a)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mq[a][j] = mq[a + 1][j];
+    CT_ACC(14);
+  }
+}
+
 template <typename TI, typename TO>
 static int launch_transform(const void* X, int64_t n, const XformParams& P, void* Y,
                             cudaStream_t s, const DeviceInfo* di) {
@@ -1090,18 +1422,53 @@ static long long compact_chunk_points(long long n, size_t elem) {
   return (per + kTilePts - 1) / kTilePts * kTilePts;                      // ... of whole tiles
 }
 
-// which compaction: 1 = single pass with look-back (default: 93 us on C2), 2 = classify + dense
-// projection kernels (104 us so far).  PBK_COMPACT_IMPL overrides.
+// which compaction: 1 = single pass with look-back (93 us on C2), 2 = classify + dense
+// projection kernels (104 us), 3 = single pass with early aggregates.
+// PBK_COMPACT_IMPL overrides.
+#ifndef PBK_COMPACT_DEFAULT
+#define PBK_COMPACT_DEFAULT 1
+#endif
 static int compact_impl() {
   const char* e = getenv("PBK_COMPACT_IMPL");           // read per call: tests switch it
-  return (e && e[0] == '2') ? 2 : 1;
+  if (e && e[0] >= '1' && e[0] <= '3') return e[0] - '0';
+  return PBK_COMPACT_DEFAULT;
+}
+
+template <typename T, bool DIST>
+static int launch_compact_early(const void* X, int64_t n, const pbk_project_params& P, void* uv,
+                                double* depth, uint8_t* valid, int64_t* count, void* scratch, cudaStream_t s,
+                                const DeviceInfo* di) {
+  constexpr int smem = EarlyCfg<T>::kBytes;
+  auto kern = project_compact_early_kernel<T, DIST>;
+  static KernelCache kc;
+  int per_sm;
+  int rc = kc.setup(di, kern, kEaThreads, smem, &per_sm);
+  if (rc) return rc;
+  const long long ncta = (n + kCtaPts - 1) / kCtaPts;
+  int grid = resident_grid(di, per_sm, ncta + 1);                // compute CTAs + the chain CTA
+  if (grid > 32 * kEaPer + 1) grid = 32 * kEaPer + 1;
+  PBK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)(2 * ncta + 2) * 8, s));          // aggregate + offset words
+  ClassifyParams C;
+  classify_params(P, &C);
+  const T* Xp = static_cast<const T*>(X);
+  long long nn = n;
+  T* uvp = static_cast<T*>(uv);
+  long long* cnt = reinterpret_cast<long long*>(count);
+  unsigned long long* scr = static_cast<unsigned long long*>(scratch);
+  pbk_project_params Pc = P;
+  void* args[] = {&Xp, &nn, &uvp, &depth, &valid, &cnt, &scr, &Pc, &C};
+  PBK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(grid), dim3(kEaThreads), args,
+                                       smem, s));
+  return PBK_OK;
 }
 
 template <typename T, bool DIST>
 static int launch_compact(const void* X, int64_t n, const pbk_project_params& P, void* uv,
                           double* depth, uint8_t* valid, int64_t* count, void* scratch, cudaStream_t s,
                           const DeviceInfo* di) {
-  if (compact_impl() == 1) return launch_compact_lookback<T, DIST>(X, n, P, uv, depth, valid, count, scratch, s, di);
+  const int impl = compact_impl();
+  if (impl == 1) return launch_compact_lookback<T, DIST>(X, n, P, uv, depth, valid, count, scratch, s, di);
+  if (impl == 3) return launch_compact_early<T, DIST>(X, n, P, uv, depth, valid, count, scratch, s, di);
   constexpr int NST = RingCfg<T>::kStages;
   constexpr int smem_a = kCpWarps * (kCpRing + 1) * CpTile<T>::kBytes + kCpWarps * kCpRing * 8;
   constexpr int smem_b = kWarps * NST * CpTile<T>::kBytes + kWarps * NST * 8;
@@ -1169,6 +1536,21 @@ int pbk_transform_points(const void* X, int in_dtype, int64_t n, const double* R
 }
 
 #ifdef PBK_COMPACT_TIMING
+#endif
+#ifdef PBK_EA_TIMELINE
+PBK_API int pbk_debug_compact_cta(unsigned long long out[2048]) {
+  return cudaMemcpyFromSymbol(out, pbk::g_ea_cta, sizeof(unsigned long long) * 2048) == cudaSuccess ? 0 : -2;
+}
+PBK_API int pbk_debug_compact_ts(unsigned long long out[512], int reset) {
+  if (cudaMemcpyFromSymbol(out, pbk::g_ea_ts, sizeof(unsigned long long) * 512) != cudaSuccess) return -2;
+  if (reset) {
+    static unsigned long long z[512] = {0};
+    if (cudaMemcpyToSymbol(pbk::g_ea_ts, z, sizeof(z)) != cudaSuccess) return -2;
+  }
+  return 0;
+}
+#endif
+#ifdef PBK_COMPACT_TIMING
 PBK_API int pbk_debug_compact_clocks(unsigned long long out[16], int reset) {
   if (cudaMemcpyFromSymbol(out, pbk::g_ct_clk, sizeof(unsigned long long) * 16) != cudaSuccess) return -2;
   if (reset) {
@@ -1188,7 +1570,7 @@ size_t pbk_project_scratch_bytes(int64_t n, int in_dtype) {
   const size_t two = pbk::cp_off_xprime(tiles) + (size_t)tiles * pbk::kTilePts * 3 * elem;
   // single-pass form: tile status words + one prefix word per generation
   const size_t one = (size_t)(2 * ((n + pbk::kCtaPts - 1) / pbk::kCtaPts) + 4) * 8;
-  return pbk::compact_impl() == 1 ? one : (two > one ? two : one);
+  return pbk::compact_impl() != 2 ? one : (two > one ? two : one);
 }
 
 int pbk_project_points(const void* X, int in_dtype, int64_t n, const pbk_project_params* params,

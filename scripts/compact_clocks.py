@@ -33,6 +33,14 @@ ntiles = (n + 1023) // 1024
 names = ["-", "-", "scan:cnt_ready wait", "scan:scan+lookback",
          "cmp:in_full wait", "cmp:read+compute", "cmp:base_ready wait", "cmp:scatter"]
 print("%.3f ms/iter, %d tiles" % (ms, ntiles))
+if os.environ.get("PBK_COMPACT_IMPL") == "3":
+    # per 1024-point tile: resolver phases once, compute-warp phases summed over the 8 warps
+    for i, nm in ((8, "chain:load+scan /gen"), (9, "chain:carry wait /gen"), (10, "chain:store /gen"),
+                  (15, "cmp:input wait (x8)"), (11, "cmp:classify (x8)"), (12, "cmp:read+project (x8)"),
+                  (13, "cmp:offset wait (x8)"), (14, "cmp:scatter (x8)")):
+        per = (ntiles + 294) // 295 if i <= 10 else ntiles
+        print("  %-26s %8.0f clk" % (nm, out[i] / reps / per))
+    sys.exit(0)
 for i, nm in enumerate(names):
     print("  %-22s %8.0f clk/tile" % (nm, out[i] / reps / ntiles))
 

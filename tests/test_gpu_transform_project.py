@@ -10,11 +10,12 @@ pytestmark = pytest.mark.gpu
 POSES = ("c2", "ident", "big")
 
 
-@pytest.fixture(params=["lookback", "two_kernel"])
+@pytest.fixture(params=["lookback", "two_kernel", "early"])
 def compact_impl(request, monkeypatch):
-    """Both compaction implementations behind Camera.project(check_*): the single-pass look-back
-    kernel (default) and the classify + dense-projection pair (PBK_COMPACT_IMPL=2)."""
-    monkeypatch.setenv("PBK_COMPACT_IMPL", "2" if request.param == "two_kernel" else "1")
+    """Every compaction implementation behind Camera.project(check_*): the single-pass look-back
+    kernel, the classify + dense-projection pair (PBK_COMPACT_IMPL=2) and the single pass with
+    early aggregates (PBK_COMPACT_IMPL=3)."""
+    monkeypatch.setenv("PBK_COMPACT_IMPL", {"lookback": "1", "two_kernel": "2", "early": "3"}[request.param])
     return request.param
 
 
