@@ -822,7 +822,7 @@ def run_c4(D, args, weak=False):
         "variants": variants,
         "limiter": {"hbm_ms_at_measured_peak": hbm_ms, "step_ms": step_ms, "fixed_ms": step_ms - hbm_ms,
                     "note": ("step = HBM time of this rank's %d observations x 96 B + launch / ramp / tail / last-CTA cost "
-                             "reduction%s" % (local_obs, " + one NVLink release/acquire round trip and the wait for "
+                             "reduction%s" % (local_obs, " + one NVLink crossing (self-validating words, no fence) and the wait for "
                                               "the slowest rank" if D.world > 1 else ""))},
         "roofline": {"bound": "hbm", "kernel": "ba_residual_jacobian_kernel<2,2> (behind ba_camera_precompute_kernel, "
                                                "whose ~3 us overlap its prologue)", "achieved": gbps,

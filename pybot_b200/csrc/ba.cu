@@ -473,7 +473,9 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
   // blocks are complete and visible after this.  A no-op for an ordinary launch.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int k = 0; k < my_tiles; ++k) process(k);
-  if (lane == 0) tma_store_wait_all();
+  // the stage must outlive the bulk stores that read it; their completion in global memory is
+  // the kernel boundary's business, so the cost chain below does not wait for it
+  if (lane == 0) tma_store_wait_read();
 
   // cost: warp -> CTA -> partial
 #pragma unroll
@@ -501,35 +503,41 @@ ba_residual_jacobian_kernel(const __grid_constant__ BaParams P) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (P.world > 1) {
-      // Fused sum-all-reduce over NVLink peer memory: lane p stores this rank's cost and
-      // then the call's sequence number into rank p's exchange buffer; lane q then waits
-      // for rank q's sequence number in the LOCAL buffer and reads its cost.  All ranks add
-      // the world values in rank order, so the result is bit-identical everywhere.  Slots
-      // alternate with the call parity: a rank can only reuse a slot after every peer has
-      // finished the call in between, i.e. has read the previous value.
-      // the call sequence is either the caller's (identical on all ranks) or the device-resident
-      // counter behind the arrival word, which lets a captured CUDA graph replay the call
+      // Fused sum-all-reduce over NVLink peer memory.  Lane p stores this rank's cost into rank
+      // p's exchange buffer as TWO SELF-VALIDATING words, [tag : 32 | half of the double : 32]
+      // with tag = the call's sequence number, in one 16-byte store; lane q then polls rank q's
+      // pair in the LOCAL buffer until both tags are this call's.  No fence and no separate flag:
+      // one NVLink crossing per call instead of a store, a system fence (a round trip) and a
+      // release store.  All ranks add the world values in rank order, so the result is
+      // bit-identical everywhere.  Slots alternate with the call parity: a rank can only reuse
+      // a slot after every peer has finished the call in between, i.e. has read the previous pair.
+      // The call sequence is either the caller's (identical on all ranks) or the device-resident
+      // counter behind the arrival word, which lets a captured CUDA graph replay the call.
       unsigned long long* dev_seq = arrived + 1;
       const unsigned long long seq = P.seq != 0 ? P.seq : (*dev_seq + 1ull);
       __syncwarp();
       if (lane == 0 && P.seq == 0) *dev_seq = seq;
       const int par = (int)(seq & 1ull);
+      const unsigned long long tag = (seq & 0xffffffffull) << 32;
       if (lane < P.world) {
         unsigned long long* slot = P.peers[lane] + (size_t)(par * P.world + P.rank) * 2;
-        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot), "l"((unsigned long long)__double_as_longlong(s)) : "memory");
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot + 1), "l"(seq) : "memory");
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(s);
+        asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(tag | (bits & 0xffffffffull)),
+                     "l"(tag | (bits >> 32)) : "memory");
       }
       double v = 0.0;
       if (lane < P.world) {
         const unsigned long long* mine = P.peers[P.rank] + (size_t)(par * P.world + lane) * 2;
-        unsigned long long got = 0, bits = 0x7ff8000000000000ull;          // NaN if a peer never arrives
+        unsigned long long w0 = 0, w1 = 0;
         const long long t0 = clock64();
+        bool ok;
         do {
-          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(mine + 1) : "memory");
-        } while (got != seq && clock64() - t0 < P.timeout_clk);              // bounded instead of a hang
-        if (got == seq) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(bits) : "l"(mine) : "memory");
-        else raise_status(P.status, kStatusPeerTimeout);                     // the cost is NaN and the host raises
+          asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(mine) : "memory");
+          ok = ((w0 ^ tag) >> 32) == 0 && ((w1 ^ tag) >> 32) == 0;
+        } while (!ok && clock64() - t0 < P.timeout_clk);                    // bounded instead of a hang
+        unsigned long long bits = 0x7ff8000000000000ull;                    // NaN if a peer never arrives
+        if (ok) bits = (w0 & 0xffffffffull) | (w1 << 32);
+        else raise_status(P.status, kStatusPeerTimeout);                    // the cost is NaN and the host raises
         v = __longlong_as_double((long long)bits);
       }
       s = 0.0;
