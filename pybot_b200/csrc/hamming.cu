@@ -332,23 +332,57 @@ hamming_knn2_kernel(const __grid_constant__ HammingParams P) {
   }
 }
 
+// Top-2 (unsigned min) of the `parts` partial key pairs of query i, by the kMergeLanes
+// consecutive lanes that share the query: lane `sub` takes the parts sub, sub + 8, ... (its
+// loads are independent and in flight together), then three shuffle steps combine the lanes.
+// A tensor-core scan leaves 74 partial pairs per query; one thread walking them one dependent
+// 16-byte load after the other took 22 us for 2000 queries.  Every lane of the warp must call it
+// (i >= nq: no loads); the result is valid in all kMergeLanes lanes of the query.
+constexpr int kMergeLanes = 8;
+__device__ __forceinline__ void top2_insert(unsigned long long& b1, unsigned long long& b2, unsigned long long v) {
+  const unsigned long long mx = max(b1, v);
+  b1 = min(b1, v);
+  b2 = min(b2, mx);
+}
+__device__ __forceinline__ void merge_parts(const unsigned long long* __restrict__ partial, int parts, long long nq,
+                                            long long i, int sub, unsigned long long& b1, unsigned long long& b2) {
+  b1 = PBK_KEY_NONE;
+  b2 = PBK_KEY_NONE;
+  if (i < nq) {
+    for (int p0 = sub; p0 < parts; p0 += 4 * kMergeLanes) {
+      ulonglong2 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int p = p0 + k * kMergeLanes;
+        v[k] = p < parts ? *reinterpret_cast<const ulonglong2*>(partial + ((long long)p * nq + i) * 2)
+                         : make_ulonglong2(PBK_KEY_NONE, PBK_KEY_NONE);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        top2_insert(b1, b2, v[k].x);
+        top2_insert(b1, b2, v[k].y);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < kMergeLanes; o <<= 1) {
+    const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, b1, o), o2 = __shfl_xor_sync(0xffffffffu, b2, o);
+    top2_insert(b1, b2, o1);
+    top2_insert(b1, b2, o2);
+  }
+}
+static inline unsigned merge_blocks(long long nq) { return (unsigned)((nq * kMergeLanes + 255) / 256); }
+
 // partial (parts, nq, 2) -> keys (nq, 2): global top-2 by unsigned min.
 __global__ void __launch_bounds__(256)
 hamming_merge_kernel(const unsigned long long* __restrict__ partial, int parts, long long nq,
                      unsigned long long* __restrict__ keys) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nq) return;
-  unsigned long long b1 = PBK_KEY_NONE, b2 = PBK_KEY_NONE;
-  for (int p = 0; p < parts; ++p) {
-    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(partial + ((long long)p * nq + i) * 2);
-    unsigned long long mx = max(b1, v.x);
-    b1 = min(b1, v.x);
-    b2 = min(b2, mx);
-    mx = max(b1, v.y);
-    b1 = min(b1, v.y);
-    b2 = min(b2, mx);
-  }
-  *reinterpret_cast<ulonglong2*>(keys + i * 2) = make_ulonglong2(b1, b2);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = t / kMergeLanes;
+  const int sub = (int)(t % kMergeLanes);
+  unsigned long long b1, b2;
+  merge_parts(partial, parts, nq, i, sub, b1, b2);
+  if (i < nq && sub == 0) *reinterpret_cast<ulonglong2*>(keys + i * 2) = make_ulonglong2(b1, b2);
 }
 
 __global__ void __launch_bounds__(256)
@@ -475,20 +509,15 @@ __device__ __forceinline__ bool hx_wait(const HammingPeers& X, int phase) {
 __global__ void __launch_bounds__(256)
 hamming_merge_push_kernel(const unsigned long long* __restrict__ partial, int parts,
                           const __grid_constant__ HammingPeers X, unsigned int* done_counter) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = t / kMergeLanes;
+  const int sub = (int)(t % kMergeLanes);
+  unsigned long long b1, b2;
+  merge_parts(partial, parts, X.nq, i, sub, b1, b2);
   if (i < X.nq) {
-    unsigned long long b1 = PBK_KEY_NONE, b2 = PBK_KEY_NONE;
-    for (int p = 0; p < parts; ++p) {
-      const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(partial + ((long long)p * X.nq + i) * 2);
-      unsigned long long mx = max(b1, v.x);
-      b1 = min(b1, v.x);
-      b2 = min(b2, mx);
-      mx = max(b1, v.y);
-      b1 = min(b1, v.y);
-      b2 = min(b2, mx);
-    }
+    // the query's lanes share the pushes: lane `sub` serves the peers sub, sub + 8, ...
     const size_t off = hx_keys(X, (int)(X.seq & 1ull), X.rank) + (size_t)i * 2;
-    for (int p = 0; p < X.world; ++p) {
+    for (int p = sub; p < X.world; p += kMergeLanes) {
       st_sys_u64(X.buf[p] + off, b1);
       st_sys_u64(X.buf[p] + off + 1, b2);
     }
@@ -718,7 +747,7 @@ int pbk_hamming_knn2(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt,
   P.nq = nq; P.nt = nt; P.rows_per_split = rps; P.train_base = train_base; P.splits = splits;
   rc = launch_knn2(P, rq, di, s);
   if (rc) return rc;
-  hamming_merge_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(P.partial, splits, nq,
+  hamming_merge_kernel<<<merge_blocks(nq), 256, 0, s>>>(P.partial, splits, nq,
                                                                     reinterpret_cast<unsigned long long*>(keys));
   PBK_CHECK_LAUNCH("hamming_merge_kernel");
   return PBK_OK;
@@ -731,7 +760,7 @@ int pbk_hamming_merge_top2(const uint64_t* partial, int parts, int64_t nq, uint6
   if (nq == 0) return PBK_OK;
   PBK_REQUIRE(partial != nullptr && keys != nullptr, PBK_EINVAL, "NULL device pointer");
   PBK_REQUIRE(aligned16(partial) && aligned16(keys), PBK_EALIGN, "device pointers must be 16-byte aligned");
-  hamming_merge_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, as_stream(stream)>>>(
+  hamming_merge_kernel<<<merge_blocks(nq), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const unsigned long long*>(partial), parts, nq,
       reinterpret_cast<unsigned long long*>(keys));
   PBK_CHECK_LAUNCH("hamming_merge_kernel");
@@ -812,7 +841,7 @@ int pbk_hamming_knn2_dist(const uint8_t* q, int64_t nq, const uint8_t* t, int64_
   rc = launch_knn2(P, rq, di, s);
   if (rc) return rc;
   const unsigned blocks = (unsigned)((nq + 255) / 256);
-  hamming_merge_push_kernel<<<blocks, 256, 0, s>>>(P.partial, splits, X, done_counter);
+  hamming_merge_push_kernel<<<merge_blocks(nq), 256, 0, s>>>(P.partial, splits, X, done_counter);
   PBK_CHECK_LAUNCH("hamming_merge_push_kernel");
   hamming_merge_world_kernel<<<blocks, 256, 0, s>>>(X, reinterpret_cast<unsigned long long*>(keys));
   PBK_CHECK_LAUNCH("hamming_merge_world_kernel");
@@ -865,7 +894,7 @@ int pbk_hamming_tc_knn2(const uint8_t* q, int64_t nq, const int8_t* t_signs, int
   int8_t* q_signs = static_cast<int8_t*>(scratch) + (((size_t)parts * (size_t)nq * 16 + 255) & ~(size_t)255);
   rc = hamming_tc_scan(q, nq, t_signs, nt, train_base, q_signs, partial, &parts, di, s);
   if (rc) return rc;
-  hamming_merge_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(partial, parts, nq,
+  hamming_merge_kernel<<<merge_blocks(nq), 256, 0, s>>>(partial, parts, nq,
                                                                     reinterpret_cast<unsigned long long*>(keys));
   PBK_CHECK_LAUNCH("hamming_merge_kernel");
   return PBK_OK;
@@ -898,7 +927,7 @@ int pbk_hamming_tc_knn2_dist(const uint8_t* q, int64_t nq, const int8_t* t_signs
   rc = hamming_tc_scan(q, nq, t_signs, nt, train_base, q_signs, partial, &parts, di, s);
   if (rc) return rc;
   const unsigned blocks = (unsigned)((nq + 255) / 256);
-  hamming_merge_push_kernel<<<blocks, 256, 0, s>>>(partial, parts, X, done_counter);
+  hamming_merge_push_kernel<<<merge_blocks(nq), 256, 0, s>>>(partial, parts, X, done_counter);
   PBK_CHECK_LAUNCH("hamming_merge_push_kernel");
   hamming_merge_world_kernel<<<blocks, 256, 0, s>>>(X, reinterpret_cast<unsigned long long*>(keys));
   PBK_CHECK_LAUNCH("hamming_merge_world_kernel");
