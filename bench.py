@@ -398,8 +398,7 @@ def run_c3(D, args):
 
     # end to end through the array API: pinned host queries in, numpy results out
     def e2e_step(rec):
-        idx, dist, r_ok, m_ok, valid = m.match(torch.from_numpy(q_pin).to("cuda", non_blocking=True))
-        return [_ffi.to_host(x) for x in (idx, dist, valid)]
+        return m.match_host(torch.from_numpy(q_pin).to("cuda", non_blocking=True))
     e2e_ms, _ = timed_steps(D, e2e_step, args.steps, args.warmup, flush)
 
     # ... and through the cv2-shaped facade: BFMatcher.knnMatch(host queries, k=2) over the
@@ -431,8 +430,9 @@ def run_c3(D, args):
                             % (" + the 288 B/row expanded copy the tensor-core scan reads" if m.signs is not None else "")},
         "e2e": {"value": pairs * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": "Gpairs/s",
                 "h2d_bytes_per_step": nq * 32,
-                "d2h_bytes_per_step": nq * (2 * 8 + 2 * 4 + 1),
-                "api": "ShardedKeyframeMatcher.match (array API: idx, dist, valid as numpy)"},
+                "d2h_bytes_per_step": nq * (2 * 8 + 2 * 4 + 3),
+                "api": "ShardedKeyframeMatcher.match_host (array API: idx, dist, ratio_ok, mutual_ok, valid "
+                       "as numpy; one packed copy)"},
         "e2e_knnMatch": {"value": pairs * args.steps / (knn_api_ms * 1e-3) / 1e9, "unit": "Gpairs/s",
                          "ms_per_step": knn_api_ms / args.steps,
                          "h2d_bytes_per_step": nq * 32, "d2h_bytes_per_step": nq * (2 * 8 + 2 * 4 + 3),

@@ -226,7 +226,8 @@ class ShardedKeyframeMatcher(object):
 
     def match_host(self, q, ratio=0.75, mutual=True):
         """match() with numpy results; raises RuntimeError if a peer timed out in this call."""
-        out = [_ffi.to_host(x) for x in self.match(q, ratio, mutual)]
+        r = self.match(q, ratio, mutual)
+        out = list(r.to_host()) if hasattr(r, "to_host") else [_ffi.to_host(x) for x in r]
         self.check()
         return out
 

@@ -492,19 +492,44 @@ def hamming_gather_best(t_dev, keys, train_base=0):
     return rows
 
 
+class MatchResult(tuple):
+    """(idx (nq,2) int64, dist (nq,2) int32, ratio_ok, mutual_ok, valid) as device tensors that are
+    views of ONE buffer, so the whole result crosses PCIe in one copy (`to_host`) instead of five
+    copies and five stream synchronisations."""
+
+    def __new__(cls, items, packed, nq):
+        self = super().__new__(cls, items)
+        self.packed, self.nq = packed, nq
+        return self
+
+    @staticmethod
+    def _views(base, m, nq, T):
+        idx = base[:16 * m].view(T.int64).view(m, 2)[:nq]
+        dist = base[16 * m:24 * m].view(T.int32).view(m, 2)[:nq]
+        fb = base[24 * m:27 * m].view(3, m).view(T.bool)
+        return idx, dist, fb[0, :nq], fb[1, :nq], fb[2, :nq]
+
+    def to_host(self):
+        """numpy (idx, dist, ratio_ok, mutual_ok, valid): one pinned copy, one synchronisation."""
+        T = _ffi.torch()
+        host = T.empty(self.packed.shape, dtype=T.uint8, pin_memory=True)
+        host.copy_(self.packed, non_blocking=True)
+        T.cuda.current_stream().synchronize()
+        return tuple(v.numpy() for v in self._views(host, max(self.nq, 1), self.nq, T))
+
+
 def hamming_ratio_mutual(keys, rev_keys, ratio):
     T = _ffi.torch()
     nq = int(keys.shape[0])
-    dev = keys.device
     m = max(nq, 1)
-    idx = T.empty((m, 2), dtype=T.int64, device=dev)[:nq]
-    dist = T.empty((m, 2), dtype=T.int32, device=dev)[:nq]
-    flags = T.empty((3, m), dtype=T.uint8, device=dev)
+    base = T.empty((27 * m,), dtype=T.uint8, device=keys.device)   # the kernel writes 0/1 bytes as flags
+    out = MatchResult._views(base, m, nq, T)
+    idx, dist = out[0], out[1]
+    flags = base[24 * m:27 * m].view(3, m)
     _ffi.check(_ffi.lib().pbk_hamming_ratio_mutual(
-        _ffi.ptr(keys), _ffi.ptr(rev_keys), nq, float(ratio), _ffi.ptr(idx), _ffi.ptr(dist),
+        _ffi.ptr(keys), _ffi.ptr(rev_keys), nq, float(ratio), _ffi.ptr(base), _ffi.ptr(base[16 * m:]),
         _ffi.ptr(flags[0]), _ffi.ptr(flags[1]), _ffi.ptr(flags[2]), _ffi.stream_ptr()))
-    fb = flags.view(T.bool)                  # the kernel writes 0/1 bytes: reinterpret, no conversion launches
-    return idx, dist, fb[0, :nq], fb[1, :nq], fb[2, :nq]
+    return MatchResult(out, base, nq)
 
 
 def knn_ratio_mutual(q, t, ratio=0.75, train_base=0, mutual=True, signs=None):
@@ -523,7 +548,7 @@ def knn_ratio_mutual(q, t, ratio=0.75, train_base=0, mutual=True, signs=None):
     out = hamming_ratio_mutual(keys, rev, ratio)
     if on_dev:
         return out
-    return tuple(_ffi.to_host(o) for o in out)
+    return out.to_host()
 
 
 class PreparedMatcher(object):

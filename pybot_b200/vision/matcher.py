@@ -276,8 +276,8 @@ class BFMatcher(object):
             else:
                 db = self.db
             offsets = db.offsets
-            idx, dist, r_ok, m_ok, valid = (_np(x) for x in ops.knn_ratio_mutual(
-                queryDescriptors, db.flat, ratio=r, mutual=mutual, signs=db.signs()))
+            res = ops.knn_ratio_mutual(queryDescriptors, db.flat, ratio=r, mutual=mutual, signs=db.signs())
+            idx, dist, r_ok, m_ok, valid = res.to_host() if hasattr(res, "to_host") else (_np(x) for x in res)
         idx, dist = np.asarray(idx), np.asarray(dist)
         img, tr = _split_global(offsets, np.maximum(idx, 0))
         img[idx < 0] = -1
