@@ -1022,7 +1022,13 @@ project_compacted_kernel(long long n, T* __restrict__ uv, double* __restrict__ d
 //
 // The chain of generation i + kEaAhead therefore runs while generation i is being projected;
 // nothing is parked, no CTA-wide barrier is executed after the prologue.
-constexpr int kEaThreads = kWarps * 32;
+#ifndef PBK_EA_WARPS
+#define PBK_EA_WARPS 8
+#endif
+constexpr int kEaWarps = PBK_EA_WARPS;      // compute warps per CTA (128 points each per tile)
+static_assert(kEaWarps >= 1 && kEaWarps <= 16, "the offset sums run over 16-lane groups");
+constexpr int kEaCtaPts = kEaWarps * kTilePts;
+constexpr int kEaThreads = kEaWarps * 32;
 constexpr int kEaSlots = 16;                // per-tile bookkeeping in shared memory (see the static_assert)
 #ifndef PBK_EA_AHEAD
 #define PBK_EA_AHEAD 2
@@ -1043,8 +1049,8 @@ template <typename T> struct EarlyCfg {
   // float64 tiles are twice as large: two tiles ahead keep two CTAs per SM
   static constexpr int kAhead = sizeof(T) == 4 ? kEaAheadMax : (kEaAheadMax < 2 ? kEaAheadMax : 2);
   static constexpr int kStages = kAhead + (sizeof(T) == 4 ? 3 : 2);       // input tiles per warp
-  static constexpr int kRing = kWarps * kStages * CpTile<T>::kBytes;
-  static constexpr int kBytes = kRing + kWarps * kStages * 8 + kEaSlots * 8 + kEaSlots * kWarps * 4;
+  static constexpr int kRing = kEaWarps * kStages * CpTile<T>::kBytes;
+  static constexpr int kBytes = kRing + kEaWarps * kStages * 8 + kEaSlots * 8 + kEaSlots * kEaWarps * 4;
 };
 constexpr int kEaPer = 14;                  // tiles of a generation per chain lane: G <= 448
 constexpr int kEaCarrySlots = 16;
@@ -1071,10 +1077,10 @@ project_compact_early_kernel(const T* __restrict__ X, long long n, T* __restrict
   extern __shared__ __align__(128) char dyn_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t* ring_bars = reinterpret_cast<uint64_t*>(dyn_smem + EarlyCfg<T>::kRing);
-  uint64_t* arr = ring_bars + kWarps * NST;                         // [slot] 8 arrivals: the counts are in
+  uint64_t* arr = ring_bars + kEaWarps * NST;                         // [slot] 8 arrivals: the counts are in
   int* cnt_w = reinterpret_cast<int*>(arr + kEaSlots);              // [slot][warp] valid points
 
-  const long long ncta = (n + kCtaPts - 1) / kCtaPts;
+  const long long ncta = (n + kEaCtaPts - 1) / kEaCtaPts;
   const int G = (int)gridDim.x - 1, b = (int)blockIdx.x; // G compute CTAs + the chain CTA
   const int mine = b < G ? (int)((ncta - b + G - 1) / G) : 0;       // tiles of this CTA (G <= ncta)
   unsigned long long* const aggw = status;               // [ncta] tile aggregates
@@ -1092,7 +1098,7 @@ project_compact_early_kernel(const T* __restrict__ X, long long n, T* __restrict
     const long long ngen = (ncta + G - 1) / G;
     const int per = (G + 31) / 32;                          // <= kEaPer (launch_compact_early)
     CT_T0();
-    for (long long k = warp; k < ngen; k += kWarps) {
+    for (long long k = warp; k < ngen; k += kEaWarps) {
       const long long t0 = k * G;
       const int Gi = (ncta - t0) < G ? (int)(ncta - t0) : G;
       unsigned long long sw[kEaPer];
@@ -1150,7 +1156,7 @@ project_compact_early_kernel(const T* __restrict__ X, long long n, T* __restrict
   }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kEaSlots; ++s) mbar_init(&arr[s], kWarps);
+    for (int s = 0; s < kEaSlots; ++s) mbar_init(&arr[s], kEaWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   WarpRing<kInBytes, NST> ring;
@@ -1162,7 +1168,7 @@ project_compact_early_kernel(const T* __restrict__ X, long long n, T* __restrict
   const unsigned lt = (1u << lane) - 1u;
   const bool valid_words = (reinterpret_cast<uintptr_t>(valid_out) & 3) == 0;
   CT_T0();
-  auto first_of = [&](int i) -> long long { return ((long long)i * G + b) * kCtaPts + warp * kTilePts; };
+  auto first_of = [&](int i) -> long long { return ((long long)i * G + b) * kEaCtaPts + warp * kTilePts; };
   auto issue = [&](int i) {                                // lane 0
     const long long first = first_of(i);
     if (first + kTilePts <= n) ring.issue(i, Xb + first * 3 * sizeof(T));
@@ -1205,14 +1211,14 @@ project_compact_early_kernel(const T* __restrict__ X, long long n, T* __restrict
       const int slot = i & (kEaSlots - 1);
       bool last = false;
       if (lane == 0) {
-        cnt_w[slot * kWarps + warp] = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+        cnt_w[slot * kEaWarps + warp] = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
         last = mbar_arrive_is_last(&arr[slot]);
       }
       if (__shfl_sync(0xffffffffu, (int)last, 0)) {        // the tile's eight counts are in
         mbar_wait(&arr[slot], (uint32_t)((i / kEaSlots) & 1));      // (acquire; the phase is complete)
-        int agg = lane < kWarps ? cnt_w[slot * kWarps + lane] : 0;
+        int agg = lane < kEaWarps ? cnt_w[slot * kEaWarps + lane] : 0;
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) agg += __shfl_xor_sync(0xffffffffu, agg, o);
+        for (int o = 8; o > 0; o >>= 1) agg += __shfl_xor_sync(0xffffffffu, agg, o);
         if (lane == 0) {
           st_status(aggw + (long long)i * G + b, kStateAgg | (unsigned long long)agg);
           EA_TS_MAX(i, 5);
@@ -1281,9 +1287,9 @@ project_compact_early_kernel(const T* __restrict__ X, long long n, T* __restrict
       if (lane == 0 && warp == 0) EA_TS_MAX(i, 6);
     }
     mbar_wait(&arr[slot], (uint32_t)((i / kEaSlots) & 1));          // (acquire; completed long ago)
-    int bsum = (lane < warp) ? cnt_w[slot * kWarps + lane] : 0;
+    int bsum = (lane < warp) ? cnt_w[slot * kEaWarps + lane] : 0;
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+    for (int o = 8; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
     const long long o0 = (long long)(w & kValueMask) + __shfl_sync(0xffffffffu, bsum, 0);
     CT_ACC(13);
     if (any) {
@@ -1444,7 +1450,7 @@ static int launch_compact_early(const void* X, int64_t n, const pbk_project_para
   int per_sm;
   int rc = kc.setup(di, kern, kEaThreads, smem, &per_sm);
   if (rc) return rc;
-  const long long ncta = (n + kCtaPts - 1) / kCtaPts;
+  const long long ncta = (n + kEaCtaPts - 1) / kEaCtaPts;
   int grid = resident_grid(di, per_sm, ncta + 1);                // compute CTAs + the chain CTA
   if (grid > 32 * kEaPer + 1) grid = 32 * kEaPer + 1;
   PBK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)(2 * ncta + 2) * 8, s));          // aggregate + offset words
