@@ -211,17 +211,26 @@ struct HammingTcParams {
 // tile_base = row in the split of the tile's column 0; rows = rows in the split.
 __device__ __forceinline__ void tc_select(const uint32_t (&v)[32], uint32_t tile_base, uint32_t rows, uint32_t& k1,
                                           uint32_t& k2) {
+  // Most items cannot change a query's top-2 once a few thousand rows have been seen, so the
+  // item is first reduced to its SMALLEST key only (a min tree: 31 packed operations instead of
+  // the 96 of the two top-2 trackers) and compared with the current second-best: k2 >> 23 >= its
+  // distance, so (k2 >> 16) | 127 bounds every 16-bit key that could still enter.  The exact
+  // selection below runs only when some lane of the warp needs it (a few per cent of the items
+  // of a 20 M-row scan); the result is the same either way.
+  {
+    uint32_t m[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) asm("min.u16x2 %0, %1, %2;" : "=r"(m[j]) : "r"(v[2 * j]), "r"(v[2 * j + 1]));
+#pragma unroll
+    for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+      for (int j = 0; j < w; ++j) asm("min.u16x2 %0, %1, %2;" : "=r"(m[j]) : "r"(m[j]), "r"(m[j + w]));
+    const uint32_t best = min(m[0] & 0xFFFFu, m[0] >> 16);
+    if (!__any_sync(0xffffffffu, best <= ((k2 >> 16) | 0x7Fu))) return;
+  }
   uint32_t p[2][2] = {{0xFFFFFFFFu, 0xFFFFFFFFu}, {0xFFFFFFFFu, 0xFFFFFFFFu}};
 #pragma unroll
   for (int j = 0; j < 32; ++j) tc_top2_u16x2(p[j & 1][0], p[j & 1][1], v[j]);
-  // Most items cannot change a query's top-2 once a few thousand rows have been seen: the item's
-  // smallest key is compared with the current second-best (k2 >> 23 >= its distance, so
-  // (k2 >> 16) | 127 bounds every 16-bit key that could still enter) and the fold below is
-  // skipped unless some lane of the warp needs it.
-  uint32_t best;
-  asm("min.u16x2 %0, %1, %2;" : "=r"(best) : "r"(p[0][0]), "r"(p[1][0]));
-  best = min(best & 0xFFFFu, best >> 16);
-  if (!__any_sync(0xffffffffu, best <= ((k2 >> 16) | 0x7Fu))) return;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const uint32_t w = p[c >> 2][(c >> 1) & 1];
