@@ -427,7 +427,7 @@ def run_c3(D, args):
                    "nq": nq, "nt": nt_total, "shard_rows": int(shard.shape[0]),
                    "l2": L2_NOTE,
                    "state": "database resident in HBM (compact rows%s); queries are the per-step input"
-                            % (" + the 288 B/row expanded copy the tensor-core scan reads" if m.signs is not None else "")},
+                            % (" + the 256 B/row expanded copy the tensor-core scan reads" if m.signs is not None else "")},
         "e2e": {"value": pairs * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": "Gpairs/s",
                 "h2d_bytes_per_step": nq * 32,
                 "d2h_bytes_per_step": nq * (2 * 8 + 2 * 4 + 3),
@@ -498,15 +498,15 @@ def run_c3(D, args):
             res["roofline"] = {
                 "bound": "tensor", "kernel": "hamming_tc_kernel (tcgen05.mma kind::i8, + query expansion and split merge)",
                 "achieved": tops, "peak": int8_peak, "unit": "TOP/s", "frac": tops / int8_peak,
-                "frac_issued": tops * 288.0 / 256.0 / int8_peak,
+                "frac_issued": tops / int8_peak,
                 "frac_of_nominal_4500": tops / 4500.0,
                 "frac_of_2x_measured_bf16": tops / (2.0 * bf16),
                 "peak_source": "pbk_hamming_tc_peak_probe, measured in this run: back-to-back tcgen05.mma kind::i8 of the "
                                "kernel's shape (M 128, N 128, K 32) on one CTA per SM, no data movement (burst; nominal "
                                "dense int8 = 4500 TOP/s; 2 x the dense bf16 of %s = %.0f TOP/s)" % (bf16_src, 2.0 * bf16),
                 "algorithmic": "256 int8 multiply-adds (2 ops each) per descriptor pair: the dot product of the +-1 "
-                               "expansions is 256 - 2 d; the kernel issues 288 (a 33rd 32-byte K step adds the "
-                               "column code and bias so that the accumulator IS the 16-bit selection key): frac_issued",
+                               "expansions is 256 - 2 d, and the kernel issues exactly those (8 K steps of 32): "
+                               "frac_issued = frac",
                 "traffic": ncu_traffic("hamming_tc_kernel", scale=float(shard.shape[0]) / 2.5e6),
                 "traffic_source": ncu_traffic_note("hamming_tc_kernel", scale=float(shard.shape[0]) / 2.5e6),
                 "traffic_stale": ncu_traffic_stale("hamming_tc.cu"),

@@ -225,7 +225,7 @@ PBK_API int pbk_hamming_gather_best_dist(const uint8_t* t, int64_t nt, uint64_t 
  * expanded to signed bytes such that the int32 dot product IS the 16-bit selection key
  * 128 d + column (see the file header), accumulators in tensor memory, the same top-2 keys and merges - results bit-identical to
  * pbk_hamming_knn2 / pbk_hamming_knn2_dist.  The expanded copy of a database is made once
- * (pbk_hamming_tc_expand, 288 B per row in the tile layout the kernel's UMMA descriptors
+ * (pbk_hamming_tc_expand, 256 B per row in the tile layout the kernel's UMMA descriptors
  * describe, padded to a multiple of 512 rows) and kept resident; queries are expanded inside
  * the call.  An appended database is extended in place: first_row = (old n / 512) * 512
  * rewrites only the rows from there on (d always points at row 0).  The scan must be given

@@ -6,31 +6,35 @@
 // A 256-bit descriptor is expanded ONCE into signed bytes: a query into a_k = bit_k ? +1 : -1,
 // a train row into b_k = bit_k ? -64 : +64, so that the exact int32 dot product is
 //     sum_k a_k b_k = -64 (256 - 2 d) = 128 d - 16384 .
-// A 33rd 32-byte K step carries constants: query side [64 x16, 1, 127, 127, 0 ...], train side
-// [16 x16, c, 0, 0, 0 ...] with c = row % 128, adding 16384 + c.  The accumulator of
-// (query, train row) is therefore the finished 16-bit selection key
-//     key = 128 d + c        (0 .. 32895; distance in the high bits, column in the low 7)
-// straight out of the tensor core, and tcgen05.ld.pack::16b delivers two adjacent columns per
-// register: the epilogue is nothing but the VIMNMX.U16x2 top-2 network (1.5 ALU instructions per
-// pair; the POPC / LOP3 route issues 23.6 and is bound by the 16-lane XU pipe at 4 pairs per
-// clock per SM, profiles/r02_hamming_inner_loop.md).  Rows past the end of the database carry
-// 127 in the two spare constant slots: +32258, a key above every real one.
+// The accumulator of (query, train row) is a multiple of 128 that orders like the distance and
+// fits 16 bits, and tcgen05.ld.pack::16b delivers two adjacent columns per register.  The epilogue
+// first takes the SMALLEST value of an item (64 columns of one query row) with a packed signed
+// min tree - 0.5 ALU instructions per pair; the POPC / LOP3 route issues 23.6 per pair and is
+// bound by the 16-lane XU pipe at 4 pairs per clock per SM (profiles/r02_hamming_inner_loop.md) -
+// and only when that value could still enter some query's top-2 (a few per cent of the items of
+// a long scan) builds the full keys
+//     key = acc + c = 128 d - 16384 + c     (c = column of the tile, 0 .. 127; signed 16 bit)
+// and runs the packed signed top-2 network over them (1.5 instructions per pair).
+// (Until round 2's last step a 33rd 32-byte K step of constants made the accumulator the finished
+// key 128 d + c: 12.5 % more tensor work and HBM bytes to save ALU work that the pre-filter had
+// already removed.)  Rows past the end of the database are all-zero (distance code 128) and are
+// dropped by row number when keys are built.
 //
-// Data layout.  Expanded rows (288 B) live in HBM in exactly the shared-memory image the UMMA
-// descriptors describe (K-major, no swizzle), tile by tile: a tile is 128 rows = 18 planes (one
+// Data layout.  Expanded rows (256 B) live in HBM in exactly the shared-memory image the UMMA
+// descriptors describe (K-major, no swizzle), tile by tile: a tile is 128 rows = 16 planes (one
 // per 16-byte K chunk) of 128 x 16 bytes, i.e. of sixteen 8-row "core matrices" (128 B each):
-//     byte address of element k of row r  =  (r / 128) * 36864 + (k / 16) * 2048 + (r % 128) * 16 + k % 16
+//     byte address of element k of row r  =  (r / 128) * 32768 + (k / 16) * 2048 + (r % 128) * 16 + k % 16
 // => stride (8-row group) byte offset 128, leading (K-chunk) byte offset 2048; a tile is one
-// contiguous 36 KB span and arrives by ONE plain 1-D bulk copy (cp.async.bulk), no tensor map.
+// contiguous 32 KB span and arrives by ONE plain 1-D bulk copy (cp.async.bulk), no tensor map.
 // (With the chunks of a row group adjacent instead - LBO 128, SBO 2304 - the same MMAs ran 6 %
 // slower in isolation: scripts/probes/utcimma_probe.cu.)  A database keeps its expanded copy resident next to the
-// compact one (9 x the bytes: 5.8 GB for the 20 M-row C3 database; the compact rows are still
+// compact one (8 x the bytes: 5.1 GB for the 20 M-row C3 database; the compact rows are still
 // what the mutual check gathers).
 //
-// Kernel.  One CTA per SM (216 KB of shared memory, all 512 TMEM columns), grid = query groups
+// Kernel.  One CTA per SM (224 KB of shared memory, all 512 TMEM columns), grid = query groups
 // of 512 x database splits.  A CTA keeps its 512 expanded queries (4 blocks of M = 128) in
-// shared memory for its whole life and streams its split in tiles of N = 128 rows (36 KB,
-// 2-stage ring).  Work item = (tile, query block): 9 UTCIMMA (K = 32 each) into one of FOUR
+// shared memory for its whole life and streams its split in tiles of N = 128 rows (32 KB,
+// 3-stage ring).  Work item = (tile, query block): 8 UTCIMMA (K = 32 each) into one of FOUR
 // 128-column accumulator slots, handed to the epilogue through mbarriers
 // (tcgen05.commit -> acc_full, epilogue arrive -> acc_empty), so the tensor pipe runs up to
 // three items ahead of the selection.
@@ -51,7 +55,7 @@ constexpr int kTcM = 128;                         // queries per UMMA (TMEM lane
 constexpr int kTcQBlocks = 4;                     // query blocks resident per CTA
 constexpr int kTcQGroup = kTcM * kTcQBlocks;      // 512 queries per CTA
 constexpr int kTcN = 128;                         // train rows per tile = UMMA N = accumulator columns
-constexpr int kTcStages = 2;
+constexpr int kTcStages = 3;
 #ifndef PBK_TC_PARK_NS
 #define PBK_TC_PARK_NS 1000
 #endif
@@ -59,12 +63,12 @@ constexpr int kTcStages = 2;
 #define PBK_TC_PREFETCH 4
 #endif
 constexpr int kTcPrefetch = PBK_TC_PREFETCH;      // tiles requested into L2 ahead of the shared-memory ring
-constexpr int kTcRowBytes = 288;                  // one expanded descriptor: 256 sign bytes + 32 constant bytes
-constexpr int kTcChunks = kTcRowBytes / 16;       // 18 K chunks of 16 bytes
-constexpr int kTcKSteps = kTcRowBytes / 32;       // 9 UTCIMMA per item
+constexpr int kTcRowBytes = 256;                  // one expanded descriptor: 256 sign bytes
+constexpr int kTcChunks = kTcRowBytes / 16;       // 16 K chunks of 16 bytes
+constexpr int kTcKSteps = kTcRowBytes / 32;       // 8 UTCIMMA per item
 constexpr int kTcPlaneBytes = 128 * 16;           // 2048: one K chunk of the 128 rows of a tile
-constexpr int kTcTileBytes = kTcN * kTcRowBytes;  // 36 KB
-constexpr int kTcBlockBytes = kTcM * kTcRowBytes; // 36 KB
+constexpr int kTcTileBytes = kTcN * kTcRowBytes;  // 32 KB
+constexpr int kTcBlockBytes = kTcM * kTcRowBytes; // 32 KB
 constexpr int kTcSlots = 4;                       // accumulator slots of 128 columns
 constexpr int kTcThreads = 352;                   // 11 warps
 constexpr int kTcEpiWarps = 8;                    // warps 0-7: warp w may only touch TMEM lanes 32 (w % 4) .. +31
@@ -82,15 +86,14 @@ constexpr uint32_t kTcKeyMul = (1u << 23) + 1u;   // 32-bit key = distance * kTc
 constexpr uint32_t kTcNone = 0xFFFFFFFFu;
 constexpr long long kTcMaxSplitRows = 1ll << 23;
 
-constexpr int kTcSmemA = kTcQGroup * kTcRowBytes;                 // 147456
-constexpr int kTcSmemB = kTcStages * kTcTileBytes;                // 73728
+constexpr int kTcSmemA = kTcQGroup * kTcRowBytes;                 // 131072
+constexpr int kTcSmemB = kTcStages * kTcTileBytes;                // 98304
 constexpr int kTcSmemBars = (2 * kTcStages + 2 * kTcSlots + 1) * 8;
 constexpr int kTcSmemBytes = kTcSmemA + kTcSmemB + kTcSmemBars + 16;
 
 // ------------------------------------------------------------ expansion: bits -> signed bytes
-// thread = (row, 16-byte K chunk): 2 descriptor bytes in, one 16-byte core-matrix row out; chunks
-// 16 and 17 are the constant K step (see the header).  QUERY: +-1 and [64.., 1, 127, 127];
-// train: -+64 and [16.., row % 128, pad, pad] with pad = 127 for the rows past the end.
+// thread = (row, 16-byte K chunk): 2 descriptor bytes in, one 16-byte core-matrix row out.
+// QUERY: +-1; train: -+64; rows past the end: zeros.
 template <bool QUERY>
 __global__ void __launch_bounds__(256)
 hamming_tc_expand_kernel(const uint8_t* __restrict__ d, long long n, long long first_row, long long n_padded,
@@ -98,29 +101,21 @@ hamming_tc_expand_kernel(const uint8_t* __restrict__ d, long long n, long long f
   // 16-byte piece index; rows [first_row, n_padded) are (re)written (first_row: a multiple of 512)
   const long long i = first_row * kTcChunks + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_padded * kTcChunks) return;
-  const long long tile = i / (kTcN * kTcChunks);      // 2304 pieces per tile: [K chunk][row of the tile]
+  const long long tile = i / (kTcN * kTcChunks);      // 2048 pieces per tile: [K chunk][row of the tile]
   const int in_t = (int)(i - tile * (kTcN * kTcChunks));
   const int kc = in_t >> 7, rt = in_t & 127;
   const long long r = tile * kTcN + rt;
   const bool real = r < n;
   uint4 o = make_uint4(0, 0, 0, 0);
-  if (kc < 16) {
-    if (real) {
-      const unsigned bits = (unsigned)d[r * 32 + kc * 2] | ((unsigned)d[r * 32 + kc * 2 + 1] << 8);
-      // nibble -> four bytes of 0 / 1 (bit i -> byte i); query: 1 -> 0x01, 0 -> 0xFF (+-1);
-      // train: 1 -> 0xC0 (-64), 0 -> 0x40 (+64)
-      auto four = [](unsigned nib) -> unsigned {
-        const unsigned t = (nib * 0x00204081u) & 0x01010101u;
-        return QUERY ? (0xFFFFFFFFu ^ (t * 0xFEu)) : (0x40404040u + t * 0x80u);
-      };
-      o = make_uint4(four(bits & 15u), four((bits >> 4) & 15u), four((bits >> 8) & 15u), four((bits >> 12) & 15u));
-    }
-  } else if (kc == 16) {
-    const unsigned v = QUERY ? (real ? 0x40404040u : 0u) : 0x10101010u;       // 64 x16 | 16 x16
-    o = make_uint4(v, v, v, v);
-  } else {
-    if (QUERY) o.x = real ? (1u | (127u << 8) | (127u << 16)) : 0u;
-    else o.x = (unsigned)(r & 127) | (real ? 0u : ((127u << 8) | (127u << 16)));
+  if (real) {
+    const unsigned bits = (unsigned)d[r * 32 + kc * 2] | ((unsigned)d[r * 32 + kc * 2 + 1] << 8);
+    // nibble -> four bytes of 0 / 1 (bit i -> byte i); query: 1 -> 0x01, 0 -> 0xFF (+-1);
+    // train: 1 -> 0xC0 (-64), 0 -> 0x40 (+64)
+    auto four = [](unsigned nib) -> unsigned {
+      const unsigned t = (nib * 0x00204081u) & 0x01010101u;
+      return QUERY ? (0xFFFFFFFFu ^ (t * 0xFEu)) : (0x40404040u + t * 0x80u);
+    };
+    o = make_uint4(four(bits & 15u), four((bits >> 4) & 15u), four((bits >> 8) & 15u), four((bits >> 12) & 15u));
   }
   signs[i] = o;
 }
@@ -186,6 +181,12 @@ __device__ __forceinline__ void tc_top2_u16x2(uint32_t& k1, uint32_t& k2, uint32
   asm("min.u16x2 %0, %1, %2;" : "=r"(k1) : "r"(k1), "r"(key));
   asm("min.u16x2 %0, %1, %2;" : "=r"(k2) : "r"(k2), "r"(mx));
 }
+__device__ __forceinline__ void tc_top2_s16x2(uint32_t& k1, uint32_t& k2, uint32_t key) {
+  uint32_t mx;
+  asm("max.s16x2 %0, %1, %2;" : "=r"(mx) : "r"(k1), "r"(key));
+  asm("min.s16x2 %0, %1, %2;" : "=r"(k1) : "r"(k1), "r"(key));
+  asm("min.s16x2 %0, %1, %2;" : "=r"(k2) : "r"(k2), "r"(mx));
+}
 __device__ __forceinline__ void tc_top2(uint32_t& k1, uint32_t& k2, uint32_t key) {
   const uint32_t mx = max(k1, key);
   k1 = min(k1, key);
@@ -203,42 +204,53 @@ struct HammingTcParams {
   int dbg;                        // PBK_TC_DEBUG timing probes (results are then wrong): 1 = no selection, 2 = no MMA
 };
 
-// top-2 of one accumulator half-slot (64 columns = 32 packed registers of finished keys
-// 128 d + c) of this thread's query row, folded into (k1, k2).  Two independent trackers (even /
-// odd registers) halve the dependent min / max chain.  ONE copy of this code serves every query
-// block and both column halves (the kernel is instruction-cache sensitive: an earlier build with
-// eight unrolled copies spent 90 % of its stall samples on instruction fetch).
-// tile_base = row in the split of the tile's column 0; rows = rows in the split.
-__device__ __forceinline__ void tc_select(const uint32_t (&v)[32], uint32_t tile_base, uint32_t rows, uint32_t& k1,
-                                          uint32_t& k2) {
+// top-2 of one accumulator half-slot (64 columns = 32 packed registers, acc = 128 d - 16384 in
+// each signed 16-bit half) of this thread's query row, folded into (k1, k2).  ONE copy of this
+// code serves every query block and both column halves (the kernel is instruction-cache
+// sensitive: an earlier build with eight unrolled copies spent 90 % of its stall samples on
+// instruction fetch).  tile_base = row in the split of the tile's column 0; rows = rows in the
+// split; h = column half of the slot this warp reads (columns 64 h ..).
+__device__ __forceinline__ void tc_select(const uint32_t (&v)[32], uint32_t tile_base, uint32_t rows, uint32_t h,
+                                          uint32_t& k1, uint32_t& k2) {
   // Most items cannot change a query's top-2 once a few thousand rows have been seen, so the
-  // item is first reduced to its SMALLEST key only (a min tree: 31 packed operations instead of
-  // the 96 of the two top-2 trackers) and compared with the current second-best: k2 >> 23 >= its
-  // distance, so (k2 >> 16) | 127 bounds every 16-bit key that could still enter.  The exact
-  // selection below runs only when some lane of the warp needs it (a few per cent of the items
-  // of a 20 M-row scan); the result is the same either way.
+  // item is first reduced to its SMALLEST accumulator only (a signed min tree: 31 packed
+  // operations) and compared with the current second-best distance k2 >> 23 (k2 = d (2^23 + 1) +
+  // row): an element can only enter with a distance <= that.  The exact selection below runs
+  // only when some lane of the warp needs it; the result is the same either way.
   {
     uint32_t m[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) asm("min.u16x2 %0, %1, %2;" : "=r"(m[j]) : "r"(v[2 * j]), "r"(v[2 * j + 1]));
+    for (int j = 0; j < 16; ++j) asm("min.s16x2 %0, %1, %2;" : "=r"(m[j]) : "r"(v[2 * j]), "r"(v[2 * j + 1]));
 #pragma unroll
     for (int w = 8; w > 0; w >>= 1)
 #pragma unroll
-      for (int j = 0; j < w; ++j) asm("min.u16x2 %0, %1, %2;" : "=r"(m[j]) : "r"(m[j]), "r"(m[j + w]));
-    const uint32_t best = min(m[0] & 0xFFFFu, m[0] >> 16);
-    if (!__any_sync(0xffffffffu, best <= ((k2 >> 16) | 0x7Fu))) return;
+      for (int j = 0; j < w; ++j) asm("min.s16x2 %0, %1, %2;" : "=r"(m[j]) : "r"(m[j]), "r"(m[j + w]));
+    const int best = min((int)(short)(m[0] & 0xFFFFu), (int)m[0] >> 16);
+    const int bound = (int)((k2 >> 23) << 7) - 16384;
+    if (!__any_sync(0xffffffffu, best <= bound)) return;
   }
-  uint32_t p[2][2] = {{0xFFFFFFFFu, 0xFFFFFFFFu}, {0xFFFFFFFFu, 0xFFFFFFFFu}};
+  // keys: acc + column of the tile (acc is a multiple of 128: the packed add never carries from
+  // one half into the other), ordered as SIGNED 16-bit values; two independent trackers (even /
+  // odd registers) halve the dependent min / max chain, then merge
+  uint32_t p[2][2] = {{0x7FFF7FFFu, 0x7FFF7FFFu}, {0x7FFF7FFFu, 0x7FFF7FFFu}};
+  const uint32_t col0 = (h * 64u) * 0x00010001u + 0x00010000u;       // columns (64 h, 64 h + 1) of register 0
 #pragma unroll
-  for (int j = 0; j < 32; ++j) tc_top2_u16x2(p[j & 1][0], p[j & 1][1], v[j]);
+  for (int j = 0; j < 32; ++j) tc_top2_s16x2(p[j & 1][0], p[j & 1][1], v[j] + col0 + (uint32_t)(2 * j) * 0x00010001u);
+  uint32_t lo, hi, t;
+  asm("min.s16x2 %0, %1, %2;" : "=r"(lo) : "r"(p[0][0]), "r"(p[1][0]));
+  asm("max.s16x2 %0, %1, %2;" : "=r"(t) : "r"(p[0][0]), "r"(p[1][0]));
+  asm("min.s16x2 %0, %1, %2;" : "=r"(hi) : "r"(p[0][1]), "r"(p[1][1]));
+  asm("min.s16x2 %0, %1, %2;" : "=r"(hi) : "r"(hi), "r"(t));
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint32_t w = p[c >> 2][(c >> 1) & 1];
-    const uint32_t key16 = (c & 1) ? (w >> 16) : (w & 0xFFFFu);
-    // distance = key >> 7, column of the tile = key & 127 -> 32-bit key = distance * kTcKeyMul + row
-    // in the split; rows past the end of the database (keys above every real one) are dropped
-    const uint32_t row = tile_base + (key16 & 127u);
-    const uint32_t key = row >= rows ? kTcNone : (key16 >> 7) * kTcKeyMul + row;
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t w = (c >> 1) ? hi : lo;
+    const int key16 = (c & 1) ? ((int)w >> 16) : (int)(short)(w & 0xFFFFu);
+    // distance = (key + 16384) >> 7, column of the tile = key & 127 -> 32-bit key = distance *
+    // kTcKeyMul + row in the split; rows past the end of the database (zero rows: distance code
+    // 128) and unused tracker slots (0x7FFF) are dropped
+    const uint32_t row = tile_base + ((uint32_t)key16 & 127u);
+    const uint32_t key = (row >= rows || key16 == 0x7FFF) ? kTcNone
+                                                          : ((uint32_t)(key16 + 16384) >> 7) * kTcKeyMul + row;
     tc_top2(k1, k2, key);
   }
 }
@@ -358,7 +370,7 @@ hamming_tc_kernel(const __grid_constant__ HammingTcParams P) {
       if (lane == 0) mbar_arrive(&acc_empty[item & (kTcSlots - 1)]);
     };
     auto select = [&](int item, const uint32_t (&v)[32]) {
-      if (!(P.dbg & 1)) tc_select(v, (uint32_t)(item >> 2) * kTcN, (uint32_t)rows, k1[0], k2[0]);
+      if (!(P.dbg & 1)) tc_select(v, (uint32_t)(item >> 2) * kTcN, (uint32_t)rows, (uint32_t)h, k1[0], k2[0]);
       else k1[0] ^= v[0] ^ v[31] ^ v[17];
       // rotate: the next item belongs to the next query block
       const uint32_t a1 = k1[0], a2 = k2[0];

@@ -422,6 +422,11 @@ def hamming_engine(nt):
     return "tc" if nt >= TC_MIN_ROWS else "popc"
 
 
+def hamming_tc_row_bytes():
+    """Bytes of one expanded row (the library's layout constant: 256)."""
+    return int(_ffi.lib().pbk_hamming_tc_signs_bytes(512)) // 512
+
+
 def hamming_tc_signs_rows(n):
     """Rows the expanded buffer of an n-row database holds (padded to 512)."""
     return -(-int(n) // 512) * 512
@@ -429,7 +434,7 @@ def hamming_tc_signs_rows(n):
 
 def hamming_tc_expand(t_dev, signs=None, first_row=0):
     """(n,32) uint8 descriptors -> the expanded signed-byte copy the tensor-core scan reads (int8
-    tensor, 288 B per row, tile layout of csrc/hamming_tc.cu).  Done once per database; with
+    tensor, 256 B per row, tile layout of csrc/hamming_tc.cu).  Done once per database; with
     `signs` (a buffer of at least pbk_hamming_tc_signs_bytes(n) bytes) and first_row (a multiple
     of 512) only the rows from first_row on are (re)written - appending to a database."""
     T = _ffi.torch()
@@ -462,7 +467,7 @@ def hamming_knn2_keys_tc(q_dev, t_signs, nt, train_base=0):
 
 def hamming_scan_keys(q_dev, t_dev, train_base=0, signs=None):
     """Top-2 keys of q against the database t: the tensor-core scan when `signs` (the expanded
-    copy) is given or the engine rule picks it (expanding on the fly: 288 B per row written once
+    copy) is given or the engine rule picks it (expanding on the fly: 256 B per row written once
     is still cheaper than the integer-pipe scan of a large database), else the integer-pipe kernel."""
     nt = int(t_dev.shape[0])
     if nt > 0 and int(q_dev.shape[0]) > 0 and hamming_engine(nt) == "tc":

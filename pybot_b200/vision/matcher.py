@@ -156,7 +156,7 @@ class KeyframeDatabase(object):
         return self._buf[:self._n]
 
     def signs(self):
-        """The expanded (288 B per row) copy the tensor-core scan reads, or None when this
+        """The expanded (256 B per row) copy the tensor-core scan reads, or None when this
         database takes the integer-pipe route (small, or PBK_HAMMING_ENGINE=popc).  Kept
         resident and extended in place: an append only expands the rows from the last whole
         block of 512 on."""
@@ -171,7 +171,7 @@ class KeyframeDatabase(object):
             cap = int(_ffi.lib().pbk_hamming_tc_signs_bytes(max(self._buf.shape[0], self._n)))
             grown = T.empty((cap,), dtype=T.int8, device="cuda")
             if self._signs is not None and self._signs_n:
-                keep = (self._signs_n // 512) * 512 * 288
+                keep = (self._signs_n // 512) * 512 * ops.hamming_tc_row_bytes()
                 grown[:keep].copy_(self._signs[:keep])
                 first = (self._signs_n // 512) * 512
             self._signs = grown

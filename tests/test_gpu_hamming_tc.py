@@ -21,27 +21,23 @@ def _keys_both(q, t, base=0):
 
 
 def test_expansion_layout():
-    """Train rows, tile by tile (128 rows): bit k of row r -> byte (r/128)*36864 + (k/16)*2048 + (r%128)*16
-    + k%16 = -64 / +64; the constant K step (chunks 16, 17): 16 x 16, then row % 128, then 127, 127 for the
-    rows past the end."""
+    """Train rows, tile by tile (128 rows): bit k of row r -> byte (r/128)*32768 + (k/16)*2048 + (r%128)*16
+    + k%16 = -64 / +64; rows past the end are zero."""
     import torch
     from pybot_b200 import ops
     rng = np.random.default_rng(0)
     n = 300
     d = rng.integers(0, 256, (n, 32), dtype=np.uint8)
     s = ops.hamming_tc_expand(torch.from_numpy(d).cuda()).cpu().numpy()
-    assert s.dtype == np.int8 and s.size == 512 * 288
+    assert ops.hamming_tc_row_bytes() == 256
+    assert s.dtype == np.int8 and s.size == 512 * 256
     bits = np.unpackbits(d, axis=1, bitorder="little").astype(np.int16)                  # (n, 256)
     r, k = np.meshgrid(np.arange(n), np.arange(256), indexing="ij")
-    addr = (r // 128) * 36864 + (k // 16) * 2048 + (r % 128) * 16 + k % 16
+    addr = (r // 128) * 32768 + (k // 16) * 2048 + (r % 128) * 16 + k % 16
     assert np.array_equal(s[addr], np.where(bits == 1, -64, 64))
     rows = np.arange(512)
-    base = (rows // 128) * 36864 + (rows % 128) * 16
-    assert np.all(s[base[:, None] + 16 * 2048 + np.arange(16)[None, :]] == 16)
-    assert np.array_equal(s[base + 17 * 2048], (rows % 128).astype(np.int8))
-    pad = np.where(rows >= n, 127, 0)
-    assert np.array_equal(s[base + 17 * 2048 + 1], pad) and np.array_equal(s[base + 17 * 2048 + 2], pad)
-    assert not s[base[n:, None] + (np.arange(16) * 2048)[None, :]].any()                 # sign bytes of pad rows are zero
+    base = (rows // 128) * 32768 + (rows % 128) * 16
+    assert not s[base[n:, None] + (np.arange(16) * 2048)[None, :]].any()                 # pad rows are zero
     # appending: expanding only from the last whole block of 512 rows gives the same buffer
     d2 = rng.integers(0, 256, (1500, 32), dtype=np.uint8)
     whole = ops.hamming_tc_expand(torch.from_numpy(d2).cuda())
