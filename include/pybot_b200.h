@@ -221,17 +221,24 @@ PBK_API int pbk_hamming_gather_best_dist(const uint8_t* t, int64_t nt, uint64_t 
                      const uint64_t* peer_bufs, int rank, int world, uint64_t seq,
                      uint32_t* done_counter, uint32_t* status, pbk_stream_t stream);
 
-/* Tensor-core route of the same scan (csrc/hamming_tc.cu): tcgen05.mma kind::i8 over descriptors
- * expanded to signed bytes such that the int32 dot product IS the 16-bit selection key
- * 128 d + column (see the file header), accumulators in tensor memory, the same top-2 keys and merges - results bit-identical to
- * pbk_hamming_knn2 / pbk_hamming_knn2_dist.  The expanded copy of a database is made once
- * (pbk_hamming_tc_expand, 256 B per row in the tile layout the kernel's UMMA descriptors
- * describe, padded to a multiple of 512 rows) and kept resident; queries are expanded inside
- * the call.  An appended database is extended in place: first_row = (old n / 512) * 512
- * rewrites only the rows from there on (d always points at row 0).  The scan must be given
- * the whole buffer with the nt it was expanded for (the rows past nt carry end markers).
+/* Tensor-core route of the same scan: tcgen05.mma over descriptors expanded ONCE into a signed
+ * element per bit, accumulators in tensor memory, the same top-2 keys and merges - results
+ * bit-identical to pbk_hamming_knn2 / pbk_hamming_knn2_dist.  Two encodings (pbk_hamming_tc_format):
+ *   4 (default)  e2m1 nibbles, tcgen05.mma kind::mxf4 with unit block scales (csrc/hamming_tc4.cu):
+ *                128 B per row, fp32 accumulator = 2 d - 256, twice the int8 MMA rate
+ *   8            signed bytes, tcgen05.mma kind::i8 (csrc/hamming_tc.cu): 256 B per row,
+ *                int32 accumulator = 128 d - 16384
+ * The format is a property of the expanded buffers: select it (PBK_TC_FORMAT=4|8 in the
+ * environment, or pbk_hamming_tc_set_format) BEFORE expanding and keep it for every scan of that
+ * copy.  The expanded copy of a database is made once (pbk_hamming_tc_expand, in the tile layout
+ * the kernel's UMMA descriptors describe, padded to a multiple of 512 rows) and kept resident;
+ * queries are expanded inside the call.  An appended database is extended in place:
+ * first_row = (old n / 512) * 512 rewrites only the rows from there on (d always points at row 0).
+ * The scan must be given the whole buffer with the nt it was expanded for.
  * signs     device, >= pbk_hamming_tc_signs_bytes(n) bytes, 16-byte aligned
  * scratch   device, >= the size pbk_hamming_tc_plan reports (partial keys + expanded queries)   */
+PBK_API int pbk_hamming_tc_format(void);
+PBK_API int pbk_hamming_tc_set_format(int format);
 PBK_API size_t pbk_hamming_tc_signs_bytes(int64_t n);
 PBK_API int pbk_hamming_tc_expand(const uint8_t* d, int64_t n, int64_t first_row, int8_t* signs,
                                   pbk_stream_t stream);
@@ -243,9 +250,10 @@ PBK_API int pbk_hamming_tc_knn2_dist(const uint8_t* q, int64_t nq, const int8_t*
                      const uint64_t* peer_bufs, int rank, int world, uint64_t seq,
                      uint32_t* done_counter, uint32_t* status, pbk_stream_t stream);
 
-/* int8 tensor-pipe peak probe (measurement only): one CTA per SM issues iters x 8
- * tcgen05.mma kind::i8 of the matcher's shape (M 128, N 128, K 32) on resident shared memory, no
- * data movement, no epilogue.  *macs_per_launch receives the multiply-adds issued.
+/* tensor-pipe peak probe (measurement only) for the selected format: one CTA per SM issues
+ * iters x (4 tcgen05.mma kind::mxf4, K 64 | 8 tcgen05.mma kind::i8, K 32) of the matcher's shape
+ * (M 128, N 128) on resident shared memory, no data movement, no epilogue.  *macs_per_launch
+ * receives the multiply-adds issued (iters x 128 x 128 x 256 per SM in either format).
  * sink: device uint32[SM count] or NULL.                                                      */
 PBK_API int pbk_hamming_tc_peak_probe(int iters, uint32_t* sink, double* macs_per_launch,
                                       pbk_stream_t stream);

@@ -72,6 +72,8 @@ SIGNATURES = {
     "pbk_hamming_exchange_words": (_sz, [_i64, _i]),
     "pbk_hamming_knn2_dist": (_i, [_vp, _i64, _vp, _i64, _u64, _vp, _vp, _vp, _i, _i, _u64, _vp, _vp, _vp]),
     "pbk_hamming_gather_best_dist": (_i, [_vp, _i64, _u64, _vp, _i64, _vp, _vp, _i, _i, _u64, _vp, _vp, _vp]),
+    "pbk_hamming_tc_format": (_i, []),
+    "pbk_hamming_tc_set_format": (_i, [_i]),
     "pbk_hamming_tc_signs_bytes": (_sz, [_i64]),
     "pbk_hamming_tc_expand": (_i, [_vp, _i64, _i64, _vp, _vp]),
     "pbk_hamming_tc_plan": (_i, [_i64, _i64, ctypes.POINTER(_i), ctypes.POINTER(_sz)]),

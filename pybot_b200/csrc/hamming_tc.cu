@@ -47,31 +47,20 @@
 //               folded into 32-bit keys.  A lane is one query row of each of the four blocks.
 // Every (split, column half) emits (distance << 32 | global row) keys; the existing merge
 // kernels reduce them - bit-identical to a single ascending scan (unsigned min).
-#include "pbk_common.cuh"
+#include <atomic>
+#include <cstdlib>
+#include "hamming_tc.cuh"
 
 namespace pbk {
 
-constexpr int kTcM = 128;                         // queries per UMMA (TMEM lanes)
-constexpr int kTcQBlocks = 4;                     // query blocks resident per CTA
-constexpr int kTcQGroup = kTcM * kTcQBlocks;      // 512 queries per CTA
-constexpr int kTcN = 128;                         // train rows per tile = UMMA N = accumulator columns
 constexpr int kTcStages = 3;
-#ifndef PBK_TC_PARK_NS
-#define PBK_TC_PARK_NS 1000
-#endif
-#ifndef PBK_TC_PREFETCH
-#define PBK_TC_PREFETCH 4
-#endif
-constexpr int kTcPrefetch = PBK_TC_PREFETCH;      // tiles requested into L2 ahead of the shared-memory ring
 constexpr int kTcRowBytes = 256;                  // one expanded descriptor: 256 sign bytes
 constexpr int kTcChunks = kTcRowBytes / 16;       // 16 K chunks of 16 bytes
 constexpr int kTcKSteps = kTcRowBytes / 32;       // 8 UTCIMMA per item
-constexpr int kTcPlaneBytes = 128 * 16;           // 2048: one K chunk of the 128 rows of a tile
 constexpr int kTcTileBytes = kTcN * kTcRowBytes;  // 32 KB
 constexpr int kTcBlockBytes = kTcM * kTcRowBytes; // 32 KB
 constexpr int kTcSlots = 4;                       // accumulator slots of 128 columns
 constexpr int kTcThreads = 352;                   // 11 warps
-constexpr int kTcEpiWarps = 8;                    // warps 0-7: warp w may only touch TMEM lanes 32 (w % 4) .. +31
 // The scheduler of an SM sub-partition favours its HIGHEST warp id.  The one lane that issues
 // every tcgen05.mma sits in warp 8 (sub-partition 0, above selecting warps 0 and 4) and the
 // producer in warp 9: as warps 1 / 0 under the selecting warps the issuer was starved for issue
@@ -81,10 +70,6 @@ constexpr int kTcEpiWarps = 8;                    // warps 0-7: warp w may only 
 // per item (barrier round trips, descriptor arithmetic, commits) were not hidden behind the 640
 // clocks of its nine MMAs - the pipe measured 55 % busy with one issuer.
 constexpr int kTcMmaWarp = 8, kTcMmaWarps = 2, kTcProducerWarp = 10;
-constexpr int kTcPad = 512;                       // expanded buffers are padded to whole query groups / tiles
-constexpr uint32_t kTcKeyMul = (1u << 23) + 1u;   // 32-bit key = distance * kTcKeyMul + row in split (as hamming.cu)
-constexpr uint32_t kTcNone = 0xFFFFFFFFu;
-constexpr long long kTcMaxSplitRows = 1ll << 23;
 
 constexpr int kTcSmemA = kTcQGroup * kTcRowBytes;                 // 131072
 constexpr int kTcSmemB = kTcStages * kTcTileBytes;                // 98304
@@ -119,90 +104,6 @@ hamming_tc_expand_kernel(const uint8_t* __restrict__ d, long long n, long long f
   }
   signs[i] = o;
 }
-
-// ------------------------------------------------------------------ tcgen05 / TMEM helpers
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// shared-memory matrix descriptor: K-major, no swizzle, LBO = 2048 B (K chunks), SBO = 128 B (8-row groups)
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(kTcPlaneBytes >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) |
-         (1ull << 46);                               // bits [46,48): descriptor version 1 (Blackwell)
-}
-// instruction descriptor, kind::i8: D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), both K-major,
-// N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t kTcIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  const uint32_t z = 0;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(kTcIdesc), "r"(accumulate), "r"(z), "r"(z), "r"(z), "r"(z)
-      : "memory");
-}
-// the mbarrier receives one arrival when every tcgen05 operation this thread issued so far is done
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// 64 consecutive accumulator columns of this thread's TMEM lane, their low 16 bits packed two per
-// register (column 2 i in the low half of r[i], column 2 i + 1 in the high half)
-__device__ __forceinline__ void tc_ld64_packed(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// mbarrier wait for the warps that may sleep: try_wait with a suspend-time hint, so a waiting warp
-// parks inside the instruction instead of polling shared memory - the tensor pipe fetches its
-// operands from the same shared memory
-__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAITP_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-      "@p bra DONEP_%=;\n\t"
-      "bra WAITP_%=;\n\t"
-      "DONEP_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(PBK_TC_PARK_NS)
-      : "memory");
-}
-
-__device__ __forceinline__ void tc_top2_u16x2(uint32_t& k1, uint32_t& k2, uint32_t key) {
-  uint32_t mx;
-  asm("max.u16x2 %0, %1, %2;" : "=r"(mx) : "r"(k1), "r"(key));
-  asm("min.u16x2 %0, %1, %2;" : "=r"(k1) : "r"(k1), "r"(key));
-  asm("min.u16x2 %0, %1, %2;" : "=r"(k2) : "r"(k2), "r"(mx));
-}
-__device__ __forceinline__ void tc_top2_s16x2(uint32_t& k1, uint32_t& k2, uint32_t key) {
-  uint32_t mx;
-  asm("max.s16x2 %0, %1, %2;" : "=r"(mx) : "r"(k1), "r"(key));
-  asm("min.s16x2 %0, %1, %2;" : "=r"(k1) : "r"(k1), "r"(key));
-  asm("min.s16x2 %0, %1, %2;" : "=r"(k2) : "r"(k2), "r"(mx));
-}
-__device__ __forceinline__ void tc_top2(uint32_t& k1, uint32_t& k2, uint32_t key) {
-  const uint32_t mx = max(k1, key);
-  k1 = min(k1, key);
-  k2 = min(k2, mx);
-}
-
-struct HammingTcParams {
-  const int8_t* q_signs;          // expanded queries, padded to whole groups of 512 rows
-  const int8_t* t_signs;          // expanded train rows of this call, padded to whole tiles
-  unsigned long long* partial;    // (2 * splits, nq, 2)
-  long long nq, nt;
-  long long rows_per_split;       // multiple of kTcN
-  unsigned long long train_base;
-  int splits;
-  int dbg;                        // PBK_TC_DEBUG timing probes (results are then wrong): 1 = no selection, 2 = no MMA
-};
 
 // top-2 of one accumulator half-slot (64 columns = 32 packed registers, acc = 128 d - 16384 in
 // each signed 16-bit half) of this thread's query row, folded into (k1, k2).  ONE copy of this
@@ -463,7 +364,24 @@ __global__ void __launch_bounds__(128, 1) hamming_tc_peak_kernel(int iters, uint
   if (threadIdx.x == 0 && sink != nullptr) sink[blockIdx.x] = tm;
 }
 
-static long long tc_pad(long long n) { return (n + kTcPad - 1) / kTcPad * kTcPad; }
+
+// ------------------------------------------------------------------ format selection
+// Two encodings of the expanded descriptors, same keys bit for bit:
+//   4  (default) e2m1 nibbles, tcgen05.mma kind::mxf4 (hamming_tc4.cu): 128 B per row, twice the MMA rate
+//   8  signed bytes, tcgen05.mma kind::i8 (this file): 256 B per row
+// The format is a property of the expanded buffers: choose it (PBK_TC_FORMAT in the environment, or
+// pbk_hamming_tc_set_format) before expanding a database and keep it for the scans of that copy.
+static std::atomic<int> g_tc_format{0};
+static int tc_format() {
+  int f = g_tc_format.load(std::memory_order_acquire);
+  if (f == 0) {
+    f = 4;
+    if (const char* e = getenv("PBK_TC_FORMAT")) f = (atoi(e) == 8) ? 8 : 4;
+    g_tc_format.store(f, std::memory_order_release);
+  }
+  return f;
+}
+static int tc_row_bytes() { return tc_format() == 8 ? kTc8RowBytes : kTc4RowBytes; }
 
 // grid: query groups x splits ~ one CTA per SM; every split a whole number of tiles
 static int tc_plan(const DeviceInfo* di, long long nq, long long nt, int* splits, long long* rows_per_split) {
@@ -484,18 +402,14 @@ static int tc_plan(const DeviceInfo* di, long long nq, long long nt, int* splits
   return PBK_OK;
 }
 
-// expands q into `q_signs` and scans t_signs: partial keys (2 * splits, nq, 2) into `partial`
-int hamming_tc_scan(const uint8_t* q, long long nq, const int8_t* t_signs, long long nt, unsigned long long train_base,
-                    int8_t* q_signs, unsigned long long* partial, int* parts, const DeviceInfo* di, cudaStream_t s) {
-  int splits;
-  long long rps;
-  int rc = tc_plan(di, nq, nt, &splits, &rps);
-  if (rc) return rc;
+int hamming_tc8_scan(const uint8_t* q, long long nq, const int8_t* t_signs, long long nt, unsigned long long train_base,
+                     int8_t* q_signs, unsigned long long* partial, int splits, long long rps, const DeviceInfo* di,
+                     cudaStream_t s) {
   const long long nqp = tc_pad(nq);
   hamming_tc_expand_kernel<true><<<(unsigned)((nqp * kTcChunks + 255) / 256), 256, 0, s>>>(q, nq, 0, nqp, reinterpret_cast<uint4*>(q_signs));
   PBK_CHECK_LAUNCH("hamming_tc_expand_kernel");
   static KernelCache kc;
-  rc = kc.setup(di, hamming_tc_kernel, kTcThreads, kTcSmemBytes, nullptr);
+  int rc = kc.setup(di, hamming_tc_kernel, kTcThreads, kTcSmemBytes, nullptr);
   if (rc) return rc;
   HammingTcParams P;
   P.q_signs = q_signs; P.t_signs = t_signs; P.partial = partial;
@@ -505,6 +419,19 @@ int hamming_tc_scan(const uint8_t* q, long long nq, const int8_t* t_signs, long 
   const dim3 grid((unsigned)((nq + kTcQGroup - 1) / kTcQGroup), (unsigned)splits);
   hamming_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, s>>>(P);
   PBK_CHECK_LAUNCH("hamming_tc_kernel");
+  return PBK_OK;
+}
+
+// expands q into `q_signs` and scans t_signs: partial keys (2 * splits, nq, 2) into `partial`
+int hamming_tc_scan(const uint8_t* q, long long nq, const int8_t* t_signs, long long nt, unsigned long long train_base,
+                    int8_t* q_signs, unsigned long long* partial, int* parts, const DeviceInfo* di, cudaStream_t s) {
+  int splits;
+  long long rps;
+  int rc = tc_plan(di, nq, nt, &splits, &rps);
+  if (rc) return rc;
+  rc = tc_format() == 8 ? hamming_tc8_scan(q, nq, t_signs, nt, train_base, q_signs, partial, splits, rps, di, s)
+                        : hamming_tc4_scan(q, nq, t_signs, nt, train_base, q_signs, partial, splits, rps, di, s);
+  if (rc) return rc;
   *parts = 2 * splits;
   return PBK_OK;
 }
@@ -513,9 +440,18 @@ int hamming_tc_scan(const uint8_t* q, long long nq, const int8_t* t_signs, long 
 
 extern "C" {
 
+int pbk_hamming_tc_format(void) { return pbk::tc_format(); }
+
+int pbk_hamming_tc_set_format(int format) {
+  using namespace pbk;
+  PBK_REQUIRE(format == 4 || format == 8, PBK_EINVAL, "format must be 4 (e2m1, kind::mxf4) or 8 (s8, kind::i8)");
+  g_tc_format.store(format, std::memory_order_release);
+  return PBK_OK;
+}
+
 size_t pbk_hamming_tc_signs_bytes(int64_t n) {
   if (n < 0) n = 0;
-  return (size_t)pbk::tc_pad(n) * pbk::kTcRowBytes;
+  return (size_t)pbk::tc_pad(n) * pbk::tc_row_bytes();
 }
 
 int pbk_hamming_tc_expand(const uint8_t* d, int64_t n, int64_t first_row, int8_t* signs, pbk_stream_t stream) {
@@ -526,6 +462,7 @@ int pbk_hamming_tc_expand(const uint8_t* d, int64_t n, int64_t first_row, int8_t
   PBK_REQUIRE(d != nullptr && signs != nullptr, PBK_EINVAL, "NULL device pointer");
   PBK_REQUIRE(aligned16(signs), PBK_EALIGN, "device pointers must be 16-byte aligned");
   const long long np = tc_pad(n);
+  if (tc_format() == 4) return hamming_tc4_expand(d, n, first_row, np, signs, as_stream(stream));
   const long long blocks = ((np - first_row) * kTcChunks + 255) / 256;
   PBK_REQUIRE(blocks < (1ll << 31), PBK_EINVAL, "too many rows for one call");
   hamming_tc_expand_kernel<false><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(d, n, first_row, np,
@@ -540,13 +477,15 @@ int pbk_hamming_tc_peak_probe(int iters, uint32_t* sink, double* macs_per_launch
   const DeviceInfo* di;
   int rc = current_device_info(&di);
   if (rc) return rc;
+  // one iteration = all 256 bits of 128 x 128 descriptor pairs in either format
+  if (macs_per_launch) *macs_per_launch = (double)iters * 8.0 * kTcM * kTcN * 32.0 * di->sm_count;
+  if (tc_format() == 4) return hamming_tc4_peak(iters, sink, di, as_stream(stream));
   constexpr int smem = 2 * kTcM * 256;
   static KernelCache kc;
   rc = kc.setup(di, hamming_tc_peak_kernel, 128, smem, nullptr);
   if (rc) return rc;
   hamming_tc_peak_kernel<<<di->sm_count, 128, smem, as_stream(stream)>>>(iters, sink);
   PBK_CHECK_LAUNCH("hamming_tc_peak_kernel");
-  if (macs_per_launch) *macs_per_launch = (double)iters * 8.0 * kTcM * kTcN * 32.0 * di->sm_count;
   return PBK_OK;
 }
 

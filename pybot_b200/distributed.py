@@ -136,10 +136,13 @@ class ShardedKeyframeMatcher(object):
         self.fused = exchange == "p2p" and self.world > 1
         self._px = None
         # large shards are scanned on the tensor cores: keep the expanded copy resident
+        # (in the format selected NOW - ops.hamming_tc_format(); scans check it has not changed)
         self.signs = None
+        self.signs_format = 0
         if cuda_path and int(shard.shape[0]) > 0:
             from . import ops
             if ops.hamming_engine(int(shard.shape[0])) == "tc":
+                self.signs_format = ops.hamming_tc_format()
                 self.signs = ops.hamming_tc_expand(shard)
 
     def use_exchange(self, px):
@@ -153,7 +156,15 @@ class ShardedKeyframeMatcher(object):
         if self._px is not None:
             self._px.check()
 
+    def _check_format(self):
+        if self.signs is not None:
+            from . import ops
+            if ops.hamming_tc_format() != self.signs_format:
+                raise RuntimeError("the tensor-core format changed after this shard was expanded "
+                                   "(expanded in %d, now %d)" % (self.signs_format, ops.hamming_tc_format()))
+
     def local_keys(self, q):
+        self._check_format()
         if self.signs is not None:
             return self.kernels.knn2(q, self.shard, self.shard_base, self.signs)
         return self.kernels.knn2(q, self.shard, self.shard_base)
@@ -181,6 +192,7 @@ class ShardedKeyframeMatcher(object):
             self._px = PeerKeyExchange(nq, self.group)               # collective, once per query count
         px = self._px
         px.check()                                                   # a timeout of the previous call
+        self._check_format()
         px.seq += 1
         L, s = _ffi.lib(), _ffi.stream_ptr()
         splits, nbytes = ctypes.c_int(0), ctypes.c_size_t(0)

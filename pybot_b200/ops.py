@@ -412,7 +412,7 @@ TC_MIN_ROWS = 1 << 16        # below this the integer-pipe kernel's latency wins
 
 
 def hamming_engine(nt):
-    """'tc' (tcgen05 int8 scan over the expanded database) or 'popc' (integer-pipe kernel).
+    """'tc' (tcgen05 scan over the expanded database) or 'popc' (integer-pipe kernel).
     PBK_HAMMING_ENGINE=popc|tc forces one; by default databases of >= 65536 rows take the
     tensor-core route.  Both return bit-identical keys."""
     import os
@@ -422,8 +422,21 @@ def hamming_engine(nt):
     return "tc" if nt >= TC_MIN_ROWS else "popc"
 
 
+def hamming_tc_format():
+    """Encoding of the expanded descriptors the tensor-core scan reads: 4 = e2m1 nibbles for
+    tcgen05.mma kind::mxf4 (128 B per row, the default), 8 = signed bytes for kind::i8 (256 B per
+    row).  PBK_TC_FORMAT=4|8 in the environment or hamming_tc_set_format() selects it."""
+    return int(_ffi.lib().pbk_hamming_tc_format())
+
+
+def hamming_tc_set_format(fmt):
+    """Selects the encoding for buffers expanded FROM NOW ON; a resident expanded copy must be
+    scanned with the format it was expanded in (KeyframeDatabase re-expands when it differs)."""
+    _ffi.check(_ffi.lib().pbk_hamming_tc_set_format(int(fmt)))
+
+
 def hamming_tc_row_bytes():
-    """Bytes of one expanded row (the library's layout constant: 256)."""
+    """Bytes of one expanded row in the selected format (128 or 256)."""
     return int(_ffi.lib().pbk_hamming_tc_signs_bytes(512)) // 512
 
 
@@ -433,8 +446,8 @@ def hamming_tc_signs_rows(n):
 
 
 def hamming_tc_expand(t_dev, signs=None, first_row=0):
-    """(n,32) uint8 descriptors -> the expanded signed-byte copy the tensor-core scan reads (int8
-    tensor, 256 B per row, tile layout of csrc/hamming_tc.cu).  Done once per database; with
+    """(n,32) uint8 descriptors -> the expanded copy the tensor-core scan reads (int8 tensor of
+    hamming_tc_row_bytes() B per row, tile layout of csrc/hamming_tc4.cu / hamming_tc.cu).  Done once per database; with
     `signs` (a buffer of at least pbk_hamming_tc_signs_bytes(n) bytes) and first_row (a multiple
     of 512) only the rows from first_row on are (re)written - appending to a database."""
     T = _ffi.torch()
@@ -451,8 +464,8 @@ def hamming_tc_expand(t_dev, signs=None, first_row=0):
 
 
 def hamming_knn2_keys_tc(q_dev, t_signs, nt, train_base=0):
-    """Top-2 packed keys (nq,2) through the tcgen05 int8 scan; t_signs from hamming_tc_expand for
-    exactly these nt rows."""
+    """Top-2 packed keys (nq,2) through the tcgen05 scan; t_signs from hamming_tc_expand (same
+    format) for exactly these nt rows."""
     T = _ffi.torch()
     nq = int(q_dev.shape[0])
     parts, nbytes = ctypes.c_int(0), ctypes.c_size_t(0)
@@ -467,7 +480,7 @@ def hamming_knn2_keys_tc(q_dev, t_signs, nt, train_base=0):
 
 def hamming_scan_keys(q_dev, t_dev, train_base=0, signs=None):
     """Top-2 keys of q against the database t: the tensor-core scan when `signs` (the expanded
-    copy) is given or the engine rule picks it (expanding on the fly: 256 B per row written once
+    copy) is given or the engine rule picks it (expanding on the fly: 128 B per row written once
     is still cheaper than the integer-pipe scan of a large database), else the integer-pipe kernel."""
     nt = int(t_dev.shape[0])
     if nt > 0 and int(q_dev.shape[0]) > 0 and hamming_engine(nt) == "tc":

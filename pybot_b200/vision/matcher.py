@@ -98,6 +98,7 @@ class KeyframeDatabase(object):
         self.offsets = np.zeros(1, np.int64)
         self._signs = None          # expanded copy for the tensor-core scan (ops.hamming_tc_expand)
         self._signs_n = 0           # rows it is valid for
+        self._signs_fmt = 0         # ops.hamming_tc_format() it was expanded in
 
     def reserve(self, rows):
         """Make room for `rows` descriptors in total (e.g. the expected session length)."""
@@ -156,12 +157,15 @@ class KeyframeDatabase(object):
         return self._buf[:self._n]
 
     def signs(self):
-        """The expanded (256 B per row) copy the tensor-core scan reads, or None when this
+        """The expanded copy (128 B per row, e2m1) the tensor-core scan reads, or None when this
         database takes the integer-pipe route (small, or PBK_HAMMING_ENGINE=popc).  Kept
         resident and extended in place: an append only expands the rows from the last whole
         block of 512 on."""
         if self._n == 0 or ops.hamming_engine(self._n) != "tc":
             return None
+        fmt = ops.hamming_tc_format()
+        if self._signs_fmt != fmt:                   # expanded in the other encoding: start over
+            self._signs, self._signs_n, self._signs_fmt = None, 0, fmt
         if self._signs_n == self._n:
             return self._signs
         T = _ffi.require_cuda()

@@ -22,6 +22,10 @@ __global__ void __launch_bounds__(256) probe(int iters, uint32_t* sink) {
         if (MODE == 4) { asm volatile("min.s16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i])); asm volatile("max.s16x2 %0, %0, %1;" : "+r"(b[i]) : "r"(a[i])); }
         if (MODE == 5) { asm volatile("min.bf16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i])); asm volatile("max.bf16x2 %0, %0, %1;" : "+r"(b[i]) : "r"(a[i])); }
         if (MODE == 6) { asm volatile("lop3.b32 %0, %0, %1, %1, 0x96;" : "+r"(a[i]) : "r"(b[i])); asm volatile("lop3.b32 %0, %0, %1, %1, 0xe8;" : "+r"(b[i]) : "r"(a[i])); }
+        if (MODE == 8) { asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(*(float*)&a[i]) : "f"(*(float*)&b[i]), "f"(*(float*)&a[(i + 1) & 7])); asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(*(float*)&b[i]) : "f"(*(float*)&a[i]), "f"(*(float*)&b[(i + 1) & 7])); }
+        if (MODE == 9) { a[i] = (uint32_t)min(min((int)a[i], (int)b[i]), (int)a[(i + 1) & 7]); b[i] = (uint32_t)max(max((int)b[i], (int)a[i]), (int)b[(i + 1) & 7]); asm volatile("" : "+r"(a[i]), "+r"(b[i])); }
+        if (MODE == 10) { asm volatile("prmt.b32 %0, %0, %1, 0x7632;" : "+r"(a[i]) : "r"(b[i])); asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(b[i]) : "r"(a[i])); }
+        if (MODE == 11) { asm volatile("min.s32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i])); asm volatile("max.s32 %0, %0, %1;" : "+r"(b[i]) : "r"(a[i])); }
         if (MODE == 7) { asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(a[i]) : "r"(b[i])); asm volatile("mad.lo.u32 %0, %0, %1, %1;" : "+r"(b[i]) : "r"(a[i])); }
       }
     }
@@ -63,6 +67,10 @@ int main() {
   run<3>("minmax.f32", sink, sms);
   run<6>("lop3", sink, sms);
   run<7>("imad", sink, sms);
+  run<8>("minmax3.f32", sink, sms);
+  run<9>("minmax3.s32", sink, sms);
+  run<10>("prmt", sink, sms);
+  run<11>("minmax.s32", sink, sms);
   cudaDeviceSynchronize();
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;

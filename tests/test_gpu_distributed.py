@@ -49,14 +49,23 @@ def _emulated_matchers(db, per_kf, nkf, nq, world):
     return ms, [torch.cuda.Stream() for _ in range(world)]
 
 
-@pytest.mark.parametrize("engine", ["popc", "tc"])
+@pytest.fixture
+def restore_tc_format():
+    from pybot_b200 import ops
+    before = ops.hamming_tc_format()
+    yield
+    ops.hamming_tc_set_format(before)
+
+
+@pytest.mark.parametrize("engine", ["popc", "tc", "tc8"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_fused_key_and_row_exchange_protocol_on_one_gpu(world, engine, monkeypatch):
+def test_fused_key_and_row_exchange_protocol_on_one_gpu(world, engine, monkeypatch, restore_tc_format):
     """Both fused exchanges (top-2 keys, matched rows) with all ranks on one device: every rank's
     result is bit-identical to the single-GPU scan of the whole database, frame after frame."""
     import torch
     from pybot_b200 import ops, synthetic as syn
-    monkeypatch.setenv("PBK_HAMMING_ENGINE", engine)
+    monkeypatch.setenv("PBK_HAMMING_ENGINE", engine[:2] if engine != "popc" else engine)
+    ops.hamming_tc_set_format(8 if engine == "tc8" else 4)
     per_kf, nkf, nq = 1000, 37, 777
     q, db = syn.c3_database(nq=nq, n_keyframes=nkf, per_kf=per_kf, n_revisit=3)
     db[30_123] = db[123]                                   # duplicate across shards: tie on the global row

@@ -10,12 +10,18 @@ from pybot_b200 import synthetic as syn
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["popc", "tc"])
+@pytest.fixture(autouse=True, params=["popc", "tc", "tc8"])
 def engine(request, monkeypatch):
-    """Every test of this file runs on both scan engines: the integer-pipe kernel and the
-    tcgen05 int8 kernel (forced here even for tiny databases and the reverse pass)."""
-    monkeypatch.setenv("PBK_HAMMING_ENGINE", request.param)
-    return request.param
+    """Every test of this file runs on all three scan engines: the integer-pipe kernel, the
+    tcgen05 kind::mxf4 kernel ("tc": the default expanded format, 4) and the tcgen05 kind::i8
+    kernel ("tc8": format 8) - the tensor-core ones forced here even for tiny databases and the
+    reverse pass."""
+    from pybot_b200 import ops
+    monkeypatch.setenv("PBK_HAMMING_ENGINE", request.param[:2] if request.param != "popc" else "popc")
+    before = ops.hamming_tc_format()
+    ops.hamming_tc_set_format(8 if request.param == "tc8" else 4)
+    yield request.param
+    ops.hamming_tc_set_format(before)
 
 
 @pytest.fixture(scope="module")

@@ -1,12 +1,22 @@
-"""GPU parity of the tensor-core (tcgen05 kind::i8) Hamming scan: its top-2 keys must be
-bit-identical to the integer-pipe kernel's (itself pinned to cv2.BFMatcher and the C oracle in
-tests/test_gpu_hamming.py) and to the oracle directly."""
+"""GPU parity of the tensor-core Hamming scans (tcgen05 kind::mxf4 over e2m1 nibbles - format 4,
+the default - and kind::i8 over signed bytes - format 8): their top-2 keys must be bit-identical
+to the integer-pipe kernel's (itself pinned to cv2.BFMatcher and the C oracle in
+tests/test_gpu_hamming.py) and to the oracle directly.  Every test runs in both formats."""
 import numpy as np
 import pytest
 
 from pybot_b200 import synthetic as syn
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=[4, 8], ids=["mxf4", "i8"])
+def tc_format(request):
+    from pybot_b200 import ops
+    before = ops.hamming_tc_format()
+    ops.hamming_tc_set_format(request.param)
+    yield request.param
+    ops.hamming_tc_set_format(before)
 
 
 def _keys_both(q, t, base=0):
@@ -20,24 +30,34 @@ def _keys_both(q, t, base=0):
     return a.cpu().numpy(), b.cpu().numpy()
 
 
-def test_expansion_layout():
-    """Train rows, tile by tile (128 rows): bit k of row r -> byte (r/128)*32768 + (k/16)*2048 + (r%128)*16
-    + k%16 = -64 / +64; rows past the end are zero."""
+def test_expansion_layout(tc_format):
+    """Train rows, tile by tile (128 rows).  Format 8: bit k of row r -> byte (r/128)*32768 + (k/16)*2048
+    + (r%128)*16 + k%16 = -64 / +64.  Format 4: nibble k%2 of byte (r/128)*16384 + (k/32)*2048 + (r%128)*16
+    + (k%32)/2 = e2m1 -1 (0xA) / +1 (0x2).  Rows past the end are zero."""
     import torch
     from pybot_b200 import ops
     rng = np.random.default_rng(0)
     n = 300
     d = rng.integers(0, 256, (n, 32), dtype=np.uint8)
     s = ops.hamming_tc_expand(torch.from_numpy(d).cuda()).cpu().numpy()
-    assert ops.hamming_tc_row_bytes() == 256
-    assert s.dtype == np.int8 and s.size == 512 * 256
+    rb = 256 if tc_format == 8 else 128
+    assert ops.hamming_tc_row_bytes() == rb
+    assert s.dtype == np.int8 and s.size == 512 * rb
     bits = np.unpackbits(d, axis=1, bitorder="little").astype(np.int16)                  # (n, 256)
     r, k = np.meshgrid(np.arange(n), np.arange(256), indexing="ij")
-    addr = (r // 128) * 32768 + (k // 16) * 2048 + (r % 128) * 16 + k % 16
-    assert np.array_equal(s[addr], np.where(bits == 1, -64, 64))
     rows = np.arange(512)
-    base = (rows // 128) * 32768 + (rows % 128) * 16
-    assert not s[base[n:, None] + (np.arange(16) * 2048)[None, :]].any()                 # pad rows are zero
+    if tc_format == 8:
+        addr = (r // 128) * 32768 + (k // 16) * 2048 + (r % 128) * 16 + k % 16
+        assert np.array_equal(s[addr], np.where(bits == 1, -64, 64))
+        base = (rows // 128) * 32768 + (rows % 128) * 16
+        assert not s[base[n:, None] + (np.arange(16) * 2048)[None, :]].any()             # pad rows are zero
+    else:
+        addr = (r // 128) * 16384 + (k // 32) * 2048 + (r % 128) * 16 + (k % 32) // 2
+        nib = (s.view(np.uint8)[addr] >> (4 * (k % 2))) & 15
+        assert np.array_equal(nib, np.where(bits == 1, 0xA, 0x2))
+        base = (rows // 128) * 16384 + (rows % 128) * 16
+        pad = base[n:, None, None] + (np.arange(8) * 2048)[None, :, None] + np.arange(16)[None, None, :]
+        assert not s[pad].any()                                                          # pad rows are zero
     # appending: expanding only from the last whole block of 512 rows gives the same buffer
     d2 = rng.integers(0, 256, (1500, 32), dtype=np.uint8)
     whole = ops.hamming_tc_expand(torch.from_numpy(d2).cuda())
@@ -46,6 +66,22 @@ def test_expansion_layout():
     grown[:part.numel()] = part
     ops.hamming_tc_expand(torch.from_numpy(d2).cuda(), grown, first_row=512)
     assert torch.equal(grown, whole)
+
+
+def test_queries_expand_with_the_opposite_sign(tc_format):
+    """A query equal to a train row must come out at distance 0 and its complement at 256 (the two
+    ends of the accumulator range of either format)."""
+    import torch
+    from pybot_b200 import ops
+    rng = np.random.default_rng(5)
+    t = rng.integers(0, 256, (1000, 32), dtype=np.uint8)
+    q = np.stack([t[17], ~t[900], t[999]])
+    a, b = _keys_both(q, t)
+    assert np.array_equal(a, b)
+    assert (a[0, 0] >> 32, a[0, 0] & 0xFFFFFFFF) == (0, 17) and (a[2, 0] >> 32, a[2, 0] & 0xFFFFFFFF) == (0, 999)
+    t2 = np.repeat(t[900:901], 200, axis=0)                                              # every row at distance 256
+    a2, b2 = _keys_both(q[1:2], t2)
+    assert np.array_equal(a2, b2) and (a2[0, 0] >> 32, a2[0, 1] >> 32) == (256, 256)
 
 
 @pytest.mark.parametrize("nq,nt", [(1, 1), (5, 3), (128, 128), (300, 1000), (512, 129), (513, 4096 + 77),
