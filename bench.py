@@ -315,7 +315,7 @@ def probe_peaks(D):
         b.record()
         torch.cuda.synchronize()
         tc_best = max(tc_best, n / (a.elapsed_time(b) * 1e-3))
-    return {"popc_per_s": best, "sm_count": sms, "int8_mac_per_s": tc_best}
+    return {"popc_per_s": best, "sm_count": sms, "tc_mac_per_s": tc_best}
 
 
 # ------------------------------------------------------------ workload C3
@@ -362,7 +362,10 @@ def run_c3(D, args):
         rev = ops.hamming_knn2_keys(rows, q_dev, 0)
         return ops.hamming_ratio_mutual(keys, rev, 0.75)
 
-    engine = "tcgen05 kind::i8 (hamming_tc_kernel)" if m.signs is not None else "integer pipe (hamming_knn2_kernel<2,4>)"
+    tc_fmt = ops.hamming_tc_format()
+    tc_kernel = "hamming_tc4_kernel" if tc_fmt == 4 else "hamming_tc_kernel"
+    tc_kind = "kind::mxf4 (e2m1 x e2m1 -> f32, unit block scales)" if tc_fmt == 4 else "kind::i8 (s8 x s8 -> s32)"
+    engine = ("tcgen05 %s (%s)" % (tc_kind.split(" ")[0], tc_kernel)) if m.signs is not None else "integer pipe (hamming_knn2_kernel<2,4>)"
     sampler = ClockSampler(D.local).start() if D.rank == 0 else None
     total_ms, knn_ms = timed_steps(D, step, args.steps, args.warmup, flush)
     clocks = sampler.stop() if sampler else None
@@ -387,6 +390,29 @@ def run_c3(D, args):
         variants["integer_pipe_kernel_same_shard"] = {
             "Gpairs_per_s": float(nq) * float(shard.shape[0]) / (popc_ms * 1e-3) / 1e9, "kernel_ms": popc_ms,
             "keys_equal_tensor_core_keys": bool(torch.equal(keys_tc, step_popc(None)))}
+        # ... and the OTHER tensor-core format (kind::i8 when the default kind::mxf4 is selected)
+        other = 8 if tc_fmt == 4 else 4
+        ops.hamming_tc_set_format(other)
+        try:
+            signs_o = ops.hamming_tc_expand(shard)
+
+            def step_other(rec):
+                a, b = ev_pair(torch)
+                a.record()
+                k = ops.hamming_knn2_keys_tc(q_dev, signs_o, int(shard.shape[0]), m.shard_base)
+                b.record()
+                if rec is not None:
+                    rec.append((a, b))
+                return k
+            _, o_ms = timed_steps(D, step_other, max(3, args.steps // 2), args.warmup, flush)
+            o_ms /= max(3, args.steps // 2)
+            variants["tcgen05_%s_same_shard" % ("kind_i8" if other == 8 else "kind_mxf4")] = {
+                "Gpairs_per_s": float(nq) * float(shard.shape[0]) / (o_ms * 1e-3) / 1e9, "kernel_ms": o_ms,
+                "expanded_row_bytes": ops.hamming_tc_row_bytes(),
+                "keys_equal_default_engine_keys": bool(torch.equal(keys_tc, step_other(None)))}
+            del signs_o
+        finally:
+            ops.hamming_tc_set_format(tc_fmt)
     if D.world > 1:
         m_nccl = ShardedKeyframeMatcher(shard, lo_kf * per_kf, exchange="nccl")
 
@@ -419,7 +445,8 @@ def run_c3(D, args):
         "metric": "hamming_knn_k2_ratio_mutual", "unit": "Gpairs/s",
         "value": pairs * args.steps / (total_ms * 1e-3) / 1e9,
         "ms_per_step": total_ms / args.steps, "scaling": "strong",
-        "dtype": "s8 x s8 -> s32 (tcgen05.mma kind::i8), u16 min/max" if m.signs is not None else "u32 (xor/popc/int-min)",
+        "dtype": ("%s (tcgen05.mma), %s" % (tc_kind, "f32 min3" if tc_fmt == 4 else "s16x2 min/max"))
+                 if m.signs is not None else "u32 (xor/popc/int-min)",
         "engine": engine,
         "config": {"workload": "C3 loop-closure: 2000 ORB queries vs %d keyframes x 2000 "
                                "(%d descriptors, %d MB), k=2 + ratio 0.75 + mutual; database sharded by "
@@ -427,7 +454,7 @@ def run_c3(D, args):
                    "nq": nq, "nt": nt_total, "shard_rows": int(shard.shape[0]),
                    "l2": L2_NOTE,
                    "state": "database resident in HBM (compact rows%s); queries are the per-step input"
-                            % (" + the 256 B/row expanded copy the tensor-core scan reads" if m.signs is not None else "")},
+                            % (" + the %d B/row expanded copy the tensor-core scan reads" % ops.hamming_tc_row_bytes() if m.signs is not None else "")},
         "e2e": {"value": pairs * args.steps / (e2e_ms * 1e-3) / 1e9, "unit": "Gpairs/s",
                 "h2d_bytes_per_step": nq * 32,
                 "d2h_bytes_per_step": nq * (2 * 8 + 2 * 4 + 3),
@@ -493,23 +520,26 @@ def run_c3(D, args):
                                    Gpairs_per_s_kernel=pair_rate / 1e9)
         else:
             bf16, bf16_src = measured_bf16()
-            int8_peak = 2.0 * pk["int8_mac_per_s"] / 1e12   # TOP/s, measured in this run (burst, ~1 ms launches)
+            tc_peak = 2.0 * pk["tc_mac_per_s"] / 1e12    # TOP/s, measured in this run (burst, ~1 ms launches)
             tops = pair_rate * 256 * 2 / 1e12            # algorithmic: 256 multiply-adds per 256-bit pair
+            nominal = 9000.0 if tc_fmt == 4 else 4500.0
             res["roofline"] = {
-                "bound": "tensor", "kernel": "hamming_tc_kernel (tcgen05.mma kind::i8, + query expansion and split merge)",
-                "achieved": tops, "peak": int8_peak, "unit": "TOP/s", "frac": tops / int8_peak,
-                "frac_issued": tops / int8_peak,
-                "frac_of_nominal_4500": tops / 4500.0,
-                "frac_of_2x_measured_bf16": tops / (2.0 * bf16),
-                "peak_source": "pbk_hamming_tc_peak_probe, measured in this run: back-to-back tcgen05.mma kind::i8 of the "
-                               "kernel's shape (M 128, N 128, K 32) on one CTA per SM, no data movement (burst; nominal "
-                               "dense int8 = 4500 TOP/s; 2 x the dense bf16 of %s = %.0f TOP/s)" % (bf16_src, 2.0 * bf16),
-                "algorithmic": "256 int8 multiply-adds (2 ops each) per descriptor pair: the dot product of the +-1 "
-                               "expansions is 256 - 2 d, and the kernel issues exactly those (8 K steps of 32): "
-                               "frac_issued = frac",
-                "traffic": ncu_traffic("hamming_tc_kernel", scale=float(shard.shape[0]) / 2.5e6),
-                "traffic_source": ncu_traffic_note("hamming_tc_kernel", scale=float(shard.shape[0]) / 2.5e6),
-                "traffic_stale": ncu_traffic_stale("hamming_tc.cu"),
+                "bound": "tensor", "kernel": "%s (tcgen05.mma %s, + query expansion and split merge)" % (tc_kernel, tc_kind.split(" ")[0]),
+                "achieved": tops, "peak": tc_peak, "unit": "TOP/s", "frac": tops / tc_peak,
+                "frac_issued": tops / tc_peak,
+                "frac_of_nominal_%d" % int(nominal): tops / nominal,
+                "frac_of_%dx_measured_bf16" % (4 if tc_fmt == 4 else 2): tops / ((4.0 if tc_fmt == 4 else 2.0) * bf16),
+                "peak_source": "pbk_hamming_tc_peak_probe, measured in this run: back-to-back tcgen05.mma %s of the "
+                               "kernel's shape (M 128, N 128, K %d) on one CTA per SM, no data movement (burst; nominal "
+                               "dense %s = %.0f TOP/s; %d x the dense bf16 of %s = %.0f TOP/s)"
+                               % (tc_kind.split(" ")[0], 64 if tc_fmt == 4 else 32, "fp4" if tc_fmt == 4 else "int8", nominal,
+                                  4 if tc_fmt == 4 else 2, bf16_src, (4.0 if tc_fmt == 4 else 2.0) * bf16),
+                "algorithmic": "256 multiply-adds (2 ops each) per descriptor pair: the dot product of the +-1 "
+                               "expansions is 2 d - 256 (mxf4) / 128 d - 16384 (i8), and the kernel issues exactly those "
+                               "(%s): frac_issued = frac" % ("4 K steps of 64" if tc_fmt == 4 else "8 K steps of 32"),
+                "traffic": ncu_traffic(tc_kernel, scale=float(shard.shape[0]) / 2.5e6),
+                "traffic_source": ncu_traffic_note(tc_kernel, scale=float(shard.shape[0]) / 2.5e6),
+                "traffic_stale": ncu_traffic_stale("hamming_tc4.cu" if tc_fmt == 4 else "hamming_tc.cu"),
                 "kernel_ms": knn_ms / args.steps, "kernel_share_of_step": knn_ms / total_ms,
                 "Gpairs_per_s_kernel": pair_rate / 1e9,
                 "integer_pipe_kernel": dict(

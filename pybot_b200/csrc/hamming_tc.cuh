@@ -104,7 +104,7 @@ struct HammingTcParams {
   long long rows_per_split;       // multiple of kTcN
   unsigned long long train_base;
   int splits;
-  int dbg;                        // PBK_TC_DEBUG timing probes, bits (results are then wrong): 1 = no selection, 2 = no MMA, 4 = no TMEM load (mxf4 kernel)
+  int dbg;                        // PBK_TC_DEBUG timing probes, bits (results are then wrong): 1 = no selection, 2 = no MMA, 4 = no TMEM load, 8 = no tile loads (mxf4 kernel)
 };
 
 

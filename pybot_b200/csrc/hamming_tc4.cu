@@ -50,11 +50,11 @@ constexpr int kT4BlockBytes = kTcM * kTc4RowBytes;  // 16 KB
 #define PBK_T4_STAGES 8
 #endif
 constexpr int kT4Stages = PBK_T4_STAGES;
-#ifndef PBK_T4_SPIN
-#define PBK_T4_SPIN 0
+#ifndef PBK_T4_SPIN_ISSUER
+#define PBK_T4_SPIN_ISSUER 0
 #endif
-#ifndef PBK_T4_EARLY
-#define PBK_T4_EARLY 1
+#ifndef PBK_T4_SPIN_EPI
+#define PBK_T4_SPIN_EPI 0
 #endif
 constexpr int kT4Slots = 3;
 constexpr int kT4SfCol = 384;                       // first of 64 TMEM columns of 0x7F scale bytes
@@ -228,7 +228,7 @@ hamming_tc4_kernel(const __grid_constant__ HammingTcParams P) {
       const int8_t* src = P.t_signs + (size_t)row0 * kTc4RowBytes;
       for (int t = 0; t < kTcPrefetch && t < ntiles; ++t)
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (size_t)t * kT4TileBytes), "r"(kT4TileBytes) : "memory");
-      for (int t = 0; t < ntiles; ++t) {
+      for (int t = 0; t < ntiles && !(P.dbg & 8); ++t) {
         const int s = t % kT4Stages;
         if (t + kTcPrefetch < ntiles)
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (size_t)(t + kTcPrefetch) * kT4TileBytes), "r"(kT4TileBytes) : "memory");
@@ -256,16 +256,22 @@ hamming_tc4_kernel(const __grid_constant__ HammingTcParams P) {
       for (int item = slot; item < nitems; item += kT4Slots, ++use) {
         const int t = item >> 2, mb = item & 3;
         const int s = t % kT4Stages;
-        mbar_wait_parked(&b_full[s], (uint32_t)((t / kT4Stages) & 1));
-        if (use > 0) mbar_wait_parked(&acc_empty[slot], (uint32_t)((use - 1) & 1));
-        tc_fence_after();
         const uint64_t ad = tc_smem_desc(a_addr + mb * kT4BlockBytes), bd = tc_smem_desc(b_addr + s * kT4TileBytes);
+        uint64_t* const full_bar = &acc_full[(item & 1) * kT4Slots + slot];
+#if PBK_T4_SPIN_ISSUER
+        if (!(P.dbg & 8)) mbar_wait(&b_full[s], (uint32_t)((t / kT4Stages) & 1));
+        if (use > 0) mbar_wait(&acc_empty[slot], (uint32_t)((use - 1) & 1));
+#else
+        if (!(P.dbg & 8)) mbar_wait_parked(&b_full[s], (uint32_t)((t / kT4Stages) & 1));
+        if (use > 0) mbar_wait_parked(&acc_empty[slot], (uint32_t)((use - 1) & 1));
+#endif
+        tc_fence_after();
         if (!(P.dbg & 2)) {
 #pragma unroll
           for (int k = 0; k < kT4KSteps; ++k)              // K = 64 elements = two planes: +4096 B = +256 in the address field
             tc_mma_mxf4(d, ad + (uint64_t)(k * 256), bd + (uint64_t)(k * 256), k > 0 ? 1u : 0u, sfa, sfb);
         }
-        tc_commit(&acc_full[(item & 1) * kT4Slots + slot]);
+        tc_commit(full_bar);
         tc_commit(&b_empty[s]);                       // one of the four arrivals (one per query block) that free the stage
       }
     }
@@ -284,13 +290,19 @@ hamming_tc4_kernel(const __grid_constant__ HammingTcParams P) {
     float v[64];
     int slot = set, use = 0;                          // item % 3, item / 3 of the current item (item = set, set + 2, ...)
     auto step = [&](int item, uint32_t& k1, uint32_t& k2) {
+      const uint32_t taddr = lane_addr + (uint32_t)(slot * kTcN);
+      uint64_t* const empty_bar = &acc_empty[slot];
+#if PBK_T4_SPIN_EPI
+      mbar_wait(&acc_full[set * kT4Slots + slot], (uint32_t)((use >> 1) & 1));
+#else
       mbar_wait_parked(&acc_full[set * kT4Slots + slot], (uint32_t)((use >> 1) & 1));   // the (set, slot) pair recurs every 6 items
+#endif
       tc_fence_after();
-      if (!(P.dbg & 4)) tc_ld64_f32(lane_addr + (uint32_t)(slot * kTcN), v);
+      if (!(P.dbg & 4)) tc_ld64_f32(taddr, v);
       tc_ld_wait();                                   // the values are in registers: the slot goes back to its issuer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[slot]);
+      if (lane == 0) mbar_arrive(empty_bar);
       if (!(P.dbg & 1)) tc4_select(v, (uint32_t)(item >> 2) * kTcN, (uint32_t)rows, (uint32_t)h, k1, k2);
       else k1 ^= __float_as_uint(v[0]) ^ __float_as_uint(v[63]) ^ __float_as_uint(v[17]);
       slot += 2;                                      // the set's next item is item + 2

@@ -42,7 +42,8 @@ FULL_METRICS = [
 
 PROBLEMS = {
     "hamming_knn2_kernel": "2000 queries x 2.5M rows (one 8-GPU shard of C3)",
-    "hamming_tc_kernel": "2000 queries x 2.5M rows (one 8-GPU shard of C3), tcgen05 kind::i8",
+    "hamming_tc_kernel": "2000 queries x 2.5M rows (one 8-GPU shard of C3), tcgen05 kind::i8 (format 8)",
+    "hamming_tc4_kernel": "2000 queries x 2.5M rows (one 8-GPU shard of C3), tcgen05 kind::mxf4 (format 4, default)",
     "project_points_kernel": "C2: 10M float32 points",
     "project_compact_kernel": "C2: 10M float32 points, bounds+depth masks, 73.7 % valid",
     "transform_points_kernel": "C2: 10M float32 points -> float64",

@@ -61,7 +61,12 @@ if which in ("hamming", "all"):
     db = torch.randint(0, 256, (nt, 32), device="cuda", dtype=torch.uint8, generator=g)
     timed("hamming", lambda: ops.hamming_knn2_keys(q, db, 0))
     signs = ops.hamming_tc_expand(db)
-    timed("hamming_tc", lambda: ops.hamming_knn2_keys_tc(q, signs, nt, 0))
+    timed("hamming_tc (format %d)" % ops.hamming_tc_format(), lambda: ops.hamming_knn2_keys_tc(q, signs, nt, 0))
+    other = 8 if ops.hamming_tc_format() == 4 else 4
+    ops.hamming_tc_set_format(other)
+    signs_o = ops.hamming_tc_expand(db)
+    timed("hamming_tc (format %d)" % other, lambda: ops.hamming_knn2_keys_tc(q, signs_o, nt, 0))
+    ops.hamming_tc_set_format(12 - other)
     del db, signs
 
 if which in ("project", "compact", "transform", "all"):

@@ -24,7 +24,7 @@ echo "launch list rc=$?"
 PROF="python scripts/prof_kernels.py all 1"
 $PROF > $OUT/${TAG}_prof_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on \
-    -k regex:'hamming_knn2_kernel|hamming_tc_kernel|project_points|project_compact|transform_points|ba_residual|reproject_dense|depth_reconstruct_dense|sceneflow_scatter' \
+    -k regex:'hamming_knn2_kernel|hamming_tc4?_kernel|project_points|project_compact|transform_points|ba_residual|reproject_dense|depth_reconstruct_dense|sceneflow_scatter' \
     -c 24 -f -o $OUT/${TAG}_full $PROF > $OUT/${TAG}_ncu_full.log 2>&1
 echo "full capture rc=$?"
 ncu -i $OUT/${TAG}_full.ncu-rep --page raw --csv > $OUT/${TAG}_full_raw.csv 2>/dev/null

@@ -45,7 +45,8 @@ for fmt in (8, 4):
     # timing probes (results are wrong): 1 = no selection, 2 = no MMA
     modes = ((1, "no selection"), (2, "no MMA"))
     if fmt == 4 and "--more" in sys.argv:
-        modes += ((3, "no MMA, no selection"), (6, "no MMA, no TMEM load"), (7, "barrier handshake only"), (5, "MMA + handshake only"))
+        modes += ((3, "no MMA, no selection"), (7, "barrier handshake only"), (5, "MMA + handshake only"),
+                  (15, "handshake, no tile loads"), (13, "MMA + handshake, no loads"), (10, "selection, no MMA, no loads"), (8, "all but tile loads"))
     for dbg, what in modes:
         os.environ["PBK_TC_DEBUG"] = str(dbg)
         timed("  %s" % what, lambda: ops.hamming_knn2_keys_tc(q, signs, nt, 0), reps=3)

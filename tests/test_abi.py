@@ -65,6 +65,22 @@ def test_sass_of_the_shipped_matcher_and_ba_kernels():
     assert len(pre) == 1 and "PREEXIT" in pre[0]                 # griddepcontrol.launch_dependents
 
 
+def test_sass_of_the_tensor_core_matchers():
+    """The two tensor-core scans are tcgen05 code: UTCOMMA (kind::mxf4, block-scaled FP4) with fp32
+    accumulators read back by LDTM and pre-filtered with 3-input minima in the default engine,
+    UTCIMMA (kind::i8) with packed 16-bit selection in the other; both fed by 1-D TMA bulk copies."""
+    import subprocess
+    from pybot_b200 import _ffi
+    out = subprocess.run(["cuobjdump", "-sass", _ffi.LIB_PATH], capture_output=True, text=True).stdout
+    funcs = out.split("Function : ")
+    f4 = [f for f in funcs if "hamming_tc4_kernel" in f.split("\n", 1)[0]]
+    i8 = [f for f in funcs if "hamming_tc_kernel" in f.split("\n", 1)[0]]
+    assert len(f4) == 1 and len(i8) == 1
+    assert f4[0].count("UTCOMMA") == 4 and "LDTM.x64" in f4[0] and "UBLKCP" in f4[0] and "UTCBAR" in f4[0]
+    assert f4[0].count("FMNMX3") >= 31 and "STTM" in f4[0]      # min tree; the unit scale bytes written to TMEM
+    assert i8[0].count("UTCIMMA") == 8 and "LDTM" in i8[0] and "VIMNMX.S16x2" in i8[0]
+
+
 def test_compute_without_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():
