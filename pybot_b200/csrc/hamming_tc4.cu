@@ -50,9 +50,6 @@ constexpr int kT4BlockBytes = kTcM * kTc4RowBytes;  // 16 KB
 #define PBK_T4_STAGES 8
 #endif
 constexpr int kT4Stages = PBK_T4_STAGES;
-#ifndef PBK_T4_SPIN_ISSUER
-#define PBK_T4_SPIN_ISSUER 0
-#endif
 #ifndef PBK_T4_SPIN_EPI
 #define PBK_T4_SPIN_EPI 0
 #endif
@@ -124,6 +121,11 @@ __device__ __forceinline__ void tc_ld64_f32(uint32_t taddr, float (&r)[64]) {
       : "memory");
 }
 #undef PBK_F8
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float tc_min3(float a, float b, float c) {
   float r;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -141,8 +143,12 @@ __device__ __forceinline__ void tc4_insert(float acc, uint32_t row, uint32_t row
   tc_top2(k1, k2, key);
 }
 
+// acc threshold of a query: rows arrive in ascending order, so only a distance BELOW the current
+// second best d2 = k2 >> 23 (>= the true one; 511 while unset) can enter: acc = 2 d - 256 < 2 d2 - 256
+__device__ __forceinline__ float tc4_threshold(uint32_t k2) { return (float)(2 * (int)(k2 >> 23) - 256); }
+
 __device__ __forceinline__ void tc4_select(const float (&v)[64], uint32_t tile_base, uint32_t rows, uint32_t h,
-                                           uint32_t& k1, uint32_t& k2) {
+                                           uint32_t& k1, uint32_t& k2, float& thr) {
   // minima of seven groups of nine columns (+ column 63), then of the item: 32 FMNMX3 / FMNMX
   float g[7];
 #pragma unroll
@@ -150,9 +156,6 @@ __device__ __forceinline__ void tc4_select(const float (&v)[64], uint32_t tile_b
     g[i] = tc_min3(tc_min3(v[9 * i], v[9 * i + 1], v[9 * i + 2]), tc_min3(v[9 * i + 3], v[9 * i + 4], v[9 * i + 5]),
                    tc_min3(v[9 * i + 6], v[9 * i + 7], v[9 * i + 8]));
   const float best = fminf(tc_min3(tc_min3(g[0], g[1], g[2]), tc_min3(g[3], g[4], g[5]), g[6]), v[63]);
-  // k2 = d2 (2^23 + 1) + row: k2 >> 23 >= d2, the second-best distance so far (511 while
-  // unset).  A later row only enters with a distance BELOW d2: acc = 2 d - 256 < 2 d2 - 256.
-  const float thr = (float)(2 * (int)(k2 >> 23) - 256);
   if (!__any_sync(0xffffffffu, best < thr)) return;
   // Rare path (some lane of the warp has a candidate; ~a fifth of the items of a 500 k-row split
   // for the 128 queries of a warp): only the groups that hold one are turned into keys - a warp
@@ -166,6 +169,7 @@ __device__ __forceinline__ void tc4_select(const float (&v)[64], uint32_t tile_b
     }
   }
   if (__any_sync(0xffffffffu, v[63] < thr)) tc4_insert(v[63], col0 + 63u, rows, k1, k2);
+  thr = tc4_threshold(k2);
 }
 
 __global__ void __launch_bounds__(kT4Threads, 1)
@@ -243,8 +247,12 @@ hamming_tc4_kernel(const __grid_constant__ HammingTcParams P) {
     // One thread per slot waits on CONSECUTIVE phases of the slot's acc_empty barrier - with the
     // items of a slot spread over several threads a thread could wait for a phase two completions
     // ahead of the barrier, which a parity wait cannot express (it returns at once).
-    if (lane == 0 && ntiles > 0) {
-      const int slot = warp - kT4MmaWarp;
+    // The WHOLE warp runs this loop with warp-uniform values (waits included) and one elected lane
+    // issues the tcgen05 instructions: under `if (lane == 0)` the compiler cannot prove the
+    // descriptors uniform and wraps every UTCOMMA / UTCBAR in an ELECT + 5 x R2UR.BROADCAST
+    // waterfall loop - ~170 instructions and ~300 clocks from "slot free" to the last MMA of an item.
+    if (ntiles > 0) {
+      const int slot = __shfl_sync(0xffffffffu, warp - kT4MmaWarp, 0);
       mbar_wait(a_full, 0);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
@@ -258,21 +266,19 @@ hamming_tc4_kernel(const __grid_constant__ HammingTcParams P) {
         const int s = t % kT4Stages;
         const uint64_t ad = tc_smem_desc(a_addr + mb * kT4BlockBytes), bd = tc_smem_desc(b_addr + s * kT4TileBytes);
         uint64_t* const full_bar = &acc_full[(item & 1) * kT4Slots + slot];
-#if PBK_T4_SPIN_ISSUER
-        if (!(P.dbg & 8)) mbar_wait(&b_full[s], (uint32_t)((t / kT4Stages) & 1));
-        if (use > 0) mbar_wait(&acc_empty[slot], (uint32_t)((use - 1) & 1));
-#else
         if (!(P.dbg & 8)) mbar_wait_parked(&b_full[s], (uint32_t)((t / kT4Stages) & 1));
         if (use > 0) mbar_wait_parked(&acc_empty[slot], (uint32_t)((use - 1) & 1));
-#endif
         tc_fence_after();
-        if (!(P.dbg & 2)) {
+        if (tc_elect_one()) {
+          if (!(P.dbg & 2)) {
 #pragma unroll
-          for (int k = 0; k < kT4KSteps; ++k)              // K = 64 elements = two planes: +4096 B = +256 in the address field
-            tc_mma_mxf4(d, ad + (uint64_t)(k * 256), bd + (uint64_t)(k * 256), k > 0 ? 1u : 0u, sfa, sfb);
+            for (int k = 0; k < kT4KSteps; ++k)            // K = 64 elements = two planes: +4096 B = +256 in the address field
+              tc_mma_mxf4(d, ad + (uint64_t)(k * 256), bd + (uint64_t)(k * 256), k > 0 ? 1u : 0u, sfa, sfb);
+          }
+          tc_commit(full_bar);
+          tc_commit(&b_empty[s]);                     // one of the four arrivals (one per query block) that free the stage
         }
-        tc_commit(full_bar);
-        tc_commit(&b_empty[s]);                       // one of the four arrivals (one per query block) that free the stage
+        __syncwarp();
       }
     }
   } else {
@@ -285,11 +291,12 @@ hamming_tc4_kernel(const __grid_constant__ HammingTcParams P) {
     // warps doing fetch / select in turn answered a finished item up to a whole selection late.
     const int lg = warp & 3, h = (warp >> 2) & 1, set = warp >> 3;
     uint32_t ka1 = kTcNone, ka2 = kTcNone, kb1 = kTcNone, kb2 = kTcNone;   // query blocks set, set + 2
+    float tha = tc4_threshold(kTcNone), thb = tha;    // their acc thresholds (kept: the hot path is one compare)
     const int nitems = ntiles * kTcQBlocks;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(h * 64);
     float v[64];
     int slot = set, use = 0;                          // item % 3, item / 3 of the current item (item = set, set + 2, ...)
-    auto step = [&](int item, uint32_t& k1, uint32_t& k2) {
+    auto step = [&](int item, uint32_t& k1, uint32_t& k2, float& thr) {
       const uint32_t taddr = lane_addr + (uint32_t)(slot * kTcN);
       uint64_t* const empty_bar = &acc_empty[slot];
 #if PBK_T4_SPIN_EPI
@@ -303,15 +310,15 @@ hamming_tc4_kernel(const __grid_constant__ HammingTcParams P) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_bar);
-      if (!(P.dbg & 1)) tc4_select(v, (uint32_t)(item >> 2) * kTcN, (uint32_t)rows, (uint32_t)h, k1, k2);
+      if (!(P.dbg & 1)) tc4_select(v, (uint32_t)(item >> 2) * kTcN, (uint32_t)rows, (uint32_t)h, k1, k2, thr);
       else k1 ^= __float_as_uint(v[0]) ^ __float_as_uint(v[63]) ^ __float_as_uint(v[17]);
       slot += 2;                                      // the set's next item is item + 2
       if (slot >= kT4Slots) { slot -= kT4Slots; ++use; }
     };
 #pragma unroll 1
     for (int item = set; item < nitems; item += 4) {  // nitems is a multiple of 4
-      step(item, ka1, ka2);
-      step(item + 2, kb1, kb2);
+      step(item, ka1, ka2, tha);
+      step(item + 2, kb1, kb2, thb);
     }
     const unsigned long long gbase = P.train_base + (unsigned long long)row0;
 #pragma unroll
