@@ -412,7 +412,7 @@ int hamming_tc8_scan(const uint8_t* q, long long nq, const int8_t* t_signs, long
   int rc = kc.setup(di, hamming_tc_kernel, kTcThreads, kTcSmemBytes, nullptr);
   if (rc) return rc;
   HammingTcParams P;
-  P.q_signs = q_signs; P.t_signs = t_signs; P.partial = partial;
+  P.q_signs = q_signs; P.t_signs = t_signs; P.partial = partial; P.gd2 = nullptr;
   P.nq = nq; P.nt = nt; P.rows_per_split = rps; P.train_base = train_base; P.splits = splits;
   P.dbg = 0;
   if (const char* e = getenv("PBK_TC_DEBUG")) P.dbg = atoi(e);
@@ -500,8 +500,10 @@ int pbk_hamming_tc_plan(int64_t nq, int64_t nt, int* parts, size_t* scratch_byte
   rc = tc_plan(di, nq, nt, &splits, &rps);
   if (rc) return rc;
   *parts = 2 * splits;
-  // partial keys, then (256 B aligned) the expanded queries
-  *scratch_bytes = (((size_t)(*parts) * (size_t)(nq > 0 ? nq : 1) * 16 + 255) & ~(size_t)255) + pbk_hamming_tc_signs_bytes(nq);
+  // partial keys, then (256 B aligned) the expanded queries, then one 32-bit word per (padded)
+  // query: the second-best distance all CTAs of a format-4 scan share (hamming_tc4.cu)
+  *scratch_bytes = (((size_t)(*parts) * (size_t)(nq > 0 ? nq : 1) * 16 + 255) & ~(size_t)255) + pbk_hamming_tc_signs_bytes(nq) +
+                   (size_t)tc_pad(nq > 0 ? nq : 1) * 4;
   return PBK_OK;
 }
 

@@ -54,6 +54,17 @@ constexpr int kT4Stages = PBK_T4_STAGES;
 #define PBK_T4_SPIN_EPI 0
 #endif
 constexpr int kT4Slots = 3;
+constexpr uint32_t kT4NoBound = 511u;              // "no second-best yet": above every distance
+#ifndef PBK_T4_SHARE
+#define PBK_T4_SHARE 1
+#endif
+#ifndef PBK_T4_REFRESH
+#define PBK_T4_REFRESH 0
+#endif
+// a stale bound corrects itself: it lets a candidate through, and the exact path re-reads it; an
+// additional periodic re-read (every PBK_T4_REFRESH tiles) costs more hot-path instructions than
+// the entries it saves (measured with 4 and 16)
+constexpr int kT4Refresh = PBK_T4_REFRESH;
 constexpr int kT4SfCol = 384;                       // first of 64 TMEM columns of 0x7F scale bytes
 constexpr int kT4EpiWarps = 16;                     // two sets of 8 (even / odd items), see the file header
 constexpr int kT4MmaWarp = kT4EpiWarps, kT4MmaWarps = kT4Slots, kT4ProducerWarp = kT4MmaWarp + kT4MmaWarps;   // one issuing warp per accumulator slot
@@ -69,13 +80,14 @@ constexpr int kT4SmemBytes = kT4SmemA + kT4SmemB + kT4SmemBars + 16;
 template <bool QUERY>
 __global__ void __launch_bounds__(256)
 hamming_tc4_expand_kernel(const uint8_t* __restrict__ d, long long n, long long first_row, long long n_padded,
-                          uint4* __restrict__ signs) {
+                          uint4* __restrict__ signs, uint32_t* __restrict__ gd2) {
   const long long i = first_row * kT4Chunks + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_padded * kT4Chunks) return;
   const long long tile = i / (kTcN * kT4Chunks);      // 1024 pieces per tile: [K chunk][row of the tile]
   const int in_t = (int)(i - tile * (kTcN * kT4Chunks));
   const int kc = in_t >> 7, rt = in_t & 127;
   const long long r = tile * kTcN + rt;
+  if (QUERY && kc == 0) gd2[r] = kT4NoBound;          // the scan's shared second-best bounds start unset
   uint4 o = make_uint4(0, 0, 0, 0);
   if (r < n) {
     // bit j of a byte -> bit 4 j + 3 (the sign of nibble j) over the constant magnitude 1.0 (0x2)
@@ -143,12 +155,22 @@ __device__ __forceinline__ void tc4_insert(float acc, uint32_t row, uint32_t row
   tc_top2(k1, k2, key);
 }
 
-// acc threshold of a query: rows arrive in ascending order, so only a distance BELOW the current
-// second best d2 = k2 >> 23 (>= the true one; 511 while unset) can enter: acc = 2 d - 256 < 2 d2 - 256
-__device__ __forceinline__ float tc4_threshold(uint32_t k2) { return (float)(2 * (int)(k2 >> 23) - 256); }
+// acc threshold of a query: an element can only matter with acc = 2 d - 256 BELOW it.
+//   own scan: rows arrive in ascending order, so only a distance below the current second best
+//             d2 = k2 >> 23 (>= the true one; 511 while unset) can enter: acc < 2 d2 - 256;
+//   all scans: gd2 bounds the second-best distance over every split and column half of the launch
+//             (each warp publishes its own with atomicMin): a row beyond it cannot be in the merged
+//             top-2 whatever its row number - acc <= 2 gd2 - 256, i.e. acc < 2 gd2 - 255.
+// The partial keys of one CTA are then no longer ITS top-2, but the merge over all of them is
+// exactly the top-2 of the database (both global winners pass both tests in their own scans).
+// Without the shared bound a warp of a 34 k-row scan (one 8-GPU shard of C3) built keys for a
+// quarter of its items; with it for 6 %.
+__device__ __forceinline__ float tc4_threshold(uint32_t k2, uint32_t gd2 = kT4NoBound) {
+  return fminf((float)(2 * (int)(k2 >> 23) - 256), (float)(2 * (int)gd2 - 255));
+}
 
 __device__ __forceinline__ void tc4_select(const float (&v)[64], uint32_t tile_base, uint32_t rows, uint32_t h,
-                                           uint32_t& k1, uint32_t& k2, float& thr) {
+                                           uint32_t& k1, uint32_t& k2, float& thr, uint32_t* gd2_q) {
   // minima of seven groups of nine columns (+ column 63), then of the item: 32 FMNMX3 / FMNMX
   float g[7];
 #pragma unroll
@@ -161,6 +183,11 @@ __device__ __forceinline__ void tc4_select(const float (&v)[64], uint32_t tile_b
   // for the 128 queries of a warp): only the groups that hold one are turned into keys - a warp
   // that inserted all 64 columns spent three times the pre-filter's instructions here.
   const uint32_t col0 = tile_base + h * 64u;
+#if PBK_T4_SHARE
+  // what the other CTAs found meanwhile: requested now, needed after the inserts (an L2 round trip)
+  const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(gd2_q);
+  const uint32_t before = k2;
+#endif
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
     if (__any_sync(0xffffffffu, g[i] < thr)) {
@@ -169,7 +196,12 @@ __device__ __forceinline__ void tc4_select(const float (&v)[64], uint32_t tile_b
     }
   }
   if (__any_sync(0xffffffffu, v[63] < thr)) tc4_insert(v[63], col0 + 63u, rows, k1, k2);
+#if PBK_T4_SHARE
+  if (k2 != before) atomicMin(gd2_q, k2 >> 23);     // result unused: a fire-and-forget RED.MIN
+  thr = tc4_threshold(k2, seen);
+#else
   thr = tc4_threshold(k2);
+#endif
 }
 
 __global__ void __launch_bounds__(kT4Threads, 1)
@@ -292,11 +324,13 @@ hamming_tc4_kernel(const __grid_constant__ HammingTcParams P) {
     const int lg = warp & 3, h = (warp >> 2) & 1, set = warp >> 3;
     uint32_t ka1 = kTcNone, ka2 = kTcNone, kb1 = kTcNone, kb2 = kTcNone;   // query blocks set, set + 2
     float tha = tc4_threshold(kTcNone), thb = tha;    // their acc thresholds (kept: the hot path is one compare)
+    // this lane's query of block `set` in the shared bound array; block set + 2 is 256 further
+    const uint32_t gq = (uint32_t)(qg * kTcQGroup + set * kTcM + lg * 32 + lane);
     const int nitems = ntiles * kTcQBlocks;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(h * 64);
     float v[64];
     int slot = set, use = 0;                          // item % 3, item / 3 of the current item (item = set, set + 2, ...)
-    auto step = [&](int item, uint32_t& k1, uint32_t& k2, float& thr) {
+    auto step = [&](int item, uint32_t& k1, uint32_t& k2, float& thr, uint32_t* gd2_q) {
       const uint32_t taddr = lane_addr + (uint32_t)(slot * kTcN);
       uint64_t* const empty_bar = &acc_empty[slot];
 #if PBK_T4_SPIN_EPI
@@ -310,15 +344,21 @@ hamming_tc4_kernel(const __grid_constant__ HammingTcParams P) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_bar);
-      if (!(P.dbg & 1)) tc4_select(v, (uint32_t)(item >> 2) * kTcN, (uint32_t)rows, (uint32_t)h, k1, k2, thr);
+      if (!(P.dbg & 1)) tc4_select(v, (uint32_t)(item >> 2) * kTcN, (uint32_t)rows, (uint32_t)h, k1, k2, thr, gd2_q);
       else k1 ^= __float_as_uint(v[0]) ^ __float_as_uint(v[63]) ^ __float_as_uint(v[17]);
       slot += 2;                                      // the set's next item is item + 2
       if (slot >= kT4Slots) { slot -= kT4Slots; ++use; }
     };
 #pragma unroll 1
     for (int item = set; item < nitems; item += 4) {  // nitems is a multiple of 4
-      step(item, ka1, ka2, tha);
-      step(item + 2, kb1, kb2, thb);
+      step(item, ka1, ka2, tha, P.gd2 + gq);
+      step(item + 2, kb1, kb2, thb, P.gd2 + gq + 2 * kTcM);
+#if PBK_T4_SHARE && PBK_T4_REFRESH
+      if (((item >> 2) & (kT4Refresh - 1)) == kT4Refresh - 1) {      // bounds the other CTAs published since
+        tha = tc4_threshold(ka2, *reinterpret_cast<volatile uint32_t*>(P.gd2 + gq));
+        thb = tc4_threshold(kb2, *reinterpret_cast<volatile uint32_t*>(P.gd2 + gq + 2 * kTcM));
+      }
+#endif
     }
     const unsigned long long gbase = P.train_base + (unsigned long long)row0;
 #pragma unroll
@@ -396,7 +436,7 @@ __global__ void __launch_bounds__(128, 1) hamming_tc4_peak_kernel(int iters, uin
 int hamming_tc4_expand(const uint8_t* d, long long n, long long first_row, long long n_padded, int8_t* signs, cudaStream_t s) {
   const long long blocks = ((n_padded - first_row) * kT4Chunks + 255) / 256;
   PBK_REQUIRE(blocks < (1ll << 31), PBK_EINVAL, "too many rows for one call");
-  hamming_tc4_expand_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(d, n, first_row, n_padded, reinterpret_cast<uint4*>(signs));
+  hamming_tc4_expand_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(d, n, first_row, n_padded, reinterpret_cast<uint4*>(signs), nullptr);
   PBK_CHECK_LAUNCH("hamming_tc4_expand_kernel");
   return PBK_OK;
 }
@@ -415,13 +455,14 @@ int hamming_tc4_scan(const uint8_t* q, long long nq, const int8_t* t_signs, long
                      int8_t* q_signs, unsigned long long* partial, int splits, long long rps, const DeviceInfo* di,
                      cudaStream_t s) {
   const long long nqp = tc_pad(nq);
-  hamming_tc4_expand_kernel<true><<<(unsigned)((nqp * kT4Chunks + 255) / 256), 256, 0, s>>>(q, nq, 0, nqp, reinterpret_cast<uint4*>(q_signs));
+  uint32_t* gd2 = reinterpret_cast<uint32_t*>(q_signs + (size_t)nqp * kTc4RowBytes);     // pbk_hamming_tc_plan sizes the scratch for it
+  hamming_tc4_expand_kernel<true><<<(unsigned)((nqp * kT4Chunks + 255) / 256), 256, 0, s>>>(q, nq, 0, nqp, reinterpret_cast<uint4*>(q_signs), gd2);
   PBK_CHECK_LAUNCH("hamming_tc4_expand_kernel");
   static KernelCache kc;
   int rc = kc.setup(di, hamming_tc4_kernel, kT4Threads, kT4SmemBytes, nullptr);
   if (rc) return rc;
   HammingTcParams P;
-  P.q_signs = q_signs; P.t_signs = t_signs; P.partial = partial;
+  P.q_signs = q_signs; P.t_signs = t_signs; P.partial = partial; P.gd2 = gd2;
   P.nq = nq; P.nt = nt; P.rows_per_split = rps; P.train_base = train_base; P.splits = splits;
   P.dbg = 0;
   if (const char* e = getenv("PBK_TC_DEBUG")) P.dbg = atoi(e);
