@@ -104,6 +104,28 @@ def test_tc_against_c_oracle_and_ties():
     assert list(idx[3]) == [7, 30_000] and list(dist[3]) == [0, 0]
 
 
+def test_ties_across_every_split_resolve_to_the_lowest_rows(tc_format):
+    """The CTAs of a format-4 scan share a bound of the second-best distance and skip rows beyond
+    it: ties AT the bound must still resolve to the lowest global rows.  (a) every row of the
+    database identical - every distance equal, the answer is rows 0 and 1 for every query;
+    (b) the best match of a query duplicated into every split and column half."""
+    rng = np.random.default_rng(11)
+    q = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    t = np.repeat(rng.integers(0, 256, (1, 32), dtype=np.uint8), 40_000, axis=0)
+    a, b = _keys_both(q, t, base=7)
+    assert np.array_equal(a, b)
+    assert np.array_equal(a & 0xFFFFFFFF, np.tile(np.array([7, 8], dtype=np.int64), (300, 1)))
+    t = rng.integers(0, 256, (60_000, 32), dtype=np.uint8)
+    q[5] = t[1234]
+    q[6] = t[1234]
+    q[6, 0] ^= 1                                       # distance 1 to all the copies: ties at the second best too
+    t[1234 + 61::61] = t[1234]                         # ~960 copies: several in every 128-row tile's neighbourhood
+    a, b = _keys_both(q, t)
+    assert np.array_equal(a, b)
+    assert list(a[5] & 0xFFFFFFFF) == [1234, 1295] and list(a[5] >> 32) == [0, 0]
+    assert list(a[6] & 0xFFFFFFFF) == [1234, 1295] and list(a[6] >> 32) == [1, 1]
+
+
 def test_tc_uniform_random_large():
     """2000 x 2.5 M uniformly random descriptors (one 8-GPU shard of C3): every split / tile / slot path."""
     import torch
