@@ -500,10 +500,10 @@ int pbk_hamming_tc_plan(int64_t nq, int64_t nt, int* parts, size_t* scratch_byte
   rc = tc_plan(di, nq, nt, &splits, &rps);
   if (rc) return rc;
   *parts = 2 * splits;
-  // partial keys, then (256 B aligned) the expanded queries, then one 32-bit word per (padded)
-  // query: the second-best distance all CTAs of a format-4 scan share (hamming_tc4.cu)
+  // partial keys, then (256 B aligned) the expanded queries, then one 16-byte record per (padded)
+  // query: the distance bounds all CTAs of a format-4 scan share (hamming_tc4.cu)
   *scratch_bytes = (((size_t)(*parts) * (size_t)(nq > 0 ? nq : 1) * 16 + 255) & ~(size_t)255) + pbk_hamming_tc_signs_bytes(nq) +
-                   (size_t)tc_pad(nq > 0 ? nq : 1) * 4;
+                   (size_t)tc_pad(nq > 0 ? nq : 1) * 16;
   return PBK_OK;
 }
 

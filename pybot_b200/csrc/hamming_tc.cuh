@@ -100,7 +100,7 @@ struct HammingTcParams {
   const int8_t* q_signs;          // expanded queries, padded to whole groups of 512 rows
   const int8_t* t_signs;          // expanded train rows of this call, padded to whole tiles
   unsigned long long* partial;    // (2 * splits, nq, 2)
-  uint32_t* gd2;                  // mxf4 kernel: per (padded) query, an upper bound of the second-best distance over ALL splits
+  uint32_t* gd2;                  // mxf4 kernel: per (padded) query, a 16-byte record of distance bounds shared by ALL CTAs (tc4_bound)
   long long nq, nt;
   long long rows_per_split;       // multiple of kTcN
   unsigned long long train_base;

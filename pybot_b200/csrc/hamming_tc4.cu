@@ -87,7 +87,8 @@ hamming_tc4_expand_kernel(const uint8_t* __restrict__ d, long long n, long long 
   const int in_t = (int)(i - tile * (kTcN * kT4Chunks));
   const int kc = in_t >> 7, rt = in_t & 127;
   const long long r = tile * kTcN + rt;
-  if (QUERY && kc == 0) gd2[r] = kT4NoBound;          // the scan's shared second-best bounds start unset
+  if (QUERY && kc == 0)                               // the scan's shared bounds (tc4_bound) start unset
+    reinterpret_cast<uint4*>(gd2)[r] = make_uint4(kT4NoBound, kT4NoBound, kT4NoBound, kT4NoBound);
   uint4 o = make_uint4(0, 0, 0, 0);
   if (r < n) {
     // bit j of a byte -> bit 4 j + 3 (the sign of nibble j) over the constant magnitude 1.0 (0x2)
@@ -158,16 +159,23 @@ __device__ __forceinline__ void tc4_insert(float acc, uint32_t row, uint32_t row
 // acc threshold of a query: an element can only matter with acc = 2 d - 256 BELOW it.
 //   own scan: rows arrive in ascending order, so only a distance below the current second best
 //             d2 = k2 >> 23 (>= the true one; 511 while unset) can enter: acc < 2 d2 - 256;
-//   all scans: gd2 bounds the second-best distance over every split and column half of the launch
-//             (each warp publishes its own with atomicMin): a row beyond it cannot be in the merged
-//             top-2 whatever its row number - acc <= 2 gd2 - 256, i.e. acc < 2 gd2 - 255.
+//   all scans: `bound` is a distance two DISTINCT rows of the database are known to reach, found
+//             by any CTA of the launch (tc4_bound): a row beyond it cannot be in the merged top-2
+//             whatever its row number - acc <= 2 bound - 256, i.e. acc < 2 bound - 255.
 // The partial keys of one CTA are then no longer ITS top-2, but the merge over all of them is
 // exactly the top-2 of the database (both global winners pass both tests in their own scans).
 // Without the shared bound a warp of a 34 k-row scan (one 8-GPU shard of C3) built keys for a
-// quarter of its items; with it for 6 %.
-__device__ __forceinline__ float tc4_threshold(uint32_t k2, uint32_t gd2 = kT4NoBound) {
-  return fminf((float)(2 * (int)(k2 >> 23) - 256), (float)(2 * (int)gd2 - 255));
+// quarter of its items; with the second-best word alone for 6 %.
+__device__ __forceinline__ float tc4_threshold(uint32_t k2, uint32_t bound = kT4NoBound) {
+  return fminf((float)(2 * (int)(k2 >> 23) - 256), (float)(2 * (int)bound - 255));
 }
+// One 16-byte record per (padded) query, every word an atomicMin target:
+//   .x  the smallest SECOND-best distance any warp of the launch has (two rows of one scan)
+//   .y  the smallest BEST distance over the scans of column half 0,  .z  the same for column half 1
+// The two halves scan disjoint rows, so max(.y, .z) is reached by two distinct rows as well - and
+// early in a scan it is far below .x (the best of ~2400 T rows against the best second-best of 74
+// scans of 64 T rows each after T tiles).
+__device__ __forceinline__ uint32_t tc4_bound(uint4 g) { return min(g.x, max(g.y, g.z)); }
 
 __device__ __forceinline__ void tc4_select(const float (&v)[64], uint32_t tile_base, uint32_t rows, uint32_t h,
                                            uint32_t& k1, uint32_t& k2, float& thr, uint32_t* gd2_q) {
@@ -185,8 +193,9 @@ __device__ __forceinline__ void tc4_select(const float (&v)[64], uint32_t tile_b
   const uint32_t col0 = tile_base + h * 64u;
 #if PBK_T4_SHARE
   // what the other CTAs found meanwhile: requested now, needed after the inserts (an L2 round trip)
-  const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(gd2_q);
-  const uint32_t before = k2;
+  uint4 seen;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(seen.x), "=r"(seen.y), "=r"(seen.z), "=r"(seen.w) : "l"(gd2_q));
+  const uint32_t before1 = k1, before2 = k2;
 #endif
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
@@ -197,8 +206,11 @@ __device__ __forceinline__ void tc4_select(const float (&v)[64], uint32_t tile_b
   }
   if (__any_sync(0xffffffffu, v[63] < thr)) tc4_insert(v[63], col0 + 63u, rows, k1, k2);
 #if PBK_T4_SHARE
-  if (k2 != before) atomicMin(gd2_q, k2 >> 23);     // result unused: a fire-and-forget RED.MIN
-  thr = tc4_threshold(k2, seen);
+  if (k2 != before2) atomicMin(gd2_q, k2 >> 23);    // results unused: fire-and-forget RED.MIN
+  if (k1 != before1) atomicMin(gd2_q + 1 + h, k1 >> 23);
+  seen.x = min(seen.x, k2 >> 23);
+  if (h == 0) seen.y = min(seen.y, k1 >> 23); else seen.z = min(seen.z, k1 >> 23);
+  thr = tc4_threshold(k2, tc4_bound(seen));
 #else
   thr = tc4_threshold(k2);
 #endif
@@ -351,12 +363,12 @@ hamming_tc4_kernel(const __grid_constant__ HammingTcParams P) {
     };
 #pragma unroll 1
     for (int item = set; item < nitems; item += 4) {  // nitems is a multiple of 4
-      step(item, ka1, ka2, tha, P.gd2 + gq);
-      step(item + 2, kb1, kb2, thb, P.gd2 + gq + 2 * kTcM);
+      step(item, ka1, ka2, tha, P.gd2 + 4 * gq);
+      step(item + 2, kb1, kb2, thb, P.gd2 + 4 * (gq + 2 * kTcM));
 #if PBK_T4_SHARE && PBK_T4_REFRESH
       if (((item >> 2) & (kT4Refresh - 1)) == kT4Refresh - 1) {      // bounds the other CTAs published since
-        tha = tc4_threshold(ka2, *reinterpret_cast<volatile uint32_t*>(P.gd2 + gq));
-        thb = tc4_threshold(kb2, *reinterpret_cast<volatile uint32_t*>(P.gd2 + gq + 2 * kTcM));
+        tha = tc4_threshold(ka2, *reinterpret_cast<volatile uint32_t*>(P.gd2 + 4 * gq));
+        thb = tc4_threshold(kb2, *reinterpret_cast<volatile uint32_t*>(P.gd2 + 4 * (gq + 2 * kTcM)));
       }
 #endif
     }
