@@ -1,8 +1,11 @@
 """Unit quaternion (x, y, z, w) - host-side scalar algebra.
 
-API of /root/reference/pybot/geometry/quaternion.py:12-228 (same method and
-property names, same float64 storage and the same "renormalise only when the
-norm is off by more than 1e-6" rule, :49-53), written fresh on numpy.
+API of /root/reference/pybot/geometry/quaternion.py:12-228: the method and
+property names, the float64 (x, y, z, w) storage and the "renormalise only when
+the norm is off by more than 1e-6" rule (:49-53) are the reference's, because
+callers and the bit-exact golden g0 (tests/test_host_geometry.py) depend on them.
+Where the golden pins bits (rotate, interpolate) the floating-point operations
+are applied in the reference's order; the code itself is vectorised numpy.
 """
 import math
 
@@ -56,38 +59,36 @@ class Quaternion(object):
     conjugate = inverse
 
     def rotate(self, v):
-        """Rotates a 3-vector; the expanded sandwich product of the reference
-        (:69-85), same term order so pose compounding is bit-identical."""
-        qx, qy, qz, qw = self.q
-        ab, ac, ad = qw * qx, qw * qy, qw * qz
-        nbb, bc, bd = -qx * qx, qx * qy, qx * qz
-        ncc, cd, ndd = -qy * qy, qy * qz, -qz * qz
-        return np.array((
-            2 * ((ncc + ndd) * v[0] + (bc - ad) * v[1] + (ac + bd) * v[2]) + v[0],
-            2 * ((ad + bc) * v[0] + (nbb + ndd) * v[1] + (cd - ab) * v[2]) + v[1],
-            2 * ((bd - ac) * v[0] + (ab + cd) * v[1] + (nbb + ncc) * v[2]) + v[2]))
+        """R(q) v for a 3-vector as  v + 2 M v  with M = R(q) / 2 - I / 2 written out in products
+        of the components (reference :69-85).  Each row is summed left to right and doubled
+        before v is added - the order the golden pose compositions are pinned to."""
+        x, y, z, w = self.q
+        xx, yy, zz = x * x, y * y, z * z
+        wx, wy, wz = w * x, w * y, w * z
+        xy, xz, yz = x * y, x * z, y * z
+        half = np.array(((-yy - zz, xy - wz, wy + xz),
+                         (wz + xy, -xx - zz, yz - wx),
+                         (xz - wy, wx + yz, -xx - yy)))
+        v = np.asarray(v)
+        return 2 * ((half[:, 0] * v[0] + half[:, 1] * v[1]) + half[:, 2] * v[2]) + v[:3]
 
     def interpolate(self, other, this_weight):
-        """Spherical interpolation in wxyz space (reference :100-125)."""
-        q0, q1 = np.roll(self.q, 1), np.roll(other.q, 1)
-        u = 1 - this_weight
-        assert 0 <= u <= 1
-        cos_omega = float(np.dot(q0, q1))
-        if cos_omega < 0:
-            start, cos_omega = -q0, -cos_omega
+        """Slerp between self (weight this_weight) and other, taking the short way round
+        (reference :100-125: evaluated on the w-first vectors)."""
+        far_weight = 1 - this_weight
+        assert 0 <= far_weight <= 1
+        mine, theirs = np.roll(self.q, 1), np.roll(other.q, 1)
+        c = float(np.dot(mine, theirs))
+        if c < 0:                                   # antipodal representation of the same rotation
+            mine, c = -mine, -c
+        angle = math.acos(min(c, 1))
+        s = math.sin(angle)
+        if abs(s) < 1e-6:                           # (nearly) the same rotation: blend and renormalise
+            out = mine * this_weight + theirs * far_weight
+            out = out / math.sqrt(np.dot(out, out))
         else:
-            start = q0.copy()
-        cos_omega = min(cos_omega, 1)
-        omega = math.acos(cos_omega)
-        sin_omega = math.sin(omega)
-        if abs(sin_omega) < 1e-6:
-            mixed = start * this_weight + q1 * u
-            mixed /= math.sqrt(np.dot(mixed, mixed))
-        else:
-            a = math.sin((1 - u) * omega) / sin_omega
-            b = math.sin(u * omega) / sin_omega
-            mixed = start * a + q1 * b
-        return Quaternion(np.roll(mixed, -1))
+            out = mine * (math.sin((1 - far_weight) * angle) / s) + theirs * (math.sin(far_weight * angle) / s)
+        return Quaternion(np.roll(out, -1))
 
     # -------------------------------------------------------- conversions
     def to_wxyz(self):
@@ -100,11 +101,11 @@ class Quaternion(object):
         return np.array(tf.euler_from_quaternion(self.q, axes=axes))
 
     def to_angle_axis(self):
-        w = np.roll(self.q, 1)
-        half = math.acos(w[0])
-        if abs(half) < 1e-12:
+        """(angle, unit axis); the identity reports angle 0 about +z."""
+        half_angle = math.acos(self.q[3])
+        if abs(half_angle) < 1e-12:
             return 0, np.array((0, 0, 1))
-        return half * 2, np.array(w[1:4]) / math.sin(half)
+        return half_angle * 2, self.q[:3] / math.sin(half_angle)
 
     def to_matrix(self):
         return tf.quaternion_matrix(self.q)
@@ -128,12 +129,13 @@ class Quaternion(object):
 
     @classmethod
     def from_angle_axis(cls, theta, axis):
-        x, y, z = axis
-        n = math.sqrt(x * x + y * y + z * z)
-        if n == 0:
-            return cls([0, 0, 0, 1])
-        t = math.sin(theta / 2) / n
-        return cls([x * t, y * t, z * t, math.cos(theta / 2)])
+        """Rotation by theta about `axis` (any length; the zero axis gives the identity)."""
+        ax, ay, az = axis
+        length = math.sqrt(ax * ax + ay * ay + az * az)
+        if length == 0:
+            return cls.identity()
+        scale = math.sin(theta / 2) / length
+        return cls([ax * scale, ay * scale, az * scale, math.cos(theta / 2)])
 
     @classmethod
     def identity(cls):

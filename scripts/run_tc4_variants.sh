@@ -8,7 +8,7 @@ if [ "$1" == "--more" ]; then MORE="--more"; shift; fi
    echo "== $v"
    if [ "$v" == "base" ]; then unset PYBOT_B200_LIB; else export PYBOT_B200_LIB=scripts/probes/_bin/libpbk_$v.so; fi
    for n in 2500000 20000000; do
-     timeout 60 python scripts/tc_probe.py $n --no-popc --rare $MORE | grep -A12 mxf4 | grep -v "TMEM load"
+     timeout 60 python scripts/tc_probe.py $n --no-popc $MORE | grep -A12 mxf4 | grep -v "TMEM load"
    done
  done) > gpurun_out/tc4_variants.log 2>&1
 cat gpurun_out/tc4_variants.log
