@@ -373,7 +373,7 @@ def run_c3(D, args):
     m.check()
     variants = {}
     # the integer-pipe kernel on the same shard (the north star's formulation; the shipped
-    # default for databases below 65536 rows): scan + split merge, same events
+    # default for databases below 16384 rows): scan + split merge, same events
     popc_ms = None
     if m.signs is not None:
         def step_popc(rec):
@@ -548,7 +548,7 @@ def run_c3(D, args):
                     frac=local_pairs / (popc_ms * 1e-3) * POPC_ISSUED_PER_PAIR / pk["popc_per_s"],
                     frac_algorithmic=local_pairs / (popc_ms * 1e-3) * 8 / pk["popc_per_s"],
                     note="the north star's formulation, timed on the same shard in this run; the default "
-                         "engine for databases below 65536 rows (per-frame matching)")}
+                         "engine for databases below 16384 rows (per-frame matching)")}
         if D.world == 1:
             base, cpu_result = cpu_baseline_c3(q_np, db_np, per_kf, args.parity_keyframes)
             res["cpu_baseline"] = base

@@ -408,18 +408,22 @@ def hamming_knn2_keys(q_dev, t_dev, train_base=0):
     return keys
 
 
-TC_MIN_ROWS = 1 << 16        # below this the integer-pipe kernel's latency wins (per-frame 2000 x 2000 matching)
+# Below these sizes the integer-pipe kernel's latency wins (per-frame 2000 x 2000 matching); measured with
+# 2000 queries by scripts/tc_size_probe.py: 16 k rows 50 us (popc) / 36 us (tc, resident copy) / 55 us (tc,
+# copy expanded inside the call); 32 k rows 89 / 37 / 52 us.
+TC_MIN_ROWS = 1 << 14          # the database keeps a resident expanded copy
+TC_MIN_ROWS_EXPAND = 1 << 15   # the copy has to be made inside the call
 
 
-def hamming_engine(nt):
+def hamming_engine(nt, resident=True):
     """'tc' (tcgen05 scan over the expanded database) or 'popc' (integer-pipe kernel).
-    PBK_HAMMING_ENGINE=popc|tc forces one; by default databases of >= 65536 rows take the
-    tensor-core route.  Both return bit-identical keys."""
+    PBK_HAMMING_ENGINE=popc|tc forces one; by default databases of >= 16384 rows (32768 when the
+    expanded copy is not resident) take the tensor-core route.  Both return bit-identical keys."""
     import os
     e = os.environ.get("PBK_HAMMING_ENGINE", "").lower()
     if e in ("popc", "tc"):
         return e
-    return "tc" if nt >= TC_MIN_ROWS else "popc"
+    return "tc" if nt >= (TC_MIN_ROWS if resident else TC_MIN_ROWS_EXPAND) else "popc"
 
 
 def hamming_tc_format():
@@ -483,7 +487,7 @@ def hamming_scan_keys(q_dev, t_dev, train_base=0, signs=None):
     copy) is given or the engine rule picks it (expanding on the fly: 128 B per row written once
     is still cheaper than the integer-pipe scan of a large database), else the integer-pipe kernel."""
     nt = int(t_dev.shape[0])
-    if nt > 0 and int(q_dev.shape[0]) > 0 and hamming_engine(nt) == "tc":
+    if nt > 0 and int(q_dev.shape[0]) > 0 and hamming_engine(nt, resident=signs is not None) == "tc":
         if signs is None:
             signs = hamming_tc_expand(t_dev)
         return hamming_knn2_keys_tc(q_dev, signs, nt, train_base)
