@@ -92,6 +92,22 @@ def test_tc_keys_equal_integer_pipe_keys(nq, nt):
     assert np.array_equal(a, b)
 
 
+def test_tc_random_shapes_sweep(tc_format):
+    """Twenty random (nq, nt) shapes - ragged last tiles, one to five query groups, splits of one to
+    hundreds of tiles - on tie-heavy and on uniform descriptors, with a random global row base."""
+    rng = np.random.default_rng(2024)
+    for case in range(20):
+        nq = int(rng.integers(1, 2600))
+        nt = int(rng.integers(1, 400_000)) if case % 4 else int(rng.integers(1, 700))
+        if case % 2:
+            q, t = syn.low_entropy_pair(seed=case, nq=nq, nt=nt)
+        else:
+            q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+            t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+        a, b = _keys_both(q, t, base=int(rng.integers(0, 1 << 30)))
+        assert np.array_equal(a, b), (case, nq, nt)
+
+
 def test_tc_against_c_oracle_and_ties():
     from oracle import c_oracle
     q, t = syn.low_entropy_pair(seed=9, nq=520, nt=150 * 256 + 200)
