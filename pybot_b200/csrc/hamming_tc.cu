@@ -215,11 +215,13 @@ hamming_tc_kernel(const __grid_constant__ HammingTcParams P) {
     }
   } else if (warp >= kTcMmaWarp && warp < kTcMmaWarp + kTcMmaWarps) {
     // =============================================================== MMA issuers
-    if (lane == 0 && ntiles > 0) {
+    // the whole warp runs the loop with warp-uniform values, one elected lane issues (see
+    // hamming_tc4.cu: under `if (lane == 0)` every UTCIMMA sits in an ELECT / R2UR waterfall loop)
+    if (ntiles > 0) {
       mbar_wait(a_full, 0);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
-      const int mine = warp - kTcMmaWarp;              // this issuer's query blocks: mine, mine + kTcMmaWarps
+      const int mine = __shfl_sync(0xffffffffu, warp - kTcMmaWarp, 0);   // this issuer's query blocks: mine, mine + kTcMmaWarps
       for (int t = 0; t < ntiles; ++t) {
         const int s = t % kTcStages;
         mbar_wait(&b_full[s], (uint32_t)((t / kTcStages) & 1));
@@ -234,14 +236,18 @@ hamming_tc_kernel(const __grid_constant__ HammingTcParams P) {
           }
           const uint32_t d = tmem_base + (uint32_t)(slot * kTcN);
           const uint64_t ad = tc_smem_desc(a_addr + mb * kTcBlockBytes), bd = tc_smem_desc(b_addr + s * kTcTileBytes);
-          if (!(P.dbg & 2)) {
+          if (tc_elect_one()) {
+            if (!(P.dbg & 2)) {
 #pragma unroll
-            for (int k = 0; k < kTcKSteps; ++k)                 // K = 32 bytes per instruction = two planes: +4096 B = +256 in the address field
-              tc_mma_i8(d, ad + (uint64_t)(k * 256), bd + (uint64_t)(k * 256), k > 0 ? 1u : 0u);
+              for (int k = 0; k < kTcKSteps; ++k)               // K = 32 bytes per instruction = two planes: +4096 B = +256 in the address field
+                tc_mma_i8(d, ad + (uint64_t)(k * 256), bd + (uint64_t)(k * 256), k > 0 ? 1u : 0u);
+            }
+            tc_commit(&acc_full[slot]);
           }
-          tc_commit(&acc_full[slot]);
+          __syncwarp();
         }
-        tc_commit(&b_empty[s]);                       // the tile's shared-memory stage may be refilled
+        if (tc_elect_one()) tc_commit(&b_empty[s]);   // the tile's shared-memory stage may be refilled
+        __syncwarp();
       }
     }
   } else {

@@ -62,6 +62,13 @@ __device__ __forceinline__ void tc_ld64_packed(uint32_t taddr, uint32_t (&r)[32]
       : "r"(taddr)
       : "memory");
 }
+// one lane of a converged warp (the tcgen05 issue instructions take uniform operands: keep the code
+// around them warp-uniform and predicate only the instruction)
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // mbarrier wait for the warps that may sleep: try_wait with a suspend-time hint, so a waiting warp

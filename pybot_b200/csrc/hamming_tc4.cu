@@ -134,11 +134,6 @@ __device__ __forceinline__ void tc_ld64_f32(uint32_t taddr, float (&r)[64]) {
       : "memory");
 }
 #undef PBK_F8
-__device__ __forceinline__ bool tc_elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ float tc_min3(float a, float b, float c) {
   float r;
   asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
