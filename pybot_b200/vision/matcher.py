@@ -311,9 +311,23 @@ class BFMatcher(object):
                 if row]
 
 
+_UNIFORM = {}     # id(offsets) -> (offsets, rows per image or 0): equal-sized keyframes split by one division
+
+
 def _split_global(offsets, g):
     """global rows -> (imgIdx, trainIdx) for a collection with row offsets `offsets`."""
     g = np.asarray(g, np.int64)
+    hit = _UNIFORM.get(id(offsets))
+    if hit is None or hit[0] is not offsets:
+        step = int(offsets[1] - offsets[0]) if len(offsets) > 1 else 0
+        if step <= 0 or int(offsets[0]) != 0 or not np.array_equal(offsets, np.arange(len(offsets), dtype=np.int64) * step):
+            step = 0
+        if len(_UNIFORM) > 64:
+            _UNIFORM.clear()
+        hit = _UNIFORM[id(offsets)] = (offsets, step)
+    if hit[1]:                                   # (a binary search over 10 001 offsets costs 120 us per 4000 rows)
+        img = np.minimum(g // hit[1], len(offsets) - 2)
+        return img.astype(np.int32), (g - img * hit[1]).astype(np.int32)
     img = np.searchsorted(offsets, g, side="right") - 1
     img = np.clip(img, 0, max(len(offsets) - 2, 0))
     return img.astype(np.int32), (g - offsets[img]).astype(np.int32)
