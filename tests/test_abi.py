@@ -65,6 +65,25 @@ def test_sass_of_the_shipped_matcher_and_ba_kernels():
     assert len(pre) == 1 and "PREEXIT" in pre[0]                 # griddepcontrol.launch_dependents
 
 
+def test_tensor_core_format_selection_is_host_state():
+    """pbk_hamming_tc_format / _set_format / _signs_bytes are host-only: the expanded row is 128 B
+    (e2m1 nibbles, kind::mxf4) by default, 256 B (signed bytes, kind::i8) in format 8; anything else
+    is refused."""
+    from pybot_b200 import _ffi
+    L = _ffi.lib()
+    before = L.pbk_hamming_tc_format()
+    try:
+        assert before in (4, 8)
+        assert L.pbk_hamming_tc_set_format(4) == 0 and L.pbk_hamming_tc_format() == 4
+        assert L.pbk_hamming_tc_signs_bytes(1) == 512 * 128 and L.pbk_hamming_tc_signs_bytes(513) == 1024 * 128
+        assert L.pbk_hamming_tc_set_format(8) == 0 and L.pbk_hamming_tc_format() == 8
+        assert L.pbk_hamming_tc_signs_bytes(512) == 512 * 256
+        assert L.pbk_hamming_tc_set_format(5) != 0 and L.pbk_hamming_tc_format() == 8
+        assert L.pbk_hamming_tc_signs_bytes(0) == 0
+    finally:
+        L.pbk_hamming_tc_set_format(before)
+
+
 def test_sass_of_the_tensor_core_matchers():
     """The two tensor-core scans are tcgen05 code: UTCOMMA (kind::mxf4, block-scaled FP4) with fp32
     accumulators read back by LDTM and pre-filtered with 3-input minima in the default engine,
