@@ -371,6 +371,31 @@ def run_c3(D, args):
     clocks = sampler.stop() if sampler else None
     result = [_ffi.to_host(x) for x in step(None)]          # idx, dist, ratio_ok, mutual_ok, valid
     m.check()
+    # The end-to-end loops run HERE, directly after the device-resident loop and before the variants:
+    # the scan is tensor-bound and follows the SM clock, which sags from ~1840 to ~1700 MHz over a
+    # few seconds of sustained tcgen05 work (scripts/c3_scan_after_copy.py: the same resident step
+    # 2.63 -> 2.99 ms while averaged board power climbs 290 -> 735 W).  Timed after ~0.5 s of
+    # integer-pipe variants, `e2e` used to show 250 us of "host overhead" that was clock drift; the
+    # copies and the synchronisation themselves cost ~40 us (scripts/c3_e2e_timeline.py).
+    # end to end through the array API: pinned host queries in, numpy results out
+    def e2e_step(rec):
+        return m.match_host(torch.from_numpy(q_pin).to("cuda", non_blocking=True))
+    sampler = ClockSampler(D.local).start() if D.rank == 0 else None
+    e2e_ms, _ = timed_steps(D, e2e_step, args.steps, args.warmup, flush)
+    e2e_clocks = sampler.stop() if sampler else None
+
+    # ... and through the cv2-shaped facade: BFMatcher.knnMatch(host queries, k=2) over the
+    # resident (sharded) collection -> rows of DMatch (imgIdx / trainIdx / distance)
+    bf = BFMatcher.from_resident(shard, per_kf, shard_base=lo_kf * per_kf, n_images_total=nkf,
+                                 group=True if D.world > 1 else None)
+    if D.world > 1 and m._px is not None:
+        bf._sharded[0].use_exchange(m._px)                  # same queries: share the peer buffers
+
+    def e2e_knn_step(rec):
+        return bf.knnMatch(q_pin, k=2)
+    knn_api_ms, _ = timed_steps(D, e2e_knn_step, args.steps, args.warmup, flush)
+    api_rows = e2e_knn_step(None)
+
     variants = {}
     # the integer-pipe kernel on the same shard (the north star's formulation; the shipped
     # default for databases below 16384 rows): scan + split merge, same events
@@ -422,23 +447,6 @@ def run_c3(D, args):
         variants["nccl_allgather_allreduce_between_kernels"] = {
             "Gpairs_per_s": float(nq) * nkf * per_kf * args.steps / (ms_n * 1e-3) / 1e9, "ms": ms_n / args.steps}
 
-    # end to end through the array API: pinned host queries in, numpy results out
-    def e2e_step(rec):
-        return m.match_host(torch.from_numpy(q_pin).to("cuda", non_blocking=True))
-    e2e_ms, _ = timed_steps(D, e2e_step, args.steps, args.warmup, flush)
-
-    # ... and through the cv2-shaped facade: BFMatcher.knnMatch(host queries, k=2) over the
-    # resident (sharded) collection -> rows of DMatch (imgIdx / trainIdx / distance)
-    bf = BFMatcher.from_resident(shard, per_kf, shard_base=lo_kf * per_kf, n_images_total=nkf,
-                                 group=True if D.world > 1 else None)
-    if D.world > 1 and m._px is not None:
-        bf._sharded[0].use_exchange(m._px)                  # same queries: share the peer buffers
-
-    def e2e_knn_step(rec):
-        return bf.knnMatch(q_pin, k=2)
-    knn_api_ms, _ = timed_steps(D, e2e_knn_step, args.steps, args.warmup, flush)
-    api_rows = e2e_knn_step(None)
-
     pairs = float(nq) * nt_total
     launches = ((6 if D.world == 1 else 9) + (1 if m.signs is not None else 0)) * args.steps
     res = {
@@ -459,7 +467,9 @@ def run_c3(D, args):
                 "h2d_bytes_per_step": nq * 32,
                 "d2h_bytes_per_step": nq * (2 * 8 + 2 * 4 + 3),
                 "api": "ShardedKeyframeMatcher.match_host (array API: idx, dist, ratio_ok, mutual_ok, valid "
-                       "as numpy; one packed copy)"},
+                       "as numpy; one packed copy)",
+                "clocks": e2e_clocks,
+                "order": "timed directly after the device-resident loop (same SM clock state), before the variants"},
         "e2e_knnMatch": {"value": pairs * args.steps / (knn_api_ms * 1e-3) / 1e9, "unit": "Gpairs/s",
                          "ms_per_step": knn_api_ms / args.steps,
                          "h2d_bytes_per_step": nq * 32, "d2h_bytes_per_step": nq * (2 * 8 + 2 * 4 + 3),
