@@ -127,8 +127,9 @@ def measured_peaks():
     return 6650.0, "B200_PROFILING.md fallback (of fallback)"
 
 
-class ClockSampler(object):
-    """nvidia-smi clocks/throttle reasons during the timed region."""
+class _SmiClockSampler(object):
+    """nvidia-smi clocks/throttle reasons around the timed region (fallback of ClockSampler: its
+    first sample arrives ~100 ms after start())."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -179,6 +180,113 @@ class ClockSampler(object):
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
                 "power_w_max": float(max(pw)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+_NVML_POLL = r"""
+import sys, time
+import pynvml as n
+n.nvmlInit()
+h = n.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+out = sys.stdout
+while True:
+    t = time.time()
+    try:
+        line = "%.6f,%d,%d,%.1f,%d\n" % (t, n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM), mx,
+                                         n.nvmlDeviceGetPowerUsage(h) / 1e3, get_reasons(h))
+    except Exception:
+        time.sleep(0.02)
+        continue
+    out.write(line)
+    out.flush()
+    time.sleep(0.004)
+"""
+
+
+class ClockSampler(object):
+    """SM clock, board power and clock-event reasons DURING a timed region.
+
+    One NVML poller per GPU index runs in its own process for the whole bench (a sample every
+    ~5 ms, each stamped with time.time()); start() / stop() mark the window and stop() reports
+    the samples that fall inside it - so a 40 ms loop is described by the clocks it ran at, not by
+    what nvidia-smi printed 100 ms after it ended.  Falls back to nvidia-smi if NVML is missing."""
+    REASONS = ((0x4, "sw_power_cap"), (0x8, "hw_slowdown"), (0x20, "sw_thermal_slowdown"),
+               (0x40, "hw_thermal_slowdown"), (0x80, "hw_power_brake_slowdown"))
+    _pollers = {}
+
+    def __init__(self, index=0):
+        self.index = index
+        self.fallback = None
+        self.t0 = None
+
+    @classmethod
+    def _poller(cls, index):
+        p = cls._pollers.get(index)
+        if p is None:
+            p = {"lines": [], "ok": False}
+            try:
+                p["proc"] = subprocess.Popen([sys.executable, "-c", _NVML_POLL, str(index)], stdout=subprocess.PIPE,
+                                             stderr=subprocess.DEVNULL, text=True)
+
+                def pump():
+                    for line in p["proc"].stdout:
+                        p["lines"].append(line)
+                threading.Thread(target=pump, daemon=True).start()
+                t_end = time.time() + 5.0                      # first sample = NVML is up
+                while time.time() < t_end and not p["lines"] and p["proc"].poll() is None:
+                    time.sleep(0.01)
+                p["ok"] = bool(p["lines"])
+            except Exception:
+                p["ok"] = False
+            cls._pollers[index] = p
+            import atexit
+            atexit.register(cls._shutdown, index)
+        return p
+
+    @classmethod
+    def _shutdown(cls, index):
+        p = cls._pollers.get(index)
+        if p and p.get("proc") is not None and p["proc"].poll() is None:
+            p["proc"].terminate()
+
+    def start(self):
+        p = self._poller(self.index)
+        if not p["ok"]:
+            self.fallback = _SmiClockSampler(self.index).start()
+            return self
+        self.t0 = time.time()
+        return self
+
+    def stop(self):
+        if self.fallback is not None:
+            return self.fallback.stop()
+        t1 = time.time()
+        time.sleep(0.012)                                      # let the sample that covers t1 arrive
+        rows = []
+        for ln in list(self._pollers[self.index]["lines"]):
+            f = ln.strip().split(",")
+            if len(f) == 5:
+                try:
+                    rows.append((float(f[0]), float(f[1]), float(f[2]), float(f[3]), int(f[4])))
+                except ValueError:
+                    pass
+        inside = [r for r in rows if self.t0 <= r[0] <= t1]
+        window = "inside the timed region"
+        if not inside:                                         # region shorter than one poll: the nearest samples
+            inside = sorted(rows, key=lambda r: abs(r[0] - 0.5 * (self.t0 + t1)))[:2]
+            window = "nearest to the timed region (shorter than one poll)"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        bits = 0
+        for r in inside:
+            bits |= r[4]
+        sm = [r[1] for r in inside]
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(max(r[2] for r in inside)),
+                "power_w_max": float(max(r[3] for r in inside)), "samples": len(inside),
+                "reasons": [name for bit, name in self.REASONS if bits & bit],
+                "source": "NVML poller process, ~5 ms period, samples " + window,
+                "window_ms": (t1 - self.t0) * 1e3}
 
 
 class Dist(object):
