@@ -191,6 +191,20 @@ PBK_API int pbk_hamming_ratio_mutual(const uint64_t* keys, const uint64_t* rev_k
                              uint8_t* mutual_ok, uint8_t* valid,
                              pbk_stream_t stream);
 
+/* The rest of cv2.BFMatcher.knnMatch(query, train, k, mask)'s signature: any
+ * 1 <= k <= PBK_HAMMING_KNNK_MAX_K and an optional per-pair mask, in BFMatcher's order
+ * (ascending distance, ties to the lowest global train row).  Not the hot path (k = 2 without
+ * a mask goes through pbk_hamming_knn2 / pbk_hamming_tc_knn2); one CTA per query, two passes.
+ * mask   NULL, or (nq, nt) uint8 row-major on the device: pair (i, j) is a candidate iff
+ *        mask[i*nt + j] != 0 (OpenCV's convention)
+ * idx    (nq, k) int64 out: train_base + row, -1 past the neighbours found
+ * dist   (nq, k) int32 out, -1 past the neighbours found
+ * count  (nq)    int32 out: min(k, allowed rows of that query)                          */
+#define PBK_HAMMING_KNNK_MAX_K 1024
+PBK_API int pbk_hamming_knnk(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, int k,
+                     const uint8_t* mask, uint64_t train_base, int64_t* idx, int32_t* dist,
+                     int32_t* count, pbk_stream_t stream);
+
 /* Sharded matching with the exchanges FUSED into the kernels: the
  * split-merge kernel stores this rank's top-2 keys into every peer's exchange
  * buffer over NVLink peer memory, the gather kernel does the same with the

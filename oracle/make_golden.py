@@ -449,11 +449,56 @@ def g11_facade(ns):
     np.savez_compressed(os.path.join(OUT, "g11_facade.npz"), **out)
 
 
+def g12_knnk():
+    """cv2.BFMatcher.knnMatch beyond the hot path's k = 2: k in {1, 3, 7, 40}, a sparse mask (with a
+    fully masked query), compactResult, and the collection overload with per-image masks."""
+    import cv2
+    out = {}
+    rng = np.random.default_rng(12)
+    q, t = syn.low_entropy_pair(seed=12, nq=120, nt=700)
+    t[40] = t[2]
+    t[333] = q[9]
+    t[11] = q[9]
+    out["q"], out["t"] = q, t
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+
+    def rows(res, k, field):
+        a = np.full((len(res), k), -1, np.int32)
+        for i, r in enumerate(res):
+            a[i, :len(r)] = [int(getattr(m, field)) for m in r]
+        return a
+
+    for k in (1, 3, 7, 40):
+        res = bf.knnMatch(q, t, k=k)
+        out["k%d_idx" % k], out["k%d_dist" % k] = rows(res, k, "trainIdx"), rows(res, k, "distance")
+    mask = (rng.random((len(q), len(t))) < 0.01).astype(np.uint8)
+    mask[3] = 0                                   # a query with no allowed row
+    mask[5, :] = 0
+    mask[5, 600] = 1                              # exactly one allowed row
+    out["mask"] = mask
+    for k in (2, 5):
+        res = bf.knnMatch(q, t, k=k, mask=mask)
+        out["m%d_idx" % k], out["m%d_dist" % k] = rows(res, k, "trainIdx"), rows(res, k, "distance")
+        out["m%d_len" % k] = np.array([len(r) for r in res], np.int32)
+    res = bf.knnMatch(q, t, k=5, mask=mask, compactResult=True)
+    out["m5_compact_query"] = np.array([r[0].queryIdx for r in res], np.int32)
+    cuts = [0, 250, 400, 700]      # (a 1-row image next to masks makes cv2 4.13 return uninitialised imgIdx/trainIdx)
+    kfs = [t[a:b].copy() for a, b in zip(cuts[:-1], cuts[1:])]
+    bf2 = cv2.BFMatcher(cv2.NORM_HAMMING)
+    bf2.add(kfs)
+    res = bf2.knnMatch(q, k=4, masks=[mask[:, a:b].copy() for a, b in zip(cuts[:-1], cuts[1:])])
+    out["cuts"] = np.array(cuts, np.int64)
+    out["c4_img"], out["c4_idx"], out["c4_dist"] = rows(res, 4, "imgIdx"), rows(res, 4, "trainIdx"), rows(res, 4, "distance")
+    res = bf2.knnMatch(q, k=6)
+    out["c6_img"], out["c6_idx"], out["c6_dist"] = rows(res, 6, "imgIdx"), rows(res, 6, "trainIdx"), rows(res, 6, "distance")
+    np.savez_compressed(os.path.join(OUT, "g12_knnk.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ns = ref_loader.load()
-    if len(sys.argv) > 1 and sys.argv[1] in ("g10", "g11"):
-        {"g10": g10_visibility, "g11": g11_facade}[sys.argv[1]](ns)
+    if len(sys.argv) > 1 and sys.argv[1] in ("g10", "g11", "g12"):
+        {"g10": g10_visibility, "g11": g11_facade, "g12": lambda ns: g12_knnk()}[sys.argv[1]](ns)
         return
     g0_host_algebra(ns)
     g1_reconstruct(ns)
@@ -467,6 +512,7 @@ def main():
     g9_epipolar_helpers(ns)
     g10_visibility(ns)
     g11_facade(ns)
+    g12_knnk()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

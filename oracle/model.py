@@ -260,24 +260,30 @@ def hamming_matrix(q, t):
     return out
 
 
-def hamming_knn(q, t, k=2):
-    """Model of BFMatcher(NORM_HAMMING).knnMatch(q, t, k): the k smallest
+def hamming_knn(q, t, k=2, mask=None):
+    """Model of BFMatcher(NORM_HAMMING).knnMatch(q, t, k, mask): the k smallest
     distances per query, ties broken by LOWEST train index.
-    Rows are padded with idx=-1, dist=-1 when Nt < k.
+    mask (Nq, Nt), non-zero = allowed pair (OpenCV's convention); excluded
+    pairs never match.  Rows are padded with idx=-1, dist=-1 when fewer than
+    k rows are allowed (Nt < k, or masked out).
     Pinned bit-exact (indices and distances) against cv2 on tie-heavy
-    low-entropy descriptors.
+    low-entropy descriptors, for k up to 40 and with masks (golden g12).
     """
     Nq = len(q)
     idx = np.full((Nq, k), -1, np.int32)
     dist = np.full((Nq, k), -1, np.int32)
     if len(t) == 0 or Nq == 0:
         return idx, dist
+    excluded = 1 << 20                     # above any distance
     for s in range(0, Nq, 256):            # bound the distance matrix
         d = hamming_matrix(q[s:s + 256], t)
+        if mask is not None:
+            d[np.asarray(mask[s:s + 256]) == 0] = excluded
         order = np.argsort(d, axis=1, kind="stable")[:, :k]
         kk = order.shape[1]
-        idx[s:s + 256, :kk] = order
-        dist[s:s + 256, :kk] = np.take_along_axis(d, order, 1)
+        dd = np.take_along_axis(d, order, 1)
+        idx[s:s + 256, :kk] = np.where(dd < excluded, order, -1)
+        dist[s:s + 256, :kk] = np.where(dd < excluded, dd, -1)
     return idx, dist
 
 

@@ -69,6 +69,7 @@ SIGNATURES = {
     "pbk_hamming_merge_top2": (_i, [_vp, _i, _i64, _vp, _vp]),
     "pbk_hamming_gather_best": (_i, [_vp, _i64, _u64, _vp, _i64, _vp, _vp]),
     "pbk_hamming_ratio_mutual": (_i, [_vp, _vp, _i64, _d, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pbk_hamming_knnk": (_i, [_vp, _i64, _vp, _i64, _i, _vp, _u64, _vp, _vp, _vp, _vp]),
     "pbk_hamming_exchange_words": (_sz, [_i64, _i]),
     "pbk_hamming_knn2_dist": (_i, [_vp, _i64, _vp, _i64, _u64, _vp, _vp, _vp, _i, _i, _u64, _vp, _vp, _vp]),
     "pbk_hamming_gather_best_dist": (_i, [_vp, _i64, _u64, _vp, _i64, _vp, _vp, _i, _i, _u64, _vp, _vp, _vp]),

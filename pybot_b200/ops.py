@@ -514,6 +514,46 @@ def hamming_gather_best(t_dev, keys, train_base=0):
     return rows
 
 
+KNNK_MAX_K = 1024      # PBK_HAMMING_KNNK_MAX_K
+
+
+def hamming_knnk(q, t, k, mask=None, train_base=0):
+    """General-k / masked kNN in cv2.BFMatcher's order (ascending distance, ties to the lowest
+    train row): the rest of knnMatch(query, train, k, mask)'s signature; k = 2 without a mask is
+    the hot path above.  q (nq,32), t (nt,32) uint8; mask None or (nq, nt), non-zero = allowed.
+    Returns (idx (nq,k) int64, dist (nq,k) int32, count (nq,) int32): numpy, or device tensors
+    if q is a CUDA tensor; entries past count are -1."""
+    T = _ffi.require_cuda()
+    on_device = isinstance(q, T.Tensor) and q.is_cuda
+    qd, td = _desc_in(q), _desc_in(t)
+    nq, nt, k = int(qd.shape[0]), int(td.shape[0]), int(k)
+    if k < 1:
+        raise ValueError("k must be >= 1")
+    md = None
+    if mask is not None:
+        if not isinstance(mask, T.Tensor):
+            mask = np.ascontiguousarray(np.asarray(mask))
+            if mask.dtype == np.bool_:
+                mask = mask.view(np.uint8)
+        elif mask.dtype == T.bool:
+            mask = mask.view(T.uint8)
+        if tuple(mask.shape) != (nq, nt):
+            raise ValueError("mask must be (%d, %d), got %s" % (nq, nt, tuple(mask.shape)))
+        if (mask.dtype != T.uint8) if isinstance(mask, T.Tensor) else (mask.dtype != np.uint8):
+            raise TypeError("mask must be uint8 or bool (OpenCV: CV_8UC1)")
+        md = _ffi.to_device(mask)[0].contiguous()
+    m = max(nq, 1)
+    idx = T.empty((m, k), dtype=T.int64, device=qd.device)[:nq]
+    dist = T.empty((m, k), dtype=T.int32, device=qd.device)[:nq]
+    count = T.empty((m,), dtype=T.int32, device=qd.device)[:nq]
+    _ffi.check(_ffi.lib().pbk_hamming_knnk(
+        _ffi.ptr(qd), nq, _ffi.ptr(td) if nt else None, nt, k, _ffi.ptr(md) if md is not None and nq * nt else None,
+        int(train_base), _ffi.ptr(idx), _ffi.ptr(dist), _ffi.ptr(count), _ffi.stream_ptr()))
+    if on_device:
+        return idx, dist, count
+    return _ffi.to_host(idx), _ffi.to_host(dist), _ffi.to_host(count)
+
+
 class MatchResult(tuple):
     """(idx (nq,2) int64, dist (nq,2) int32, ratio_ok, mutual_ok, valid) as device tensors that are
     views of ONE buffer, so the whole result crosses PCIe in one copy (`to_host`) instead of five

@@ -289,22 +289,70 @@ class BFMatcher(object):
         return dict(idx=idx, imgIdx=img, trainIdx=tr, dist=dist, ratio_ok=r_ok, mutual_ok=m_ok, valid=valid)
 
     # -- OpenCV API --------------------------------------------------------
-    def knnMatch(self, queryDescriptors, trainDescriptors=None, k=2, mask=None, compactResult=False):
-        if mask is not None:
-            raise NotImplementedError("masks are not supported")
-        if k not in (1, 2):
-            raise NotImplementedError("k must be 1 or 2")
+    def knnMatch(self, queryDescriptors, trainDescriptors=None, k=2, mask=None, compactResult=False, masks=None):
+        """cv2's two overloads in one: knnMatch(query, train, k[, mask[, compactResult]]) against one
+        train matrix and knnMatch(query, k[, masks[, compactResult]]) against the added collection
+        (an integer in second position is k, as in OpenCV).  k = 1 / 2 without a mask is the hot
+        path; any other k (<= ops.KNNK_MAX_K) or a mask goes through pbk_hamming_knnk, same order
+        (ascending distance, ties to the lowest (imgIdx, trainIdx)); masked-out pairs never match
+        and a query may come back with fewer than k rows - dropped when compactResult is set.
+        mask: (nq, nt) uint8 / bool, non-zero = allowed; for the collection either `masks`, a list
+        with one (nq, n_i) mask (or None = all allowed) per added image, or one (nq, total) matrix."""
+        if isinstance(trainDescriptors, (int, np.integer)) and not isinstance(trainDescriptors, bool):
+            trainDescriptors, k = None, int(trainDescriptors)        # the collection overload: (query, k, ...)
+        if masks is not None:
+            if mask is not None:
+                raise ValueError("give mask or masks, not both")
+            mask = masks
+        k = int(k)
+        if k < 1:
+            raise ValueError("k must be >= 1 (OpenCV asserts knn > 0)")
         if self.crossCheck and k != 1:
             raise ValueError("crossCheck=True needs k == 1 (OpenCV asserts the same)")
-        r = self.knn_arrays(queryDescriptors, trainDescriptors, mutual=self.crossCheck)
-        counts = (r["idx"][:, :k] >= 0).sum(1)              # fewer than k rows when the train set is smaller
-        if self.crossCheck:
-            counts = np.where(r["mutual_ok"], counts, 0)
+        if mask is None and k <= 2:
+            r = self.knn_arrays(queryDescriptors, trainDescriptors, mutual=self.crossCheck)
+            counts = (r["idx"][:, :k] >= 0).sum(1)              # fewer than k rows when the train set is smaller
+            if self.crossCheck:
+                counts = np.where(r["mutual_ok"], counts, 0)
+        else:
+            r, counts = self._knn_general(queryDescriptors, trainDescriptors, k, mask)
         rows = np.arange(len(counts))
         if compactResult:
             rows = rows[counts > 0]
             counts = counts[counts > 0]
         return KnnMatches(rows, r["trainIdx"], r["imgIdx"], r["dist"], counts, arrays=r)
+
+    def _knn_general(self, queryDescriptors, trainDescriptors, k, mask):
+        """any k, optional mask: one launch of pbk_hamming_knnk over the flat collection."""
+        if self.crossCheck:
+            raise NotImplementedError("crossCheck together with a mask is not implemented")
+        if trainDescriptors is None and self.group is not None:
+            raise NotImplementedError("the sharded collection answers k <= 2 without a mask")
+        if trainDescriptors is not None:
+            db = KeyframeDatabase()
+            db.add([trainDescriptors])
+        else:
+            db = self.db
+        offsets = db.offsets
+        nq, total = int(np.shape(queryDescriptors)[0]), int(offsets[-1])
+        if isinstance(mask, (list, tuple)):
+            if len(mask) != len(offsets) - 1:
+                raise ValueError("masks must hold one entry per added image (%d), got %d" % (len(offsets) - 1, len(mask)))
+            full = np.ones((nq, total), np.uint8)
+            for i, m in enumerate(mask):
+                if m is None:
+                    continue
+                m = np.asarray(_np(m))
+                lo, hi = int(offsets[i]), int(offsets[i + 1])
+                if m.shape != (nq, hi - lo):
+                    raise ValueError("masks[%d] must be (%d, %d), got %s" % (i, nq, hi - lo, m.shape))
+                full[:, lo:hi] = m != 0
+            mask = full
+        idx, dist, counts = (np.asarray(_np(x)) for x in ops.hamming_knnk(queryDescriptors, db.flat, k, mask))
+        img, tr = _split_global(offsets, np.maximum(idx, 0))
+        img[idx < 0] = -1
+        tr[idx < 0] = -1
+        return dict(idx=idx, imgIdx=img, trainIdx=tr, dist=dist), counts
 
     def match(self, queryDescriptors, trainDescriptors=None, mask=None):
         return [row[0] for row in self.knnMatch(queryDescriptors, trainDescriptors, k=1, mask=mask)

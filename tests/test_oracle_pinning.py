@@ -122,6 +122,34 @@ def test_hamming_models_vs_cv2_golden(golden_dir):
     assert np.array_equal(pidx, want) and np.array_equal(pimg, g["kf_img"])
 
 
+def test_hamming_model_general_k_and_mask_vs_cv2_golden(golden_dir):
+    """knnMatch beyond k = 2 (golden g12, generated by cv2.BFMatcher): any k, masks, and live cv2
+    on a second seeded case."""
+    g = np.load(golden_dir + "/g12_knnk.npz")
+    q, t, mask = g["q"], g["t"], g["mask"]
+    for k in (1, 3, 7, 40):
+        idx, dist = model.hamming_knn(q, t, k)
+        assert np.array_equal(idx, g["k%d_idx" % k]) and np.array_equal(dist, g["k%d_dist" % k])
+    for k in (2, 5):
+        idx, dist = model.hamming_knn(q, t, k, mask=mask)
+        assert np.array_equal(idx, g["m%d_idx" % k]) and np.array_equal(dist, g["m%d_dist" % k])
+        assert np.array_equal((idx >= 0).sum(1), g["m%d_len" % k])
+    assert g["m5_len"][3] == 0 and g["m5_len"][5] == 1
+    assert np.array_equal(np.nonzero(g["m5_len"])[0], g["m5_compact_query"])
+    cuts = g["cuts"]
+    for k, name, m in ((4, "c4", mask), (6, "c6", None)):
+        idx, dist = model.hamming_knn(q, t, k, mask=m)
+        want = np.where(g[name + "_idx"] >= 0, cuts[np.maximum(g[name + "_img"], 0)] + g[name + "_idx"], -1)
+        assert np.array_equal(idx, want) and np.array_equal(dist, g[name + "_dist"])
+    q2, t2 = syn.low_entropy_pair(seed=99, nq=40, nt=300)
+    m2 = (np.random.default_rng(5).random((40, 300)) < 0.1).astype(np.uint8)
+    res = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q2, t2, k=9, mask=m2)
+    idx, dist = model.hamming_knn(q2, t2, 9, mask=m2)
+    for i, r in enumerate(res):
+        assert [m.trainIdx for m in r] == idx[i][idx[i] >= 0].tolist()
+        assert [int(m.distance) for m in r] == dist[i][dist[i] >= 0].tolist()
+
+
 def test_ratio_mutual_port_equals_model():
     q, t = syn.orb_pair(seed=5, nq=400, nt=700)
     a = model.ratio_mutual(q, t, 0.75)
