@@ -1252,6 +1252,36 @@ def run_next_rows(D, args):
         "algorithmic": "32 B in + 24 B out per point; compute-bound (fp64 Jacobi sweeps)", "l2": L2_NOTE,
         "cpu_baseline": {"value": len(a) / cpu_dt / 1e6, "unit": "Mpts/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": "cv2.triangulatePoints + dehomogenisation (camera_utils.py:108-116) on 200k pairs"}}
+
+    # knnMatch beyond the hot path: k = 8, with and without a per-pair mask (pbk_hamming_knnk)
+    nqk, ntk, kk = 2000, 20_000, 8
+    qk, tk = syn.orb_pair(seed=1007, nq=nqk, nt=ntk)
+    mk8 = (np.random.default_rng(1007).random((nqk, ntk)) < 0.25).astype(np.uint8)
+    qd, td, md = (torch.from_numpy(x).cuda() for x in (qk, tk, mk8))
+    ms5, _ = timed_steps(D, lambda rec: ops.hamming_knnk(qd, td, kk), args.steps, args.warmup, flush)
+    ms6, _ = timed_steps(D, lambda rec: ops.hamming_knnk(qd, td, kk, md), args.steps, args.warmup, flush)
+    got = [x.cpu().numpy() for x in ops.hamming_knnk(qd, td, kk, md)]
+    entry = {
+        "workload": "BFMatcher.knnMatch(k=%d): %d queries x %d rows, without / with a 25 %% per-pair mask" % (kk, nqk, ntk),
+        "Gpairs_per_s": nqk * ntk * args.steps / (ms5 * 1e-3) / 1e9, "ms": ms5 / args.steps,
+        "masked_Gpairs_per_s": nqk * ntk * args.steps / (ms6 * 1e-3) / 1e9, "masked_ms": ms6 / args.steps,
+        "algorithmic": "two passes of 8 POPC per pair (histogram -> threshold, then ordered collection); not the "
+                       "hot path: k = 2 without a mask runs on the tensor-core scan", "l2": L2_NOTE}
+    try:
+        import cv2
+        cv2.setNumThreads(os.cpu_count())
+        t0 = time.perf_counter()
+        res = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(qk, tk, k=kk, mask=mk8)
+        cpu_dt = time.perf_counter() - t0
+        ref_idx = np.array([[m.trainIdx for m in r] + [-1] * (kk - len(r)) for r in res], np.int64)
+        ref_dist = np.array([[int(m.distance) for m in r] + [-1] * (kk - len(r)) for r in res], np.int32)
+        entry["parity"] = {"bit_exact": bool(np.array_equal(got[0], ref_idx) and np.array_equal(got[1], ref_dist)),
+                           "reference": "cv2.BFMatcher.knnMatch(q, t, k=%d, mask) on the same inputs" % kk}
+        entry["cpu_baseline"] = {"value": nqk * ntk / cpu_dt / 1e9, "unit": "Gpairs/s", "cores": os.cpu_count(),
+                                 "kind": "port", "sample": "the masked call above, whole workload, once"}
+    except ImportError:
+        entry["parity"] = {"bit_exact": None, "reference": "cv2 not importable on this box"}
+    out["knnMatch_k8"] = entry
     return out
 
 
