@@ -100,6 +100,23 @@ def test_sass_of_the_tensor_core_matchers():
     assert i8[0].count("UTCIMMA") == 8 and "LDTM" in i8[0] and "VIMNMX.S16x2" in i8[0]
 
 
+def test_knnk_argument_checks_are_host_side():
+    """pbk_hamming_knnk validates its arguments before it touches the device: the error codes and
+    messages of include/pybot_b200.h, checked here without a GPU."""
+    import ctypes
+    from pybot_b200 import _ffi
+    L = _ffi.lib()
+    nul = ctypes.c_void_p(0)
+    call = lambda nq, nt, k: L.pbk_hamming_knnk(nul, nq, nul, nt, k, nul, 0, nul, nul, nul, nul)   # noqa: E731
+    assert call(0, 0, 3) == 0                                       # no queries: nothing to do
+    assert call(4, 4, 0) == -1 and b"k must be" in L.pbk_last_error_string()          # PBK_EINVAL
+    assert call(4, 4, 1025) == -4 and b"1024" in L.pbk_last_error_string()            # PBK_EUNSUPPORTED
+    assert call(-1, 4, 2) == -1 and call(4, 1 << 32, 2) == -1
+    assert call(4, 4, 2) == -1 and b"NULL" in L.pbk_last_error_string()
+    with pytest.raises(NotImplementedError):
+        _ffi.check(call(4, 4, 1025))
+
+
 def test_compute_without_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():
@@ -113,6 +130,9 @@ def test_compute_without_gpu_fails_loudly():
         StereoCamera.simulate().reconstruct(np.ones((4, 4), np.float32))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         BFMatcher().knnMatch(np.zeros((2, 32), np.uint8), np.zeros((2, 32), np.uint8), k=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        BFMatcher().knnMatch(np.zeros((2, 32), np.uint8), np.zeros((2, 32), np.uint8), k=5,
+                             mask=np.ones((2, 2), np.uint8))
 
 
 def test_missing_library_fails_loudly(monkeypatch):
