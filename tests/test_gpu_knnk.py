@@ -70,7 +70,8 @@ def test_collection_overload_with_masks(g12):
 
 @pytest.mark.parametrize("nq,nt,k,density", [
     (1, 1, 1, None), (3, 5, 8, None), (70, 255, 3, None), (70, 256, 256, None), (33, 257, 31, 0.5),
-    (257, 1000, 1024, None), (64, 5000, 100, 0.02), (9, 70001, 17, None), (300, 4099, 5, 0.001)])
+    (257, 1000, 1024, None), (64, 5000, 100, 0.02), (9, 70001, 17, None), (300, 4099, 5, 0.001),
+    (1500, 300, 4, 0.3)])      # more queries than resident CTAs: the per-CTA query loop
 def test_seeded_shapes_against_model(nq, nt, k, density):
     """tie-heavy descriptors around the 256-row chunk boundaries of the ordered tie selection,
     k above / below the row count, k at the supported maximum, sparse and dense masks."""
