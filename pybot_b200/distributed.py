@@ -58,6 +58,10 @@ class _CudaMatchKernels(object):
         from . import ops
         return ops.hamming_ratio_mutual(keys, rev, ratio)
 
+    def knnk(self, q, t, k, mask, train_base):
+        from . import ops
+        return ops.hamming_knnk(q, t, k, mask, train_base)
+
 
 class PeerKeyExchange(object):
     """Peer-mapped exchange buffer of the fused matcher exchanges
@@ -235,6 +239,45 @@ class ShardedKeyframeMatcher(object):
                 self.dist.all_reduce(rows, op=self.dist.ReduceOp.SUM, group=self.group)
             rev = self.kernels.knn2(rows, q, 0)
         return self.kernels.ratio_mutual(keys, rev, ratio)
+
+    def knnk_local_keys(self, q, k, mask=None):
+        """(nq, k) int64 keys (distance << 32 | global row; INT64_MAX = none) of this shard's k best
+        rows per query.  mask: (nq, rows of the WHOLE database) or None; the shard reads its own
+        column range."""
+        T = _ffi.torch()
+        nl = int(self.shard.shape[0])
+        if mask is not None:
+            mask = mask[:, self.shard_base:self.shard_base + nl]
+            mask = mask.contiguous() if isinstance(mask, T.Tensor) else np.ascontiguousarray(mask)
+        idx, dist, _ = self.kernels.knnk(q, self.shard, int(k), mask, self.shard_base)
+        idx, dist = T.as_tensor(idx), T.as_tensor(dist)
+        return T.where(idx >= 0, (dist.to(T.int64) << 32) | idx, T.full_like(idx, T.iinfo(T.int64).max))
+
+    @staticmethod
+    def knnk_merge(keys, k):
+        """keys (nq, parts * k) -> (idx (nq,k) global rows, dist (nq,k) int32, count (nq,) int32):
+        the k smallest by (distance, global row) - BFMatcher's order over the whole collection."""
+        T = _ffi.torch()
+        keys = T.sort(keys, dim=1).values[:, :int(k)]
+        found = keys != T.iinfo(T.int64).max
+        return (T.where(found, keys & 0xFFFFFFFF, T.full_like(keys, -1)),
+                T.where(found, keys >> 32, T.full_like(keys, -1)).to(T.int32),
+                found.sum(1).to(T.int32))
+
+    def knnk(self, q, k, mask=None):
+        """knnMatch's general form over the sharded database: any k (<= ops.KNNK_MAX_K), optional
+        per-pair mask (every rank passes the same (nq, total rows) matrix).  Returns (idx, dist,
+        count), identical on every rank and equal to the single-GPU call: each rank's k best
+        (pbk_hamming_knnk), ONE all-gather of the (nq, k) keys, the k smallest of the world x k
+        candidates per query.  Not the hot path: k = 2 without a mask is match()."""
+        T = _ffi.torch()
+        nq, k = int(q.shape[0]), int(k)
+        keys = self.knnk_local_keys(q, k, mask)
+        if self.world > 1:
+            gathered = T.empty((self.world * nq, k), dtype=T.int64, device=keys.device)
+            self.dist.all_gather_into_tensor(gathered, keys.contiguous(), group=self.group)
+            keys = gathered.view(self.world, nq, k).permute(1, 0, 2).reshape(nq, self.world * k)
+        return self.knnk_merge(keys, k)
 
     def match_host(self, q, ratio=0.75, mutual=True):
         """match() with numpy results; raises RuntimeError if a peer timed out in this call."""

@@ -326,14 +326,17 @@ class BFMatcher(object):
         """any k, optional mask: one launch of pbk_hamming_knnk over the flat collection."""
         if self.crossCheck:
             raise NotImplementedError("crossCheck together with a mask is not implemented")
-        if trainDescriptors is None and self.group is not None:
-            raise NotImplementedError("the sharded collection answers k <= 2 without a mask")
-        if trainDescriptors is not None:
+        sharded = trainDescriptors is None and self.group is not None
+        if sharded:
+            self.train()
+            offsets = self._sharded[1]
+        elif trainDescriptors is not None:
             db = KeyframeDatabase()
             db.add([trainDescriptors])
+            offsets = db.offsets
         else:
             db = self.db
-        offsets = db.offsets
+            offsets = db.offsets
         nq, total = int(np.shape(queryDescriptors)[0]), int(offsets[-1])
         if isinstance(mask, (list, tuple)):
             if len(mask) != len(offsets) - 1:
@@ -348,7 +351,11 @@ class BFMatcher(object):
                     raise ValueError("masks[%d] must be (%d, %d), got %s" % (i, nq, hi - lo, m.shape))
                 full[:, lo:hi] = m != 0
             mask = full
-        idx, dist, counts = (np.asarray(_np(x)) for x in ops.hamming_knnk(queryDescriptors, db.flat, k, mask))
+        if sharded:       # every rank: its shard's k best, one all-gather, the k smallest by (distance, row)
+            res = self._sharded[0].knnk(ops._desc_in(queryDescriptors), k, mask)
+        else:
+            res = ops.hamming_knnk(queryDescriptors, db.flat, k, mask)
+        idx, dist, counts = (np.asarray(_np(x)) for x in res)
         img, tr = _split_global(offsets, np.maximum(idx, 0))
         img[idx < 0] = -1
         tr[idx < 0] = -1

@@ -59,6 +59,11 @@ def main():
     assert got_rows == one.knnMatch(q, k=2), "sharded BFMatcher.knnMatch differs from the single-GPU facade"
     assert (got_rows[9][0].imgIdx, got_rows[9][0].trainIdx, got_rows[9][1].imgIdx, got_rows[9][1].trainIdx) == (0, 123, 40, 123)
 
+    # ... and the rest of knnMatch's signature over the sharded collection (k > 2, masks)
+    kmask = (np.random.default_rng(2).random((len(q), len(db))) < 0.001).astype(np.uint8)
+    assert bf.knnMatch(q, k=5) == one.knnMatch(q, k=5), "sharded knnMatch(k=5) differs from the single-GPU facade"
+    assert bf.knnMatch(q, k=3, mask=kmask) == one.knnMatch(q, k=3, mask=kmask), "sharded masked knnMatch differs"
+
     prob = syn.c4_problem(n_cams=50, n_points=20_000)
     sb = ShardedBA(*prob)                                 # fused peer-memory exchange
     assert sb.exchange is not None

@@ -46,6 +46,10 @@ class OracleMatchKernels(object):
         rows[own] = t.numpy()[g[own]]
         return torch.from_numpy(rows)
 
+    def knnk(self, q, t, k, mask, train_base):
+        idx, d = model.hamming_knn(np.asarray(q), np.asarray(t), k, mask=None if mask is None else np.asarray(mask))
+        return (np.where(idx >= 0, idx.astype(np.int64) + int(train_base), -1), d, (idx >= 0).sum(1).astype(np.int32))
+
     def ratio_mutual(self, keys, rev, ratio):
         k = keys.numpy().view(np.uint64)
         has = k != KEY_NONE
@@ -120,6 +124,43 @@ def test_sharded_keyframe_matching_equals_unsharded_oracle():
         for a, b in zip(rank_out, want):
             assert np.array_equal(np.asarray(a).astype(np.int64), np.asarray(b).astype(np.int64))
     assert want[0][5, 0] == 40 and want[0][5, 1] == 1900 and want[1][5, 1] == 0   # lowest global row first
+
+
+def _knnk_case():
+    per_kf, nkf = 120, 5                                   # 5 keyframes: uneven shards (3 + 2)
+    q, db = syn.low_entropy_pair(seed=31, nq=60, nt=per_kf * nkf)     # tie-heavy: the merge order matters
+    db[400] = db[7]                                        # duplicates across the shard boundary
+    q[3] = db[7]
+    mask = (np.random.default_rng(8).random((len(q), len(db))) < 0.05).astype(np.uint8)
+    mask[11] = 0                                           # a query with no allowed row anywhere
+    mask[12] = 0
+    mask[12, 599] = 1                                      # ... and one whose only row is on the last rank
+    return per_kf, nkf, q, db, mask
+
+
+def _knnk_job(rank, world):
+    per_kf, nkf, q, db, mask = _knnk_case()
+    lo, hi = shard_range(nkf, rank, world)
+    m = ShardedKeyframeMatcher(torch.from_numpy(db[lo * per_kf:hi * per_kf].copy()), lo * per_kf,
+                               kernels=OracleMatchKernels())
+    out = []
+    for k, msk in ((1, None), (5, None), (9, mask), (700, None)):
+        out.append([np.asarray(x) for x in m.knnk(torch.from_numpy(q), k, msk)])
+    return out
+
+
+def test_sharded_general_k_and_mask_equals_unsharded_oracle():
+    """BFMatcher(group=...).knnMatch(k > 2 / mask): per-rank k best + all-gather + (distance, row)
+    merge equals the unsharded model, ties across the shard boundary included."""
+    per_kf, nkf, q, db, mask = _knnk_case()
+    got = _run(_knnk_job)
+    for i, (k, msk) in enumerate(((1, None), (5, None), (9, mask), (700, None))):
+        idx, d = model.hamming_knn(q, db, k, mask=msk)
+        for rank_out in got:
+            assert np.array_equal(rank_out[i][0], idx) and np.array_equal(rank_out[i][1], d)
+            assert np.array_equal(rank_out[i][2], (idx >= 0).sum(1))
+    idx5 = model.hamming_knn(q, db, 5)[0]
+    assert idx5[3, 0] == 7 and idx5[3, 1] == 400           # the duplicate pair, lowest global row first
 
 
 def _ba_job(rank, world):

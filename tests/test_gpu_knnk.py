@@ -128,3 +128,29 @@ def test_device_tensors_and_errors():
         BFMatcher(crossCheck=True).knnMatch(q, t, k=3)
     with pytest.raises(ValueError):
         BFMatcher().knnMatch(q, t, k=0)
+
+
+def test_sharded_keys_merge_equals_whole_database():
+    """the sharded form (BFMatcher(group=...).knnMatch with k > 2 / a mask): per-shard k best as
+    (distance, global row) keys, merged - here three shards of one GPU, the all-gather replaced by
+    a concatenation - equals the single call over the whole database, ties across shards included."""
+    import torch
+    from pybot_b200 import ops
+    from pybot_b200.distributed import ShardedKeyframeMatcher
+    q, t = syn.low_entropy_pair(seed=77, nq=150, nt=3000)
+    t[2500] = t[9]
+    q[4] = t[9]
+    mask = (np.random.default_rng(3).random((150, 3000)) < 0.03).astype(np.uint8)
+    mask[7] = 0
+    qd = torch.from_numpy(q).cuda()
+    cuts = [0, 1100, 1101, 3000]
+    shards = [ShardedKeyframeMatcher(torch.from_numpy(t[a:b]).cuda(), a) for a, b in zip(cuts[:-1], cuts[1:])]
+    for k, m in ((6, None), (6, mask), (64, torch.from_numpy(mask).cuda())):
+        keys = torch.cat([s.knnk_local_keys(qd, k, m) for s in shards], dim=1)
+        idx, dist, count = (x.cpu().numpy() for x in ShardedKeyframeMatcher.knnk_merge(keys, k))
+        mm = None if m is None else mask
+        ridx, rdist = model.hamming_knn(q, t, k, mask=mm)
+        assert np.array_equal(idx, ridx) and np.array_equal(dist, rdist) and np.array_equal(count, (ridx >= 0).sum(1))
+        one = ShardedKeyframeMatcher(torch.from_numpy(t).cuda(), 0).knnk(qd, k, m)     # world 1: same call path
+        assert np.array_equal(one[0].cpu().numpy(), ridx)
+    assert model.hamming_knn(q, t, 2)[0][4].tolist() == [9, 2500]      # the duplicate pair sits in two shards
