@@ -293,7 +293,8 @@ class BFMatcher(object):
         """cv2's two overloads in one: knnMatch(query, train, k[, mask[, compactResult]]) against one
         train matrix and knnMatch(query, k[, masks[, compactResult]]) against the added collection
         (an integer in second position is k, as in OpenCV).  k = 1 / 2 without a mask is the hot
-        path; any other k (<= ops.KNNK_MAX_K) or a mask goes through pbk_hamming_knnk, same order
+        path; any other k (<= ops.KNNK_MAX_K) or a mask goes through pbk_hamming_knnk (sharded
+        collections: per-shard k best + one all-gather + merge), same order
         (ascending distance, ties to the lowest (imgIdx, trainIdx)); masked-out pairs never match
         and a query may come back with fewer than k rows - dropped when compactResult is set.
         mask: (nq, nt) uint8 / bool, non-zero = allowed; for the collection either `masks`, a list
