@@ -51,6 +51,27 @@ def test_hamming_knn_models_equal_bfmatcher(seed, nq, nt, nbytes):
 
 
 @settings(**_SET)
+@given(seed=st.integers(0, 2**31 - 1), nq=st.integers(1, 40), nt=st.integers(1, 300), nbytes=st.integers(1, 32),
+       k=st.integers(1, 40), density=st.sampled_from([None, 0.02, 0.3, 1.0]))
+def test_hamming_knn_model_general_k_and_mask_equals_bfmatcher(seed, nq, nt, nbytes, k, density):
+    """any k, optional per-pair mask (knnMatch's full signature): rows shorter than k when fewer
+    rows are allowed, empty when none is; order and ties as cv2.BFMatcher."""
+    rng = np.random.default_rng(seed)
+    q = np.zeros((nq, 32), np.uint8)
+    t = np.zeros((nt, 32), np.uint8)
+    q[:, :nbytes] = rng.integers(0, 4, (nq, nbytes))
+    t[:, :nbytes] = rng.integers(0, 4, (nt, nbytes))
+    mask = None if density is None else (rng.random((nq, nt)) < density).astype(np.uint8)
+    res = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=k, mask=mask)
+    idx, dist = model.hamming_knn(q, t, k, mask=mask)
+    assert len(res) == nq
+    for i, r in enumerate(res):
+        assert [m.trainIdx for m in r] == idx[i][idx[i] >= 0].tolist()
+        assert [int(m.distance) for m in r] == dist[i][dist[i] >= 0].tolist()
+        assert (idx[i] >= 0).sum() == (dist[i] >= 0).sum() == min(k, nt if mask is None else int(mask[i].sum()))
+
+
+@settings(**_SET)
 @given(seed=st.integers(0, 2**31 - 1), h=st.integers(1, 24), w=st.integers(1, 40),
        dt=st.sampled_from([np.uint8, np.int16, np.int32, np.float32]))
 def test_reproject_model_equals_cv2(seed, h, w, dt):
