@@ -141,6 +141,10 @@ def test_hamming_model_general_k_and_mask_vs_cv2_golden(golden_dir):
         idx, dist = model.hamming_knn(q, t, k, mask=m)
         want = np.where(g[name + "_idx"] >= 0, cuts[np.maximum(g[name + "_img"], 0)] + g[name + "_idx"], -1)
         assert np.array_equal(idx, want) and np.array_equal(dist, g[name + "_dist"])
+    for k, m in ((1, None), (7, None), (40, None), (5, mask), (900, None), (900, mask)):   # the C restatement
+        idx, dist = model.hamming_knn(q, t, k, mask=m)
+        cidx, cdist, ccount = c_oracle.hamming_knnk(q, t, k, m)
+        assert np.array_equal(cidx, idx) and np.array_equal(cdist, dist) and np.array_equal(ccount, (idx >= 0).sum(1))
     q2, t2 = syn.low_entropy_pair(seed=99, nq=40, nt=300)
     m2 = (np.random.default_rng(5).random((40, 300)) < 0.1).astype(np.uint8)
     res = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q2, t2, k=9, mask=m2)

@@ -69,6 +69,8 @@ def test_hamming_knn_model_general_k_and_mask_equals_bfmatcher(seed, nq, nt, nby
         assert [m.trainIdx for m in r] == idx[i][idx[i] >= 0].tolist()
         assert [int(m.distance) for m in r] == dist[i][dist[i] >= 0].tolist()
         assert (idx[i] >= 0).sum() == (dist[i] >= 0).sum() == min(k, nt if mask is None else int(mask[i].sum()))
+    cidx, cdist, ccount = c_oracle.hamming_knnk(q, t, k, mask)                  # the C restatement too
+    assert np.array_equal(cidx, idx) and np.array_equal(cdist, dist) and np.array_equal(ccount, (idx >= 0).sum(1))
 
 
 @settings(**_SET)
